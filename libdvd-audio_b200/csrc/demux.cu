@@ -1,0 +1,266 @@
+// demux.cu — AOB sector scan, audio packet table, elementary-stream gather and
+// PCM unpack kernels.
+//
+// Replaces (reference tree):
+//   src/packet.c:137-188  read_pack_header          -> pack_header_size()
+//   src/packet.c:60-135   packet_reader_next_packet / _next_audio_packet
+//                                                   -> k_sector_count + k_packet_fill
+//   src/dvd-audio.c:1238-1248 read_audio_packet_header -> k_packet_fill
+//   src/pcm.c:79-96       dvda_pcmdecoder_decode_params -> k_packet_fill
+//   src/bitstream.c:2259,2442 queue enqueue / push copies -> k_es_gather
+//   src/pcm.c:98-169      dvda_pcmdecoder_decode_packet + src/dvd-audio.c:781-792
+//                         interleave                 -> k_pcm_unpack
+//
+// The reference pulls one sector at a time through a byte queue; here every
+// sector is looked at by its own thread, the audio packets found are numbered by
+// a prefix sum, and payload bytes are moved once, coalesced, into one contiguous
+// elementary stream.
+#include "common.cuh"
+#include "kernels.cuh"
+
+// ---------------------------------------------------------------- sector scan
+
+// size of the pack header incl. stuffing, 0 if the sector does not start with a
+// valid one (sync 0x000001BA, marker bits 01,1,1,1,1,11)
+__device__ __forceinline__ uint32_t pack_header_size(const uint8_t *s)
+{
+    // the first 16 bytes of a sector are 16-byte aligned: one vector load
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(s));
+    if (v.x != 0xBA010000u) return 0;                 // bytes 00 00 01 BA
+    const uint32_t b4 = v.y & 0xFF, b6 = (v.y >> 16) & 0xFF;
+    const uint32_t b8 = v.z & 0xFF, b9 = (v.z >> 8) & 0xFF;
+    const uint32_t b12 = v.w & 0xFF, b13 = (v.w >> 8) & 0xFF;
+    if ((b4 >> 6) != 1 || !((b4 >> 2) & 1) || !((b6 >> 2) & 1) || !((b8 >> 2) & 1) ||
+        !(b9 & 1) || (b12 & 3) != 3)
+        return 0;
+    return 14u + (b13 & 7u);
+}
+
+struct PacketWalk {
+    const uint8_t *sec;
+    uint32_t off;
+    bool bad;
+};
+
+// advances to the next packet of the sector; false when the sector is used up
+// (or the chain is broken: w.bad)
+__device__ __forceinline__ bool next_packet(PacketWalk &w, uint32_t &id, uint32_t &payload, uint32_t &len)
+{
+    if (w.off == DVDA_SECTOR) return false;
+    if (w.off + 6 > DVDA_SECTOR) { w.bad = true; return false; }
+    const uint8_t *h = w.sec + w.off;
+    if (ld_u8(h) != 0 || ld_u8(h + 1) != 0 || ld_u8(h + 2) != 1) { w.bad = true; return false; }
+    id = ld_u8(h + 3);
+    len = ld_be16(h + 4);
+    if (w.off + 6 + len > DVDA_SECTOR) { w.bad = true; return false; }
+    payload = w.off + 6;
+    w.off += 6 + len;
+    return true;
+}
+
+// one thread per sector: how many audio packets, and is the packet chain intact
+__global__ void k_sector_count(const uint8_t *__restrict__ sectors, uint32_t n_sectors,
+                               uint32_t *__restrict__ sec_cnt, uint32_t *__restrict__ sec_bad)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sectors) return;
+    PacketWalk w = {sectors + (uint64_t)s * DVDA_SECTOR, 0, false};
+    w.off = pack_header_size(w.sec);
+    uint32_t cnt = 0;
+    if (!w.off) {
+        w.bad = true;
+    } else {
+        uint32_t id, payload, len;
+        while (next_packet(w, id, payload, len)) cnt += (id == 0xBD);
+    }
+    sec_cnt[s] = cnt;
+    sec_bad[s] = w.bad ? 1u : 0u;
+}
+
+__device__ __forceinline__ uint32_t pcm_bytes_per_sample(uint32_t g0_bps) { return g0_bps == 0 ? 2u : g0_bps == 2 ? 3u : 0u; }
+__device__ __forceinline__ uint32_t channels_of(uint32_t a)
+{
+    // channel count per assignment (reference dvd-audio.c:1459-1496), 3 bits each
+    const unsigned long long packed =
+        (1ull << 0) | (2ull << 3) | (3ull << 6) | (4ull << 9) | (3ull << 12) | (4ull << 15) | (5ull << 18) |
+        (3ull << 21) | (4ull << 24) | (5ull << 27) | (4ull << 30) | (5ull << 33) | (6ull << 36) | (4ull << 39) |
+        (5ull << 42) | (4ull << 45) | (5ull << 48) | (6ull << 51) | (5ull << 54) | (5ull << 57) | (6ull << 60);
+    return a <= 20 ? (uint32_t)((packed >> (3 * a)) & 7) : 0;
+}
+
+// one thread per sector: rows of the packet table
+__global__ void k_packet_fill(const uint8_t *__restrict__ sectors, uint32_t n_sectors,
+                              const uint32_t *__restrict__ sec_base, PacketTable pt)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sectors) return;
+    PacketWalk w = {sectors + (uint64_t)s * DVDA_SECTOR, 0, false};
+    w.off = pack_header_size(w.sec);
+    if (!w.off) return;
+    uint32_t i = sec_base[s];
+    uint32_t id, payload, len;
+    while (next_packet(w, id, payload, len)) {
+        if (id != 0xBD) continue;
+        // "16p 8u" pad_1 skip "8u 8p 8p 8u"
+        uint32_t codec = 0xFF, pad2 = 0, hdr = 0;
+        const uint8_t *p = w.sec + payload;
+        if (len >= 3) {
+            const uint32_t pad1 = ld_u8(p + 2);
+            if (len >= 3 + pad1 + 4) {
+                codec = ld_u8(p + 3 + pad1);
+                pad2 = ld_u8(p + 6 + pad1);
+                hdr = 7 + pad1;
+            }
+        }
+        uint32_t rest = len - hdr;                   // bytes behind the pad_2_size byte
+        uint32_t mlp_len = 0, pcm_frames = 0, params = 0xFFFFFFFFu;
+        if (codec == CODEC_MLP) {
+            if (pad2 <= rest) mlp_len = rest - pad2; else codec = 0xFF;
+        } else if (codec == CODEC_PCM) {
+            if (pad2 >= 9 && pad2 <= rest) {
+                const uint8_t *q = p + hdr;           // 9 parameter bytes
+                const uint32_t b3 = ld_u8(q + 3), b4 = ld_u8(q + 4), asg = ld_u8(q + 6);
+                params = (b3 << 16) | (b4 << 8) | asg;
+                const uint32_t chunk = pcm_bytes_per_sample(b3 >> 4) * channels_of(asg) * 2;
+                if (chunk) pcm_frames = ((rest - pad2) / chunk) * 2;
+            } else codec = 0xFF;
+        } else {
+            codec = 0xFF;
+        }
+        pt.sector[i] = s;
+        pt.off[i] = (uint16_t)(payload + hdr);
+        pt.len[i] = (uint16_t)rest;
+        pt.codec[i] = (uint8_t)codec;
+        pt.pad2[i] = (uint8_t)pad2;
+        pt.params[i] = params;
+        pt.mlp_len[i] = mlp_len;
+        pt.pcm_frames[i] = pcm_frames;
+        i++;
+    }
+}
+
+// per-packet flags that feed the prefix counts used by track setup
+__global__ void k_packet_flags(PacketTable pt, uint32_t np, uint32_t *__restrict__ nonmlp, uint32_t *__restrict__ pcm_stop)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    nonmlp[i] = pt.codec[i] != CODEC_MLP;
+    // a PCM track stops in front of a packet that is not PCM, changes the stream
+    // parameters or holds no whole chunk (reference dvd-audio.c:1042-1056, 770-774)
+    uint32_t stop = pt.codec[i] != CODEC_PCM || pt.pcm_frames[i] == 0;
+    if (!stop && i > 0) stop = pt.codec[i - 1] != CODEC_PCM || pt.params[i - 1] != pt.params[i];
+    pcm_stop[i] = stop;
+}
+
+// ------------------------------------------------------- elementary stream
+
+// One warp per MLP packet: payload bytes -> ES[es_off ...].  Byte-granular on
+// both sides (neither side is aligned); lanes take consecutive bytes so the
+// accesses coalesce into 32-byte segments.
+__global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t np,
+                            const uint64_t *__restrict__ pk_es, uint8_t *__restrict__ es)
+{
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warp >= np) return;
+    const uint32_t n = pt.mlp_len[warp];
+    if (!n) return;
+    const uint8_t *src = sectors + (uint64_t)pt.sector[warp] * DVDA_SECTOR + pt.off[warp] + pt.pad2[warp];
+    uint8_t *dst = es + pk_es[warp];
+    // head bytes up to a 4-byte boundary of dst, then whole words, then the tail
+    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+    if (lane < head) dst[lane] = ld_u8(src + lane);
+    const uint32_t words = (n - head) >> 2;
+    const uint8_t *s = src + head;
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t mis = (uint32_t)((uintptr_t)s & 3);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s - mis);
+    for (uint32_t i = lane; i < words; i += 32) {
+        const uint32_t a = __ldg(sw + i);
+        const uint32_t b = mis ? __ldg(sw + i + 1) : 0;   // still inside the sector (or the pad behind the buffer)
+        d[i] = __funnelshift_r(a, b, mis * 8);
+    }
+    const uint32_t tail0 = head + words * 4;
+    if (tail0 + lane < n) dst[tail0 + lane] = ld_u8(src + tail0 + lane);
+}
+
+// ---------------------------------------------------------------------- PCM
+
+// Sample order inside a chunk (two frames), as group lists: see
+// build_pcm_tables() in engine.cu.  tab[i] = destination byte (little-endian
+// sample bytes, sample-major) of chunk byte i — the same permutation the
+// reference applies (src/pcm.c:103-166), rebuilt from the layout rule.
+__constant__ uint8_t c_pcm_perm[2][6][36];
+
+// One block per PCM packet; each thread unpacks whole chunks (two frames).
+__global__ void k_pcm_unpack(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t np,
+                             const uint64_t *__restrict__ pk_pf, const TrackDev *__restrict__ tracks,
+                             const uint32_t *__restrict__ trk_pk_lo, uint32_t n_tracks,
+                             int32_t *__restrict__ pcm)
+{
+    const uint32_t i = blockIdx.x;
+    if (i >= np || pt.codec[i] != CODEC_PCM) return;
+    // owning track: the last one whose first packet is <= i
+    const uint32_t t = upper_bound_dev(trk_pk_lo, n_tracks, i);
+    if (t == 0) return;
+    const TrackDev &T = tracks[t - 1];
+    if (T.status != 0 || T.codec != 0 || i < T.pk_lo || i >= T.pcm_pk_end) return;
+    const uint32_t ch = T.channels, bytes = T.bits >> 3, chunk = T.pcm_chunk;
+    const uint32_t nchunks = pt.pcm_frames[i] >> 1;
+    const uint8_t *src = sectors + (uint64_t)pt.sector[i] * DVDA_SECTOR + pt.off[i] + pt.pad2[i];
+    int32_t *dst = pcm + T.out_base + (pk_pf[i] - T.pcm_frame0) * ch;
+    const uint8_t *perm = c_pcm_perm[bytes == 3][ch - 1];
+    for (uint32_t k = threadIdx.x; k < nchunks; k += blockDim.x) {
+        const uint8_t *c = src + k * chunk;
+        uint8_t un[36];
+        for (uint32_t b = 0; b < chunk; b++) un[perm[b]] = (uint8_t)ld_u8(c + b);
+        int32_t *o = dst + (uint64_t)k * 2 * ch;
+        for (uint32_t smp = 0; smp < 2 * ch; smp++) {
+            int32_t v;
+            if (bytes == 2) v = (int16_t)(un[2 * smp] | (un[2 * smp + 1] << 8));
+            else {
+                v = un[3 * smp] | (un[3 * smp + 1] << 8) | (un[3 * smp + 2] << 16);
+                v = (v << 8) >> 8;
+            }
+            o[smp] = v;
+        }
+    }
+}
+
+int upload_pcm_tables(const uint8_t *tables)
+{
+    CUDA_TRY(cudaMemcpyToSymbol(c_pcm_perm, tables, 2 * 6 * 36));
+    return 0;
+}
+
+// ------------------------------------------------------------ host launchers
+
+int launch_sector_count(const uint8_t *sectors, uint32_t n_sectors, uint32_t *sec_cnt, uint32_t *sec_bad, cudaStream_t s)
+{
+    LAUNCH(k_sector_count, div_up_u32(n_sectors, 128), 128, 0, s, sectors, n_sectors, sec_cnt, sec_bad);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_t *sec_base, PacketTable pt, uint32_t np,
+                       uint32_t *nonmlp, uint32_t *pcm_stop, cudaStream_t s)
+{
+    LAUNCH(k_packet_fill, div_up_u32(n_sectors, 128), 128, 0, s, sectors, n_sectors, sec_base, pt);
+    if (np) LAUNCH(k_packet_flags, div_up_u32(np, 256), 256, 0, s, pt, np, nonmlp, pcm_stop);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_es_gather(const uint8_t *sectors, PacketTable pt, uint32_t np, const uint64_t *pk_es, uint8_t *es, cudaStream_t s)
+{
+    if (!np) return 0;
+    LAUNCH(k_es_gather, div_up_u32((uint64_t)np * 32, 256), 256, 0, s, sectors, pt, np, pk_es, es);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t np, const uint64_t *pk_pf,
+                      const TrackDev *tracks, const uint32_t *trk_pk_lo, uint32_t n_tracks, int32_t *pcm, cudaStream_t s)
+{
+    if (!np) return 0;
+    LAUNCH(k_pcm_unpack, np, 128, 0, s, sectors, pt, np, pk_pf, tracks, trk_pk_lo, n_tracks, pcm);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,524 @@
+// engine.cu — host side of the CUDA engine: device buffers, the kernel sequence
+// of one decode, and the C ABI declared in include/dvdagpu.h.
+//
+// One decode = one pass of the whole hot path over a batch of tracks that share
+// a sector buffer:
+//
+//   demux   k_sector_count -> scan -> k_packet_fill -> scans -> k_es_gather
+//   index   k_sync_scan x2 -> k_track_setup -> k_segment_fill -> k_au_chase x2
+//           -> k_yield_* -> k_group_setup
+//   decode  k_checkdata -> k_mlp_decode (-> k_carry_fix) -> k_seg_finalize
+//   output  k_rematrix (MLP), k_pcm_unpack (PCM)
+//
+// The host only sizes buffers between stages (a handful of 4- or 8-byte
+// read-backs); no sample or stream byte is touched by the CPU.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "../../include/dvdagpu.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+thread_local uint32_t g_launch_count = 0;
+static thread_local char g_error[512] = "";
+
+void dvdagpu_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *dvdagpu_last_error(void) { return g_error; }
+
+int upload_crc_table(const uint8_t *t);
+
+// a device buffer that only ever grows
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            dvdagpu_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return -1;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+enum {
+    B_SECTORS, B_SEC_CNT, B_SEC_BAD, B_SEC_BASE, B_BAD_PREFIX,
+    B_PK_SECTOR, B_PK_OFF, B_PK_LEN, B_PK_CODEC, B_PK_PAD2, B_PK_PARAMS, B_PK_MLPLEN, B_PK_PCMF,
+    B_PK_ES, B_PK_PF, B_PK_NONMLP, B_PK_NM_PREFIX, B_PK_STOP, B_PK_STOP_PREFIX, B_PK_YIELD,
+    B_ES, B_SYNC_CNT_RAW, B_SYNC_CNT_VALID, B_SYNC_BASE_RAW, B_SYNC_BASE_VALID, B_RAW, B_VALID,
+    B_TRACKS, B_TRK_PK_LO, B_TRK_SEG_BASE, B_TRK_GRP_BASE,
+    B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
+    B_SS_FLAGS, B_SS_FLAGS_PREV, B_FIR_TAIL,
+    B_GROUPS, B_GRP_CELLS, B_CELL_BASE, B_GRP_CHUNKS, B_GRP_CHUNK_BASE,
+    B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
+    B_COUNT
+};
+
+struct dvdagpu_ctx {
+    int device;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    DevBuf buf[B_COUNT];
+    cudaEvent_t ev[6];
+    cudaEvent_t kev[8][2];
+    bool kev_used[8];
+    dvdagpu_stats stats;
+    uint64_t pcm_samples;
+    std::vector<TrackDev> h_tracks;
+};
+
+// ---- constant tables, derived (not copied) --------------------------------
+
+// PCM chunk permutation from the layout rule: a chunk is one or
+// two groups of samples; 16-bit groups hold big-endian samples, 24-bit groups all
+// (high, middle) byte pairs then all low bytes.  tab[i] = little-endian byte slot
+// of stream byte i.
+static void build_pcm_tables(uint8_t tab[2][6][36])
+{
+    memset(tab, 0, 2 * 6 * 36);
+    for (int b24 = 0; b24 < 2; b24++) {
+        for (int ch = 1; ch <= 6; ch++) {
+            const int n = 2 * ch;
+            int order[12], cnt = 0, first;
+            const bool two = (ch == 6) || (b24 && ch >= 3);
+            if (!two) { for (int i = 0; i < n; i++) order[cnt++] = i; first = n; }
+            else {
+                const int hi = ch == 6 ? 4 : ch;
+                for (int f = 0; f < 2; f++) for (int c = 2; c < hi; c++) order[cnt++] = f * ch + c;
+                first = cnt;
+                for (int f = 0; f < 2; f++) for (int c = 0; c < ch; c++) if (c < 2 || c >= hi) order[cnt++] = f * ch + c;
+            }
+            uint8_t *t = tab[b24][ch - 1];
+            int i = 0;
+            for (int g = 0; g < 2; g++) {
+                const int a = g ? first : 0, b = g ? n : first;
+                if (!b24) for (int k = a; k < b; k++) { t[i++] = (uint8_t)(order[k] * 2 + 1); t[i++] = (uint8_t)(order[k] * 2); }
+                else {
+                    for (int k = a; k < b; k++) { t[i++] = (uint8_t)(order[k] * 3 + 2); t[i++] = (uint8_t)(order[k] * 3 + 1); }
+                    for (int k = a; k < b; k++) t[i++] = (uint8_t)(order[k] * 3);
+                }
+            }
+        }
+    }
+}
+
+static void build_crc8(uint8_t t[256])
+{
+    for (unsigned i = 0; i < 256; i++) {
+        unsigned c = i;
+        for (int k = 0; k < 8; k++) c = (c & 0x80) ? ((c << 1) ^ 0x63) & 0xFF : (c << 1) & 0xFF;
+        t[i] = (uint8_t)c;
+    }
+}
+
+// ---- context -----------------------------------------------------------------
+
+extern "C" int dvdagpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" dvdagpu_ctx *dvdagpu_create(int device)
+{
+    g_error[0] = 0;
+    int n = dvdagpu_device_count();
+    if (n <= 0) { dvdagpu_set_error("no CUDA device: this engine has no CPU path"); return nullptr; }
+    if (device < 0 || device >= n) { dvdagpu_set_error("device %d out of range (%d present)", device, n); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { dvdagpu_set_error("cudaSetDevice(%d) failed", device); return nullptr; }
+    dvdagpu_ctx *c = new dvdagpu_ctx();
+    c->device = device;
+    c->pcm_samples = 0;
+    memset(&c->stats, 0, sizeof c->stats);
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        dvdagpu_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    c->stream = c->own_stream;
+    for (auto &e : c->ev) cudaEventCreate(&e);
+    for (auto &k : c->kev) { cudaEventCreate(&k[0]); cudaEventCreate(&k[1]); }
+    uint8_t pcm_tab[2][6][36], crc[256];
+    build_pcm_tables(pcm_tab);
+    build_crc8(crc);
+    if (upload_pcm_tables(&pcm_tab[0][0][0]) || upload_crc_table(crc)) { dvdagpu_destroy(c); return nullptr; }
+    return c;
+}
+
+extern "C" void dvdagpu_destroy(dvdagpu_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &b : c->buf) b.release();
+    for (auto &e : c->ev) cudaEventDestroy(e);
+    for (auto &k : c->kev) { cudaEventDestroy(k[0]); cudaEventDestroy(k[1]); }
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int dvdagpu_set_stream(dvdagpu_ctx *c, void *cuda_stream)
+{
+    if (!c) return -1;
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return 0;
+}
+
+extern "C" void *dvdagpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        dvdagpu_set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void dvdagpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int dvdagpu_get_stats(dvdagpu_ctx *c, dvdagpu_stats *out)
+{
+    if (!c || !out) return -1;
+    *out = c->stats;
+    return 0;
+}
+
+extern "C" const void *dvdagpu_pcm_device(dvdagpu_ctx *c, uint64_t *n_samples)
+{
+    if (!c) return nullptr;
+    if (n_samples) *n_samples = c->pcm_samples;
+    return c->buf[B_PCM].p;
+}
+
+extern "C" int dvdagpu_fetch(dvdagpu_ctx *c, uint64_t offset, uint64_t count, int32_t *dst)
+{
+    if (!c) return -1;
+    if (offset + count > c->pcm_samples) { dvdagpu_set_error("fetch beyond the decoded samples"); return -1; }
+    if (!count) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(dst, c->buf[B_PCM].as<int32_t>() + offset, count * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- one decode ----------------------------------------------------------------
+
+#define ENSURE(id, bytes) do { if (c->buf[id].ensure(bytes)) return -1; } while (0)
+#define TRY(expr) do { if ((expr) != 0) return -1; } while (0)
+// device time of one kernel (or a short run of kernels) into stats.kernel_ms[id]
+#define TIMED(id, expr)                                                        \
+    do {                                                                       \
+        CUDA_TRY(cudaEventRecord(c->kev[id][0], s));                           \
+        TRY(expr);                                                             \
+        CUDA_TRY(cudaEventRecord(c->kev[id][1], s));                           \
+        c->kev_used[id] = true;                                                \
+    } while (0)
+
+template <typename T>
+static int read_back(dvdagpu_ctx *c, const T *dev, T *host)
+{
+    CUDA_TRY(cudaMemcpyAsync(host, dev, sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n_sectors64,
+                            uint32_t n_tracks, const dvdagpu_track_desc *descs, dvdagpu_track_result *results)
+{
+    g_error[0] = 0;
+    g_launch_count = 0;
+    cudaStream_t s = c->stream;
+    if (n_sectors64 == 0 || n_sectors64 > 0x7FFFFFFFull) { dvdagpu_set_error("bad sector count"); return -1; }
+    if (!n_tracks) { c->pcm_samples = 0; return 0; }
+    const uint32_t n_sectors = (uint32_t)n_sectors64;
+    memset(&c->stats, 0, sizeof c->stats);
+    memset(c->kev_used, 0, sizeof c->kev_used);
+    CUDA_TRY(cudaEventRecord(c->ev[0], s));
+
+    // tracks in sector order (the kernels binary-search them); results go back in caller order
+    std::vector<uint32_t> order(n_tracks);
+    for (uint32_t i = 0; i < n_tracks; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return descs[a].first_sector < descs[b].first_sector; });
+    std::vector<TrackDev> &ht = c->h_tracks;
+    ht.assign(n_tracks, TrackDev());
+    for (uint32_t i = 0; i < n_tracks; i++) {
+        memset(&ht[i], 0, sizeof(TrackDev));
+        ht[i].first_sector = descs[order[i]].first_sector;
+        ht[i].last_sector = descs[order[i]].last_sector;
+        ht[i].pts_length = descs[order[i]].pts_length;
+    }
+
+    // ---------------- demux
+    ENSURE(B_SEC_CNT, (size_t)n_sectors * 4);
+    ENSURE(B_SEC_BAD, (size_t)n_sectors * 4);
+    ENSURE(B_SEC_BASE, (size_t)(n_sectors + 1) * 4);
+    ENSURE(B_BAD_PREFIX, (size_t)(n_sectors + 1) * 4);
+    ENSURE(B_SCAN_TMP, scan_tmp_bytes((uint64_t)n_sectors * 2048 / 32 + 4096));
+    void *tmp = c->buf[B_SCAN_TMP].p;
+    const size_t tmp_bytes = c->buf[B_SCAN_TMP].cap;
+    uint32_t *sec_cnt = c->buf[B_SEC_CNT].as<uint32_t>(), *sec_bad = c->buf[B_SEC_BAD].as<uint32_t>();
+    uint32_t *sec_base = c->buf[B_SEC_BASE].as<uint32_t>(), *bad_prefix = c->buf[B_BAD_PREFIX].as<uint32_t>();
+    TRY(launch_sector_count(d_sectors, n_sectors, sec_cnt, sec_bad, s));
+    TRY(scan_u32_to_u32(sec_cnt, sec_base, n_sectors, tmp, tmp_bytes, s));
+    TRY(scan_u32_to_u32(sec_bad, bad_prefix, n_sectors, tmp, tmp_bytes, s));
+    uint32_t np = 0;
+    TRY(read_back(c, sec_base + n_sectors, &np));
+
+    const size_t npa = (size_t)np + 1;
+    ENSURE(B_PK_SECTOR, npa * 4); ENSURE(B_PK_OFF, npa * 2); ENSURE(B_PK_LEN, npa * 2);
+    ENSURE(B_PK_CODEC, npa); ENSURE(B_PK_PAD2, npa); ENSURE(B_PK_PARAMS, npa * 4);
+    ENSURE(B_PK_MLPLEN, npa * 4); ENSURE(B_PK_PCMF, npa * 4);
+    ENSURE(B_PK_ES, npa * 8); ENSURE(B_PK_PF, npa * 8);
+    ENSURE(B_PK_NONMLP, npa * 4); ENSURE(B_PK_NM_PREFIX, npa * 4);
+    ENSURE(B_PK_STOP, npa * 4); ENSURE(B_PK_STOP_PREFIX, npa * 4);
+    ENSURE(B_PK_YIELD, npa);
+    PacketTable pt;
+    pt.sector = c->buf[B_PK_SECTOR].as<uint32_t>(); pt.off = c->buf[B_PK_OFF].as<uint16_t>();
+    pt.len = c->buf[B_PK_LEN].as<uint16_t>(); pt.codec = c->buf[B_PK_CODEC].as<uint8_t>();
+    pt.pad2 = c->buf[B_PK_PAD2].as<uint8_t>(); pt.params = c->buf[B_PK_PARAMS].as<uint32_t>();
+    pt.mlp_len = c->buf[B_PK_MLPLEN].as<uint32_t>(); pt.pcm_frames = c->buf[B_PK_PCMF].as<uint32_t>();
+    uint64_t *pk_es = c->buf[B_PK_ES].as<uint64_t>(), *pk_pf = c->buf[B_PK_PF].as<uint64_t>();
+    uint32_t *nonmlp = c->buf[B_PK_NONMLP].as<uint32_t>(), *nm_prefix = c->buf[B_PK_NM_PREFIX].as<uint32_t>();
+    uint32_t *pstop = c->buf[B_PK_STOP].as<uint32_t>(), *stop_prefix = c->buf[B_PK_STOP_PREFIX].as<uint32_t>();
+    TRY(launch_packet_fill(d_sectors, n_sectors, sec_base, pt, np, nonmlp, pstop, s));
+    TRY(scan_u32_to_u64(pt.mlp_len, pk_es, np, tmp, tmp_bytes, s));
+    TRY(scan_u32_to_u64(pt.pcm_frames, pk_pf, np, tmp, tmp_bytes, s));
+    TRY(scan_u32_to_u32(nonmlp, nm_prefix, np, tmp, tmp_bytes, s));
+    TRY(scan_u32_to_u32(pstop, stop_prefix, np, tmp, tmp_bytes, s));
+    uint64_t es_total = 0;
+    TRY(read_back(c, pk_es + np, &es_total));
+
+    ENSURE(B_ES, es_total + DVDA_ES_PAD);
+    uint8_t *es = c->buf[B_ES].as<uint8_t>();
+    CUDA_TRY(cudaMemsetAsync(es + es_total, 0, DVDA_ES_PAD, s));
+    TIMED(DVDAGPU_K_ES_GATHER, launch_es_gather(d_sectors, pt, np, pk_es, es, s));
+    CUDA_TRY(cudaEventRecord(c->ev[1], s));
+
+    // ---------------- index
+    const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
+    ENSURE(B_SYNC_CNT_RAW, (size_t)chunks * 4); ENSURE(B_SYNC_CNT_VALID, (size_t)chunks * 4);
+    ENSURE(B_SYNC_BASE_RAW, (size_t)(chunks + 1) * 4); ENSURE(B_SYNC_BASE_VALID, (size_t)(chunks + 1) * 4);
+    uint32_t *cnt_raw = c->buf[B_SYNC_CNT_RAW].as<uint32_t>(), *cnt_valid = c->buf[B_SYNC_CNT_VALID].as<uint32_t>();
+    uint32_t *base_raw = c->buf[B_SYNC_BASE_RAW].as<uint32_t>(), *base_valid = c->buf[B_SYNC_BASE_VALID].as<uint32_t>();
+    uint32_t n_raw = 0, n_valid = 0;
+    if (es_total) {
+        TRY(launch_sync_count(es, es_total, cnt_raw, cnt_valid, s));
+        TRY(scan_u32_to_u32(cnt_raw, base_raw, chunks, tmp, tmp_bytes, s));
+        TRY(scan_u32_to_u32(cnt_valid, base_valid, chunks, tmp, tmp_bytes, s));
+        TRY(read_back(c, base_raw + chunks, &n_raw));
+        TRY(read_back(c, base_valid + chunks, &n_valid));
+    }
+    ENSURE(B_RAW, ((size_t)n_raw + 1) * 8); ENSURE(B_VALID, ((size_t)n_valid + 1) * 8);
+    uint64_t *raw = c->buf[B_RAW].as<uint64_t>(), *valid = c->buf[B_VALID].as<uint64_t>();
+    if (n_raw) TRY(launch_sync_fill(es, es_total, base_raw, base_valid, raw, valid, s));
+
+    ENSURE(B_TRACKS, (size_t)n_tracks * sizeof(TrackDev));
+    ENSURE(B_TRK_PK_LO, (size_t)n_tracks * 4); ENSURE(B_TRK_SEG_BASE, (size_t)(n_tracks + 1) * 4);
+    ENSURE(B_TRK_GRP_BASE, (size_t)(n_tracks + 1) * 4);
+    TrackDev *d_tracks = c->buf[B_TRACKS].as<TrackDev>();
+    CUDA_TRY(cudaMemcpyAsync(d_tracks, ht.data(), n_tracks * sizeof(TrackDev), cudaMemcpyHostToDevice, s));
+    TrackSetupArgs ta;
+    ta.es = es; ta.es_total = es_total; ta.n_sectors = n_sectors; ta.sec_base = sec_base; ta.bad_prefix = bad_prefix;
+    ta.pt = pt; ta.np = np; ta.pk_es = pk_es; ta.pk_pf = pk_pf; ta.pk_nonmlp = nm_prefix; ta.pk_pcm_stop = stop_prefix;
+    ta.raw = raw; ta.n_raw = n_raw; ta.valid = valid; ta.n_valid = n_valid;
+    TRY(launch_track_setup(ta, d_tracks, n_tracks, s));
+    CUDA_TRY(cudaMemcpyAsync(ht.data(), d_tracks, n_tracks * sizeof(TrackDev), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+
+    std::vector<uint32_t> h_pk_lo(n_tracks), h_seg_base(n_tracks + 1), h_grp_base(n_tracks + 1);
+    uint32_t nseg = 0, ngroups = 0;
+    for (uint32_t i = 0; i < n_tracks; i++) {
+        h_pk_lo[i] = ht[i].pk_lo;
+        if (ht[i].status != 0 || ht[i].codec != 1) { ht[i].nseg = 0; ht[i].ngrp = 0; }
+        ht[i].seg_base = nseg; ht[i].grp_base = ngroups;
+        h_seg_base[i] = nseg; h_grp_base[i] = ngroups;
+        nseg += ht[i].nseg; ngroups += ht[i].ngrp;
+    }
+    h_seg_base[n_tracks] = nseg; h_grp_base[n_tracks] = ngroups;
+    uint32_t *trk_pk_lo = c->buf[B_TRK_PK_LO].as<uint32_t>(), *trk_seg_base = c->buf[B_TRK_SEG_BASE].as<uint32_t>();
+    uint32_t *trk_grp_base = c->buf[B_TRK_GRP_BASE].as<uint32_t>();
+    CUDA_TRY(cudaMemcpyAsync(d_tracks, ht.data(), n_tracks * sizeof(TrackDev), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(trk_pk_lo, h_pk_lo.data(), n_tracks * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(trk_seg_base, h_seg_base.data(), (n_tracks + 1) * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(trk_grp_base, h_grp_base.data(), (n_tracks + 1) * 4, cudaMemcpyHostToDevice, s));
+
+    MlpTables m;
+    memset(&m, 0, sizeof m);
+    m.es = es; m.es_total = es_total; m.pk_es = pk_es; m.np = np;
+    m.tracks = d_tracks; m.n_tracks = n_tracks; m.nseg = nseg; m.ngroups = ngroups;
+    uint32_t nau = 0;
+    uint64_t total_chunks = 0;
+    uint64_t *grp_chunk_base = nullptr;
+    if (nseg) {
+        ENSURE(B_SEGS, (size_t)nseg * sizeof(SegDev));
+        ENSURE(B_SEG_NAU, (size_t)nseg * 4); ENSURE(B_SEG_AU_BASE, (size_t)(nseg + 1) * 4);
+        m.segs = c->buf[B_SEGS].as<SegDev>();
+        uint32_t *seg_nau = c->buf[B_SEG_NAU].as<uint32_t>(), *seg_au_base = c->buf[B_SEG_AU_BASE].as<uint32_t>();
+        TRY(launch_segment_fill(d_tracks, n_tracks, trk_seg_base, valid, m.segs, nseg, s));
+        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, nullptr, seg_au_base, 0, s));
+        TRY(scan_u32_to_u32(seg_nau, seg_au_base, nseg, tmp, tmp_bytes, s));
+        TRY(read_back(c, seg_au_base + nseg, &nau));
+        m.nau = nau;
+        const size_t naua = (size_t)nau + 1;
+        ENSURE(B_AU_POS, naua * 8); ENSURE(B_AU_ERR, naua); ENSURE(B_AU, naua * sizeof(AuDev));
+        ENSURE(B_PSETS, naua * sizeof(ParamSet)); ENSURE(B_AU_FRAMES, naua * 2 * 4);
+        ENSURE(B_SS_FLAGS, (size_t)nseg * 2 * 4); ENSURE(B_SS_FLAGS_PREV, (size_t)nseg * 2 * 4);
+        ENSURE(B_FIR_TAIL, (size_t)nseg * 2 * DVDA_MAX_CH * 8 * 4);
+        m.au_pos = c->buf[B_AU_POS].as<uint64_t>(); m.au_err = c->buf[B_AU_ERR].as<uint8_t>();
+        m.au = c->buf[B_AU].as<AuDev>(); m.psets = c->buf[B_PSETS].as<ParamSet>();
+        m.au_frames_ss = c->buf[B_AU_FRAMES].as<uint32_t>();
+        m.ss_flags = c->buf[B_SS_FLAGS].as<uint32_t>(); m.ss_flags_prev = c->buf[B_SS_FLAGS_PREV].as<uint32_t>();
+        m.fir_tail = c->buf[B_FIR_TAIL].as<int32_t>();
+        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, m.au_pos, seg_au_base, 1, s));
+        TRY(launch_yield(m, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), s));
+        CUDA_TRY(cudaEventRecord(c->ev[2], s));
+
+        // ---------------- decode
+        TIMED(DVDAGPU_K_CHECKDATA, launch_checkdata(m, seg_au_base, s));
+        ENSURE(B_GROUPS, (size_t)ngroups * sizeof(GroupDev));
+        ENSURE(B_GRP_CELLS, (size_t)ngroups * 4); ENSURE(B_CELL_BASE, (size_t)(ngroups + 1) * 8);
+        ENSURE(B_GRP_CHUNKS, (size_t)ngroups * 4); ENSURE(B_GRP_CHUNK_BASE, (size_t)(ngroups + 1) * 8);
+        ENSURE(B_SEG_FRAMES, (size_t)nseg * 4); ENSURE(B_SEG_FRAME_SCAN, (size_t)(nseg + 1) * 8);
+        ENSURE(B_STATUS, 64);
+        m.groups = c->buf[B_GROUPS].as<GroupDev>();
+        uint32_t *grp_cells = c->buf[B_GRP_CELLS].as<uint32_t>(), *grp_chunks = c->buf[B_GRP_CHUNKS].as<uint32_t>();
+        uint64_t *cell_base = c->buf[B_CELL_BASE].as<uint64_t>();
+        grp_chunk_base = c->buf[B_GRP_CHUNK_BASE].as<uint64_t>();
+        uint32_t *seg_frames = c->buf[B_SEG_FRAMES].as<uint32_t>();
+        uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
+        uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
+
+        for (int attempt = 0; attempt < 2; attempt++) {
+            TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, s));
+            TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
+            TRY(scan_u32_to_u64(grp_chunks, grp_chunk_base, ngroups, tmp, tmp_bytes, s));
+            uint64_t cells = 0;
+            TRY(read_back(c, cell_base + ngroups, &cells));
+            TRY(read_back(c, grp_chunk_base + ngroups, &total_chunks));
+            ENSURE(B_TILES, (cells * DVDA_LANES + 64) * sizeof(int32_t));
+            ENSURE(B_BYPASS, cells * DVDA_LANES + 64);
+            m.tiles = c->buf[B_TILES].as<int32_t>(); m.bypass = c->buf[B_BYPASS].as<uint8_t>();
+            TRY(launch_group_offsets(m.groups, ngroups, cell_base, s));
+            CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
+            TIMED(DVDAGPU_K_MLP_DECODE, launch_mlp_decode(m, s));
+            CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
+            TIMED(DVDAGPU_K_CARRY_FIX, launch_carry_fix(m, s));
+            TRY(launch_seg_finalize(m, seg_frames, d_status, s));
+            uint32_t status = 0;
+            TRY(read_back(c, d_status, &status));
+            if (!(status & SEG_OVERFLOW)) break;
+            if (attempt == 1) { dvdagpu_set_error("tile overflow persists"); return -1; }
+        }
+        TRY(scan_u32_to_u64(seg_frames, seg_frame_scan, nseg, tmp, tmp_bytes, s));
+        TRY(launch_track_finalize(m, seg_frame_scan, s));
+    } else {
+        CUDA_TRY(cudaEventRecord(c->ev[2], s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(ht.data(), d_tracks, n_tracks * sizeof(TrackDev), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaEventRecord(c->ev[3], s));
+    if (getenv("DVDAGPU_DEBUG")) {
+        fprintf(stderr, "[dvdagpu] sectors=%u packets=%u es=%llu raw=%u valid=%u segs=%u groups=%u aus=%u\n",
+                n_sectors, np, (unsigned long long)es_total, n_raw, n_valid, nseg, ngroups, nau);
+        for (uint32_t i = 0; i < n_tracks; i++) {
+            const TrackDev &T = ht[i];
+            fprintf(stderr, "[dvdagpu] track %u: status=%d codec=%d err=%x ch=%u pk=[%u,%u) pk_x=%u pk_open=%u es=[%llu,%llu) cut=%llu nss=%u nseg=%u err_seg=%u frames=%llu trunc=%u\n",
+                    i, T.status, T.codec, T.error_flags, T.channels, T.pk_lo, T.pk_hi, T.pk_x, T.pk_open,
+                    (unsigned long long)T.es_start, (unsigned long long)T.es_end, (unsigned long long)T.es_cut,
+                    T.nss, T.nseg, T.err_seg, (unsigned long long)T.frames, T.truncated);
+        }
+        if (nseg) {
+            std::vector<SegDev> hs(std::min<uint32_t>(nseg, 8));
+            cudaMemcpy(hs.data(), m.segs, hs.size() * sizeof(SegDev), cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < hs.size(); i++)
+                fprintf(stderr, "[dvdagpu] seg %zu: es=[%llu,%llu) n_au=%u au_base=%u flags=%x frames=%u err=%x err_au=%u frame0=%llu\n",
+                        i, (unsigned long long)hs[i].es_pos, (unsigned long long)hs[i].es_limit, hs[i].n_au, hs[i].au_base,
+                        hs[i].flags, hs[i].frames, hs[i].err, hs[i].err_au, (unsigned long long)hs[i].frame0);
+        }
+    }
+
+    // ---------------- output
+    uint64_t total_samples = 0;
+    bool any_pcm = false;
+    for (uint32_t i = 0; i < n_tracks; i++) {
+        ht[i].out_base = total_samples;
+        if (ht[i].status == 0) total_samples += ht[i].frames * ht[i].channels;
+        any_pcm |= ht[i].status == 0 && ht[i].codec == 0;
+    }
+    ENSURE(B_PCM, (total_samples + 64) * sizeof(int32_t));
+    m.pcm = c->buf[B_PCM].as<int32_t>();
+    c->pcm_samples = total_samples;
+    CUDA_TRY(cudaMemcpyAsync(d_tracks, ht.data(), n_tracks * sizeof(TrackDev), cudaMemcpyHostToDevice, s));
+    if (nseg && total_chunks) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, total_chunks, grp_chunk_base, s));
+    if (any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, np, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));
+    CUDA_TRY(cudaEventRecord(c->ev[4], s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+
+    // ---------------- results
+    uint64_t es_used = 0;
+    for (uint32_t i = 0; i < n_tracks; i++) {
+        const TrackDev &T = ht[i];
+        dvdagpu_track_result &R = results[order[i]];
+        memset(&R, 0, sizeof R);
+        R.status = T.status;
+        if (T.status != 0) continue;
+        R.error_flags = T.error_flags; R.codec = T.codec;
+        R.group_0_bps = T.g0_bps; R.group_1_bps = T.g1_bps; R.group_0_rate = T.g0_rate; R.group_1_rate = T.g1_rate;
+        R.channel_assignment = T.assignment; R.channels = T.channels; R.bits_per_sample = T.bits; R.sample_rate = T.rate;
+        R.frames = T.frames; R.pcm_offset = T.out_base; R.truncated = T.truncated;
+        if (T.codec == 1) es_used += T.es_end - T.es_start;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.demux_ms = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stats.index_ms = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.decode_ms = ms;
+    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.output_ms = ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); c->stats.total_ms = ms;
+    for (int k = 0; k < 8; k++) {
+        if (c->kev_used[k] && cudaEventElapsedTime(&ms, c->kev[k][0], c->kev[k][1]) == cudaSuccess) c->stats.kernel_ms[k] = ms;
+    }
+    c->stats.launches = g_launch_count;
+    c->stats.segments = nseg;
+    c->stats.access_units = nau;
+    c->stats.es_bytes = es_used;
+    c->stats.samples = total_samples;
+    return 0;
+}
+
+extern "C" int dvdagpu_decode_device(dvdagpu_ctx *c, const void *device_sectors, uint64_t n_sectors,
+                                     uint32_t n_tracks, const dvdagpu_track_desc *tracks, dvdagpu_track_result *results)
+{
+    if (!c || !device_sectors || !tracks || !results) { dvdagpu_set_error("null argument"); return -1; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    return decode_on_device(c, (const uint8_t *)device_sectors, n_sectors, n_tracks, tracks, results);
+}
+
+extern "C" int dvdagpu_decode_host(dvdagpu_ctx *c, const uint8_t *sectors, uint64_t n_sectors,
+                                   uint32_t n_tracks, const dvdagpu_track_desc *tracks, dvdagpu_track_result *results)
+{
+    if (!c || !sectors || !tracks || !results) { dvdagpu_set_error("null argument"); return -1; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    ENSURE(B_SECTORS, n_sectors * DVDA_SECTOR + 256);
+    CUDA_TRY(cudaMemcpyAsync(c->buf[B_SECTORS].p, sectors, n_sectors * DVDA_SECTOR, cudaMemcpyHostToDevice, c->stream));
+    return decode_on_device(c, c->buf[B_SECTORS].as<uint8_t>(), n_sectors, n_tracks, tracks, results);
+}

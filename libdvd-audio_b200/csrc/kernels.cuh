@@ -1,0 +1,92 @@
+// kernels.cuh — tables shared between the kernel files and the host-side
+// launchers the engine (engine.cu) calls.
+#pragma once
+#include "common.cuh"
+
+// one row per audio (0xBD) packet, in sector order
+struct PacketTable {
+    uint32_t *sector;      // sector index inside the uploaded buffer
+    uint16_t *off;         // offset in the sector of the byte behind pad_2_size
+    uint16_t *len;         // bytes from there to the end of the packet
+    uint8_t *codec;        // 0xA0 PCM, 0xA1 MLP, 0xFF anything else / malformed
+    uint8_t *pad2;         // pad_2_size
+    uint32_t *params;      // PCM: packed stream parameters of this packet
+    uint32_t *mlp_len;     // MLP: elementary-stream bytes in this packet
+    uint32_t *pcm_frames;  // PCM: whole frames in this packet
+};
+
+// everything the MLP kernels need to find their data
+struct MlpTables {
+    const uint8_t *es;             // elementary stream (padded with DVDA_ES_PAD zero bytes)
+    uint64_t es_total;
+    const uint64_t *pk_es;         // [np + 1] ES offset of every packet
+    uint32_t np;
+    TrackDev *tracks;
+    uint32_t n_tracks;
+    SegDev *segs;
+    uint32_t nseg;
+    GroupDev *groups;
+    uint32_t ngroups;
+    uint64_t *au_pos;              // [nau] ES offset of every access unit
+    uint8_t *au_err;               // [nau] 0 ok, 1 drop (parameter change), else ERR_* bits
+    AuDev *au;                     // [nau]
+    ParamSet *psets;               // [nau]
+    uint32_t *au_frames_ss;        // [2][nau] frames each substream decoded
+    uint32_t nau;
+    uint32_t *ss_flags;            // [2][nseg] SEG_* per substream
+    uint32_t *ss_flags_prev;       // snapshot taken before the carry fix-up
+    int32_t *fir_tail;             // [2][nseg][8 ch][8] last outputs per channel
+    int32_t *tiles;
+    uint8_t *bypass;
+    int32_t *pcm;
+};
+
+// demux.cu
+int upload_pcm_tables(const uint8_t *tables);
+int launch_sector_count(const uint8_t *sectors, uint32_t n_sectors, uint32_t *sec_cnt, uint32_t *sec_bad, cudaStream_t s);
+int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_t *sec_base, PacketTable pt, uint32_t np,
+                       uint32_t *nonmlp, uint32_t *pcm_stop, cudaStream_t s);
+int launch_es_gather(const uint8_t *sectors, PacketTable pt, uint32_t np, const uint64_t *pk_es, uint8_t *es, cudaStream_t s);
+int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t np, const uint64_t *pk_pf,
+                      const TrackDev *tracks, const uint32_t *trk_pk_lo, uint32_t n_tracks, int32_t *pcm, cudaStream_t s);
+
+// mlp_index.cu
+#define SYNC_CHUNK 4096u          // ES bytes per block of the sync scan
+int launch_sync_count(const uint8_t *es, uint64_t es_total, uint32_t *cnt_raw, uint32_t *cnt_valid, cudaStream_t s);
+int launch_sync_fill(const uint8_t *es, uint64_t es_total, const uint32_t *base_raw, const uint32_t *base_valid,
+                     uint64_t *raw, uint64_t *valid, cudaStream_t s);
+struct TrackSetupArgs {
+    const uint8_t *es;
+    uint64_t es_total;
+    uint32_t n_sectors;
+    const uint32_t *sec_base;      // [n_sectors + 1]
+    const uint32_t *bad_prefix;    // [n_sectors + 1]
+    PacketTable pt;
+    uint32_t np;
+    const uint64_t *pk_es;         // [np + 1]
+    const uint64_t *pk_pf;         // [np + 1] PCM frames
+    const uint32_t *pk_nonmlp;     // [np + 1]
+    const uint32_t *pk_pcm_stop;   // [np + 1]
+    const uint64_t *raw;
+    uint32_t n_raw;
+    const uint64_t *valid;
+    uint32_t n_valid;
+};
+int launch_track_setup(TrackSetupArgs a, TrackDev *tracks, uint32_t n_tracks, cudaStream_t s);
+int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_seg_base,
+                        const uint64_t *valid, SegDev *segs, uint32_t nseg, cudaStream_t s);
+int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t nseg, const TrackDev *tracks,
+                    uint32_t *seg_nau, uint64_t *au_pos, const uint32_t *seg_au_base, int fill, cudaStream_t s);
+int launch_yield(MlpTables m, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
+                 uint8_t *pk_yield, cudaStream_t s);
+int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_grp_base, const SegDev *segs,
+                       GroupDev *groups, uint32_t ngroups, uint32_t *grp_cells, uint32_t *grp_chunks, cudaStream_t s);
+int launch_group_offsets(GroupDev *groups, uint32_t ngroups, const uint64_t *cell_base, cudaStream_t s);
+
+// mlp_decode.cu
+int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s);
+int launch_mlp_decode(MlpTables m, cudaStream_t s);
+int launch_carry_fix(MlpTables m, cudaStream_t s);
+int launch_seg_finalize(MlpTables m, uint32_t *seg_frames, uint32_t *status, cudaStream_t s);
+int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, cudaStream_t s);
+int launch_rematrix(MlpTables m, uint64_t total_chunks, const uint64_t *grp_chunk_base, cudaStream_t s);

@@ -1,0 +1,440 @@
+// mlp_index.cu — finding the work: major syncs, track boundaries, restart
+// segments, access units.
+//
+// Replaces (reference tree):
+//   src/dvd-audio.c:1250-1286 find_major_sync         -> k_sync_scan (all positions at once)
+//   src/dvd-audio.c:1318-1365 locate_mlp_parameters   -> k_track_setup (first sync, parameters)
+//   src/dvd-audio.c:1367-1421 mlp_data_to_major_sync  -> k_track_setup (end of track)
+//   src/dvd-audio.c:952-1082  PCM track length rules  -> k_track_setup
+//   src/mlp.c:384-405         read_mlp_frame          -> k_au_chase (12-bit length chain)
+//   src/dvd-audio.c:766-775   "a packet that completes no access unit ends the
+//                              stream"                -> k_yield_mark / k_yield_find
+//
+// The reference discovers all of this one packet at a time while decoding.  Here
+// the sync pattern is matched at every byte of the elementary stream in parallel,
+// tracks are resolved with binary searches over prefix-summed tables, and each
+// restart segment walks its own chain of access-unit lengths.
+#include "common.cuh"
+#include "kernels.cuh"
+
+#define SYNC_THREADS 256
+#define SYNC_PER_THREAD (SYNC_CHUNK / SYNC_THREADS)    // 16 positions
+
+// A sync position starts a *segment* only if the access unit there is a
+// well-formed major sync (1 or 2 substreams) and every substream opens with a
+// restart header: params-present bit, restart bit, 13-bit sync 0x18F5
+// (reference mlp.c:749-759, 822-835).  Anything else stays inside the previous
+// segment (or is a chance match in the payload).
+__device__ bool sync_starts_segment(const uint8_t *es, uint64_t p, uint64_t es_total)
+{
+    if (p + 4 + 28 + 2 > es_total) return false;
+    const uint32_t total = ((ld_u8(es + p) & 15u) << 8 | ld_u8(es + p + 1)) * 2;
+    const uint32_t ns = ld_u8(es + p + 20) >> 4;
+    if (ns != 1 && ns != 2) return false;
+    uint64_t d = p + 32;
+    uint32_t end[2] = {0, 0};
+    for (uint32_t k = 0; k < ns; k++) {
+        if (d + 2 > es_total) return false;
+        const uint32_t b0 = ld_u8(es + d);
+        end[k] = (((b0 & 15u) << 8) | ld_u8(es + d + 1)) * 2;
+        d += 2 + ((b0 >> 7) ? 2 : 0);
+    }
+    for (uint32_t k = 0; k < ns; k++) {
+        const uint64_t s = d + (k ? end[0] : 0);
+        if (s + 2 > p + total || s + 2 > es_total) return false;
+        if (ld_u8(es + s) != 0xF1 || (ld_u8(es + s + 1) & 0xFE) != 0xEA) return false;
+    }
+    return true;
+}
+
+// FILL = false: count raw / valid syncs per chunk.  FILL = true: write them, in
+// stream order, at the scanned bases.
+template <bool FILL>
+__global__ void __launch_bounds__(SYNC_THREADS)
+k_sync_scan(const uint8_t *__restrict__ es, uint64_t es_total,
+            uint32_t *__restrict__ cnt_raw, uint32_t *__restrict__ cnt_valid,
+            const uint32_t *__restrict__ base_raw, const uint32_t *__restrict__ base_valid,
+            uint64_t *__restrict__ raw, uint64_t *__restrict__ valid)
+{
+    const uint64_t p0 = (uint64_t)blockIdx.x * SYNC_CHUNK + (uint64_t)threadIdx.x * SYNC_PER_THREAD;
+    // bytes p0+4 .. p0+4+23 as six big-endian words (the ES buffer is padded)
+    uint32_t w[6];
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(es + p0 + 4);
+#pragma unroll
+    for (int k = 0; k < 6; k++) w[k] = (p0 + 4 + 4 * k < es_total + 8) ? ld_be32_aligned(src + k) : 0;
+    uint32_t m_raw = 0, m_valid = 0;
+#pragma unroll
+    for (int j = 0; j < SYNC_PER_THREAD; j++) {
+        const uint32_t v = __funnelshift_l(w[j / 4 + 1], w[j / 4], (j & 3) * 8);
+        if (v == 0xF8726FBBu && p0 + j + 8 <= es_total) {
+            m_raw |= 1u << j;
+            if (sync_starts_segment(es, p0 + j, es_total)) m_valid |= 1u << j;
+        }
+    }
+    const uint64_t mine = (uint64_t)__popc(m_raw) | ((uint64_t)__popc(m_valid) << 32);
+    uint64_t total;
+    const uint64_t ex = block_excl_scan<SYNC_THREADS>(mine, &total);
+    if (!FILL) {
+        if (threadIdx.x == 0) {
+            cnt_raw[blockIdx.x] = (uint32_t)total;
+            cnt_valid[blockIdx.x] = (uint32_t)(total >> 32);
+        }
+    } else {
+        uint32_t ir = base_raw[blockIdx.x] + (uint32_t)ex;
+        uint32_t iv = base_valid[blockIdx.x] + (uint32_t)(ex >> 32);
+        while (m_raw) {
+            const int j = __ffs(m_raw) - 1;
+            m_raw &= m_raw - 1;
+            raw[ir++] = p0 + j;
+            if ((m_valid >> j) & 1) valid[iv++] = p0 + j;
+        }
+    }
+}
+
+int launch_sync_count(const uint8_t *es, uint64_t es_total, uint32_t *cnt_raw, uint32_t *cnt_valid, cudaStream_t s)
+{
+    const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
+    LAUNCH(k_sync_scan<false>, chunks, SYNC_THREADS, 0, s, es, es_total, cnt_raw, cnt_valid, nullptr, nullptr, nullptr, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_sync_fill(const uint8_t *es, uint64_t es_total, const uint32_t *base_raw, const uint32_t *base_valid,
+                     uint64_t *raw, uint64_t *valid, cudaStream_t s)
+{
+    const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
+    LAUNCH(k_sync_scan<true>, chunks, SYNC_THREADS, 0, s, es, es_total, nullptr, nullptr, base_raw, base_valid, raw, valid);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------- track setup
+
+__device__ __forceinline__ uint32_t unpack_bps(uint32_t f) { return f == 0 ? 16 : f == 1 ? 20 : f == 2 ? 24 : 0; }
+__device__ __forceinline__ uint32_t unpack_rate(uint32_t f)
+{
+    switch (f) {
+    case 0: return 48000; case 1: return 96000; case 2: return 192000;
+    case 8: return 44100; case 9: return 88200; case 10: return 176400;
+    default: return 0;
+    }
+}
+__device__ __forceinline__ uint32_t channel_count(uint32_t a)
+{
+    const unsigned long long packed =
+        (1ull << 0) | (2ull << 3) | (3ull << 6) | (4ull << 9) | (3ull << 12) | (4ull << 15) | (5ull << 18) |
+        (3ull << 21) | (4ull << 24) | (5ull << 27) | (4ull << 30) | (5ull << 33) | (6ull << 36) | (4ull << 39) |
+        (5ull << 42) | (4ull << 45) | (5ull << 48) | (6ull << 51) | (5ull << 54) | (5ull << 57) | (6ull << 60);
+    return a <= 20 ? (uint32_t)((packed >> (3 * a)) & 7) : 0;
+}
+
+// first packet index i >= from whose prefix count differs from prefix[from], or np
+__device__ uint32_t first_flagged(const uint32_t *prefix, uint32_t np, uint32_t from)
+{
+    if (from >= np) return np;
+    const uint32_t base = prefix[from];
+    // prefix[i + 1] > base  <=>  some flag in [from, i]
+    uint32_t lo = from, hi = np;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (prefix[mid + 1] > base) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// One thread per track.  Everything is a table lookup or a binary search.
+__global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, uint32_t n_tracks)
+{
+    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= n_tracks) return;
+    TrackDev T = tracks[ti];
+    T.status = 1;
+    T.error_flags = 0;
+    T.codec = -1;
+    T.frames = 0;
+    T.nseg = 0; T.ngrp = 0; T.err_seg = 0xFFFFFFFFu;
+    T.pk_lo = T.pk_hi = T.pk_x = T.pcm_pk_end = 0;
+    T.es_start = T.es_end = T.es_cut = 0;
+    T.truncated = 0;
+    do {
+        if (T.first_sector >= a.n_sectors) break;              // aob_reader_seek fails (aob.c:181-199)
+        // a broken packet chain ends the stream for good (packet.c:60-116)
+        uint32_t dead = a.n_sectors;
+        {
+            const uint32_t base = a.bad_prefix[T.first_sector];
+            uint32_t lo = T.first_sector, hi = a.n_sectors;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (a.bad_prefix[mid + 1] > base) hi = mid; else lo = mid + 1;
+            }
+            dead = lo;
+        }
+        T.pk_lo = a.sec_base[T.first_sector];
+        T.pk_hi = dead < a.n_sectors ? a.sec_base[dead + 1] : a.np;
+        if (T.pk_lo >= T.pk_hi) break;                         // no audio packet
+        const uint32_t codec = a.pt.codec[T.pk_lo];
+        uint32_t pk_x = (T.last_sector < a.n_sectors - 1 && T.last_sector + 1 > T.last_sector)
+                            ? a.sec_base[T.last_sector + 1] : a.np;
+
+        if (codec == CODEC_PCM) {
+            // open_pcm_track_reader (dvd-audio.c:952-1014)
+            const uint32_t prm = a.pt.params[T.pk_lo];
+            T.g0_bps = (prm >> 20) & 15; T.g1_bps = (prm >> 16) & 15;
+            T.g0_rate = (prm >> 12) & 15; T.g1_rate = (prm >> 8) & 15;
+            T.assignment = prm & 0xFF;
+            T.bits = unpack_bps(T.g0_bps);
+            T.rate = unpack_rate(T.g0_rate);
+            T.channels = channel_count(T.assignment);
+            if (!T.channels || (T.bits != 16 && T.bits != 24)) break;
+            T.codec = 0;
+            T.pcm_chunk = (T.bits >> 3) * T.channels * 2;
+            // frame budget: lround(pts * rate / 90000)
+            const uint64_t total = (uint64_t)llround((double)T.pts_length * (double)T.rate / 90000.0);
+            T.pcm_frame0 = a.pk_pf[T.pk_lo];
+            // stop in front of the first later packet that is not PCM / differs / is empty
+            uint32_t stop = first_flagged(a.pk_pcm_stop, a.np, T.pk_lo + 1);
+            if (stop > T.pk_hi) stop = T.pk_hi;
+            // ... and behind the packet in which the budget is used up: first i with
+            // frames(pk_lo..i) >= total
+            uint32_t lo = T.pk_lo, hi = stop;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (a.pk_pf[mid + 1] - T.pcm_frame0 >= total) hi = mid; else lo = mid + 1;
+            }
+            T.pcm_pk_end = lo < stop ? lo + 1 : stop;
+            T.truncated = (lo >= stop && stop == a.np);        // budget left, buffer used up
+            T.frames = a.pk_pf[T.pcm_pk_end] - T.pcm_frame0;
+            T.status = 0;
+        } else if (codec == CODEC_MLP) {
+            // open_mlp_track_reader / locate_mlp_parameters (dvd-audio.c:1094-1149, 1318-1365)
+            const uint64_t es_avail = a.pk_es[T.pk_hi];
+            const uint64_t es_lo = a.pk_es[T.pk_lo];
+            const uint32_t ci = lower_bound_dev(a.raw, a.n_raw, es_lo);
+            if (ci >= a.n_raw || a.raw[ci] + 18 > es_avail) break;   // reference asserts
+            const uint64_t p = a.raw[ci];
+            T.es_start = p;
+            const uint32_t b8 = ld_u8(a.es + p + 8), b9 = ld_u8(a.es + p + 9);
+            T.g0_bps = b8 >> 4; T.g1_bps = b8 & 15; T.g0_rate = b9 >> 4; T.g1_rate = b9 & 15;
+            T.assignment = ld_u8(a.es + p + 11) & 31;
+            T.bits = unpack_bps(T.g0_bps);
+            T.rate = unpack_rate(T.g0_rate);
+            T.channels = channel_count(T.assignment);
+            if (!T.channels) break;
+            T.codec = 1;
+            T.status = 0;
+            T.nss = (p + 21 <= es_avail) ? (ld_u8(a.es + p + 20) >> 4) : 0;
+            const uint32_t rc = T.g0_rate & 7;
+            T.au_nominal = 40u << (rc > 2 ? 0 : rc);
+            // the packet holding byte p + 17 is the last one consumed while opening
+            T.pk_open = upper_bound_dev(a.pk_es, a.np + 1, p + 17) - 1;
+            if (pk_x < T.pk_open + 1) pk_x = T.pk_open + 1;
+            // end of the track
+            uint64_t es_end = es_avail;
+            if (pk_x < T.pk_hi) {
+                const uint64_t P0 = a.pk_es[pk_x];
+                if (a.pt.codec[pk_x] != CODEC_MLP) {
+                    es_end = P0;                               // codec mismatch: nothing more
+                } else {
+                    const uint32_t cj = lower_bound_dev(a.raw, a.n_raw, P0);
+                    if (cj < a.n_raw && a.raw[cj] + 8 <= es_avail) es_end = a.raw[cj];
+                    else { es_end = (es_avail >= P0 + 8) ? es_avail - 7 : P0; T.truncated = 1; }
+                }
+            } else {
+                T.truncated = 1;                               // no packet behind last_sector in the buffer
+            }
+            // a non-MLP audio packet met while decoding ends the stream (dvd-audio.c:1203-1208)
+            const uint32_t nm = first_flagged(a.pk_nonmlp, a.np, T.pk_open + 1);
+            if (nm < pk_x && nm < T.pk_hi && a.pk_es[nm] < es_end) es_end = a.pk_es[nm];
+            if (es_end < p) es_end = p;
+            T.es_end = es_end;
+            T.es_cut = es_end;
+            if (T.nss != 1 && T.nss != 2) {
+                // the first access unit is not a usable major sync: nothing decodes
+                T.error_flags |= ERR_SYNTAX;
+                T.es_end = T.es_cut = p;
+            }
+            // restart segments: the start plus every segment-starting sync inside (p, es_end)
+            T.cand_lo = upper_bound_dev(a.valid, a.n_valid, p);
+            const uint32_t cand_hi = lower_bound_dev(a.valid, a.n_valid, T.es_end);
+            T.nseg = T.es_end > p ? 1 + (cand_hi > T.cand_lo ? cand_hi - T.cand_lo : 0) : 0;
+            T.ngrp = (T.nseg + DVDA_LANES - 1) / DVDA_LANES;
+        }
+        T.pk_x = pk_x;
+    } while (0);
+    tracks[ti] = T;
+}
+
+int launch_track_setup(TrackSetupArgs a, TrackDev *tracks, uint32_t n_tracks, cudaStream_t s)
+{
+    LAUNCH(k_track_setup, div_up_u32(n_tracks, 64), 64, 0, s, a, tracks, n_tracks);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------- segments and AUs
+
+// one thread per segment: where it starts and where it must end
+__global__ void k_segment_fill(const TrackDev *__restrict__ tracks, uint32_t n_tracks,
+                               const uint32_t *__restrict__ trk_seg_base, const uint64_t *__restrict__ valid,
+                               SegDev *__restrict__ segs, uint32_t nseg)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg) return;
+    const uint32_t t = upper_bound_dev(trk_seg_base, n_tracks, i) - 1;
+    const TrackDev &T = tracks[t];
+    const uint32_t j = i - trk_seg_base[t];
+    SegDev S;
+    S.es_pos = j == 0 ? T.es_start : valid[T.cand_lo + j - 1];
+    S.es_limit = j + 1 == T.nseg ? T.es_end : valid[T.cand_lo + j];
+    S.track = t;
+    S.n_au = 0; S.au_base = 0; S.flags = 0; S.frames = 0; S.err = 0; S.err_au = 0xFFFFFFFFu; S.pad = 0; S.frame0 = 0;
+    segs[i] = S;
+}
+
+int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_seg_base,
+                        const uint64_t *valid, SegDev *segs, uint32_t nseg, cudaStream_t s)
+{
+    if (!nseg) return 0;
+    LAUNCH(k_segment_fill, div_up_u32(nseg, 128), 128, 0, s, tracks, n_tracks, trk_seg_base, valid, segs, nseg);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// One thread per segment walks the chain of 12-bit access-unit lengths
+// (reference mlp.c:392-394).  Pass 1 counts, pass 2 (fill) records positions.
+__global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ segs, uint32_t nseg,
+                           const TrackDev *__restrict__ tracks, uint32_t *__restrict__ seg_nau,
+                           uint64_t *__restrict__ au_pos, const uint32_t *__restrict__ seg_au_base, int fill)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg) return;
+    SegDev &S = segs[i];
+    if (fill) S.au_base = seg_au_base[i];
+    const uint64_t limit = S.es_limit;
+    uint64_t pos = S.es_pos;
+    uint32_t n = 0;
+    bool stalled = false;
+    while (pos + 4 <= limit) {
+        const uint32_t total = (((ld_u8(es + pos) & 15u) << 8) | ld_u8(es + pos + 1)) * 2;
+        if (total < 4) { stalled = true; break; }              // the reference's queue never advances again
+        if (pos + total > limit) break;                        // incomplete (end of track) or overshoot
+        if (fill) au_pos[S.au_base + n] = pos;
+        pos += total;
+        n++;
+    }
+    if (!fill) {
+        seg_nau[i] = n;
+        S.n_au = n;
+        const TrackDev &T = tracks[S.track];
+        const bool last = (i + 1 - T.seg_base) == T.nseg;
+        // every segment but the last must land exactly on the next one
+        if (stalled || (!last && pos != limit)) S.flags |= SEG_IRREGULAR;
+    }
+}
+
+int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t nseg, const TrackDev *tracks,
+                    uint32_t *seg_nau, uint64_t *au_pos, const uint32_t *seg_au_base, int fill, cudaStream_t s)
+{
+    if (!nseg) return 0;
+    LAUNCH(k_au_chase, div_up_u32(nseg, 128), 128, 0, s, es, segs, nseg, tracks, seg_nau, au_pos, seg_au_base, fill);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- "a packet that completes no access unit ends the stream" ---------------
+// dvda_read() stops at the first decode call that returns no frames
+// (dvd-audio.c:766-775); decode_mlp_audio is called once per packet, so a packet
+// in which no access unit ends terminates the track.  Mark the packets in which
+// some access unit ends, then find the first unmarked one per track.
+
+__global__ void k_yield_mark(MlpTables m, const uint32_t *__restrict__ seg_au_base, uint8_t *__restrict__ pk_yield)
+{
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= m.nau) return;
+    const uint64_t pos = m.au_pos[a];
+    const uint32_t total = (((ld_u8(m.es + pos) & 15u) << 8) | ld_u8(m.es + pos + 1)) * 2;
+    const uint64_t last_byte = pos + total - 1;
+    const uint32_t pk = upper_bound_dev(m.pk_es, m.np + 1, last_byte) - 1;
+    pk_yield[pk] = 1;
+    (void)seg_au_base;
+}
+
+__global__ void k_yield_find(MlpTables m, PacketTable pt, const uint32_t *__restrict__ trk_pk_lo,
+                             const uint8_t *__restrict__ pk_yield)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.np || pk_yield[i] || pt.codec[i] != CODEC_MLP) return;
+    const uint32_t t = upper_bound_dev(trk_pk_lo, m.n_tracks, i);
+    if (t == 0) return;
+    TrackDev &T = m.tracks[t - 1];
+    if (T.status != 0 || T.codec != 1) return;
+    // only packets handed to decode_mlp_audio inside the track's sector range count
+    if (i <= T.pk_open || i >= T.pk_x || i >= T.pk_hi) return;
+    atomicMin((unsigned long long *)&T.es_cut, (unsigned long long)m.pk_es[i]);
+}
+
+int launch_yield(MlpTables m, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
+                 uint8_t *pk_yield, cudaStream_t s)
+{
+    if (!m.np) return 0;
+    CUDA_TRY(cudaMemsetAsync(pk_yield, 0, m.np, s));
+    if (m.nau) LAUNCH(k_yield_mark, div_up_u32(m.nau, 256), 256, 0, s, m, seg_au_base, pk_yield);
+    LAUNCH(k_yield_find, div_up_u32(m.np, 256), 256, 0, s, m, pt, trk_pk_lo, pk_yield);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------ groups
+
+// A group is up to 32 consecutive segments of one track: the 32 lanes of the
+// decoding warp.  Its tile holds `cap` frames per segment.
+__global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tracks,
+                              const uint32_t *__restrict__ trk_grp_base, const SegDev *__restrict__ segs,
+                              GroupDev *__restrict__ groups, uint32_t ngroups, uint32_t *__restrict__ grp_cells,
+                              uint32_t *__restrict__ grp_chunks)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const uint32_t t = upper_bound_dev(trk_grp_base, n_tracks, g) - 1;
+    const TrackDev &T = tracks[t];
+    const uint32_t j = g - trk_grp_base[t];
+    GroupDev G;
+    G.track = t;
+    G.seg0 = T.seg_base + j * DVDA_LANES;
+    G.nseg = min((uint32_t)DVDA_LANES, T.nseg - j * DVDA_LANES);
+    uint32_t cap = 0;
+    for (uint32_t l = 0; l < G.nseg; l++) {
+        const SegDev &S = segs[G.seg0 + l];
+        // second attempt after an overflow: the frame counts are known
+        const uint32_t need = (S.flags & SEG_OVERFLOW) ? S.frames : S.n_au * T.au_nominal;
+        cap = max(cap, need);
+    }
+    G.cap = cap;
+    G.tile_off = 0; G.byp_off = 0;
+    groups[g] = G;
+    grp_cells[g] = cap * T.channels;
+    grp_chunks[g] = (cap + 31) / 32;
+}
+
+__global__ void k_group_offsets(GroupDev *__restrict__ groups, uint32_t ngroups, const uint64_t *__restrict__ cell_base)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    groups[g].tile_off = cell_base[g] * DVDA_LANES;
+    groups[g].byp_off = cell_base[g] * DVDA_LANES;
+}
+
+int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_grp_base, const SegDev *segs,
+                       GroupDev *groups, uint32_t ngroups, uint32_t *grp_cells, uint32_t *grp_chunks, cudaStream_t s)
+{
+    if (!ngroups) return 0;
+    LAUNCH(k_group_setup, div_up_u32(ngroups, 128), 128, 0, s, tracks, n_tracks, trk_grp_base, segs, groups, ngroups, grp_cells, grp_chunks);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_group_offsets(GroupDev *groups, uint32_t ngroups, const uint64_t *cell_base, cudaStream_t s)
+{
+    if (!ngroups) return 0;
+    LAUNCH(k_group_offsets, div_up_u32(ngroups, 128), 128, 0, s, groups, ngroups, cell_base);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,153 @@
+"""GPU parity tests: the CUDA engine against the CPU oracle and the golden
+records of the reference, bit for bit.  Everything goes through the C ABI
+(include/dvdagpu.h) or the public API (include/dvd-audio.h)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import catalog
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "catalog_golden.json")))
+DISCS = sorted(catalog.discs().keys())
+
+
+@pytest.fixture(scope="module")
+def engine(pkg):
+    e = pkg.Engine(0)
+    yield e
+    e.close()
+
+
+def check_track(oracle, eng, res, sectors, g, label):
+    """One decoded track (TrackResult res) against the oracle run on the same sectors."""
+    ref = oracle.decode_track(sectors, g["first"], g["last"], g["pts"])
+    if ref is None:
+        assert res.status != 0, label
+        return
+    assert res.status == 0, label
+    got = eng.fetch(res)
+    assert ("MLP" if res.codec else "PCM") == ref["codec"], label
+    assert (res.channels, res.bits_per_sample, res.sample_rate, res.channel_assignment) == \
+           (ref["channels"], ref["bits_per_sample"], ref["sample_rate"], ref["assignment"]), label
+    assert res.frames == ref["frames"], (label, res.frames, ref["frames"])
+    assert res.error_flags == ref["error_flags"], label
+    if not np.array_equal(got, ref["pcm"]):
+        bad = np.argwhere(got != ref["pcm"])
+        raise AssertionError("%s: %d samples differ, first at frame %d channel %d: got %d want %d" % (
+            label, len(bad), bad[0][0], bad[0][1], got[tuple(bad[0])], ref["pcm"][tuple(bad[0])]))
+
+
+@pytest.mark.parametrize("name", DISCS)
+def test_tracks_one_by_one(pkg, oracle, engine, disc_cache, name):
+    directory, _ = disc_cache(name)
+    sectors = oracle.read_aobs(directory)
+    for g in GOLDEN[name]["tracks"]:
+        res = engine.decode_host(sectors, [(g["first"], g["last"], g["pts"])])
+        check_track(oracle, engine, res[0], sectors, g, "%s %d/%d" % (name, g["title"], g["track"]))
+        # and against the reference's own hash
+        assert res[0].frames == g["frames"]
+        assert oracle.fnv1a(engine.fetch(res[0])) == g["fnv"]
+
+
+@pytest.mark.parametrize("name", DISCS)
+def test_whole_titleset_in_one_call(pkg, oracle, engine, disc_cache, name):
+    """All tracks of the disc as one batch over one sector buffer (the multi-track path)."""
+    directory, _ = disc_cache(name)
+    sectors = oracle.read_aobs(directory)
+    golden = GOLDEN[name]["tracks"]
+    res = engine.decode_host(sectors, [(g["first"], g["last"], g["pts"]) for g in golden])
+    for r, g in zip(res, golden):
+        assert r.status == 0
+        assert r.frames == g["frames"], (name, g["title"], g["track"])
+        assert oracle.fnv1a(engine.fetch(r)) == g["fnv"], (name, g["title"], g["track"])
+
+
+@pytest.mark.parametrize("name", ["c5_mixed", "mlp_wild_1", "pcm_rates_ragged", "mlp_zero_yield"])
+def test_public_api(pkg, oracle, disc_cache, name):
+    """dvda_open .. dvda_open_track_reader .. dvda_read, as a program written for the
+    reference would call it (odd read sizes included)."""
+    directory, _ = disc_cache(name)
+    d = pkg.Disc(directory)
+    for g in GOLDEN[name]["tracks"]:
+        info, pcm = d.read_track(g["title"], g["track"], chunk=4096 if g["track"] % 2 else 1013)
+        assert (info["codec"], info["channels"], info["bits_per_sample"], info["sample_rate"], info["mask"]) == \
+               (g["codec"], g["ch"], g["bps"], g["rate"], g["mask"])
+        assert len(pcm) == g["frames"]
+        assert oracle.fnv1a(pcm) == g["fnv"]
+    d.close()
+
+
+def test_drop_in_dumper(pkg, oracle, disc_cache, tmp_path):
+    """The api_dump program, linked against OUR library, prints what it prints when
+    linked against the reference (golden records)."""
+    directory, _ = disc_cache("c5_mixed")
+    rc, tracks, _samples, err = oracle.run_dump(pkg.DUMP_BIN, directory, str(tmp_path / "out.raw"))
+    assert rc == 0, err
+    assert tracks == GOLDEN["c5_mixed"]["tracks"]
+
+
+@pytest.mark.parametrize("name,offset", [("c2_mlp_2ch96", 20 * 2048 + 1000), ("c3_mlp_6ch96", 31 * 2048 + 700),
+                                         ("c3_mlp_6ch96", 40 * 2048 + 1500)])
+def test_damage_is_caught_like_the_oracle(pkg, oracle, engine, disc_cache, name, offset):
+    directory, _ = disc_cache(name)
+    g = GOLDEN[name]["tracks"][0]
+    sectors = oracle.read_aobs(directory).copy()
+    sectors[offset] ^= 0x04
+    res = engine.decode_host(sectors, [(g["first"], g["last"], g["pts"])])
+    ref = oracle.decode_track(sectors, g["first"], g["last"], g["pts"])
+    assert ref["error_flags"] & (oracle.ERR_PARITY | oracle.ERR_CRC)
+    check_track(oracle, engine, res[0], sectors, g, name + " damaged")
+
+
+def test_truncated_window_is_reported(pkg, oracle, engine, disc_cache):
+    directory, _ = disc_cache("c2_mlp_2ch96")
+    g = GOLDEN["c2_mlp_2ch96"]["tracks"][0]
+    sectors = oracle.read_aobs(directory)
+    part = sectors[: 30 * 2048]
+    res = engine.decode_host(part, [(0, g["last"], g["pts"])])
+    assert res[0].status == 0 and res[0].truncated == 1
+    ref = oracle.decode_track(part, 0, g["last"], g["pts"])
+    assert res[0].frames == ref["frames"]
+    assert np.array_equal(engine.fetch(res[0]), ref["pcm"])
+
+
+def test_open_failures(pkg, oracle, engine):
+    junk = np.zeros(8 * 2048, np.uint8)
+    res = engine.decode_host(junk, [(0, 7, 1000), (100, 200, 1000)])
+    assert res[0].status != 0 and res[1].status != 0
+
+
+@pytest.mark.parametrize("name", sorted(catalog.GPU_LARGE.keys()))
+def test_large(pkg, oracle, engine, disc_cache, name):
+    directory, _ = disc_cache(name)
+    sectors = oracle.read_aobs(directory)
+    golden = GOLDEN[name]["tracks"]
+    res = engine.decode_host(sectors, [(g["first"], g["last"], g["pts"]) for g in golden])
+    for r, g in zip(res, golden):
+        check_track(oracle, engine, r, sectors, g, name)
+        assert r.frames == g["frames"]
+
+
+def test_device_resident_input(pkg, oracle, engine, disc_cache):
+    """Sectors already in HBM (a torch tensor), engine on torch's stream."""
+    import torch
+    directory, _ = disc_cache("c2_large")
+    g = GOLDEN["c2_large"]["tracks"][0]
+    sectors = oracle.read_aobs(directory)
+    dev = torch.from_numpy(sectors).cuda()
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        res = engine.decode_device(dev.data_ptr(), len(sectors) // 2048, [(g["first"], g["last"], g["pts"])])
+        assert res[0].frames == g["frames"]
+        ptr, n = engine.pcm_device()
+        assert n == g["frames"] * g["ch"]
+        assert oracle.fnv1a(engine.fetch(res[0])) == g["fnv"]
+        st = engine.stats()
+        assert st["launches"] > 10 and st["samples"] == n
+    finally:
+        engine.set_stream(0)
