@@ -355,6 +355,14 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         nseg += ht[i].nseg; ngroups += ht[i].ngrp;
     }
     h_seg_base[n_tracks] = nseg; h_grp_base[n_tracks] = ngroups;
+    // channel counts per substream present in this batch: picks the decode kernel instantiations
+    uint32_t nch_mask = 0;
+    for (uint32_t i = 0; i < n_tracks; i++) {
+        if (!ht[i].nseg) continue;
+        const uint32_t a = ht[i].nss == 1 ? ht[i].channels : 2, b = ht[i].nss == 1 ? a : ht[i].channels - 2;
+        nch_mask |= 1u << (a <= 4 ? a : 0);
+        nch_mask |= 1u << (b <= 4 ? b : 0);
+    }
     uint32_t *trk_pk_lo = c->buf[B_TRK_PK_LO].as<uint32_t>(), *trk_seg_base = c->buf[B_TRK_SEG_BASE].as<uint32_t>();
     uint32_t *trk_grp_base = c->buf[B_TRK_GRP_BASE].as<uint32_t>();
     CUDA_TRY(cudaMemcpyAsync(d_tracks, ht.data(), n_tracks * sizeof(TrackDev), cudaMemcpyHostToDevice, s));
@@ -420,7 +428,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             m.tiles = c->buf[B_TILES].as<int32_t>(); m.bypass = c->buf[B_BYPASS].as<uint8_t>();
             TRY(launch_group_offsets(m.groups, ngroups, cell_base, s));
             CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
-            TIMED(DVDAGPU_K_MLP_DECODE, launch_mlp_decode(m, s));
+            TIMED(DVDAGPU_K_MLP_DECODE, launch_mlp_decode(m, nch_mask, s));
             CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
             TIMED(DVDAGPU_K_CARRY_FIX, launch_carry_fix(m, s));
             TRY(launch_seg_finalize(m, seg_frames, d_status, s));

@@ -123,56 +123,161 @@ int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
 // ------------------------------------------------------------- bit reader
 
 // MSB-first reader over the elementary stream (reference src/bitstream.c:1077-1111).
-// `pos` counts bits from word `wbase`, so 32 bits suffice inside one access unit.
-struct BitReader {
-    const uint32_t *words;
-    uint64_t wbase;
-    uint32_t pos;
-    uint32_t cw;           // word offset of the cached pair, 0xFFFFFFFE = none
-    uint32_t hi, lo;
+//
+// Every lane walks its own stream, so plain loads would miss in a different
+// cache line per lane and — worse — any per-lane "refill when low" branch
+// diverges: an event that is rare for one lane happens almost every step for
+// some lane of the warp.  So:
+//   * each lane owns a 512-byte ring in shared memory (eight 64-byte chunks),
+//     layout [16-byte slot][lane];
+//   * it fills the ring itself with cp.async (16 bytes per copy, L2 -> shared),
+//     at warp-uniform points (top of every 8-frame iteration): up to two chunks,
+//     always two commit groups, then wait_group 2 — everything issued in earlier
+//     iterations has landed, nothing ever waits on DRAM in steady state;
+//   * the hot loop tops the 64-bit window up without branching (the load from
+//     the ring is unconditional, the merge is predicated).
+// Headers use the same reader through the checked (cold) entry points.
+#define RING_SLOTS 32                 // 16-byte slots per lane: 512 bytes
+#define CHUNK_WORDS 16                // 64 bytes per cp.async group
+#define RING_WORDS (RING_SLOTS * 4)
+
+struct Rd {
+    const uint8_t *es;      // elementary stream (global)
+    uint32_t ring;          // shared-memory address of this lane's slot 0
+    uint64_t win;           // upcoming bits, MSB aligned
+    int32_t avail;          // valid bits in win
+    uint32_t next_w;        // absolute word index of the next word to pull
+    uint32_t fill_c;        // chunks [.., fill_c) have been issued
+    uint32_t safe_w;        // words [.., safe_w) are known to have landed
+    uint32_t base_w;        // word index the bit counter is relative to
 };
 
-__device__ __forceinline__ void br_open(BitReader &b, const uint8_t *es, uint64_t byte_pos)
+__device__ __forceinline__ void cp_async16(uint32_t smem, const void *g)
 {
-    b.words = reinterpret_cast<const uint32_t *>(es);
-    b.wbase = byte_pos >> 2;
-    b.pos = (uint32_t)(byte_pos & 3) * 8;
-    b.cw = 0xFFFFFFFEu;                        // neither w nor w - 1 for any real word offset
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void rd_issue_chunk(Rd &r, uint32_t c)
+{
+    const uint8_t *g = r.es + (uint64_t)c * (CHUNK_WORDS * 4);
+#pragma unroll
+    for (int t = 0; t < 4; t++) cp_async16(r.ring + (((c * 4 + t) & (RING_SLOTS - 1)) << 9), g + t * 16);
+}
+// may chunk fill_c be written?  Its slot held chunk fill_c - 8, which must lie
+// entirely behind the read position.
+__device__ __forceinline__ bool rd_room(const Rd &r) { return (int32_t)((r.fill_c - 7) * CHUNK_WORDS - r.next_w) <= 0; }
+
+__device__ __forceinline__ void rd_init(Rd &r, const uint8_t *es, uint32_t ring)
+{
+    r.es = es; r.ring = ring; r.win = 0; r.avail = 0; r.next_w = 0; r.fill_c = 0; r.safe_w = 0; r.base_w = 0;
+}
+
+// warp-uniform prefetch point: keep the ring ~5 chunks ahead of the reader
+__device__ __forceinline__ void rd_prefetch(Rd &r)
+{
+    const uint32_t landed = r.fill_c * CHUNK_WORDS;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        if (r.fill_c * CHUNK_WORDS < r.next_w + 96 && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
+        cp_commit();
+    }
+    cp_wait<2>();
+    r.safe_w = landed;
+}
+
+// cold: the word at next_w is not known to be in the ring
+__device__ __noinline__ void rd_slow_fill(Rd &r)
+{
+    while (r.fill_c * CHUNK_WORDS < r.next_w + 64 && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
+    cp_commit();
+    cp_wait<0>();
+    r.safe_w = r.fill_c * CHUNK_WORDS;
+}
+
+// position the reader at an absolute byte offset
+__device__ __forceinline__ void rd_seat(Rd &r, uint64_t byte_pos)
+{
+    const uint32_t w = (uint32_t)(byte_pos >> 2);
+    if (w >= r.fill_c * CHUNK_WORDS || w + RING_WORDS - CHUNK_WORDS < r.fill_c * CHUNK_WORDS) {
+        cp_wait<0>();                       // nothing may still be landing in slots we reuse
+        r.fill_c = w / CHUNK_WORDS;
+        r.safe_w = r.fill_c * CHUNK_WORDS;
+    }
+    r.next_w = w;
+    r.base_w = w;
+    r.win = 0;
+    r.avail = 0;
+}
+
+__device__ __forceinline__ uint32_t rd_ring_word(const Rd &r, uint32_t w)
+{
+    uint32_t word;
+    const uint32_t addr = r.ring + (((w >> 2) & (RING_SLOTS - 1)) << 9) + ((w & 3) << 2);
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr) : "memory");
+    return __byte_perm(word, 0, 0x0123);
+}
+
+// checked pull (headers, generic path): avail must be <= 32
+__device__ __forceinline__ void rd_pull(Rd &r)
+{
+    if (r.next_w >= r.safe_w) rd_slow_fill(r);
+    const uint32_t word = rd_ring_word(r, r.next_w);
+    r.win |= (uint64_t)word << (32 - r.avail);
+    r.avail += 32;
+    r.next_w++;
+}
+
+// hot pull: no branch; afterwards avail > 32.  The caller guarantees (through
+// rd_prefetch) that the next words have landed.
+__device__ __forceinline__ void rd_top_up(Rd &r)
+{
+    const uint32_t word = rd_ring_word(r, r.next_w);
+    const bool need = r.avail <= 32;
+    const uint64_t add = (uint64_t)word << ((32 - r.avail) & 63);
+    r.win |= need ? add : 0ull;
+    r.avail += need ? 32 : 0;
+    r.next_w += need ? 1u : 0u;
 }
 
 // next n bits (1..32) without consuming them
-__device__ __forceinline__ uint32_t br_peek(BitReader &b, uint32_t n)
+__device__ __forceinline__ uint32_t rd_peek(Rd &r, uint32_t n)
 {
-    const uint32_t w = b.pos >> 5;
-    if (w != b.cw) {
-        b.hi = (w == b.cw + 1) ? b.lo : ld_be32_aligned(b.words + b.wbase + w);
-        b.lo = ld_be32_aligned(b.words + b.wbase + w + 1);
-        b.cw = w;
-    }
-    return __funnelshift_l(b.lo, b.hi, b.pos & 31) >> (32 - n);
+    if (r.avail < (int32_t)n) rd_pull(r);
+    return (uint32_t)(r.win >> (64 - n));
 }
-__device__ __forceinline__ uint32_t br_get(BitReader &b, uint32_t n)
+__device__ __forceinline__ void rd_drop(Rd &r, uint32_t n) { r.win <<= n; r.avail -= n; }
+__device__ __forceinline__ uint32_t rd_get(Rd &r, uint32_t n)
 {
     if (!n) return 0;
-    const uint32_t v = br_peek(b, n);
-    b.pos += n;
+    const uint32_t v = rd_peek(r, n);
+    rd_drop(r, n);
     return v;
 }
 // two's complement, n in 1..32 (src/bitstream.c:1198-1206)
-__device__ __forceinline__ int32_t br_get_s(BitReader &b, uint32_t n)
+__device__ __forceinline__ int32_t rd_get_s(Rd &r, uint32_t n)
 {
-    const uint32_t v = br_get(b, n);
+    const uint32_t v = rd_get(r, n);
     return (int32_t)(v << (32 - n)) >> (32 - n);
 }
+__device__ __forceinline__ void rd_skip(Rd &r, uint32_t n)
+{
+    while (n > 32) { rd_get(r, 32); n -= 32; }
+    rd_get(r, n);
+}
+// bits consumed since rd_seat (counted from the seated word's first bit)
+__device__ __forceinline__ uint32_t rd_pos(const Rd &r) { return (r.next_w - r.base_w) * 32 - r.avail; }
 
 // ------------------------------------------------------------ decoder state
 
 struct ChanState {
     int32_t fir_c[8], iir_c[8];
-    int32_t fst[8], ist[8];          // circular histories
+    int32_t fst[8], ist[8];          // circular histories (generic path; IIR state as transmitted)
     uint8_t fir_order, iir_order, fir_shift, iir_shift;
     uint8_t fhead, ihead;            // next write slot
     uint8_t flen, ilen;              // valid entries (<= 8)
+    uint8_t ist_new;                 // IIR history was replaced by a parameter block
     int32_t huff_offset;
     uint8_t codebook, huff_lsbs;
 };
@@ -189,12 +294,13 @@ struct SubState {
     ChanState ch[DVDA_MAX_CH];
 };
 
-// Huffman LUT: 9 peeked bits -> value | length << 8; 0xFFFF = invalid code.
+// Huffman LUT [codebook 0..3][9 peeked bits] -> value | length << 8; 0xFFFF = invalid code.
 // Built from the prefix structure of the three codebooks
 // (src/mlp_codebook{1,2,3}.json): 0^z 1 -> 8 - z; 1 + literal -> 7 + literal;
 // 01 0^k 1 -> hi_base + k.
 __device__ uint16_t huff_entry(uint32_t cb, uint32_t v9)
 {
+    if (cb == 0) return 0;                               // codebook 0: no code, MSB = 0
     const uint32_t lit = 3 - cb;                       // literal bits behind a leading 1
     if (v9 & 0x100) return (uint16_t)((7 + ((v9 >> (8 - lit)) & ((1u << lit) - 1))) | ((1 + lit) << 8));
     if (v9 & 0x080) {
@@ -217,154 +323,193 @@ struct DecodeJob {
 
 // ---- parameter parsing (cold path) ------------------------------------------
 
-__device__ bool restart_header(BitReader &b, SubState &s)
+__device__ bool restart_header(Rd &b, SubState &s)
 {
-    const uint32_t sync = br_get(b, 13), noise_type = br_get(b, 1);
-    b.pos += 16;
-    s.min_ch = br_get(b, 4); s.max_ch = br_get(b, 4); s.mmc = br_get(b, 4);
-    s.noise_shift = br_get(b, 4);
-    s.seed = br_get(b, 23);
-    b.pos += 19 + 1 + 8 + 16;
+    const uint32_t sync = rd_get(b, 13), noise_type = rd_get(b, 1);
+    rd_skip(b, 16);
+    s.min_ch = rd_get(b, 4); s.max_ch = rd_get(b, 4); s.mmc = rd_get(b, 4);
+    s.noise_shift = rd_get(b, 4);
+    s.seed = rd_get(b, 23);
+    rd_skip(b, 19 + 1 + 8 + 16);
     if (sync != 0x18F5 || noise_type != 0) return false;
     if (s.max_ch < s.min_ch || s.mmc < s.max_ch || s.mmc >= DVDA_MAX_CH) return false;
-    for (uint32_t c = 0; c <= s.mmc; c++) if (br_get(b, 6) > s.mmc) return false;
-    b.pos += 8;
+    for (uint32_t c = 0; c <= s.mmc; c++) if (rd_get(b, 6) > s.mmc) return false;
+    rd_skip(b, 8);
     s.have_header = 1;
     s.dirty = 1;
     return true;
 }
 
-__device__ bool filter_params(BitReader &b, ChanState &C, bool iir)
+__device__ bool filter_params(Rd &b, ChanState &C, bool iir)
 {
-    const uint32_t order = br_get(b, 4);
+    const uint32_t order = rd_get(b, 4);
     if (order > 8) return false;
     if (!order) {
-        if (iir) { C.iir_order = 0; C.iir_shift = 0; C.ilen = 0; C.ihead = 0; }
+        if (iir) { C.iir_order = 0; C.iir_shift = 0; C.ilen = 0; C.ihead = 0; C.ist_new = 1; }
         else { C.fir_order = 0; C.fir_shift = 0; }
         return true;
     }
-    const uint32_t shift = br_get(b, 4), bits = br_get(b, 5);
+    const uint32_t shift = rd_get(b, 4), bits = rd_get(b, 5);
     if (bits < 1 || bits > 16) return false;
-    const uint32_t cshift = br_get(b, 3);
+    const uint32_t cshift = rd_get(b, 3);
     if (bits + cshift > 16) return false;
     int32_t *coef = iir ? C.iir_c : C.fir_c;
-    for (uint32_t i = 0; i < order; i++) coef[i] = (int32_t)((uint32_t)br_get_s(b, bits) << cshift);
+    for (uint32_t i = 0; i < order; i++) coef[i] = (int32_t)((uint32_t)rd_get_s(b, bits) << cshift);
     if (!iir) {
         C.fir_order = order; C.fir_shift = shift;
-        if (br_get(b, 1)) return false;
+        if (rd_get(b, 1)) return false;
     } else {
         C.iir_order = order; C.iir_shift = shift;
-        C.ilen = 0; C.ihead = 0;
-        if (br_get(b, 1)) {
-            const uint32_t sbits = br_get(b, 4), sshift = br_get(b, 4);
+        C.ilen = 0; C.ihead = 0; C.ist_new = 1;
+        if (rd_get(b, 1)) {
+            const uint32_t sbits = rd_get(b, 4), sshift = rd_get(b, 4);
             if (!sbits) return false;                           // reference underflows (G2)
             // first value sent pairs with coeff[0] = most recent (mlp.c:1103-1107):
             // store so that reading backwards from ihead yields sent[0], sent[1], ...
             for (uint32_t i = 0; i < order; i++)
-                C.ist[(order - 1 - i) & 7] = (int32_t)((uint32_t)br_get_s(b, sbits) << sshift);
+                C.ist[(order - 1 - i) & 7] = (int32_t)((uint32_t)rd_get_s(b, sbits) << sshift);
             C.ilen = order; C.ihead = order & 7;
         }
     }
     return true;
 }
 
-__device__ bool decoding_params(BitReader &b, SubState &s, bool restart)
+__device__ bool decoding_params(Rd &b, SubState &s, bool restart)
 {
     if (restart) {
-        if (br_get(b, 1)) { uint32_t f = 0; for (int k = 0; k < 8; k++) f |= br_get(b, 1) << k; s.flags = f; }
+        if (rd_get(b, 1)) { uint32_t f = 0; for (int k = 0; k < 8; k++) f |= rd_get(b, 1) << k; s.flags = f; }
         else s.flags = 0xFF;
-    } else if ((s.flags & 1) && br_get(b, 1)) {
-        uint32_t f = 0; for (int k = 0; k < 8; k++) f |= br_get(b, 1) << k; s.flags = f;
+    } else if ((s.flags & 1) && rd_get(b, 1)) {
+        uint32_t f = 0; for (int k = 0; k < 8; k++) f |= rd_get(b, 1) << k; s.flags = f;
     }
-    if ((s.flags & 0x80) && br_get(b, 1)) {
-        s.block_size = br_get(b, 9);
+    if ((s.flags & 0x80) && rd_get(b, 1)) {
+        s.block_size = rd_get(b, 9);
         if (s.block_size < 8) return false;
     } else if (restart) s.block_size = 8;
 
-    if ((s.flags & 0x40) && br_get(b, 1)) {
+    if ((s.flags & 0x40) && rd_get(b, 1)) {
         s.dirty = 1;
-        s.matrix_len = br_get(b, 4);
+        s.matrix_len = rd_get(b, 4);
         if (s.matrix_len > DVDA_MAX_MAT || s.mmc + 3 > DVDA_MAX_CH) return false;
         for (uint32_t m = 0; m < s.matrix_len; m++) {
-            if ((s.mat_out[m] = br_get(b, 4)) > s.mmc) return false;
-            const uint32_t frac = br_get(b, 4);
+            if ((s.mat_out[m] = rd_get(b, 4)) > s.mmc) return false;
+            const uint32_t frac = rd_get(b, 4);
             if (frac > 14) return false;
-            s.mat_bypass[m] = br_get(b, 1);
+            s.mat_bypass[m] = rd_get(b, 1);
             for (uint32_t c = 0; c < DVDA_MAX_CH; c++) s.coeff[m][c] = 0;
             for (uint32_t c = 0; c < (uint32_t)s.mmc + 3; c++)
-                if (br_get(b, 1)) s.coeff[m][c] = (int16_t)((uint32_t)br_get_s(b, frac + 2) << (14 - frac));
+                if (rd_get(b, 1)) s.coeff[m][c] = (int16_t)((uint32_t)rd_get_s(b, frac + 2) << (14 - frac));
         }
     } else if (restart) { s.matrix_len = 0; s.dirty = 1; }
 
-    if ((s.flags & 0x20) && br_get(b, 1)) {
+    if ((s.flags & 0x20) && rd_get(b, 1)) {
         s.dirty = 1;
-        for (uint32_t c = 0; c <= s.mmc; c++) s.out_shift[c] = (uint8_t)(br_get_s(b, 4) & 31);
+        for (uint32_t c = 0; c <= s.mmc; c++) s.out_shift[c] = (uint8_t)(rd_get_s(b, 4) & 31);
     } else if (restart) { for (int c = 0; c < DVDA_MAX_CH; c++) s.out_shift[c] = 0; s.dirty = 1; }
 
-    if ((s.flags & 0x10) && br_get(b, 1)) {
+    if ((s.flags & 0x10) && rd_get(b, 1)) {
         s.dirty = 1;
-        for (uint32_t c = 0; c <= s.max_ch; c++) s.q[c] = br_get(b, 4);
+        for (uint32_t c = 0; c <= s.max_ch; c++) s.q[c] = rd_get(b, 4);
     } else if (restart) { for (int c = 0; c < DVDA_MAX_CH; c++) s.q[c] = 0; s.dirty = 1; }
 
     for (uint32_t c = s.min_ch; c <= s.max_ch; c++) {
         ChanState &C = s.ch[c];
-        if (br_get(b, 1)) {
-            if ((s.flags & 0x08) && br_get(b, 1)) { if (!filter_params(b, C, false)) return false; }
+        if (rd_get(b, 1)) {
+            if ((s.flags & 0x08) && rd_get(b, 1)) { if (!filter_params(b, C, false)) return false; }
             else if (restart) { C.fir_order = 0; C.fir_shift = 0; }
-            if ((s.flags & 0x04) && br_get(b, 1)) { if (!filter_params(b, C, true)) return false; }
-            else if (restart) { C.iir_order = 0; C.iir_shift = 0; C.ilen = 0; C.ihead = 0; }
-            if ((s.flags & 0x02) && br_get(b, 1)) C.huff_offset = br_get_s(b, 15);
+            if ((s.flags & 0x04) && rd_get(b, 1)) { if (!filter_params(b, C, true)) return false; }
+            else if (restart) { C.iir_order = 0; C.iir_shift = 0; C.ilen = 0; C.ihead = 0; C.ist_new = 1; }
+            if ((s.flags & 0x02) && rd_get(b, 1)) C.huff_offset = rd_get_s(b, 15);
             else if (restart) C.huff_offset = 0;
-            C.codebook = br_get(b, 2);
-            C.huff_lsbs = br_get(b, 5);
+            C.codebook = rd_get(b, 2);
+            C.huff_lsbs = rd_get(b, 5);
             if (C.huff_lsbs > 24) return false;
         } else if (restart) {
             C.fir_order = 0; C.fir_shift = 0;
-            C.iir_order = 0; C.iir_shift = 0; C.ilen = 0; C.ihead = 0;
+            C.iir_order = 0; C.iir_shift = 0; C.ilen = 0; C.ihead = 0; C.ist_new = 1;
             C.huff_offset = 0; C.codebook = 0; C.huff_lsbs = 24;
         }
     }
     return true;
 }
 
-// ---- one block: entropy decode + prediction filters (hot path) --------------
+// block header: optional restart header + decoding parameters (mlp.c:749-771)
+__device__ __forceinline__ bool block_header(Rd &b, SubState &s, bool &changed)
+{
+    changed = false;
+    if (rd_get(b, 1)) {
+        const bool restart = rd_get(b, 1);
+        if (restart && !restart_header(b, s)) return false;
+        if (!s.have_header) return false;
+        if (!decoding_params(b, s, restart)) return false;
+        changed = true;
+    }
+    return s.have_header;
+}
+
+// per-channel constants of one block (mlp.c:1151-1176, 1260-1270); false = syntax error
+__device__ __forceinline__ bool channel_setup(const SubState &s, const ChanState &C, uint32_t q, bool exact_history,
+                                              uint32_t &flags, uint32_t &lsb_bits, int32_t &sho, uint32_t &shift)
+{
+    if (C.huff_lsbs < q) return false;
+    const uint32_t nb = C.huff_lsbs - q;
+    lsb_bits = nb;
+    if (C.codebook) {
+        const int ss = (int)nb + 2 - (int)C.codebook;
+        sho = C.huff_offset - 7 * (1 << nb) - (ss >= 0 ? (1 << ss) : 0);
+    } else {
+        sho = C.huff_offset - (nb >= 1 ? (1 << (nb - 1)) : 0);
+    }
+    if (C.fir_order + C.iir_order > 8) return false;
+    if (C.fir_shift > 0 && C.iir_shift > 0 && C.fir_shift != C.iir_shift) return false;
+    shift = (C.fir_shift > 0 && C.iir_shift > 0) ? C.fir_shift : C.fir_order > 0 ? C.fir_shift : C.iir_shift;
+    if (C.iir_order > C.ilen) return false;                     // reference reads out of bounds (G2)
+    if (C.fir_order > C.flen) {
+        if (exact_history) return false;                        // reference reads out of bounds (G1)
+        flags |= SEG_NEEDS_CARRY;                               // history lives in the previous segment
+    }
+    (void)s;
+    return true;
+}
+
+// LSB-bypass bits of one frame: one bit per matrix that has the flag, in matrix order
+__device__ __forceinline__ uint32_t bypass_bits(Rd &b, uint32_t want_mask)
+{
+    uint32_t out = 0;
+    if (want_mask) {
+        uint32_t t = __popc(want_mask);
+        const uint32_t bits = rd_get(b, t);
+        uint32_t m = want_mask;
+        while (m) {
+            const uint32_t k = __ffs(m) - 1;
+            m &= m - 1;
+            t--;
+            out |= ((bits >> t) & 1u) << k;
+        }
+    }
+    return out;
+}
+
+// ---- one block, generic: any channel count, histories in local memory --------
 
 // returns frames decoded, 0 on a syntax error
-__device__ uint32_t decode_block(const MlpTables &m, const GroupDev &G, const DecodeJob &job,
-                                 SubState &s, BitReader &b, uint32_t end_bits, uint32_t frame0,
-                                 uint32_t nch, bool governing, const uint16_t (*lut)[512], uint32_t &flags)
+__device__ uint32_t decode_block_generic(const MlpTables &m, const GroupDev &G, const DecodeJob &job,
+                                         SubState &s, Rd &b, uint32_t end_bits, uint32_t frame0,
+                                         uint32_t nch, bool governing, const uint16_t (*lut)[512], uint32_t &flags)
 {
-    if (br_get(b, 1)) {
-        const bool restart = br_get(b, 1);
-        if (restart && !restart_header(b, s)) return 0;
-        if (!s.have_header) return 0;
-        if (!decoding_params(b, s, restart)) return 0;
-    }
-    if (!s.have_header || b.pos > end_bits) return 0;
+    bool changed;
+    if (!block_header(b, s, changed)) return 0;
+    if (rd_pos(b) > end_bits) return 0;
 
     const uint32_t n = s.block_size;
     int32_t sho[DVDA_MAX_CH];
     uint32_t lsb_bits[DVDA_MAX_CH], shift[DVDA_MAX_CH];
     for (uint32_t c = s.min_ch; c <= s.max_ch; c++) {
-        const ChanState &C = s.ch[c];
-        if (C.huff_lsbs < s.q[c]) return 0;
-        const uint32_t nb = C.huff_lsbs - s.q[c];
-        lsb_bits[c] = nb;
-        if (C.codebook) {
-            const int ss = (int)nb + 2 - (int)C.codebook;
-            sho[c] = C.huff_offset - 7 * (1 << nb) - (ss >= 0 ? (1 << ss) : 0);
-        } else {
-            sho[c] = C.huff_offset - (nb >= 1 ? (1 << (nb - 1)) : 0);
-        }
-        if (C.fir_order + C.iir_order > 8) return 0;
-        if (C.fir_shift > 0 && C.iir_shift > 0 && C.fir_shift != C.iir_shift) return 0;
-        shift[c] = (C.fir_shift > 0 && C.iir_shift > 0) ? C.fir_shift : C.fir_order > 0 ? C.fir_shift : C.iir_shift;
-        if (C.iir_order > C.ilen) return 0;                     // reference reads out of bounds (G2)
-        if (C.fir_order > C.flen) {
-            if (job.exact_history) return 0;                    // reference reads out of bounds (G1)
-            flags |= SEG_NEEDS_CARRY;                           // history lives in the previous segment
-        }
+        if (!channel_setup(s, s.ch[c], s.q[c], job.exact_history, flags, lsb_bits[c], sho[c], shift[c])) return 0;
+        s.ch[c].ist_new = 0;
     }
+    uint32_t want = 0;
+    for (uint32_t k = 0; k < s.matrix_len; k++) want |= (uint32_t)(s.mat_bypass[k] != 0) << k;
 
     int32_t *tile = m.tiles + G.tile_off + job.lane;
     uint8_t *byp = m.bypass + G.byp_off + job.lane;
@@ -372,22 +517,19 @@ __device__ uint32_t decode_block(const MlpTables &m, const GroupDev &G, const De
         const uint32_t f = frame0 + i;
         const bool room = f < G.cap;
         if (!room) flags |= SEG_OVERFLOW;
-        uint32_t bmask = 0;
-        for (uint32_t k = 0; k < s.matrix_len; k++)
-            if (s.mat_bypass[k]) bmask |= br_get(b, 1) << k;
+        const uint32_t bmask = bypass_bits(b, want);
         if (governing && room) byp[(uint64_t)f * DVDA_LANES] = (uint8_t)bmask;
         for (uint32_t c = s.min_ch; c <= s.max_ch; c++) {
             ChanState &C = s.ch[c];
             int32_t msb = 0;
             if (C.codebook) {
-                const uint32_t e = lut[C.codebook - 1][br_peek(b, 9)];
+                const uint32_t e = lut[C.codebook][rd_peek(b, 9)];
                 if (e == 0xFFFF) return 0;
                 msb = e & 0xFF;
-                b.pos += e >> 8;
+                rd_drop(b, e >> 8);
             }
-            const int32_t lsb = (int32_t)br_get(b, lsb_bits[c]);
+            const int32_t lsb = (int32_t)rd_get(b, lsb_bits[c]);
             const int32_t res = (int32_t)((uint32_t)((msb << lsb_bits[c]) + lsb + sho[c]) << s.q[c]);
-            // prediction: FIR over previous outputs, IIR over previous residual-ish state
             long long sum = 0;
             for (uint32_t j = 0; j < C.fir_order; j++) sum += (long long)C.fir_c[j] * C.fst[(C.fhead - 1 - j) & 7];
             for (uint32_t j = 0; j < C.iir_order; j++) sum += (long long)C.iir_c[j] * C.ist[(C.ihead - 1 - j) & 7];
@@ -399,8 +541,135 @@ __device__ uint32_t decode_block(const MlpTables &m, const GroupDev &G, const De
             C.ist[C.ihead] = (int32_t)((uint32_t)v - (uint32_t)ssum); C.ihead = (C.ihead + 1) & 7; if (C.ilen < 8) C.ilen++;
             if (room) tile[((uint64_t)f * nch + c) * DVDA_LANES] = v;
         }
-        if (b.pos > end_bits) return 0;
+        if (rd_pos(b) > end_bits) return 0;
     }
+    return n;
+}
+
+// ---- one block, fast: NCH channels, filter state in registers ----------------
+//
+// Histories are kept as 8 registers per channel and filter.  The frame loop is
+// unrolled by 8 so that "age a at frame j" is register (a - j) mod 8 with both
+// indices known at compile time: no register moves, no local memory.  Taps
+// beyond the transmitted orders carry zero coefficients, so every lane runs the
+// same 16 multiply-adds whatever its filter orders are (no divergence).
+
+template <int NCH>
+struct Hot {
+    int32_t fh[NCH][8], ih[NCH][8];      // histories, [0] = most recent at chunk boundaries
+    int32_t cf[NCH][8], ci[NCH][8];      // coefficients, zero beyond the order
+};
+
+template <int NCH>
+__device__ __forceinline__ void hot_load_params(Hot<NCH> &H, SubState &s)
+{
+#pragma unroll
+    for (int cc = 0; cc < NCH; cc++) {
+        ChanState &C = s.ch[s.min_ch + cc];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            H.cf[cc][j] = j < C.fir_order ? C.fir_c[j] : 0;
+            H.ci[cc][j] = j < C.iir_order ? C.iir_c[j] : 0;
+        }
+        if (C.ist_new) {
+            // IIR history replaced by the transmitted state (or emptied)
+#pragma unroll
+            for (int a = 0; a < 8; a++) H.ih[cc][a] = a < C.ilen ? C.ist[(C.ihead - 1 - a) & 7] : 0;
+            C.ist_new = 0;
+        }
+    }
+}
+
+template <int NCH>
+__device__ uint32_t decode_block_fast(const MlpTables &m, const GroupDev &G, const DecodeJob &job,
+                                      SubState &s, Hot<NCH> &H, Rd &b, uint32_t end_bits, uint32_t frame0,
+                                      uint32_t nch, bool governing, const uint16_t (*lut)[512], uint32_t &flags)
+{
+    bool changed;
+    if (!block_header(b, s, changed)) return 0;
+    if (rd_pos(b) > end_bits) return 0;
+    if ((uint32_t)(s.max_ch - s.min_ch + 1) != NCH) return 0xFFFFFFFFu;   // not the expected channel split: generic path
+    if (changed) hot_load_params(H, s);
+
+    const uint32_t n = s.block_size;
+    int32_t sho[NCH];
+    uint32_t lsb_bits[NCH], shift[NCH], cb[NCH], q[NCH];
+#pragma unroll
+    for (int cc = 0; cc < NCH; cc++) {
+        ChanState &C = s.ch[s.min_ch + cc];
+        q[cc] = s.q[s.min_ch + cc];
+        cb[cc] = C.codebook;
+        if (!channel_setup(s, C, q[cc], job.exact_history, flags, lsb_bits[cc], sho[cc], shift[cc])) return 0;
+        // histories are full after any block (blocks hold >= 8 frames)
+        C.flen = 8; C.ilen = 8;
+    }
+    uint32_t want = 0;
+    for (uint32_t k = 0; k < s.matrix_len; k++) want |= (uint32_t)(s.mat_bypass[k] != 0) << k;
+
+    int32_t *tile = m.tiles + G.tile_off + job.lane + ((uint64_t)frame0 * nch + s.min_ch) * DVDA_LANES;
+    uint8_t *byp = m.bypass + G.byp_off + job.lane + (uint64_t)frame0 * DVDA_LANES;
+    const uint32_t tile_step = nch * DVDA_LANES;
+    uint32_t f = frame0;
+
+    // one frame with the histories rotated by J (compile time); no data-dependent
+    // branch: invalid codes are collected in `bad` and looked at once per 8 frames
+    uint32_t bad = 0;
+#define DVDA_FRAME(J)                                                                              \
+    {                                                                                              \
+        const bool room = f < G.cap;                                                               \
+        if (!room) flags |= SEG_OVERFLOW;                                                          \
+        if (want) {                                                                                \
+            const uint32_t bmask = bypass_bits(b, want);                                           \
+            if (governing && room) *byp = (uint8_t)bmask;                                          \
+        } else if (governing && room) *byp = 0;                                                    \
+        _Pragma("unroll") for (int cc = 0; cc < NCH; cc++) {                                       \
+            rd_top_up(b);                                                                          \
+            const uint32_t e = lut[cb[cc]][(uint32_t)(b.win >> 55)];                               \
+            bad |= e;                                                                              \
+            const uint32_t hl = (e >> 8) & 15;                                                     \
+            const int32_t msb = e & 0xFF;                                                          \
+            b.win <<= hl;                                                                          \
+            const int32_t lsb = (int32_t)(uint32_t)((b.win >> 1) >> (63 - lsb_bits[cc]));          \
+            b.win <<= lsb_bits[cc];                                                                \
+            b.avail -= hl + lsb_bits[cc];                                                          \
+            const int32_t res = (int32_t)((uint32_t)((msb << lsb_bits[cc]) + lsb + sho[cc]) << q[cc]); \
+            long long s0 = 0, s1 = 0;                                                              \
+            _Pragma("unroll") for (int a = 0; a < 8; a++) {                                        \
+                s0 += (long long)H.cf[cc][a] * H.fh[cc][(a - (J)) & 7];                            \
+                s1 += (long long)H.ci[cc][a] * H.ih[cc][(a - (J)) & 7];                            \
+            }                                                                                      \
+            const long long sum = s0 + s1;                                                         \
+            const int32_t ssum = (int32_t)(sum >> shift[cc]);                                      \
+            int32_t v = (int32_t)((uint32_t)ssum + (uint32_t)res);                                 \
+            v = (v >> q[cc]) << q[cc];                                                             \
+            H.fh[cc][(7 - (J)) & 7] = v;                                                           \
+            H.ih[cc][(7 - (J)) & 7] = (int32_t)((uint32_t)v - (uint32_t)ssum);                     \
+            if (room) tile[cc * DVDA_LANES] = v;                                                   \
+        }                                                                                          \
+        f++; tile += tile_step; byp += DVDA_LANES;                                                 \
+    }
+
+    uint32_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        rd_prefetch(b);
+        DVDA_FRAME(0) DVDA_FRAME(1) DVDA_FRAME(2) DVDA_FRAME(3)
+        DVDA_FRAME(4) DVDA_FRAME(5) DVDA_FRAME(6) DVDA_FRAME(7)
+        if ((bad & 0x8000) || rd_pos(b) > end_bits) return 0;
+    }
+    // leftover frames (block size not a multiple of 8): rotate the registers for real
+    for (; i < n; i++) {
+        rd_prefetch(b);
+        DVDA_FRAME(0)
+#pragma unroll
+        for (int cc = 0; cc < NCH; cc++) {
+            const int32_t nf = H.fh[cc][7], ni = H.ih[cc][7];
+#pragma unroll
+            for (int a = 7; a > 0; a--) { H.fh[cc][a] = H.fh[cc][a - 1]; H.ih[cc][a] = H.ih[cc][a - 1]; }
+            H.fh[cc][0] = nf; H.ih[cc][0] = ni;
+        }
+        if ((bad & 0x8000) || rd_pos(b) > end_bits) return 0;
+    }
+#undef DVDA_FRAME
     return n;
 }
 
@@ -410,9 +679,58 @@ __device__ __forceinline__ uint32_t noise_step(uint32_t seed)
     return (seed << 16) ^ sh ^ (sh << 5);
 }
 
+// access-unit header through the reader: "4p 12u 16p", optional major sync,
+// substream directory (mlp.c:392-394, 614-668).  Leaves the reader anywhere.
+__device__ AuLayout au_layout_rd(Rd &b, uint64_t pos, const TrackDev &T)
+{
+    AuLayout L;
+    L.ok = false; L.has_sync = false; L.params_differ = false;
+    rd_seat(b, pos);
+    rd_skip(b, (uint32_t)(pos & 3) * 8);
+    L.total = ((rd_get(b, 32) >> 16) & 0xFFF) * 2;
+    uint32_t q = 4;
+    if (L.total >= 32 && rd_peek(b, 32) == 0xF8726FBBu) {
+        rd_drop(b, 32);
+        const uint32_t w8 = rd_get(b, 32);                 // bytes 8..11: formats, 11 skipped bits, assignment
+        rd_skip(b, 64);                                    // bytes 12..19
+        const uint32_t ns = rd_get(b, 4);                  // byte 20, high nibble
+        if (ns == 1 || ns == 2) {
+            L.has_sync = true;
+            L.params_differ = (w8 >> 28) != T.g0_bps || ((w8 >> 24) & 15) != T.g1_bps || ((w8 >> 20) & 15) != T.g0_rate ||
+                              ((w8 >> 16) & 15) != T.g1_rate || (w8 & 31) != T.assignment;
+            rd_skip(b, 92);
+            q = 32;
+        } else {
+            // not a major sync after all: the bytes are the directory (mlp.c:641-643)
+            rd_seat(b, pos);
+            rd_skip(b, (uint32_t)(pos & 3) * 8 + 32);
+        }
+    }
+    L.end[0] = L.end[1] = 0; L.chk0 = 0;
+    for (uint32_t k = 0; k < T.nss; k++) {
+        if (q + 2 > L.total) return L;
+        const uint32_t d = rd_get(b, 16);
+        L.end[k] = (d & 0xFFF) * 2;
+        if (k == 0) L.chk0 = (d >> 13) & 1;
+        q += 2;
+        if (d >> 15) { rd_skip(b, 16); q += 2; }
+    }
+    L.data0 = q;
+    if (q > L.total) return L;
+    for (uint32_t k = 0; k < T.nss; k++) {
+        const uint32_t start = k ? L.end[0] : 0;
+        if (L.end[k] < start || q + L.end[k] > L.total) return L;
+        if (L.chk0 && L.end[k] - start < 2) return L;
+    }
+    L.ok = true;
+    return L;
+}
+
 // Decodes substream job.k of segment job.seg, access unit by access unit.
+// NCH > 0: fast path for exactly NCH channels in the substream; NCH = 0: generic.
+template <int NCH>
 __device__ void decode_segment(const MlpTables &m, const DecodeJob &job, const uint16_t (*lut)[512],
-                               const int32_t *init_hist)
+                               uint32_t ring, const int32_t *init_hist)
 {
     SegDev &S = m.segs[job.seg];
     const TrackDev &T = m.tracks[S.track];
@@ -423,20 +741,31 @@ __device__ void decode_segment(const MlpTables &m, const DecodeJob &job, const u
     SubState s;
     memset(&s, 0, sizeof s);
     s.flags = 0xFF;
-    if (init_hist) {
+    Hot<(NCH > 0 ? NCH : 1)> H;
+    if (NCH > 0) {
+#pragma unroll
+        for (int cc = 0; cc < (NCH > 0 ? NCH : 1); cc++)
+#pragma unroll
+            for (int a = 0; a < 8; a++) { H.fh[cc][a] = 0; H.ih[cc][a] = 0; H.cf[cc][a] = 0; H.ci[cc][a] = 0; }
+    } else if (init_hist) {
         for (int c = 0; c < DVDA_MAX_CH; c++) {
             for (int j = 0; j < 8; j++) s.ch[c].fst[j] = init_hist[c * 8 + j];
             s.ch[c].flen = 8; s.ch[c].fhead = 0;
         }
     }
+    Rd b;
+    rd_init(b, m.es, ring);
 
     uint32_t frames = 0, flags = 0, err = 0, stop_au = 0xFFFFFFFFu, pset = 0xFFFFFFFFu;
+    bool abandon = false;          // fast path only: hand the segment to the generic fix-up pass
+    uint64_t pos = S.n_au ? m.au_pos[S.au_base] : 0;
     for (uint32_t a = 0; a < S.n_au; a++) {
         const uint32_t A = S.au_base + a;
-        const uint64_t pos = m.au_pos[A];
         const uint32_t e = m.au_err[A];
-        const AuLayout L = au_layout(m.es, pos, T);
-        if (pos + L.total > T.es_cut) { stop_au = a; break; }     // end of track, not an error
+        const AuLayout L = au_layout_rd(b, pos, T);
+        const uint64_t au_pos = pos;
+        pos += L.total;                                           // the chain k_au_chase walked
+        if (au_pos + L.total > T.es_cut) { stop_au = a; break; }  // end of track, not an error
         if (e == 1) {                                             // dropped access unit
             if (governing) { AuDev R = {frames, 0, s.seed, pset}; m.au[A] = R; }
             m.au_frames_ss[job.k * m.nau + A] = 0;
@@ -445,19 +774,24 @@ __device__ void decode_segment(const MlpTables &m, const DecodeJob &job, const u
         if (e) { err |= e; stop_au = a; break; }
         const uint32_t start = job.k ? L.end[0] : 0;
         const uint32_t len = L.end[job.k] - start - (L.chk0 ? 2 : 0);
-        BitReader b;
-        br_open(b, m.es, pos + L.data0 + start);
-        const uint32_t end_bits = b.pos + len * 8;
+        const uint64_t data = au_pos + L.data0 + start;
+        rd_seat(b, data);
+        rd_skip(b, (uint32_t)(data & 3) * 8);
+        const uint32_t end_bits = (uint32_t)(data & 3) * 8 + len * 8;
         const uint32_t au_frame0 = frames;
         bool bad = false;
         for (;;) {
-            const uint32_t n = decode_block(m, G, job, s, b, end_bits, frames, nch, governing, lut, flags);
+            uint32_t n;
+            if (NCH > 0) n = decode_block_fast<(NCH > 0 ? NCH : 1)>(m, G, job, s, H, b, end_bits, frames, nch, governing, lut, flags);
+            else n = decode_block_generic(m, G, job, s, b, end_bits, frames, nch, governing, lut, flags);
+            if (n == 0xFFFFFFFFu) { abandon = true; break; }
             if (!n) { bad = true; break; }
             frames += n;
-            const uint32_t last = br_get(b, 1);
-            if (b.pos > end_bits) { bad = true; break; }
+            const uint32_t last = rd_get(b, 1);
+            if (rd_pos(b) > end_bits) { bad = true; break; }
             if (last) break;
         }
+        if (abandon) break;
         if (bad) { err |= ERR_SYNTAX; stop_au = a; frames = au_frame0; break; }
         const uint32_t nf = frames - au_frame0;
         // a restart header inside the AU reloads the noise seed before the AU is
@@ -489,13 +823,26 @@ __device__ void decode_segment(const MlpTables &m, const DecodeJob &job, const u
             s.seed = seed;
         }
     }
+    cp_wait<0>();
+    if (abandon) {
+        m.ss_flags[job.k * m.nseg + job.seg] = SEG_NEEDS_CARRY;
+        return;
+    }
 
-    // last 8 outputs per channel, oldest first is not needed: store most-recent-last order
+    // last 8 outputs per channel: slot 7 = most recent (what a circular buffer with fhead = 0 expects)
     int32_t *tail = m.fir_tail + ((uint64_t)job.k * m.nseg + job.seg) * (DVDA_MAX_CH * 8);
-    for (uint32_t c = s.min_ch; c <= s.max_ch && s.have_header; c++) {
-        const ChanState &C = s.ch[c];
-        // slot j of the stored tail = what a fresh circular buffer with fhead = 0 expects
-        for (int j = 0; j < 8; j++) tail[c * 8 + j] = C.fst[(C.fhead + j) & 7];
+    if (s.have_header) {
+        if (NCH > 0) {
+#pragma unroll
+            for (int cc = 0; cc < (NCH > 0 ? NCH : 1); cc++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) tail[(s.min_ch + cc) * 8 + j] = H.fh[cc][7 - j];
+        } else {
+            for (uint32_t c = s.min_ch; c <= s.max_ch; c++) {
+                const ChanState &C = s.ch[c];
+                for (int j = 0; j < 8; j++) tail[c * 8 + j] = C.fst[(C.fhead + j) & 7];
+            }
+        }
     }
     m.ss_flags[job.k * m.nseg + job.seg] = flags;
     if (job.k == 0) S.frames = frames;
@@ -503,15 +850,32 @@ __device__ void decode_segment(const MlpTables &m, const DecodeJob &job, const u
     if (stop_au != 0xFFFFFFFFu) atomicMin(&S.err_au, stop_au);
 }
 
-#define DEC_WARPS 4
+// channels substream k of a track normally carries (DVD-Audio layout: substream 0
+// holds the stereo pair).  A stream that does something else is noticed by the
+// fast path and handed to the generic fix-up pass.
+__device__ __forceinline__ uint32_t expected_channels(const TrackDev &T, uint32_t k)
+{
+    if (T.nss == 1) return T.channels;
+    return k == 0 ? 2 : T.channels - 2;
+}
 
-// one warp per (group, substream); lane = segment of the group
+#define DEC_WARPS 4
+#define DEC_SMEM_BYTES (DEC_WARPS * RING_SLOTS * DVDA_LANES * 16 + 4 * 512 * 2)
+
+// One warp per (group, substream); lane = segment of the group.  One
+// instantiation per channel count (NCH = 0: generic, more than 4 channels), so
+// that the common stereo case is not compiled with the register budget of the
+// 4-channel one; warps whose substream has another channel count leave at once.
+template <int NCH>
 __global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_decode(MlpTables m)
 {
-    __shared__ uint16_t lut[3][512];
-    for (uint32_t i = threadIdx.x; i < 3 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry((i >> 9) + 1, i & 511);
+    extern __shared__ uint4 dyn_smem[];
+    uint4 (*ring)[RING_SLOTS][DVDA_LANES] = reinterpret_cast<uint4 (*)[RING_SLOTS][DVDA_LANES]>(dyn_smem);
+    uint16_t (*lut)[512] = reinterpret_cast<uint16_t (*)[512]>(dyn_smem + DEC_WARPS * RING_SLOTS * DVDA_LANES);
+    for (uint32_t i = threadIdx.x; i < 4 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry(i >> 9, i & 511);
     __syncthreads();
-    const uint32_t warp = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
+    const uint32_t wib = threadIdx.x >> 5;
+    const uint32_t warp = blockIdx.x * DEC_WARPS + wib;
     const uint32_t lane = threadIdx.x & 31;
     // work items: (group, substream) pairs, substream-major inside a group
     const uint32_t g = warp >> 1, k = warp & 1;
@@ -519,29 +883,51 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_decode(MlpTables m)
     const GroupDev &G = m.groups[g];
     const TrackDev &T = m.tracks[G.track];
     if (k >= T.nss || lane >= G.nseg) return;
+    const uint32_t want = expected_channels(T, k);
+    if ((want <= 4 ? want : 0) != NCH) return;
     DecodeJob job;
     job.seg = G.seg0 + lane;
     job.k = k;
     job.lane = lane;
     job.exact_history = (job.seg == T.seg_base);      // a track starts with empty histories
-    decode_segment(m, job, lut, nullptr);
+    const uint32_t rs = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]);
+    decode_segment<NCH>(m, job, lut, rs, nullptr);
 }
 
-int launch_mlp_decode(MlpTables m, cudaStream_t s)
+// nch_mask: bit n set = some substream of the batch carries n channels (bit 0: more than 4)
+int launch_mlp_decode(MlpTables m, uint32_t nch_mask, cudaStream_t s)
 {
     if (!m.ngroups) return 0;
-    LAUNCH(k_mlp_decode, div_up_u32((uint64_t)m.ngroups * 2, DEC_WARPS), DEC_WARPS * 32, 0, s, m);
+    const uint32_t grid = div_up_u32((uint64_t)m.ngroups * 2, DEC_WARPS);
+    const size_t smem = DEC_SMEM_BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (nch_mask & 1) LAUNCH(k_mlp_decode<0>, grid, DEC_WARPS * 32, smem, s, m);
+    if (nch_mask & 2) LAUNCH(k_mlp_decode<1>, grid, DEC_WARPS * 32, smem, s, m);
+    if (nch_mask & 4) LAUNCH(k_mlp_decode<2>, grid, DEC_WARPS * 32, smem, s, m);
+    if (nch_mask & 8) LAUNCH(k_mlp_decode<3>, grid, DEC_WARPS * 32, smem, s, m);
+    if (nch_mask & 16) LAUNCH(k_mlp_decode<4>, grid, DEC_WARPS * 32, smem, s, m);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 // Segments whose first filtered block needs FIR history from the previous
-// segment (the reference never clears it, mlp.c:948-952) are decoded again, in
-// order, run by run: one thread per (run head, substream).
-__global__ void k_carry_fix(MlpTables m)
+// segment (the reference never clears it, mlp.c:948-952), and segments the fast
+// path could not take (unexpected channel split), are decoded again with the
+// generic routine, in order, run by run: one thread per (run head, substream).
+#define FIX_THREADS 32
+__global__ void __launch_bounds__(FIX_THREADS) k_carry_fix(MlpTables m)
 {
-    __shared__ uint16_t lut[3][512];
-    for (uint32_t i = threadIdx.x; i < 3 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry((i >> 9) + 1, i & 511);
+    __shared__ uint16_t lut[4][512];
+    __shared__ uint4 ring[RING_SLOTS][DVDA_LANES];
+    for (uint32_t i = threadIdx.x; i < 4 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry(i >> 9, i & 511);
     __syncthreads();
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t seg = idx >> 1, k = idx & 1;
@@ -553,20 +939,21 @@ __global__ void k_carry_fix(MlpTables m)
     // run head: predecessor (same track) is not waiting for a carry itself
     if (seg > T.seg_base && (fl[seg - 1] & SEG_NEEDS_CARRY)) return;
     const uint32_t track_end = T.seg_base + T.nseg;
+    const uint32_t rs = (uint32_t)__cvta_generic_to_shared(&ring[0][threadIdx.x & 31]);
     for (uint32_t s = seg; s < track_end && (fl[s] & SEG_NEEDS_CARRY); s++) {
         DecodeJob job;
         job.seg = s; job.k = k; job.lane = (s - T.seg_base) % DVDA_LANES; job.exact_history = true;
         const int32_t *prev = m.fir_tail + ((uint64_t)k * m.nseg + (s - 1)) * (DVDA_MAX_CH * 8);
         // parsing does not depend on filter history, so the error bookkeeping of the
         // first pass (merged with atomics) is reproduced exactly
-        decode_segment(m, job, lut, s > T.seg_base ? prev : nullptr);
+        decode_segment<0>(m, job, lut, rs, s > T.seg_base ? prev : nullptr);
     }
 }
 
 int launch_carry_fix(MlpTables m, cudaStream_t s)
 {
     if (!m.nseg) return 0;
-    LAUNCH(k_carry_fix, div_up_u32((uint64_t)m.nseg * 2, 64), 64, 0, s, m);
+    LAUNCH(k_carry_fix, div_up_u32((uint64_t)m.nseg * 2, FIX_THREADS), FIX_THREADS, 0, s, m);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
