@@ -69,7 +69,7 @@ enum {
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
     B_SS_FLAGS, B_SS_FLAGS_PREV, B_FIR_TAIL,
     B_GROUPS, B_GRP_CELLS, B_CELL_BASE, B_GRP_CHUNKS, B_GRP_CHUNK_BASE,
-    B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
+    B_DEC_WORK, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
     B_COUNT
 };
 
@@ -355,13 +355,19 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         nseg += ht[i].nseg; ngroups += ht[i].ngrp;
     }
     h_seg_base[n_tracks] = nseg; h_grp_base[n_tracks] = ngroups;
-    // channel counts per substream present in this batch: picks the decode kernel instantiations
-    uint32_t nch_mask = 0;
+    // decode work lists, one per channel-count class (0 = generic, more than 4 channels):
+    // substream 0 of a two-substream stream carries the stereo pair (DVD-Audio layout)
+    std::vector<DecWork> h_work[5];
+    uint32_t n_warps[5] = {0, 0, 0, 0, 0};
     for (uint32_t i = 0; i < n_tracks; i++) {
         if (!ht[i].nseg) continue;
-        const uint32_t a = ht[i].nss == 1 ? ht[i].channels : 2, b = ht[i].nss == 1 ? a : ht[i].channels - 2;
-        nch_mask |= 1u << (a <= 4 ? a : 0);
-        nch_mask |= 1u << (b <= 4 ? b : 0);
+        for (uint32_t k = 0; k < ht[i].nss; k++) {
+            const uint32_t nch = ht[i].nss == 1 ? ht[i].channels : (k == 0 ? 2 : ht[i].channels - 2);
+            const uint32_t cls = (nch >= 1 && nch <= 4) ? nch : 0;
+            DecWork w = {n_warps[cls], i, k, 0};
+            h_work[cls].push_back(w);
+            n_warps[cls] += ht[i].ngrp;
+        }
     }
     uint32_t *trk_pk_lo = c->buf[B_TRK_PK_LO].as<uint32_t>(), *trk_seg_base = c->buf[B_TRK_SEG_BASE].as<uint32_t>();
     uint32_t *trk_grp_base = c->buf[B_TRK_GRP_BASE].as<uint32_t>();
@@ -370,6 +376,23 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     CUDA_TRY(cudaMemcpyAsync(trk_seg_base, h_seg_base.data(), (n_tracks + 1) * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(trk_grp_base, h_grp_base.data(), (n_tracks + 1) * 4, cudaMemcpyHostToDevice, s));
 
+    const DecWork *d_work[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t n_work[5] = {0, 0, 0, 0, 0};
+    {
+        size_t total = 0;
+        for (int cl = 0; cl < 5; cl++) total += h_work[cl].size();
+        ENSURE(B_DEC_WORK, (total + 1) * sizeof(DecWork));
+        DecWork *base = c->buf[B_DEC_WORK].as<DecWork>();
+        size_t off = 0;
+        for (int cl = 0; cl < 5; cl++) {
+            n_work[cl] = (uint32_t)h_work[cl].size();
+            d_work[cl] = base + off;
+            if (n_work[cl])
+                CUDA_TRY(cudaMemcpyAsync(base + off, h_work[cl].data(), n_work[cl] * sizeof(DecWork), cudaMemcpyHostToDevice, s));
+            off += n_work[cl];
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));      // h_work goes out of use only after the copies
+    }
     MlpTables m;
     memset(&m, 0, sizeof m);
     m.es = es; m.es_total = es_total; m.pk_es = pk_es; m.np = np;
@@ -428,7 +451,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             m.tiles = c->buf[B_TILES].as<int32_t>(); m.bypass = c->buf[B_BYPASS].as<uint8_t>();
             TRY(launch_group_offsets(m.groups, ngroups, cell_base, s));
             CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
-            TIMED(DVDAGPU_K_MLP_DECODE, launch_mlp_decode(m, nch_mask, s));
+            TIMED(DVDAGPU_K_MLP_DECODE, launch_mlp_decode(m, d_work, n_work, n_warps, s));
             CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
             TIMED(DVDAGPU_K_CARRY_FIX, launch_carry_fix(m, s));
             TRY(launch_seg_finalize(m, seg_frames, d_status, s));

@@ -85,7 +85,9 @@ int launch_group_offsets(GroupDev *groups, uint32_t ngroups, const uint64_t *cel
 
 // mlp_decode.cu
 int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s);
-int launch_mlp_decode(MlpTables m, uint32_t nch_mask, cudaStream_t s);
+// a run of decode warps: the groups of substream k of one track
+struct DecWork { uint32_t warp0, track, k, pad; };
+int launch_mlp_decode(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s);
 int launch_carry_fix(MlpTables m, cudaStream_t s);
 int launch_seg_finalize(MlpTables m, uint32_t *seg_frames, uint32_t *status, cudaStream_t s);
 int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, cudaStream_t s);

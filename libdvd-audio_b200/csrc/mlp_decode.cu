@@ -73,31 +73,59 @@ __device__ AuLayout au_layout(const uint8_t *es, uint64_t pos, const TrackDev &T
     return L;
 }
 
-// One thread per access unit: parity and CRC-8 of each substream.
-// au_err: 0 ok, 1 = drop silently (stream parameters changed, mlp.c:452-455),
-// else ERR_* bits.
-__global__ void k_checkdata(MlpTables m, const uint32_t *__restrict__ seg_au_base)
+// One thread per access unit: parity and CRC-8 of each substream
+// (mlp.c:670-712, 1360-1399: parity over all bytes but the last two, CRC-8
+// (poly 0x63, start 0x3C) over the same bytes where the check byte is compared
+// with the value *in front of* the last table step).
+// The stream is read 16 bytes at a time; the CRC advances four bytes per step
+// with four 256-byte tables in shared memory (table k = "byte followed by k
+// zero bytes").  au_err: 0 ok, 1 = drop silently (stream parameters changed,
+// mlp.c:452-455), else ERR_* bits.
+#define CHK_THREADS 128
+__global__ void __launch_bounds__(CHK_THREADS) k_checkdata(MlpTables m, const uint32_t *__restrict__ seg_au_base)
 {
+    __shared__ uint8_t T[4][256];
+    for (uint32_t i = threadIdx.x; i < 256; i += CHK_THREADS) {
+        const uint8_t t0 = c_crc8[i], t1 = c_crc8[t0], t2 = c_crc8[t1];
+        T[0][i] = t0; T[1][i] = t1; T[2][i] = t2; T[3][i] = c_crc8[t2];
+    }
+    __syncthreads();
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= m.nau) return;
     const uint32_t si = upper_bound_dev(seg_au_base, m.nseg, a) - 1;
-    const TrackDev &T = m.tracks[m.segs[si].track];
+    const TrackDev &Tr = m.tracks[m.segs[si].track];
     const uint64_t pos = m.au_pos[a];
-    const AuLayout L = au_layout(m.es, pos, T);
+    const AuLayout L = au_layout(m.es, pos, Tr);
     uint32_t err = 0;
     if (L.has_sync && L.params_differ) err = 1;
     else if (!L.ok) err = ERR_SYNTAX;
     else if (L.chk0) {
-        for (uint32_t k = 0; k < T.nss && !err; k++) {
+        for (uint32_t k = 0; k < Tr.nss && !err; k++) {
             const uint32_t start = k ? L.end[0] : 0;
             const uint8_t *p = m.es + pos + L.data0 + start;
-            const uint32_t n = L.end[k] - start - 2;
+            const uint32_t n = L.end[k] - start - 2;          // bytes covered
             uint32_t parity = 0, crc = 0x3C, fin = 0;
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t b = ld_u8(p + i);
-                parity ^= b;
-                fin = crc ^ b;
-                crc = c_crc8[fin];
+            if (n) {
+                // all bytes but the last advance the CRC; the last one only forms `fin`
+                const uint32_t body = n - 1;
+                uint32_t i = 0;
+                const uint32_t head = min(body, (uint32_t)((16 - ((uintptr_t)p & 15)) & 15));
+                for (; i < head; i++) { const uint32_t b = ld_u8(p + i); parity ^= b; crc = T[0][crc ^ b]; }
+                uint32_t pw = 0;
+                for (; i + 16 <= body; i += 16) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + i));
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        pw ^= w[j];
+                        crc = T[3][(crc ^ w[j]) & 0xFF] ^ T[2][(w[j] >> 8) & 0xFF] ^ T[1][(w[j] >> 16) & 0xFF] ^ T[0][w[j] >> 24];
+                    }
+                }
+                parity ^= (pw ^ (pw >> 8) ^ (pw >> 16) ^ (pw >> 24)) & 0xFF;
+                for (; i < body; i++) { const uint32_t b = ld_u8(p + i); parity ^= b; crc = T[0][crc ^ b]; }
+                const uint32_t last = ld_u8(p + body);
+                parity ^= last;
+                fin = crc ^ last;
             }
             if (((ld_u8(p + n) ^ parity) & 0xFF) != 0xA9) err = ERR_PARITY;
             else if (ld_u8(p + n + 1) != fin) err = ERR_CRC;
@@ -115,7 +143,7 @@ int upload_crc_table(const uint8_t *t)
 int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
 {
     if (!m.nau) return 0;
-    LAUNCH(k_checkdata, div_up_u32(m.nau, 128), 128, 0, s, m, seg_au_base);
+    LAUNCH(k_checkdata, div_up_u32(m.nau, CHK_THREADS), CHK_THREADS, 0, s, m, seg_au_base);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -150,6 +178,7 @@ struct Rd {
     uint32_t fill_c;        // chunks [.., fill_c) have been issued
     uint32_t safe_w;        // words [.., safe_w) are known to have landed
     uint32_t base_w;        // word index the bit counter is relative to
+    uint32_t ahead;         // hot loop only: ring word next_w, fetched one step early
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t smem, const void *g)
@@ -174,8 +203,20 @@ __device__ __forceinline__ void rd_init(Rd &r, const uint8_t *es, uint32_t ring)
     r.es = es; r.ring = ring; r.win = 0; r.avail = 0; r.next_w = 0; r.fill_c = 0; r.safe_w = 0; r.base_w = 0;
 }
 
-// warp-uniform prefetch point: keep the ring ~5 chunks ahead of the reader
-__device__ __forceinline__ void rd_prefetch(Rd &r)
+// cold: make sure words [next_w, next_w + need) are in the ring
+__device__ __noinline__ void rd_slow_fill(Rd &r, uint32_t need)
+{
+    while (r.fill_c * CHUNK_WORDS < r.next_w + need + CHUNK_WORDS && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
+    cp_commit();
+    cp_wait<0>();
+    r.safe_w = r.fill_c * CHUNK_WORDS;
+}
+
+// warp-uniform prefetch point: keep the ring ~6 chunks ahead of the reader and
+// guarantee that the next `need` words have landed (the hot loop reads them
+// without checking).  In steady state the guarantee holds by construction;
+// right after a long header it may not, then the lane takes the slow path.
+__device__ __forceinline__ void rd_prefetch(Rd &r, uint32_t need)
 {
     const uint32_t landed = r.fill_c * CHUNK_WORDS;
 #pragma unroll
@@ -185,15 +226,7 @@ __device__ __forceinline__ void rd_prefetch(Rd &r)
     }
     cp_wait<2>();
     r.safe_w = landed;
-}
-
-// cold: the word at next_w is not known to be in the ring
-__device__ __noinline__ void rd_slow_fill(Rd &r)
-{
-    while (r.fill_c * CHUNK_WORDS < r.next_w + 64 && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
-    cp_commit();
-    cp_wait<0>();
-    r.safe_w = r.fill_c * CHUNK_WORDS;
+    if (r.next_w + need > r.safe_w) rd_slow_fill(r, need);
 }
 
 // position the reader at an absolute byte offset
@@ -222,7 +255,7 @@ __device__ __forceinline__ uint32_t rd_ring_word(const Rd &r, uint32_t w)
 // checked pull (headers, generic path): avail must be <= 32
 __device__ __forceinline__ void rd_pull(Rd &r)
 {
-    if (r.next_w >= r.safe_w) rd_slow_fill(r);
+    if (r.next_w >= r.safe_w) rd_slow_fill(r, 48);
     const uint32_t word = rd_ring_word(r, r.next_w);
     r.win |= (uint64_t)word << (32 - r.avail);
     r.avail += 32;
@@ -230,15 +263,18 @@ __device__ __forceinline__ void rd_pull(Rd &r)
 }
 
 // hot pull: no branch; afterwards avail > 32.  The caller guarantees (through
-// rd_prefetch) that the next words have landed.
+// rd_prefetch) that the next words have landed.  The ring word is fetched one
+// step ahead (r.ahead) so that the shared-memory latency is off the critical
+// path of the window; rd_hot_begin() primes it.
+__device__ __forceinline__ void rd_hot_begin(Rd &r) { r.ahead = rd_ring_word(r, r.next_w); }
 __device__ __forceinline__ void rd_top_up(Rd &r)
 {
-    const uint32_t word = rd_ring_word(r, r.next_w);
     const bool need = r.avail <= 32;
-    const uint64_t add = (uint64_t)word << ((32 - r.avail) & 63);
+    const uint64_t add = (uint64_t)r.ahead << ((32 - r.avail) & 63);
     r.win |= need ? add : 0ull;
     r.avail += need ? 32 : 0;
     r.next_w += need ? 1u : 0u;
+    r.ahead = rd_ring_word(r, r.next_w);
 }
 
 // next n bits (1..32) without consuming them
@@ -581,7 +617,7 @@ __device__ __forceinline__ void hot_load_params(Hot<NCH> &H, SubState &s)
 }
 
 template <int NCH>
-__device__ uint32_t decode_block_fast(const MlpTables &m, const GroupDev &G, const DecodeJob &job,
+__device__ __forceinline__ uint32_t decode_block_fast(const MlpTables &m, const GroupDev &G, const DecodeJob &job,
                                       SubState &s, Hot<NCH> &H, Rd &b, uint32_t end_bits, uint32_t frame0,
                                       uint32_t nch, bool governing, const uint16_t (*lut)[512], uint32_t &flags)
 {
@@ -609,17 +645,19 @@ __device__ uint32_t decode_block_fast(const MlpTables &m, const GroupDev &G, con
     int32_t *tile = m.tiles + G.tile_off + job.lane + ((uint64_t)frame0 * nch + s.min_ch) * DVDA_LANES;
     uint8_t *byp = m.bypass + G.byp_off + job.lane + (uint64_t)frame0 * DVDA_LANES;
     const uint32_t tile_step = nch * DVDA_LANES;
-    uint32_t f = frame0;
+    const uint32_t cap = G.cap;
+    uint32_t f = frame0, over = 0;
 
     // one frame with the histories rotated by J (compile time); no data-dependent
     // branch: invalid codes are collected in `bad` and looked at once per 8 frames
     uint32_t bad = 0;
 #define DVDA_FRAME(J)                                                                              \
     {                                                                                              \
-        const bool room = f < G.cap;                                                               \
-        if (!room) flags |= SEG_OVERFLOW;                                                          \
+        const bool room = f < cap;                                                                 \
+        over |= room ? 0u : SEG_OVERFLOW;                                                          \
         if (want) {                                                                                \
             const uint32_t bmask = bypass_bits(b, want);                                           \
+            rd_hot_begin(b);                      /* the checked reader moved next_w */             \
             if (governing && room) *byp = (uint8_t)bmask;                                          \
         } else if (governing && room) *byp = 0;                                                    \
         _Pragma("unroll") for (int cc = 0; cc < NCH; cc++) {                                       \
@@ -649,16 +687,21 @@ __device__ uint32_t decode_block_fast(const MlpTables &m, const GroupDev &G, con
         f++; tile += tile_step; byp += DVDA_LANES;                                                 \
     }
 
+    // words 8 frames can consume at most (33 bits per sample, 6 bypass bits per frame), plus
+    // the word fetched ahead
+    const uint32_t need8 = (8 * (NCH * 33 + 6) + 31) / 32 + 2;
     uint32_t i = 0;
     for (; i + 8 <= n; i += 8) {
-        rd_prefetch(b);
+        rd_prefetch(b, need8);
+        rd_hot_begin(b);
         DVDA_FRAME(0) DVDA_FRAME(1) DVDA_FRAME(2) DVDA_FRAME(3)
         DVDA_FRAME(4) DVDA_FRAME(5) DVDA_FRAME(6) DVDA_FRAME(7)
         if ((bad & 0x8000) || rd_pos(b) > end_bits) return 0;
     }
     // leftover frames (block size not a multiple of 8): rotate the registers for real
     for (; i < n; i++) {
-        rd_prefetch(b);
+        rd_prefetch(b, need8);
+        rd_hot_begin(b);
         DVDA_FRAME(0)
 #pragma unroll
         for (int cc = 0; cc < NCH; cc++) {
@@ -670,6 +713,7 @@ __device__ uint32_t decode_block_fast(const MlpTables &m, const GroupDev &G, con
         if ((bad & 0x8000) || rd_pos(b) > end_bits) return 0;
     }
 #undef DVDA_FRAME
+    flags |= over;
     return n;
 }
 
@@ -729,7 +773,7 @@ __device__ AuLayout au_layout_rd(Rd &b, uint64_t pos, const TrackDev &T)
 // Decodes substream job.k of segment job.seg, access unit by access unit.
 // NCH > 0: fast path for exactly NCH channels in the substream; NCH = 0: generic.
 template <int NCH>
-__device__ void decode_segment(const MlpTables &m, const DecodeJob &job, const uint16_t (*lut)[512],
+__device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJob &job, const uint16_t (*lut)[512],
                                uint32_t ring, const int32_t *init_hist)
 {
     SegDev &S = m.segs[job.seg];
@@ -850,24 +894,17 @@ __device__ void decode_segment(const MlpTables &m, const DecodeJob &job, const u
     if (stop_au != 0xFFFFFFFFu) atomicMin(&S.err_au, stop_au);
 }
 
-// channels substream k of a track normally carries (DVD-Audio layout: substream 0
-// holds the stereo pair).  A stream that does something else is noticed by the
-// fast path and handed to the generic fix-up pass.
-__device__ __forceinline__ uint32_t expected_channels(const TrackDev &T, uint32_t k)
-{
-    if (T.nss == 1) return T.channels;
-    return k == 0 ? 2 : T.channels - 2;
-}
-
 #define DEC_WARPS 4
 #define DEC_SMEM_BYTES (DEC_WARPS * RING_SLOTS * DVDA_LANES * 16 + 4 * 512 * 2)
 
 // One warp per (group, substream); lane = segment of the group.  One
 // instantiation per channel count (NCH = 0: generic, more than 4 channels), so
 // that the common stereo case is not compiled with the register budget of the
-// 4-channel one; warps whose substream has another channel count leave at once.
+// 4-channel one.  Each instantiation gets a dense list of exactly its warps
+// (DecWork rows: a run of warps = the groups of one track's substream).
 template <int NCH>
-__global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_decode(MlpTables m)
+__global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_decode(MlpTables m, const DecWork *__restrict__ work,
+                                                               uint32_t n_work, uint32_t n_warps)
 {
     extern __shared__ uint4 dyn_smem[];
     uint4 (*ring)[RING_SLOTS][DVDA_LANES] = reinterpret_cast<uint4 (*)[RING_SLOTS][DVDA_LANES]>(dyn_smem);
@@ -877,43 +914,47 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_decode(MlpTables m)
     const uint32_t wib = threadIdx.x >> 5;
     const uint32_t warp = blockIdx.x * DEC_WARPS + wib;
     const uint32_t lane = threadIdx.x & 31;
-    // work items: (group, substream) pairs, substream-major inside a group
-    const uint32_t g = warp >> 1, k = warp & 1;
-    if (g >= m.ngroups) return;
-    const GroupDev &G = m.groups[g];
-    const TrackDev &T = m.tracks[G.track];
-    if (k >= T.nss || lane >= G.nseg) return;
-    const uint32_t want = expected_channels(T, k);
-    if ((want <= 4 ? want : 0) != NCH) return;
+    if (warp >= n_warps) return;
+    // last work row whose first warp is <= warp
+    uint32_t lo = 0, hi = n_work;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
+    }
+    const DecWork W = work[lo];
+    const TrackDev &T = m.tracks[W.track];
+    const GroupDev &G = m.groups[T.grp_base + (warp - W.warp0)];
+    if (lane >= G.nseg) return;
     DecodeJob job;
     job.seg = G.seg0 + lane;
-    job.k = k;
+    job.k = W.k;
     job.lane = lane;
     job.exact_history = (job.seg == T.seg_base);      // a track starts with empty histories
     const uint32_t rs = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]);
     decode_segment<NCH>(m, job, lut, rs, nullptr);
 }
 
-// nch_mask: bit n set = some substream of the batch carries n channels (bit 0: more than 4)
-int launch_mlp_decode(MlpTables m, uint32_t nch_mask, cudaStream_t s)
+template <int NCH>
+static int launch_one_decode(MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
 {
-    if (!m.ngroups) return 0;
-    const uint32_t grid = div_up_u32((uint64_t)m.ngroups * 2, DEC_WARPS);
-    const size_t smem = DEC_SMEM_BYTES;
+    if (!n_warps) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES));
         attr_set = true;
     }
-    if (nch_mask & 1) LAUNCH(k_mlp_decode<0>, grid, DEC_WARPS * 32, smem, s, m);
-    if (nch_mask & 2) LAUNCH(k_mlp_decode<1>, grid, DEC_WARPS * 32, smem, s, m);
-    if (nch_mask & 4) LAUNCH(k_mlp_decode<2>, grid, DEC_WARPS * 32, smem, s, m);
-    if (nch_mask & 8) LAUNCH(k_mlp_decode<3>, grid, DEC_WARPS * 32, smem, s, m);
-    if (nch_mask & 16) LAUNCH(k_mlp_decode<4>, grid, DEC_WARPS * 32, smem, s, m);
+    LAUNCH(k_mlp_decode<NCH>, div_up_u32(n_warps, DEC_WARPS), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
+    return 0;
+}
+
+// work[c], n_work[c], n_warps[c] for channel class c = 0..4 (0 = generic)
+int launch_mlp_decode(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s)
+{
+    if (launch_one_decode<0>(m, work[0], n_work[0], n_warps[0], s)) return -1;
+    if (launch_one_decode<1>(m, work[1], n_work[1], n_warps[1], s)) return -1;
+    if (launch_one_decode<2>(m, work[2], n_work[2], n_warps[2], s)) return -1;
+    if (launch_one_decode<3>(m, work[3], n_work[3], n_warps[3], s)) return -1;
+    if (launch_one_decode<4>(m, work[4], n_work[4], n_warps[4], s)) return -1;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
