@@ -307,13 +307,9 @@ def main():
         # the two paths must agree with each other
         check = int(host_out[:: max(1, samples // 65536)].to(torch.int64).sum())
 
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-        tot = torch.tensor([float(samples)], dtype=torch.float64, device="cuda")
-        if dist:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        ms, ms_e2e = float(t[0]), float(t[1])
-        total_samples = float(tot[0])
+        shard = importlib.import_module("libdvd-audio_b200.shard")
+        ms, total_samples = shard.reduce_job(ms, samples, dist, "cuda")            # MAX time, SUM samples
+        ms_e2e, _ = shard.reduce_job(ms_e2e, samples, dist, "cuda")
 
         if rank == 0:
             value = total_samples * args.steps / (ms * 1e-3)
