@@ -51,8 +51,17 @@ typedef struct {
     uint32_t first_sector;      /* first sector of the track */
     uint32_t last_sector;       /* last sector (MLP: decoding runs on to the next major sync) */
     uint32_t pts_length;        /* track length in 90 kHz ticks (PCM frame budget) */
-    uint32_t reserved;
+    uint32_t flags;             /* DVDAGPU_PART_* : the "track" is one part of a longer MLP track */
 } dvdagpu_track_desc;
+
+/* A long MLP track may be decoded in parts, each part given as its own
+ * "track" over consecutive sector ranges (the cut lands on the first major sync
+ * behind last_sector, exactly like the disc's own track boundaries).  The flags
+ * keep the reference's per-packet rules exact across the cuts. */
+enum {
+    DVDAGPU_PART_CONTINUES_PREVIOUS = 1,   /* not the real start of the track */
+    DVDAGPU_PART_CONTINUED_BY_NEXT = 2     /* not the real end of the track */
+};
 
 /* What the reference exposes through dvda_codec(), dvda_bits_per_sample(),
  * dvda_sample_rate(), dvda_channel_count() plus the decoded length. */
@@ -64,6 +73,11 @@ typedef struct {
     uint32_t channels, bits_per_sample, sample_rate;
     uint32_t truncated;         /* 1: the sector buffer ended before the track's natural end
                                    (next major sync / PCM frame budget); pass more sectors */
+    uint32_t stopped;           /* 0: ran to its natural end; 1: ended early (damage, or the reference's
+                                   "packet without a complete access unit" rule): later parts must be
+                                   dropped; 2: a continued part needs the previous part's filter
+                                   history: decode the parts in one piece instead */
+    uint32_t reserved;
     uint64_t frames;            /* PCM frames decoded */
     uint64_t pcm_offset;        /* first sample of the track in the engine's PCM buffer (in int32 units) */
 } dvdagpu_track_result;
@@ -80,7 +94,7 @@ typedef struct {
     uint64_t access_units;
     uint64_t es_bytes;          /* MLP elementary-stream bytes */
     uint64_t samples;           /* total samples produced */
-    float kernel_ms[8];         /* device time of the main kernels, see DVDAGPU_K_* */
+    float kernel_ms[12];        /* device time of the main kernels, see DVDAGPU_K_* */
 } dvdagpu_stats;
 
 /* indices into dvdagpu_stats.kernel_ms */
@@ -89,10 +103,13 @@ enum {
     DVDAGPU_K_SYNC_SCAN = 1,    /* major sync search (both passes) */
     DVDAGPU_K_AU_CHASE = 2,     /* access-unit chains (both passes) */
     DVDAGPU_K_CHECKDATA = 3,    /* parity / CRC-8 */
-    DVDAGPU_K_MLP_DECODE = 4,   /* entropy decode + prediction filters */
+    DVDAGPU_K_MLP_DECODE = 4,   /* complete single-pass MLP decoder (fallback of the three-pass path) */
     DVDAGPU_K_CARRY_FIX = 5,    /* segments needing the previous segment's FIR history */
     DVDAGPU_K_REMATRIX = 6,     /* matrices, bypass, shift, interleave */
-    DVDAGPU_K_PCM_UNPACK = 7
+    DVDAGPU_K_PCM_UNPACK = 7,
+    DVDAGPU_K_MLP_HEADERS = 8,  /* fast path, pass A: block headers of every access unit */
+    DVDAGPU_K_MLP_ENTROPY = 9,  /* fast path, pass B: residual entropy decode, one lane per access unit */
+    DVDAGPU_K_MLP_FILTER = 10   /* fast path, pass C: FIR/IIR prediction, one lane per channel */
 };
 
 /* number of CUDA devices the engine can use (0 = none) */
@@ -121,6 +138,20 @@ int dvdagpu_decode_host(dvdagpu_ctx *ctx, const uint8_t *sectors, uint64_t n_sec
 int dvdagpu_decode_device(dvdagpu_ctx *ctx, const void *device_sectors, uint64_t n_sectors,
                           uint32_t n_tracks, const dvdagpu_track_desc *tracks,
                           dvdagpu_track_result *results);
+
+/* Decode ONE track from host memory with the copies overlapped: the track is
+ * cut into parts of `part_sectors` sectors (0 = default), part i+1 is uploaded
+ * and part i-1 downloaded while part i is decoded, and the interleaved samples
+ * land in `pcm_host` (pinned memory, room for `pcm_capacity` int32) in order.
+ * result->pcm_offset is 0.  Falls back to the one-piece path by itself when the
+ * track cannot be cut (PCM, short, filter history crossing a cut).  Returns 0,
+ * 3 if pcm_host is too small, another nonzero value on an engine error.
+ * Replaces: dvda_open_track_reader + decode loop + dvda_read copies for a whole
+ * track (dvd-audio.c:597-795). */
+int dvdagpu_decode_track_pipelined(dvdagpu_ctx *ctx, const uint8_t *sectors, uint64_t n_sectors,
+                                   const dvdagpu_track_desc *track, uint32_t part_sectors,
+                                   int32_t *pcm_host, uint64_t pcm_capacity,
+                                   dvdagpu_track_result *result);
 
 /* Copy decoded samples of the last decode to host memory: `count` int32
  * samples starting at sample `offset` of the engine's PCM buffer (use

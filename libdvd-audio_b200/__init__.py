@@ -30,7 +30,8 @@ ERR_PARITY, ERR_CRC, ERR_SYNTAX = 1 << 4, 1 << 5, 1 << 6
 # every symbol include/dvdagpu.h declares
 ENGINE_SYMBOLS = [
     "dvdagpu_device_count", "dvdagpu_create", "dvdagpu_destroy", "dvdagpu_set_stream",
-    "dvdagpu_decode_host", "dvdagpu_decode_device", "dvdagpu_fetch", "dvdagpu_pcm_device",
+    "dvdagpu_decode_host", "dvdagpu_decode_device", "dvdagpu_decode_track_pipelined",
+    "dvdagpu_fetch", "dvdagpu_pcm_device",
     "dvdagpu_host_alloc", "dvdagpu_host_free", "dvdagpu_get_stats", "dvdagpu_last_error",
 ]
 # every function include/dvd-audio.h declares
@@ -47,7 +48,7 @@ API_SYMBOLS = [
 
 class TrackDesc(ctypes.Structure):
     _fields_ = [("first_sector", ctypes.c_uint32), ("last_sector", ctypes.c_uint32),
-                ("pts_length", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("pts_length", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
 
 
 class TrackResult(ctypes.Structure):
@@ -57,6 +58,7 @@ class TrackResult(ctypes.Structure):
                 ("channel_assignment", ctypes.c_uint32),
                 ("channels", ctypes.c_uint32), ("bits_per_sample", ctypes.c_uint32),
                 ("sample_rate", ctypes.c_uint32), ("truncated", ctypes.c_uint32),
+                ("stopped", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
                 ("frames", ctypes.c_uint64), ("pcm_offset", ctypes.c_uint64)]
 
 
@@ -65,9 +67,10 @@ class Stats(ctypes.Structure):
                 ("output_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("launches", ctypes.c_uint32), ("segments", ctypes.c_uint32),
                 ("access_units", ctypes.c_uint64), ("es_bytes", ctypes.c_uint64), ("samples", ctypes.c_uint64),
-                ("kernel_ms", ctypes.c_float * 8)]
+                ("kernel_ms", ctypes.c_float * 12)]
 
-KERNEL_NAMES = ["es_gather", "sync_scan", "au_chase", "checkdata", "mlp_decode", "carry_fix", "rematrix", "pcm_unpack"]
+KERNEL_NAMES = ["es_gather", "sync_scan", "au_chase", "checkdata", "mlp_decode", "carry_fix", "rematrix", "pcm_unpack",
+                "mlp_headers", "mlp_entropy", "mlp_filter", "reserved"]
 
 
 _engine = None
@@ -92,6 +95,10 @@ def engine_lib():
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32,
                           ctypes.POINTER(TrackDesc), ctypes.POINTER(TrackResult)]
+        L.dvdagpu_decode_track_pipelined.restype = ctypes.c_int
+        L.dvdagpu_decode_track_pipelined.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(TrackDesc), ctypes.c_uint32,
+            ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(TrackResult)]
         L.dvdagpu_fetch.restype = ctypes.c_int
         L.dvdagpu_fetch.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
         L.dvdagpu_pcm_device.restype = ctypes.c_void_p
@@ -167,8 +174,9 @@ class Engine:
 
     def _descs(self, tracks):
         arr = (TrackDesc * len(tracks))()
-        for i, (first, last, pts) in enumerate(tracks):
-            arr[i].first_sector, arr[i].last_sector, arr[i].pts_length = first, last, pts
+        for i, t in enumerate(tracks):
+            arr[i].first_sector, arr[i].last_sector, arr[i].pts_length = t[0], t[1], t[2]
+            arr[i].flags = t[3] if len(t) > 3 else 0
         return arr
 
     def decode_host(self, sectors, tracks):
@@ -182,6 +190,18 @@ class Engine:
         descs = self._descs(tracks)
         res = (TrackResult * len(tracks))()
         rc = self.lib.dvdagpu_decode_host(self.ctx, ctypes.c_void_p(ptr), n, len(tracks), descs, res)
+        if rc:
+            raise EngineError(self.lib.dvdagpu_last_error().decode())
+        return res
+
+    def decode_track_pipelined(self, sectors_ptr, n_sectors, track, pcm_ptr, pcm_capacity, part_sectors=0):
+        """One track from (pinned) host sectors into (pinned) host PCM with overlapped copies.
+        Returns the merged TrackResult."""
+        descs = self._descs([track])
+        res = TrackResult()
+        rc = self.lib.dvdagpu_decode_track_pipelined(self.ctx, ctypes.c_void_p(sectors_ptr), n_sectors, descs,
+                                                     part_sectors, ctypes.c_void_p(pcm_ptr), pcm_capacity,
+                                                     ctypes.byref(res))
         if rc:
             raise EngineError(self.lib.dvdagpu_last_error().decode())
         return res

@@ -51,7 +51,7 @@ def build_engine(force=False, verbose=False, ptxas_info=False):
         src = os.path.join(CSRC, cu)
         obj = os.path.join(OBJDIR, cu.replace(".cu", ".o"))
         if force or _newer(obj, [src] + headers):
-            flags = list(NVCC_FLAGS)
+            flags = list(NVCC_FLAGS) + os.environ.get("DVDA_NVCC_EXTRA", "").split()
             if ptxas_info:
                 flags += ["-Xptxas", "-v"]
             _run([_nvcc()] + flags + ["-c", src, "-o", obj], verbose)

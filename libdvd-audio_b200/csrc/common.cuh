@@ -36,10 +36,16 @@
 #define SEG_IRREGULAR 1u       // access-unit chain did not land on the next sync
 #define SEG_NEEDS_CARRY 2u     // FIR history of the previous segment is needed
 #define SEG_OVERFLOW 4u        // more frames than the tile has room for
+#define SEG_FALLBACK 8u        // the three-pass fast path gave up: decode with the complete decoder
+
+// TrackDev.cont / dvdagpu_track_desc.flags
+#define TRACK_CONT_PREV 1u
+#define TRACK_CONT_NEXT 2u
 
 struct TrackDev {
     // inputs
     uint32_t first_sector, last_sector, pts_length;
+    uint32_t cont;             // bit 0: continues a previous part, bit 1: is continued by a next part
     // results of track setup
     int32_t status, error_flags, codec;
     uint32_t g0_bps, g1_bps, g0_rate, g1_rate, assignment;
@@ -51,6 +57,9 @@ struct TrackDev {
     uint64_t es_start, es_end; // elementary-stream byte range [start, end)
     uint64_t es_cut;           // zero-yield packet rule: no access unit may end behind this
     uint32_t pk_open;          // last packet consumed while opening the reader
+    uint32_t pk_check;         // packets [pk_check, pk_check_end) are subject to the zero-yield rule
+    uint32_t pk_check_end;
+    uint32_t stopped;          // 1: ended before its natural end, 2: needs the previous part's FIR history
     uint32_t nss;              // substreams
     uint32_t au_nominal;       // expected frames per access unit (tile sizing only)
     uint32_t cand_lo, nseg;    // valid syncs after es_start, segments

@@ -61,7 +61,7 @@ struct DevBuf {
 };
 
 enum {
-    B_SECTORS, B_SEC_CNT, B_SEC_BAD, B_SEC_BASE, B_BAD_PREFIX,
+    B_SECTORS, B_SECTORS2, B_PCM2, B_SEC_CNT, B_SEC_BAD, B_SEC_BASE, B_BAD_PREFIX,
     B_PK_SECTOR, B_PK_OFF, B_PK_LEN, B_PK_CODEC, B_PK_PAD2, B_PK_PARAMS, B_PK_MLPLEN, B_PK_PCMF,
     B_PK_ES, B_PK_PF, B_PK_NONMLP, B_PK_NM_PREFIX, B_PK_STOP, B_PK_STOP_PREFIX, B_PK_YIELD,
     B_ES, B_SYNC_CNT_RAW, B_SYNC_CNT_VALID, B_SYNC_BASE_RAW, B_SYNC_BASE_VALID, B_RAW, B_VALID,
@@ -69,7 +69,7 @@ enum {
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
     B_SS_FLAGS, B_SS_FLAGS_PREV, B_FIR_TAIL,
     B_GROUPS, B_GRP_CELLS, B_CELL_BASE, B_GRP_CHUNKS, B_GRP_CHUNK_BASE,
-    B_DEC_WORK, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
+    B_DEC_WORK, B_AU_SNAP, B_FILT_SNAP, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
     B_COUNT
 };
 
@@ -77,10 +77,15 @@ struct dvdagpu_ctx {
     int device;
     cudaStream_t own_stream;
     cudaStream_t stream;
+    cudaStream_t h2d_stream, d2h_stream;      // copy engines of the pipelined path
+    cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
+    int pcm_slot;                             // which PCM buffer the next decode writes
     DevBuf buf[B_COUNT];
     cudaEvent_t ev[6];
     cudaEvent_t kev[8][2];
     bool kev_used[8];
+    cudaEvent_t fev[4];                       // fast path: before pass A, B, C, after C
+    bool fast_timed;
     dvdagpu_stats stats;
     uint64_t pcm_samples;
     std::vector<TrackDev> h_tracks;
@@ -156,8 +161,13 @@ extern "C" dvdagpu_ctx *dvdagpu_create(int device)
         return nullptr;
     }
     c->stream = c->own_stream;
+    c->pcm_slot = 0;
+    cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
+    for (auto &e : c->pev) { cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming); }
     for (auto &e : c->ev) cudaEventCreate(&e);
     for (auto &k : c->kev) { cudaEventCreate(&k[0]); cudaEventCreate(&k[1]); }
+    for (auto &e : c->fev) cudaEventCreate(&e);
     uint8_t pcm_tab[2][6][36], crc[256];
     build_pcm_tables(pcm_tab);
     build_crc8(crc);
@@ -173,6 +183,10 @@ extern "C" void dvdagpu_destroy(dvdagpu_ctx *c)
     for (auto &b : c->buf) b.release();
     for (auto &e : c->ev) cudaEventDestroy(e);
     for (auto &k : c->kev) { cudaEventDestroy(k[0]); cudaEventDestroy(k[1]); }
+    for (auto &e : c->fev) cudaEventDestroy(e);
+    for (auto &e : c->pev) { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
+    cudaStreamDestroy(c->h2d_stream);
+    cudaStreamDestroy(c->d2h_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -206,7 +220,7 @@ extern "C" const void *dvdagpu_pcm_device(dvdagpu_ctx *c, uint64_t *n_samples)
 {
     if (!c) return nullptr;
     if (n_samples) *n_samples = c->pcm_samples;
-    return c->buf[B_PCM].p;
+    return c->buf[c->pcm_slot ? B_PCM2 : B_PCM].p;
 }
 
 extern "C" int dvdagpu_fetch(dvdagpu_ctx *c, uint64_t offset, uint64_t count, int32_t *dst)
@@ -215,7 +229,7 @@ extern "C" int dvdagpu_fetch(dvdagpu_ctx *c, uint64_t offset, uint64_t count, in
     if (offset + count > c->pcm_samples) { dvdagpu_set_error("fetch beyond the decoded samples"); return -1; }
     if (!count) return 0;
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaMemcpyAsync(dst, c->buf[B_PCM].as<int32_t>() + offset, count * sizeof(int32_t),
+    CUDA_TRY(cudaMemcpyAsync(dst, c->buf[c->pcm_slot ? B_PCM2 : B_PCM].as<int32_t>() + offset, count * sizeof(int32_t),
                              cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
@@ -253,6 +267,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     const uint32_t n_sectors = (uint32_t)n_sectors64;
     memset(&c->stats, 0, sizeof c->stats);
     memset(c->kev_used, 0, sizeof c->kev_used);
+    c->fast_timed = false;
     CUDA_TRY(cudaEventRecord(c->ev[0], s));
 
     // tracks in sector order (the kernels binary-search them); results go back in caller order
@@ -266,6 +281,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         ht[i].first_sector = descs[order[i]].first_sector;
         ht[i].last_sector = descs[order[i]].last_sector;
         ht[i].pts_length = descs[order[i]].pts_length;
+        ht[i].cont = descs[order[i]].flags & 3u;
     }
 
     // ---------------- demux
@@ -439,18 +455,38 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
         uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
 
+        const bool use_fast = getenv("DVDAGPU_NO_FAST") == nullptr;
+        if (use_fast) {
+            ENSURE(B_AU_SNAP, naua * 2 * au_snap_bytes());
+            ENSURE(B_FILT_SNAP, naua * 2 * 4 * filt_snap_bytes());
+            m.au_snap = reinterpret_cast<AuSnap *>(c->buf[B_AU_SNAP].p);
+            m.filt_snap = reinterpret_cast<FiltSnap *>(c->buf[B_FILT_SNAP].p);
+        }
         for (int attempt = 0; attempt < 2; attempt++) {
-            TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, s));
+            CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
+            TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, d_status + 1, s));
             TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
             TRY(scan_u32_to_u64(grp_chunks, grp_chunk_base, ngroups, tmp, tmp_bytes, s));
             uint64_t cells = 0;
             TRY(read_back(c, cell_base + ngroups, &cells));
             TRY(read_back(c, grp_chunk_base + ngroups, &total_chunks));
+            TRY(read_back(c, d_status + 1, &m.max_au));
             ENSURE(B_TILES, (cells * DVDA_LANES + 64) * sizeof(int32_t));
             ENSURE(B_BYPASS, cells * DVDA_LANES + 64);
             m.tiles = c->buf[B_TILES].as<int32_t>(); m.bypass = c->buf[B_BYPASS].as<uint8_t>();
             TRY(launch_group_offsets(m.groups, ngroups, cell_base, s));
-            CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
+            m.fast = 0;
+            if (use_fast) {
+                // three passes with access-unit parallelism; what they give up on is flagged ...
+                // (start with every segment flagged: substreams with more than 4 channels
+                // are not visited by the fast path at all)
+                CUDA_TRY(cudaMemsetAsync(m.ss_flags, SEG_FALLBACK, (size_t)nseg * 2 * 4, s));
+                TRY(launch_mlp_fast(m, d_work, n_work, n_warps, c->fev, s));
+                c->fast_timed = true;
+                CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
+                m.fast = 1;
+            }
+            // ... and decoded by the complete single-pass decoder (everything, without the fast path)
             TIMED(DVDAGPU_K_MLP_DECODE, launch_mlp_decode(m, d_work, n_work, n_warps, s));
             CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
             TIMED(DVDAGPU_K_CARRY_FIX, launch_carry_fix(m, s));
@@ -477,6 +513,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
                     i, T.status, T.codec, T.error_flags, T.channels, T.pk_lo, T.pk_hi, T.pk_x, T.pk_open,
                     (unsigned long long)T.es_start, (unsigned long long)T.es_end, (unsigned long long)T.es_cut,
                     T.nss, T.nseg, T.err_seg, (unsigned long long)T.frames, T.truncated);
+            fprintf(stderr, "[dvdagpu]          cont=%u check=[%u,%u) stopped=%u\n", T.cont, T.pk_check, T.pk_check_end, T.stopped);
         }
         if (nseg) {
             std::vector<SegDev> hs(std::min<uint32_t>(nseg, 8));
@@ -496,8 +533,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         if (ht[i].status == 0) total_samples += ht[i].frames * ht[i].channels;
         any_pcm |= ht[i].status == 0 && ht[i].codec == 0;
     }
-    ENSURE(B_PCM, (total_samples + 64) * sizeof(int32_t));
-    m.pcm = c->buf[B_PCM].as<int32_t>();
+    const int pcm_buf = c->pcm_slot ? B_PCM2 : B_PCM;
+    ENSURE(pcm_buf, (total_samples + 64) * sizeof(int32_t));
+    m.pcm = c->buf[pcm_buf].as<int32_t>();
     c->pcm_samples = total_samples;
     CUDA_TRY(cudaMemcpyAsync(d_tracks, ht.data(), n_tracks * sizeof(TrackDev), cudaMemcpyHostToDevice, s));
     if (nseg && total_chunks) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, total_chunks, grp_chunk_base, s));
@@ -516,7 +554,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         R.error_flags = T.error_flags; R.codec = T.codec;
         R.group_0_bps = T.g0_bps; R.group_1_bps = T.g1_bps; R.group_0_rate = T.g0_rate; R.group_1_rate = T.g1_rate;
         R.channel_assignment = T.assignment; R.channels = T.channels; R.bits_per_sample = T.bits; R.sample_rate = T.rate;
-        R.frames = T.frames; R.pcm_offset = T.out_base; R.truncated = T.truncated;
+        R.frames = T.frames; R.pcm_offset = T.out_base; R.truncated = T.truncated; R.stopped = T.stopped;
         if (T.codec == 1) es_used += T.es_end - T.es_start;
     }
     float ms = 0;
@@ -527,6 +565,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); c->stats.total_ms = ms;
     for (int k = 0; k < 8; k++) {
         if (c->kev_used[k] && cudaEventElapsedTime(&ms, c->kev[k][0], c->kev[k][1]) == cudaSuccess) c->stats.kernel_ms[k] = ms;
+    }
+    if (c->fast_timed) {
+        for (int k = 0; k < 3; k++)
+            if (cudaEventElapsedTime(&ms, c->fev[k], c->fev[k + 1]) == cudaSuccess) c->stats.kernel_ms[DVDAGPU_K_MLP_HEADERS + k] = ms;
     }
     c->stats.launches = g_launch_count;
     c->stats.segments = nseg;
@@ -552,4 +594,124 @@ extern "C" int dvdagpu_decode_host(dvdagpu_ctx *c, const uint8_t *sectors, uint6
     ENSURE(B_SECTORS, n_sectors * DVDA_SECTOR + 256);
     CUDA_TRY(cudaMemcpyAsync(c->buf[B_SECTORS].p, sectors, n_sectors * DVDA_SECTOR, cudaMemcpyHostToDevice, c->stream));
     return decode_on_device(c, c->buf[B_SECTORS].as<uint8_t>(), n_sectors, n_tracks, tracks, results);
+}
+
+
+// ---- one long track, pipelined ----------------------------------------------------
+//
+// The track is decoded in parts of `part_sectors` sectors.  Each part is a
+// "track" of its own (DVDAGPU_PART_* flags): the cut lands on the first major
+// sync behind the part's last sector, exactly like the disc's own track
+// boundaries, so the parts' outputs concatenate to the whole track.  Upload of
+// part i+1 (copy engine, h2d_stream) and download of part i-1 (d2h_stream) run
+// while part i is being decoded; sector and PCM buffers are double-buffered, all
+// other buffers are reused because decodes are serial.
+
+static void add_stats(dvdagpu_stats &a, const dvdagpu_stats &b)
+{
+    a.demux_ms += b.demux_ms; a.index_ms += b.index_ms; a.decode_ms += b.decode_ms; a.output_ms += b.output_ms;
+    a.total_ms += b.total_ms; a.launches += b.launches; a.segments += b.segments; a.access_units += b.access_units;
+    a.es_bytes += b.es_bytes; a.samples += b.samples;
+    for (int k = 0; k < 12; k++) a.kernel_ms[k] += b.kernel_ms[k];
+}
+
+extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sectors, uint64_t n_sectors,
+                                              const dvdagpu_track_desc *track, uint32_t part_sectors,
+                                              int32_t *pcm_host, uint64_t pcm_capacity, dvdagpu_track_result *result)
+{
+    if (!c || !sectors || !track || !result || !pcm_host) { dvdagpu_set_error("null argument"); return -1; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!part_sectors) part_sectors = 24576;                    // 48 MiB of AOB per part
+    const uint64_t first = track->first_sector;
+    const uint64_t last = track->last_sector < n_sectors ? track->last_sector : n_sectors - 1;
+    const uint64_t margin = 64;
+    dvdagpu_stats total_stats;
+    memset(&total_stats, 0, sizeof total_stats);
+
+    bool fallback = first >= n_sectors || last < first || (last - first + 1) < 2ull * part_sectors;
+    uint64_t total_samples = 0, total_frames = 0;
+    dvdagpu_track_result merged;
+    memset(&merged, 0, sizeof merged);
+    if (!fallback) {
+        const uint32_t parts = (uint32_t)((last - first + 1 + part_sectors - 1) / part_sectors);
+        auto window = [&](uint32_t i, uint64_t &s0, uint64_t &len, uint64_t &e_rel) {
+            s0 = first + (uint64_t)i * part_sectors;
+            uint64_t e = s0 + part_sectors - 1;
+            if (e > last || i + 1 == parts) e = last;
+            uint64_t stop = (i + 1 == parts) ? n_sectors : e + 1 + margin;
+            if (stop > n_sectors) stop = n_sectors;
+            len = stop - s0;
+            e_rel = e - s0;
+        };
+        auto upload = [&](uint32_t i) -> int {
+            uint64_t s0, len, e_rel;
+            window(i, s0, len, e_rel);
+            const int slot = i & 1, buf = slot ? B_SECTORS2 : B_SECTORS;
+            ENSURE(buf, len * DVDA_SECTOR + 256);
+            if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->h2d_stream, c->pev[1][slot], 0));   // part i-2 decoded
+            CUDA_TRY(cudaMemcpyAsync(c->buf[buf].p, sectors + s0 * DVDA_SECTOR, len * DVDA_SECTOR,
+                                     cudaMemcpyHostToDevice, c->h2d_stream));
+            CUDA_TRY(cudaEventRecord(c->pev[0][slot], c->h2d_stream));
+            return 0;
+        };
+        TRY(upload(0));
+        for (uint32_t i = 0; i < parts && !fallback; i++) {
+            if (i + 1 < parts) TRY(upload(i + 1));
+            uint64_t s0, len, e_rel;
+            window(i, s0, len, e_rel);
+            const int slot = i & 1;
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->pev[0][slot], 0));
+            if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->pev[2][slot], 0));       // PCM slot downloaded
+            c->pcm_slot = slot;
+            dvdagpu_track_desc d = {0, (uint32_t)e_rel, track->pts_length,
+                                    (i ? (uint32_t)DVDAGPU_PART_CONTINUES_PREVIOUS : (track->flags & 1u)) |
+                                    (i + 1 < parts ? (uint32_t)DVDAGPU_PART_CONTINUED_BY_NEXT : (track->flags & 2u))};
+            dvdagpu_track_result r;
+            TRY(decode_on_device(c, c->buf[slot ? B_SECTORS2 : B_SECTORS].as<uint8_t>(), len, 1, &d, &r));
+            CUDA_TRY(cudaEventRecord(c->pev[1][slot], c->stream));
+            add_stats(total_stats, c->stats);
+            // anything the parts cannot express: decode in one piece instead
+            if (r.status != 0 || r.codec != 1 || r.stopped == 2 || (r.truncated && i + 1 < parts) ||
+                (i && (r.channels != merged.channels || r.sample_rate != merged.sample_rate))) { fallback = true; break; }
+            if (i == 0) merged = r;
+            const uint64_t n = r.frames * r.channels;
+            if (total_samples + n > pcm_capacity) {
+                cudaStreamSynchronize(c->d2h_stream);
+                dvdagpu_set_error("PCM buffer too small");
+                result->frames = 0;
+                return 3;
+            }
+            CUDA_TRY(cudaStreamWaitEvent(c->d2h_stream, c->pev[1][slot], 0));
+            if (n) CUDA_TRY(cudaMemcpyAsync(pcm_host + total_samples, c->buf[slot ? B_PCM2 : B_PCM].as<int32_t>() + r.pcm_offset,
+                                            n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
+            CUDA_TRY(cudaEventRecord(c->pev[2][slot], c->d2h_stream));
+            total_samples += n;
+            total_frames += r.frames;
+            merged.error_flags |= r.error_flags;
+            merged.truncated = r.truncated;
+            if (r.stopped == 1) { merged.stopped = 1; break; }      // the track ended inside this part
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
+        CUDA_TRY(cudaStreamSynchronize(c->h2d_stream));
+    }
+    if (fallback) {
+        c->pcm_slot = 0;
+        dvdagpu_track_result r;
+        TRY(dvdagpu_decode_host(c, sectors, n_sectors, 1, track, &r));
+        add_stats(total_stats, c->stats);
+        *result = r;
+        if (r.status == 0) {
+            const uint64_t n = r.frames * r.channels;
+            if (n > pcm_capacity) { dvdagpu_set_error("PCM buffer too small"); return 3; }
+            TRY(dvdagpu_fetch(c, r.pcm_offset, n, pcm_host));
+        }
+        c->stats = total_stats;
+        return 0;
+    }
+    merged.frames = total_frames;
+    merged.pcm_offset = 0;
+    *result = merged;
+    c->stats = total_stats;
+    c->stats.samples = total_samples;
+    return 0;
 }

@@ -15,6 +15,9 @@ struct PacketTable {
     uint32_t *pcm_frames;  // PCM: whole frames in this packet
 };
 
+struct AuSnap;      // mlp_decode.cu: what pass B needs to entropy-decode one access unit
+struct FiltSnap;    // mlp_decode.cu: filter parameters of one channel for one access unit
+
 // everything the MLP kernels need to find their data
 struct MlpTables {
     const uint8_t *es;             // elementary stream (padded with DVDA_ES_PAD zero bytes)
@@ -39,6 +42,10 @@ struct MlpTables {
     int32_t *tiles;
     uint8_t *bypass;
     int32_t *pcm;
+    AuSnap *au_snap;               // [2][nau]
+    FiltSnap *filt_snap;           // [2][nau][4]
+    uint32_t fast;                 // 1: the complete decoder only takes segments flagged SEG_FALLBACK
+    uint32_t max_au;               // largest access-unit count of a segment
 };
 
 // demux.cu
@@ -80,7 +87,7 @@ int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t nseg, const TrackD
 int launch_yield(MlpTables m, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
                  uint8_t *pk_yield, cudaStream_t s);
 int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_grp_base, const SegDev *segs,
-                       GroupDev *groups, uint32_t ngroups, uint32_t *grp_cells, uint32_t *grp_chunks, cudaStream_t s);
+                       GroupDev *groups, uint32_t ngroups, uint32_t *grp_cells, uint32_t *grp_chunks, uint32_t *max_au, cudaStream_t s);
 int launch_group_offsets(GroupDev *groups, uint32_t ngroups, const uint64_t *cell_base, cudaStream_t s);
 
 // mlp_decode.cu
@@ -89,6 +96,11 @@ int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s);
 struct DecWork { uint32_t warp0, track, k, pad; };
 int launch_mlp_decode(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s);
 int launch_carry_fix(MlpTables m, cudaStream_t s);
+size_t au_snap_bytes();
+size_t filt_snap_bytes();
+// fast path: pass A (headers), B (entropy, one lane per access unit), C (filters, one lane per channel)
+int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
+                    cudaEvent_t ev[4], cudaStream_t s);
 int launch_seg_finalize(MlpTables m, uint32_t *seg_frames, uint32_t *status, cudaStream_t s);
 int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, cudaStream_t s);
 int launch_rematrix(MlpTables m, uint64_t total_chunks, const uint64_t *grp_chunk_base, cudaStream_t s);

@@ -165,6 +165,9 @@ int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
 //   * the hot loop tops the 64-bit window up without branching (the load from
 //     the ring is unconditional, the merge is predicated).
 // Headers use the same reader through the checked (cold) entry points.
+#ifndef DVDA_UNROLL
+#define DVDA_UNROLL 8
+#endif
 #define RING_SLOTS 32                 // 16-byte slots per lane: 512 bytes
 #define CHUNK_WORDS 16                // 64 bytes per cp.async group
 #define RING_WORDS (RING_SLOTS * 4)
@@ -691,6 +694,7 @@ __device__ __forceinline__ uint32_t decode_block_fast(const MlpTables &m, const 
     // the word fetched ahead
     const uint32_t need8 = (8 * (NCH * 33 + 6) + 31) / 32 + 2;
     uint32_t i = 0;
+#if DVDA_UNROLL == 8
     for (; i + 8 <= n; i += 8) {
         rd_prefetch(b, need8);
         rd_hot_begin(b);
@@ -698,6 +702,24 @@ __device__ __forceinline__ uint32_t decode_block_fast(const MlpTables &m, const 
         DVDA_FRAME(4) DVDA_FRAME(5) DVDA_FRAME(6) DVDA_FRAME(7)
         if ((bad & 0x8000) || rd_pos(b) > end_bits) return 0;
     }
+#else
+    // half the code: four frames with static rotation, then swap the register halves
+    for (; i + 4 <= n; i += 4) {
+        rd_prefetch(b, need8);
+        rd_hot_begin(b);
+        DVDA_FRAME(0) DVDA_FRAME(1) DVDA_FRAME(2) DVDA_FRAME(3)
+#pragma unroll
+        for (int cc = 0; cc < NCH; cc++) {
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int32_t tf = H.fh[cc][a], ti = H.ih[cc][a];
+                H.fh[cc][a] = H.fh[cc][a + 4]; H.ih[cc][a] = H.ih[cc][a + 4];
+                H.fh[cc][a + 4] = tf; H.ih[cc][a + 4] = ti;
+            }
+        }
+        if ((bad & 0x8000) || rd_pos(b) > end_bits) return 0;
+    }
+#endif
     // leftover frames (block size not a multiple of 8): rotate the registers for real
     for (; i < n; i++) {
         rd_prefetch(b, need8);
@@ -894,7 +916,301 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
     if (stop_au != 0xFFFFFFFFu) atomicMin(&S.err_au, stop_au);
 }
 
+// =============================================================================
+// Fast path: three passes with access-unit parallelism.
+//
+// Decoding a segment in one thread (decode_segment above) is bound by the
+// latency of one lane's dependent chain: the time does not shrink with the
+// amount of work.  What actually chains across access units is small:
+//   * decoding parameters inherit        -> pass A walks the *headers* of a
+//     segment (first block of each AU; the AU positions are known from the
+//     length chain, no residual has to be decoded to find them) and writes a
+//     snapshot of what each AU needs;
+//   * the entropy decode of an AU needs only that snapshot
+//                                        -> pass B: one lane per (segment, AU),
+//     16x more parallelism, residuals go to the tile;
+//   * the prediction filters chain over frames but not over channels
+//                                        -> pass C: one lane per (segment,
+//     channel) runs the recurrence over the residuals in the tile, in place.
+// The passes assume the common shape: at most 4 channels per substream,
+// parameters only in the first block of an AU, AUs of the nominal length, no
+// damage, no FIR history needed from the previous segment.  Anything else sets
+// SEG_FALLBACK and the segment is decoded again by decode_segment (and
+// k_carry_fix), which is the complete implementation.
+// =============================================================================
+
+struct ChanSnap { int32_t sho; uint8_t cb, lsb_bits, q, shift; };
+struct AuSnap {
+    uint64_t bit0;          // absolute bit position (in the ES) of the first residual bit
+    uint64_t bit_end;       // absolute bit position of the end of the substream data
+    uint16_t block_size;
+    uint8_t want, valid;
+    uint8_t min_ch, nch, pad0, pad1;
+    ChanSnap ch[4];
+};
+struct FiltSnap {
+    int16_t cf[8], ci[8];   // coefficients, zero beyond the orders
+    int32_t ist[8];         // IIR history to install (age order) when ist_new
+    uint8_t shift, q, ist_new, pad;
+};
+
+// noise generator advanced by n frames
+__device__ __forceinline__ uint32_t noise_advance(uint32_t seed, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; i++) seed = noise_step(seed);
+    return seed;
+}
+
+// ---- pass A: headers ------------------------------------------------------------
+template <int NCH>
+__device__ __forceinline__ void headers_segment(const MlpTables &m, const DecodeJob &job, uint32_t ring)
+{
+    SegDev &S = m.segs[job.seg];
+    const TrackDev &T = m.tracks[S.track];
+    const bool governing = job.k + 1 == T.nss;
+    const uint32_t nominal = T.au_nominal;
+
+    SubState s;
+    memset(&s, 0, sizeof s);
+    s.flags = 0xFF;
+    Rd b;
+    rd_init(b, m.es, ring);
+    AuSnap *snaps = m.au_snap + (uint64_t)job.k * m.nau;
+    FiltSnap *fsnaps = m.filt_snap + (uint64_t)job.k * m.nau * 4;
+
+    uint32_t frames = 0, flags = 0, pset = 0xFFFFFFFFu;
+    bool fallback = false;
+    uint64_t pos = S.n_au ? m.au_pos[S.au_base] : 0;
+    for (uint32_t a = 0; a < S.n_au; a++) {
+        const uint32_t A = S.au_base + a;
+        snaps[A].valid = 0;
+        const uint32_t e = m.au_err[A];
+        const AuLayout L = au_layout_rd(b, pos, T);
+        const uint64_t au_pos = pos;
+        pos += L.total;
+        // damage, dropped AUs and the end-of-track rules are the complete decoder's business
+        if (au_pos + L.total > T.es_cut || e) { fallback = true; break; }
+        const uint32_t start = job.k ? L.end[0] : 0;
+        const uint32_t len = L.end[job.k] - start - (L.chk0 ? 2 : 0);
+        const uint64_t data = au_pos + L.data0 + start;
+        rd_seat(b, data);
+        rd_skip(b, (uint32_t)(data & 3) * 8);
+        const uint32_t end_bits = (uint32_t)(data & 3) * 8 + len * 8;
+        bool changed;
+        if (!block_header(b, s, changed) || rd_pos(b) > end_bits) { fallback = true; break; }
+        if ((uint32_t)(s.max_ch - s.min_ch + 1) != NCH || s.block_size > nominal || nominal % s.block_size) { fallback = true; break; }
+
+        AuSnap sn;
+        const uint64_t origin = (data & ~3ull) * 8;
+        sn.bit0 = origin + rd_pos(b);
+        sn.bit_end = origin + end_bits;
+        sn.block_size = s.block_size;
+        sn.min_ch = s.min_ch; sn.nch = NCH; sn.pad0 = sn.pad1 = 0;
+        uint32_t want = 0;
+        for (uint32_t k = 0; k < s.matrix_len; k++) want |= (uint32_t)(s.mat_bypass[k] != 0) << k;
+        sn.want = (uint8_t)want;
+        uint32_t cflags = 0;
+#pragma unroll
+        for (int cc = 0; cc < NCH; cc++) {
+            ChanState &C = s.ch[s.min_ch + cc];
+            const uint32_t q = s.q[s.min_ch + cc];
+            uint32_t lsb_bits = 0, shift = 0;
+            int32_t sho = 0;
+            if (!channel_setup(s, C, q, job.exact_history, cflags, lsb_bits, sho, shift)) { fallback = true; break; }
+            sn.ch[cc].sho = sho; sn.ch[cc].cb = C.codebook; sn.ch[cc].lsb_bits = (uint8_t)lsb_bits;
+            sn.ch[cc].q = (uint8_t)q; sn.ch[cc].shift = (uint8_t)shift;
+            FiltSnap fs;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                fs.cf[j] = j < C.fir_order ? (int16_t)C.fir_c[j] : (int16_t)0;
+                fs.ci[j] = j < C.iir_order ? (int16_t)C.iir_c[j] : (int16_t)0;
+                fs.ist[j] = (C.ist_new && j < C.ilen) ? C.ist[(C.ihead - 1 - j) & 7] : 0;
+            }
+            fs.shift = (uint8_t)shift; fs.q = (uint8_t)q; fs.ist_new = C.ist_new; fs.pad = 0;
+            fsnaps[(uint64_t)A * 4 + cc] = fs;
+            C.ist_new = 0;
+            C.flen = 8; C.ilen = 8;
+        }
+        if (fallback || (cflags & SEG_NEEDS_CARRY)) { fallback = true; break; }
+        sn.valid = 1;
+        snaps[A] = sn;
+
+        const uint32_t au_frame0 = frames;
+        frames += nominal;
+        m.au_frames_ss[job.k * m.nau + A] = nominal;
+        if (governing) {
+            if (s.dirty || pset == 0xFFFFFFFFu) {
+                ParamSet P;
+                memset(&P, 0, sizeof P);
+                P.matrix_len = s.matrix_len; P.mmc = s.mmc; P.noise_shift = s.noise_shift;
+                uint32_t uses = 0;
+                for (uint32_t k = 0; k < s.matrix_len; k++) {
+                    P.out_ch[k] = s.mat_out[k];
+                    for (int c = 0; c < DVDA_MAX_CH; c++) P.coeff[k][c] = s.coeff[k][c];
+                    uses |= (s.coeff[k][s.mmc + 1] != 0) | (s.coeff[k][s.mmc + 2] != 0);
+                }
+                P.uses_noise = uses;
+                for (int c = 0; c < DVDA_MAX_CH; c++) { P.q[c] = s.q[c]; P.out_shift[c] = s.out_shift[c]; }
+                m.psets[A] = P;
+                pset = A;
+                s.dirty = 0;
+            }
+            AuDev R = {au_frame0, nominal, s.seed, pset};
+            m.au[A] = R;
+            s.seed = noise_advance(s.seed, nominal);
+        }
+    }
+    cp_wait<0>();
+    if (fallback) flags |= SEG_FALLBACK;
+    m.ss_flags[job.k * m.nseg + job.seg] = flags;
+    if (job.k == 0) S.frames = frames;
+}
+
+// ---- pass B: entropy decode of one access unit -------------------------------------
+template <int NCH>
+__device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &job, uint32_t a,
+                                           const uint16_t (*lut)[512], uint32_t ring)
+{
+    const SegDev &S = m.segs[job.seg];
+    const TrackDev &T = m.tracks[S.track];
+    const GroupDev &G = m.groups[T.grp_base + (job.seg - T.seg_base) / DVDA_LANES];
+    const bool governing = job.k + 1 == T.nss;
+    const uint32_t nch = T.channels, nominal = T.au_nominal;
+    const uint32_t A = S.au_base + a;
+    // pass A gave up on the segment: its later snapshots were never written
+    if (m.ss_flags[job.k * m.nseg + job.seg] & SEG_FALLBACK) return;
+    const AuSnap sn = m.au_snap[(uint64_t)job.k * m.nau + A];
+    if (!sn.valid) return;
+
+    Rd b;
+    rd_init(b, m.es, ring);
+    rd_seat(b, (sn.bit0 >> 5) << 2);
+    rd_skip(b, (uint32_t)(sn.bit0 & 31));
+    const uint32_t end_bits = (uint32_t)(sn.bit_end - ((sn.bit0 >> 5) << 5));
+
+    int32_t sho[NCH];
+    uint32_t lsb_bits[NCH], cb[NCH], q[NCH];
+#pragma unroll
+    for (int cc = 0; cc < NCH; cc++) { sho[cc] = sn.ch[cc].sho; lsb_bits[cc] = sn.ch[cc].lsb_bits; cb[cc] = sn.ch[cc].cb; q[cc] = sn.ch[cc].q; }
+    const uint32_t want = sn.want, bs = sn.block_size, cap = G.cap;
+    const uint32_t frame0 = a * nominal;
+    int32_t *tile = m.tiles + G.tile_off + job.lane + ((uint64_t)frame0 * nch + sn.min_ch) * DVDA_LANES;
+    uint8_t *byp = m.bypass + G.byp_off + job.lane + (uint64_t)frame0 * DVDA_LANES;
+    const uint32_t tile_step = nch * DVDA_LANES;
+    const uint32_t need4 = (4 * (NCH * 33 + 6) + 31) / 32 + 2;
+    uint32_t f = frame0, done = 0, bad = 0, flags = 0;
+
+#define DVDA_EFRAME()                                                                              \
+    {                                                                                              \
+        const bool room = f < cap;                                                                 \
+        flags |= room ? 0u : SEG_OVERFLOW;                                                         \
+        if (want) {                                                                                \
+            const uint32_t bmask = bypass_bits(b, want);                                           \
+            rd_hot_begin(b);                                                                       \
+            if (governing && room) *byp = (uint8_t)bmask;                                          \
+        } else if (governing && room) *byp = 0;                                                    \
+        _Pragma("unroll") for (int cc = 0; cc < NCH; cc++) {                                       \
+            rd_top_up(b);                                                                          \
+            const uint32_t e = lut[cb[cc]][(uint32_t)(b.win >> 55)];                               \
+            bad |= e;                                                                              \
+            const uint32_t hl = (e >> 8) & 15;                                                     \
+            const int32_t msb = e & 0xFF;                                                          \
+            b.win <<= hl;                                                                          \
+            const int32_t lsb = (int32_t)(uint32_t)((b.win >> 1) >> (63 - lsb_bits[cc]));          \
+            b.win <<= lsb_bits[cc];                                                                \
+            b.avail -= hl + lsb_bits[cc];                                                          \
+            const int32_t res = (int32_t)((uint32_t)((msb << lsb_bits[cc]) + lsb + sho[cc]) << q[cc]); \
+            if (room) tile[cc * DVDA_LANES] = res;                                                 \
+        }                                                                                          \
+        f++; tile += tile_step; byp += DVDA_LANES;                                                 \
+    }
+
+    bool ok = true;
+    while (ok) {
+        // one block of bs frames (bs divides the nominal AU length, bs >= 8)
+        uint32_t i = 0;
+        for (; i + 4 <= bs; i += 4) {
+            rd_prefetch(b, need4);
+            rd_hot_begin(b);
+            DVDA_EFRAME() DVDA_EFRAME() DVDA_EFRAME() DVDA_EFRAME()
+        }
+        for (; i < bs; i++) {
+            rd_prefetch(b, need4);
+            rd_hot_begin(b);
+            DVDA_EFRAME()
+        }
+        done += bs;
+        if ((bad & 0x8000) || rd_pos(b) > end_bits) { ok = false; break; }
+        const uint32_t last = rd_get(b, 1);
+        if (rd_pos(b) > end_bits) { ok = false; break; }
+        if (last) break;
+        // another block: it must not bring parameters of its own, and must fit the AU
+        if (done + bs > nominal || rd_get(b, 1)) { ok = false; break; }
+    }
+#undef DVDA_EFRAME
+    cp_wait<0>();
+    if (!ok || done != nominal) flags |= SEG_FALLBACK;
+    if (flags) atomicOr(&m.ss_flags[job.k * m.nseg + job.seg], flags);
+}
+
+// ---- pass C: prediction filters of one channel over a whole segment -------------------
+__device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint32_t seg, uint32_t k, uint32_t cc, uint32_t lane)
+{
+    const SegDev &S = m.segs[seg];
+    const TrackDev &T = m.tracks[S.track];
+    if ((m.ss_flags[seg] | (T.nss == 2 ? m.ss_flags[m.nseg + seg] : 0)) & SEG_FALLBACK) return;
+    const GroupDev &G = m.groups[T.grp_base + (seg - T.seg_base) / DVDA_LANES];
+    const uint32_t nch = T.channels, nominal = T.au_nominal, cap = G.cap;
+    const AuSnap *snaps = m.au_snap + (uint64_t)k * m.nau;
+    const FiltSnap *fsnaps = m.filt_snap + (uint64_t)k * m.nau * 4;
+    if (!S.n_au) return;
+    const uint32_t c = snaps[S.au_base].min_ch + cc;
+    int32_t fh[8], ih[8], cf[8], ci[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { fh[j] = 0; ih[j] = 0; cf[j] = 0; ci[j] = 0; }
+    int32_t *tile = m.tiles + G.tile_off + lane + (uint64_t)c * DVDA_LANES;
+    const uint32_t tile_step = nch * DVDA_LANES;
+    uint32_t f = 0;
+    for (uint32_t a = 0; a < S.n_au; a++) {
+        const FiltSnap fs = fsnaps[(uint64_t)(S.au_base + a) * 4 + cc];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
+        const uint32_t shift = fs.shift, q = fs.q;
+        // the nominal AU length is a multiple of 8 (40 * rate multiple)
+        for (uint32_t i = 0; i < nominal; i += 8) {
+            int32_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = (f + j < cap) ? tile[(uint64_t)j * tile_step] : 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                long long s0 = 0, s1 = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    s0 += (long long)cf[t] * fh[(t - j) & 7];
+                    s1 += (long long)ci[t] * ih[(t - j) & 7];
+                }
+                const int32_t ssum = (int32_t)((s0 + s1) >> shift);
+                int32_t v = (int32_t)((uint32_t)ssum + (uint32_t)r[j]);
+                v = (v >> q) << q;
+                fh[(7 - j) & 7] = v;
+                ih[(7 - j) & 7] = (int32_t)((uint32_t)v - (uint32_t)ssum);
+                r[j] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (f + j < cap) tile[(uint64_t)j * tile_step] = r[j];
+            f += 8;
+            tile += (uint64_t)8 * tile_step;
+        }
+    }
+    int32_t *tail = m.fir_tail + ((uint64_t)k * m.nseg + seg) * (DVDA_MAX_CH * 8);
+#pragma unroll
+    for (int j = 0; j < 8; j++) tail[c * 8 + j] = fh[7 - j];
+}
+
 #define DEC_WARPS 4
+#ifndef DEC_MIN_BLOCKS
+#define DEC_MIN_BLOCKS 3
+#endif
 #define DEC_SMEM_BYTES (DEC_WARPS * RING_SLOTS * DVDA_LANES * 16 + 4 * 512 * 2)
 
 // One warp per (group, substream); lane = segment of the group.  One
@@ -903,7 +1219,7 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
 // 4-channel one.  Each instantiation gets a dense list of exactly its warps
 // (DecWork rows: a run of warps = the groups of one track's substream).
 template <int NCH>
-__global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_decode(MlpTables m, const DecWork *__restrict__ work,
+__global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_BLOCKS) k_mlp_decode(MlpTables m, const DecWork *__restrict__ work,
                                                                uint32_t n_work, uint32_t n_warps)
 {
     extern __shared__ uint4 dyn_smem[];
@@ -929,9 +1245,119 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_decode(MlpTables m, cons
     job.seg = G.seg0 + lane;
     job.k = W.k;
     job.lane = lane;
-    job.exact_history = (job.seg == T.seg_base);      // a track starts with empty histories
+    // a track starts with empty histories; a continued part does not
+    job.exact_history = (job.seg == T.seg_base) && !(T.cont & TRACK_CONT_PREV);
+    if (m.fast) {
+        // after the three-pass fast path: only what it gave up on (any substream of the segment)
+        const uint32_t f = m.ss_flags_prev[job.seg] | (T.nss == 2 ? m.ss_flags_prev[m.nseg + job.seg] : 0);
+        if (!(f & SEG_FALLBACK)) return;
+    }
     const uint32_t rs = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]);
     decode_segment<NCH>(m, job, lut, rs, nullptr);
+}
+
+// ---- fast path kernels ------------------------------------------------------------
+
+__device__ __forceinline__ bool fast_job(const MlpTables &m, const DecWork *work, uint32_t n_work, uint32_t warp,
+                                         uint32_t lane, DecodeJob &job)
+{
+    uint32_t lo = 0, hi = n_work;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
+    }
+    const DecWork W = work[lo];
+    const TrackDev &T = m.tracks[W.track];
+    const GroupDev &G = m.groups[T.grp_base + (warp - W.warp0)];
+    if (lane >= G.nseg) return false;
+    job.seg = G.seg0 + lane;
+    job.k = W.k;
+    job.lane = lane;
+    job.exact_history = (job.seg == T.seg_base) && !(T.cont & TRACK_CONT_PREV);
+    return true;
+}
+
+// pass A: one warp per (group, substream), lane = segment
+template <int NCH>
+__global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_headers(MlpTables m, const DecWork *__restrict__ work,
+                                                                uint32_t n_work, uint32_t n_warps)
+{
+    extern __shared__ uint4 dyn_smem[];
+    uint4 (*ring)[RING_SLOTS][DVDA_LANES] = reinterpret_cast<uint4 (*)[RING_SLOTS][DVDA_LANES]>(dyn_smem);
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * DEC_WARPS + wib;
+    if (warp >= n_warps) return;
+    DecodeJob job;
+    if (!fast_job(m, work, n_work, warp, lane, job)) return;
+    headers_segment<NCH>(m, job, (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]));
+}
+
+// pass B: one warp per (group, substream, access unit index), lane = segment
+template <int NCH>
+__global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_entropy(MlpTables m, const DecWork *__restrict__ work,
+                                                                uint32_t n_work, uint32_t n_warps)
+{
+    extern __shared__ uint4 dyn_smem[];
+    uint4 (*ring)[RING_SLOTS][DVDA_LANES] = reinterpret_cast<uint4 (*)[RING_SLOTS][DVDA_LANES]>(dyn_smem);
+    uint16_t (*lut)[512] = reinterpret_cast<uint16_t (*)[512]>(dyn_smem + DEC_WARPS * RING_SLOTS * DVDA_LANES);
+    for (uint32_t i = threadIdx.x; i < 4 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry(i >> 9, i & 511);
+    __syncthreads();
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * DEC_WARPS + wib;
+    const uint32_t a = blockIdx.y;
+    if (warp >= n_warps) return;
+    DecodeJob job;
+    if (!fast_job(m, work, n_work, warp, lane, job)) return;
+    if (a >= m.segs[job.seg].n_au) return;
+    entropy_au<NCH>(m, job, a, lut, (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]));
+}
+
+// pass C: one warp per (group, substream, channel of the substream), lane = segment
+template <int NCH>
+__global__ void __launch_bounds__(128) k_mlp_filter(MlpTables m, const DecWork *__restrict__ work,
+                                                    uint32_t n_work, uint32_t n_warps)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w >= n_warps * NCH) return;
+    DecodeJob job;
+    if (!fast_job(m, work, n_work, w / NCH, lane, job)) return;
+    filter_channel_segment(m, job.seg, job.k, w % NCH, lane);
+}
+
+size_t au_snap_bytes() { return sizeof(AuSnap); }
+size_t filt_snap_bytes() { return sizeof(FiltSnap); }
+
+template <int NCH>
+static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
+{
+    if (!n_warps) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_mlp_headers<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_mlp_entropy<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES));
+        attr_set = true;
+    }
+    const uint32_t blocks = div_up_u32(n_warps, DEC_WARPS);
+    if (pass == 0) LAUNCH(k_mlp_headers<NCH>, blocks, DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
+    else if (pass == 1) LAUNCH(k_mlp_entropy<NCH>, dim3(blocks, m.max_au ? m.max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
+    else LAUNCH(k_mlp_filter<NCH>, div_up_u32((uint64_t)n_warps * NCH, 4), 128, 0, s, m, work, n_work, n_warps);
+    return 0;
+}
+
+int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
+                    cudaEvent_t ev[4], cudaStream_t s)
+{
+    for (int pass = 0; pass < 3; pass++) {
+        CUDA_TRY(cudaEventRecord(ev[pass], s));
+        if (launch_fast_pass<1>(pass, m, work[1], n_work[1], n_warps[1], s)) return -1;
+        if (launch_fast_pass<2>(pass, m, work[2], n_work[2], n_warps[2], s)) return -1;
+        if (launch_fast_pass<3>(pass, m, work[3], n_work[3], n_warps[3], s)) return -1;
+        if (launch_fast_pass<4>(pass, m, work[4], n_work[4], n_warps[4], s)) return -1;
+    }
+    CUDA_TRY(cudaEventRecord(ev[3], s));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 template <int NCH>
@@ -980,6 +1406,11 @@ __global__ void __launch_bounds__(FIX_THREADS) k_carry_fix(MlpTables m)
     // run head: predecessor (same track) is not waiting for a carry itself
     if (seg > T.seg_base && (fl[seg - 1] & SEG_NEEDS_CARRY)) return;
     const uint32_t track_end = T.seg_base + T.nseg;
+    if (seg == T.seg_base && (T.cont & TRACK_CONT_PREV)) {
+        // the history lives in a part decoded elsewhere: the caller has to decode the parts together
+        m.tracks[m.segs[seg].track].stopped = 2;
+        return;
+    }
     const uint32_t rs = (uint32_t)__cvta_generic_to_shared(&ring[0][threadIdx.x & 31]);
     for (uint32_t s = seg; s < track_end && (fl[s] & SEG_NEEDS_CARRY); s++) {
         DecodeJob job;
@@ -1029,6 +1460,7 @@ __global__ void k_seg_finalize(MlpTables m, uint32_t *__restrict__ seg_frames, u
     S.frames = frames;
     seg_frames[i] = frames;
     if (stop != 0xFFFFFFFFu) {
+        atomicMax(&T.stopped, 1u);
         atomicMin(&T.err_seg, i - T.seg_base);
         if (err) atomicOr((unsigned int *)&T.error_flags, err);
     }

@@ -155,6 +155,8 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
     T.pk_lo = T.pk_hi = T.pk_x = T.pcm_pk_end = 0;
     T.es_start = T.es_end = T.es_cut = 0;
     T.truncated = 0;
+    T.stopped = 0;
+    T.pk_open = T.pk_check = T.pk_check_end = 0;
     do {
         if (T.first_sector >= a.n_sectors) break;              // aob_reader_seek fails (aob.c:181-199)
         // a broken packet chain ends the stream for good (packet.c:60-116)
@@ -209,7 +211,10 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
             const uint64_t es_avail = a.pk_es[T.pk_hi];
             const uint64_t es_lo = a.pk_es[T.pk_lo];
             const uint32_t ci = lower_bound_dev(a.raw, a.n_raw, es_lo);
-            if (ci >= a.n_raw || a.raw[ci] + 18 > es_avail) break;   // reference asserts
+            if (ci >= a.n_raw || a.raw[ci] + 18 > es_avail) {
+                if (T.cont & TRACK_CONT_PREV) { T.status = 0; T.codec = 1; T.truncated = 1; }   // an empty part
+                break;                                               // reference asserts
+            }
             const uint64_t p = a.raw[ci];
             T.es_start = p;
             const uint32_t b8 = ld_u8(a.es + p + 8), b9 = ld_u8(a.es + p + 9);
@@ -226,7 +231,16 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
             T.au_nominal = 40u << (rc > 2 ? 0 : rc);
             // the packet holding byte p + 17 is the last one consumed while opening
             T.pk_open = upper_bound_dev(a.pk_es, a.np + 1, p + 17) - 1;
+            // a continued part whose range holds no sync at all is empty: the sync it found
+            // lies in (and will be found again by) a later part
+            const bool empty_part = (T.cont & TRACK_CONT_PREV) && pk_x < T.pk_hi && p >= a.pk_es[pk_x];
             if (pk_x < T.pk_open + 1) pk_x = T.pk_open + 1;
+            // zero-yield rule: a real track start exempts the packets consumed while opening;
+            // a continued part checks from its first packet on, unless the previous part's
+            // last access unit ended inside that packet (then the packet did yield)
+            T.pk_check = T.pk_open + 1;
+            if (T.cont & TRACK_CONT_PREV)
+                T.pk_check = p > es_lo ? upper_bound_dev(a.pk_es, a.np + 1, p - 1) : T.pk_lo;
             // end of the track
             uint64_t es_end = es_avail;
             if (pk_x < T.pk_hi) {
@@ -236,17 +250,23 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
                 } else {
                     const uint32_t cj = lower_bound_dev(a.raw, a.n_raw, P0);
                     if (cj < a.n_raw && a.raw[cj] + 8 <= es_avail) es_end = a.raw[cj];
+                    else if (T.cont & TRACK_CONT_NEXT) { es_end = es_avail; T.truncated = 1; }   // the parts behind are empty
                     else { es_end = (es_avail >= P0 + 8) ? es_avail - 7 : P0; T.truncated = 1; }
                 }
             } else {
                 T.truncated = 1;                               // no packet behind last_sector in the buffer
             }
             // a non-MLP audio packet met while decoding ends the stream (dvd-audio.c:1203-1208)
-            const uint32_t nm = first_flagged(a.pk_nonmlp, a.np, T.pk_open + 1);
+            const uint32_t nm = first_flagged(a.pk_nonmlp, a.np, (T.cont & TRACK_CONT_PREV) ? T.pk_lo : T.pk_open + 1);
             if (nm < pk_x && nm < T.pk_hi && a.pk_es[nm] < es_end) es_end = a.pk_es[nm];
             if (es_end < p) es_end = p;
             T.es_end = es_end;
+            // a part that is continued also answers for the packets its last access units end in
+            T.pk_check_end = pk_x;
+            if ((T.cont & TRACK_CONT_NEXT) && pk_x < T.pk_hi && es_end > a.pk_es[pk_x])
+                T.pk_check_end = min(T.pk_hi, upper_bound_dev(a.pk_es, a.np + 1, es_end - 1));
             T.es_cut = es_end;
+            if (empty_part) T.es_end = T.es_cut = p;
             if (T.nss != 1 && T.nss != 2) {
                 // the first access unit is not a usable major sync: nothing decodes
                 T.error_flags |= ERR_SYNTAX;
@@ -326,8 +346,10 @@ __global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ 
         S.n_au = n;
         const TrackDev &T = tracks[S.track];
         const bool last = (i + 1 - T.seg_base) == T.nseg;
-        // every segment but the last must land exactly on the next one
-        if (stalled || (!last && pos != limit)) S.flags |= SEG_IRREGULAR;
+        // every segment but the last must land exactly on the next one; so must the last
+        // one of a part that is continued (the cut has to be a real access-unit boundary)
+        const bool must_land = !last || ((T.cont & TRACK_CONT_NEXT) && !T.truncated);
+        if (stalled || (must_land && pos != limit)) S.flags |= SEG_IRREGULAR;
     }
 }
 
@@ -363,13 +385,17 @@ __global__ void k_yield_find(MlpTables m, PacketTable pt, const uint32_t *__rest
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.np || pk_yield[i] || pt.codec[i] != CODEC_MLP) return;
+    // Tracks are sorted by first packet.  Normally the owner is the last track that
+    // starts at or before packet i; parts of one long track may also answer for the
+    // first packets of the parts behind them, so look a few tracks back as well.
     const uint32_t t = upper_bound_dev(trk_pk_lo, m.n_tracks, i);
-    if (t == 0) return;
-    TrackDev &T = m.tracks[t - 1];
-    if (T.status != 0 || T.codec != 1) return;
-    // only packets handed to decode_mlp_audio inside the track's sector range count
-    if (i <= T.pk_open || i >= T.pk_x || i >= T.pk_hi) return;
-    atomicMin((unsigned long long *)&T.es_cut, (unsigned long long)m.pk_es[i]);
+    for (uint32_t tt = t, steps = 0; tt > 0 && steps < 64; tt--, steps++) {
+        TrackDev &T = m.tracks[tt - 1];
+        if (T.status != 0 || T.codec != 1) continue;
+        // only packets handed to decode_mlp_audio inside the track's sector range count
+        if (i < T.pk_check || i >= T.pk_check_end || i >= T.pk_hi) continue;
+        atomicMin((unsigned long long *)&T.es_cut, (unsigned long long)m.pk_es[i]);
+    }
 }
 
 int launch_yield(MlpTables m, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
@@ -390,7 +416,7 @@ int launch_yield(MlpTables m, const uint32_t *seg_au_base, PacketTable pt, const
 __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tracks,
                               const uint32_t *__restrict__ trk_grp_base, const SegDev *__restrict__ segs,
                               GroupDev *__restrict__ groups, uint32_t ngroups, uint32_t *__restrict__ grp_cells,
-                              uint32_t *__restrict__ grp_chunks)
+                              uint32_t *__restrict__ grp_chunks, uint32_t *__restrict__ max_au)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= ngroups) return;
@@ -401,9 +427,10 @@ __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tr
     G.track = t;
     G.seg0 = T.seg_base + j * DVDA_LANES;
     G.nseg = min((uint32_t)DVDA_LANES, T.nseg - j * DVDA_LANES);
-    uint32_t cap = 0;
+    uint32_t cap = 0, most = 0;
     for (uint32_t l = 0; l < G.nseg; l++) {
         const SegDev &S = segs[G.seg0 + l];
+        most = max(most, S.n_au);
         // second attempt after an overflow: the frame counts are known
         const uint32_t need = (S.flags & SEG_OVERFLOW) ? S.frames : S.n_au * T.au_nominal;
         cap = max(cap, need);
@@ -413,6 +440,7 @@ __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tr
     groups[g] = G;
     grp_cells[g] = cap * T.channels;
     grp_chunks[g] = (cap + 31) / 32;
+    atomicMax(max_au, most);
 }
 
 __global__ void k_group_offsets(GroupDev *__restrict__ groups, uint32_t ngroups, const uint64_t *__restrict__ cell_base)
@@ -424,10 +452,10 @@ __global__ void k_group_offsets(GroupDev *__restrict__ groups, uint32_t ngroups,
 }
 
 int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_grp_base, const SegDev *segs,
-                       GroupDev *groups, uint32_t ngroups, uint32_t *grp_cells, uint32_t *grp_chunks, cudaStream_t s)
+                       GroupDev *groups, uint32_t ngroups, uint32_t *grp_cells, uint32_t *grp_chunks, uint32_t *max_au, cudaStream_t s)
 {
     if (!ngroups) return 0;
-    LAUNCH(k_group_setup, div_up_u32(ngroups, 128), 128, 0, s, tracks, n_tracks, trk_grp_base, segs, groups, ngroups, grp_cells, grp_chunks);
+    LAUNCH(k_group_setup, div_up_u32(ngroups, 128), 128, 0, s, tracks, n_tracks, trk_grp_base, segs, groups, ngroups, grp_cells, grp_chunks, max_au);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -432,8 +432,11 @@ DVDA_Track_Reader *dvda_open_track_reader(const DVDA_Track *track)
     dvdagpu_ctx *eng = engine();
     if (!eng) goto out;
 
-    /* Upload the track's sectors plus a margin for the run to the next major
-       sync; widen the window while the engine reports that it ran out. */
+    /* Read the track's sectors plus a margin for the run to the next major
+       sync into pinned memory; widen the window while the engine reports that
+       it ran out.  A probe of the first sectors tells the sample format, which
+       sizes the PCM buffer (from the track's PTS length) for the pipelined
+       decode; if that estimate is too small the one-piece path is used. */
     unsigned long long last = track->t.last_sector < first ? first : track->t.last_sector;
     unsigned long long margin = 64;
     for (;;) {
@@ -447,31 +450,59 @@ DVDA_Track_Reader *dvda_open_track_reader(const DVDA_Track *track)
         dvdagpu_track_desc desc = {0, 0, track->t.pts_length, 0};
         desc.last_sector = (uint32_t)(track->t.last_sector >= first ? track->t.last_sector - first : 0);
         dvdagpu_track_result res;
-        int rc = got ? dvdagpu_decode_host(eng, sec, got, 1, &desc, &res) : -1;
+        memset(&res, 0, sizeof res);
+        int rc = got ? 0 : -1;
+        int *pcm = NULL;
+        size_t pcm_bytes = 0;
+        int have_pcm = 0;
+        if (!rc && got > 4096) {
+            /* long track: probe the format on a short window, then decode with overlapped copies */
+            dvdagpu_track_desc pd = {0, 63, track->t.pts_length, 0};
+            dvdagpu_track_result pr;
+            if (!dvdagpu_decode_host(eng, sec, 256, 1, &pd, &pr) && pr.status == DVDAGPU_TRACK_OK &&
+                pr.codec == 1 && pr.sample_rate && pr.channels) {
+                const double seconds = (double)track->t.pts_length / PTS_PER_SECOND + 2.0;
+                const unsigned long long cap = (unsigned long long)(seconds * pr.sample_rate) * pr.channels;
+                pcm_bytes = round_up((size_t)cap * sizeof(int) + 1, 1 << 20);
+                pcm = pool_take(pcm_bytes);
+                if (pcm) {
+                    rc = dvdagpu_decode_track_pipelined(eng, sec, got, &desc, 0, pcm, pcm_bytes / sizeof(int), &res);
+                    if (rc == 0) have_pcm = 1;
+                    else { pool_give(pcm, pcm_bytes); pcm = NULL; rc = 0; }   /* too small: one piece */
+                }
+            }
+        }
+        if (!rc && !have_pcm) rc = dvdagpu_decode_host(eng, sec, got, 1, &desc, &res);
         pool_give(sec, sec_bytes);
         if (rc) {
             if (got) fprintf(stderr, "libdvd-audio (B200): %s\n", dvdagpu_last_error());
+            if (pcm) pool_give(pcm, pcm_bytes);
             break;
         }
-        if (res.status != DVDAGPU_TRACK_OK) break;
-        if (res.truncated && stop < aobs.total) { margin *= 8; continue; }
+        if (res.status != DVDAGPU_TRACK_OK) { if (pcm) pool_give(pcm, pcm_bytes); break; }
+        if (res.truncated && stop < aobs.total) { if (pcm) pool_give(pcm, pcm_bytes); margin *= 8; continue; }
 
         if (res.error_flags & DVDAGPU_ERR_PARITY) fprintf(stderr, "parity mismatch\n");
         if (res.error_flags & DVDAGPU_ERR_CRC) fprintf(stderr, "CRC-8 mismatch\n");
         r = calloc(1, sizeof *r);
-        if (!r) break;
+        if (!r) { if (pcm) pool_give(pcm, pcm_bytes); break; }
         r->codec = res.codec ? DVDA_MLP : DVDA_PCM;
         r->bits = res.bits_per_sample;
         r->rate = res.sample_rate;
         r->channels = res.channels;
         r->assignment = res.channel_assignment;
         r->frames = res.frames;
-        r->pcm_bytes = round_up((size_t)res.frames * res.channels * sizeof(int) + 1, 1 << 20);
-        r->pcm = pool_take(r->pcm_bytes);
-        if (!r->pcm || dvdagpu_fetch(eng, res.pcm_offset, res.frames * res.channels, r->pcm)) {
-            pool_give(r->pcm, r->pcm_bytes);
-            free(r);
-            r = NULL;
+        if (have_pcm) {
+            r->pcm = pcm;
+            r->pcm_bytes = pcm_bytes;
+        } else {
+            r->pcm_bytes = round_up((size_t)res.frames * res.channels * sizeof(int) + 1, 1 << 20);
+            r->pcm = pool_take(r->pcm_bytes);
+            if (!r->pcm || dvdagpu_fetch(eng, res.pcm_offset, res.frames * res.channels, r->pcm)) {
+                pool_give(r->pcm, r->pcm_bytes);
+                free(r);
+                r = NULL;
+            }
         }
         break;
     }
