@@ -295,6 +295,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if len(tracks) == 1:
+            for _ in range(max(1, min(args.warmup, 2))):      # sizes the double buffers of the pipelined path
+                eng.decode_track_pipelined(host_in.data_ptr(), n_sectors, tracks[0], host_out.data_ptr(), samples)
         e2e_launches = 0
         t_wall = time.perf_counter()
         e2.record(stream)

@@ -23,6 +23,8 @@
 #include <cstring>
 #include <vector>
 
+#define MAP_BYTES (1u << 20)      // mapped pinned staging area for small transfers
+
 thread_local uint32_t g_launch_count = 0;
 static thread_local char g_error[512] = "";
 
@@ -80,6 +82,8 @@ struct dvdagpu_ctx {
     cudaStream_t h2d_stream, d2h_stream;      // copy engines of the pipelined path
     cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
     int pcm_slot;                             // which PCM buffer the next decode writes
+    uint8_t *hmap, *dmap;                     // mapped pinned staging area (host / device alias)
+    size_t map_used;
     DevBuf buf[B_COUNT];
     cudaEvent_t ev[6];
     cudaEvent_t kev[8][2];
@@ -162,6 +166,13 @@ extern "C" dvdagpu_ctx *dvdagpu_create(int device)
     }
     c->stream = c->own_stream;
     c->pcm_slot = 0;
+    c->hmap = c->dmap = nullptr; c->map_used = 0;
+    if (cudaHostAlloc((void **)&c->hmap, MAP_BYTES, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&c->dmap, c->hmap, 0) != cudaSuccess) {
+        dvdagpu_set_error("cannot allocate mapped staging memory: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
     cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
     for (auto &e : c->pev) { cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming); }
@@ -185,6 +196,7 @@ extern "C" void dvdagpu_destroy(dvdagpu_ctx *c)
     for (auto &k : c->kev) { cudaEventDestroy(k[0]); cudaEventDestroy(k[1]); }
     for (auto &e : c->fev) cudaEventDestroy(e);
     for (auto &e : c->pev) { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
+    if (c->hmap) cudaFreeHost(c->hmap);
     cudaStreamDestroy(c->h2d_stream);
     cudaStreamDestroy(c->d2h_stream);
     cudaStreamDestroy(c->own_stream);
@@ -248,12 +260,49 @@ extern "C" int dvdagpu_fetch(dvdagpu_ctx *c, uint64_t offset, uint64_t count, in
         c->kev_used[id] = true;                                                \
     } while (0)
 
+// Small transfers do not go through the copy engines: a bulk upload or download
+// of another part may be queued there for milliseconds (the pipelined path), and
+// a 4-byte read-back would wait behind it.  A one-block kernel moves the words
+// to / from a mapped pinned staging area instead (plain loads/stores over PCIe).
+__global__ void k_copy_words(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint32_t nwords)
+{
+    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+}
+
+// device -> host, synchronous
+static int small_d2h(dvdagpu_ctx *c, void *host, const void *dev, size_t bytes)
+{
+    if (bytes > MAP_BYTES / 2 || (bytes & 3)) {
+        CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    // the upper half of the staging area is for read-backs
+    LAUNCH(k_copy_words, 1, 256, 0, c->stream, (uint32_t *)(c->dmap + MAP_BYTES / 2), (const uint32_t *)dev, (uint32_t)(bytes / 4));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(host, c->hmap + MAP_BYTES / 2, bytes);
+    return 0;
+}
+
+// host -> device, asynchronous (the staging bytes stay untouched until the next decode)
+static int small_h2d(dvdagpu_ctx *c, void *dev, const void *host, size_t bytes)
+{
+    if (!bytes) return 0;
+    if ((bytes & 3) || c->map_used + bytes > MAP_BYTES / 2) {
+        CUDA_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    memcpy(c->hmap + c->map_used, host, bytes);
+    LAUNCH(k_copy_words, 1, 256, 0, c->stream, (uint32_t *)dev, (const uint32_t *)(c->dmap + c->map_used), (uint32_t)(bytes / 4));
+    c->map_used += (bytes + 15) & ~(size_t)15;
+    return 0;
+}
+
 template <typename T>
 static int read_back(dvdagpu_ctx *c, const T *dev, T *host)
 {
-    CUDA_TRY(cudaMemcpyAsync(host, dev, sizeof(T), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return small_d2h(c, host, dev, sizeof(T));
 }
 
 static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n_sectors64,
@@ -261,6 +310,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
 {
     g_error[0] = 0;
     g_launch_count = 0;
+    c->map_used = 0;
     cudaStream_t s = c->stream;
     if (n_sectors64 == 0 || n_sectors64 > 0x7FFFFFFFull) { dvdagpu_set_error("bad sector count"); return -1; }
     if (!n_tracks) { c->pcm_samples = 0; return 0; }
@@ -352,14 +402,13 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     ENSURE(B_TRK_PK_LO, (size_t)n_tracks * 4); ENSURE(B_TRK_SEG_BASE, (size_t)(n_tracks + 1) * 4);
     ENSURE(B_TRK_GRP_BASE, (size_t)(n_tracks + 1) * 4);
     TrackDev *d_tracks = c->buf[B_TRACKS].as<TrackDev>();
-    CUDA_TRY(cudaMemcpyAsync(d_tracks, ht.data(), n_tracks * sizeof(TrackDev), cudaMemcpyHostToDevice, s));
+    TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
     TrackSetupArgs ta;
     ta.es = es; ta.es_total = es_total; ta.n_sectors = n_sectors; ta.sec_base = sec_base; ta.bad_prefix = bad_prefix;
     ta.pt = pt; ta.np = np; ta.pk_es = pk_es; ta.pk_pf = pk_pf; ta.pk_nonmlp = nm_prefix; ta.pk_pcm_stop = stop_prefix;
     ta.raw = raw; ta.n_raw = n_raw; ta.valid = valid; ta.n_valid = n_valid;
     TRY(launch_track_setup(ta, d_tracks, n_tracks, s));
-    CUDA_TRY(cudaMemcpyAsync(ht.data(), d_tracks, n_tracks * sizeof(TrackDev), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    TRY(small_d2h(c, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
 
     std::vector<uint32_t> h_pk_lo(n_tracks), h_seg_base(n_tracks + 1), h_grp_base(n_tracks + 1);
     uint32_t nseg = 0, ngroups = 0;
@@ -387,10 +436,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     }
     uint32_t *trk_pk_lo = c->buf[B_TRK_PK_LO].as<uint32_t>(), *trk_seg_base = c->buf[B_TRK_SEG_BASE].as<uint32_t>();
     uint32_t *trk_grp_base = c->buf[B_TRK_GRP_BASE].as<uint32_t>();
-    CUDA_TRY(cudaMemcpyAsync(d_tracks, ht.data(), n_tracks * sizeof(TrackDev), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(trk_pk_lo, h_pk_lo.data(), n_tracks * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(trk_seg_base, h_seg_base.data(), (n_tracks + 1) * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(trk_grp_base, h_grp_base.data(), (n_tracks + 1) * 4, cudaMemcpyHostToDevice, s));
+    TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
+    TRY(small_h2d(c, trk_pk_lo, h_pk_lo.data(), n_tracks * 4));
+    TRY(small_h2d(c, trk_seg_base, h_seg_base.data(), (n_tracks + 1) * 4));
+    TRY(small_h2d(c, trk_grp_base, h_grp_base.data(), (n_tracks + 1) * 4));
 
     const DecWork *d_work[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t n_work[5] = {0, 0, 0, 0, 0};
@@ -404,10 +453,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             n_work[cl] = (uint32_t)h_work[cl].size();
             d_work[cl] = base + off;
             if (n_work[cl])
-                CUDA_TRY(cudaMemcpyAsync(base + off, h_work[cl].data(), n_work[cl] * sizeof(DecWork), cudaMemcpyHostToDevice, s));
+                TRY(small_h2d(c, base + off, h_work[cl].data(), n_work[cl] * sizeof(DecWork)));
             off += n_work[cl];
         }
-        CUDA_TRY(cudaStreamSynchronize(s));      // h_work goes out of use only after the copies
     }
     MlpTables m;
     memset(&m, 0, sizeof m);
@@ -455,7 +503,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
         uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
 
-        const bool use_fast = getenv("DVDAGPU_NO_FAST") == nullptr;
+        // The three-pass path is bit-exact (the GPU tests run it too) but on a B200 its header
+        // pass is still slower than the single-pass decoder it replaces: opt-in for now.
+        const bool use_fast = getenv("DVDAGPU_FAST") != nullptr;
         if (use_fast) {
             ENSURE(B_AU_SNAP, naua * 2 * au_snap_bytes());
             ENSURE(B_FILT_SNAP, naua * 2 * 4 * filt_snap_bytes());
@@ -501,8 +551,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     } else {
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
     }
-    CUDA_TRY(cudaMemcpyAsync(ht.data(), d_tracks, n_tracks * sizeof(TrackDev), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    TRY(small_d2h(c, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
     CUDA_TRY(cudaEventRecord(c->ev[3], s));
     if (getenv("DVDAGPU_DEBUG")) {
         fprintf(stderr, "[dvdagpu] sectors=%u packets=%u es=%llu raw=%u valid=%u segs=%u groups=%u aus=%u\n",
@@ -528,7 +577,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     // ---------------- output
     uint64_t total_samples = 0;
     bool any_pcm = false;
+    uint32_t mlp_channel_mask = 0;
+    for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].status == 0 && ht[i].codec == 1) mlp_channel_mask |= 1u << ht[i].channels;
     for (uint32_t i = 0; i < n_tracks; i++) {
+        total_samples = (total_samples + 3) & ~3ull;          // 16-byte aligned tracks (vector stores)
         ht[i].out_base = total_samples;
         if (ht[i].status == 0) total_samples += ht[i].frames * ht[i].channels;
         any_pcm |= ht[i].status == 0 && ht[i].codec == 0;
@@ -537,8 +589,8 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     ENSURE(pcm_buf, (total_samples + 64) * sizeof(int32_t));
     m.pcm = c->buf[pcm_buf].as<int32_t>();
     c->pcm_samples = total_samples;
-    CUDA_TRY(cudaMemcpyAsync(d_tracks, ht.data(), n_tracks * sizeof(TrackDev), cudaMemcpyHostToDevice, s));
-    if (nseg && total_chunks) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, total_chunks, grp_chunk_base, s));
+    TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
+    if (nseg && total_chunks) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, total_chunks, grp_chunk_base, mlp_channel_mask, s));
     if (any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, np, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));
     CUDA_TRY(cudaEventRecord(c->ev[4], s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -621,9 +673,17 @@ extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sec
 {
     if (!c || !sectors || !track || !result || !pcm_host) { dvdagpu_set_error("null argument"); return -1; }
     CUDA_TRY(cudaSetDevice(c->device));
-    if (!part_sectors) part_sectors = 24576;                    // 48 MiB of AOB per part
     const uint64_t first = track->first_sector;
     const uint64_t last = track->last_sector < n_sectors ? track->last_sector : n_sectors - 1;
+    if (!part_sectors) {
+        // a decode has a latency floor of a few milliseconds whatever its size, so few, large
+        // parts: about 100 MB of AOB each, between 2 and 8 of them
+        const uint64_t n = last >= first ? last - first + 1 : 0;
+        uint64_t parts = n / 50000;
+        parts = parts < 2 ? 2 : parts > 8 ? 8 : parts;
+        part_sectors = (uint32_t)((n + parts - 1) / parts);
+        if (part_sectors < 8192) part_sectors = 8192;
+    }
     const uint64_t margin = 64;
     dvdagpu_stats total_stats;
     memset(&total_stats, 0, sizeof total_stats);

@@ -232,6 +232,14 @@ __device__ __forceinline__ void rd_prefetch(Rd &r, uint32_t need)
     if (r.next_w + need > r.safe_w) rd_slow_fill(r, need);
 }
 
+// fill the whole ring ahead of the reader without waiting (cold starts: one DRAM
+// latency then covers ~450 bytes, about one access unit)
+__device__ __forceinline__ void rd_issue_ahead(Rd &r)
+{
+    while (r.fill_c * CHUNK_WORDS < r.next_w + RING_WORDS - CHUNK_WORDS && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
+    cp_commit();
+}
+
 // position the reader at an absolute byte offset
 __device__ __forceinline__ void rd_seat(Rd &r, uint64_t byte_pos)
 {
@@ -593,6 +601,14 @@ __device__ uint32_t decode_block_generic(const MlpTables &m, const GroupDev &G, 
 // beyond the transmitted orders carry zero coefficients, so every lane runs the
 // same 16 multiply-adds whatever its filter orders are (no divergence).
 
+// 32 x 32 -> 64-bit multiply-add in one instruction (IMAD.WIDE)
+__device__ __forceinline__ long long mad_wide(int32_t a, int32_t b, long long c)
+{
+    long long d;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
 template <int NCH>
 struct Hot {
     int32_t fh[NCH][8], ih[NCH][8];      // histories, [0] = most recent at chunk boundaries
@@ -877,9 +893,11 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
                     uses |= (s.coeff[k][s.mmc + 1] != 0) | (s.coeff[k][s.mmc + 2] != 0);
                 }
                 P.uses_noise = uses;
-                for (int c = 0; c < DVDA_MAX_CH; c++) { P.q[c] = s.q[c]; P.out_shift[c] = s.out_shift[c]; }
+                uint32_t shifts = 0;
+                for (int c = 0; c < DVDA_MAX_CH; c++) { P.q[c] = s.q[c]; P.out_shift[c] = s.out_shift[c]; shifts |= s.out_shift[c]; }
                 m.psets[A] = P;
-                pset = A;
+                // top bit: nothing to do for these frames but to copy them
+                pset = A | ((s.matrix_len == 0 && shifts == 0) ? 0x80000000u : 0u);
                 s.dirty = 0;
             }
             AuDev R = {au_frame0, nf, seed0, pset};
@@ -994,6 +1012,7 @@ __device__ __forceinline__ void headers_segment(const MlpTables &m, const Decode
         const uint32_t len = L.end[job.k] - start - (L.chk0 ? 2 : 0);
         const uint64_t data = au_pos + L.data0 + start;
         rd_seat(b, data);
+        rd_issue_ahead(b);                       // also brings the next access unit's header in
         rd_skip(b, (uint32_t)(data & 3) * 8);
         const uint32_t end_bits = (uint32_t)(data & 3) * 8 + len * 8;
         bool changed;
@@ -1050,9 +1069,11 @@ __device__ __forceinline__ void headers_segment(const MlpTables &m, const Decode
                     uses |= (s.coeff[k][s.mmc + 1] != 0) | (s.coeff[k][s.mmc + 2] != 0);
                 }
                 P.uses_noise = uses;
-                for (int c = 0; c < DVDA_MAX_CH; c++) { P.q[c] = s.q[c]; P.out_shift[c] = s.out_shift[c]; }
+                uint32_t shifts = 0;
+                for (int c = 0; c < DVDA_MAX_CH; c++) { P.q[c] = s.q[c]; P.out_shift[c] = s.out_shift[c]; shifts |= s.out_shift[c]; }
                 m.psets[A] = P;
-                pset = A;
+                // top bit: nothing to do for these frames but to copy them
+                pset = A | ((s.matrix_len == 0 && shifts == 0) ? 0x80000000u : 0u);
                 s.dirty = 0;
             }
             AuDev R = {au_frame0, nominal, s.seed, pset};
@@ -1085,6 +1106,7 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
     Rd b;
     rd_init(b, m.es, ring);
     rd_seat(b, (sn.bit0 >> 5) << 2);
+    rd_issue_ahead(b);
     rd_skip(b, (uint32_t)(sn.bit0 & 31));
     const uint32_t end_bits = (uint32_t)(sn.bit_end - ((sn.bit0 >> 5) << 5));
 
@@ -1171,23 +1193,30 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
     int32_t *tile = m.tiles + G.tile_off + lane + (uint64_t)c * DVDA_LANES;
     const uint32_t tile_step = nch * DVDA_LANES;
     uint32_t f = 0;
+    int32_t nx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) nx[j] = ((uint32_t)j < cap) ? tile[(uint64_t)j * tile_step] : 0;
     for (uint32_t a = 0; a < S.n_au; a++) {
         const FiltSnap fs = fsnaps[(uint64_t)(S.au_base + a) * 4 + cc];
 #pragma unroll
         for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
         const uint32_t shift = fs.shift, q = fs.q;
-        // the nominal AU length is a multiple of 8 (40 * rate multiple)
+        // the nominal AU length is a multiple of 8 (40 * rate multiple); the residuals of
+        // the next 8 frames are loaded while the current 8 are filtered
         for (uint32_t i = 0; i < nominal; i += 8) {
             int32_t r[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = (f + j < cap) ? tile[(uint64_t)j * tile_step] : 0;
+            for (int j = 0; j < 8; j++) r[j] = nx[j];
+            const bool more = (i + 8 < nominal) || (a + 1 < S.n_au);
+#pragma unroll
+            for (int j = 0; j < 8; j++) nx[j] = (more && f + 8 + j < cap) ? tile[(uint64_t)(8 + j) * tile_step] : 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 long long s0 = 0, s1 = 0;
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
-                    s0 += (long long)cf[t] * fh[(t - j) & 7];
-                    s1 += (long long)ci[t] * ih[(t - j) & 7];
+                    s0 = mad_wide(cf[t], fh[(t - j) & 7], s0);
+                    s1 = mad_wide(ci[t], ih[(t - j) & 7], s1);
                 }
                 const int32_t ssum = (int32_t)((s0 + s1) >> shift);
                 int32_t v = (int32_t)((uint32_t)ssum + (uint32_t)r[j]);
@@ -1515,6 +1544,12 @@ __device__ __forceinline__ uint32_t wave_slot(uint32_t assignment, uint32_t c)
 // patch of the tile coalesced, then every warp takes segments (lanes of the
 // patch) and its 32 threads take the 32 frames: noise, matrices, bypass, shift,
 // channel order, interleaved store.
+//
+// Per frame the access unit is found by division (AUs normally have the nominal
+// length; a binary search covers the rest), and an AU whose parameters are
+// trivial — no matrix, no output shift, identity channel order — skips the
+// parameter set altogether: the kernel is then a pure transpose at HBM speed.
+template <int NCH>
 __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m, const uint64_t *__restrict__ grp_chunk_base)
 {
     extern __shared__ int32_t sm[];                      // [nch][32][33] samples, then [32][33] bypass bytes as ints
@@ -1522,7 +1557,9 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m, const uint
     const uint32_t g = upper_bound_dev(grp_chunk_base, m.ngroups, chunk) - 1;
     const GroupDev &G = m.groups[g];
     const TrackDev &T = m.tracks[G.track];
-    const uint32_t nch = T.channels;
+    const uint32_t nch = NCH ? NCH : T.channels;
+    if (NCH && T.channels != NCH) return;
+    if (!NCH && T.channels <= 2) return;                 // handled by the specialised instantiations
     const uint32_t f0 = (uint32_t)(chunk - grp_chunk_base[g]) * 32;
     const uint32_t nf = min(32u, G.cap - f0);
     int32_t *bsm = sm + nch * 32 * 33;
@@ -1538,22 +1575,41 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m, const uint
     __syncthreads();
 
     const uint32_t f = threadIdx.x & 31;                 // frame inside the chunk
+    const uint32_t nominal = T.au_nominal;
+    const bool plain_order = !(T.assignment >= 0x12 && T.assignment <= 0x14);
     for (uint32_t l = threadIdx.x >> 5; l < G.nseg; l += RM_THREADS / 32) {
         const SegDev &S = m.segs[G.seg0 + l];
         const uint32_t F = f0 + f;                       // frame inside the segment
         if (F >= S.frames) continue;
-        // access unit holding frame F: last one with frame0 <= F among the decoded ones
-        uint32_t lo = 0, hi = min(S.n_au, S.err_au);
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (m.au[S.au_base + mid].frame0 <= F) lo = mid; else hi = mid;
+        // access unit holding frame F
+        const uint32_t n_ok = min(S.n_au, S.err_au);
+        uint32_t ai = min(F / nominal, n_ok - 1);
+        AuDev au = m.au[S.au_base + ai];
+        if (F < au.frame0 || F >= au.frame0 + au.nframes) {
+            // irregular lengths or dropped AUs: last one with frame0 <= F (dropped AUs have no
+            // frames and share frame0 with their successor)
+            uint32_t lo = 0, hi = n_ok;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (m.au[S.au_base + mid].frame0 <= F) lo = mid; else hi = mid;
+            }
+            au = m.au[S.au_base + lo];
         }
-        // dropped AUs have no frames and share frame0 with their successor: take the last match
-        const AuDev au = m.au[S.au_base + lo];
-        const ParamSet &P = m.psets[au.pset];
         int32_t v[DVDA_MAX_CH];
 #pragma unroll
         for (uint32_t c = 0; c < DVDA_MAX_CH; c++) v[c] = (c < nch) ? sm[(c * 32 + f) * 33 + l] : 0;
+        int32_t *dst = m.pcm + T.out_base + (S.frame0 + F) * nch;
+        if ((au.pset & 0x80000000u) && plain_order) {
+            // trivial parameters: straight copy
+            if (NCH == 2) {
+                *reinterpret_cast<int2 *>(dst) = make_int2(v[0], v[1]);     // out_base and nch are even
+            } else {
+#pragma unroll
+                for (uint32_t c = 0; c < DVDA_MAX_CH; c++) if (c < nch) dst[c] = v[c];
+            }
+            continue;
+        }
+        const ParamSet &P = m.psets[au.pset & 0x7FFFFFFFu];
         const uint32_t ml = P.matrix_len;
         if (ml) {
             int32_t n0 = 0, n1 = 0;
@@ -1578,7 +1634,6 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m, const uint
                 for (uint32_t c = 0; c < DVDA_MAX_CH; c++) if (c == oc) v[c] = r;
             }
         }
-        int32_t *dst = m.pcm + T.out_base + (S.frame0 + F) * nch;
 #pragma unroll
         for (uint32_t c = 0; c < DVDA_MAX_CH; c++) {
             if (c < nch) {
@@ -1590,16 +1645,19 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m, const uint
     }
 }
 
-int launch_rematrix(MlpTables m, uint64_t total_chunks, const uint64_t *grp_chunk_base, cudaStream_t s)
+int launch_rematrix(MlpTables m, uint64_t total_chunks, const uint64_t *grp_chunk_base, uint32_t channel_mask, cudaStream_t s)
 {
     if (!total_chunks) return 0;
     const size_t smem = (size_t)(DVDA_MAX_CH + 1) * 32 * 33 * sizeof(int32_t);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_rematrix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_rematrix<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    LAUNCH(k_rematrix, (uint32_t)total_chunks, RM_THREADS, smem, s, m, grp_chunk_base);
+    // channel_mask: bit n = some MLP track of the batch has n channels
+    if (channel_mask & 2) LAUNCH(k_rematrix<1>, (uint32_t)total_chunks, RM_THREADS, (size_t)2 * 32 * 33 * 4, s, m, grp_chunk_base);
+    if (channel_mask & 4) LAUNCH(k_rematrix<2>, (uint32_t)total_chunks, RM_THREADS, (size_t)3 * 32 * 33 * 4, s, m, grp_chunk_base);
+    if (channel_mask & ~6u) LAUNCH(k_rematrix<0>, (uint32_t)total_chunks, RM_THREADS, smem, s, m, grp_chunk_base);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

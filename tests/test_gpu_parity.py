@@ -16,11 +16,18 @@ GOLDEN = json.load(open(os.path.join(HERE, "golden", "catalog_golden.json")))
 DISCS = sorted(catalog.discs().keys())
 
 
-@pytest.fixture(scope="module")
-def engine(pkg):
+@pytest.fixture(scope="module", params=["single-pass", "three-pass"])
+def engine(pkg, request):
+    """Every test runs against both MLP decode paths: the complete single-pass decoder
+    (default) and the access-unit-parallel three-pass path (DVDAGPU_FAST=1)."""
+    if request.param == "three-pass":
+        os.environ["DVDAGPU_FAST"] = "1"
+    else:
+        os.environ.pop("DVDAGPU_FAST", None)
     e = pkg.Engine(0)
     yield e
     e.close()
+    os.environ.pop("DVDAGPU_FAST", None)
 
 
 def check_track(oracle, eng, res, sectors, g, label):
