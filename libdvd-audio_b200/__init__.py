@@ -24,6 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ENGINE_LIB = _build.ENGINE_LIB
 HOST_LIB = _build.HOST_LIB
 DUMP_BIN = _build.DUMP_BIN
+WAV_BIN = _build.WAV_BIN
 
 ERR_PARITY, ERR_CRC, ERR_SYNTAX = 1 << 4, 1 << 5, 1 << 6
 

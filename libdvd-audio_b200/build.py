@@ -18,6 +18,7 @@ INCLUDE = os.path.join(ROOT, "include")
 ENGINE_LIB = os.path.join(LIBDIR, "libdvdagpu.so")
 HOST_LIB = os.path.join(LIBDIR, "libdvd-audio.so")
 DUMP_BIN = os.path.join(LIBDIR, "b200_dump")
+WAV_BIN = os.path.join(LIBDIR, "dvda2wav")
 
 CU_FILES = ["scan.cu", "demux.cu", "mlp_index.cu", "mlp_decode.cu", "engine.cu"]
 NVCC_FLAGS = [
@@ -72,6 +73,11 @@ def build_host(force=False, verbose=False):
     if force or _newer(DUMP_BIN, [dump_src, HOST_LIB]):
         # the same dumper source the reference build uses (oracle/_ref/ref_dump)
         _run(["gcc", "-O2", "-g", "-Wall", "-I", INCLUDE, "-o", DUMP_BIN, dump_src,
+              "-L", LIBDIR, "-ldvd-audio", "-Wl,-rpath,$ORIGIN"], verbose)
+    wav_src = os.path.join(ROOT, "tools", "dvda2wav.c")
+    if force or _newer(WAV_BIN, [wav_src, HOST_LIB]):
+        # our equivalent of the reference's extraction tool, on the GPU-backed library
+        _run(["gcc", "-O2", "-g", "-Wall", "-I", INCLUDE, "-o", WAV_BIN, wav_src,
               "-L", LIBDIR, "-ldvd-audio", "-Wl,-rpath,$ORIGIN"], verbose)
     return HOST_LIB
 

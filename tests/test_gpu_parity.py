@@ -219,3 +219,29 @@ def test_pipelined_track_decode(pkg, oracle, engine, disc_cache, name, part):
         assert (r.channels, r.bits_per_sample, r.sample_rate) == (ref["channels"], ref["bits_per_sample"], ref["sample_rate"])
         got = out[: r.frames * r.channels].reshape(-1, r.channels)
         assert np.array_equal(got, ref["pcm"]), (name, g["track"])
+
+
+@pytest.mark.parametrize("name", ["c1_pcm_2ch16", "c2_mlp_2ch96", "pcm_layouts"])
+def test_dvda2wav_matches_the_reference_tool(pkg, oracle, disc_cache, tmp_path, name):
+    """tools/dvda2wav.c on the GPU library writes the same .wav files, byte for byte, as the
+    reference's own dvda2wav (unmodified, built into oracle/_ref) — for discs whose
+    samples fit their bits per sample (the reference mangles the others, App. B-12)."""
+    import subprocess
+    ref_tool = os.path.join(oracle.REF_DIR, "dvda2wav")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref/dvda2wav not built")
+    directory, _ = disc_cache(name)
+    ours, theirs = tmp_path / "ours", tmp_path / "ref"
+    ours.mkdir()
+    theirs.mkdir()
+    a = subprocess.run([pkg.WAV_BIN, "-A", directory, "-d", str(ours)], capture_output=True, text=True)
+    b = subprocess.run([ref_tool, "-A", directory, "-d", str(theirs)], capture_output=True, text=True)
+    assert a.returncode == 0, a.stderr
+    assert b.returncode == 0, b.stderr
+    files = sorted(os.listdir(theirs))
+    assert files and files == sorted(os.listdir(ours))
+    for f in files:
+        assert (ours / f).read_bytes() == (theirs / f).read_bytes(), f
+    # same progress lines too
+    assert [l for l in a.stdout.splitlines() if l.startswith("* Extracting")] == \
+           [l for l in b.stdout.splitlines() if l.startswith("* Extracting")]
