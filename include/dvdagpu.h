@@ -109,7 +109,8 @@ enum {
     DVDAGPU_K_PCM_UNPACK = 7,
     DVDAGPU_K_MLP_HEADERS = 8,  /* fast path, pass A: block headers of every access unit */
     DVDAGPU_K_MLP_ENTROPY = 9,  /* fast path, pass B: residual entropy decode, one lane per access unit */
-    DVDAGPU_K_MLP_FILTER = 10   /* fast path, pass C: FIR/IIR prediction, one lane per channel */
+    DVDAGPU_K_MLP_FILTER = 10,  /* fast path, pass C: FIR/IIR prediction, one lane per channel (2 substreams) */
+    DVDAGPU_K_MLP_FILTER_OUT = 11 /* fast path, single substream: prediction + rematrix + interleaved output */
 };
 
 /* number of CUDA devices the engine can use (0 = none) */

@@ -71,7 +71,7 @@ class Stats(ctypes.Structure):
                 ("kernel_ms", ctypes.c_float * 12)]
 
 KERNEL_NAMES = ["es_gather", "sync_scan", "au_chase", "checkdata", "mlp_decode", "carry_fix", "rematrix", "pcm_unpack",
-                "mlp_headers", "mlp_entropy", "mlp_filter", "reserved"]
+                "mlp_headers", "mlp_entropy", "mlp_filter", "mlp_filter_out"]
 
 
 _engine = None

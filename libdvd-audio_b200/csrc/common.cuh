@@ -37,6 +37,7 @@
 #define SEG_NEEDS_CARRY 2u     // FIR history of the previous segment is needed
 #define SEG_OVERFLOW 4u        // more frames than the tile has room for
 #define SEG_FALLBACK 8u        // the three-pass fast path gave up: decode with the complete decoder
+#define SEG_WANTS_PREV 16u     // ... because it needs the previous segment's FIR history
 
 // TrackDev.cont / dvdagpu_track_desc.flags
 #define TRACK_CONT_PREV 1u

@@ -69,7 +69,7 @@ enum {
     B_ES, B_SYNC_CNT_RAW, B_SYNC_CNT_VALID, B_SYNC_BASE_RAW, B_SYNC_BASE_VALID, B_RAW, B_VALID,
     B_TRACKS, B_TRK_PK_LO, B_TRK_SEG_BASE, B_TRK_GRP_BASE,
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
-    B_SS_FLAGS, B_SS_FLAGS_PREV, B_FIR_TAIL,
+    B_SS_FLAGS, B_SS_FLAGS_PREV, B_SS_FLAGS_FAST, B_FIR_TAIL,
     B_GROUPS, B_GRP_CELLS, B_CELL_BASE, B_GRP_CHUNKS, B_GRP_CHUNK_BASE,
     B_DEC_WORK, B_AU_SNAP, B_FILT_SNAP, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
     B_COUNT
@@ -88,7 +88,7 @@ struct dvdagpu_ctx {
     cudaEvent_t ev[6];
     cudaEvent_t kev[8][2];
     bool kev_used[8];
-    cudaEvent_t fev[4];                       // fast path: before pass A, B, C, after C
+    cudaEvent_t fev[6];                       // fast path: before pass A, B, C, after C; around the fused output pass
     bool fast_timed;
     dvdagpu_stats stats;
     uint64_t pcm_samples;
@@ -477,12 +477,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         const size_t naua = (size_t)nau + 1;
         ENSURE(B_AU_POS, naua * 8); ENSURE(B_AU_ERR, naua); ENSURE(B_AU, naua * sizeof(AuDev));
         ENSURE(B_PSETS, naua * sizeof(ParamSet)); ENSURE(B_AU_FRAMES, naua * 2 * 4);
-        ENSURE(B_SS_FLAGS, (size_t)nseg * 2 * 4); ENSURE(B_SS_FLAGS_PREV, (size_t)nseg * 2 * 4);
+        ENSURE(B_SS_FLAGS, (size_t)nseg * 2 * 4); ENSURE(B_SS_FLAGS_PREV, (size_t)nseg * 2 * 4); ENSURE(B_SS_FLAGS_FAST, (size_t)nseg * 2 * 4);
         ENSURE(B_FIR_TAIL, (size_t)nseg * 2 * DVDA_MAX_CH * 8 * 4);
         m.au_pos = c->buf[B_AU_POS].as<uint64_t>(); m.au_err = c->buf[B_AU_ERR].as<uint8_t>();
         m.au = c->buf[B_AU].as<AuDev>(); m.psets = c->buf[B_PSETS].as<ParamSet>();
         m.au_frames_ss = c->buf[B_AU_FRAMES].as<uint32_t>();
-        m.ss_flags = c->buf[B_SS_FLAGS].as<uint32_t>(); m.ss_flags_prev = c->buf[B_SS_FLAGS_PREV].as<uint32_t>();
+        m.ss_flags = c->buf[B_SS_FLAGS].as<uint32_t>(); m.ss_flags_prev = c->buf[B_SS_FLAGS_PREV].as<uint32_t>(); m.ss_flags_fast = c->buf[B_SS_FLAGS_FAST].as<uint32_t>();
         m.fir_tail = c->buf[B_FIR_TAIL].as<int32_t>();
         TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, m.au_pos, seg_au_base, 1, s));
         TRY(launch_yield(m, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), s));
@@ -534,6 +534,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
                 TRY(launch_mlp_fast(m, d_work, n_work, n_warps, c->fev, s));
                 c->fast_timed = true;
                 CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
+                CUDA_TRY(cudaMemcpyAsync(m.ss_flags_fast, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
                 m.fast = 1;
             }
             // ... and decoded by the complete single-pass decoder (everything, without the fast path)
@@ -590,6 +591,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     m.pcm = c->buf[pcm_buf].as<int32_t>();
     c->pcm_samples = total_samples;
     TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
+    if (nseg && m.fast) {
+        // fast path, single-substream tracks: filters + rematrix + interleaved output in one pass
+        CUDA_TRY(cudaEventRecord(c->fev[4], s));
+        TRY(launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
+        CUDA_TRY(cudaEventRecord(c->fev[5], s));
+    }
     if (nseg && total_chunks) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, total_chunks, grp_chunk_base, mlp_channel_mask, s));
     if (any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, np, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));
     CUDA_TRY(cudaEventRecord(c->ev[4], s));
@@ -621,6 +628,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     if (c->fast_timed) {
         for (int k = 0; k < 3; k++)
             if (cudaEventElapsedTime(&ms, c->fev[k], c->fev[k + 1]) == cudaSuccess) c->stats.kernel_ms[DVDAGPU_K_MLP_HEADERS + k] = ms;
+        if (cudaEventElapsedTime(&ms, c->fev[4], c->fev[5]) == cudaSuccess) c->stats.kernel_ms[DVDAGPU_K_MLP_FILTER_OUT] = ms;
     }
     c->stats.launches = g_launch_count;
     c->stats.segments = nseg;

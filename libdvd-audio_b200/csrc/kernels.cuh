@@ -38,6 +38,7 @@ struct MlpTables {
     uint32_t nau;
     uint32_t *ss_flags;            // [2][nseg] SEG_* per substream
     uint32_t *ss_flags_prev;       // snapshot taken before the carry fix-up
+    uint32_t *ss_flags_fast;       // snapshot taken after passes A and B of the fast path
     int32_t *fir_tail;             // [2][nseg][8 ch][8] last outputs per channel
     int32_t *tiles;
     uint8_t *bypass;
@@ -96,6 +97,7 @@ int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s);
 struct DecWork { uint32_t warp0, track, k, pad; };
 int launch_mlp_decode(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s);
 int launch_carry_fix(MlpTables m, cudaStream_t s);
+int launch_mlp_filter_out(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s);
 size_t au_snap_bytes();
 size_t filt_snap_bytes();
 // fast path: pass A (headers), B (entropy, one lane per access unit), C (filters, one lane per channel)

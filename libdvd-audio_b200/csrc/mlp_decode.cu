@@ -691,7 +691,8 @@ __device__ __forceinline__ uint32_t decode_block_fast(const MlpTables &m, const 
             b.avail -= hl + lsb_bits[cc];                                                          \
             const int32_t res = (int32_t)((uint32_t)((msb << lsb_bits[cc]) + lsb + sho[cc]) << q[cc]); \
             long long s0 = 0, s1 = 0;                                                              \
-            _Pragma("unroll") for (int a = 0; a < 8; a++) {                                        \
+            /* oldest taps first: only the last multiply-add waits for the previous sample */      \
+            _Pragma("unroll") for (int a = 7; a >= 0; a--) {                                       \
                 s0 += (long long)H.cf[cc][a] * H.fh[cc][(a - (J)) & 7];                            \
                 s1 += (long long)H.ci[cc][a] * H.ih[cc][(a - (J)) & 7];                            \
             }                                                                                      \
@@ -957,6 +958,15 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
 // k_carry_fix), which is the complete implementation.
 // =============================================================================
 
+// RIFF WAVE slot of MLP channel c (table at mlp.c:416-438): identity except for
+// assignments 0x12-0x14
+__device__ __forceinline__ uint32_t wave_slot(uint32_t assignment, uint32_t c)
+{
+    if (assignment == 0x12 || assignment == 0x13) return (0x24310u >> (4 * c)) & 15;      // 0,1,3,4,2
+    if (assignment == 0x14) return (0x325410u >> (4 * c)) & 15;                          // 0,1,4,5,2,3
+    return c;
+}
+
 struct ChanSnap { int32_t sho; uint8_t cb, lsb_bits, q, shift; };
 struct AuSnap {
     uint64_t bit0;          // absolute bit position (in the ES) of the first residual bit
@@ -1050,7 +1060,8 @@ __device__ __forceinline__ void headers_segment(const MlpTables &m, const Decode
             C.ist_new = 0;
             C.flen = 8; C.ilen = 8;
         }
-        if (fallback || (cflags & SEG_NEEDS_CARRY)) { fallback = true; break; }
+        if (cflags & SEG_NEEDS_CARRY) { flags |= SEG_WANTS_PREV; fallback = true; break; }
+        if (fallback) break;
         sn.valid = 1;
         snaps[A] = sn;
 
@@ -1180,7 +1191,8 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
 {
     const SegDev &S = m.segs[seg];
     const TrackDev &T = m.tracks[S.track];
-    if ((m.ss_flags[seg] | (T.nss == 2 ? m.ss_flags[m.nseg + seg] : 0)) & SEG_FALLBACK) return;
+    if (T.nss != 2) return;                      // single substream: filter_output_segment does it
+    if ((m.ss_flags[seg] | m.ss_flags[m.nseg + seg]) & SEG_FALLBACK) return;
     const GroupDev &G = m.groups[T.grp_base + (seg - T.seg_base) / DVDA_LANES];
     const uint32_t nch = T.channels, nominal = T.au_nominal, cap = G.cap;
     const AuSnap *snaps = m.au_snap + (uint64_t)k * m.nau;
@@ -1214,7 +1226,7 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
             for (int j = 0; j < 8; j++) {
                 long long s0 = 0, s1 = 0;
 #pragma unroll
-                for (int t = 0; t < 8; t++) {
+                for (int t = 7; t >= 0; t--) {          // oldest taps first: short dependent chain
                     s0 = mad_wide(cf[t], fh[(t - j) & 7], s0);
                     s1 = mad_wide(ci[t], ih[(t - j) & 7], s1);
                 }
@@ -1234,6 +1246,199 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
     int32_t *tail = m.fir_tail + ((uint64_t)k * m.nseg + seg) * (DVDA_MAX_CH * 8);
 #pragma unroll
     for (int j = 0; j < 8; j++) tail[c * 8 + j] = fh[7 - j];
+}
+
+// ---- pass C', single-substream tracks: filters + rematrix + interleaved output ---------
+//
+// One lane per segment runs the recurrences of all NCH channels frame by frame
+// (the channels are independent chains: instruction-level parallelism), applies
+// the access unit's matrices / bypass bits / output shifts in registers (the noise
+// generator simply steps along with the frames) and parks the finished frames in
+// a shared-memory patch [lane][32 frames][NCH].  Every 32 frames the warp writes
+// the patch out row by row: 32 * NCH consecutive ints per segment, coalesced.
+// Runs after the frame counts are final (it writes straight into the PCM buffer).
+#define OUT_WARPS 4
+template <int NCH>
+__global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, const DecWork *__restrict__ work,
+                                                                   uint32_t n_work, uint32_t n_warps)
+{
+    extern __shared__ int32_t out_sm[];
+    constexpr int ROW = 32 * NCH + 1;                    // one segment's 32 frames (+1: bank spread)
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * OUT_WARPS + wib;
+    if (warp >= n_warps) return;
+    int32_t *patch = out_sm + (size_t)wib * 32 * ROW;
+    // (group, substream) of this warp; only single-substream tracks are handled here
+    uint32_t lo = 0, hi = n_work;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
+    }
+    const DecWork W = work[lo];
+    const TrackDev &T = m.tracks[W.track];
+    if (T.nss != 1) return;
+    const GroupDev &G = m.groups[T.grp_base + (warp - W.warp0)];
+    const uint32_t nominal = T.au_nominal, cap = G.cap;
+
+    // per lane: its segment (or nothing)
+    const bool have = lane < G.nseg;
+    const uint32_t seg = G.seg0 + (have ? lane : 0);
+    const SegDev &S = m.segs[seg];
+    const bool mine = have && !(m.ss_flags_fast[seg] & SEG_FALLBACK) && S.frames > 0;
+    const uint32_t my_frames = mine ? S.frames : 0;
+    uint32_t max_frames = my_frames;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) max_frames = max(max_frames, __shfl_xor_sync(0xFFFFFFFFu, max_frames, d));
+    if (!max_frames) return;
+
+    const AuSnap *snaps = m.au_snap;
+    const FiltSnap *fsnaps = m.filt_snap;
+    const uint32_t c0 = mine ? snaps[S.au_base].min_ch : 0;      // 0 for a single substream
+    int32_t fh[NCH][8], ih[NCH][8], cf[NCH][8], ci[NCH][8];
+    uint32_t shift[NCH], q[NCH];
+#pragma unroll
+    for (int cc = 0; cc < NCH; cc++) {
+        shift[cc] = 0; q[cc] = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { fh[cc][j] = 0; ih[cc][j] = 0; cf[cc][j] = 0; ci[cc][j] = 0; }
+    }
+    const int32_t *tile = m.tiles + G.tile_off + lane + (uint64_t)c0 * DVDA_LANES;
+    const uint8_t *byp = m.bypass + G.byp_off + lane;
+    const uint32_t tile_step = NCH * DVDA_LANES;                 // single substream: nch == NCH
+    int32_t *const pcm_row = m.pcm + T.out_base;
+    const bool plain_order = !(T.assignment >= 0x12 && T.assignment <= 0x14);
+
+    uint32_t au_left = 0, a = 0, seed = 0, pset = 0xFFFFFFFFu;
+    const ParamSet *P = nullptr;
+    bool trivial = true;
+    for (uint32_t f0 = 0; f0 < max_frames; f0 += 32) {
+        // ---- 32 frames of this lane's segment into the patch
+        for (uint32_t fb = 0; fb < 32; fb += 8) {
+            const uint32_t f = f0 + fb;
+            if (f < my_frames) {
+                if (au_left == 0) {
+                    // next access unit: filter parameters of every channel, rematrix parameters
+                    const uint32_t A = S.au_base + a;
+#pragma unroll
+                    for (int cc = 0; cc < NCH; cc++) {
+                        const FiltSnap fs = fsnaps[(uint64_t)A * 4 + cc];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { cf[cc][j] = fs.cf[j]; ci[cc][j] = fs.ci[j]; if (fs.ist_new) ih[cc][j] = fs.ist[j]; }
+                        shift[cc] = fs.shift; q[cc] = fs.q;
+                    }
+                    const AuDev au = m.au[A];
+                    seed = au.seed;
+                    if (au.pset != pset) {
+                        pset = au.pset;
+                        P = &m.psets[pset & 0x7FFFFFFFu];
+                        trivial = (pset & 0x80000000u) && plain_order;
+                    }
+                    au_left = nominal;
+                    a++;
+                }
+                int32_t r[8][NCH];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+#pragma unroll
+                    for (int cc = 0; cc < NCH; cc++)
+                        r[j][cc] = (f + j < cap) ? tile[(uint64_t)(f + j) * tile_step + cc * DVDA_LANES] : 0;
+                uint32_t bm[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) bm[j] = (!trivial && f + j < cap) ? byp[(uint64_t)(f + j) * DVDA_LANES] : 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    int32_t v[DVDA_MAX_CH];
+#pragma unroll
+                    for (int c = 0; c < DVDA_MAX_CH; c++) v[c] = 0;
+#pragma unroll
+                    for (int cc = 0; cc < NCH; cc++) {
+                        long long s0 = 0, s1 = 0;
+#pragma unroll
+                        for (int t = 7; t >= 0; t--) {  // oldest taps first: short dependent chain
+                            s0 = mad_wide(cf[cc][t], fh[cc][(t - j) & 7], s0);
+                            s1 = mad_wide(ci[cc][t], ih[cc][(t - j) & 7], s1);
+                        }
+                        const int32_t ssum = (int32_t)((s0 + s1) >> shift[cc]);
+                        int32_t x = (int32_t)((uint32_t)ssum + (uint32_t)r[j][cc]);
+                        x = (x >> q[cc]) << q[cc];
+                        fh[cc][(7 - j) & 7] = x;
+                        ih[cc][(7 - j) & 7] = (int32_t)((uint32_t)x - (uint32_t)ssum);
+                        v[cc] = x;
+                    }
+                    int32_t *dst = patch + lane * ROW + (fb + j) * NCH;
+                    if (trivial) {
+#pragma unroll
+                        for (int cc = 0; cc < NCH; cc++) dst[cc] = v[cc];
+                    } else {
+                        // noise, matrices in order, bypass bit, output shift, RIFF WAVE order (mlp.c:504-538, 1308-1358)
+                        const uint32_t sh = (seed >> 7) & 0xFFFF;
+                        const int32_t n0 = (int32_t)((uint32_t)(int32_t)(int8_t)(seed >> 15) << P->noise_shift);
+                        const int32_t n1 = (int32_t)((uint32_t)(int32_t)(int8_t)sh << P->noise_shift);
+                        const uint32_t ml = P->matrix_len, mmc = P->mmc;
+                        for (uint32_t k = 0; k < ml; k++) {
+                            long long sum = 0;
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) sum += (long long)v[c] * P->coeff[k][c];
+                            sum += (long long)n0 * P->coeff[k][mmc + 1];
+                            sum += (long long)n1 * P->coeff[k][mmc + 2];
+                            const uint32_t oc = P->out_ch[k], qq = P->q[oc];
+                            const int32_t rr = (((int32_t)(sum >> 14)) >> qq << qq) + (int32_t)((bm[j] >> k) & 1);
+#pragma unroll
+                            for (int c = 0; c < NCH; c++) if ((uint32_t)c == oc) v[c] = rr;
+                        }
+#pragma unroll
+                        for (int c = 0; c < NCH; c++)
+                            dst[wave_slot(T.assignment, c)] = (int32_t)((uint32_t)v[c] << P->out_shift[c]);
+                    }
+                    seed = noise_step(seed);
+                }
+                au_left -= 8;
+            }
+        }
+        __syncwarp();
+        // ---- flush: row l = 32 frames of segment l, contiguous in the output
+        for (uint32_t l = 0; l < G.nseg; l++) {
+            const uint32_t fr = __shfl_sync(0xFFFFFFFFu, my_frames, l);
+            if (f0 >= fr) continue;
+            const uint32_t nfr = min(32u, fr - f0);
+            const uint64_t base = (__shfl_sync(0xFFFFFFFFu, (unsigned long long)(mine ? S.frame0 : 0), l) + f0) * NCH;
+            const int32_t *src = patch + l * ROW;
+            for (uint32_t i = lane; i < nfr * NCH; i += 32) pcm_row[base + i] = src[i];
+        }
+        __syncwarp();
+    }
+    // FIR tails for a following segment that needs them
+    if (mine) {
+        int32_t *tail = m.fir_tail + (uint64_t)seg * (DVDA_MAX_CH * 8);
+#pragma unroll
+        for (int cc = 0; cc < NCH; cc++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) tail[(c0 + cc) * 8 + j] = fh[cc][7 - j];
+    }
+}
+
+template <int NCH>
+static int launch_one_filter_out(MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
+{
+    if (!n_warps) return 0;
+    const size_t smem = (size_t)OUT_WARPS * 32 * (32 * NCH + 1) * sizeof(int32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    LAUNCH(k_mlp_filter_out<NCH>, div_up_u32(n_warps, OUT_WARPS), OUT_WARPS * 32, smem, s, m, work, n_work, n_warps);
+    return 0;
+}
+
+int launch_mlp_filter_out(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s)
+{
+    if (launch_one_filter_out<1>(m, work[1], n_work[1], n_warps[1], s)) return -1;
+    if (launch_one_filter_out<2>(m, work[2], n_work[2], n_warps[2], s)) return -1;
+    if (launch_one_filter_out<3>(m, work[3], n_work[3], n_warps[3], s)) return -1;
+    if (launch_one_filter_out<4>(m, work[4], n_work[4], n_warps[4], s)) return -1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 #define DEC_WARPS 4
@@ -1354,6 +1559,19 @@ __global__ void __launch_bounds__(128) k_mlp_filter(MlpTables m, const DecWork *
     filter_channel_segment(m, job.seg, job.k, w % NCH, lane);
 }
 
+// A segment that needs its predecessor's FIR history is decoded by the complete decoder
+// (+ k_carry_fix), which reads the predecessor's stored tail: have the complete decoder
+// produce that one too (the fused output pass would store it too late).
+__global__ void k_flag_predecessors(MlpTables m)
+{
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t seg = idx >> 1, k = idx & 1;
+    if (seg >= m.nseg) return;
+    if (!(m.ss_flags[k * m.nseg + seg] & SEG_WANTS_PREV)) return;
+    const TrackDev &T = m.tracks[m.segs[seg].track];
+    if (seg > T.seg_base) atomicOr(&m.ss_flags[k * m.nseg + seg - 1], SEG_FALLBACK);
+}
+
 size_t au_snap_bytes() { return sizeof(AuSnap); }
 size_t filt_snap_bytes() { return sizeof(FiltSnap); }
 
@@ -1384,6 +1602,7 @@ int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_
         if (launch_fast_pass<3>(pass, m, work[3], n_work[3], n_warps[3], s)) return -1;
         if (launch_fast_pass<4>(pass, m, work[4], n_work[4], n_warps[4], s)) return -1;
     }
+    LAUNCH(k_flag_predecessors, div_up_u32((uint64_t)m.nseg * 2, 256), 256, 0, s, m);
     CUDA_TRY(cudaEventRecord(ev[3], s));
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1529,15 +1748,6 @@ int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, cudaStrea
 
 // ---------------------------------------------------------------- rematrix
 
-// RIFF WAVE slot of MLP channel c (table at mlp.c:416-438): identity except for
-// assignments 0x12-0x14
-__device__ __forceinline__ uint32_t wave_slot(uint32_t assignment, uint32_t c)
-{
-    if (assignment == 0x12 || assignment == 0x13) return (0x24310u >> (4 * c)) & 15;      // 0,1,3,4,2
-    if (assignment == 0x14) return (0x325410u >> (4 * c)) & 15;                          // 0,1,4,5,2,3
-    return c;
-}
-
 #define RM_THREADS 256
 
 // One block per (group, 32-frame chunk).  Loads the [32 frames][nch][32 lanes]
@@ -1563,6 +1773,11 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m, const uint
     const uint32_t f0 = (uint32_t)(chunk - grp_chunk_base[g]) * 32;
     const uint32_t nf = min(32u, G.cap - f0);
     int32_t *bsm = sm + nch * 32 * 33;
+    if (m.fast && T.nss == 1 && T.channels <= 4) {
+        // segments the fused filter + output pass has written need nothing here
+        const int left = (threadIdx.x < G.nseg) && (m.ss_flags_fast[G.seg0 + threadIdx.x] & SEG_FALLBACK);
+        if (!__syncthreads_or(left)) return;
+    }
 
     // coalesced load: consecutive threads read consecutive lanes
     const int32_t *src = m.tiles + G.tile_off + (uint64_t)f0 * nch * DVDA_LANES;
@@ -1581,6 +1796,8 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m, const uint
         const SegDev &S = m.segs[G.seg0 + l];
         const uint32_t F = f0 + f;                       // frame inside the segment
         if (F >= S.frames) continue;
+        // already written by the fused filter + output pass of the fast path?
+        if (m.fast && T.nss == 1 && T.channels <= 4 && !(m.ss_flags_fast[G.seg0 + l] & SEG_FALLBACK)) continue;
         // access unit holding frame F
         const uint32_t n_ok = min(S.n_au, S.err_au);
         uint32_t ai = min(F / nominal, n_ok - 1);
