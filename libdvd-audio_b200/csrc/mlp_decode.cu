@@ -156,7 +156,7 @@ int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
 // cache line per lane and — worse — any per-lane "refill when low" branch
 // diverges: an event that is rare for one lane happens almost every step for
 // some lane of the warp.  So:
-//   * each lane owns a 512-byte ring in shared memory (eight 64-byte chunks),
+//   * each lane owns a 256-byte ring in shared memory (four 64-byte chunks),
 //     layout [16-byte slot][lane];
 //   * it fills the ring itself with cp.async (16 bytes per copy, L2 -> shared),
 //     at warp-uniform points (top of every 8-frame iteration): up to two chunks,
@@ -168,7 +168,7 @@ int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
 #ifndef DVDA_UNROLL
 #define DVDA_UNROLL 8
 #endif
-#define RING_SLOTS 32                 // 16-byte slots per lane: 512 bytes
+#define RING_SLOTS 16                 // 16-byte slots per lane: 256 bytes
 #define CHUNK_WORDS 16                // 64 bytes per cp.async group
 #define RING_WORDS (RING_SLOTS * 4)
 
@@ -198,8 +198,9 @@ __device__ __forceinline__ void rd_issue_chunk(Rd &r, uint32_t c)
     for (int t = 0; t < 4; t++) cp_async16(r.ring + (((c * 4 + t) & (RING_SLOTS - 1)) << 9), g + t * 16);
 }
 // may chunk fill_c be written?  Its slot held chunk fill_c - 8, which must lie
-// entirely behind the read position.
-__device__ __forceinline__ bool rd_room(const Rd &r) { return (int32_t)((r.fill_c - 7) * CHUNK_WORDS - r.next_w) <= 0; }
+// entirely behind the read position (the slot held chunk fill_c - RING_CHUNKS).
+#define RING_CHUNKS (RING_SLOTS / 4)
+__device__ __forceinline__ bool rd_room(const Rd &r) { return (int32_t)((r.fill_c - (RING_CHUNKS - 1)) * CHUNK_WORDS - r.next_w) <= 0; }
 
 __device__ __forceinline__ void rd_init(Rd &r, const uint8_t *es, uint32_t ring)
 {
@@ -207,7 +208,7 @@ __device__ __forceinline__ void rd_init(Rd &r, const uint8_t *es, uint32_t ring)
 }
 
 // cold: make sure words [next_w, next_w + need) are in the ring
-__device__ __noinline__ void rd_slow_fill(Rd &r, uint32_t need)
+__device__ __forceinline__ void rd_slow_fill(Rd &r, uint32_t need)
 {
     while (r.fill_c * CHUNK_WORDS < r.next_w + need + CHUNK_WORDS && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
     cp_commit();
@@ -224,7 +225,7 @@ __device__ __forceinline__ void rd_prefetch(Rd &r, uint32_t need)
     const uint32_t landed = r.fill_c * CHUNK_WORDS;
 #pragma unroll
     for (int t = 0; t < 2; t++) {
-        if (r.fill_c * CHUNK_WORDS < r.next_w + 96 && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
+        if (r.fill_c * CHUNK_WORDS < r.next_w + RING_WORDS - CHUNK_WORDS && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
         cp_commit();
     }
     cp_wait<2>();
@@ -709,13 +710,15 @@ __device__ __forceinline__ uint32_t decode_block_fast(const MlpTables &m, const 
 
     // words 8 frames can consume at most (33 bits per sample, 6 bypass bits per frame), plus
     // the word fetched ahead
-    const uint32_t need8 = (8 * (NCH * 33 + 6) + 31) / 32 + 2;
+    const uint32_t need8 = (4 * (NCH * 33 + 6) + 31) / 32 + 2;      // per four frames (the ring is small)
     uint32_t i = 0;
 #if DVDA_UNROLL == 8
     for (; i + 8 <= n; i += 8) {
         rd_prefetch(b, need8);
         rd_hot_begin(b);
         DVDA_FRAME(0) DVDA_FRAME(1) DVDA_FRAME(2) DVDA_FRAME(3)
+        rd_prefetch(b, need8);
+        rd_hot_begin(b);
         DVDA_FRAME(4) DVDA_FRAME(5) DVDA_FRAME(6) DVDA_FRAME(7)
         if ((bad & 0x8000) || rd_pos(b) > end_bits) return 0;
     }
