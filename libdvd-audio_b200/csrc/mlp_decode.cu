@@ -1253,39 +1253,48 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
 
 // ---- pass C', single-substream tracks: filters + rematrix + interleaved output ---------
 //
-// One lane per segment runs the recurrences of all NCH channels frame by frame
-// (the channels are independent chains: instruction-level parallelism), applies
-// the access unit's matrices / bypass bits / output shifts in registers (the noise
-// generator simply steps along with the frames) and parks the finished frames in
-// a shared-memory patch [lane][32 frames][NCH].  Every 32 frames the warp writes
-// the patch out row by row: 32 * NCH consecutive ints per segment, coalesced.
-// Runs after the frame counts are final (it writes straight into the PCM buffer).
+// One lane per (segment, channel): a warp takes SPW = 32 / NCH segments of a
+// group, lane = segment-in-warp * NCH + channel, so the NCH recurrences of a
+// segment run in neighbouring lanes.  Residuals come from the tile (the next 8
+// frames are loaded while the current 8 are filtered).  For access units with
+// non-trivial parameters the NCH lanes of a segment exchange their samples by
+// shuffle and each applies the matrices / bypass bits / output shift for the whole
+// frame (the noise generator simply steps along), keeping its own channel.
+// Finished frames are parked in a shared-memory patch [segment][32 frames][NCH]
+// and written out row by row every 32 frames: 32 * NCH consecutive ints per
+// segment, coalesced.  Runs after the frame counts are final (it writes straight
+// into the PCM buffer).
 #define OUT_WARPS 4
 template <int NCH>
 __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, const DecWork *__restrict__ work,
                                                                    uint32_t n_work, uint32_t n_warps)
 {
     extern __shared__ int32_t out_sm[];
+    constexpr int SPW = 32 / NCH;                        // segments per warp
+    constexpr int SUB = (32 + SPW - 1) / SPW;            // warps per group
     constexpr int ROW = 32 * NCH + 1;                    // one segment's 32 frames (+1: bank spread)
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * OUT_WARPS + wib;
-    if (warp >= n_warps) return;
-    int32_t *patch = out_sm + (size_t)wib * 32 * ROW;
+    if (warp >= n_warps * SUB) return;
+    int32_t *patch = out_sm + (size_t)wib * SPW * ROW;
+    const uint32_t gw = warp / SUB, sub = warp % SUB;
     // (group, substream) of this warp; only single-substream tracks are handled here
     uint32_t lo = 0, hi = n_work;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
+        if (work[mid].warp0 <= gw) lo = mid; else hi = mid;
     }
     const DecWork W = work[lo];
     const TrackDev &T = m.tracks[W.track];
     if (T.nss != 1) return;
-    const GroupDev &G = m.groups[T.grp_base + (warp - W.warp0)];
+    const GroupDev &G = m.groups[T.grp_base + (gw - W.warp0)];
     const uint32_t nominal = T.au_nominal, cap = G.cap;
 
-    // per lane: its segment (or nothing)
-    const bool have = lane < G.nseg;
-    const uint32_t seg = G.seg0 + (have ? lane : 0);
+    // per lane: its segment and channel (or nothing)
+    const uint32_t sl = lane / NCH, cc = lane % NCH;
+    const uint32_t sg = sub * SPW + sl;                  // segment inside the group = column of the tile
+    const bool have = sl < SPW && sg < G.nseg;
+    const uint32_t seg = G.seg0 + (have ? sg : 0);
     const SegDev &S = m.segs[seg];
     const bool mine = have && !(m.ss_flags_fast[seg] & SEG_FALLBACK) && S.frames > 0;
     const uint32_t my_frames = mine ? S.frames : 0;
@@ -1294,86 +1303,80 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
     for (int d = 16; d > 0; d >>= 1) max_frames = max(max_frames, __shfl_xor_sync(0xFFFFFFFFu, max_frames, d));
     if (!max_frames) return;
 
-    const AuSnap *snaps = m.au_snap;
     const FiltSnap *fsnaps = m.filt_snap;
-    const uint32_t c0 = mine ? snaps[S.au_base].min_ch : 0;      // 0 for a single substream
-    int32_t fh[NCH][8], ih[NCH][8], cf[NCH][8], ci[NCH][8];
-    uint32_t shift[NCH], q[NCH];
+    const uint32_t c0 = mine ? m.au_snap[S.au_base].min_ch : 0;  // 0 for a single substream
+    int32_t fh[8], ih[8], cf[8], ci[8];
 #pragma unroll
-    for (int cc = 0; cc < NCH; cc++) {
-        shift[cc] = 0; q[cc] = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { fh[cc][j] = 0; ih[cc][j] = 0; cf[cc][j] = 0; ci[cc][j] = 0; }
-    }
-    const int32_t *tile = m.tiles + G.tile_off + lane + (uint64_t)c0 * DVDA_LANES;
-    const uint8_t *byp = m.bypass + G.byp_off + lane;
+    for (int j = 0; j < 8; j++) { fh[j] = 0; ih[j] = 0; cf[j] = 0; ci[j] = 0; }
+    uint32_t shift = 0, q = 0;
+    const int32_t *tile = m.tiles + G.tile_off + sg + (uint64_t)(c0 + cc) * DVDA_LANES;
+    const uint8_t *byp = m.bypass + G.byp_off + sg;
     const uint32_t tile_step = NCH * DVDA_LANES;                 // single substream: nch == NCH
     int32_t *const pcm_row = m.pcm + T.out_base;
     const bool plain_order = !(T.assignment >= 0x12 && T.assignment <= 0x14);
+    const uint32_t out_slot = wave_slot(T.assignment, cc);
+    const uint32_t group_lane0 = sl * NCH;                       // first lane of this segment's channels
 
     uint32_t au_left = 0, a = 0, seed = 0, pset = 0xFFFFFFFFu;
     const ParamSet *P = nullptr;
     bool trivial = true;
+    int32_t nx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) nx[j] = (mine && (uint32_t)j < cap) ? tile[(uint64_t)j * tile_step] : 0;
+
     for (uint32_t f0 = 0; f0 < max_frames; f0 += 32) {
-        // ---- 32 frames of this lane's segment into the patch
+        // ---- 32 frames of this lane's (segment, channel) into the patch
         for (uint32_t fb = 0; fb < 32; fb += 8) {
             const uint32_t f = f0 + fb;
-            if (f < my_frames) {
-                if (au_left == 0) {
-                    // next access unit: filter parameters of every channel, rematrix parameters
-                    const uint32_t A = S.au_base + a;
+            const bool act = f < my_frames;
+            if (act && au_left == 0) {
+                // next access unit: this channel's filter parameters, the frame's rematrix parameters
+                const uint32_t A = S.au_base + a;
+                const FiltSnap fs = fsnaps[(uint64_t)A * 4 + cc];
 #pragma unroll
-                    for (int cc = 0; cc < NCH; cc++) {
-                        const FiltSnap fs = fsnaps[(uint64_t)A * 4 + cc];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) { cf[cc][j] = fs.cf[j]; ci[cc][j] = fs.ci[j]; if (fs.ist_new) ih[cc][j] = fs.ist[j]; }
-                        shift[cc] = fs.shift; q[cc] = fs.q;
-                    }
-                    const AuDev au = m.au[A];
-                    seed = au.seed;
-                    if (au.pset != pset) {
-                        pset = au.pset;
-                        P = &m.psets[pset & 0x7FFFFFFFu];
-                        trivial = (pset & 0x80000000u) && plain_order;
-                    }
-                    au_left = nominal;
-                    a++;
+                for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
+                shift = fs.shift; q = fs.q;
+                const AuDev au = m.au[A];
+                seed = au.seed;
+                if (au.pset != pset) {
+                    pset = au.pset;
+                    P = &m.psets[pset & 0x7FFFFFFFu];
+                    trivial = (pset & 0x80000000u) && plain_order;
                 }
-                int32_t r[8][NCH];
+                au_left = nominal;
+                a++;
+            }
+            int32_t r[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++)
+            for (int j = 0; j < 8; j++) r[j] = nx[j];
 #pragma unroll
-                    for (int cc = 0; cc < NCH; cc++)
-                        r[j][cc] = (f + j < cap) ? tile[(uint64_t)(f + j) * tile_step + cc * DVDA_LANES] : 0;
-                uint32_t bm[8];
+            for (int j = 0; j < 8; j++) nx[j] = (mine && f + 8 + j < my_frames && f + 8 + j < cap) ? tile[(uint64_t)(f + 8 + j) * tile_step] : 0;
+            uint32_t bm[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) bm[j] = (!trivial && f + j < cap) ? byp[(uint64_t)(f + j) * DVDA_LANES] : 0;
+            for (int j = 0; j < 8; j++) bm[j] = (act && !trivial && f + j < cap) ? byp[(uint64_t)(f + j) * DVDA_LANES] : 0;
+            // the shuffles below need the whole warp: lanes without work just run along on zeros
+            const bool any_matrix = __any_sync(0xFFFFFFFFu, act && !trivial);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    int32_t v[DVDA_MAX_CH];
+            for (int j = 0; j < 8; j++) {
+                long long s0 = 0, s1 = 0;
 #pragma unroll
-                    for (int c = 0; c < DVDA_MAX_CH; c++) v[c] = 0;
+                for (int t = 7; t >= 0; t--) {          // oldest taps first: short dependent chain
+                    s0 = mad_wide(cf[t], fh[(t - j) & 7], s0);
+                    s1 = mad_wide(ci[t], ih[(t - j) & 7], s1);
+                }
+                const int32_t ssum = (int32_t)((s0 + s1) >> shift);
+                int32_t x = (int32_t)((uint32_t)ssum + (uint32_t)r[j]);
+                x = (x >> q) << q;
+                fh[(7 - j) & 7] = x;
+                ih[(7 - j) & 7] = (int32_t)((uint32_t)x - (uint32_t)ssum);
+                int32_t out = x;
+                if (any_matrix) {
+                    // all channels of the frame, from the neighbouring lanes
+                    int32_t v[NCH];
 #pragma unroll
-                    for (int cc = 0; cc < NCH; cc++) {
-                        long long s0 = 0, s1 = 0;
-#pragma unroll
-                        for (int t = 7; t >= 0; t--) {  // oldest taps first: short dependent chain
-                            s0 = mad_wide(cf[cc][t], fh[cc][(t - j) & 7], s0);
-                            s1 = mad_wide(ci[cc][t], ih[cc][(t - j) & 7], s1);
-                        }
-                        const int32_t ssum = (int32_t)((s0 + s1) >> shift[cc]);
-                        int32_t x = (int32_t)((uint32_t)ssum + (uint32_t)r[j][cc]);
-                        x = (x >> q[cc]) << q[cc];
-                        fh[cc][(7 - j) & 7] = x;
-                        ih[cc][(7 - j) & 7] = (int32_t)((uint32_t)x - (uint32_t)ssum);
-                        v[cc] = x;
-                    }
-                    int32_t *dst = patch + lane * ROW + (fb + j) * NCH;
-                    if (trivial) {
-#pragma unroll
-                        for (int cc = 0; cc < NCH; cc++) dst[cc] = v[cc];
-                    } else {
-                        // noise, matrices in order, bypass bit, output shift, RIFF WAVE order (mlp.c:504-538, 1308-1358)
+                    for (int c = 0; c < NCH; c++) v[c] = __shfl_sync(0xFFFFFFFFu, x, group_lane0 + c);
+                    if (act && !trivial) {
+                        // noise, matrices in order, bypass bit, output shift (mlp.c:504-538, 1308-1358)
                         const uint32_t sh = (seed >> 7) & 0xFFFF;
                         const int32_t n0 = (int32_t)((uint32_t)(int32_t)(int8_t)(seed >> 15) << P->noise_shift);
                         const int32_t n1 = (int32_t)((uint32_t)(int32_t)(int8_t)sh << P->noise_shift);
@@ -1389,34 +1392,34 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
 #pragma unroll
                             for (int c = 0; c < NCH; c++) if ((uint32_t)c == oc) v[c] = rr;
                         }
+                        int32_t mineval = 0;
 #pragma unroll
-                        for (int c = 0; c < NCH; c++)
-                            dst[wave_slot(T.assignment, c)] = (int32_t)((uint32_t)v[c] << P->out_shift[c]);
+                        for (int c = 0; c < NCH; c++) if ((uint32_t)c == cc) mineval = v[c];
+                        out = (int32_t)((uint32_t)mineval << P->out_shift[cc]);
                     }
-                    seed = noise_step(seed);
                 }
-                au_left -= 8;
+                if (act) patch[sl * ROW + (fb + j) * NCH + out_slot] = out;
+                seed = noise_step(seed);
             }
+            if (act) au_left -= 8;
         }
         __syncwarp();
-        // ---- flush: row l = 32 frames of segment l, contiguous in the output
-        for (uint32_t l = 0; l < G.nseg; l++) {
-            const uint32_t fr = __shfl_sync(0xFFFFFFFFu, my_frames, l);
+        // ---- flush: row s = 32 frames of segment s, contiguous in the output
+        for (uint32_t s2 = 0; s2 < (uint32_t)SPW; s2++) {
+            const uint32_t fr = __shfl_sync(0xFFFFFFFFu, my_frames, s2 * NCH);
             if (f0 >= fr) continue;
             const uint32_t nfr = min(32u, fr - f0);
-            const uint64_t base = (__shfl_sync(0xFFFFFFFFu, (unsigned long long)(mine ? S.frame0 : 0), l) + f0) * NCH;
-            const int32_t *src = patch + l * ROW;
+            const uint64_t base = (__shfl_sync(0xFFFFFFFFu, (unsigned long long)(mine ? S.frame0 : 0), s2 * NCH) + f0) * NCH;
+            const int32_t *src = patch + s2 * ROW;
             for (uint32_t i = lane; i < nfr * NCH; i += 32) pcm_row[base + i] = src[i];
         }
         __syncwarp();
     }
-    // FIR tails for a following segment that needs them
+    // FIR tail for a following segment that needs it
     if (mine) {
         int32_t *tail = m.fir_tail + (uint64_t)seg * (DVDA_MAX_CH * 8);
 #pragma unroll
-        for (int cc = 0; cc < NCH; cc++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) tail[(c0 + cc) * 8 + j] = fh[cc][7 - j];
+        for (int j = 0; j < 8; j++) tail[(c0 + cc) * 8 + j] = fh[7 - j];
     }
 }
 
@@ -1424,13 +1427,14 @@ template <int NCH>
 static int launch_one_filter_out(MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
 {
     if (!n_warps) return 0;
-    const size_t smem = (size_t)OUT_WARPS * 32 * (32 * NCH + 1) * sizeof(int32_t);
+    constexpr int SPW = 32 / NCH, SUB = (32 + SPW - 1) / SPW;
+    const size_t smem = (size_t)OUT_WARPS * SPW * (32 * NCH + 1) * sizeof(int32_t);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    LAUNCH(k_mlp_filter_out<NCH>, div_up_u32(n_warps, OUT_WARPS), OUT_WARPS * 32, smem, s, m, work, n_work, n_warps);
+    LAUNCH(k_mlp_filter_out<NCH>, div_up_u32((uint64_t)n_warps * SUB, OUT_WARPS), OUT_WARPS * 32, smem, s, m, work, n_work, n_warps);
     return 0;
 }
 
