@@ -38,6 +38,7 @@
 #define SEG_OVERFLOW 4u        // more frames than the tile has room for
 #define SEG_FALLBACK 8u        // the three-pass fast path gave up: decode with the complete decoder
 #define SEG_WANTS_PREV 16u     // ... because it needs the previous segment's FIR history
+#define STATUS_WANTS_REMATRIX 0x100u   // k_seg_finalize -> host: some segment still needs k_rematrix (fast path)
 
 // TrackDev.cont / dvdagpu_track_desc.flags
 #define TRACK_CONT_PREV 1u

@@ -462,8 +462,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     m.es = es; m.es_total = es_total; m.pk_es = pk_es; m.np = np;
     m.tracks = d_tracks; m.n_tracks = n_tracks; m.nseg = nseg; m.ngroups = ngroups;
     uint32_t nau = 0;
-    uint64_t total_chunks = 0;
-    uint64_t *grp_chunk_base = nullptr;
+    uint32_t max_chunks = 0, status = 0;
     if (nseg) {
         ENSURE(B_SEGS, (size_t)nseg * sizeof(SegDev));
         ENSURE(B_SEG_NAU, (size_t)nseg * 4); ENSURE(B_SEG_AU_BASE, (size_t)(nseg + 1) * 4);
@@ -492,13 +491,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         TIMED(DVDAGPU_K_CHECKDATA, launch_checkdata(m, seg_au_base, s));
         ENSURE(B_GROUPS, (size_t)ngroups * sizeof(GroupDev));
         ENSURE(B_GRP_CELLS, (size_t)ngroups * 4); ENSURE(B_CELL_BASE, (size_t)(ngroups + 1) * 8);
-        ENSURE(B_GRP_CHUNKS, (size_t)ngroups * 4); ENSURE(B_GRP_CHUNK_BASE, (size_t)(ngroups + 1) * 8);
+        ENSURE(B_GRP_CHUNKS, (size_t)ngroups * 4);
         ENSURE(B_SEG_FRAMES, (size_t)nseg * 4); ENSURE(B_SEG_FRAME_SCAN, (size_t)(nseg + 1) * 8);
         ENSURE(B_STATUS, 64);
         m.groups = c->buf[B_GROUPS].as<GroupDev>();
         uint32_t *grp_cells = c->buf[B_GRP_CELLS].as<uint32_t>(), *grp_chunks = c->buf[B_GRP_CHUNKS].as<uint32_t>();
         uint64_t *cell_base = c->buf[B_CELL_BASE].as<uint64_t>();
-        grp_chunk_base = c->buf[B_GRP_CHUNK_BASE].as<uint64_t>();
         uint32_t *seg_frames = c->buf[B_SEG_FRAMES].as<uint32_t>();
         uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
         uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
@@ -516,12 +514,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
             TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, d_status + 1, s));
             TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
-            TRY(scan_u32_to_u64(grp_chunks, grp_chunk_base, ngroups, tmp, tmp_bytes, s));
             uint64_t cells = 0;
             TRY(read_back(c, cell_base + ngroups, &cells));
-            TRY(read_back(c, grp_chunk_base + ngroups, &total_chunks));
-            TRY(read_back(c, d_status + 1, &m.max_au));
-            ENSURE(B_TILES, (cells * DVDA_LANES + 64) * sizeof(int32_t));
+            struct { uint32_t au, chunks; } most = {0, 0};
+            TRY(small_d2h(c, &most, d_status + 1, sizeof most));
+            m.max_au = most.au; max_chunks = most.chunks;
+            ENSURE(B_TILES, (cells * DVDA_LANES + 64 + 16 * DVDA_MAX_CH * DVDA_LANES) * sizeof(int32_t));   // 16 frames of slack: the filter passes read ahead
             ENSURE(B_BYPASS, cells * DVDA_LANES + 64);
             m.tiles = c->buf[B_TILES].as<int32_t>(); m.bypass = c->buf[B_BYPASS].as<uint8_t>();
             TRY(launch_group_offsets(m.groups, ngroups, cell_base, s));
@@ -542,7 +540,6 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
             TIMED(DVDAGPU_K_CARRY_FIX, launch_carry_fix(m, s));
             TRY(launch_seg_finalize(m, seg_frames, d_status, s));
-            uint32_t status = 0;
             TRY(read_back(c, d_status, &status));
             if (!(status & SEG_OVERFLOW)) break;
             if (attempt == 1) { dvdagpu_set_error("tile overflow persists"); return -1; }
@@ -597,7 +594,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         TRY(launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
         CUDA_TRY(cudaEventRecord(c->fev[5], s));
     }
-    if (nseg && total_chunks) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, total_chunks, grp_chunk_base, mlp_channel_mask, s));
+    if (nseg && max_chunks && (!m.fast || (status & STATUS_WANTS_REMATRIX))) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, max_chunks, mlp_channel_mask, s));
     if (any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, np, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));
     CUDA_TRY(cudaEventRecord(c->ev[4], s));
     CUDA_TRY(cudaStreamSynchronize(s));

@@ -105,4 +105,4 @@ int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_
                     cudaEvent_t ev[4], cudaStream_t s);
 int launch_seg_finalize(MlpTables m, uint32_t *seg_frames, uint32_t *status, cudaStream_t s);
 int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, cudaStream_t s);
-int launch_rematrix(MlpTables m, uint64_t total_chunks, const uint64_t *grp_chunk_base, uint32_t channel_mask, cudaStream_t s);
+int launch_rematrix(MlpTables m, uint32_t max_chunks, uint32_t channel_mask, cudaStream_t s);

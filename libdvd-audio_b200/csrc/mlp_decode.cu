@@ -982,7 +982,7 @@ struct AuSnap {
 struct FiltSnap {
     int16_t cf[8], ci[8];   // coefficients, zero beyond the orders
     int32_t ist[8];         // IIR history to install (age order) when ist_new
-    uint8_t shift, q, ist_new, pad;
+    uint8_t shift, q, ist_new, orders;   // orders: FIR | IIR << 4
 };
 
 // noise generator advanced by n frames
@@ -1058,7 +1058,8 @@ __device__ __forceinline__ void headers_segment(const MlpTables &m, const Decode
                 fs.ci[j] = j < C.iir_order ? (int16_t)C.iir_c[j] : (int16_t)0;
                 fs.ist[j] = (C.ist_new && j < C.ilen) ? C.ist[(C.ihead - 1 - j) & 7] : 0;
             }
-            fs.shift = (uint8_t)shift; fs.q = (uint8_t)q; fs.ist_new = C.ist_new; fs.pad = 0;
+            fs.shift = (uint8_t)shift; fs.q = (uint8_t)q; fs.ist_new = C.ist_new;
+            fs.orders = (uint8_t)(C.fir_order | C.iir_order << 4);
             fsnaps[(uint64_t)A * 4 + cc] = fs;
             C.ist_new = 0;
             C.flen = 8; C.ilen = 8;
@@ -1255,16 +1256,40 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
 //
 // One lane per (segment, channel): a warp takes SPW = 32 / NCH segments of a
 // group, lane = segment-in-warp * NCH + channel, so the NCH recurrences of a
-// segment run in neighbouring lanes.  Residuals come from the tile (the next 8
-// frames are loaded while the current 8 are filtered).  For access units with
-// non-trivial parameters the NCH lanes of a segment exchange their samples by
-// shuffle and each applies the matrices / bypass bits / output shift for the whole
-// frame (the noise generator simply steps along), keeping its own channel.
-// Finished frames are parked in a shared-memory patch [segment][32 frames][NCH]
-// and written out row by row every 32 frames: 32 * NCH consecutive ints per
-// segment, coalesced.  Runs after the frame counts are final (it writes straight
-// into the PCM buffer).
+// segment run in neighbouring lanes and all lanes step through the frames of
+// their segments together (access units have the nominal length here).
+// Residuals come from the tile; the next 8 frames are loaded while the current 8
+// are filtered (the tile carries 16 frames of slack, no bounds tests).  Per
+// access unit the warp picks the smallest compiled tap count that covers the
+// filter orders of all its lanes (0, 4 or 8 taps each for FIR and IIR).
+// Access units whose parameters ask for more than a copy (matrices, bypass bits,
+// output shift, permuted channel order) take the slow branch: the NCH lanes of
+// a segment exchange their samples by shuffle and each applies the matrices for
+// the whole frame, keeping its own channel.  Finished frames are parked in a
+// shared-memory patch [segment][32 frames][NCH] and written out row by row every
+// 32 frames: 32 * NCH consecutive ints per segment, coalesced.  Runs after the
+// frame counts are final (it writes straight into the PCM buffer).
 #define OUT_WARPS 4
+
+template <int NF, int NI>
+__device__ __forceinline__ void filt8(const int32_t (&cf)[8], const int32_t (&ci)[8], int32_t (&fh)[8], int32_t (&ih)[8],
+                                      int32_t (&r)[8], uint32_t shift, uint32_t qmask)
+{
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        long long s0 = 0, s1 = 0;
+#pragma unroll
+        for (int t = NF - 1; t >= 0; t--) s0 = mad_wide(cf[t], fh[(t - j) & 7], s0);   // oldest taps first:
+#pragma unroll
+        for (int t = NI - 1; t >= 0; t--) s1 = mad_wide(ci[t], ih[(t - j) & 7], s1);   // short dependent chain
+        const int32_t ssum = (NF + NI) ? (int32_t)((s0 + s1) >> shift) : 0;
+        const int32_t x = (int32_t)(((uint32_t)ssum + (uint32_t)r[j]) & qmask);
+        fh[(7 - j) & 7] = x;
+        ih[(7 - j) & 7] = (int32_t)((uint32_t)x - (uint32_t)ssum);
+        r[j] = x;
+    }
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, const DecWork *__restrict__ work,
                                                                    uint32_t n_work, uint32_t n_warps)
@@ -1272,11 +1297,13 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
     extern __shared__ int32_t out_sm[];
     constexpr int SPW = 32 / NCH;                        // segments per warp
     constexpr int SUB = (32 + SPW - 1) / SPW;            // warps per group
-    constexpr int ROW = 32 * NCH + 1;                    // one segment's 32 frames (+1: bank spread)
+    constexpr int ROW = 32 * NCH + NCH;                  // one segment's 32 frames (+NCH: bank = lane when parking)
+    constexpr int WARP_WORDS = SPW * (ROW + 4);          // + per segment {output base lo, hi, frames, -}
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * OUT_WARPS + wib;
     if (warp >= n_warps * SUB) return;
-    int32_t *patch = out_sm + (size_t)wib * SPW * ROW;
+    int32_t *patch = out_sm + (size_t)wib * WARP_WORDS;
+    uint32_t *meta = reinterpret_cast<uint32_t *>(patch + SPW * ROW);
     const uint32_t gw = warp / SUB, sub = warp % SUB;
     // (group, substream) of this warp; only single-substream tracks are handled here
     uint32_t lo = 0, hi = n_work;
@@ -1288,7 +1315,7 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
     const TrackDev &T = m.tracks[W.track];
     if (T.nss != 1) return;
     const GroupDev &G = m.groups[T.grp_base + (gw - W.warp0)];
-    const uint32_t nominal = T.au_nominal, cap = G.cap;
+    const uint32_t nominal = T.au_nominal;
 
     // per lane: its segment and channel (or nothing)
     const uint32_t sl = lane / NCH, cc = lane % NCH;
@@ -1298,85 +1325,116 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
     const SegDev &S = m.segs[seg];
     const bool mine = have && !(m.ss_flags_fast[seg] & SEG_FALLBACK) && S.frames > 0;
     const uint32_t my_frames = mine ? S.frames : 0;
-    uint32_t max_frames = my_frames;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) max_frames = max(max_frames, __shfl_xor_sync(0xFFFFFFFFu, max_frames, d));
+    const uint32_t max_frames = __reduce_max_sync(0xFFFFFFFFu, my_frames);
     if (!max_frames) return;
+    if (cc == 0 && sl < SPW) {
+        const uint64_t base = (mine ? S.frame0 : 0) * NCH;
+        meta[sl * 4 + 0] = (uint32_t)base; meta[sl * 4 + 1] = (uint32_t)(base >> 32); meta[sl * 4 + 2] = my_frames;
+    }
+    __syncwarp();
 
     const FiltSnap *fsnaps = m.filt_snap;
     const uint32_t c0 = mine ? m.au_snap[S.au_base].min_ch : 0;  // 0 for a single substream
     int32_t fh[8], ih[8], cf[8], ci[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) { fh[j] = 0; ih[j] = 0; cf[j] = 0; ci[j] = 0; }
-    uint32_t shift = 0, q = 0;
-    const int32_t *tile = m.tiles + G.tile_off + sg + (uint64_t)(c0 + cc) * DVDA_LANES;
-    const uint8_t *byp = m.bypass + G.byp_off + sg;
-    const uint32_t tile_step = NCH * DVDA_LANES;                 // single substream: nch == NCH
+    uint32_t shift = 0, qmask = 0xFFFFFFFFu;
+    constexpr uint32_t tile_step = NCH * DVDA_LANES;             // single substream: nch == NCH
+    const int32_t *tp = m.tiles + G.tile_off + (have ? sg : 0) + (uint64_t)(c0 + cc) * DVDA_LANES;
+    const uint8_t *byp = m.bypass + G.byp_off + (have ? sg : 0);
     int32_t *const pcm_row = m.pcm + T.out_base;
     const bool plain_order = !(T.assignment >= 0x12 && T.assignment <= 0x14);
     const uint32_t out_slot = wave_slot(T.assignment, cc);
     const uint32_t group_lane0 = sl * NCH;                       // first lane of this segment's channels
+    int32_t *const park = patch + (sl < SPW ? sl : 0) * ROW + out_slot;
 
-    uint32_t au_left = 0, a = 0, seed = 0, pset = 0xFFFFFFFFu;
+    uint32_t seed = 0, pset = 0xFFFFFFFFu, f = 0, a = 0;
     const ParamSet *P = nullptr;
     bool trivial = true;
     int32_t nx[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) nx[j] = (mine && (uint32_t)j < cap) ? tile[(uint64_t)j * tile_step] : 0;
+    for (int j = 0; j < 8; j++) nx[j] = tp[j * tile_step];
+    tp += 8 * tile_step;
 
-    for (uint32_t f0 = 0; f0 < max_frames; f0 += 32) {
-        // ---- 32 frames of this lane's (segment, channel) into the patch
-        for (uint32_t fb = 0; fb < 32; fb += 8) {
-            const uint32_t f = f0 + fb;
-            const bool act = f < my_frames;
-            if (act && au_left == 0) {
-                // next access unit: this channel's filter parameters, the frame's rematrix parameters
-                const uint32_t A = S.au_base + a;
-                const FiltSnap fs = fsnaps[(uint64_t)A * 4 + cc];
+    auto flush = [&](uint32_t f0) {
+        __syncwarp();
+        // row s = 32 frames of segment s, contiguous in the output
+#pragma unroll 4
+        for (uint32_t s2 = 0; s2 < (uint32_t)SPW; s2++) {
+            const uint32_t fr = meta[s2 * 4 + 2];
+            if (f0 >= fr) continue;
+            const uint64_t base = ((uint64_t)meta[s2 * 4 + 1] << 32 | meta[s2 * 4 + 0]) + (uint64_t)f0 * NCH;
+            const int32_t *src = patch + s2 * ROW;
+            int32_t *dst = pcm_row + base;
+            if (f0 + 32 <= fr) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
-                shift = fs.shift; q = fs.q;
-                const AuDev au = m.au[A];
-                seed = au.seed;
-                if (au.pset != pset) {
-                    pset = au.pset;
-                    P = &m.psets[pset & 0x7FFFFFFFu];
-                    trivial = (pset & 0x80000000u) && plain_order;
-                }
-                au_left = nominal;
-                a++;
+                for (int k = 0; k < NCH; k++) dst[lane + 32 * k] = src[lane + 32 * k];
+            } else {
+                const uint32_t n = (fr - f0) * NCH;
+#pragma unroll
+                for (int k = 0; k < NCH; k++) if (lane + 32 * k < n) dst[lane + 32 * k] = src[lane + 32 * k];
             }
+        }
+        __syncwarp();
+    };
+
+    while (f < max_frames) {
+        // ---- next access unit: this channel's filter parameters, the frame's rematrix parameters
+        const bool au_act = f < my_frames;
+        uint32_t cls = 0;
+        if (au_act) {
+            const uint32_t A = S.au_base + a;
+            const FiltSnap fs = fsnaps[(uint64_t)A * 4 + cc];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
+            shift = fs.shift; qmask = 0xFFFFFFFFu << fs.q;
+            cls = fs.orders;
+            const AuDev au = m.au[A];
+            seed = au.seed;
+            if (au.pset != pset) {
+                pset = au.pset;
+                P = &m.psets[pset & 0x7FFFFFFFu];
+                trivial = (pset & 0x80000000u) && plain_order;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { cf[j] = 0; ci[j] = 0; }
+        }
+        a++;
+        const uint32_t nf = __reduce_max_sync(0xFFFFFFFFu, ((cls & 15) + 3) >> 2);
+        const uint32_t ni = __reduce_max_sync(0xFFFFFFFFu, ((cls >> 4) + 3) >> 2);
+        const uint32_t code = nf * 3 + ni;
+        const bool any_matrix = __any_sync(0xFFFFFFFFu, au_act && !trivial);
+
+        for (uint32_t i = 0; i < nominal; i += 8) {
             int32_t r[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) r[j] = nx[j];
 #pragma unroll
-            for (int j = 0; j < 8; j++) nx[j] = (mine && f + 8 + j < my_frames && f + 8 + j < cap) ? tile[(uint64_t)(f + 8 + j) * tile_step] : 0;
-            uint32_t bm[8];
+            for (int j = 0; j < 8; j++) nx[j] = tp[j * tile_step];
+            tp += 8 * tile_step;
+            switch (code) {
+            case 0: filt8<0, 0>(cf, ci, fh, ih, r, shift, qmask); break;
+            case 1: filt8<0, 4>(cf, ci, fh, ih, r, shift, qmask); break;
+            case 2: filt8<0, 8>(cf, ci, fh, ih, r, shift, qmask); break;
+            case 3: filt8<4, 0>(cf, ci, fh, ih, r, shift, qmask); break;
+            case 4: filt8<4, 4>(cf, ci, fh, ih, r, shift, qmask); break;
+            case 5: filt8<4, 8>(cf, ci, fh, ih, r, shift, qmask); break;
+            case 6: filt8<8, 0>(cf, ci, fh, ih, r, shift, qmask); break;
+            case 7: filt8<8, 4>(cf, ci, fh, ih, r, shift, qmask); break;
+            default: filt8<8, 8>(cf, ci, fh, ih, r, shift, qmask); break;
+            }
+            if (any_matrix) {
+                // the shuffles need the whole warp: lanes without work just run along
+                const uint32_t fa = f < my_frames ? f : 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) bm[j] = (act && !trivial && f + j < cap) ? byp[(uint64_t)(f + j) * DVDA_LANES] : 0;
-            // the shuffles below need the whole warp: lanes without work just run along on zeros
-            const bool any_matrix = __any_sync(0xFFFFFFFFu, act && !trivial);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                long long s0 = 0, s1 = 0;
-#pragma unroll
-                for (int t = 7; t >= 0; t--) {          // oldest taps first: short dependent chain
-                    s0 = mad_wide(cf[t], fh[(t - j) & 7], s0);
-                    s1 = mad_wide(ci[t], ih[(t - j) & 7], s1);
-                }
-                const int32_t ssum = (int32_t)((s0 + s1) >> shift);
-                int32_t x = (int32_t)((uint32_t)ssum + (uint32_t)r[j]);
-                x = (x >> q) << q;
-                fh[(7 - j) & 7] = x;
-                ih[(7 - j) & 7] = (int32_t)((uint32_t)x - (uint32_t)ssum);
-                int32_t out = x;
-                if (any_matrix) {
-                    // all channels of the frame, from the neighbouring lanes
+                for (int j = 0; j < 8; j++) {
                     int32_t v[NCH];
 #pragma unroll
-                    for (int c = 0; c < NCH; c++) v[c] = __shfl_sync(0xFFFFFFFFu, x, group_lane0 + c);
-                    if (act && !trivial) {
+                    for (int c = 0; c < NCH; c++) v[c] = __shfl_sync(0xFFFFFFFFu, r[j], group_lane0 + c);
+                    if (au_act && !trivial) {
                         // noise, matrices in order, bypass bit, output shift (mlp.c:504-538, 1308-1358)
+                        const uint32_t bm = byp[(uint64_t)(fa + j) * DVDA_LANES];
                         const uint32_t sh = (seed >> 7) & 0xFFFF;
                         const int32_t n0 = (int32_t)((uint32_t)(int32_t)(int8_t)(seed >> 15) << P->noise_shift);
                         const int32_t n1 = (int32_t)((uint32_t)(int32_t)(int8_t)sh << P->noise_shift);
@@ -1388,33 +1446,28 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
                             sum += (long long)n0 * P->coeff[k][mmc + 1];
                             sum += (long long)n1 * P->coeff[k][mmc + 2];
                             const uint32_t oc = P->out_ch[k], qq = P->q[oc];
-                            const int32_t rr = (((int32_t)(sum >> 14)) >> qq << qq) + (int32_t)((bm[j] >> k) & 1);
+                            const int32_t rr = (((int32_t)(sum >> 14)) >> qq << qq) + (int32_t)((bm >> k) & 1);
 #pragma unroll
                             for (int c = 0; c < NCH; c++) if ((uint32_t)c == oc) v[c] = rr;
                         }
                         int32_t mineval = 0;
 #pragma unroll
                         for (int c = 0; c < NCH; c++) if ((uint32_t)c == cc) mineval = v[c];
-                        out = (int32_t)((uint32_t)mineval << P->out_shift[cc]);
+                        r[j] = (int32_t)((uint32_t)mineval << P->out_shift[cc]);
                     }
+                    seed = noise_step(seed);
                 }
-                if (act) patch[sl * ROW + (fb + j) * NCH + out_slot] = out;
-                seed = noise_step(seed);
             }
-            if (act) au_left -= 8;
+            if (au_act) {
+                int32_t *pk = park + (f & 31) * NCH;
+#pragma unroll
+                for (int j = 0; j < 8; j++) pk[j * NCH] = r[j];
+            }
+            f += 8;
+            if ((f & 31) == 0) flush(f - 32);
         }
-        __syncwarp();
-        // ---- flush: row s = 32 frames of segment s, contiguous in the output
-        for (uint32_t s2 = 0; s2 < (uint32_t)SPW; s2++) {
-            const uint32_t fr = __shfl_sync(0xFFFFFFFFu, my_frames, s2 * NCH);
-            if (f0 >= fr) continue;
-            const uint32_t nfr = min(32u, fr - f0);
-            const uint64_t base = (__shfl_sync(0xFFFFFFFFu, (unsigned long long)(mine ? S.frame0 : 0), s2 * NCH) + f0) * NCH;
-            const int32_t *src = patch + s2 * ROW;
-            for (uint32_t i = lane; i < nfr * NCH; i += 32) pcm_row[base + i] = src[i];
-        }
-        __syncwarp();
     }
+    if (f & 31) flush(f & ~31u);
     // FIR tail for a following segment that needs it
     if (mine) {
         int32_t *tail = m.fir_tail + (uint64_t)seg * (DVDA_MAX_CH * 8);
@@ -1428,7 +1481,7 @@ static int launch_one_filter_out(MlpTables m, const DecWork *work, uint32_t n_wo
 {
     if (!n_warps) return 0;
     constexpr int SPW = 32 / NCH, SUB = (32 + SPW - 1) / SPW;
-    const size_t smem = (size_t)OUT_WARPS * SPW * (32 * NCH + 1) * sizeof(int32_t);
+    const size_t smem = (size_t)OUT_WARPS * SPW * (32 * NCH + NCH + 4) * sizeof(int32_t);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1710,6 +1763,8 @@ __global__ void k_seg_finalize(MlpTables m, uint32_t *__restrict__ seg_frames, u
     if ((flags & SEG_IRREGULAR) && stop == 0xFFFFFFFFu) { err |= ERR_SYNTAX; stop = S.n_au; }
     S.flags = flags & ~SEG_NEEDS_CARRY;
     if (now & SEG_OVERFLOW) atomicOr(status, SEG_OVERFLOW);
+    // anything left for k_rematrix once the fused filter + output pass has run?
+    if (m.fast && frames && (T.nss != 1 || T.channels > 4 || (m.ss_flags_fast[i] & SEG_FALLBACK))) atomicOr(status, STATUS_WANTS_REMATRIX);
     S.err = err;
     S.err_au = stop;
     S.frames = frames;
@@ -1757,27 +1812,28 @@ int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, cudaStrea
 
 #define RM_THREADS 256
 
-// One block per (group, 32-frame chunk).  Loads the [32 frames][nch][32 lanes]
-// patch of the tile coalesced, then every warp takes segments (lanes of the
-// patch) and its 32 threads take the 32 frames: noise, matrices, bypass, shift,
-// channel order, interleaved store.
+// One block per (group, 32-frame chunk): blockIdx.x = group, blockIdx.y = chunk
+// (groups with fewer chunks than the largest leave at once).  Loads the
+// [32 frames][nch][32 lanes] patch of the tile coalesced, then every warp takes
+// segments (lanes of the patch) and its 32 threads take the 32 frames: noise,
+// matrices, bypass, shift, channel order, interleaved store.
 //
 // Per frame the access unit is found by division (AUs normally have the nominal
 // length; a binary search covers the rest), and an AU whose parameters are
 // trivial — no matrix, no output shift, identity channel order — skips the
 // parameter set altogether: the kernel is then a pure transpose at HBM speed.
 template <int NCH>
-__global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m, const uint64_t *__restrict__ grp_chunk_base)
+__global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
 {
     extern __shared__ int32_t sm[];                      // [nch][32][33] samples, then [32][33] bypass bytes as ints
-    const uint64_t chunk = blockIdx.x;
-    const uint32_t g = upper_bound_dev(grp_chunk_base, m.ngroups, chunk) - 1;
+    const uint32_t g = blockIdx.x;
     const GroupDev &G = m.groups[g];
+    const uint32_t f0 = blockIdx.y * 32;
+    if (f0 >= G.cap) return;
     const TrackDev &T = m.tracks[G.track];
     const uint32_t nch = NCH ? NCH : T.channels;
     if (NCH && T.channels != NCH) return;
     if (!NCH && T.channels <= 2) return;                 // handled by the specialised instantiations
-    const uint32_t f0 = (uint32_t)(chunk - grp_chunk_base[g]) * 32;
     const uint32_t nf = min(32u, G.cap - f0);
     int32_t *bsm = sm + nch * 32 * 33;
     if (m.fast && T.nss == 1 && T.channels <= 4) {
@@ -1869,9 +1925,10 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m, const uint
     }
 }
 
-int launch_rematrix(MlpTables m, uint64_t total_chunks, const uint64_t *grp_chunk_base, uint32_t channel_mask, cudaStream_t s)
+int launch_rematrix(MlpTables m, uint32_t max_chunks, uint32_t channel_mask, cudaStream_t s)
 {
-    if (!total_chunks) return 0;
+    if (!max_chunks || !m.ngroups) return 0;
+    const dim3 grid(m.ngroups, max_chunks);
     const size_t smem = (size_t)(DVDA_MAX_CH + 1) * 32 * 33 * sizeof(int32_t);
     static bool attr_set = false;
     if (!attr_set) {
@@ -1879,9 +1936,9 @@ int launch_rematrix(MlpTables m, uint64_t total_chunks, const uint64_t *grp_chun
         attr_set = true;
     }
     // channel_mask: bit n = some MLP track of the batch has n channels
-    if (channel_mask & 2) LAUNCH(k_rematrix<1>, (uint32_t)total_chunks, RM_THREADS, (size_t)2 * 32 * 33 * 4, s, m, grp_chunk_base);
-    if (channel_mask & 4) LAUNCH(k_rematrix<2>, (uint32_t)total_chunks, RM_THREADS, (size_t)3 * 32 * 33 * 4, s, m, grp_chunk_base);
-    if (channel_mask & ~6u) LAUNCH(k_rematrix<0>, (uint32_t)total_chunks, RM_THREADS, smem, s, m, grp_chunk_base);
+    if (channel_mask & 2) LAUNCH(k_rematrix<1>, grid, RM_THREADS, (size_t)2 * 32 * 33 * 4, s, m);
+    if (channel_mask & 4) LAUNCH(k_rematrix<2>, grid, RM_THREADS, (size_t)3 * 32 * 33 * 4, s, m);
+    if (channel_mask & ~6u) LAUNCH(k_rematrix<0>, grid, RM_THREADS, smem, s, m);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -441,6 +441,7 @@ __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tr
     grp_cells[g] = cap * T.channels;
     grp_chunks[g] = (cap + 31) / 32;
     atomicMax(max_au, most);
+    atomicMax(max_au + 1, (cap + 31) / 32);              // most 32-frame chunks in a group
 }
 
 __global__ void k_group_offsets(GroupDev *__restrict__ groups, uint32_t ngroups, const uint64_t *__restrict__ cell_base)
