@@ -71,7 +71,7 @@ enum {
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
     B_SS_FLAGS, B_SS_FLAGS_PREV, B_SS_FLAGS_FAST, B_FIR_TAIL,
     B_GROUPS, B_GRP_CELLS, B_CELL_BASE, B_GRP_CHUNKS, B_GRP_CHUNK_BASE,
-    B_DEC_WORK, B_AU_SNAP, B_FILT_SNAP, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
+    B_DEC_WORK, B_AU_SNAP, B_FILT_SNAP, B_AU_FCHG, B_SEG_CTX, B_AU_DELTA, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
     B_COUNT
 };
 
@@ -509,6 +509,11 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             ENSURE(B_FILT_SNAP, naua * 2 * 4 * filt_snap_bytes());
             m.au_snap = reinterpret_cast<AuSnap *>(c->buf[B_AU_SNAP].p);
             m.filt_snap = reinterpret_cast<FiltSnap *>(c->buf[B_FILT_SNAP].p);
+            ENSURE(B_AU_FCHG, naua * 2); ENSURE(B_SEG_CTX, (size_t)nseg * 2 * seg_ctx_bytes());
+            ENSURE(B_AU_DELTA, naua * 2 * au_delta_bytes());
+            m.au_fchg = c->buf[B_AU_FCHG].as<uint8_t>();
+            m.seg_ctx = reinterpret_cast<SegCtx *>(c->buf[B_SEG_CTX].p);
+            m.au_delta = reinterpret_cast<AuDelta *>(c->buf[B_AU_DELTA].p);
         }
         for (int attempt = 0; attempt < 2; attempt++) {
             CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));

@@ -17,6 +17,8 @@ struct PacketTable {
 
 struct AuSnap;      // mlp_decode.cu: what pass B needs to entropy-decode one access unit
 struct FiltSnap;    // mlp_decode.cu: filter parameters of one channel for one access unit
+struct SegCtx;      // mlp_decode.cu: what a segment's restart header fixes for its parameter blocks
+struct AuDelta;     // mlp_decode.cu: the parameters one access unit transmits
 
 // everything the MLP kernels need to find their data
 struct MlpTables {
@@ -44,7 +46,10 @@ struct MlpTables {
     uint8_t *bypass;
     int32_t *pcm;
     AuSnap *au_snap;               // [2][nau]
-    FiltSnap *filt_snap;           // [2][nau][4]
+    FiltSnap *filt_snap;           // [2][nau][4], written where au_fchg says so
+    uint8_t *au_fchg;              // [2][nau]: filter parameters (re)stated with this access unit
+    SegCtx *seg_ctx;               // [2][nseg]
+    AuDelta *au_delta;             // [2][nau], written where the AU brings parameters
     uint32_t fast;                 // 1: the complete decoder only takes segments flagged SEG_FALLBACK
     uint32_t max_au;               // largest access-unit count of a segment
 };
@@ -100,6 +105,8 @@ int launch_carry_fix(MlpTables m, cudaStream_t s);
 int launch_mlp_filter_out(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s);
 size_t au_snap_bytes();
 size_t filt_snap_bytes();
+size_t seg_ctx_bytes();
+size_t au_delta_bytes();
 // fast path: pass A (headers), B (entropy, one lane per access unit), C (filters, one lane per channel)
 int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
                     cudaEvent_t ev[4], cudaStream_t s);

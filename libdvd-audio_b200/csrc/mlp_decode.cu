@@ -289,14 +289,37 @@ __device__ __forceinline__ void rd_top_up(Rd &r)
     r.ahead = rd_ring_word(r, r.next_w);
 }
 
+// ---- reader straight over global memory (header-only passes: a few dozen bytes per
+// access unit, served by L1/L2; no shared-memory ring to set up)
+struct GRd {
+    const uint8_t *es;
+    uint64_t win;
+    int32_t avail;
+    uint32_t next_w, base_w;
+};
+__device__ __forceinline__ void grd_seat(GRd &r, const uint8_t *es, uint64_t byte_pos)
+{
+    r.es = es; r.next_w = r.base_w = (uint32_t)(byte_pos >> 2); r.win = 0; r.avail = 0;
+}
+__device__ __forceinline__ void rd_pull(GRd &r)
+{
+    const uint32_t word = __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(r.es) + r.next_w), 0, 0x0123);
+    r.win |= (uint64_t)word << (32 - r.avail);
+    r.avail += 32;
+    r.next_w++;
+}
+
 // next n bits (1..32) without consuming them
-__device__ __forceinline__ uint32_t rd_peek(Rd &r, uint32_t n)
+template <typename RD>
+__device__ __forceinline__ uint32_t rd_peek(RD &r, uint32_t n)
 {
     if (r.avail < (int32_t)n) rd_pull(r);
     return (uint32_t)(r.win >> (64 - n));
 }
-__device__ __forceinline__ void rd_drop(Rd &r, uint32_t n) { r.win <<= n; r.avail -= n; }
-__device__ __forceinline__ uint32_t rd_get(Rd &r, uint32_t n)
+template <typename RD>
+__device__ __forceinline__ void rd_drop(RD &r, uint32_t n) { r.win <<= n; r.avail -= n; }
+template <typename RD>
+__device__ __forceinline__ uint32_t rd_get(RD &r, uint32_t n)
 {
     if (!n) return 0;
     const uint32_t v = rd_peek(r, n);
@@ -304,18 +327,21 @@ __device__ __forceinline__ uint32_t rd_get(Rd &r, uint32_t n)
     return v;
 }
 // two's complement, n in 1..32 (src/bitstream.c:1198-1206)
-__device__ __forceinline__ int32_t rd_get_s(Rd &r, uint32_t n)
+template <typename RD>
+__device__ __forceinline__ int32_t rd_get_s(RD &r, uint32_t n)
 {
     const uint32_t v = rd_get(r, n);
     return (int32_t)(v << (32 - n)) >> (32 - n);
 }
-__device__ __forceinline__ void rd_skip(Rd &r, uint32_t n)
+template <typename RD>
+__device__ __forceinline__ void rd_skip(RD &r, uint32_t n)
 {
     while (n > 32) { rd_get(r, 32); n -= 32; }
     rd_get(r, n);
 }
-// bits consumed since rd_seat (counted from the seated word's first bit)
-__device__ __forceinline__ uint32_t rd_pos(const Rd &r) { return (r.next_w - r.base_w) * 32 - r.avail; }
+// bits consumed since the reader was seated (counted from the seated word's first bit)
+template <typename RD>
+__device__ __forceinline__ uint32_t rd_pos(const RD &r) { return (r.next_w - r.base_w) * 32 - r.avail; }
 
 // ------------------------------------------------------------ decoder state
 
@@ -371,7 +397,8 @@ struct DecodeJob {
 
 // ---- parameter parsing (cold path) ------------------------------------------
 
-__device__ bool restart_header(Rd &b, SubState &s)
+template <typename RD>
+__device__ bool restart_header(RD &b, SubState &s)
 {
     const uint32_t sync = rd_get(b, 13), noise_type = rd_get(b, 1);
     rd_skip(b, 16);
@@ -388,7 +415,8 @@ __device__ bool restart_header(Rd &b, SubState &s)
     return true;
 }
 
-__device__ bool filter_params(Rd &b, ChanState &C, bool iir)
+template <typename RD>
+__device__ bool filter_params(RD &b, ChanState &C, bool iir)
 {
     const uint32_t order = rd_get(b, 4);
     if (order > 8) return false;
@@ -422,7 +450,8 @@ __device__ bool filter_params(Rd &b, ChanState &C, bool iir)
     return true;
 }
 
-__device__ bool decoding_params(Rd &b, SubState &s, bool restart)
+template <typename RD>
+__device__ bool decoding_params(RD &b, SubState &s, bool restart)
 {
     if (restart) {
         if (rd_get(b, 1)) { uint32_t f = 0; for (int k = 0; k < 8; k++) f |= rd_get(b, 1) << k; s.flags = f; }
@@ -482,7 +511,8 @@ __device__ bool decoding_params(Rd &b, SubState &s, bool restart)
 }
 
 // block header: optional restart header + decoding parameters (mlp.c:749-771)
-__device__ __forceinline__ bool block_header(Rd &b, SubState &s, bool &changed)
+template <typename RD>
+__device__ __forceinline__ bool block_header(RD &b, SubState &s, bool &changed)
 {
     changed = false;
     if (rd_get(b, 1)) {
@@ -993,8 +1023,235 @@ __device__ __forceinline__ uint32_t noise_advance(uint32_t seed, uint32_t n)
 }
 
 // ---- pass A: headers ------------------------------------------------------------
+//
+// Three small kernels instead of one walk per segment:
+//   A0  k_mlp_segctx    lane = (segment, substream): the restart header and the
+//                       parameters of the segment's first access unit give the
+//                       context every later parameter block is parsed in (channel
+//                       range, matrix channel count, presence flags);
+//   A1  k_mlp_au_parse  lane = (segment, substream, access unit > 0): parses the
+//                       AU's parameter block *as a delta* (what was transmitted,
+//                       nothing resolved) and notes where the residuals begin;
+//   A2  k_mlp_resolve   lane = (segment, substream): walks the deltas of the
+//                       segment in order — no bit stream access past the first AU —
+//                       and writes what passes B and C need per AU.
+// A parameter block that changes the presence flags, a restart header in the
+// middle of a segment and everything malformed give the segment to the complete
+// decoder.
+
+struct SegCtx { uint8_t min_ch, max_ch, mmc, flags, ok, pad[3]; };
+
+#define CD_PRESENT 1u
+#define CD_FIR 2u
+#define CD_IIR 4u
+#define CD_IIR_STATE 8u
+#define CD_OFFSET 16u
+struct ChanDelta {
+    int32_t ist[8];                  // IIR history as transmitted: [0] pairs with coefficient 0
+    int16_t fir_c[8], iir_c[8];
+    int32_t huff_offset;
+    uint8_t fir_order, fir_shift, iir_order, iir_shift;
+    uint8_t codebook, huff_lsbs, present, pad;
+};
+#define AD_BLOCK 1u
+#define AD_MATRIX 2u
+#define AD_SHIFT 4u
+#define AD_Q 8u
+struct AuDelta {
+    uint16_t block_size;
+    uint8_t present, matrix_len;
+    uint8_t mat_out[DVDA_MAX_MAT], mat_bypass[DVDA_MAX_MAT];
+    int16_t coeff[DVDA_MAX_MAT][DVDA_MAX_CH];
+    uint8_t out_shift[DVDA_MAX_CH], q[DVDA_MAX_CH];
+    ChanDelta ch[4];
+};
+
+// seat a global-memory reader on substream k of access unit A; false = not for the fast path
+__device__ __forceinline__ bool au_seat(const MlpTables &m, const TrackDev &T, uint32_t A, uint32_t k, GRd &b,
+                                        uint32_t &end_bits, uint64_t &origin)
+{
+    const uint64_t au_pos = m.au_pos[A];
+    const AuLayout L = au_layout(m.es, au_pos, T);
+    // damage, dropped AUs and the end-of-track rules are the complete decoder's business
+    if (!L.ok || au_pos + L.total > T.es_cut || m.au_err[A]) return false;
+    const uint32_t start = k ? L.end[0] : 0;
+    const uint32_t len = L.end[k] - start - (L.chk0 ? 2 : 0);
+    const uint64_t data = au_pos + L.data0 + start;
+    grd_seat(b, m.es, data);
+    rd_skip(b, (uint32_t)(data & 3) * 8);
+    end_bits = (uint32_t)(data & 3) * 8 + len * 8;
+    origin = (data & ~3ull) * 8;
+    return true;
+}
+
+// one channel's FIR or IIR block of a delta (mlp.c:1029-1120)
+template <typename RD>
+__device__ bool delta_filter(RD &b, ChanDelta &C, bool iir, uint32_t &present)
+{
+    const uint32_t order = rd_get(b, 4);
+    if (order > 8) return false;
+    uint32_t shift = 0;
+    if (order) {
+        shift = rd_get(b, 4);
+        const uint32_t bits = rd_get(b, 5);
+        if (bits < 1 || bits > 16) return false;
+        const uint32_t cshift = rd_get(b, 3);
+        if (bits + cshift > 16) return false;
+        int16_t *coef = iir ? C.iir_c : C.fir_c;
+        for (uint32_t i = 0; i < order; i++) coef[i] = (int16_t)((uint32_t)rd_get_s(b, bits) << cshift);
+        if (rd_get(b, 1)) {
+            if (!iir) return false;
+            const uint32_t sbits = rd_get(b, 4), sshift = rd_get(b, 4);
+            if (!sbits) return false;                           // reference underflows (G2)
+            for (uint32_t i = 0; i < order; i++) C.ist[i] = (int32_t)((uint32_t)rd_get_s(b, sbits) << sshift);
+            present |= CD_IIR_STATE;
+        }
+    }
+    if (iir) { C.iir_order = (uint8_t)order; C.iir_shift = (uint8_t)shift; present |= CD_IIR; }
+    else { C.fir_order = (uint8_t)order; C.fir_shift = (uint8_t)shift; present |= CD_FIR; }
+    return true;
+}
+
+// decoding parameters of a block without restart header, as a delta (mlp.c:856-993)
+template <typename RD>
+__device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D)
+{
+    uint32_t present = 0;
+    if ((cx.flags & 1) && rd_get(b, 1)) return false;           // new presence flags: complete decoder
+    if ((cx.flags & 0x80) && rd_get(b, 1)) {
+        const uint32_t bs = rd_get(b, 9);
+        if (bs < 8) return false;
+        D.block_size = (uint16_t)bs; present |= AD_BLOCK;
+    }
+    if ((cx.flags & 0x40) && rd_get(b, 1)) {
+        const uint32_t ml = rd_get(b, 4);
+        if (ml > DVDA_MAX_MAT || cx.mmc + 3 > DVDA_MAX_CH) return false;
+        D.matrix_len = (uint8_t)ml; present |= AD_MATRIX;
+        for (uint32_t k = 0; k < ml; k++) {
+            const uint32_t out = rd_get(b, 4), frac = rd_get(b, 4);
+            if (out > cx.mmc || frac > 14) return false;
+            D.mat_out[k] = (uint8_t)out;
+            D.mat_bypass[k] = (uint8_t)rd_get(b, 1);
+            for (uint32_t c = 0; c < DVDA_MAX_CH; c++) {
+                int16_t v = 0;
+                if (c < (uint32_t)cx.mmc + 3 && rd_get(b, 1)) v = (int16_t)((uint32_t)rd_get_s(b, frac + 2) << (14 - frac));
+                D.coeff[k][c] = v;
+            }
+        }
+    }
+    if ((cx.flags & 0x20) && rd_get(b, 1)) {
+        present |= AD_SHIFT;
+        for (uint32_t c = 0; c <= cx.mmc; c++) D.out_shift[c] = (uint8_t)(rd_get_s(b, 4) & 31);
+    }
+    if ((cx.flags & 0x10) && rd_get(b, 1)) {
+        present |= AD_Q;
+        for (uint32_t c = 0; c <= cx.max_ch; c++) D.q[c] = (uint8_t)rd_get(b, 4);
+    }
+    for (uint32_t c = cx.min_ch; c <= cx.max_ch; c++) {
+        ChanDelta &C = D.ch[c - cx.min_ch];
+        uint32_t p = 0;
+        if (rd_get(b, 1)) {
+            p = CD_PRESENT;
+            if ((cx.flags & 0x08) && rd_get(b, 1) && !delta_filter(b, C, false, p)) return false;
+            if ((cx.flags & 0x04) && rd_get(b, 1) && !delta_filter(b, C, true, p)) return false;
+            if ((cx.flags & 0x02) && rd_get(b, 1)) { C.huff_offset = rd_get_s(b, 15); p |= CD_OFFSET; }
+            C.codebook = (uint8_t)rd_get(b, 2);
+            C.huff_lsbs = (uint8_t)rd_get(b, 5);
+            if (C.huff_lsbs > 24) return false;
+        }
+        C.present = (uint8_t)p;
+    }
+    D.present = (uint8_t)present;
+    return true;
+}
+
+// the same parameters, merged into the running state (what decoding_params does in place)
+__device__ void apply_delta(SubState &s, const AuDelta &D)
+{
+    if (D.present & AD_BLOCK) s.block_size = D.block_size;
+    if (D.present & AD_MATRIX) {
+        s.dirty = 1;
+        s.matrix_len = D.matrix_len;
+        for (uint32_t k = 0; k < D.matrix_len; k++) {
+            s.mat_out[k] = D.mat_out[k]; s.mat_bypass[k] = D.mat_bypass[k];
+            for (uint32_t c = 0; c < DVDA_MAX_CH; c++) s.coeff[k][c] = D.coeff[k][c];
+        }
+    }
+    if (D.present & AD_SHIFT) { s.dirty = 1; for (uint32_t c = 0; c <= s.mmc; c++) s.out_shift[c] = D.out_shift[c]; }
+    if (D.present & AD_Q) { s.dirty = 1; for (uint32_t c = 0; c <= s.max_ch; c++) s.q[c] = D.q[c]; }
+    for (uint32_t c = s.min_ch; c <= s.max_ch; c++) {
+        const ChanDelta &X = D.ch[c - s.min_ch];
+        ChanState &C = s.ch[c];
+        if (!(X.present & CD_PRESENT)) continue;
+        if (X.present & CD_FIR) {
+            C.fir_order = X.fir_order; C.fir_shift = X.fir_shift;
+            for (uint32_t i = 0; i < X.fir_order; i++) C.fir_c[i] = X.fir_c[i];
+        }
+        if (X.present & CD_IIR) {
+            C.iir_order = X.iir_order; C.iir_shift = X.iir_shift;
+            for (uint32_t i = 0; i < X.iir_order; i++) C.iir_c[i] = X.iir_c[i];
+            C.ilen = 0; C.ihead = 0; C.ist_new = 1;
+            if (X.present & CD_IIR_STATE) {
+                for (uint32_t i = 0; i < X.iir_order; i++) C.ist[(X.iir_order - 1 - i) & 7] = X.ist[i];
+                C.ilen = X.iir_order; C.ihead = X.iir_order & 7;
+            }
+        }
+        if (X.present & CD_OFFSET) C.huff_offset = X.huff_offset;
+        C.codebook = X.codebook; C.huff_lsbs = X.huff_lsbs;
+    }
+}
+
+// A0: context of a segment's substream
+__device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJob &job)
+{
+    const SegDev &S = m.segs[job.seg];
+    const TrackDev &T = m.tracks[S.track];
+    SegCtx cx;
+    memset(&cx, 0, sizeof cx);
+    if (S.n_au) {
+        GRd b;
+        uint32_t end_bits;
+        uint64_t origin;
+        SubState s;
+        memset(&s, 0, sizeof s);
+        s.flags = 0xFF;
+        bool changed;
+        if (au_seat(m, T, S.au_base, job.k, b, end_bits, origin) && block_header(b, s, changed) && rd_pos(b) <= end_bits &&
+            s.max_ch - s.min_ch < 4) {
+            cx.min_ch = s.min_ch; cx.max_ch = s.max_ch; cx.mmc = s.mmc; cx.flags = s.flags; cx.ok = 1;
+        }
+    }
+    m.seg_ctx[job.k * m.nseg + job.seg] = cx;
+}
+
+// A1: parameter block of access unit a > 0 as a delta
+__device__ __forceinline__ void parse_au(const MlpTables &m, const DecodeJob &job, uint32_t a)
+{
+    const SegDev &S = m.segs[job.seg];
+    const TrackDev &T = m.tracks[S.track];
+    const uint32_t A = S.au_base + a;
+    AuSnap &sn = m.au_snap[(uint64_t)job.k * m.nau + A];
+    const SegCtx cx = m.seg_ctx[job.k * m.nseg + job.seg];
+    uint32_t state = 0;                                   // 0: not for the fast path, 1: no parameters, 2: delta written
+    GRd b;
+    uint32_t end_bits;
+    uint64_t origin;
+    if (cx.ok && au_seat(m, T, A, job.k, b, end_bits, origin)) {
+        state = 1;
+        if (rd_get(b, 1)) {
+            // a restart header here would start a new run of parameters: complete decoder
+            state = (!rd_get(b, 1) && parse_delta(b, cx, m.au_delta[(uint64_t)job.k * m.nau + A])) ? 2 : 0;
+        }
+        if (rd_pos(b) > end_bits) state = 0;
+        sn.bit0 = origin + rd_pos(b);
+        sn.bit_end = origin + end_bits;
+    }
+    sn.valid = (uint8_t)state;
+}
+
+// A2: the segment's parameter chain, resolved per access unit
 template <int NCH>
-__device__ __forceinline__ void headers_segment(const MlpTables &m, const DecodeJob &job, uint32_t ring)
+__device__ __forceinline__ void resolve_segment(const MlpTables &m, const DecodeJob &job)
 {
     SegDev &S = m.segs[job.seg];
     const TrackDev &T = m.tracks[S.track];
@@ -1004,38 +1261,34 @@ __device__ __forceinline__ void headers_segment(const MlpTables &m, const Decode
     SubState s;
     memset(&s, 0, sizeof s);
     s.flags = 0xFF;
-    Rd b;
-    rd_init(b, m.es, ring);
     AuSnap *snaps = m.au_snap + (uint64_t)job.k * m.nau;
     FiltSnap *fsnaps = m.filt_snap + (uint64_t)job.k * m.nau * 4;
+    uint8_t *fchg = m.au_fchg + (uint64_t)job.k * m.nau;
 
     uint32_t frames = 0, flags = 0, pset = 0xFFFFFFFFu;
-    bool fallback = false;
-    uint64_t pos = S.n_au ? m.au_pos[S.au_base] : 0;
-    for (uint32_t a = 0; a < S.n_au; a++) {
+    bool fallback = !m.seg_ctx[job.k * m.nseg + job.seg].ok;
+    for (uint32_t a = 0; a < S.n_au && !fallback; a++) {
         const uint32_t A = S.au_base + a;
+        AuSnap sn;
+        bool fresh;                                      // parameters arrived with this access unit
+        if (a == 0) {
+            GRd b;
+            uint32_t end_bits;
+            uint64_t origin;
+            bool changed;
+            if (!au_seat(m, T, A, job.k, b, end_bits, origin) || !block_header(b, s, changed) || rd_pos(b) > end_bits) { fallback = true; break; }
+            sn.bit0 = origin + rd_pos(b);
+            sn.bit_end = origin + end_bits;
+            fresh = true;
+        } else {
+            sn = snaps[A];
+            if (!sn.valid) { fallback = true; break; }
+            fresh = sn.valid == 2;
+            if (fresh) apply_delta(s, m.au_delta[(uint64_t)job.k * m.nau + A]);
+        }
         snaps[A].valid = 0;
-        const uint32_t e = m.au_err[A];
-        const AuLayout L = au_layout_rd(b, pos, T);
-        const uint64_t au_pos = pos;
-        pos += L.total;
-        // damage, dropped AUs and the end-of-track rules are the complete decoder's business
-        if (au_pos + L.total > T.es_cut || e) { fallback = true; break; }
-        const uint32_t start = job.k ? L.end[0] : 0;
-        const uint32_t len = L.end[job.k] - start - (L.chk0 ? 2 : 0);
-        const uint64_t data = au_pos + L.data0 + start;
-        rd_seat(b, data);
-        rd_issue_ahead(b);                       // also brings the next access unit's header in
-        rd_skip(b, (uint32_t)(data & 3) * 8);
-        const uint32_t end_bits = (uint32_t)(data & 3) * 8 + len * 8;
-        bool changed;
-        if (!block_header(b, s, changed) || rd_pos(b) > end_bits) { fallback = true; break; }
         if ((uint32_t)(s.max_ch - s.min_ch + 1) != NCH || s.block_size > nominal || nominal % s.block_size) { fallback = true; break; }
 
-        AuSnap sn;
-        const uint64_t origin = (data & ~3ull) * 8;
-        sn.bit0 = origin + rd_pos(b);
-        sn.bit_end = origin + end_bits;
         sn.block_size = s.block_size;
         sn.min_ch = s.min_ch; sn.nch = NCH; sn.pad0 = sn.pad1 = 0;
         uint32_t want = 0;
@@ -1051,21 +1304,24 @@ __device__ __forceinline__ void headers_segment(const MlpTables &m, const Decode
             if (!channel_setup(s, C, q, job.exact_history, cflags, lsb_bits, sho, shift)) { fallback = true; break; }
             sn.ch[cc].sho = sho; sn.ch[cc].cb = C.codebook; sn.ch[cc].lsb_bits = (uint8_t)lsb_bits;
             sn.ch[cc].q = (uint8_t)q; sn.ch[cc].shift = (uint8_t)shift;
-            FiltSnap fs;
+            if (fresh) {
+                FiltSnap fs;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                fs.cf[j] = j < C.fir_order ? (int16_t)C.fir_c[j] : (int16_t)0;
-                fs.ci[j] = j < C.iir_order ? (int16_t)C.iir_c[j] : (int16_t)0;
-                fs.ist[j] = (C.ist_new && j < C.ilen) ? C.ist[(C.ihead - 1 - j) & 7] : 0;
+                for (int j = 0; j < 8; j++) {
+                    fs.cf[j] = j < C.fir_order ? (int16_t)C.fir_c[j] : (int16_t)0;
+                    fs.ci[j] = j < C.iir_order ? (int16_t)C.iir_c[j] : (int16_t)0;
+                    fs.ist[j] = (C.ist_new && j < C.ilen) ? C.ist[(C.ihead - 1 - j) & 7] : 0;
+                }
+                fs.shift = (uint8_t)shift; fs.q = (uint8_t)q; fs.ist_new = C.ist_new;
+                fs.orders = (uint8_t)(C.fir_order | C.iir_order << 4);
+                fsnaps[(uint64_t)A * 4 + cc] = fs;
             }
-            fs.shift = (uint8_t)shift; fs.q = (uint8_t)q; fs.ist_new = C.ist_new;
-            fs.orders = (uint8_t)(C.fir_order | C.iir_order << 4);
-            fsnaps[(uint64_t)A * 4 + cc] = fs;
             C.ist_new = 0;
             C.flen = 8; C.ilen = 8;
         }
         if (cflags & SEG_NEEDS_CARRY) { flags |= SEG_WANTS_PREV; fallback = true; break; }
         if (fallback) break;
+        fchg[A] = fresh;
         sn.valid = 1;
         snaps[A] = sn;
 
@@ -1096,7 +1352,6 @@ __device__ __forceinline__ void headers_segment(const MlpTables &m, const Decode
             s.seed = noise_advance(s.seed, nominal);
         }
     }
-    cp_wait<0>();
     if (fallback) flags |= SEG_FALLBACK;
     m.ss_flags[job.k * m.nseg + job.seg] = flags;
     if (job.k == 0) S.frames = frames;
@@ -1210,13 +1465,16 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
     const uint32_t tile_step = nch * DVDA_LANES;
     uint32_t f = 0;
     int32_t nx[8];
+    uint32_t shift = 0, q = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) nx[j] = ((uint32_t)j < cap) ? tile[(uint64_t)j * tile_step] : 0;
     for (uint32_t a = 0; a < S.n_au; a++) {
-        const FiltSnap fs = fsnaps[(uint64_t)(S.au_base + a) * 4 + cc];
+        if (m.au_fchg[(uint64_t)k * m.nau + S.au_base + a]) {
+            const FiltSnap fs = fsnaps[(uint64_t)(S.au_base + a) * 4 + cc];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
-        const uint32_t shift = fs.shift, q = fs.q;
+            for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
+            shift = fs.shift; q = fs.q;
+        }
         // the nominal AU length is a multiple of 8 (40 * rate multiple); the residuals of
         // the next 8 frames are loaded while the current 8 are filtered
         for (uint32_t i = 0; i < nominal; i += 8) {
@@ -1348,7 +1606,7 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
     const uint32_t group_lane0 = sl * NCH;                       // first lane of this segment's channels
     int32_t *const park = patch + (sl < SPW ? sl : 0) * ROW + out_slot;
 
-    uint32_t seed = 0, pset = 0xFFFFFFFFu, f = 0, a = 0;
+    uint32_t seed = 0, pset = 0xFFFFFFFFu, f = 0, a = 0, cls = 0;
     const ParamSet *P = nullptr;
     bool trivial = true;
     int32_t nx[8];
@@ -1381,14 +1639,15 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
     while (f < max_frames) {
         // ---- next access unit: this channel's filter parameters, the frame's rematrix parameters
         const bool au_act = f < my_frames;
-        uint32_t cls = 0;
         if (au_act) {
             const uint32_t A = S.au_base + a;
-            const FiltSnap fs = fsnaps[(uint64_t)A * 4 + cc];
+            if (m.au_fchg[A]) {
+                const FiltSnap fs = fsnaps[(uint64_t)A * 4 + cc];
 #pragma unroll
-            for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
-            shift = fs.shift; qmask = 0xFFFFFFFFu << fs.q;
-            cls = fs.orders;
+                for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
+                shift = fs.shift; qmask = 0xFFFFFFFFu << fs.q;
+                cls = fs.orders;
+            }
             const AuDev au = m.au[A];
             seed = au.seed;
             if (au.pset != pset) {
@@ -1397,6 +1656,7 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
                 trivial = (pset & 0x80000000u) && plain_order;
             }
         } else {
+            cls = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) { cf[j] = 0; ci[j] = 0; }
         }
@@ -1571,19 +1831,34 @@ __device__ __forceinline__ bool fast_job(const MlpTables &m, const DecWork *work
     return true;
 }
 
-// pass A: one warp per (group, substream), lane = segment
-template <int NCH>
-__global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_headers(MlpTables m, const DecWork *__restrict__ work,
-                                                                uint32_t n_work, uint32_t n_warps)
+// pass A0 / A2: one warp per (group, substream), lane = segment
+__global__ void __launch_bounds__(128) k_mlp_segctx(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
 {
-    extern __shared__ uint4 dyn_smem[];
-    uint4 (*ring)[RING_SLOTS][DVDA_LANES] = reinterpret_cast<uint4 (*)[RING_SLOTS][DVDA_LANES]>(dyn_smem);
-    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t warp = blockIdx.x * DEC_WARPS + wib;
+    const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (warp >= n_warps) return;
     DecodeJob job;
     if (!fast_job(m, work, n_work, warp, lane, job)) return;
-    headers_segment<NCH>(m, job, (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]));
+    segctx_segment(m, job);
+}
+template <int NCH>
+__global__ void __launch_bounds__(128) k_mlp_resolve(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (warp >= n_warps) return;
+    DecodeJob job;
+    if (!fast_job(m, work, n_work, warp, lane, job)) return;
+    resolve_segment<NCH>(m, job);
+}
+// pass A1: one warp per (group, substream, access unit index > 0), lane = segment
+__global__ void __launch_bounds__(128) k_mlp_au_parse(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint32_t a = blockIdx.y + 1;
+    if (warp >= n_warps) return;
+    DecodeJob job;
+    if (!fast_job(m, work, n_work, warp, lane, job)) return;
+    if (a >= m.segs[job.seg].n_au) return;
+    parse_au(m, job, a);
 }
 
 // pass B: one warp per (group, substream, access unit index), lane = segment
@@ -1634,6 +1909,8 @@ __global__ void k_flag_predecessors(MlpTables m)
 
 size_t au_snap_bytes() { return sizeof(AuSnap); }
 size_t filt_snap_bytes() { return sizeof(FiltSnap); }
+size_t seg_ctx_bytes() { return sizeof(SegCtx); }
+size_t au_delta_bytes() { return sizeof(AuDelta); }
 
 template <int NCH>
 static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
@@ -1641,12 +1918,15 @@ static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t
     if (!n_warps) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_mlp_headers<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_mlp_entropy<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES));
         attr_set = true;
     }
     const uint32_t blocks = div_up_u32(n_warps, DEC_WARPS);
-    if (pass == 0) LAUNCH(k_mlp_headers<NCH>, blocks, DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
+    if (pass == 0) {
+        LAUNCH(k_mlp_segctx, div_up_u32(n_warps, 4), 128, 0, s, m, work, n_work, n_warps);
+        if (m.max_au > 1) LAUNCH(k_mlp_au_parse, dim3(div_up_u32(n_warps, 4), m.max_au - 1), 128, 0, s, m, work, n_work, n_warps);
+        LAUNCH(k_mlp_resolve<NCH>, div_up_u32(n_warps, 4), 128, 0, s, m, work, n_work, n_warps);
+    }
     else if (pass == 1) LAUNCH(k_mlp_entropy<NCH>, dim3(blocks, m.max_au ? m.max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
     else LAUNCH(k_mlp_filter<NCH>, div_up_u32((uint64_t)n_warps * NCH, 4), 128, 0, s, m, work, n_work, n_warps);
     return 0;
