@@ -68,10 +68,10 @@ class Stats(ctypes.Structure):
                 ("output_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("launches", ctypes.c_uint32), ("segments", ctypes.c_uint32),
                 ("access_units", ctypes.c_uint64), ("es_bytes", ctypes.c_uint64), ("samples", ctypes.c_uint64),
-                ("kernel_ms", ctypes.c_float * 12)]
+                ("kernel_ms", ctypes.c_float * 16)]
 
 KERNEL_NAMES = ["es_gather", "sync_scan", "au_chase", "checkdata", "mlp_decode", "carry_fix", "rematrix", "pcm_unpack",
-                "mlp_headers", "mlp_entropy", "mlp_filter", "mlp_filter_out"]
+                "mlp_segctx", "mlp_entropy", "mlp_filter", "mlp_filter_out", "mlp_au_parse", "mlp_resolve"]
 
 
 _engine = None

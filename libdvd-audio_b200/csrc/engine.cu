@@ -86,10 +86,8 @@ struct dvdagpu_ctx {
     size_t map_used;
     DevBuf buf[B_COUNT];
     cudaEvent_t ev[6];
-    cudaEvent_t kev[8][2];
-    bool kev_used[8];
-    cudaEvent_t fev[6];                       // fast path: before pass A, B, C, after C; around the fused output pass
-    bool fast_timed;
+    cudaEvent_t kev[16][2];
+    bool kev_used[16];
     dvdagpu_stats stats;
     uint64_t pcm_samples;
     std::vector<TrackDev> h_tracks;
@@ -178,7 +176,6 @@ extern "C" dvdagpu_ctx *dvdagpu_create(int device)
     for (auto &e : c->pev) { cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming); }
     for (auto &e : c->ev) cudaEventCreate(&e);
     for (auto &k : c->kev) { cudaEventCreate(&k[0]); cudaEventCreate(&k[1]); }
-    for (auto &e : c->fev) cudaEventCreate(&e);
     uint8_t pcm_tab[2][6][36], crc[256];
     build_pcm_tables(pcm_tab);
     build_crc8(crc);
@@ -194,7 +191,6 @@ extern "C" void dvdagpu_destroy(dvdagpu_ctx *c)
     for (auto &b : c->buf) b.release();
     for (auto &e : c->ev) cudaEventDestroy(e);
     for (auto &k : c->kev) { cudaEventDestroy(k[0]); cudaEventDestroy(k[1]); }
-    for (auto &e : c->fev) cudaEventDestroy(e);
     for (auto &e : c->pev) { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
     if (c->hmap) cudaFreeHost(c->hmap);
     cudaStreamDestroy(c->h2d_stream);
@@ -317,7 +313,6 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     const uint32_t n_sectors = (uint32_t)n_sectors64;
     memset(&c->stats, 0, sizeof c->stats);
     memset(c->kev_used, 0, sizeof c->kev_used);
-    c->fast_timed = false;
     CUDA_TRY(cudaEventRecord(c->ev[0], s));
 
     // tracks in sector order (the kernels binary-search them); results go back in caller order
@@ -501,14 +496,13 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
         uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
 
-        // The three-pass path is bit-exact (the GPU tests run it too) but on a B200 its header
-        // pass is still slower than the single-pass decoder it replaces: opt-in for now.
-        const bool use_fast = getenv("DVDAGPU_FAST") != nullptr;
+        // The three-pass path (access-unit parallel) decodes what has the common shape; the complete
+        // single-pass decoder takes the rest.  DVDAGPU_SINGLE_PASS=1 gives everything to the latter
+        // (the GPU tests run both ways).
+        const bool use_fast = getenv("DVDAGPU_SINGLE_PASS") == nullptr;
         if (use_fast) {
             ENSURE(B_AU_SNAP, naua * 2 * au_snap_bytes());
-            ENSURE(B_FILT_SNAP, naua * 2 * 4 * filt_snap_bytes());
             m.au_snap = reinterpret_cast<AuSnap *>(c->buf[B_AU_SNAP].p);
-            m.filt_snap = reinterpret_cast<FiltSnap *>(c->buf[B_FILT_SNAP].p);
             ENSURE(B_AU_FCHG, naua * 2); ENSURE(B_SEG_CTX, (size_t)nseg * 2 * seg_ctx_bytes());
             ENSURE(B_AU_DELTA, naua * 2 * au_delta_bytes());
             m.au_fchg = c->buf[B_AU_FCHG].as<uint8_t>();
@@ -534,8 +528,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
                 // (start with every segment flagged: substreams with more than 4 channels
                 // are not visited by the fast path at all)
                 CUDA_TRY(cudaMemsetAsync(m.ss_flags, SEG_FALLBACK, (size_t)nseg * 2 * 4, s));
-                TRY(launch_mlp_fast(m, d_work, n_work, n_warps, c->fev, s));
-                c->fast_timed = true;
+                TRY(launch_mlp_fast(m, d_work, n_work, n_warps, c->kev, c->kev_used, s));
                 CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
                 CUDA_TRY(cudaMemcpyAsync(m.ss_flags_fast, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
                 m.fast = 1;
@@ -595,9 +588,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
     if (nseg && m.fast) {
         // fast path, single-substream tracks: filters + rematrix + interleaved output in one pass
-        CUDA_TRY(cudaEventRecord(c->fev[4], s));
-        TRY(launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
-        CUDA_TRY(cudaEventRecord(c->fev[5], s));
+        TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
     }
     if (nseg && max_chunks && (!m.fast || (status & STATUS_WANTS_REMATRIX))) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, max_chunks, mlp_channel_mask, s));
     if (any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, np, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));
@@ -624,13 +615,8 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.decode_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.output_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); c->stats.total_ms = ms;
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 16; k++) {
         if (c->kev_used[k] && cudaEventElapsedTime(&ms, c->kev[k][0], c->kev[k][1]) == cudaSuccess) c->stats.kernel_ms[k] = ms;
-    }
-    if (c->fast_timed) {
-        for (int k = 0; k < 3; k++)
-            if (cudaEventElapsedTime(&ms, c->fev[k], c->fev[k + 1]) == cudaSuccess) c->stats.kernel_ms[DVDAGPU_K_MLP_HEADERS + k] = ms;
-        if (cudaEventElapsedTime(&ms, c->fev[4], c->fev[5]) == cudaSuccess) c->stats.kernel_ms[DVDAGPU_K_MLP_FILTER_OUT] = ms;
     }
     c->stats.launches = g_launch_count;
     c->stats.segments = nseg;

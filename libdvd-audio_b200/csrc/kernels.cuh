@@ -16,7 +16,6 @@ struct PacketTable {
 };
 
 struct AuSnap;      // mlp_decode.cu: what pass B needs to entropy-decode one access unit
-struct FiltSnap;    // mlp_decode.cu: filter parameters of one channel for one access unit
 struct SegCtx;      // mlp_decode.cu: what a segment's restart header fixes for its parameter blocks
 struct AuDelta;     // mlp_decode.cu: the parameters one access unit transmits
 
@@ -46,8 +45,7 @@ struct MlpTables {
     uint8_t *bypass;
     int32_t *pcm;
     AuSnap *au_snap;               // [2][nau]
-    FiltSnap *filt_snap;           // [2][nau][4], written where au_fchg says so
-    uint8_t *au_fchg;              // [2][nau]: filter parameters (re)stated with this access unit
+    uint8_t *au_fchg;              // [2][nau]: bit cc = the filter set-up of channel cc changes with this access unit
     SegCtx *seg_ctx;               // [2][nseg]
     AuDelta *au_delta;             // [2][nau], written where the AU brings parameters
     uint32_t fast;                 // 1: the complete decoder only takes segments flagged SEG_FALLBACK
@@ -104,12 +102,11 @@ int launch_mlp_decode(MlpTables m, const DecWork *const work[5], const uint32_t 
 int launch_carry_fix(MlpTables m, cudaStream_t s);
 int launch_mlp_filter_out(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s);
 size_t au_snap_bytes();
-size_t filt_snap_bytes();
 size_t seg_ctx_bytes();
 size_t au_delta_bytes();
 // fast path: pass A (headers), B (entropy, one lane per access unit), C (filters, one lane per channel)
 int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
-                    cudaEvent_t ev[4], cudaStream_t s);
+                    cudaEvent_t (*kev)[2], bool *kev_used, cudaStream_t s);
 int launch_seg_finalize(MlpTables m, uint32_t *seg_frames, uint32_t *status, cudaStream_t s);
 int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, cudaStream_t s);
 int launch_rematrix(MlpTables m, uint32_t max_chunks, uint32_t channel_mask, cudaStream_t s);

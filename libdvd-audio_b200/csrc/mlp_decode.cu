@@ -23,6 +23,7 @@
 // matrices, LSB bypass and output shift, and writes interleaved frames.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "../../include/dvdagpu.h"
 
 // ------------------------------------------------------------- check data
 
@@ -1009,11 +1010,6 @@ struct AuSnap {
     uint8_t min_ch, nch, pad0, pad1;
     ChanSnap ch[4];
 };
-struct FiltSnap {
-    int16_t cf[8], ci[8];   // coefficients, zero beyond the orders
-    int32_t ist[8];         // IIR history to install (age order) when ist_new
-    uint8_t shift, q, ist_new, orders;   // orders: FIR | IIR << 4
-};
 
 // noise generator advanced by n frames
 __device__ __forceinline__ uint32_t noise_advance(uint32_t seed, uint32_t n)
@@ -1028,55 +1024,69 @@ __device__ __forceinline__ uint32_t noise_advance(uint32_t seed, uint32_t n)
 //   A0  k_mlp_segctx    lane = (segment, substream): the restart header and the
 //                       parameters of the segment's first access unit give the
 //                       context every later parameter block is parsed in (channel
-//                       range, matrix channel count, presence flags);
+//                       range, matrix channel count, presence flags, noise seed);
 //   A1  k_mlp_au_parse  lane = (segment, substream, access unit > 0): parses the
 //                       AU's parameter block *as a delta* (what was transmitted,
 //                       nothing resolved) and notes where the residuals begin;
-//   A2  k_mlp_resolve   lane = (segment, substream): walks the deltas of the
-//                       segment in order — no bit stream access past the first AU —
-//                       and writes what passes B and C need per AU.
-// A parameter block that changes the presence flags, a restart header in the
-// middle of a segment and everything malformed give the segment to the complete
-// decoder.
+//   A2  k_mlp_resolve   lane = (segment, substream): walks the heads of the deltas
+//                       in order — no bit stream access — and writes what pass B
+//                       needs per AU, the rematrix parameter sets and the noise seeds.
+// The first access unit's "delta" states everything (defaults included), so the
+// consumers treat all access units alike.  The filter passes read coefficients and
+// histories straight from the deltas.  A parameter block that changes the presence
+// flags, a restart header in the middle of a segment and everything malformed give
+// the segment to the complete decoder.
 
-struct SegCtx { uint8_t min_ch, max_ch, mmc, flags, ok, pad[3]; };
+struct SegCtx { uint32_t seed; uint8_t min_ch, max_ch, mmc, flags, noise_shift, ok, pad[2]; };
 
 #define CD_PRESENT 1u
 #define CD_FIR 2u
 #define CD_IIR 4u
 #define CD_IIR_STATE 8u
 #define CD_OFFSET 16u
-struct ChanDelta {
-    int32_t ist[8];                  // IIR history as transmitted: [0] pairs with coefficient 0
-    int16_t fir_c[8], iir_c[8];
-    int32_t huff_offset;
-    uint8_t fir_order, fir_shift, iir_order, iir_shift;
-    uint8_t codebook, huff_lsbs, present, pad;
-};
 #define AD_BLOCK 1u
 #define AD_MATRIX 2u
 #define AD_SHIFT 4u
 #define AD_Q 8u
-struct AuDelta {
+struct ChanHead {
+    int32_t huff_offset;
+    uint8_t fir_order, fir_shift, iir_order, iir_shift;
+    uint8_t codebook, huff_lsbs, present, pad;
+};
+struct ChanCoef {
+    int32_t ist[8];                  // IIR history as transmitted: [0] pairs with coefficient 0
+    int16_t fir_c[8], iir_c[8];
+};
+struct __align__(16) AuDelta {
+    // head (80 bytes): all the resolve pass looks at
     uint16_t block_size;
     uint8_t present, matrix_len;
     uint8_t mat_out[DVDA_MAX_MAT], mat_bypass[DVDA_MAX_MAT];
-    int16_t coeff[DVDA_MAX_MAT][DVDA_MAX_CH];
     uint8_t out_shift[DVDA_MAX_CH], q[DVDA_MAX_CH];
-    ChanDelta ch[4];
+    ChanHead ch[4];
+    // bulk
+    ChanCoef cf[4];
+    int16_t coeff[DVDA_MAX_MAT][DVDA_MAX_CH];
 };
+static_assert(offsetof(AuDelta, cf) == 80 && sizeof(AuDelta) % 16 == 0, "AuDelta layout");
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // seat a global-memory reader on substream k of access unit A; false = not for the fast path
 __device__ __forceinline__ bool au_seat(const MlpTables &m, const TrackDev &T, uint32_t A, uint32_t k, GRd &b,
                                         uint32_t &end_bits, uint64_t &origin)
 {
     const uint64_t au_pos = m.au_pos[A];
+    // the header and a typical parameter block, in flight together
+    const uint8_t *line = m.es + (au_pos & ~31ull);
+    prefetch_l1(line); prefetch_l1(line + 32); prefetch_l1(line + 64); prefetch_l1(line + 96);
     const AuLayout L = au_layout(m.es, au_pos, T);
     // damage, dropped AUs and the end-of-track rules are the complete decoder's business
     if (!L.ok || au_pos + L.total > T.es_cut || m.au_err[A]) return false;
     const uint32_t start = k ? L.end[0] : 0;
     const uint32_t len = L.end[k] - start - (L.chk0 ? 2 : 0);
     const uint64_t data = au_pos + L.data0 + start;
+    if (k) { const uint8_t *l2 = m.es + (data & ~31ull); prefetch_l1(l2); prefetch_l1(l2 + 32); prefetch_l1(l2 + 64); }
     grd_seat(b, m.es, data);
     rd_skip(b, (uint32_t)(data & 3) * 8);
     end_bits = (uint32_t)(data & 3) * 8 + len * 8;
@@ -1086,7 +1096,7 @@ __device__ __forceinline__ bool au_seat(const MlpTables &m, const TrackDev &T, u
 
 // one channel's FIR or IIR block of a delta (mlp.c:1029-1120)
 template <typename RD>
-__device__ bool delta_filter(RD &b, ChanDelta &C, bool iir, uint32_t &present)
+__device__ bool delta_filter(RD &b, ChanHead &C, ChanCoef &K, bool iir, uint32_t &present)
 {
     const uint32_t order = rd_get(b, 4);
     if (order > 8) return false;
@@ -1097,13 +1107,13 @@ __device__ bool delta_filter(RD &b, ChanDelta &C, bool iir, uint32_t &present)
         if (bits < 1 || bits > 16) return false;
         const uint32_t cshift = rd_get(b, 3);
         if (bits + cshift > 16) return false;
-        int16_t *coef = iir ? C.iir_c : C.fir_c;
+        int16_t *coef = iir ? K.iir_c : K.fir_c;
         for (uint32_t i = 0; i < order; i++) coef[i] = (int16_t)((uint32_t)rd_get_s(b, bits) << cshift);
         if (rd_get(b, 1)) {
             if (!iir) return false;
             const uint32_t sbits = rd_get(b, 4), sshift = rd_get(b, 4);
             if (!sbits) return false;                           // reference underflows (G2)
-            for (uint32_t i = 0; i < order; i++) C.ist[i] = (int32_t)((uint32_t)rd_get_s(b, sbits) << sshift);
+            for (uint32_t i = 0; i < order; i++) K.ist[i] = (int32_t)((uint32_t)rd_get_s(b, sbits) << sshift);
             present |= CD_IIR_STATE;
         }
     }
@@ -1148,12 +1158,13 @@ __device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D)
         for (uint32_t c = 0; c <= cx.max_ch; c++) D.q[c] = (uint8_t)rd_get(b, 4);
     }
     for (uint32_t c = cx.min_ch; c <= cx.max_ch; c++) {
-        ChanDelta &C = D.ch[c - cx.min_ch];
+        ChanHead &C = D.ch[c - cx.min_ch];
+        ChanCoef &K = D.cf[c - cx.min_ch];
         uint32_t p = 0;
         if (rd_get(b, 1)) {
             p = CD_PRESENT;
-            if ((cx.flags & 0x08) && rd_get(b, 1) && !delta_filter(b, C, false, p)) return false;
-            if ((cx.flags & 0x04) && rd_get(b, 1) && !delta_filter(b, C, true, p)) return false;
+            if ((cx.flags & 0x08) && rd_get(b, 1) && !delta_filter(b, C, K, false, p)) return false;
+            if ((cx.flags & 0x04) && rd_get(b, 1) && !delta_filter(b, C, K, true, p)) return false;
             if ((cx.flags & 0x02) && rd_get(b, 1)) { C.huff_offset = rd_get_s(b, 15); p |= CD_OFFSET; }
             C.codebook = (uint8_t)rd_get(b, 2);
             C.huff_lsbs = (uint8_t)rd_get(b, 5);
@@ -1165,43 +1176,7 @@ __device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D)
     return true;
 }
 
-// the same parameters, merged into the running state (what decoding_params does in place)
-__device__ void apply_delta(SubState &s, const AuDelta &D)
-{
-    if (D.present & AD_BLOCK) s.block_size = D.block_size;
-    if (D.present & AD_MATRIX) {
-        s.dirty = 1;
-        s.matrix_len = D.matrix_len;
-        for (uint32_t k = 0; k < D.matrix_len; k++) {
-            s.mat_out[k] = D.mat_out[k]; s.mat_bypass[k] = D.mat_bypass[k];
-            for (uint32_t c = 0; c < DVDA_MAX_CH; c++) s.coeff[k][c] = D.coeff[k][c];
-        }
-    }
-    if (D.present & AD_SHIFT) { s.dirty = 1; for (uint32_t c = 0; c <= s.mmc; c++) s.out_shift[c] = D.out_shift[c]; }
-    if (D.present & AD_Q) { s.dirty = 1; for (uint32_t c = 0; c <= s.max_ch; c++) s.q[c] = D.q[c]; }
-    for (uint32_t c = s.min_ch; c <= s.max_ch; c++) {
-        const ChanDelta &X = D.ch[c - s.min_ch];
-        ChanState &C = s.ch[c];
-        if (!(X.present & CD_PRESENT)) continue;
-        if (X.present & CD_FIR) {
-            C.fir_order = X.fir_order; C.fir_shift = X.fir_shift;
-            for (uint32_t i = 0; i < X.fir_order; i++) C.fir_c[i] = X.fir_c[i];
-        }
-        if (X.present & CD_IIR) {
-            C.iir_order = X.iir_order; C.iir_shift = X.iir_shift;
-            for (uint32_t i = 0; i < X.iir_order; i++) C.iir_c[i] = X.iir_c[i];
-            C.ilen = 0; C.ihead = 0; C.ist_new = 1;
-            if (X.present & CD_IIR_STATE) {
-                for (uint32_t i = 0; i < X.iir_order; i++) C.ist[(X.iir_order - 1 - i) & 7] = X.ist[i];
-                C.ilen = X.iir_order; C.ihead = X.iir_order & 7;
-            }
-        }
-        if (X.present & CD_OFFSET) C.huff_offset = X.huff_offset;
-        C.codebook = X.codebook; C.huff_lsbs = X.huff_lsbs;
-    }
-}
-
-// A0: context of a segment's substream
+// A0: context of a segment's substream, and its first access unit as an all-stating delta
 __device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJob &job)
 {
     const SegDev &S = m.segs[job.seg];
@@ -1209,6 +1184,8 @@ __device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJ
     SegCtx cx;
     memset(&cx, 0, sizeof cx);
     if (S.n_au) {
+        const uint32_t A = S.au_base;
+        AuSnap &sn = m.au_snap[(uint64_t)job.k * m.nau + A];
         GRd b;
         uint32_t end_bits;
         uint64_t origin;
@@ -1216,9 +1193,35 @@ __device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJ
         memset(&s, 0, sizeof s);
         s.flags = 0xFF;
         bool changed;
-        if (au_seat(m, T, S.au_base, job.k, b, end_bits, origin) && block_header(b, s, changed) && rd_pos(b) <= end_bits &&
+        if (au_seat(m, T, A, job.k, b, end_bits, origin) && block_header(b, s, changed) && rd_pos(b) <= end_bits &&
             s.max_ch - s.min_ch < 4) {
+            cx.seed = s.seed; cx.noise_shift = s.noise_shift;
             cx.min_ch = s.min_ch; cx.max_ch = s.max_ch; cx.mmc = s.mmc; cx.flags = s.flags; cx.ok = 1;
+            sn.bit0 = origin + rd_pos(b);
+            sn.bit_end = origin + end_bits;
+            sn.valid = 2;
+            AuDelta &D = m.au_delta[(uint64_t)job.k * m.nau + A];
+            D.block_size = s.block_size;
+            D.present = (uint8_t)(AD_BLOCK | AD_MATRIX | AD_SHIFT | AD_Q);
+            D.matrix_len = s.matrix_len;
+            for (uint32_t k = 0; k < DVDA_MAX_MAT; k++) {
+                D.mat_out[k] = s.mat_out[k]; D.mat_bypass[k] = s.mat_bypass[k];
+                for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.coeff[k][c] = s.coeff[k][c];
+            }
+            for (uint32_t c = 0; c < DVDA_MAX_CH; c++) { D.out_shift[c] = s.out_shift[c]; D.q[c] = s.q[c]; }
+            for (uint32_t c = s.min_ch; c <= s.max_ch; c++) {
+                const ChanState &C = s.ch[c];
+                ChanHead &H = D.ch[c - s.min_ch];
+                ChanCoef &K = D.cf[c - s.min_ch];
+                H.huff_offset = C.huff_offset;
+                H.fir_order = C.fir_order; H.fir_shift = C.fir_shift; H.iir_order = C.iir_order; H.iir_shift = C.iir_shift;
+                H.codebook = C.codebook; H.huff_lsbs = C.huff_lsbs;
+                H.present = (uint8_t)(CD_PRESENT | CD_FIR | CD_IIR | CD_OFFSET | (C.ilen ? CD_IIR_STATE : 0u));
+                for (uint32_t i = 0; i < 8; i++) {
+                    K.fir_c[i] = (int16_t)C.fir_c[i]; K.iir_c[i] = (int16_t)C.iir_c[i];
+                    K.ist[i] = i < C.ilen ? C.ist[(C.ihead - 1 - i) & 7] : 0;
+                }
+            }
         }
     }
     m.seg_ctx[job.k * m.nseg + job.seg] = cx;
@@ -1257,104 +1260,185 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
     const TrackDev &T = m.tracks[S.track];
     const bool governing = job.k + 1 == T.nss;
     const uint32_t nominal = T.au_nominal;
-
-    SubState s;
-    memset(&s, 0, sizeof s);
-    s.flags = 0xFF;
+    const SegCtx cx = m.seg_ctx[job.k * m.nseg + job.seg];
     AuSnap *snaps = m.au_snap + (uint64_t)job.k * m.nau;
-    FiltSnap *fsnaps = m.filt_snap + (uint64_t)job.k * m.nau * 4;
+    const AuDelta *deltas = m.au_delta + (uint64_t)job.k * m.nau;
     uint8_t *fchg = m.au_fchg + (uint64_t)job.k * m.nau;
 
-    uint32_t frames = 0, flags = 0, pset = 0xFFFFFFFFu;
-    bool fallback = !m.seg_ctx[job.k * m.nseg + job.seg].ok;
+    // running state: what the entropy decoder needs, per channel of the substream
+    uint32_t block_size = 8, want = 0, q8 = 0;            // q8: quant_step_size of channels 0..7, a nibble each
+    uint64_t shift8 = 0;                                  // output shifts, a byte each
+    uint32_t mat_src = 0;                                 // access unit whose delta holds the matrices in force
+    uint32_t matrix_len = 0;
+    int32_t offset[NCH];
+    uint32_t cb[NCH], lsbs[NCH], fo[NCH], io[NCH], fs[NCH], is[NCH];
+#pragma unroll
+    for (int cc = 0; cc < NCH; cc++) { offset[cc] = 0; cb[cc] = 0; lsbs[cc] = 24; fo[cc] = io[cc] = fs[cc] = is[cc] = 0; }
+    uint32_t seed = cx.seed, frames = 0, flags = 0, pset = 0xFFFFFFFFu;
+    bool fallback = !cx.ok || (uint32_t)(cx.max_ch - cx.min_ch + 1) != NCH;
+
     for (uint32_t a = 0; a < S.n_au && !fallback; a++) {
         const uint32_t A = S.au_base + a;
-        AuSnap sn;
-        bool fresh;                                      // parameters arrived with this access unit
-        if (a == 0) {
-            GRd b;
-            uint32_t end_bits;
-            uint64_t origin;
-            bool changed;
-            if (!au_seat(m, T, A, job.k, b, end_bits, origin) || !block_header(b, s, changed) || rd_pos(b) > end_bits) { fallback = true; break; }
-            sn.bit0 = origin + rd_pos(b);
-            sn.bit_end = origin + end_bits;
-            fresh = true;
-        } else {
-            sn = snaps[A];
-            if (!sn.valid) { fallback = true; break; }
-            fresh = sn.valid == 2;
-            if (fresh) apply_delta(s, m.au_delta[(uint64_t)job.k * m.nau + A]);
+        const uint32_t state = snaps[A].valid;
+        if (!state) { fallback = true; break; }
+        bool dirty = false;
+        uint32_t chg = 0;                                 // channels whose filter set-up changes with this AU
+        if (state == 2) {
+            // the head of the delta: five 16-byte loads in flight together
+            union { uint4 v[5]; AuDelta d; } u;           // (only the head of d is populated)
+            const uint4 *src = reinterpret_cast<const uint4 *>(deltas + A);
+#pragma unroll
+            for (int i = 0; i < 5; i++) u.v[i] = src[i];
+            const uint8_t *raw = reinterpret_cast<const uint8_t *>(u.v);
+            const uint32_t present = raw[offsetof(AuDelta, present)];
+            if (present & AD_BLOCK) block_size = *reinterpret_cast<const uint16_t *>(raw + offsetof(AuDelta, block_size));
+            if (present & AD_MATRIX) {
+                dirty = true; mat_src = A;
+                matrix_len = raw[offsetof(AuDelta, matrix_len)];
+                want = 0;
+#pragma unroll
+                for (int k = 0; k < DVDA_MAX_MAT; k++)
+                    want |= ((uint32_t)k < matrix_len && raw[offsetof(AuDelta, mat_bypass) + k]) ? 1u << k : 0u;
+            }
+            if (present & AD_SHIFT) {
+                dirty = true;
+#pragma unroll
+                for (int c = 0; c < DVDA_MAX_CH; c++)
+                    if ((uint32_t)c <= cx.mmc) shift8 = (shift8 & ~(0xFFull << (8 * c))) | ((uint64_t)raw[offsetof(AuDelta, out_shift) + c] << (8 * c));
+            }
+            if (present & AD_Q) {
+                dirty = true;
+#pragma unroll
+                for (int c = 0; c < DVDA_MAX_CH; c++)
+                    if ((uint32_t)c <= cx.max_ch) q8 = (q8 & ~(15u << (4 * c))) | ((uint32_t)raw[offsetof(AuDelta, q) + c] << (4 * c));
+                chg = (1u << NCH) - 1;
+            }
+#pragma unroll
+            for (int cc = 0; cc < NCH; cc++) {
+                const uint8_t *h = raw + offsetof(AuDelta, ch) + cc * sizeof(ChanHead);
+                const uint32_t p = h[offsetof(ChanHead, present)];
+                if (!(p & CD_PRESENT)) continue;
+                if (p & CD_FIR) { fo[cc] = h[offsetof(ChanHead, fir_order)]; fs[cc] = h[offsetof(ChanHead, fir_shift)]; chg |= 1u << cc; }
+                if (p & CD_IIR) {
+                    io[cc] = h[offsetof(ChanHead, iir_order)]; is[cc] = h[offsetof(ChanHead, iir_shift)]; chg |= 1u << cc;
+                    // the history is replaced by what was sent: too short = reference reads out of bounds (G2)
+                    if (io[cc] && !(p & CD_IIR_STATE)) fallback = true;
+                }
+                if (p & CD_OFFSET) offset[cc] = *reinterpret_cast<const int32_t *>(h + offsetof(ChanHead, huff_offset));
+                cb[cc] = h[offsetof(ChanHead, codebook)]; lsbs[cc] = h[offsetof(ChanHead, huff_lsbs)];
+            }
         }
-        snaps[A].valid = 0;
-        if ((uint32_t)(s.max_ch - s.min_ch + 1) != NCH || s.block_size > nominal || nominal % s.block_size) { fallback = true; break; }
+        if (block_size > nominal || nominal % block_size) { fallback = true; break; }
 
-        sn.block_size = s.block_size;
-        sn.min_ch = s.min_ch; sn.nch = NCH; sn.pad0 = sn.pad1 = 0;
-        uint32_t want = 0;
-        for (uint32_t k = 0; k < s.matrix_len; k++) want |= (uint32_t)(s.mat_bypass[k] != 0) << k;
-        sn.want = (uint8_t)want;
-        uint32_t cflags = 0;
+        // per-channel constants of the AU's blocks (mlp.c:1151-1176, 1260-1270)
+        struct { uint16_t block_size; uint8_t want, valid, min_ch, nch, pad0, pad1; ChanSnap ch[4]; } out;
+        out.block_size = (uint16_t)block_size; out.want = (uint8_t)want; out.valid = 1;
+        out.min_ch = cx.min_ch; out.nch = NCH; out.pad0 = out.pad1 = 0;
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) { out.ch[cc].sho = 0; out.ch[cc].cb = out.ch[cc].lsb_bits = out.ch[cc].q = out.ch[cc].shift = 0; }
 #pragma unroll
         for (int cc = 0; cc < NCH; cc++) {
-            ChanState &C = s.ch[s.min_ch + cc];
-            const uint32_t q = s.q[s.min_ch + cc];
-            uint32_t lsb_bits = 0, shift = 0;
-            int32_t sho = 0;
-            if (!channel_setup(s, C, q, job.exact_history, cflags, lsb_bits, sho, shift)) { fallback = true; break; }
-            sn.ch[cc].sho = sho; sn.ch[cc].cb = C.codebook; sn.ch[cc].lsb_bits = (uint8_t)lsb_bits;
-            sn.ch[cc].q = (uint8_t)q; sn.ch[cc].shift = (uint8_t)shift;
-            if (fresh) {
-                FiltSnap fs;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    fs.cf[j] = j < C.fir_order ? (int16_t)C.fir_c[j] : (int16_t)0;
-                    fs.ci[j] = j < C.iir_order ? (int16_t)C.iir_c[j] : (int16_t)0;
-                    fs.ist[j] = (C.ist_new && j < C.ilen) ? C.ist[(C.ihead - 1 - j) & 7] : 0;
-                }
-                fs.shift = (uint8_t)shift; fs.q = (uint8_t)q; fs.ist_new = C.ist_new;
-                fs.orders = (uint8_t)(C.fir_order | C.iir_order << 4);
-                fsnaps[(uint64_t)A * 4 + cc] = fs;
+            const uint32_t q = (q8 >> (4 * (cx.min_ch + cc))) & 15;
+            if (lsbs[cc] < q) { fallback = true; break; }
+            const uint32_t nb = lsbs[cc] - q;
+            int32_t sho;
+            if (cb[cc]) {
+                const int ss = (int)nb + 2 - (int)cb[cc];
+                sho = offset[cc] - 7 * (1 << nb) - (ss >= 0 ? (1 << ss) : 0);
+            } else {
+                sho = offset[cc] - (nb >= 1 ? (1 << (nb - 1)) : 0);
             }
-            C.ist_new = 0;
-            C.flen = 8; C.ilen = 8;
+            if (fo[cc] + io[cc] > 8) { fallback = true; break; }
+            if (fs[cc] > 0 && is[cc] > 0 && fs[cc] != is[cc]) { fallback = true; break; }
+            if (a == 0 && fo[cc] > 0) {
+                // FIR history of the previous segment is needed (the reference never clears it)
+                if (!job.exact_history) flags |= SEG_WANTS_PREV;
+                fallback = true; break;
+            }
+            out.ch[cc].sho = sho; out.ch[cc].cb = (uint8_t)cb[cc]; out.ch[cc].lsb_bits = (uint8_t)nb; out.ch[cc].q = (uint8_t)q;
+            out.ch[cc].shift = (uint8_t)((fs[cc] > 0 && is[cc] > 0) ? fs[cc] : fo[cc] > 0 ? fs[cc] : is[cc]);
         }
-        if (cflags & SEG_NEEDS_CARRY) { flags |= SEG_WANTS_PREV; fallback = true; break; }
         if (fallback) break;
-        fchg[A] = fresh;
-        sn.valid = 1;
-        snaps[A] = sn;
+        // bytes 16..55 of the snapshot (the positions in front are pass A0/A1's)
+        static_assert(sizeof(out) == 40 && offsetof(AuSnap, block_size) == 16 && sizeof(AuSnap) == 56, "AuSnap layout");
+        {
+            const uint64_t *o = reinterpret_cast<const uint64_t *>(&out);
+            uint64_t *dst = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(snaps + A) + 16);
+#pragma unroll
+            for (int i = 0; i < 5; i++) dst[i] = o[i];
+        }
+        fchg[A] = (uint8_t)chg;
 
         const uint32_t au_frame0 = frames;
         frames += nominal;
         m.au_frames_ss[job.k * m.nau + A] = nominal;
         if (governing) {
-            if (s.dirty || pset == 0xFFFFFFFFu) {
+            if (dirty || pset == 0xFFFFFFFFu) {
                 ParamSet P;
                 memset(&P, 0, sizeof P);
-                P.matrix_len = s.matrix_len; P.mmc = s.mmc; P.noise_shift = s.noise_shift;
+                P.matrix_len = (uint8_t)matrix_len; P.mmc = cx.mmc; P.noise_shift = cx.noise_shift;
+                const AuDelta &M = m.au_delta[(uint64_t)job.k * m.nau + mat_src];
                 uint32_t uses = 0;
-                for (uint32_t k = 0; k < s.matrix_len; k++) {
-                    P.out_ch[k] = s.mat_out[k];
-                    for (int c = 0; c < DVDA_MAX_CH; c++) P.coeff[k][c] = s.coeff[k][c];
-                    uses |= (s.coeff[k][s.mmc + 1] != 0) | (s.coeff[k][s.mmc + 2] != 0);
+                for (uint32_t k = 0; k < matrix_len; k++) {
+                    P.out_ch[k] = M.mat_out[k];
+                    for (int c = 0; c < DVDA_MAX_CH; c++) P.coeff[k][c] = M.coeff[k][c];
+                    uses |= (M.coeff[k][cx.mmc + 1] != 0) | (M.coeff[k][cx.mmc + 2] != 0);
                 }
                 P.uses_noise = uses;
-                uint32_t shifts = 0;
-                for (int c = 0; c < DVDA_MAX_CH; c++) { P.q[c] = s.q[c]; P.out_shift[c] = s.out_shift[c]; shifts |= s.out_shift[c]; }
+                for (int c = 0; c < DVDA_MAX_CH; c++) { P.q[c] = (q8 >> (4 * c)) & 15; P.out_shift[c] = (uint8_t)(shift8 >> (8 * c)); }
                 m.psets[A] = P;
                 // top bit: nothing to do for these frames but to copy them
-                pset = A | ((s.matrix_len == 0 && shifts == 0) ? 0x80000000u : 0u);
-                s.dirty = 0;
+                pset = A | ((matrix_len == 0 && shift8 == 0) ? 0x80000000u : 0u);
             }
-            AuDev R = {au_frame0, nominal, s.seed, pset};
+            AuDev R = {au_frame0, nominal, seed, pset};
             m.au[A] = R;
-            s.seed = noise_advance(s.seed, nominal);
+            seed = noise_advance(seed, nominal);
         }
     }
     if (fallback) flags |= SEG_FALLBACK;
     m.ss_flags[job.k * m.nseg + job.seg] = flags;
     if (job.k == 0) S.frames = frames;
+}
+
+// ---- filter passes: one channel's set-up from the delta of an access unit -----------------
+struct FiltSetup { uint32_t fo, io, fsh, ish, q; };      // orders, shifts, quant_step_size in force
+
+__device__ __forceinline__ void filt_take_delta(const AuDelta &D, uint32_t cc, uint32_t c, FiltSetup &F,
+                                                int32_t (&cf)[8], int32_t (&ci)[8], int32_t (&ih)[8])
+{
+    const uint32_t *hw = reinterpret_cast<const uint32_t *>(&D.ch[cc]);
+    const uint32_t h1 = hw[1], h2 = hw[2];               // orders + shifts; codebook, lsbs, present
+    const uint32_t p = (h2 >> 16) & 0xFF;
+    if (D.present & AD_Q) F.q = D.q[c];
+    if (!(p & (CD_FIR | CD_IIR))) return;
+    const uint4 *kw = reinterpret_cast<const uint4 *>(&D.cf[cc]);
+    const uint4 s0 = kw[0], s1 = kw[1], fc = kw[2], ic = kw[3];
+    if (p & CD_FIR) {
+        F.fo = h1 & 0xFF; F.fsh = (h1 >> 8) & 0xFF;
+        const uint32_t w[4] = {fc.x, fc.y, fc.z, fc.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
+            cf[j] = (uint32_t)j < F.fo ? v : 0;
+        }
+    }
+    if (p & CD_IIR) {
+        F.io = (h1 >> 16) & 0xFF; F.ish = h1 >> 24;
+        const uint32_t w[4] = {ic.x, ic.y, ic.z, ic.w};
+        const int32_t st[8] = {(int32_t)s0.x, (int32_t)s0.y, (int32_t)s0.z, (int32_t)s0.w,
+                               (int32_t)s1.x, (int32_t)s1.y, (int32_t)s1.z, (int32_t)s1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
+            ci[j] = (uint32_t)j < F.io ? v : 0;
+            // the history is replaced by what was sent (or emptied)
+            ih[j] = ((p & CD_IIR_STATE) && (uint32_t)j < F.io) ? st[j] : 0;
+        }
+    }
+}
+__device__ __forceinline__ uint32_t filt_shift(const FiltSetup &F)
+{
+    return (F.fsh > 0 && F.ish > 0) ? F.fsh : F.fo > 0 ? F.fsh : F.ish;
 }
 
 // ---- pass B: entropy decode of one access unit -------------------------------------
@@ -1455,7 +1539,7 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
     const GroupDev &G = m.groups[T.grp_base + (seg - T.seg_base) / DVDA_LANES];
     const uint32_t nch = T.channels, nominal = T.au_nominal, cap = G.cap;
     const AuSnap *snaps = m.au_snap + (uint64_t)k * m.nau;
-    const FiltSnap *fsnaps = m.filt_snap + (uint64_t)k * m.nau * 4;
+    const AuDelta *deltas = m.au_delta + (uint64_t)k * m.nau;
     if (!S.n_au) return;
     const uint32_t c = snaps[S.au_base].min_ch + cc;
     int32_t fh[8], ih[8], cf[8], ci[8];
@@ -1466,14 +1550,13 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
     uint32_t f = 0;
     int32_t nx[8];
     uint32_t shift = 0, q = 0;
+    FiltSetup F = {0, 0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 8; j++) nx[j] = ((uint32_t)j < cap) ? tile[(uint64_t)j * tile_step] : 0;
     for (uint32_t a = 0; a < S.n_au; a++) {
-        if (m.au_fchg[(uint64_t)k * m.nau + S.au_base + a]) {
-            const FiltSnap fs = fsnaps[(uint64_t)(S.au_base + a) * 4 + cc];
-#pragma unroll
-            for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
-            shift = fs.shift; q = fs.q;
+        if ((m.au_fchg[(uint64_t)k * m.nau + S.au_base + a] >> cc) & 1) {
+            filt_take_delta(deltas[S.au_base + a], cc, c, F, cf, ci, ih);
+            shift = filt_shift(F); q = F.q;
         }
         // the nominal AU length is a multiple of 8 (40 * rate multiple); the residuals of
         // the next 8 frames are loaded while the current 8 are filtered
@@ -1528,6 +1611,9 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
 // 32 frames: 32 * NCH consecutive ints per segment, coalesced.  Runs after the
 // frame counts are final (it writes straight into the PCM buffer).
 #define OUT_WARPS 4
+#ifndef OUT_MIN_BLOCKS
+#define OUT_MIN_BLOCKS 5
+#endif
 
 template <int NF, int NI>
 __device__ __forceinline__ void filt8(const int32_t (&cf)[8], const int32_t (&ci)[8], int32_t (&fh)[8], int32_t (&ih)[8],
@@ -1549,7 +1635,7 @@ __device__ __forceinline__ void filt8(const int32_t (&cf)[8], const int32_t (&ci
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, const DecWork *__restrict__ work,
+__global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_out(MlpTables m, const DecWork *__restrict__ work,
                                                                    uint32_t n_work, uint32_t n_warps)
 {
     extern __shared__ int32_t out_sm[];
@@ -1591,7 +1677,8 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
     }
     __syncwarp();
 
-    const FiltSnap *fsnaps = m.filt_snap;
+    const AuDelta *deltas = m.au_delta;
+    FiltSetup F = {0, 0, 0, 0, 0};
     const uint32_t c0 = mine ? m.au_snap[S.au_base].min_ch : 0;  // 0 for a single substream
     int32_t fh[8], ih[8], cf[8], ci[8];
 #pragma unroll
@@ -1641,12 +1728,14 @@ __global__ void __launch_bounds__(OUT_WARPS * 32) k_mlp_filter_out(MlpTables m, 
         const bool au_act = f < my_frames;
         if (au_act) {
             const uint32_t A = S.au_base + a;
-            if (m.au_fchg[A]) {
-                const FiltSnap fs = fsnaps[(uint64_t)A * 4 + cc];
-#pragma unroll
-                for (int j = 0; j < 8; j++) { cf[j] = fs.cf[j]; ci[j] = fs.ci[j]; if (fs.ist_new) ih[j] = fs.ist[j]; }
-                shift = fs.shift; qmask = 0xFFFFFFFFu << fs.q;
-                cls = fs.orders;
+            // the next access unit's records, on their way while this one is filtered
+            prefetch_l1(&deltas[A + 1].ch[cc]); prefetch_l1(&deltas[A + 1].cf[cc]);
+            prefetch_l1(reinterpret_cast<const uint8_t *>(&deltas[A + 1].cf[cc]) + 32);
+            prefetch_l1(&m.au[A + 1]);
+            if ((m.au_fchg[A] >> cc) & 1) {
+                filt_take_delta(deltas[A], cc, c0 + cc, F, cf, ci, ih);
+                shift = filt_shift(F); qmask = 0xFFFFFFFFu << F.q;
+                cls = F.fo | F.io << 4;
             }
             const AuDev au = m.au[A];
             seed = au.seed;
@@ -1908,7 +1997,6 @@ __global__ void k_flag_predecessors(MlpTables m)
 }
 
 size_t au_snap_bytes() { return sizeof(AuSnap); }
-size_t filt_snap_bytes() { return sizeof(FiltSnap); }
 size_t seg_ctx_bytes() { return sizeof(SegCtx); }
 size_t au_delta_bytes() { return sizeof(AuDelta); }
 
@@ -1922,28 +2010,30 @@ static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t
         attr_set = true;
     }
     const uint32_t blocks = div_up_u32(n_warps, DEC_WARPS);
-    if (pass == 0) {
-        LAUNCH(k_mlp_segctx, div_up_u32(n_warps, 4), 128, 0, s, m, work, n_work, n_warps);
-        if (m.max_au > 1) LAUNCH(k_mlp_au_parse, dim3(div_up_u32(n_warps, 4), m.max_au - 1), 128, 0, s, m, work, n_work, n_warps);
-        LAUNCH(k_mlp_resolve<NCH>, div_up_u32(n_warps, 4), 128, 0, s, m, work, n_work, n_warps);
-    }
-    else if (pass == 1) LAUNCH(k_mlp_entropy<NCH>, dim3(blocks, m.max_au ? m.max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
+    const uint32_t small = div_up_u32(n_warps, 4);
+    if (pass == 0) LAUNCH(k_mlp_segctx, small, 128, 0, s, m, work, n_work, n_warps);
+    else if (pass == 1) { if (m.max_au > 1) LAUNCH(k_mlp_au_parse, dim3(small, m.max_au - 1), 128, 0, s, m, work, n_work, n_warps); }
+    else if (pass == 2) LAUNCH(k_mlp_resolve<NCH>, small, 128, 0, s, m, work, n_work, n_warps);
+    else if (pass == 3) LAUNCH(k_mlp_entropy<NCH>, dim3(blocks, m.max_au ? m.max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
     else LAUNCH(k_mlp_filter<NCH>, div_up_u32((uint64_t)n_warps * NCH, 4), 128, 0, s, m, work, n_work, n_warps);
     return 0;
 }
 
 int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
-                    cudaEvent_t ev[4], cudaStream_t s)
+                    cudaEvent_t (*kev)[2], bool *kev_used, cudaStream_t s)
 {
-    for (int pass = 0; pass < 3; pass++) {
-        CUDA_TRY(cudaEventRecord(ev[pass], s));
+    static const int slot[5] = {DVDAGPU_K_MLP_SEGCTX, DVDAGPU_K_MLP_AU_PARSE, DVDAGPU_K_MLP_RESOLVE, DVDAGPU_K_MLP_ENTROPY,
+                                DVDAGPU_K_MLP_FILTER};
+    for (int pass = 0; pass < 5; pass++) {
+        CUDA_TRY(cudaEventRecord(kev[slot[pass]][0], s));
         if (launch_fast_pass<1>(pass, m, work[1], n_work[1], n_warps[1], s)) return -1;
         if (launch_fast_pass<2>(pass, m, work[2], n_work[2], n_warps[2], s)) return -1;
         if (launch_fast_pass<3>(pass, m, work[3], n_work[3], n_warps[3], s)) return -1;
         if (launch_fast_pass<4>(pass, m, work[4], n_work[4], n_warps[4], s)) return -1;
+        CUDA_TRY(cudaEventRecord(kev[slot[pass]][1], s));
+        kev_used[slot[pass]] = true;
     }
     LAUNCH(k_flag_predecessors, div_up_u32((uint64_t)m.nseg * 2, 256), 256, 0, s, m);
-    CUDA_TRY(cudaEventRecord(ev[3], s));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

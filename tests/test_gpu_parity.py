@@ -16,18 +16,19 @@ GOLDEN = json.load(open(os.path.join(HERE, "golden", "catalog_golden.json")))
 DISCS = sorted(catalog.discs().keys())
 
 
-@pytest.fixture(scope="module", params=["single-pass", "three-pass"])
+@pytest.fixture(scope="module", params=["three-pass", "single-pass"])
 def engine(pkg, request):
-    """Every test runs against both MLP decode paths: the complete single-pass decoder
-    (default) and the access-unit-parallel three-pass path (DVDAGPU_FAST=1)."""
-    if request.param == "three-pass":
-        os.environ["DVDAGPU_FAST"] = "1"
+    """Every test runs against both MLP decode paths: the access-unit-parallel three-pass
+    path with the complete decoder as its fall-back (default), and the complete single-pass
+    decoder alone (DVDAGPU_SINGLE_PASS=1)."""
+    if request.param == "single-pass":
+        os.environ["DVDAGPU_SINGLE_PASS"] = "1"
     else:
-        os.environ.pop("DVDAGPU_FAST", None)
+        os.environ.pop("DVDAGPU_SINGLE_PASS", None)
     e = pkg.Engine(0)
     yield e
     e.close()
-    os.environ.pop("DVDAGPU_FAST", None)
+    os.environ.pop("DVDAGPU_SINGLE_PASS", None)
 
 
 def check_track(oracle, eng, res, sectors, g, label):
