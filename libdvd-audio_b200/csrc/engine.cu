@@ -66,7 +66,7 @@ enum {
     B_SECTORS, B_SECTORS2, B_PCM2, B_SEC_CNT, B_SEC_BAD, B_SEC_BASE, B_BAD_PREFIX,
     B_PK_SECTOR, B_PK_OFF, B_PK_LEN, B_PK_CODEC, B_PK_PAD2, B_PK_PARAMS, B_PK_MLPLEN, B_PK_PCMF,
     B_PK_ES, B_PK_PF, B_PK_NONMLP, B_PK_NM_PREFIX, B_PK_STOP, B_PK_STOP_PREFIX, B_PK_YIELD,
-    B_ES, B_SYNC_CNT_RAW, B_SYNC_CNT_VALID, B_SYNC_BASE_RAW, B_SYNC_BASE_VALID, B_RAW, B_VALID,
+    B_ES, B_SYNC_SLOTS, B_SYNC_CNT_RAW, B_SYNC_CNT_VALID, B_SYNC_BASE_RAW, B_SYNC_BASE_VALID, B_RAW, B_VALID,
     B_TRACKS, B_TRK_PK_LO, B_TRK_SEG_BASE, B_TRK_GRP_BASE,
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
     B_SS_FLAGS, B_SS_FLAGS_PREV, B_SS_FLAGS_FAST, B_FIR_TAIL,
@@ -379,11 +379,15 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
     ENSURE(B_SYNC_CNT_RAW, (size_t)chunks * 4); ENSURE(B_SYNC_CNT_VALID, (size_t)chunks * 4);
     ENSURE(B_SYNC_BASE_RAW, (size_t)(chunks + 1) * 4); ENSURE(B_SYNC_BASE_VALID, (size_t)(chunks + 1) * 4);
+    ENSURE(B_SYNC_SLOTS, (size_t)chunks * SYNC_SLOT_BYTES);
+    uint16_t *sync_slots = c->buf[B_SYNC_SLOTS].as<uint16_t>();
+    // (test hook: DVDAGPU_SYNC_SLOTS=0 sends every chunk with a match through the re-search path)
+    const uint32_t nslots = getenv("DVDAGPU_SYNC_SLOTS") ? (uint32_t)atoi(getenv("DVDAGPU_SYNC_SLOTS")) : 6u;
     uint32_t *cnt_raw = c->buf[B_SYNC_CNT_RAW].as<uint32_t>(), *cnt_valid = c->buf[B_SYNC_CNT_VALID].as<uint32_t>();
     uint32_t *base_raw = c->buf[B_SYNC_BASE_RAW].as<uint32_t>(), *base_valid = c->buf[B_SYNC_BASE_VALID].as<uint32_t>();
     uint32_t n_raw = 0, n_valid = 0;
     if (es_total) {
-        TRY(launch_sync_count(es, es_total, cnt_raw, cnt_valid, s));
+        TRY(launch_sync_count(es, es_total, cnt_raw, cnt_valid, sync_slots, nslots, s));
         TRY(scan_u32_to_u32(cnt_raw, base_raw, chunks, tmp, tmp_bytes, s));
         TRY(scan_u32_to_u32(cnt_valid, base_valid, chunks, tmp, tmp_bytes, s));
         TRY(read_back(c, base_raw + chunks, &n_raw));
@@ -391,7 +395,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     }
     ENSURE(B_RAW, ((size_t)n_raw + 1) * 8); ENSURE(B_VALID, ((size_t)n_valid + 1) * 8);
     uint64_t *raw = c->buf[B_RAW].as<uint64_t>(), *valid = c->buf[B_VALID].as<uint64_t>();
-    if (n_raw) TRY(launch_sync_fill(es, es_total, base_raw, base_valid, raw, valid, s));
+    if (n_raw) TRY(launch_sync_fill(es, es_total, cnt_raw, sync_slots, nslots, base_raw, base_valid, raw, valid, s));
 
     ENSURE(B_TRACKS, (size_t)n_tracks * sizeof(TrackDev));
     ENSURE(B_TRK_PK_LO, (size_t)n_tracks * 4); ENSURE(B_TRK_SEG_BASE, (size_t)(n_tracks + 1) * 4);

@@ -17,8 +17,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
-#define SYNC_THREADS 256
-#define SYNC_PER_THREAD (SYNC_CHUNK / SYNC_THREADS)    // 16 positions
+#define SYNC_THREADS (SYNC_CHUNK / 16)   // 16 positions per thread
 
 // A sync position starts a *segment* only if the access unit there is a
 // well-formed major sync (1 or 2 substreams) and every substream opens with a
@@ -47,25 +46,37 @@ __device__ bool sync_starts_segment(const uint8_t *es, uint64_t p, uint64_t es_t
     return true;
 }
 
-// FILL = false: count raw / valid syncs per chunk.  FILL = true: write them, in
-// stream order, at the scanned bases.
-template <bool FILL>
+// The elementary stream is read once.  k_sync_find: one block per 2 KiB chunk, one
+// 16-byte load per thread (the following 7 bytes come from the next lane); the few
+// matches of a chunk go, in stream order, into the chunk's slots (offset in the
+// chunk | valid << 15) next to its counts.  After the counts are scanned,
+// k_sync_emit (one thread per chunk) moves the slots to their places in the
+// ordered lists; a chunk with more matches than slots is searched again by its
+// thread (never seen outside of tests with synthetic pattern floods).
+#define SYNC_SLOTS 6
+
 __global__ void __launch_bounds__(SYNC_THREADS)
-k_sync_scan(const uint8_t *__restrict__ es, uint64_t es_total,
-            uint32_t *__restrict__ cnt_raw, uint32_t *__restrict__ cnt_valid,
-            const uint32_t *__restrict__ base_raw, const uint32_t *__restrict__ base_valid,
-            uint64_t *__restrict__ raw, uint64_t *__restrict__ valid)
+k_sync_find(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t *__restrict__ cnt_raw,
+            uint32_t *__restrict__ cnt_valid, uint16_t *__restrict__ slots, uint32_t nslots)
 {
-    const uint64_t p0 = (uint64_t)blockIdx.x * SYNC_CHUNK + (uint64_t)threadIdx.x * SYNC_PER_THREAD;
-    // bytes p0+4 .. p0+4+23 as six big-endian words (the ES buffer is padded)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t p0 = (uint64_t)blockIdx.x * SYNC_CHUNK + (uint64_t)threadIdx.x * 16;
+    // bytes p0 .. p0+15 (the ES buffer is padded well past es_total)
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(es + p0));
     uint32_t w[6];
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(es + p0 + 4);
-#pragma unroll
-    for (int k = 0; k < 6; k++) w[k] = (p0 + 4 + 4 * k < es_total + 8) ? ld_be32_aligned(src + k) : 0;
+    w[0] = __byte_perm(q.x, 0, 0x0123); w[1] = __byte_perm(q.y, 0, 0x0123);
+    w[2] = __byte_perm(q.z, 0, 0x0123); w[3] = __byte_perm(q.w, 0, 0x0123);
+    w[4] = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
+    w[5] = __shfl_down_sync(0xFFFFFFFFu, w[1], 1);
+    if (lane == 31) {
+        const uint2 n = __ldg(reinterpret_cast<const uint2 *>(es + p0 + 16));
+        w[4] = __byte_perm(n.x, 0, 0x0123); w[5] = __byte_perm(n.y, 0, 0x0123);
+    }
     uint32_t m_raw = 0, m_valid = 0;
 #pragma unroll
-    for (int j = 0; j < SYNC_PER_THREAD; j++) {
-        const uint32_t v = __funnelshift_l(w[j / 4 + 1], w[j / 4], (j & 3) * 8);
+    for (int j = 0; j < 16; j++) {
+        // bytes p0+j+4 .. p0+j+7
+        const uint32_t v = __funnelshift_l(w[j / 4 + 2], w[j / 4 + 1], (j & 3) * 8);
         if (v == 0xF8726FBBu && p0 + j + 8 <= es_total) {
             m_raw |= 1u << j;
             if (sync_starts_segment(es, p0 + j, es_total)) m_valid |= 1u << j;
@@ -74,35 +85,59 @@ k_sync_scan(const uint8_t *__restrict__ es, uint64_t es_total,
     const uint64_t mine = (uint64_t)__popc(m_raw) | ((uint64_t)__popc(m_valid) << 32);
     uint64_t total;
     const uint64_t ex = block_excl_scan<SYNC_THREADS>(mine, &total);
-    if (!FILL) {
-        if (threadIdx.x == 0) {
-            cnt_raw[blockIdx.x] = (uint32_t)total;
-            cnt_valid[blockIdx.x] = (uint32_t)(total >> 32);
-        }
-    } else {
-        uint32_t ir = base_raw[blockIdx.x] + (uint32_t)ex;
-        uint32_t iv = base_valid[blockIdx.x] + (uint32_t)(ex >> 32);
-        while (m_raw) {
-            const int j = __ffs(m_raw) - 1;
-            m_raw &= m_raw - 1;
-            raw[ir++] = p0 + j;
-            if ((m_valid >> j) & 1) valid[iv++] = p0 + j;
-        }
+    if (threadIdx.x == 0) {
+        cnt_raw[blockIdx.x] = (uint32_t)total;
+        cnt_valid[blockIdx.x] = (uint32_t)(total >> 32);
+    }
+    uint32_t i = (uint32_t)ex;
+    while (m_raw) {
+        const int j = __ffs(m_raw) - 1;
+        m_raw &= m_raw - 1;
+        if (i < nslots) slots[(uint64_t)blockIdx.x * SYNC_SLOTS + i] = (uint16_t)((threadIdx.x * 16 + j) | (((m_valid >> j) & 1) << 15));
+        i++;
     }
 }
 
-int launch_sync_count(const uint8_t *es, uint64_t es_total, uint32_t *cnt_raw, uint32_t *cnt_valid, cudaStream_t s)
+__global__ void k_sync_emit(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t chunks,
+                            const uint32_t *__restrict__ cnt_raw, const uint16_t *__restrict__ slots, uint32_t nslots,
+                            const uint32_t *__restrict__ base_raw, const uint32_t *__restrict__ base_valid,
+                            uint64_t *__restrict__ raw, uint64_t *__restrict__ valid)
+{
+    const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= chunks) return;
+    const uint32_t n = cnt_raw[ch];
+    if (!n) return;
+    uint32_t ir = base_raw[ch], iv = base_valid[ch];
+    const uint64_t p0 = (uint64_t)ch * SYNC_CHUNK;
+    if (n <= nslots) {
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t e = slots[(uint64_t)ch * SYNC_SLOTS + i];
+            raw[ir++] = p0 + (e & 0x7FFF);
+            if (e >> 15) valid[iv++] = p0 + (e & 0x7FFF);
+        }
+        return;
+    }
+    for (uint32_t j = 0; j < SYNC_CHUNK; j++) {
+        const uint64_t p = p0 + j;
+        if (p + 8 > es_total) break;
+        if (ld_be32(es + p + 4) != 0xF8726FBBu) continue;
+        raw[ir++] = p;
+        if (sync_starts_segment(es, p, es_total)) valid[iv++] = p;
+    }
+}
+
+int launch_sync_count(const uint8_t *es, uint64_t es_total, uint32_t *cnt_raw, uint32_t *cnt_valid, uint16_t *slots, uint32_t nslots, cudaStream_t s)
 {
     const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
-    LAUNCH(k_sync_scan<false>, chunks, SYNC_THREADS, 0, s, es, es_total, cnt_raw, cnt_valid, nullptr, nullptr, nullptr, nullptr);
+    LAUNCH(k_sync_find, chunks, SYNC_THREADS, 0, s, es, es_total, cnt_raw, cnt_valid, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int launch_sync_fill(const uint8_t *es, uint64_t es_total, const uint32_t *base_raw, const uint32_t *base_valid,
-                     uint64_t *raw, uint64_t *valid, cudaStream_t s)
+int launch_sync_fill(const uint8_t *es, uint64_t es_total, const uint32_t *cnt_raw, const uint16_t *slots, uint32_t nslots,
+                     const uint32_t *base_raw, const uint32_t *base_valid, uint64_t *raw, uint64_t *valid, cudaStream_t s)
 {
     const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
-    LAUNCH(k_sync_scan<true>, chunks, SYNC_THREADS, 0, s, es, es_total, nullptr, nullptr, base_raw, base_valid, raw, valid);
+    LAUNCH(k_sync_emit, div_up_u32(chunks, 128), 128, 0, s, es, es_total, chunks, cnt_raw, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS, base_raw, base_valid, raw, valid);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

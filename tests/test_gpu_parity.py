@@ -75,6 +75,25 @@ def test_whole_titleset_in_one_call(pkg, oracle, engine, disc_cache, name):
         assert oracle.fnv1a(engine.fetch(r)) == g["fnv"], (name, g["title"], g["track"])
 
 
+@pytest.mark.parametrize("name", ["mlp_wild_0", "mlp_short_segments", "c5_mixed"])
+def test_sync_search_overflow_path(pkg, oracle, disc_cache, name, monkeypatch):
+    """With no slots per chunk every chunk that holds a sync pattern is searched again by one
+    thread (the path taken when a 2 KiB chunk holds more patterns than it has slots)."""
+    monkeypatch.setenv("DVDAGPU_SYNC_SLOTS", "0")
+    directory, _ = disc_cache(name)
+    sectors = oracle.read_aobs(directory)
+    golden = GOLDEN[name]["tracks"]
+    eng = pkg.Engine(0)
+    try:
+        res = eng.decode_host(sectors, [(g["first"], g["last"], g["pts"]) for g in golden])
+        for r, g in zip(res, golden):
+            assert r.status == 0
+            assert r.frames == g["frames"], (name, g["title"], g["track"])
+            assert oracle.fnv1a(eng.fetch(r)) == g["fnv"], (name, g["title"], g["track"])
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("name", ["c5_mixed", "mlp_wild_1", "pcm_rates_ragged", "mlp_zero_yield"])
 def test_public_api(pkg, oracle, disc_cache, name):
     """dvda_open .. dvda_open_track_reader .. dvda_read, as a program written for the
