@@ -382,12 +382,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     ENSURE(B_SYNC_SLOTS, (size_t)chunks * SYNC_SLOT_BYTES);
     uint16_t *sync_slots = c->buf[B_SYNC_SLOTS].as<uint16_t>();
     // (test hook: DVDAGPU_SYNC_SLOTS=0 sends every chunk with a match through the re-search path)
-    const uint32_t nslots = getenv("DVDAGPU_SYNC_SLOTS") ? (uint32_t)atoi(getenv("DVDAGPU_SYNC_SLOTS")) : 6u;
+    const uint32_t nslots = getenv("DVDAGPU_SYNC_SLOTS") ? (uint32_t)atoi(getenv("DVDAGPU_SYNC_SLOTS")) : 2u;
     uint32_t *cnt_raw = c->buf[B_SYNC_CNT_RAW].as<uint32_t>(), *cnt_valid = c->buf[B_SYNC_CNT_VALID].as<uint32_t>();
     uint32_t *base_raw = c->buf[B_SYNC_BASE_RAW].as<uint32_t>(), *base_valid = c->buf[B_SYNC_BASE_VALID].as<uint32_t>();
     uint32_t n_raw = 0, n_valid = 0;
     if (es_total) {
-        TRY(launch_sync_count(es, es_total, cnt_raw, cnt_valid, sync_slots, nslots, s));
+        TIMED(DVDAGPU_K_SYNC_SCAN, launch_sync_count(es, es_total, cnt_raw, cnt_valid, sync_slots, nslots, s));
         TRY(scan_u32_to_u32(cnt_raw, base_raw, chunks, tmp, tmp_bytes, s));
         TRY(scan_u32_to_u32(cnt_valid, base_valid, chunks, tmp, tmp_bytes, s));
         TRY(read_back(c, base_raw + chunks, &n_raw));

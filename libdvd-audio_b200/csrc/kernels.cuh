@@ -62,8 +62,8 @@ int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t np, const
                       const TrackDev *tracks, const uint32_t *trk_pk_lo, uint32_t n_tracks, int32_t *pcm, cudaStream_t s);
 
 // mlp_index.cu
-#define SYNC_CHUNK 2048u          // ES bytes per block of the sync search
-#define SYNC_SLOT_BYTES 12u       // per chunk: 6 slots of 16 bits
+#define SYNC_CHUNK 512u           // ES bytes per warp step of the sync search
+#define SYNC_SLOT_BYTES 4u        // per chunk: 2 slots of 16 bits
 int launch_sync_count(const uint8_t *es, uint64_t es_total, uint32_t *cnt_raw, uint32_t *cnt_valid, uint16_t *slots, uint32_t nslots, cudaStream_t s);
 int launch_sync_fill(const uint8_t *es, uint64_t es_total, const uint32_t *cnt_raw, const uint16_t *slots, uint32_t nslots,
                      const uint32_t *base_raw, const uint32_t *base_valid, uint64_t *raw, uint64_t *valid, cudaStream_t s);

@@ -91,6 +91,12 @@ __global__ void __launch_bounds__(CHK_THREADS) k_checkdata(MlpTables m, const ui
         T[0][i] = t0; T[1][i] = t1; T[2][i] = t2; T[3][i] = c_crc8[t2];
     }
     __syncthreads();
+#define CHK_WORD(wv)                                                                                       \
+    {                                                                                                      \
+        const uint32_t w_ = (wv);                                                                          \
+        pw ^= w_;                                                                                          \
+        crc = T[3][(crc ^ w_) & 0xFF] ^ T[2][(w_ >> 8) & 0xFF] ^ T[1][(w_ >> 16) & 0xFF] ^ T[0][w_ >> 24]; \
+    }
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= m.nau) return;
     const uint32_t si = upper_bound_dev(seg_au_base, m.nseg, a) - 1;
@@ -113,14 +119,15 @@ __global__ void __launch_bounds__(CHK_THREADS) k_checkdata(MlpTables m, const ui
                 const uint32_t head = min(body, (uint32_t)((16 - ((uintptr_t)p & 15)) & 15));
                 for (; i < head; i++) { const uint32_t b = ld_u8(p + i); parity ^= b; crc = T[0][crc ^ b]; }
                 uint32_t pw = 0;
+                for (; i + 32 <= body; i += 32) {
+                    const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(p + i));
+                    const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(p + i + 16));
+                    CHK_WORD(v0.x) CHK_WORD(v0.y) CHK_WORD(v0.z) CHK_WORD(v0.w)
+                    CHK_WORD(v1.x) CHK_WORD(v1.y) CHK_WORD(v1.z) CHK_WORD(v1.w)
+                }
                 for (; i + 16 <= body; i += 16) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + i));
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        pw ^= w[j];
-                        crc = T[3][(crc ^ w[j]) & 0xFF] ^ T[2][(w[j] >> 8) & 0xFF] ^ T[1][(w[j] >> 16) & 0xFF] ^ T[0][w[j] >> 24];
-                    }
+                    const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(p + i));
+                    CHK_WORD(v0.x) CHK_WORD(v0.y) CHK_WORD(v0.z) CHK_WORD(v0.w)
                 }
                 parity ^= (pw ^ (pw >> 8) ^ (pw >> 16) ^ (pw >> 24)) & 0xFF;
                 for (; i < body; i++) { const uint32_t b = ld_u8(p + i); parity ^= b; crc = T[0][crc ^ b]; }
@@ -133,6 +140,7 @@ __global__ void __launch_bounds__(CHK_THREADS) k_checkdata(MlpTables m, const ui
         }
     }
     m.au_err[a] = (uint8_t)err;
+#undef CHK_WORD
 }
 
 int upload_crc_table(const uint8_t *t)
@@ -1122,17 +1130,22 @@ __device__ bool delta_filter(RD &b, ChanHead &C, ChanCoef &K, bool iir, uint32_t
     return true;
 }
 
-// decoding parameters of a block without restart header, as a delta (mlp.c:856-993)
-template <typename RD>
+// decoding parameters of one block as a delta (mlp.c:856-993).  RESTART: the block
+// follows a restart header, where everything not transmitted falls back to its
+// default — the delta then states every field.
+template <bool RESTART, typename RD>
 __device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D)
 {
     uint32_t present = 0;
-    if ((cx.flags & 1) && rd_get(b, 1)) return false;           // new presence flags: complete decoder
+    if (RESTART) {
+        if (rd_get(b, 1)) rd_skip(b, 8);                        // the presence flags themselves: in cx.flags already
+        present = AD_BLOCK | AD_MATRIX | AD_SHIFT | AD_Q;
+    } else if ((cx.flags & 1) && rd_get(b, 1)) return false;    // new presence flags: complete decoder
     if ((cx.flags & 0x80) && rd_get(b, 1)) {
         const uint32_t bs = rd_get(b, 9);
         if (bs < 8) return false;
         D.block_size = (uint16_t)bs; present |= AD_BLOCK;
-    }
+    } else if (RESTART) D.block_size = 8;
     if ((cx.flags & 0x40) && rd_get(b, 1)) {
         const uint32_t ml = rd_get(b, 4);
         if (ml > DVDA_MAX_MAT || cx.mmc + 3 > DVDA_MAX_CH) return false;
@@ -1148,21 +1161,27 @@ __device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D)
                 D.coeff[k][c] = v;
             }
         }
-    }
+    } else if (RESTART) D.matrix_len = 0;
     if ((cx.flags & 0x20) && rd_get(b, 1)) {
         present |= AD_SHIFT;
-        for (uint32_t c = 0; c <= cx.mmc; c++) D.out_shift[c] = (uint8_t)(rd_get_s(b, 4) & 31);
-    }
+        for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.out_shift[c] = c <= cx.mmc ? (uint8_t)(rd_get_s(b, 4) & 31) : 0;
+    } else if (RESTART) { for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.out_shift[c] = 0; }
     if ((cx.flags & 0x10) && rd_get(b, 1)) {
         present |= AD_Q;
-        for (uint32_t c = 0; c <= cx.max_ch; c++) D.q[c] = (uint8_t)rd_get(b, 4);
-    }
+        for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.q[c] = c <= cx.max_ch ? (uint8_t)rd_get(b, 4) : 0;
+    } else if (RESTART) { for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.q[c] = 0; }
     for (uint32_t c = cx.min_ch; c <= cx.max_ch; c++) {
         ChanHead &C = D.ch[c - cx.min_ch];
         ChanCoef &K = D.cf[c - cx.min_ch];
         uint32_t p = 0;
+        if (RESTART) {
+            // defaults (mlp.c:904-989); the FIR history alone survives a restart
+            C.fir_order = C.fir_shift = C.iir_order = C.iir_shift = 0;
+            C.huff_offset = 0; C.codebook = 0; C.huff_lsbs = 24;
+            p = CD_PRESENT | CD_FIR | CD_IIR | CD_OFFSET;
+        }
         if (rd_get(b, 1)) {
-            p = CD_PRESENT;
+            p |= CD_PRESENT;
             if ((cx.flags & 0x08) && rd_get(b, 1) && !delta_filter(b, C, K, false, p)) return false;
             if ((cx.flags & 0x04) && rd_get(b, 1) && !delta_filter(b, C, K, true, p)) return false;
             if ((cx.flags & 0x02) && rd_get(b, 1)) { C.huff_offset = rd_get_s(b, 15); p |= CD_OFFSET; }
@@ -1176,7 +1195,24 @@ __device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D)
     return true;
 }
 
-// A0: context of a segment's substream, and its first access unit as an all-stating delta
+// restart header (mlp.c:809-854) into the segment context; the reader is left behind it
+template <typename RD>
+__device__ bool restart_ctx(RD &b, SegCtx &cx)
+{
+    const uint32_t sync = rd_get(b, 13), noise_type = rd_get(b, 1);
+    rd_skip(b, 16);
+    cx.min_ch = (uint8_t)rd_get(b, 4); cx.max_ch = (uint8_t)rd_get(b, 4); cx.mmc = (uint8_t)rd_get(b, 4);
+    cx.noise_shift = (uint8_t)rd_get(b, 4);
+    cx.seed = rd_get(b, 23);
+    rd_skip(b, 19 + 1 + 8 + 16);
+    if (sync != 0x18F5 || noise_type != 0) return false;
+    if (cx.max_ch < cx.min_ch || cx.mmc < cx.max_ch || cx.mmc >= DVDA_MAX_CH) return false;
+    for (uint32_t c = 0; c <= cx.mmc; c++) if (rd_get(b, 6) > cx.mmc) return false;
+    rd_skip(b, 8);
+    return true;
+}
+
+// A0: context of a segment's substream (no parameters yet: those are pass A1's)
 __device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJob &job)
 {
     const SegDev &S = m.segs[job.seg];
@@ -1184,50 +1220,22 @@ __device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJ
     SegCtx cx;
     memset(&cx, 0, sizeof cx);
     if (S.n_au) {
-        const uint32_t A = S.au_base;
-        AuSnap &sn = m.au_snap[(uint64_t)job.k * m.nau + A];
         GRd b;
         uint32_t end_bits;
         uint64_t origin;
-        SubState s;
-        memset(&s, 0, sizeof s);
-        s.flags = 0xFF;
-        bool changed;
-        if (au_seat(m, T, A, job.k, b, end_bits, origin) && block_header(b, s, changed) && rd_pos(b) <= end_bits &&
-            s.max_ch - s.min_ch < 4) {
-            cx.seed = s.seed; cx.noise_shift = s.noise_shift;
-            cx.min_ch = s.min_ch; cx.max_ch = s.max_ch; cx.mmc = s.mmc; cx.flags = s.flags; cx.ok = 1;
-            sn.bit0 = origin + rd_pos(b);
-            sn.bit_end = origin + end_bits;
-            sn.valid = 2;
-            AuDelta &D = m.au_delta[(uint64_t)job.k * m.nau + A];
-            D.block_size = s.block_size;
-            D.present = (uint8_t)(AD_BLOCK | AD_MATRIX | AD_SHIFT | AD_Q);
-            D.matrix_len = s.matrix_len;
-            for (uint32_t k = 0; k < DVDA_MAX_MAT; k++) {
-                D.mat_out[k] = s.mat_out[k]; D.mat_bypass[k] = s.mat_bypass[k];
-                for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.coeff[k][c] = s.coeff[k][c];
-            }
-            for (uint32_t c = 0; c < DVDA_MAX_CH; c++) { D.out_shift[c] = s.out_shift[c]; D.q[c] = s.q[c]; }
-            for (uint32_t c = s.min_ch; c <= s.max_ch; c++) {
-                const ChanState &C = s.ch[c];
-                ChanHead &H = D.ch[c - s.min_ch];
-                ChanCoef &K = D.cf[c - s.min_ch];
-                H.huff_offset = C.huff_offset;
-                H.fir_order = C.fir_order; H.fir_shift = C.fir_shift; H.iir_order = C.iir_order; H.iir_shift = C.iir_shift;
-                H.codebook = C.codebook; H.huff_lsbs = C.huff_lsbs;
-                H.present = (uint8_t)(CD_PRESENT | CD_FIR | CD_IIR | CD_OFFSET | (C.ilen ? CD_IIR_STATE : 0u));
-                for (uint32_t i = 0; i < 8; i++) {
-                    K.fir_c[i] = (int16_t)C.fir_c[i]; K.iir_c[i] = (int16_t)C.iir_c[i];
-                    K.ist[i] = i < C.ilen ? C.ist[(C.ihead - 1 - i) & 7] : 0;
-                }
-            }
+        if (au_seat(m, T, S.au_base, job.k, b, end_bits, origin) && rd_get(b, 1) && rd_get(b, 1) && restart_ctx(b, cx) &&
+            cx.max_ch - cx.min_ch < 4) {
+            // presence flags in force for the segment (all set unless the block says otherwise)
+            uint32_t f = 0xFF;
+            if (rd_get(b, 1)) { f = 0; for (int k = 0; k < 8; k++) f |= rd_get(b, 1) << k; }
+            cx.flags = (uint8_t)f;
+            cx.ok = rd_pos(b) <= end_bits;
         }
     }
     m.seg_ctx[job.k * m.nseg + job.seg] = cx;
 }
 
-// A1: parameter block of access unit a > 0 as a delta
+// A1: parameter block of one access unit as a delta
 __device__ __forceinline__ void parse_au(const MlpTables &m, const DecodeJob &job, uint32_t a)
 {
     const SegDev &S = m.segs[job.seg];
@@ -1240,10 +1248,15 @@ __device__ __forceinline__ void parse_au(const MlpTables &m, const DecodeJob &jo
     uint32_t end_bits;
     uint64_t origin;
     if (cx.ok && au_seat(m, T, A, job.k, b, end_bits, origin)) {
-        state = 1;
-        if (rd_get(b, 1)) {
+        AuDelta &D = m.au_delta[(uint64_t)job.k * m.nau + A];
+        if (a == 0) {
+            // "parameters present", "restart header", the header itself (checked by pass A0)
+            rd_skip(b, 2 + 113 + 6 * (cx.mmc + 1u) + 8);
+            state = parse_delta<true>(b, cx, D) ? 2 : 0;
+        } else {
+            state = 1;
             // a restart header here would start a new run of parameters: complete decoder
-            state = (!rd_get(b, 1) && parse_delta(b, cx, m.au_delta[(uint64_t)job.k * m.nau + A])) ? 2 : 0;
+            if (rd_get(b, 1)) state = (!rd_get(b, 1) && parse_delta<false>(b, cx, D)) ? 2 : 0;
         }
         if (rd_pos(b) > end_bits) state = 0;
         sn.bit0 = origin + rd_pos(b);
@@ -1277,8 +1290,13 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
     uint32_t seed = cx.seed, frames = 0, flags = 0, pset = 0xFFFFFFFFu;
     bool fallback = !cx.ok || (uint32_t)(cx.max_ch - cx.min_ch + 1) != NCH;
 
+    uint32_t seed_at = 0;                                 // frame the seed belongs to (advanced only when some matrix uses noise)
+    bool uses_noise = false;
     for (uint32_t a = 0; a < S.n_au && !fallback; a++) {
         const uint32_t A = S.au_base + a;
+        // two access units ahead: their records are on the way while this one is resolved
+        prefetch_l1(snaps + A + 2);
+        prefetch_l1(deltas + A + 2); prefetch_l1(reinterpret_cast<const uint8_t *>(deltas + A + 2) + 64);
         const uint32_t state = snaps[A].valid;
         if (!state) { fallback = true; break; }
         bool dirty = false;
@@ -1385,14 +1403,16 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
                     uses |= (M.coeff[k][cx.mmc + 1] != 0) | (M.coeff[k][cx.mmc + 2] != 0);
                 }
                 P.uses_noise = uses;
+                uses_noise = uses != 0;
                 for (int c = 0; c < DVDA_MAX_CH; c++) { P.q[c] = (q8 >> (4 * c)) & 15; P.out_shift[c] = (uint8_t)(shift8 >> (8 * c)); }
                 m.psets[A] = P;
                 // top bit: nothing to do for these frames but to copy them
                 pset = A | ((matrix_len == 0 && shift8 == 0) ? 0x80000000u : 0u);
             }
+            // the generator steps once per frame; nobody looks at the seed of an AU whose matrices ignore the noise
+            if (uses_noise) { seed = noise_advance(seed, au_frame0 - seed_at); seed_at = au_frame0; }
             AuDev R = {au_frame0, nominal, seed, pset};
             m.au[A] = R;
-            seed = noise_advance(seed, nominal);
         }
     }
     if (fallback) flags |= SEG_FALLBACK;
@@ -1938,11 +1958,11 @@ __global__ void __launch_bounds__(128) k_mlp_resolve(MlpTables m, const DecWork 
     if (!fast_job(m, work, n_work, warp, lane, job)) return;
     resolve_segment<NCH>(m, job);
 }
-// pass A1: one warp per (group, substream, access unit index > 0), lane = segment
+// pass A1: one warp per (group, substream, access unit index), lane = segment
 __global__ void __launch_bounds__(128) k_mlp_au_parse(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
 {
     const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const uint32_t a = blockIdx.y + 1;
+    const uint32_t a = blockIdx.y;
     if (warp >= n_warps) return;
     DecodeJob job;
     if (!fast_job(m, work, n_work, warp, lane, job)) return;
@@ -2012,7 +2032,7 @@ static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t
     const uint32_t blocks = div_up_u32(n_warps, DEC_WARPS);
     const uint32_t small = div_up_u32(n_warps, 4);
     if (pass == 0) LAUNCH(k_mlp_segctx, small, 128, 0, s, m, work, n_work, n_warps);
-    else if (pass == 1) { if (m.max_au > 1) LAUNCH(k_mlp_au_parse, dim3(small, m.max_au - 1), 128, 0, s, m, work, n_work, n_warps); }
+    else if (pass == 1) { if (m.max_au) LAUNCH(k_mlp_au_parse, dim3(small, m.max_au), 128, 0, s, m, work, n_work, n_warps); }
     else if (pass == 2) LAUNCH(k_mlp_resolve<NCH>, small, 128, 0, s, m, work, n_work, n_warps);
     else if (pass == 3) LAUNCH(k_mlp_entropy<NCH>, dim3(blocks, m.max_au ? m.max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
     else LAUNCH(k_mlp_filter<NCH>, div_up_u32((uint64_t)n_warps * NCH, 4), 128, 0, s, m, work, n_work, n_warps);

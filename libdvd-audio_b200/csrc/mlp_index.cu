@@ -17,14 +17,13 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
-#define SYNC_THREADS (SYNC_CHUNK / 16)   // 16 positions per thread
 
 // A sync position starts a *segment* only if the access unit there is a
 // well-formed major sync (1 or 2 substreams) and every substream opens with a
 // restart header: params-present bit, restart bit, 13-bit sync 0x18F5
 // (reference mlp.c:749-759, 822-835).  Anything else stays inside the previous
 // segment (or is a chance match in the payload).
-__device__ bool sync_starts_segment(const uint8_t *es, uint64_t p, uint64_t es_total)
+__device__ __noinline__ bool sync_starts_segment(const uint8_t *es, uint64_t p, uint64_t es_total)
 {
     if (p + 4 + 28 + 2 > es_total) return false;
     const uint32_t total = ((ld_u8(es + p) & 15u) << 8 | ld_u8(es + p + 1)) * 2;
@@ -46,55 +45,79 @@ __device__ bool sync_starts_segment(const uint8_t *es, uint64_t p, uint64_t es_t
     return true;
 }
 
-// The elementary stream is read once.  k_sync_find: one block per 2 KiB chunk, one
-// 16-byte load per thread (the following 7 bytes come from the next lane); the few
-// matches of a chunk go, in stream order, into the chunk's slots (offset in the
-// chunk | valid << 15) next to its counts.  After the counts are scanned,
-// k_sync_emit (one thread per chunk) moves the slots to their places in the
-// ordered lists; a chunk with more matches than slots is searched again by its
+// The elementary stream is read once.  k_sync_find: one warp per 512-byte chunk, one
+// 16-byte load per lane (the following 7 bytes come from the next lane), no block
+// barrier; the few matches of a chunk go, in stream order, into the chunk's slots
+// (offset in the chunk | valid << 15) next to its counts.  After the counts are
+// scanned, k_sync_emit (one thread per chunk) moves the slots to their places in
+// the ordered lists; a chunk with more matches than slots is searched again by its
 // thread (never seen outside of tests with synthetic pattern floods).
-#define SYNC_SLOTS 6
+#define SYNC_SLOTS 2
+#define SYNC_WARPS 8                  // warps per block
+#define SYNC_CHUNKS_PER_WARP 4
 
-__global__ void __launch_bounds__(SYNC_THREADS)
-k_sync_find(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t *__restrict__ cnt_raw,
+__global__ void __launch_bounds__(SYNC_WARPS * 32)
+k_sync_find(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t chunks, uint32_t *__restrict__ cnt_raw,
             uint32_t *__restrict__ cnt_valid, uint16_t *__restrict__ slots, uint32_t nslots)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t p0 = (uint64_t)blockIdx.x * SYNC_CHUNK + (uint64_t)threadIdx.x * 16;
-    // bytes p0 .. p0+15 (the ES buffer is padded well past es_total)
-    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(es + p0));
-    uint32_t w[6];
-    w[0] = __byte_perm(q.x, 0, 0x0123); w[1] = __byte_perm(q.y, 0, 0x0123);
-    w[2] = __byte_perm(q.z, 0, 0x0123); w[3] = __byte_perm(q.w, 0, 0x0123);
-    w[4] = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
-    w[5] = __shfl_down_sync(0xFFFFFFFFu, w[1], 1);
-    if (lane == 31) {
-        const uint2 n = __ldg(reinterpret_cast<const uint2 *>(es + p0 + 16));
-        w[4] = __byte_perm(n.x, 0, 0x0123); w[5] = __byte_perm(n.y, 0, 0x0123);
-    }
-    uint32_t m_raw = 0, m_valid = 0;
+    const uint32_t chunk0 = (blockIdx.x * SYNC_WARPS + (threadIdx.x >> 5)) * SYNC_CHUNKS_PER_WARP;
+    // all loads of the warp's chunks first (the ES buffer is padded well past es_total)
+    uint4 q[SYNC_CHUNKS_PER_WARP];
+    uint2 nx[SYNC_CHUNKS_PER_WARP];
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        // bytes p0+j+4 .. p0+j+7
-        const uint32_t v = __funnelshift_l(w[j / 4 + 2], w[j / 4 + 1], (j & 3) * 8);
-        if (v == 0xF8726FBBu && p0 + j + 8 <= es_total) {
-            m_raw |= 1u << j;
-            if (sync_starts_segment(es, p0 + j, es_total)) m_valid |= 1u << j;
+    for (int c = 0; c < SYNC_CHUNKS_PER_WARP; c++) {
+        const uint64_t p0 = (uint64_t)(chunk0 + c) * SYNC_CHUNK + lane * 16;
+        const bool in = chunk0 + c < chunks;
+        q[c] = in ? __ldg(reinterpret_cast<const uint4 *>(es + p0)) : make_uint4(0, 0, 0, 0);
+        nx[c] = (in && lane == 31) ? __ldg(reinterpret_cast<const uint2 *>(es + p0 + 16)) : make_uint2(0, 0);
+    }
+#pragma unroll
+    for (int c = 0; c < SYNC_CHUNKS_PER_WARP; c++) {
+        const uint32_t chunk = chunk0 + c;
+        if (chunk >= chunks) break;                                   // warp-uniform
+        uint32_t w[6];
+        w[0] = __byte_perm(q[c].x, 0, 0x0123); w[1] = __byte_perm(q[c].y, 0, 0x0123);
+        w[2] = __byte_perm(q[c].z, 0, 0x0123); w[3] = __byte_perm(q[c].w, 0, 0x0123);
+        w[4] = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
+        w[5] = __shfl_down_sync(0xFFFFFFFFu, w[1], 1);
+        if (lane == 31) { w[4] = __byte_perm(nx[c].x, 0, 0x0123); w[5] = __byte_perm(nx[c].y, 0, 0x0123); }
+        // the pattern at bytes p0+j+4 .. p0+j+7 for some j in 0..15?  (one shift and one compare each)
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 16; j++) any |= __funnelshift_l(w[j / 4 + 2], w[j / 4 + 1], (j & 3) * 8) == 0xF8726FBBu;
+        if (!__any_sync(0xFFFFFFFFu, any)) {
+            if (lane == 0) { cnt_raw[chunk] = 0; cnt_valid[chunk] = 0; }
+            continue;
         }
-    }
-    const uint64_t mine = (uint64_t)__popc(m_raw) | ((uint64_t)__popc(m_valid) << 32);
-    uint64_t total;
-    const uint64_t ex = block_excl_scan<SYNC_THREADS>(mine, &total);
-    if (threadIdx.x == 0) {
-        cnt_raw[blockIdx.x] = (uint32_t)total;
-        cnt_valid[blockIdx.x] = (uint32_t)(total >> 32);
-    }
-    uint32_t i = (uint32_t)ex;
-    while (m_raw) {
-        const int j = __ffs(m_raw) - 1;
-        m_raw &= m_raw - 1;
-        if (i < nslots) slots[(uint64_t)blockIdx.x * SYNC_SLOTS + i] = (uint16_t)((threadIdx.x * 16 + j) | (((m_valid >> j) & 1) << 15));
-        i++;
+        // rare: which positions exactly, and do they start segments
+        const uint64_t p0 = (uint64_t)chunk * SYNC_CHUNK + lane * 16;
+        uint32_t m_raw = 0, m_valid = 0;
+        if (any) {
+            for (int j = 0; j < 16; j++) {
+                const uint32_t v = __funnelshift_l(w[j / 4 + 2], w[j / 4 + 1], (j & 3) * 8);
+                if (v == 0xF8726FBBu && p0 + j + 8 <= es_total) {
+                    m_raw |= 1u << j;
+                    if (sync_starts_segment(es, p0 + j, es_total)) m_valid |= 1u << j;
+                }
+            }
+        }
+        const uint32_t mine = (uint32_t)__popc(m_raw) | ((uint32_t)__popc(m_valid) << 16);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (uint32_t)d) incl += o;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (lane == 0) { cnt_raw[chunk] = total & 0xFFFF; cnt_valid[chunk] = total >> 16; }
+        uint32_t i = (incl - mine) & 0xFFFF;
+        while (m_raw) {
+            const int j = __ffs(m_raw) - 1;
+            m_raw &= m_raw - 1;
+            if (i < nslots) slots[(uint64_t)chunk * SYNC_SLOTS + i] = (uint16_t)((lane * 16 + j) | (((m_valid >> j) & 1) << 15));
+            i++;
+        }
     }
 }
 
@@ -129,7 +152,7 @@ __global__ void k_sync_emit(const uint8_t *__restrict__ es, uint64_t es_total, u
 int launch_sync_count(const uint8_t *es, uint64_t es_total, uint32_t *cnt_raw, uint32_t *cnt_valid, uint16_t *slots, uint32_t nslots, cudaStream_t s)
 {
     const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
-    LAUNCH(k_sync_find, chunks, SYNC_THREADS, 0, s, es, es_total, cnt_raw, cnt_valid, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS);
+    LAUNCH(k_sync_find, div_up_u32(chunks, SYNC_WARPS * SYNC_CHUNKS_PER_WARP), SYNC_WARPS * 32, 0, s, es, es_total, chunks, cnt_raw, cnt_valid, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
