@@ -80,6 +80,8 @@ struct dvdagpu_ctx {
     cudaStream_t own_stream;
     cudaStream_t stream;
     cudaStream_t h2d_stream, d2h_stream;      // copy engines of the pipelined path
+    cudaStream_t aux_stream;                  // check data runs beside the header passes
+    cudaEvent_t aux_ev[2];
     cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
     int pcm_slot;                             // which PCM buffer the next decode writes
     uint8_t *hmap, *dmap;                     // mapped pinned staging area (host / device alias)
@@ -173,6 +175,8 @@ extern "C" dvdagpu_ctx *dvdagpu_create(int device)
     }
     cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+    for (auto &e : c->aux_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : c->pev) { cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming); }
     for (auto &e : c->ev) cudaEventCreate(&e);
     for (auto &k : c->kev) { cudaEventCreate(&k[0]); cudaEventCreate(&k[1]); }
@@ -195,6 +199,8 @@ extern "C" void dvdagpu_destroy(dvdagpu_ctx *c)
     if (c->hmap) cudaFreeHost(c->hmap);
     cudaStreamDestroy(c->h2d_stream);
     cudaStreamDestroy(c->d2h_stream);
+    cudaStreamDestroy(c->aux_stream);
+    for (auto &e : c->aux_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -487,7 +493,14 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
 
         // ---------------- decode
-        TIMED(DVDAGPU_K_CHECKDATA, launch_checkdata(m, seg_au_base, s));
+        // parity / CRC-8 on a second stream, beside the group set-up and the first header passes
+        CUDA_TRY(cudaEventRecord(c->aux_ev[0], s));
+        CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->aux_ev[0], 0));
+        CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][0], c->aux_stream));
+        TRY(launch_checkdata(m, seg_au_base, c->aux_stream));
+        CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][1], c->aux_stream));
+        c->kev_used[DVDAGPU_K_CHECKDATA] = true;
+        CUDA_TRY(cudaEventRecord(c->aux_ev[1], c->aux_stream));
         ENSURE(B_GROUPS, (size_t)ngroups * sizeof(GroupDev));
         ENSURE(B_GRP_CELLS, (size_t)ngroups * 4); ENSURE(B_CELL_BASE, (size_t)(ngroups + 1) * 8);
         ENSURE(B_GRP_CHUNKS, (size_t)ngroups * 4);
@@ -532,11 +545,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
                 // (start with every segment flagged: substreams with more than 4 channels
                 // are not visited by the fast path at all)
                 CUDA_TRY(cudaMemsetAsync(m.ss_flags, SEG_FALLBACK, (size_t)nseg * 2 * 4, s));
-                TRY(launch_mlp_fast(m, d_work, n_work, n_warps, c->kev, c->kev_used, s));
+                TRY(launch_mlp_fast(m, d_work, n_work, n_warps, c->kev, c->kev_used, c->aux_ev[1], s));
                 CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
                 CUDA_TRY(cudaMemcpyAsync(m.ss_flags_fast, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
                 m.fast = 1;
             }
+            CUDA_TRY(cudaStreamWaitEvent(s, c->aux_ev[1], 0));
             // ... and decoded by the complete single-pass decoder (everything, without the fast path)
             TIMED(DVDAGPU_K_MLP_DECODE, launch_mlp_decode(m, d_work, n_work, n_warps, s));
             CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));

@@ -38,18 +38,20 @@ struct AuLayout {
     bool has_sync, params_differ, ok;
 };
 
-__device__ AuLayout au_layout(const uint8_t *es, uint64_t pos, const TrackDev &T)
+// BYTES: byte source, b(i) = byte i of the access unit
+template <typename BYTES>
+__device__ __forceinline__ AuLayout au_layout_from(const BYTES &b, const TrackDev &T)
 {
     AuLayout L;
     L.ok = false; L.has_sync = false; L.params_differ = false;
-    L.total = (((ld_u8(es + pos) & 15u) << 8) | ld_u8(es + pos + 1)) * 2;
+    L.total = (((b(0) & 15u) << 8) | b(1)) * 2;
     uint32_t q = 4;
     // major sync: needs all 28 bytes inside the AU (mlp.c:614-654)
-    if (L.total >= 32 && ld_be32(es + pos + 4) == 0xF8726FBBu) {
-        const uint32_t ns = ld_u8(es + pos + 20) >> 4;
+    if (L.total >= 32 && ((b(4) << 24) | (b(5) << 16) | (b(6) << 8) | b(7)) == 0xF8726FBBu) {
+        const uint32_t ns = b(20) >> 4;
         if (ns == 1 || ns == 2) {
             L.has_sync = true;
-            const uint32_t b8 = ld_u8(es + pos + 8), b9 = ld_u8(es + pos + 9), asg = ld_u8(es + pos + 11) & 31;
+            const uint32_t b8 = b(8), b9 = b(9), asg = b(11) & 31;
             L.params_differ = (b8 >> 4) != T.g0_bps || (b8 & 15) != T.g1_bps || (b9 >> 4) != T.g0_rate ||
                               (b9 & 15) != T.g1_rate || asg != T.assignment;
             q = 32;
@@ -58,8 +60,8 @@ __device__ AuLayout au_layout(const uint8_t *es, uint64_t pos, const TrackDev &T
     L.end[0] = L.end[1] = 0; L.chk0 = 0;
     for (uint32_t k = 0; k < T.nss; k++) {
         if (q + 2 > L.total) return L;
-        const uint32_t b0 = ld_u8(es + pos + q);
-        L.end[k] = (((b0 & 15u) << 8) | ld_u8(es + pos + q + 1)) * 2;
+        const uint32_t b0 = b(q);
+        L.end[k] = (((b0 & 15u) << 8) | b(q + 1)) * 2;
         if (k == 0) L.chk0 = (b0 >> 5) & 1;
         q += 2 + ((b0 >> 7) ? 2 : 0);
     }
@@ -72,6 +74,12 @@ __device__ AuLayout au_layout(const uint8_t *es, uint64_t pos, const TrackDev &T
     }
     L.ok = true;
     return L;
+}
+
+__device__ AuLayout au_layout(const uint8_t *es, uint64_t pos, const TrackDev &T)
+{
+    const uint8_t *p = es + pos;
+    return au_layout_from([p](uint32_t i) { return ld_u8(p + i); }, T);
 }
 
 // One thread per access unit: parity and CRC-8 of each substream
@@ -298,21 +306,53 @@ __device__ __forceinline__ void rd_top_up(Rd &r)
     r.ahead = rd_ring_word(r, r.next_w);
 }
 
-// ---- reader straight over global memory (header-only passes: a few dozen bytes per
-// access unit, served by L1/L2; no shared-memory ring to set up)
+// ---- reader for the header-only passes.  The 128 bytes behind a seat are fetched with
+// eight independent 16-byte loads into the thread's column of a shared-memory window
+// (one memory latency for a whole parameter block instead of one per 32-byte sector);
+// words beyond the window come straight from global memory.
+#define GRD_WIN_WORDS 32
+#define GRD_THREADS 128
 struct GRd {
     const uint8_t *es;
+    uint32_t *col;              // this thread's column of the window: word i at col[i * GRD_THREADS]
+    uint32_t win_w0;            // absolute word index of window word 0
     uint64_t win;
     int32_t avail;
     uint32_t next_w, base_w;
 };
-__device__ __forceinline__ void grd_seat(GRd &r, const uint8_t *es, uint64_t byte_pos)
+// fetch the window: the 16-byte aligned 128 bytes from byte_pos on
+__device__ __forceinline__ void grd_stage(GRd &r, const uint8_t *es, uint32_t *col, uint64_t byte_pos)
 {
-    r.es = es; r.next_w = r.base_w = (uint32_t)(byte_pos >> 2); r.win = 0; r.avail = 0;
+    r.es = es; r.col = col;
+    const uint64_t base = byte_pos & ~15ull;
+    r.win_w0 = (uint32_t)(base >> 2);
+    const uint4 *src = reinterpret_cast<const uint4 *>(es + base);
+    uint4 v[GRD_WIN_WORDS / 4];
+#pragma unroll
+    for (int i = 0; i < GRD_WIN_WORDS / 4; i++) v[i] = __ldg(src + i);
+#pragma unroll
+    for (int i = 0; i < GRD_WIN_WORDS / 4; i++) {
+        col[(4 * i + 0) * GRD_THREADS] = v[i].x; col[(4 * i + 1) * GRD_THREADS] = v[i].y;
+        col[(4 * i + 2) * GRD_THREADS] = v[i].z; col[(4 * i + 3) * GRD_THREADS] = v[i].w;
+    }
+}
+// word w (absolute index), as stored (little endian)
+__device__ __forceinline__ uint32_t grd_word(const GRd &r, uint32_t w)
+{
+    const uint32_t i = w - r.win_w0;
+    return i < GRD_WIN_WORDS ? r.col[i * GRD_THREADS] : __ldg(reinterpret_cast<const uint32_t *>(r.es) + w);
+}
+__device__ __forceinline__ uint32_t grd_byte(const GRd &r, uint64_t byte_pos)
+{
+    return (grd_word(r, (uint32_t)(byte_pos >> 2)) >> (8 * (byte_pos & 3))) & 0xFF;
+}
+__device__ __forceinline__ void grd_seat(GRd &r, uint64_t byte_pos)
+{
+    r.next_w = r.base_w = (uint32_t)(byte_pos >> 2); r.win = 0; r.avail = 0;
 }
 __device__ __forceinline__ void rd_pull(GRd &r)
 {
-    const uint32_t word = __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(r.es) + r.next_w), 0, 0x0123);
+    const uint32_t word = __byte_perm(grd_word(r, r.next_w), 0, 0x0123);
     r.win |= (uint64_t)word << (32 - r.avail);
     r.avail += 32;
     r.next_w++;
@@ -1080,22 +1120,22 @@ static_assert(offsetof(AuDelta, cf) == 80 && sizeof(AuDelta) % 16 == 0, "AuDelta
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// seat a global-memory reader on substream k of access unit A; false = not for the fast path
-__device__ __forceinline__ bool au_seat(const MlpTables &m, const TrackDev &T, uint32_t A, uint32_t k, GRd &b,
+// seat a reader on substream k of access unit A; false = not for the fast path
+__device__ __forceinline__ bool au_seat(const MlpTables &m, const TrackDev &T, uint32_t A, uint32_t k, GRd &b, uint32_t *col,
                                         uint32_t &end_bits, uint64_t &origin)
 {
     const uint64_t au_pos = m.au_pos[A];
-    // the header and a typical parameter block, in flight together
-    const uint8_t *line = m.es + (au_pos & ~31ull);
-    prefetch_l1(line); prefetch_l1(line + 32); prefetch_l1(line + 64); prefetch_l1(line + 96);
-    const AuLayout L = au_layout(m.es, au_pos, T);
-    // damage, dropped AUs and the end-of-track rules are the complete decoder's business
-    if (!L.ok || au_pos + L.total > T.es_cut || m.au_err[A]) return false;
+    // the header and a typical parameter block in one go
+    grd_stage(b, m.es, col, au_pos);
+    const AuLayout L = au_layout_from([&b, au_pos](uint32_t i) { return grd_byte(b, au_pos + i); }, T);
+    // damage and the end-of-track rules are the complete decoder's business (check data runs
+    // beside this pass: the resolve pass looks at its verdicts)
+    if (!L.ok || au_pos + L.total > T.es_cut) return false;
     const uint32_t start = k ? L.end[0] : 0;
     const uint32_t len = L.end[k] - start - (L.chk0 ? 2 : 0);
     const uint64_t data = au_pos + L.data0 + start;
-    if (k) { const uint8_t *l2 = m.es + (data & ~31ull); prefetch_l1(l2); prefetch_l1(l2 + 32); prefetch_l1(l2 + 64); }
-    grd_seat(b, m.es, data);
+    if (k) grd_stage(b, m.es, col, data);                 // the second substream sits further back
+    grd_seat(b, data);
     rd_skip(b, (uint32_t)(data & 3) * 8);
     end_bits = (uint32_t)(data & 3) * 8 + len * 8;
     origin = (data & ~3ull) * 8;
@@ -1213,7 +1253,7 @@ __device__ bool restart_ctx(RD &b, SegCtx &cx)
 }
 
 // A0: context of a segment's substream (no parameters yet: those are pass A1's)
-__device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJob &job)
+__device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJob &job, uint32_t *col)
 {
     const SegDev &S = m.segs[job.seg];
     const TrackDev &T = m.tracks[S.track];
@@ -1223,7 +1263,7 @@ __device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJ
         GRd b;
         uint32_t end_bits;
         uint64_t origin;
-        if (au_seat(m, T, S.au_base, job.k, b, end_bits, origin) && rd_get(b, 1) && rd_get(b, 1) && restart_ctx(b, cx) &&
+        if (au_seat(m, T, S.au_base, job.k, b, col, end_bits, origin) && rd_get(b, 1) && rd_get(b, 1) && restart_ctx(b, cx) &&
             cx.max_ch - cx.min_ch < 4) {
             // presence flags in force for the segment (all set unless the block says otherwise)
             uint32_t f = 0xFF;
@@ -1236,7 +1276,7 @@ __device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJ
 }
 
 // A1: parameter block of one access unit as a delta
-__device__ __forceinline__ void parse_au(const MlpTables &m, const DecodeJob &job, uint32_t a)
+__device__ __forceinline__ void parse_au(const MlpTables &m, const DecodeJob &job, uint32_t a, uint32_t *col)
 {
     const SegDev &S = m.segs[job.seg];
     const TrackDev &T = m.tracks[S.track];
@@ -1247,7 +1287,7 @@ __device__ __forceinline__ void parse_au(const MlpTables &m, const DecodeJob &jo
     GRd b;
     uint32_t end_bits;
     uint64_t origin;
-    if (cx.ok && au_seat(m, T, A, job.k, b, end_bits, origin)) {
+    if (cx.ok && au_seat(m, T, A, job.k, b, col, end_bits, origin)) {
         AuDelta &D = m.au_delta[(uint64_t)job.k * m.nau + A];
         if (a == 0) {
             // "parameters present", "restart header", the header itself (checked by pass A0)
@@ -1292,21 +1332,32 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
 
     uint32_t seed_at = 0;                                 // frame the seed belongs to (advanced only when some matrix uses noise)
     bool uses_noise = false;
+    // The state byte and the head of the delta (five 16-byte loads) of the next access unit are
+    // requested before the current one is worked on: one memory latency per step is hidden.
+    struct Head { uint4 v[5]; };
+    Head nextv;
+    uint32_t next_state = 0;
+    if (S.n_au && !fallback) {
+        next_state = m.au_err[S.au_base] ? 0u : snaps[S.au_base].valid;
+        const uint4 *src = reinterpret_cast<const uint4 *>(deltas + S.au_base);
+#pragma unroll
+        for (int i = 0; i < 5; i++) nextv.v[i] = src[i];
+    }
     for (uint32_t a = 0; a < S.n_au && !fallback; a++) {
         const uint32_t A = S.au_base + a;
-        // two access units ahead: their records are on the way while this one is resolved
-        prefetch_l1(snaps + A + 2);
-        prefetch_l1(deltas + A + 2); prefetch_l1(reinterpret_cast<const uint8_t *>(deltas + A + 2) + 64);
-        const uint32_t state = snaps[A].valid;
+        const uint32_t state = next_state;
+        Head u = nextv;
+        if (a + 1 < S.n_au) {
+            // damaged or dropped access units (parity, CRC, changed stream parameters): complete decoder
+            next_state = m.au_err[A + 1] ? 0u : snaps[A + 1].valid;
+            const uint4 *src = reinterpret_cast<const uint4 *>(deltas + A + 1);
+#pragma unroll
+            for (int i = 0; i < 5; i++) nextv.v[i] = src[i];
+        }
         if (!state) { fallback = true; break; }
         bool dirty = false;
         uint32_t chg = 0;                                 // channels whose filter set-up changes with this AU
         if (state == 2) {
-            // the head of the delta: five 16-byte loads in flight together
-            union { uint4 v[5]; AuDelta d; } u;           // (only the head of d is populated)
-            const uint4 *src = reinterpret_cast<const uint4 *>(deltas + A);
-#pragma unroll
-            for (int i = 0; i < 5; i++) u.v[i] = src[i];
             const uint8_t *raw = reinterpret_cast<const uint8_t *>(u.v);
             const uint32_t present = raw[offsetof(AuDelta, present)];
             if (present & AD_BLOCK) block_size = *reinterpret_cast<const uint16_t *>(raw + offsetof(AuDelta, block_size));
@@ -1318,19 +1369,21 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
                 for (int k = 0; k < DVDA_MAX_MAT; k++)
                     want |= ((uint32_t)k < matrix_len && raw[offsetof(AuDelta, mat_bypass) + k]) ? 1u << k : 0u;
             }
+            const uint64_t shift8_was = shift8;
+            const uint32_t q8_was = q8;
             if (present & AD_SHIFT) {
-                dirty = true;
 #pragma unroll
                 for (int c = 0; c < DVDA_MAX_CH; c++)
                     if ((uint32_t)c <= cx.mmc) shift8 = (shift8 & ~(0xFFull << (8 * c))) | ((uint64_t)raw[offsetof(AuDelta, out_shift) + c] << (8 * c));
             }
             if (present & AD_Q) {
-                dirty = true;
 #pragma unroll
                 for (int c = 0; c < DVDA_MAX_CH; c++)
                     if ((uint32_t)c <= cx.max_ch) q8 = (q8 & ~(15u << (4 * c))) | ((uint32_t)raw[offsetof(AuDelta, q) + c] << (4 * c));
-                chg = (1u << NCH) - 1;
             }
+            // re-stated values that did not change need no new parameter set
+            if (shift8 != shift8_was || q8 != q8_was) dirty = true;
+            if (q8 != q8_was) chg = (1u << NCH) - 1;
 #pragma unroll
             for (int cc = 0; cc < NCH; cc++) {
                 const uint8_t *h = raw + offsetof(AuDelta, ch) + cc * sizeof(ChanHead);
@@ -1941,13 +1994,14 @@ __device__ __forceinline__ bool fast_job(const MlpTables &m, const DecWork *work
 }
 
 // pass A0 / A2: one warp per (group, substream), lane = segment
-__global__ void __launch_bounds__(128) k_mlp_segctx(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
+__global__ void __launch_bounds__(GRD_THREADS) k_mlp_segctx(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
 {
+    __shared__ uint32_t window[GRD_WIN_WORDS * GRD_THREADS];
     const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (warp >= n_warps) return;
     DecodeJob job;
     if (!fast_job(m, work, n_work, warp, lane, job)) return;
-    segctx_segment(m, job);
+    segctx_segment(m, job, window + threadIdx.x);
 }
 template <int NCH>
 __global__ void __launch_bounds__(128) k_mlp_resolve(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
@@ -1959,15 +2013,16 @@ __global__ void __launch_bounds__(128) k_mlp_resolve(MlpTables m, const DecWork 
     resolve_segment<NCH>(m, job);
 }
 // pass A1: one warp per (group, substream, access unit index), lane = segment
-__global__ void __launch_bounds__(128) k_mlp_au_parse(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
+__global__ void __launch_bounds__(GRD_THREADS) k_mlp_au_parse(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
 {
+    __shared__ uint32_t window[GRD_WIN_WORDS * GRD_THREADS];
     const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * 4 + (threadIdx.x >> 5);
     const uint32_t a = blockIdx.y;
     if (warp >= n_warps) return;
     DecodeJob job;
     if (!fast_job(m, work, n_work, warp, lane, job)) return;
     if (a >= m.segs[job.seg].n_au) return;
-    parse_au(m, job, a);
+    parse_au(m, job, a, window + threadIdx.x);
 }
 
 // pass B: one warp per (group, substream, access unit index), lane = segment
@@ -2040,11 +2095,12 @@ static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t
 }
 
 int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
-                    cudaEvent_t (*kev)[2], bool *kev_used, cudaStream_t s)
+                    cudaEvent_t (*kev)[2], bool *kev_used, cudaEvent_t checked, cudaStream_t s)
 {
     static const int slot[5] = {DVDAGPU_K_MLP_SEGCTX, DVDAGPU_K_MLP_AU_PARSE, DVDAGPU_K_MLP_RESOLVE, DVDAGPU_K_MLP_ENTROPY,
                                 DVDAGPU_K_MLP_FILTER};
     for (int pass = 0; pass < 5; pass++) {
+        if (pass == 2) CUDA_TRY(cudaStreamWaitEvent(s, checked, 0));     // the resolve pass reads the check-data verdicts
         CUDA_TRY(cudaEventRecord(kev[slot[pass]][0], s));
         if (launch_fast_pass<1>(pass, m, work[1], n_work[1], n_warps[1], s)) return -1;
         if (launch_fast_pass<2>(pass, m, work[2], n_work[2], n_warps[2], s)) return -1;
