@@ -1142,9 +1142,12 @@ __device__ __forceinline__ bool au_seat(const MlpTables &m, const TrackDev &T, u
     return true;
 }
 
-// one channel's FIR or IIR block of a delta (mlp.c:1029-1120)
+// One channel's FIR or IIR block of a delta (mlp.c:1029-1120).  The values are collected
+// in registers (loops over all eight slots with compile-time indices): the record is
+// written once, with 16-byte stores, by the caller.
 template <typename RD>
-__device__ bool delta_filter(RD &b, ChanHead &C, ChanCoef &K, bool iir, uint32_t &present)
+__device__ __forceinline__ bool delta_filter(RD &b, bool iir, uint32_t &order_out, uint32_t &shift_out,
+                                             int32_t (&coef)[8], int32_t (&ist)[8], uint32_t &present)
 {
     const uint32_t order = rd_get(b, 4);
     if (order > 8) return false;
@@ -1155,20 +1158,23 @@ __device__ bool delta_filter(RD &b, ChanHead &C, ChanCoef &K, bool iir, uint32_t
         if (bits < 1 || bits > 16) return false;
         const uint32_t cshift = rd_get(b, 3);
         if (bits + cshift > 16) return false;
-        int16_t *coef = iir ? K.iir_c : K.fir_c;
-        for (uint32_t i = 0; i < order; i++) coef[i] = (int16_t)((uint32_t)rd_get_s(b, bits) << cshift);
+#pragma unroll
+        for (int i = 0; i < 8; i++) if ((uint32_t)i < order) coef[i] = (int32_t)((uint32_t)rd_get_s(b, bits) << cshift);
         if (rd_get(b, 1)) {
             if (!iir) return false;
             const uint32_t sbits = rd_get(b, 4), sshift = rd_get(b, 4);
             if (!sbits) return false;                           // reference underflows (G2)
-            for (uint32_t i = 0; i < order; i++) K.ist[i] = (int32_t)((uint32_t)rd_get_s(b, sbits) << sshift);
+#pragma unroll
+            for (int i = 0; i < 8; i++) if ((uint32_t)i < order) ist[i] = (int32_t)((uint32_t)rd_get_s(b, sbits) << sshift);
             present |= CD_IIR_STATE;
         }
     }
-    if (iir) { C.iir_order = (uint8_t)order; C.iir_shift = (uint8_t)shift; present |= CD_IIR; }
-    else { C.fir_order = (uint8_t)order; C.fir_shift = (uint8_t)shift; present |= CD_FIR; }
+    order_out = order; shift_out = shift;
+    present |= iir ? CD_IIR : CD_FIR;
     return true;
 }
+
+__device__ __forceinline__ uint32_t pack16(int32_t lo, int32_t hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
 // decoding parameters of one block as a delta (mlp.c:856-993).  RESTART: the block
 // follows a restart header, where everything not transmitted falls back to its
@@ -1176,62 +1182,86 @@ __device__ bool delta_filter(RD &b, ChanHead &C, ChanCoef &K, bool iir, uint32_t
 template <bool RESTART, typename RD>
 __device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D)
 {
-    uint32_t present = 0;
+    uint32_t present = 0, block_size = 8, matrix_len = 0;
+    uint32_t mo[2] = {0, 0}, mb[2] = {0, 0};                    // mat_out / mat_bypass bytes 0-3, 4-5
+    uint32_t os[2] = {0, 0}, qq[2] = {0, 0};                    // out_shift / q bytes 0-3, 4-7
     if (RESTART) {
         if (rd_get(b, 1)) rd_skip(b, 8);                        // the presence flags themselves: in cx.flags already
         present = AD_BLOCK | AD_MATRIX | AD_SHIFT | AD_Q;
     } else if ((cx.flags & 1) && rd_get(b, 1)) return false;    // new presence flags: complete decoder
     if ((cx.flags & 0x80) && rd_get(b, 1)) {
-        const uint32_t bs = rd_get(b, 9);
-        if (bs < 8) return false;
-        D.block_size = (uint16_t)bs; present |= AD_BLOCK;
-    } else if (RESTART) D.block_size = 8;
+        block_size = rd_get(b, 9);
+        if (block_size < 8) return false;
+        present |= AD_BLOCK;
+    }
     if ((cx.flags & 0x40) && rd_get(b, 1)) {
-        const uint32_t ml = rd_get(b, 4);
-        if (ml > DVDA_MAX_MAT || cx.mmc + 3 > DVDA_MAX_CH) return false;
-        D.matrix_len = (uint8_t)ml; present |= AD_MATRIX;
-        for (uint32_t k = 0; k < ml; k++) {
+        matrix_len = rd_get(b, 4);
+        if (matrix_len > DVDA_MAX_MAT || cx.mmc + 3 > DVDA_MAX_CH) return false;
+        present |= AD_MATRIX;
+#pragma unroll
+        for (int k = 0; k < DVDA_MAX_MAT; k++) {
+            if ((uint32_t)k >= matrix_len) break;
             const uint32_t out = rd_get(b, 4), frac = rd_get(b, 4);
             if (out > cx.mmc || frac > 14) return false;
-            D.mat_out[k] = (uint8_t)out;
-            D.mat_bypass[k] = (uint8_t)rd_get(b, 1);
-            for (uint32_t c = 0; c < DVDA_MAX_CH; c++) {
-                int16_t v = 0;
-                if (c < (uint32_t)cx.mmc + 3 && rd_get(b, 1)) v = (int16_t)((uint32_t)rd_get_s(b, frac + 2) << (14 - frac));
-                D.coeff[k][c] = v;
+            mo[k >> 2] |= out << (8 * (k & 3));
+            mb[k >> 2] |= rd_get(b, 1) << (8 * (k & 3));
+            uint32_t row[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < DVDA_MAX_CH; c++) {
+                if ((uint32_t)c < (uint32_t)cx.mmc + 3 && rd_get(b, 1))
+                    row[c >> 1] |= ((uint32_t)rd_get_s(b, frac + 2) << (14 - frac) & 0xFFFFu) << (16 * (c & 1));
             }
+            *reinterpret_cast<uint4 *>(&D.coeff[k][0]) = make_uint4(row[0], row[1], row[2], row[3]);
         }
-    } else if (RESTART) D.matrix_len = 0;
+    }
     if ((cx.flags & 0x20) && rd_get(b, 1)) {
         present |= AD_SHIFT;
-        for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.out_shift[c] = c <= cx.mmc ? (uint8_t)(rd_get_s(b, 4) & 31) : 0;
-    } else if (RESTART) { for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.out_shift[c] = 0; }
+#pragma unroll
+        for (int c = 0; c < DVDA_MAX_CH; c++) if ((uint32_t)c <= cx.mmc) os[c >> 2] |= ((uint32_t)rd_get_s(b, 4) & 31u) << (8 * (c & 3));
+    }
     if ((cx.flags & 0x10) && rd_get(b, 1)) {
         present |= AD_Q;
-        for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.q[c] = c <= cx.max_ch ? (uint8_t)rd_get(b, 4) : 0;
-    } else if (RESTART) { for (uint32_t c = 0; c < DVDA_MAX_CH; c++) D.q[c] = 0; }
+#pragma unroll
+        for (int c = 0; c < DVDA_MAX_CH; c++) if ((uint32_t)c <= cx.max_ch) qq[c >> 2] |= rd_get(b, 4) << (8 * (c & 3));
+    }
+    // head bytes 0..31: block_size, present, matrix_len | mat_out[6] mat_bypass[6] | out_shift[8] | q[8]
+    static_assert(offsetof(AuDelta, mat_out) == 4 && offsetof(AuDelta, mat_bypass) == 10 && offsetof(AuDelta, out_shift) == 16 &&
+                  offsetof(AuDelta, q) == 24 && offsetof(AuDelta, ch) == 32 && sizeof(ChanHead) == 12, "AuDelta head layout");
+    uint4 *head = reinterpret_cast<uint4 *>(&D);
+    head[0] = make_uint4(block_size | present << 16 | matrix_len << 24, mo[0],
+                         (mo[1] & 0xFFFFu) | (mb[0] << 16), (mb[0] >> 16) | (mb[1] << 16));
+    head[1] = make_uint4(os[0], os[1], qq[0], qq[1]);
+    uint32_t *chw = reinterpret_cast<uint32_t *>(&D.ch[0]);
+#pragma unroll 1
     for (uint32_t c = cx.min_ch; c <= cx.max_ch; c++) {
-        ChanHead &C = D.ch[c - cx.min_ch];
-        ChanCoef &K = D.cf[c - cx.min_ch];
-        uint32_t p = 0;
-        if (RESTART) {
-            // defaults (mlp.c:904-989); the FIR history alone survives a restart
-            C.fir_order = C.fir_shift = C.iir_order = C.iir_shift = 0;
-            C.huff_offset = 0; C.codebook = 0; C.huff_lsbs = 24;
-            p = CD_PRESENT | CD_FIR | CD_IIR | CD_OFFSET;
-        }
+        const uint32_t cc = c - cx.min_ch;
+        // defaults after a restart (mlp.c:904-989; the FIR history alone survives it)
+        uint32_t p = RESTART ? (CD_PRESENT | CD_FIR | CD_IIR | CD_OFFSET) : 0u;
+        uint32_t fo = 0, fsh = 0, io = 0, ish = 0, cb = 0, lsbs = 24;
+        int32_t off = 0;
+        int32_t fc[8], ic[8], st[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { fc[i] = 0; ic[i] = 0; st[i] = 0; }
         if (rd_get(b, 1)) {
             p |= CD_PRESENT;
-            if ((cx.flags & 0x08) && rd_get(b, 1) && !delta_filter(b, C, K, false, p)) return false;
-            if ((cx.flags & 0x04) && rd_get(b, 1) && !delta_filter(b, C, K, true, p)) return false;
-            if ((cx.flags & 0x02) && rd_get(b, 1)) { C.huff_offset = rd_get_s(b, 15); p |= CD_OFFSET; }
-            C.codebook = (uint8_t)rd_get(b, 2);
-            C.huff_lsbs = (uint8_t)rd_get(b, 5);
-            if (C.huff_lsbs > 24) return false;
+            if ((cx.flags & 0x08) && rd_get(b, 1) && !delta_filter(b, false, fo, fsh, fc, st, p)) return false;
+            if ((cx.flags & 0x04) && rd_get(b, 1) && !delta_filter(b, true, io, ish, ic, st, p)) return false;
+            if ((cx.flags & 0x02) && rd_get(b, 1)) { off = rd_get_s(b, 15); p |= CD_OFFSET; }
+            cb = rd_get(b, 2);
+            lsbs = rd_get(b, 5);
+            if (lsbs > 24) return false;
         }
-        C.present = (uint8_t)p;
+        chw[cc * 3 + 0] = (uint32_t)off;
+        chw[cc * 3 + 1] = fo | fsh << 8 | io << 16 | ish << 24;
+        chw[cc * 3 + 2] = cb | lsbs << 8 | p << 16;
+        if (p & (CD_FIR | CD_IIR)) {
+            uint4 *k = reinterpret_cast<uint4 *>(&D.cf[cc]);
+            k[0] = make_uint4((uint32_t)st[0], (uint32_t)st[1], (uint32_t)st[2], (uint32_t)st[3]);
+            k[1] = make_uint4((uint32_t)st[4], (uint32_t)st[5], (uint32_t)st[6], (uint32_t)st[7]);
+            k[2] = make_uint4(pack16(fc[0], fc[1]), pack16(fc[2], fc[3]), pack16(fc[4], fc[5]), pack16(fc[6], fc[7]));
+            k[3] = make_uint4(pack16(ic[0], ic[1]), pack16(ic[2], ic[3]), pack16(ic[4], ic[5]), pack16(ic[6], ic[7]));
+        }
     }
-    D.present = (uint8_t)present;
     return true;
 }
 
