@@ -286,19 +286,48 @@ static int small_d2h(dvdagpu_ctx *c, void *host, const void *dev, size_t bytes)
     return 0;
 }
 
-// host -> device, asynchronous (the staging bytes stay untouched until the next decode)
-static int small_h2d(dvdagpu_ctx *c, void *dev, const void *host, size_t bytes)
+// host -> device, asynchronous (the staging bytes stay untouched until the next decode).
+// Uploads can be queued and sent by one launch (flush_h2d).
+#define H2D_BATCH 10
+struct CopyBatch { uint32_t *dst[H2D_BATCH]; const uint32_t *src[H2D_BATCH]; uint32_t nwords[H2D_BATCH]; uint32_t n; };
+__global__ void k_copy_multi(CopyBatch b)
+{
+    for (uint32_t j = 0; j < b.n; j++)
+        for (uint32_t i = threadIdx.x; i < b.nwords[j]; i += blockDim.x) b.dst[j][i] = b.src[j][i];
+}
+static thread_local CopyBatch g_h2d_batch;
+
+static int flush_h2d(dvdagpu_ctx *c)
+{
+    CopyBatch &b = g_h2d_batch;
+    if (!b.n) return 0;
+    if (b.n == 1) LAUNCH(k_copy_words, 1, 256, 0, c->stream, b.dst[0], b.src[0], b.nwords[0]);
+    else LAUNCH(k_copy_multi, 1, 256, 0, c->stream, b);
+    b.n = 0;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int queue_h2d(dvdagpu_ctx *c, void *dev, const void *host, size_t bytes)
 {
     if (!bytes) return 0;
     if ((bytes & 3) || c->map_used + bytes > MAP_BYTES / 2) {
+        TRY(flush_h2d(c));
         CUDA_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         return 0;
     }
+    CopyBatch &b = g_h2d_batch;
+    if (b.n == H2D_BATCH) TRY(flush_h2d(c));
     memcpy(c->hmap + c->map_used, host, bytes);
-    LAUNCH(k_copy_words, 1, 256, 0, c->stream, (uint32_t *)dev, (const uint32_t *)(c->dmap + c->map_used), (uint32_t)(bytes / 4));
+    b.dst[b.n] = (uint32_t *)dev; b.src[b.n] = (const uint32_t *)(c->dmap + c->map_used); b.nwords[b.n] = (uint32_t)(bytes / 4);
+    b.n++;
     c->map_used += (bytes + 15) & ~(size_t)15;
     return 0;
+}
+static int small_h2d(dvdagpu_ctx *c, void *dev, const void *host, size_t bytes)
+{
+    TRY(queue_h2d(c, dev, host, bytes));
+    return flush_h2d(c);
 }
 
 template <typename T>
@@ -313,6 +342,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     g_error[0] = 0;
     g_launch_count = 0;
     c->map_used = 0;
+    g_h2d_batch.n = 0;
     cudaStream_t s = c->stream;
     if (n_sectors64 == 0 || n_sectors64 > 0x7FFFFFFFull) { dvdagpu_set_error("bad sector count"); return -1; }
     if (!n_tracks) { c->pcm_samples = 0; return 0; }
@@ -346,8 +376,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     uint32_t *sec_cnt = c->buf[B_SEC_CNT].as<uint32_t>(), *sec_bad = c->buf[B_SEC_BAD].as<uint32_t>();
     uint32_t *sec_base = c->buf[B_SEC_BASE].as<uint32_t>(), *bad_prefix = c->buf[B_BAD_PREFIX].as<uint32_t>();
     TRY(launch_sector_count(d_sectors, n_sectors, sec_cnt, sec_bad, s));
-    TRY(scan_u32_to_u32(sec_cnt, sec_base, n_sectors, tmp, tmp_bytes, s));
-    TRY(scan_u32_to_u32(sec_bad, bad_prefix, n_sectors, tmp, tmp_bytes, s));
+    {
+        const uint32_t *in[2] = {sec_cnt, sec_bad}; void *out[2] = {sec_base, bad_prefix}; const bool wide[2] = {false, false};
+        TRY(scan_batch(in, out, wide, 2, n_sectors, tmp, tmp_bytes, s));
+    }
     uint32_t np = 0;
     TRY(read_back(c, sec_base + n_sectors, &np));
 
@@ -368,10 +400,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     uint32_t *nonmlp = c->buf[B_PK_NONMLP].as<uint32_t>(), *nm_prefix = c->buf[B_PK_NM_PREFIX].as<uint32_t>();
     uint32_t *pstop = c->buf[B_PK_STOP].as<uint32_t>(), *stop_prefix = c->buf[B_PK_STOP_PREFIX].as<uint32_t>();
     TRY(launch_packet_fill(d_sectors, n_sectors, sec_base, pt, np, nonmlp, pstop, s));
-    TRY(scan_u32_to_u64(pt.mlp_len, pk_es, np, tmp, tmp_bytes, s));
-    TRY(scan_u32_to_u64(pt.pcm_frames, pk_pf, np, tmp, tmp_bytes, s));
-    TRY(scan_u32_to_u32(nonmlp, nm_prefix, np, tmp, tmp_bytes, s));
-    TRY(scan_u32_to_u32(pstop, stop_prefix, np, tmp, tmp_bytes, s));
+    {
+        const uint32_t *in[4] = {pt.mlp_len, pt.pcm_frames, nonmlp, pstop};
+        void *out[4] = {pk_es, pk_pf, nm_prefix, stop_prefix};
+        const bool wide[4] = {true, true, false, false};
+        TRY(scan_batch(in, out, wide, 4, np, tmp, tmp_bytes, s));
+    }
     uint64_t es_total = 0;
     TRY(read_back(c, pk_es + np, &es_total));
 
@@ -394,8 +428,8 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     uint32_t n_raw = 0, n_valid = 0;
     if (es_total) {
         TIMED(DVDAGPU_K_SYNC_SCAN, launch_sync_count(es, es_total, cnt_raw, cnt_valid, sync_slots, nslots, s));
-        TRY(scan_u32_to_u32(cnt_raw, base_raw, chunks, tmp, tmp_bytes, s));
-        TRY(scan_u32_to_u32(cnt_valid, base_valid, chunks, tmp, tmp_bytes, s));
+        const uint32_t *in[2] = {cnt_raw, cnt_valid}; void *out[2] = {base_raw, base_valid}; const bool wide[2] = {false, false};
+        TRY(scan_batch(in, out, wide, 2, chunks, tmp, tmp_bytes, s));
         TRY(read_back(c, base_raw + chunks, &n_raw));
         TRY(read_back(c, base_valid + chunks, &n_valid));
     }
@@ -441,10 +475,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     }
     uint32_t *trk_pk_lo = c->buf[B_TRK_PK_LO].as<uint32_t>(), *trk_seg_base = c->buf[B_TRK_SEG_BASE].as<uint32_t>();
     uint32_t *trk_grp_base = c->buf[B_TRK_GRP_BASE].as<uint32_t>();
-    TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
-    TRY(small_h2d(c, trk_pk_lo, h_pk_lo.data(), n_tracks * 4));
-    TRY(small_h2d(c, trk_seg_base, h_seg_base.data(), (n_tracks + 1) * 4));
-    TRY(small_h2d(c, trk_grp_base, h_grp_base.data(), (n_tracks + 1) * 4));
+    TRY(queue_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
+    TRY(queue_h2d(c, trk_pk_lo, h_pk_lo.data(), n_tracks * 4));
+    TRY(queue_h2d(c, trk_seg_base, h_seg_base.data(), (n_tracks + 1) * 4));
+    TRY(queue_h2d(c, trk_grp_base, h_grp_base.data(), (n_tracks + 1) * 4));
 
     const DecWork *d_work[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t n_work[5] = {0, 0, 0, 0, 0};
@@ -458,9 +492,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             n_work[cl] = (uint32_t)h_work[cl].size();
             d_work[cl] = base + off;
             if (n_work[cl])
-                TRY(small_h2d(c, base + off, h_work[cl].data(), n_work[cl] * sizeof(DecWork)));
+                TRY(queue_h2d(c, base + off, h_work[cl].data(), n_work[cl] * sizeof(DecWork)));
             off += n_work[cl];
         }
+        TRY(flush_h2d(c));
     }
     MlpTables m;
     memset(&m, 0, sizeof m);

@@ -9,9 +9,18 @@
 #define SCAN_THREADS 512
 #define SCAN_ITEMS 4
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+#define SCAN_MAX_JOBS 4
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ sums)
+// up to four tables of the same length are scanned by one set of launches (blockIdx.y = table)
+struct ScanBatch {
+    const uint32_t *in[SCAN_MAX_JOBS];
+    void *out[SCAN_MAX_JOBS];
+    uint32_t out64;                 // bit j: table j's prefix sums are 64-bit
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(ScanBatch b, uint64_t n, uint64_t *__restrict__ sums, uint32_t nblocks)
 {
+    const uint32_t *__restrict__ in = b.in[blockIdx.y];
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
     uint64_t v = 0;
 #pragma unroll
@@ -21,12 +30,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t *__
     }
     uint64_t total;
     block_excl_scan<SCAN_THREADS>(v, &total);
-    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+    if (threadIdx.x == 0) sums[(uint64_t)blockIdx.y * (nblocks + 2) + blockIdx.x] = total;
 }
 
-// one block: exclusive scan of the block sums in place, total behind them
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint64_t *sums, uint32_t nblocks)
+// one block per table: exclusive scan of the block sums in place, total behind them
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint64_t *all_sums, uint32_t nblocks)
 {
+    uint64_t *sums = all_sums + (uint64_t)blockIdx.x * (nblocks + 2);
     uint64_t carry = 0;
     for (uint32_t base = 0; base < nblocks; base += SCAN_THREADS) {
         const uint32_t i = base + threadIdx.x;
@@ -39,9 +49,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint64_t *sums, uint
     if (threadIdx.x == 0) sums[nblocks] = carry;
 }
 
-template <typename OutT>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ sums, uint32_t nblocks, OutT *__restrict__ out)
+// SINGLE: the table fits one tile, no block sums needed (one launch instead of three)
+template <bool SINGLE>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(ScanBatch b, uint64_t n, const uint64_t *__restrict__ all_sums, uint32_t nblocks)
 {
+    const uint32_t *__restrict__ in = b.in[blockIdx.y];
+    const uint64_t *sums = all_sums + (uint64_t)blockIdx.y * (nblocks + 2);
     // items of one thread are contiguous so the per-thread prefix is a running sum
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t x[SCAN_ITEMS];
@@ -52,41 +65,66 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t *__r
         v += x[k];
     }
     uint64_t total;
-    uint64_t ex = block_excl_scan<SCAN_THREADS>(v, &total) + sums[blockIdx.x];
+    uint64_t ex = block_excl_scan<SCAN_THREADS>(v, &total) + (SINGLE ? 0ull : sums[blockIdx.x]);
+    const uint64_t grand = SINGLE ? total : sums[nblocks];
+    if ((b.out64 >> blockIdx.y) & 1) {
+        uint64_t *out = static_cast<uint64_t *>(b.out[blockIdx.y]);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        if (base + k < n) out[base + k] = (OutT)ex;
-        ex += x[k];
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (base + k < n) out[base + k] = ex;
+            ex += x[k];
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = grand;
+    } else {
+        uint32_t *out = static_cast<uint32_t *>(b.out[blockIdx.y]);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (base + k < n) out[base + k] = (uint32_t)ex;
+            ex += x[k];
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = (uint32_t)grand;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = (OutT)sums[nblocks];
 }
 
 size_t scan_tmp_bytes(uint64_t n)
 {
-    return (size_t)(div_up_u32(n ? n : 1, SCAN_TILE) + 2) * sizeof(uint64_t);
+    return (size_t)SCAN_MAX_JOBS * (div_up_u32(n ? n : 1, SCAN_TILE) + 2) * sizeof(uint64_t);
 }
 
-template <typename OutT>
-static int scan_impl(const uint32_t *in, OutT *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t s)
+// exclusive prefix sums of njobs (<= 4) tables of n entries each; out[j] has n + 1 entries
+int scan_batch(const uint32_t *const in[], void *const out[], const bool out64[], int njobs, uint64_t n,
+               void *tmp, size_t tmp_bytes, cudaStream_t s)
 {
-    if (tmp_bytes < scan_tmp_bytes(n)) {
-        dvdagpu_set_error("scan: temporary buffer too small");
+    if (njobs < 1 || njobs > SCAN_MAX_JOBS || tmp_bytes < scan_tmp_bytes(n)) {
+        dvdagpu_set_error("scan: bad batch or temporary buffer too small");
         return -1;
+    }
+    ScanBatch b;
+    b.out64 = 0;
+    for (int j = 0; j < SCAN_MAX_JOBS; j++) {
+        b.in[j] = in[j < njobs ? j : 0]; b.out[j] = out[j < njobs ? j : 0];
+        if (j < njobs && out64[j]) b.out64 |= 1u << j;
     }
     uint64_t *sums = (uint64_t *)tmp;
     const uint32_t nblocks = div_up_u32(n ? n : 1, SCAN_TILE);
-    LAUNCH(k_scan_reduce, nblocks, SCAN_THREADS, 0, s, in, n, sums);
-    LAUNCH(k_scan_sums, 1, SCAN_THREADS, 0, s, sums, nblocks);
-    LAUNCH(k_scan_apply<OutT>, nblocks, SCAN_THREADS, 0, s, in, n, sums, nblocks, out);
+    if (nblocks == 1) {
+        LAUNCH(k_scan_apply<true>, dim3(1, njobs), SCAN_THREADS, 0, s, b, n, sums, nblocks);
+    } else {
+        LAUNCH(k_scan_reduce, dim3(nblocks, njobs), SCAN_THREADS, 0, s, b, n, sums, nblocks);
+        LAUNCH(k_scan_sums, njobs, SCAN_THREADS, 0, s, sums, nblocks);
+        LAUNCH(k_scan_apply<false>, dim3(nblocks, njobs), SCAN_THREADS, 0, s, b, n, sums, nblocks);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 int scan_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t s)
 {
-    return scan_impl<uint64_t>(in, out, n, tmp, tmp_bytes, s);
+    const uint32_t *i[1] = {in}; void *o[1] = {out}; const bool w[1] = {true};
+    return scan_batch(i, o, w, 1, n, tmp, tmp_bytes, s);
 }
 int scan_u32_to_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t s)
 {
-    return scan_impl<uint32_t>(in, out, n, tmp, tmp_bytes, s);
+    const uint32_t *i[1] = {in}; void *o[1] = {out}; const bool w[1] = {false};
+    return scan_batch(i, o, w, 1, n, tmp, tmp_bytes, s);
 }
