@@ -336,6 +336,26 @@ static int read_back(dvdagpu_ctx *c, const T *dev, T *host)
     return small_d2h(c, host, dev, sizeof(T));
 }
 
+// two read-backs, one round trip (each one costs tens of microseconds, more while bulk copies run)
+static int small_d2h_pair(dvdagpu_ctx *c, void *host_a, const void *dev_a, size_t bytes_a,
+                          void *host_b, const void *dev_b, size_t bytes_b)
+{
+    const size_t off_b = (bytes_a + 15) & ~(size_t)15;
+    if (off_b + bytes_b > MAP_BYTES / 2 || ((bytes_a | bytes_b) & 3)) {
+        TRY(small_d2h(c, host_a, dev_a, bytes_a));
+        return small_d2h(c, host_b, dev_b, bytes_b);
+    }
+    CopyBatch b;
+    b.n = 2;
+    b.dst[0] = (uint32_t *)(c->dmap + MAP_BYTES / 2); b.src[0] = (const uint32_t *)dev_a; b.nwords[0] = (uint32_t)(bytes_a / 4);
+    b.dst[1] = (uint32_t *)(c->dmap + MAP_BYTES / 2 + off_b); b.src[1] = (const uint32_t *)dev_b; b.nwords[1] = (uint32_t)(bytes_b / 4);
+    LAUNCH(k_copy_multi, 1, 256, 0, c->stream, b);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(host_a, c->hmap + MAP_BYTES / 2, bytes_a);
+    memcpy(host_b, c->hmap + MAP_BYTES / 2 + off_b, bytes_b);
+    return 0;
+}
+
 static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n_sectors64,
                             uint32_t n_tracks, const dvdagpu_track_desc *descs, dvdagpu_track_result *results)
 {
@@ -430,8 +450,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         TIMED(DVDAGPU_K_SYNC_SCAN, launch_sync_count(es, es_total, cnt_raw, cnt_valid, sync_slots, nslots, s));
         const uint32_t *in[2] = {cnt_raw, cnt_valid}; void *out[2] = {base_raw, base_valid}; const bool wide[2] = {false, false};
         TRY(scan_batch(in, out, wide, 2, chunks, tmp, tmp_bytes, s));
-        TRY(read_back(c, base_raw + chunks, &n_raw));
-        TRY(read_back(c, base_valid + chunks, &n_valid));
+        TRY(small_d2h_pair(c, &n_raw, base_raw + chunks, 4, &n_valid, base_valid + chunks, 4));
     }
     ENSURE(B_RAW, ((size_t)n_raw + 1) * 8); ENSURE(B_VALID, ((size_t)n_valid + 1) * 8);
     uint64_t *raw = c->buf[B_RAW].as<uint64_t>(), *valid = c->buf[B_VALID].as<uint64_t>();
@@ -566,9 +585,8 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, d_status + 1, s));
             TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
             uint64_t cells = 0;
-            TRY(read_back(c, cell_base + ngroups, &cells));
             struct { uint32_t au, chunks; } most = {0, 0};
-            TRY(small_d2h(c, &most, d_status + 1, sizeof most));
+            TRY(small_d2h_pair(c, &cells, cell_base + ngroups, 8, &most, d_status + 1, sizeof most));
             m.max_au = most.au; max_chunks = most.chunks;
             ENSURE(B_TILES, (cells * DVDA_LANES + 64 + 16 * DVDA_MAX_CH * DVDA_LANES) * sizeof(int32_t));   // 16 frames of slack: the filter passes read ahead
             ENSURE(B_BYPASS, cells * DVDA_LANES + 64);
@@ -591,16 +609,18 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
             TIMED(DVDAGPU_K_CARRY_FIX, launch_carry_fix(m, s));
             TRY(launch_seg_finalize(m, seg_frames, d_status, s));
-            TRY(read_back(c, d_status, &status));
+            // the track totals are computed before the status is known (one round trip for both);
+            // after an overflow they are simply computed again
+            TRY(scan_u32_to_u64(seg_frames, seg_frame_scan, nseg, tmp, tmp_bytes, s));
+            TRY(launch_track_finalize(m, seg_frame_scan, d_status, s));
+            TRY(small_d2h_pair(c, &status, d_status, 4, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
             if (!(status & SEG_OVERFLOW)) break;
             if (attempt == 1) { dvdagpu_set_error("tile overflow persists"); return -1; }
         }
-        TRY(scan_u32_to_u64(seg_frames, seg_frame_scan, nseg, tmp, tmp_bytes, s));
-        TRY(launch_track_finalize(m, seg_frame_scan, s));
     } else {
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
+        TRY(small_d2h(c, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
     }
-    TRY(small_d2h(c, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
     CUDA_TRY(cudaEventRecord(c->ev[3], s));
     if (getenv("DVDAGPU_DEBUG")) {
         fprintf(stderr, "[dvdagpu] sectors=%u packets=%u es=%llu raw=%u valid=%u segs=%u groups=%u aus=%u\n",
@@ -713,7 +733,7 @@ static void add_stats(dvdagpu_stats &a, const dvdagpu_stats &b)
     a.demux_ms += b.demux_ms; a.index_ms += b.index_ms; a.decode_ms += b.decode_ms; a.output_ms += b.output_ms;
     a.total_ms += b.total_ms; a.launches += b.launches; a.segments += b.segments; a.access_units += b.access_units;
     a.es_bytes += b.es_bytes; a.samples += b.samples;
-    for (int k = 0; k < 12; k++) a.kernel_ms[k] += b.kernel_ms[k];
+    for (int k = 0; k < 16; k++) a.kernel_ms[k] += b.kernel_ms[k];
 }
 
 extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sectors, uint64_t n_sectors,

@@ -109,5 +109,5 @@ size_t au_delta_bytes();
 int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
                     cudaEvent_t (*kev)[2], bool *kev_used, cudaEvent_t checked, cudaStream_t s);
 int launch_seg_finalize(MlpTables m, uint32_t *seg_frames, uint32_t *status, cudaStream_t s);
-int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, cudaStream_t s);
+int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, const uint32_t *status, cudaStream_t s);
 int launch_rematrix(MlpTables m, uint32_t max_chunks, uint32_t channel_mask, cudaStream_t s);

@@ -2254,10 +2254,11 @@ __global__ void k_seg_finalize(MlpTables m, uint32_t *__restrict__ seg_frames, u
 
 // one thread per segment: position in the track's output; thread of the first
 // segment also totals the track
-__global__ void k_track_finalize(MlpTables m, const uint64_t *__restrict__ scan)
+__global__ void k_track_finalize(MlpTables m, const uint64_t *__restrict__ scan, const uint32_t *__restrict__ status)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.nseg) return;
+    if (*status & SEG_OVERFLOW) return;                   // the batch is decoded once more: leave the counts alone
     SegDev &S = m.segs[i];
     TrackDev &T = m.tracks[S.track];
     const uint32_t local = i - T.seg_base;
@@ -2276,10 +2277,10 @@ int launch_seg_finalize(MlpTables m, uint32_t *seg_frames, uint32_t *status, cud
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, cudaStream_t s)
+int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, const uint32_t *status, cudaStream_t s)
 {
     if (!m.nseg) return 0;
-    LAUNCH(k_track_finalize, div_up_u32(m.nseg, 128), 128, 0, s, m, seg_frame_scan);
+    LAUNCH(k_track_finalize, div_up_u32(m.nseg, 128), 128, 0, s, m, seg_frame_scan, status);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
