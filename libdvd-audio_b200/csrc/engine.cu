@@ -746,9 +746,9 @@ extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sec
     const uint64_t last = track->last_sector < n_sectors ? track->last_sector : n_sectors - 1;
     if (!part_sectors) {
         // a decode has a latency floor of a few milliseconds whatever its size, so few, large
-        // parts: about 100 MB of AOB each, between 2 and 8 of them
+        // parts: about 75 MB of AOB each, between 2 and 8 of them
         const uint64_t n = last >= first ? last - first + 1 : 0;
-        uint64_t parts = n / 50000;
+        uint64_t parts = (n + 19000) / 38000;
         parts = parts < 2 ? 2 : parts > 8 ? 8 : parts;
         part_sectors = (uint32_t)((n + parts - 1) / parts);
         if (part_sectors < 8192) part_sectors = 8192;
