@@ -1055,7 +1055,7 @@ struct AuSnap {
     uint64_t bit_end;       // absolute bit position of the end of the substream data
     uint16_t block_size;
     uint8_t want, valid;
-    uint8_t min_ch, nch, pad0, pad1;
+    uint8_t min_ch, nch, has_matrix, pad1;
     ChanSnap ch[4];
 };
 
@@ -1432,9 +1432,9 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
         if (block_size > nominal || nominal % block_size) { fallback = true; break; }
 
         // per-channel constants of the AU's blocks (mlp.c:1151-1176, 1260-1270)
-        struct { uint16_t block_size; uint8_t want, valid, min_ch, nch, pad0, pad1; ChanSnap ch[4]; } out;
+        struct { uint16_t block_size; uint8_t want, valid, min_ch, nch, has_matrix, pad1; ChanSnap ch[4]; } out;
         out.block_size = (uint16_t)block_size; out.want = (uint8_t)want; out.valid = 1;
-        out.min_ch = cx.min_ch; out.nch = NCH; out.pad0 = out.pad1 = 0;
+        out.min_ch = cx.min_ch; out.nch = NCH; out.has_matrix = matrix_len != 0; out.pad1 = 0;
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) { out.ch[cc].sho = 0; out.ch[cc].cb = out.ch[cc].lsb_bits = out.ch[cc].q = out.ch[cc].shift = 0; }
 #pragma unroll
@@ -1545,6 +1545,12 @@ __device__ __forceinline__ uint32_t filt_shift(const FiltSetup &F)
 }
 
 // ---- pass B: entropy decode of one access unit -------------------------------------
+//
+// The bit window is kept as two 32-bit halves (hi holds the next bits, MSB first):
+// peeking is a shift of hi, consuming n <= 32 bits a funnel shift, topping up two
+// funnel shifts — about half the instructions of 64-bit shifts.  All frames of the
+// access unit fit the tile by construction (the group's capacity is its longest
+// segment, access units have the nominal length here).
 template <int NCH>
 __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &job, uint32_t a,
                                            const uint16_t (*lut)[512], uint32_t ring)
@@ -1559,6 +1565,8 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
     if (m.ss_flags[job.k * m.nseg + job.seg] & SEG_FALLBACK) return;
     const AuSnap sn = m.au_snap[(uint64_t)job.k * m.nau + A];
     if (!sn.valid) return;
+    const uint32_t frame0 = a * nominal;
+    if (frame0 + nominal > G.cap) { atomicOr(&m.ss_flags[job.k * m.nseg + job.seg], SEG_OVERFLOW | SEG_FALLBACK); return; }
 
     Rd b;
     rd_init(b, m.es, ring);
@@ -1568,55 +1576,74 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
     const uint32_t end_bits = (uint32_t)(sn.bit_end - ((sn.bit0 >> 5) << 5));
 
     int32_t sho[NCH];
-    uint32_t lsb_bits[NCH], cb[NCH], q[NCH];
+    uint32_t lsb_bits[NCH], q[NCH];
+    const uint16_t *cbt[NCH];
 #pragma unroll
-    for (int cc = 0; cc < NCH; cc++) { sho[cc] = sn.ch[cc].sho; lsb_bits[cc] = sn.ch[cc].lsb_bits; cb[cc] = sn.ch[cc].cb; q[cc] = sn.ch[cc].q; }
-    const uint32_t want = sn.want, bs = sn.block_size, cap = G.cap;
-    const uint32_t frame0 = a * nominal;
+    for (int cc = 0; cc < NCH; cc++) { sho[cc] = sn.ch[cc].sho; lsb_bits[cc] = sn.ch[cc].lsb_bits; cbt[cc] = lut[sn.ch[cc].cb]; q[cc] = sn.ch[cc].q; }
+    const uint32_t want = sn.want, bs = sn.block_size;
+    // the bypass bits are looked at wherever the governing substream has matrices at all
+    const bool store_byp = governing && sn.has_matrix;
     int32_t *tile = m.tiles + G.tile_off + job.lane + ((uint64_t)frame0 * nch + sn.min_ch) * DVDA_LANES;
     uint8_t *byp = m.bypass + G.byp_off + job.lane + (uint64_t)frame0 * DVDA_LANES;
     const uint32_t tile_step = nch * DVDA_LANES;
-    const uint32_t need4 = (4 * (NCH * 33 + 6) + 31) / 32 + 2;
-    uint32_t f = frame0, done = 0, bad = 0, flags = 0;
+    constexpr uint32_t need8 = (8 * (NCH * 33 + 6) + 31) / 32 + 2;     // words eight frames can consume, plus the one fetched ahead
+    constexpr uint32_t need1 = ((NCH * 33 + 6) + 31) / 32 + 2;
+    uint32_t done = 0, bad = 0;
+    uint32_t hi, lo;
 
-#define DVDA_EFRAME()                                                                              \
+#define DVDA_WIN_LOAD() { hi = (uint32_t)(b.win >> 32); lo = (uint32_t)b.win; }
+#define DVDA_WIN_STORE() { b.win = ((uint64_t)hi << 32) | lo; }
+    // frame FI of the current run (FI: compile-time offset into the tile)
+#define DVDA_EFRAME(FI)                                                                            \
     {                                                                                              \
-        const bool room = f < cap;                                                                 \
-        flags |= room ? 0u : SEG_OVERFLOW;                                                         \
         if (want) {                                                                                \
+            DVDA_WIN_STORE()                                                                       \
             const uint32_t bmask = bypass_bits(b, want);                                           \
             rd_hot_begin(b);                                                                       \
-            if (governing && room) *byp = (uint8_t)bmask;                                          \
-        } else if (governing && room) *byp = 0;                                                    \
+            DVDA_WIN_LOAD()                                                                        \
+            if (store_byp) byp[(FI) * DVDA_LANES] = (uint8_t)bmask;                                \
+        } else if (store_byp) byp[(FI) * DVDA_LANES] = 0;                                          \
         _Pragma("unroll") for (int cc = 0; cc < NCH; cc++) {                                       \
-            rd_top_up(b);                                                                          \
-            const uint32_t e = lut[cb[cc]][(uint32_t)(b.win >> 55)];                               \
+            if (b.avail <= 32) {                                                                   \
+                hi |= __funnelshift_rc(b.ahead, 0u, (uint32_t)b.avail);                            \
+                lo = __funnelshift_rc(0u, b.ahead, (uint32_t)b.avail);                             \
+                b.avail += 32;                                                                     \
+                b.next_w++;                                                                        \
+            }                                                                                      \
+            b.ahead = rd_ring_word(b, b.next_w);                                                   \
+            const uint32_t e = cbt[cc][hi >> 23];                                                  \
             bad |= e;                                                                              \
             const uint32_t hl = (e >> 8) & 15;                                                     \
             const int32_t msb = e & 0xFF;                                                          \
-            b.win <<= hl;                                                                          \
-            const int32_t lsb = (int32_t)(uint32_t)((b.win >> 1) >> (63 - lsb_bits[cc]));          \
-            b.win <<= lsb_bits[cc];                                                                \
+            hi = __funnelshift_l(lo, hi, hl); lo <<= hl;                                           \
+            const int32_t lsb = (int32_t)((hi >> 1) >> (31 - lsb_bits[cc]));                       \
+            hi = __funnelshift_l(lo, hi, lsb_bits[cc]); lo <<= lsb_bits[cc];                       \
             b.avail -= hl + lsb_bits[cc];                                                          \
-            const int32_t res = (int32_t)((uint32_t)((msb << lsb_bits[cc]) + lsb + sho[cc]) << q[cc]); \
-            if (room) tile[cc * DVDA_LANES] = res;                                                 \
+            tile[(FI) * tile_step + cc * DVDA_LANES] =                                             \
+                (int32_t)((uint32_t)((msb << lsb_bits[cc]) + lsb + sho[cc]) << q[cc]);             \
         }                                                                                          \
-        f++; tile += tile_step; byp += DVDA_LANES;                                                 \
     }
 
     bool ok = true;
     while (ok) {
         // one block of bs frames (bs divides the nominal AU length, bs >= 8)
         uint32_t i = 0;
-        for (; i + 4 <= bs; i += 4) {
-            rd_prefetch(b, need4);
+        for (; i + 8 <= bs; i += 8) {
+            rd_prefetch(b, need8);
             rd_hot_begin(b);
-            DVDA_EFRAME() DVDA_EFRAME() DVDA_EFRAME() DVDA_EFRAME()
+            DVDA_WIN_LOAD()
+            DVDA_EFRAME(0) DVDA_EFRAME(1) DVDA_EFRAME(2) DVDA_EFRAME(3)
+            DVDA_EFRAME(4) DVDA_EFRAME(5) DVDA_EFRAME(6) DVDA_EFRAME(7)
+            DVDA_WIN_STORE()
+            tile += 8 * tile_step; byp += 8 * DVDA_LANES;
         }
         for (; i < bs; i++) {
-            rd_prefetch(b, need4);
+            rd_prefetch(b, need1);
             rd_hot_begin(b);
-            DVDA_EFRAME()
+            DVDA_WIN_LOAD()
+            DVDA_EFRAME(0)
+            DVDA_WIN_STORE()
+            tile += tile_step; byp += DVDA_LANES;
         }
         done += bs;
         if ((bad & 0x8000) || rd_pos(b) > end_bits) { ok = false; break; }
@@ -1627,9 +1654,10 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
         if (done + bs > nominal || rd_get(b, 1)) { ok = false; break; }
     }
 #undef DVDA_EFRAME
+#undef DVDA_WIN_LOAD
+#undef DVDA_WIN_STORE
     cp_wait<0>();
-    if (!ok || done != nominal) flags |= SEG_FALLBACK;
-    if (flags) atomicOr(&m.ss_flags[job.k * m.nseg + job.seg], flags);
+    if (!ok || done != nominal) atomicOr(&m.ss_flags[job.k * m.nseg + job.seg], SEG_FALLBACK);
 }
 
 // ---- pass C: prediction filters of one channel over a whole segment -------------------
