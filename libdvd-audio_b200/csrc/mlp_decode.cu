@@ -1772,8 +1772,8 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
     extern __shared__ int32_t out_sm[];
     constexpr int SPW = 32 / NCH;                        // segments per warp
     constexpr int SUB = (32 + SPW - 1) / SPW;            // warps per group
-    constexpr int ROW = 32 * NCH + NCH;                  // one segment's 32 frames (+NCH: bank = lane when parking)
-    constexpr int WARP_WORDS = SPW * (ROW + 4);          // + per segment {output base lo, hi, frames, -}
+    constexpr int ROW = 32 * NCH + 4;                    // one segment's 32 frames (+4: rows stay 16-byte aligned, banks spread)
+    constexpr int WARP_WORDS = SPW * (ROW + 4);          // + per segment {output base lo, hi, frames, 16-byte aligned?}
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * OUT_WARPS + wib;
     if (warp >= n_warps * SUB) return;
@@ -1805,6 +1805,7 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
     if (cc == 0 && sl < SPW) {
         const uint64_t base = (mine ? S.frame0 : 0) * NCH;
         meta[sl * 4 + 0] = (uint32_t)base; meta[sl * 4 + 1] = (uint32_t)(base >> 32); meta[sl * 4 + 2] = my_frames;
+        meta[sl * 4 + 3] = ((T.out_base + base) & 3) == 0;       // the rows of this segment start on 16-byte boundaries
     }
     __syncwarp();
 
@@ -1834,21 +1835,25 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
 
     auto flush = [&](uint32_t f0) {
         __syncwarp();
-        // row s = 32 frames of segment s, contiguous in the output
-#pragma unroll 4
-        for (uint32_t s2 = 0; s2 < (uint32_t)SPW; s2++) {
-            const uint32_t fr = meta[s2 * 4 + 2];
-            if (f0 >= fr) continue;
-            const uint64_t base = ((uint64_t)meta[s2 * 4 + 1] << 32 | meta[s2 * 4 + 0]) + (uint64_t)f0 * NCH;
-            const int32_t *src = patch + s2 * ROW;
-            int32_t *dst = pcm_row + base;
-            if (f0 + 32 <= fr) {
+        // The patch leaves as 16-byte pieces: piece q = row * (8 * NCH) + column, 32 pieces per
+        // step, so a step writes whole rows (32 frames of a segment = 128 * NCH contiguous bytes).
+        constexpr uint32_t ROW_QUADS = 8 * NCH, QUADS = SPW * ROW_QUADS;
 #pragma unroll
-                for (int k = 0; k < NCH; k++) dst[lane + 32 * k] = src[lane + 32 * k];
-            } else {
-                const uint32_t n = (fr - f0) * NCH;
-#pragma unroll
-                for (int k = 0; k < NCH; k++) if (lane + 32 * k < n) dst[lane + 32 * k] = src[lane + 32 * k];
+        for (uint32_t t = 0; t < (QUADS + 31) / 32; t++) {
+            const uint32_t qd = t * 32 + lane, row = qd / ROW_QUADS, c4 = (qd % ROW_QUADS) * 4;
+            if (row >= (uint32_t)SPW) continue;
+            const uint4 mt = *reinterpret_cast<const uint4 *>(meta + row * 4);     // base lo, hi, frames, aligned
+            if (f0 >= mt.z) continue;
+            const int32_t *src = patch + row * ROW + c4;
+            int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * NCH) + c4;
+            const int4 v = *reinterpret_cast<const int4 *>(src);
+            if (f0 + 32 <= mt.z && mt.w) *reinterpret_cast<int4 *>(dst) = v;
+            else {
+                const uint32_t n = min(32u, mt.z - f0) * NCH;
+                if (c4 + 0 < n) dst[0] = v.x;
+                if (c4 + 1 < n) dst[1] = v.y;
+                if (c4 + 2 < n) dst[2] = v.z;
+                if (c4 + 3 < n) dst[3] = v.w;
             }
         }
         __syncwarp();
@@ -1961,7 +1966,7 @@ static int launch_one_filter_out(MlpTables m, const DecWork *work, uint32_t n_wo
 {
     if (!n_warps) return 0;
     constexpr int SPW = 32 / NCH, SUB = (32 + SPW - 1) / SPW;
-    const size_t smem = (size_t)OUT_WARPS * SPW * (32 * NCH + NCH + 4) * sizeof(int32_t);
+    const size_t smem = (size_t)OUT_WARPS * SPW * (32 * NCH + 4 + 4) * sizeof(int32_t);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
