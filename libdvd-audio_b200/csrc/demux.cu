@@ -192,38 +192,58 @@ __global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt,
 // reference applies (src/pcm.c:103-166), rebuilt from the layout rule.
 __constant__ uint8_t c_pcm_perm[2][6][36];
 
-// One block per PCM packet; each thread unpacks whole chunks (two frames).
-__global__ void k_pcm_unpack(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t np,
-                             const uint64_t *__restrict__ pk_pf, const TrackDev *__restrict__ tracks,
-                             const uint32_t *__restrict__ trk_pk_lo, uint32_t n_tracks,
-                             int32_t *__restrict__ pcm)
+// One warp per PCM packet (many packets in flight per SM: the work of a packet is a
+// chain of small table loads followed by 2 KiB of payload).  The payload is staged
+// in shared memory with 16-byte loads; then every lane assembles whole samples (the
+// two or three bytes of a sample are found through the inverse of the chunk
+// permutation) and consecutive lanes store consecutive samples.
+#define PCM_WARPS 8
+__global__ void __launch_bounds__(PCM_WARPS * 32)
+k_pcm_unpack(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t np,
+             const uint64_t *__restrict__ pk_pf, const TrackDev *__restrict__ tracks,
+             const uint32_t *__restrict__ trk_pk_lo, uint32_t n_tracks,
+             int32_t *__restrict__ pcm)
 {
-    const uint32_t i = blockIdx.x;
+    __shared__ uint4 stage_all[PCM_WARPS][DVDA_SECTOR / 16 + 2];
+    __shared__ uint8_t inv_all[PCM_WARPS][40];
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * PCM_WARPS + wib;
     if (i >= np || pt.codec[i] != CODEC_PCM) return;
     // owning track: the last one whose first packet is <= i
     const uint32_t t = upper_bound_dev(trk_pk_lo, n_tracks, i);
     if (t == 0) return;
     const TrackDev &T = tracks[t - 1];
     if (T.status != 0 || T.codec != 0 || i < T.pk_lo || i >= T.pcm_pk_end) return;
+    uint4 *stage = stage_all[wib];
+    uint8_t *inv = inv_all[wib];
     const uint32_t ch = T.channels, bytes = T.bits >> 3, chunk = T.pcm_chunk;
     const uint32_t nchunks = pt.pcm_frames[i] >> 1;
     const uint8_t *src = sectors + (uint64_t)pt.sector[i] * DVDA_SECTOR + pt.off[i] + pt.pad2[i];
     int32_t *dst = pcm + T.out_base + (pk_pf[i] - T.pcm_frame0) * ch;
     const uint8_t *perm = c_pcm_perm[bytes == 3][ch - 1];
-    for (uint32_t k = threadIdx.x; k < nchunks; k += blockDim.x) {
-        const uint8_t *c = src + k * chunk;
-        uint8_t un[36];
-        for (uint32_t b = 0; b < chunk; b++) un[perm[b]] = (uint8_t)ld_u8(c + b);
-        int32_t *o = dst + (uint64_t)k * 2 * ch;
-        for (uint32_t smp = 0; smp < 2 * ch; smp++) {
-            int32_t v;
-            if (bytes == 2) v = (int16_t)(un[2 * smp] | (un[2 * smp + 1] << 8));
-            else {
-                v = un[3 * smp] | (un[3 * smp + 1] << 8) | (un[3 * smp + 2] << 16);
-                v = (v << 8) >> 8;
-            }
-            o[smp] = v;
+    for (uint32_t b = lane; b < chunk; b += 32) inv[perm[b]] = (uint8_t)b;
+    // the 16-byte pieces covering the payload (sectors are 16-byte aligned, a packet stays inside its sector)
+    const uint32_t used = nchunks * chunk;
+    const uint32_t mis = (uint32_t)((uintptr_t)src & 15);
+    const uint4 *base = reinterpret_cast<const uint4 *>(src - mis);
+    for (uint32_t k = lane; k * 16 < mis + used; k += 32) stage[k] = __ldg(base + k);
+    __syncwarp();
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(stage) + mis;
+    const uint32_t per_chunk = 2 * ch, nsamples = nchunks * per_chunk;
+    // lane -> (chunk, sample in chunk), advanced by 32 samples per step without dividing
+    uint32_t k = lane / per_chunk, w = lane - k * per_chunk;
+    const uint32_t dk = 32 / per_chunk, dw = 32 - dk * per_chunk;
+    for (uint32_t smp = lane; smp < nsamples; smp += 32) {
+        const uint8_t *c = sb + k * chunk;
+        int32_t v;
+        if (bytes == 2) v = (int16_t)(c[inv[2 * w]] | (c[inv[2 * w + 1]] << 8));
+        else {
+            v = c[inv[3 * w]] | (c[inv[3 * w + 1]] << 8) | (c[inv[3 * w + 2]] << 16);
+            v = (v << 8) >> 8;
         }
+        dst[smp] = v;
+        k += dk; w += dw;
+        if (w >= per_chunk) { w -= per_chunk; k++; }
     }
 }
 
@@ -260,7 +280,7 @@ int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t np, const
                       const TrackDev *tracks, const uint32_t *trk_pk_lo, uint32_t n_tracks, int32_t *pcm, cudaStream_t s)
 {
     if (!np) return 0;
-    LAUNCH(k_pcm_unpack, np, 128, 0, s, sectors, pt, np, pk_pf, tracks, trk_pk_lo, n_tracks, pcm);
+    LAUNCH(k_pcm_unpack, div_up_u32(np, PCM_WARPS), PCM_WARPS * 32, 0, s, sectors, pt, np, pk_pf, tracks, trk_pk_lo, n_tracks, pcm);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
