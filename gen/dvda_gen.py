@@ -138,3 +138,31 @@ def make_disc(directory, titles, max_aob_bytes=0):
             k += 1
         out.append(row)
     return out
+
+
+def make_disc_multi(directory, titlesets, max_aob_bytes=0):
+    """A disc with several title sets (ATS_01 .. ATS_nn): titlesets is a list of
+    `titles` arguments of make_disc().  Every title set is generated on its own
+    and renamed; AUDIO_TS.IFO gets the count.  Returns the list of make_disc()
+    results."""
+    import shutil
+    import tempfile
+    os.makedirs(directory, exist_ok=True)
+    out = []
+    for n, titles in enumerate(titlesets, start=1):
+        tmp = tempfile.mkdtemp(prefix="dvda_ts%02d_" % n, dir=directory)
+        try:
+            out.append(make_disc(tmp, titles, max_aob_bytes))
+            for name in sorted(os.listdir(tmp)):
+                if name.startswith("ATS_01_"):
+                    shutil.move(os.path.join(tmp, name), os.path.join(directory, "ATS_%02d_%s" % (n, name[7:])))
+                elif n == 1 and name == "AUDIO_TS.IFO":
+                    shutil.move(os.path.join(tmp, name), os.path.join(directory, name))
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    # title set count: one byte of the manager file (reference dvd-audio.c:824-858)
+    path = os.path.join(directory, "AUDIO_TS.IFO")
+    data = bytearray(open(path, "rb").read())
+    data[63] = len(titlesets)
+    open(path, "wb").write(bytes(data))
+    return out

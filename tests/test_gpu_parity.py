@@ -118,6 +118,34 @@ def test_drop_in_dumper(pkg, oracle, disc_cache, tmp_path):
     assert tracks == GOLDEN["c5_mixed"]["tracks"]
 
 
+def test_several_title_sets(pkg, oracle, tmp_path):
+    """dvda_titleset_count / dvda_open_titleset(n) on a disc with three title sets, every
+    track of every set against the reference library through the same dumper."""
+    import dvda_gen as g
+    directory = str(tmp_path / "AUDIO_TS")
+    g.make_disc_multi(directory, [
+        [[g.pcm(3000, bps=16, seed=9001), g.mlp(4000, seed=9002, restart_interval=4)]],
+        [[g.mlp(5000, seed=9003, assignment=12, substreams=2, matrices=3, features=catalog.RICH, restart_interval=4)],
+         [g.pcm(2000, bps=24, assignment=3, seed=9004)]],
+        [[g.mlp(3000, rate=192000, seed=9005, restart_interval=8, features=g.CHECKDATA | g.MAX_ORDERS, fir_max=8, iir_max=4)]],
+    ])
+    disc = pkg.Disc(directory)
+    try:
+        assert disc.titleset_count() == 3
+    finally:
+        disc.close()
+    for ts in (1, 2, 3):
+        rc_r, tracks_r, pcm_r, err_r = oracle.run_dump(oracle.REF_DUMP, directory, str(tmp_path / ("ref%d.raw" % ts)), extra=("-s", str(ts)))
+        rc_b, tracks_b, pcm_b, err_b = oracle.run_dump(pkg.DUMP_BIN, directory, str(tmp_path / ("b200_%d.raw" % ts)), extra=("-s", str(ts)))
+        assert rc_r == 0, err_r
+        assert rc_b == 0, err_b
+        assert tracks_b == tracks_r and len(tracks_r) > 0
+        assert np.array_equal(pcm_b, pcm_r)
+    # a title set that does not exist
+    rc_b, _t, _p, _e = oracle.run_dump(pkg.DUMP_BIN, directory, extra=("-s", "4"))
+    assert rc_b != 0
+
+
 @pytest.mark.parametrize("name,offset", [("c2_mlp_2ch96", 20 * 2048 + 1000), ("c3_mlp_6ch96", 31 * 2048 + 700),
                                          ("c3_mlp_6ch96", 40 * 2048 + 1500)])
 def test_damage_is_caught_like_the_oracle(pkg, oracle, engine, disc_cache, name, offset):
