@@ -231,6 +231,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
     dist = None
+    # stdout carries exactly one line (rank 0's JSON): whatever libraries print while the job
+    # runs (NCCL's version banner, for one) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -353,9 +357,9 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "k_" + top, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": top_ms},
-                "roofline_step": {"achieved": alg_bytes * args.steps / (ms * 1e-3) / 1e9 / world, "unit": "GB/s",
-                                  "frac": alg_bytes * args.steps / (ms * 1e-3) / 1e9 / world / peak,
-                                  "note": "same algorithmic bytes over the whole device-resident step (all kernels)"},
+                "roofline_step": {"achieved": alg_bytes * args.steps / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                                  "frac": alg_bytes * args.steps / (ms * 1e-3) / 1e9 / peak,
+                                  "note": "same algorithmic bytes over the whole device-resident step (all kernels), per GPU"},
                 "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "clocks": clocks,
@@ -376,7 +380,10 @@ def main():
                     shutil.rmtree(ds, ignore_errors=True)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
                                         "sample": "%d s of the same stream shape, one process, dvda_read to memory" % sample_seconds}
-            print(json.dumps(line))
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
+            print(json.dumps(line), flush=True)
+            os.dup2(2, 1)
         eng.close()
     finally:
         shutil.rmtree(d, ignore_errors=True)
