@@ -71,7 +71,7 @@ enum {
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
     B_SS_FLAGS, B_SS_FLAGS_PREV, B_SS_FLAGS_FAST, B_FIR_TAIL,
     B_GROUPS, B_GRP_CELLS, B_CELL_BASE, B_GRP_CHUNKS, B_GRP_CHUNK_BASE,
-    B_DEC_WORK, B_AU_SNAP, B_FILT_SNAP, B_AU_FCHG, B_SEG_CTX, B_AU_DELTA, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
+    B_DEC_WORK, B_AU_SEG, B_AU_SNAP, B_FILT_SNAP, B_AU_FCHG, B_SEG_CTX, B_AU_DELTA, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
     B_COUNT
 };
 
@@ -528,21 +528,21 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         m.segs = c->buf[B_SEGS].as<SegDev>();
         uint32_t *seg_nau = c->buf[B_SEG_NAU].as<uint32_t>(), *seg_au_base = c->buf[B_SEG_AU_BASE].as<uint32_t>();
         TRY(launch_segment_fill(d_tracks, n_tracks, trk_seg_base, valid, m.segs, nseg, s));
-        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, nullptr, seg_au_base, 0, s));
+        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, nullptr, nullptr, seg_au_base, 0, s));
         TRY(scan_u32_to_u32(seg_nau, seg_au_base, nseg, tmp, tmp_bytes, s));
         TRY(read_back(c, seg_au_base + nseg, &nau));
         m.nau = nau;
         const size_t naua = (size_t)nau + 1;
-        ENSURE(B_AU_POS, naua * 8); ENSURE(B_AU_ERR, naua); ENSURE(B_AU, naua * sizeof(AuDev));
+        ENSURE(B_AU_POS, naua * 8); ENSURE(B_AU_ERR, naua); ENSURE(B_AU, naua * sizeof(AuDev)); ENSURE(B_AU_SEG, naua * 4);
         ENSURE(B_PSETS, naua * sizeof(ParamSet)); ENSURE(B_AU_FRAMES, naua * 2 * 4);
         ENSURE(B_SS_FLAGS, (size_t)nseg * 2 * 4); ENSURE(B_SS_FLAGS_PREV, (size_t)nseg * 2 * 4); ENSURE(B_SS_FLAGS_FAST, (size_t)nseg * 2 * 4);
         ENSURE(B_FIR_TAIL, (size_t)nseg * 2 * DVDA_MAX_CH * 8 * 4);
-        m.au_pos = c->buf[B_AU_POS].as<uint64_t>(); m.au_err = c->buf[B_AU_ERR].as<uint8_t>();
+        m.au_pos = c->buf[B_AU_POS].as<uint64_t>(); m.au_err = c->buf[B_AU_ERR].as<uint8_t>(); m.au_seg = c->buf[B_AU_SEG].as<uint32_t>();
         m.au = c->buf[B_AU].as<AuDev>(); m.psets = c->buf[B_PSETS].as<ParamSet>();
         m.au_frames_ss = c->buf[B_AU_FRAMES].as<uint32_t>();
         m.ss_flags = c->buf[B_SS_FLAGS].as<uint32_t>(); m.ss_flags_prev = c->buf[B_SS_FLAGS_PREV].as<uint32_t>(); m.ss_flags_fast = c->buf[B_SS_FLAGS_FAST].as<uint32_t>();
         m.fir_tail = c->buf[B_FIR_TAIL].as<int32_t>();
-        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, m.au_pos, seg_au_base, 1, s));
+        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, m.au_pos, m.au_seg, seg_au_base, 1, s));
         TRY(launch_yield(m, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), s));
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
 
@@ -579,6 +579,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             m.au_fchg = c->buf[B_AU_FCHG].as<uint8_t>();
             m.seg_ctx = reinterpret_cast<SegCtx *>(c->buf[B_SEG_CTX].p);
             m.au_delta = reinterpret_cast<AuDelta *>(c->buf[B_AU_DELTA].p);
+            // contexts exist only where pass A0 goes (substreams of up to four channels)
+            CUDA_TRY(cudaMemsetAsync(m.seg_ctx, 0, (size_t)nseg * 2 * seg_ctx_bytes(), s));
+            m.nss_max = 1;
+            for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].nseg && ht[i].nss > m.nss_max) m.nss_max = ht[i].nss;
         }
         for (int attempt = 0; attempt < 2; attempt++) {
             CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));

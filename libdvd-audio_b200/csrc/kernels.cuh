@@ -45,6 +45,8 @@ struct MlpTables {
     uint8_t *bypass;
     int32_t *pcm;
     AuSnap *au_snap;               // [2][nau]
+    uint32_t *au_seg;              // [nau]: segment of every access unit
+    uint32_t nss_max;              // most substreams in a track of the batch
     uint8_t *au_fchg;              // [2][nau]: bit cc = the filter set-up of channel cc changes with this access unit
     SegCtx *seg_ctx;               // [2][nseg]
     AuDelta *au_delta;             // [2][nau], written where the AU brings parameters
@@ -88,7 +90,7 @@ int launch_track_setup(TrackSetupArgs a, TrackDev *tracks, uint32_t n_tracks, cu
 int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_seg_base,
                         const uint64_t *valid, SegDev *segs, uint32_t nseg, cudaStream_t s);
 int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t nseg, const TrackDev *tracks,
-                    uint32_t *seg_nau, uint64_t *au_pos, const uint32_t *seg_au_base, int fill, cudaStream_t s);
+                    uint32_t *seg_nau, uint64_t *au_pos, uint32_t *au_seg, const uint32_t *seg_au_base, int fill, cudaStream_t s);
 int launch_yield(MlpTables m, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
                  uint8_t *pk_yield, cudaStream_t s);
 int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_grp_base, const SegDev *segs,

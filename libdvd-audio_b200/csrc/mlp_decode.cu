@@ -2075,17 +2075,20 @@ __global__ void __launch_bounds__(128) k_mlp_resolve(MlpTables m, const DecWork 
     if (!fast_job(m, work, n_work, warp, lane, job)) return;
     resolve_segment<NCH>(m, job);
 }
-// pass A1: one warp per (group, substream, access unit index), lane = segment
-__global__ void __launch_bounds__(GRD_THREADS) k_mlp_au_parse(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
+// pass A1: one thread per (access unit, substream), consecutive threads = consecutive access units
+__global__ void __launch_bounds__(GRD_THREADS) k_mlp_au_parse(MlpTables m)
 {
     __shared__ uint32_t window[GRD_WIN_WORDS * GRD_THREADS];
-    const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const uint32_t a = blockIdx.y;
-    if (warp >= n_warps) return;
+    const uint32_t A = blockIdx.x * GRD_THREADS + threadIdx.x, k = blockIdx.y;
+    if (A >= m.nau) return;
     DecodeJob job;
-    if (!fast_job(m, work, n_work, warp, lane, job)) return;
-    if (a >= m.segs[job.seg].n_au) return;
-    parse_au(m, job, a, window + threadIdx.x);
+    job.seg = m.au_seg[A];
+    job.k = k;
+    job.lane = 0;
+    job.exact_history = false;
+    const SegDev &S = m.segs[job.seg];
+    if (k >= m.tracks[S.track].nss) return;
+    parse_au(m, job, A - S.au_base, window + threadIdx.x);
 }
 
 // pass B: one warp per (group, substream, access unit index), lane = segment
@@ -2150,7 +2153,7 @@ static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t
     const uint32_t blocks = div_up_u32(n_warps, DEC_WARPS);
     const uint32_t small = div_up_u32(n_warps, 4);
     if (pass == 0) LAUNCH(k_mlp_segctx, small, 128, 0, s, m, work, n_work, n_warps);
-    else if (pass == 1) { if (m.max_au) LAUNCH(k_mlp_au_parse, dim3(small, m.max_au), 128, 0, s, m, work, n_work, n_warps); }
+    else if (pass == 1) return 0;                       // one launch for all classes, see launch_mlp_fast
     else if (pass == 2) LAUNCH(k_mlp_resolve<NCH>, small, 128, 0, s, m, work, n_work, n_warps);
     else if (pass == 3) LAUNCH(k_mlp_entropy<NCH>, dim3(blocks, m.max_au ? m.max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
     else LAUNCH(k_mlp_filter<NCH>, div_up_u32((uint64_t)n_warps * NCH, 4), 128, 0, s, m, work, n_work, n_warps);
@@ -2165,6 +2168,7 @@ int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_
     for (int pass = 0; pass < 5; pass++) {
         if (pass == 2) CUDA_TRY(cudaStreamWaitEvent(s, checked, 0));     // the resolve pass reads the check-data verdicts
         CUDA_TRY(cudaEventRecord(kev[slot[pass]][0], s));
+        if (pass == 1 && m.nau) LAUNCH(k_mlp_au_parse, dim3(div_up_u32(m.nau, GRD_THREADS), m.nss_max), GRD_THREADS, 0, s, m);
         if (launch_fast_pass<1>(pass, m, work[1], n_work[1], n_warps[1], s)) return -1;
         if (launch_fast_pass<2>(pass, m, work[2], n_work[2], n_warps[2], s)) return -1;
         if (launch_fast_pass<3>(pass, m, work[3], n_work[3], n_warps[3], s)) return -1;

@@ -381,7 +381,8 @@ int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_
 // (reference mlp.c:392-394).  Pass 1 counts, pass 2 (fill) records positions.
 __global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ segs, uint32_t nseg,
                            const TrackDev *__restrict__ tracks, uint32_t *__restrict__ seg_nau,
-                           uint64_t *__restrict__ au_pos, const uint32_t *__restrict__ seg_au_base, int fill)
+                           uint64_t *__restrict__ au_pos, uint32_t *__restrict__ au_seg,
+                           const uint32_t *__restrict__ seg_au_base, int fill)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nseg) return;
@@ -395,7 +396,7 @@ __global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ 
         const uint32_t total = (((ld_u8(es + pos) & 15u) << 8) | ld_u8(es + pos + 1)) * 2;
         if (total < 4) { stalled = true; break; }              // the reference's queue never advances again
         if (pos + total > limit) break;                        // incomplete (end of track) or overshoot
-        if (fill) au_pos[S.au_base + n] = pos;
+        if (fill) { au_pos[S.au_base + n] = pos; au_seg[S.au_base + n] = i; }
         pos += total;
         n++;
     }
@@ -412,10 +413,10 @@ __global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ 
 }
 
 int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t nseg, const TrackDev *tracks,
-                    uint32_t *seg_nau, uint64_t *au_pos, const uint32_t *seg_au_base, int fill, cudaStream_t s)
+                    uint32_t *seg_nau, uint64_t *au_pos, uint32_t *au_seg, const uint32_t *seg_au_base, int fill, cudaStream_t s)
 {
     if (!nseg) return 0;
-    LAUNCH(k_au_chase, div_up_u32(nseg, 128), 128, 0, s, es, segs, nseg, tracks, seg_nau, au_pos, seg_au_base, fill);
+    LAUNCH(k_au_chase, div_up_u32(nseg, 128), 128, 0, s, es, segs, nseg, tracks, seg_nau, au_pos, au_seg, seg_au_base, fill);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
