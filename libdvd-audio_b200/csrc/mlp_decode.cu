@@ -1179,8 +1179,8 @@ __device__ __forceinline__ uint32_t pack16(int32_t lo, int32_t hi) { return ((ui
 // decoding parameters of one block as a delta (mlp.c:856-993).  RESTART: the block
 // follows a restart header, where everything not transmitted falls back to its
 // default — the delta then states every field.
-template <bool RESTART, typename RD>
-__device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D)
+template <typename RD>
+__device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D, const bool RESTART)
 {
     uint32_t present = 0, block_size = 8, matrix_len = 0;
     uint32_t mo[2] = {0, 0}, mb[2] = {0, 0};                    // mat_out / mat_bypass bytes 0-3, 4-5
@@ -1198,20 +1198,20 @@ __device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D)
         matrix_len = rd_get(b, 4);
         if (matrix_len > DVDA_MAX_MAT || cx.mmc + 3 > DVDA_MAX_CH) return false;
         present |= AD_MATRIX;
-#pragma unroll
-        for (int k = 0; k < DVDA_MAX_MAT; k++) {
-            if ((uint32_t)k >= matrix_len) break;
+        // (rolled loops: matrices are rare next to filter parameters, and the kernel's code
+        // size matters — eight warps per scheduler run through different parts of it)
+#pragma unroll 1
+        for (uint32_t k = 0; k < matrix_len; k++) {
             const uint32_t out = rd_get(b, 4), frac = rd_get(b, 4);
             if (out > cx.mmc || frac > 14) return false;
             mo[k >> 2] |= out << (8 * (k & 3));
             mb[k >> 2] |= rd_get(b, 1) << (8 * (k & 3));
-            uint32_t row[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int c = 0; c < DVDA_MAX_CH; c++) {
-                if ((uint32_t)c < (uint32_t)cx.mmc + 3 && rd_get(b, 1))
-                    row[c >> 1] |= ((uint32_t)rd_get_s(b, frac + 2) << (14 - frac) & 0xFFFFu) << (16 * (c & 1));
+#pragma unroll 1
+            for (uint32_t c = 0; c < DVDA_MAX_CH; c++) {
+                int16_t v = 0;
+                if (c < (uint32_t)cx.mmc + 3 && rd_get(b, 1)) v = (int16_t)((uint32_t)rd_get_s(b, frac + 2) << (14 - frac));
+                D.coeff[k][c] = v;
             }
-            *reinterpret_cast<uint4 *>(&D.coeff[k][0]) = make_uint4(row[0], row[1], row[2], row[3]);
         }
     }
     if ((cx.flags & 0x20) && rd_get(b, 1)) {
@@ -1322,12 +1322,14 @@ __device__ __forceinline__ void parse_au(const MlpTables &m, const DecodeJob &jo
         if (a == 0) {
             // "parameters present", "restart header", the header itself (checked by pass A0)
             rd_skip(b, 2 + 113 + 6 * (cx.mmc + 1u) + 8);
-            state = parse_delta<true>(b, cx, D) ? 2 : 0;
+            state = 2;
         } else {
             state = 1;
             // a restart header here would start a new run of parameters: complete decoder
-            if (rd_get(b, 1)) state = (!rd_get(b, 1) && parse_delta<false>(b, cx, D)) ? 2 : 0;
+            if (rd_get(b, 1)) state = rd_get(b, 1) ? 0 : 2;
         }
+        // one call site: the parser is the bulk of this kernel's code
+        if (state == 2 && !parse_delta(b, cx, D, a == 0)) state = 0;
         if (rd_pos(b) > end_bits) state = 0;
         sn.bit0 = origin + rd_pos(b);
         sn.bit_end = origin + end_bits;
