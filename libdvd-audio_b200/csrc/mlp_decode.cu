@@ -350,9 +350,17 @@ __device__ __forceinline__ void grd_seat(GRd &r, uint64_t byte_pos)
 {
     r.next_w = r.base_w = (uint32_t)(byte_pos >> 2); r.win = 0; r.avail = 0;
 }
+// (out of line, arguments by value: the header parsers pull at some sixty places, and the size
+// of their code is what limits them)
+__device__ __noinline__ uint32_t grd_fetch_be(const uint32_t *col, uint32_t win_w0, const uint8_t *es, uint32_t w)
+{
+    const uint32_t i = w - win_w0;
+    const uint32_t v = i < GRD_WIN_WORDS ? col[i * GRD_THREADS] : __ldg(reinterpret_cast<const uint32_t *>(es) + w);
+    return __byte_perm(v, 0, 0x0123);
+}
 __device__ __forceinline__ void rd_pull(GRd &r)
 {
-    const uint32_t word = __byte_perm(grd_word(r, r.next_w), 0, 0x0123);
+    const uint32_t word = grd_fetch_be(r.col, r.win_w0, r.es, r.next_w);
     r.win |= (uint64_t)word << (32 - r.avail);
     r.avail += 32;
     r.next_w++;
