@@ -1398,55 +1398,63 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
         bool dirty = false;
         uint32_t chg = 0;                                 // channels whose filter set-up changes with this AU
         if (state == 2) {
-            const uint8_t *raw = reinterpret_cast<const uint8_t *>(u.v);
-            const uint32_t present = raw[offsetof(AuDelta, present)];
-            if (present & AD_BLOCK) block_size = *reinterpret_cast<const uint16_t *>(raw + offsetof(AuDelta, block_size));
+            // words of the head by compile-time index (they stay in registers)
+            uint32_t hw[20];
+#pragma unroll
+            for (int i = 0; i < 5; i++) { hw[4 * i] = u.v[i].x; hw[4 * i + 1] = u.v[i].y; hw[4 * i + 2] = u.v[i].z; hw[4 * i + 3] = u.v[i].w; }
+#define HEAD_U8(off) ((hw[(off) >> 2] >> (8 * ((off) & 3))) & 0xFFu)
+            const uint32_t present = HEAD_U8(offsetof(AuDelta, present));
+            if (present & AD_BLOCK) block_size = hw[0] & 0xFFFFu;
             if (present & AD_MATRIX) {
-                dirty = true; mat_src = A;
-                matrix_len = raw[offsetof(AuDelta, matrix_len)];
+                const uint32_t len_was = matrix_len;
+                mat_src = A;
+                matrix_len = HEAD_U8(offsetof(AuDelta, matrix_len));
+                if (len_was | matrix_len) dirty = true;       // "no matrices" re-stated changes nothing
                 want = 0;
 #pragma unroll
                 for (int k = 0; k < DVDA_MAX_MAT; k++)
-                    want |= ((uint32_t)k < matrix_len && raw[offsetof(AuDelta, mat_bypass) + k]) ? 1u << k : 0u;
+                    want |= ((uint32_t)k < matrix_len && HEAD_U8(offsetof(AuDelta, mat_bypass) + k)) ? 1u << k : 0u;
             }
             const uint64_t shift8_was = shift8;
             const uint32_t q8_was = q8;
             if (present & AD_SHIFT) {
 #pragma unroll
                 for (int c = 0; c < DVDA_MAX_CH; c++)
-                    if ((uint32_t)c <= cx.mmc) shift8 = (shift8 & ~(0xFFull << (8 * c))) | ((uint64_t)raw[offsetof(AuDelta, out_shift) + c] << (8 * c));
+                    if ((uint32_t)c <= cx.mmc) shift8 = (shift8 & ~(0xFFull << (8 * c))) | ((uint64_t)HEAD_U8(offsetof(AuDelta, out_shift) + c) << (8 * c));
             }
             if (present & AD_Q) {
 #pragma unroll
                 for (int c = 0; c < DVDA_MAX_CH; c++)
-                    if ((uint32_t)c <= cx.max_ch) q8 = (q8 & ~(15u << (4 * c))) | ((uint32_t)raw[offsetof(AuDelta, q) + c] << (4 * c));
+                    if ((uint32_t)c <= cx.max_ch) q8 = (q8 & ~(15u << (4 * c))) | (HEAD_U8(offsetof(AuDelta, q) + c) << (4 * c));
             }
             // re-stated values that did not change need no new parameter set
             if (shift8 != shift8_was || q8 != q8_was) dirty = true;
             if (q8 != q8_was) chg = (1u << NCH) - 1;
 #pragma unroll
             for (int cc = 0; cc < NCH; cc++) {
-                const uint8_t *h = raw + offsetof(AuDelta, ch) + cc * sizeof(ChanHead);
-                const uint32_t p = h[offsetof(ChanHead, present)];
+                const int o = (int)offsetof(AuDelta, ch) + cc * (int)sizeof(ChanHead);
+                const uint32_t p = HEAD_U8(o + offsetof(ChanHead, present));
                 if (!(p & CD_PRESENT)) continue;
-                if (p & CD_FIR) { fo[cc] = h[offsetof(ChanHead, fir_order)]; fs[cc] = h[offsetof(ChanHead, fir_shift)]; chg |= 1u << cc; }
+                if (p & CD_FIR) { fo[cc] = HEAD_U8(o + offsetof(ChanHead, fir_order)); fs[cc] = HEAD_U8(o + offsetof(ChanHead, fir_shift)); chg |= 1u << cc; }
                 if (p & CD_IIR) {
-                    io[cc] = h[offsetof(ChanHead, iir_order)]; is[cc] = h[offsetof(ChanHead, iir_shift)]; chg |= 1u << cc;
+                    io[cc] = HEAD_U8(o + offsetof(ChanHead, iir_order)); is[cc] = HEAD_U8(o + offsetof(ChanHead, iir_shift)); chg |= 1u << cc;
                     // the history is replaced by what was sent: too short = reference reads out of bounds (G2)
                     if (io[cc] && !(p & CD_IIR_STATE)) fallback = true;
                 }
-                if (p & CD_OFFSET) offset[cc] = *reinterpret_cast<const int32_t *>(h + offsetof(ChanHead, huff_offset));
-                cb[cc] = h[offsetof(ChanHead, codebook)]; lsbs[cc] = h[offsetof(ChanHead, huff_lsbs)];
+                if (p & CD_OFFSET) offset[cc] = (int32_t)hw[(o + offsetof(ChanHead, huff_offset)) >> 2];
+                cb[cc] = HEAD_U8(o + offsetof(ChanHead, codebook)); lsbs[cc] = HEAD_U8(o + offsetof(ChanHead, huff_lsbs));
             }
+#undef HEAD_U8
         }
         if (block_size > nominal || nominal % block_size) { fallback = true; break; }
 
-        // per-channel constants of the AU's blocks (mlp.c:1151-1176, 1260-1270)
-        struct { uint16_t block_size; uint8_t want, valid, min_ch, nch, has_matrix, pad1; ChanSnap ch[4]; } out;
-        out.block_size = (uint16_t)block_size; out.want = (uint8_t)want; out.valid = 1;
-        out.min_ch = cx.min_ch; out.nch = NCH; out.has_matrix = matrix_len != 0; out.pad1 = 0;
-#pragma unroll
-        for (int cc = 0; cc < 4; cc++) { out.ch[cc].sho = 0; out.ch[cc].cb = out.ch[cc].lsb_bits = out.ch[cc].q = out.ch[cc].shift = 0; }
+        // per-channel constants of the AU's blocks (mlp.c:1151-1176, 1260-1270), packed as the
+        // five 64-bit words behind the positions in the snapshot: block_size, want, valid, min_ch,
+        // nch, has_matrix, - | four times {sho, cb, lsb_bits, q, shift}
+        uint64_t ow[5];
+        ow[0] = (uint64_t)block_size | (uint64_t)want << 16 | 1ull << 24 | (uint64_t)cx.min_ch << 32 | (uint64_t)NCH << 40 |
+                (uint64_t)(matrix_len != 0) << 48;
+        ow[1] = ow[2] = ow[3] = ow[4] = 0;
 #pragma unroll
         for (int cc = 0; cc < NCH; cc++) {
             const uint32_t q = (q8 >> (4 * (cx.min_ch + cc))) & 15;
@@ -1466,17 +1474,18 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
                 if (!job.exact_history) flags |= SEG_WANTS_PREV;
                 fallback = true; break;
             }
-            out.ch[cc].sho = sho; out.ch[cc].cb = (uint8_t)cb[cc]; out.ch[cc].lsb_bits = (uint8_t)nb; out.ch[cc].q = (uint8_t)q;
-            out.ch[cc].shift = (uint8_t)((fs[cc] > 0 && is[cc] > 0) ? fs[cc] : fo[cc] > 0 ? fs[cc] : is[cc]);
+            const uint32_t shift = (fs[cc] > 0 && is[cc] > 0) ? fs[cc] : fo[cc] > 0 ? fs[cc] : is[cc];
+            ow[1 + cc] = (uint64_t)(uint32_t)sho | (uint64_t)(cb[cc] | nb << 8 | q << 16 | shift << 24) << 32;
         }
         if (fallback) break;
-        // bytes 16..55 of the snapshot (the positions in front are pass A0/A1's)
-        static_assert(sizeof(out) == 40 && offsetof(AuSnap, block_size) == 16 && sizeof(AuSnap) == 56, "AuSnap layout");
+        // bytes 16..55 of the snapshot (the positions in front are pass A1's)
+        static_assert(offsetof(AuSnap, block_size) == 16 && offsetof(AuSnap, want) == 18 && offsetof(AuSnap, valid) == 19 &&
+                      offsetof(AuSnap, min_ch) == 20 && offsetof(AuSnap, nch) == 21 && offsetof(AuSnap, has_matrix) == 22 &&
+                      offsetof(AuSnap, ch) == 24 && sizeof(ChanSnap) == 8 && sizeof(AuSnap) == 56, "AuSnap layout");
         {
-            const uint64_t *o = reinterpret_cast<const uint64_t *>(&out);
             uint64_t *dst = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(snaps + A) + 16);
 #pragma unroll
-            for (int i = 0; i < 5; i++) dst[i] = o[i];
+            for (int i = 0; i < 5; i++) dst[i] = ow[i];
         }
         fchg[A] = (uint8_t)chg;
 
