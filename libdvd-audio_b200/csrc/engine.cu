@@ -336,24 +336,37 @@ static int read_back(dvdagpu_ctx *c, const T *dev, T *host)
     return small_d2h(c, host, dev, sizeof(T));
 }
 
-// two read-backs, one round trip (each one costs tens of microseconds, more while bulk copies run)
+// several read-backs, one round trip (each one costs tens of microseconds, more while bulk copies run)
+static int small_d2h_multi(dvdagpu_ctx *c, int n, void *const host[], const void *const dev[], const size_t bytes[])
+{
+    size_t off[H2D_BATCH], total = 0;
+    bool ok = n <= H2D_BATCH;
+    for (int i = 0; i < n && ok; i++) {
+        off[i] = total;
+        total += (bytes[i] + 15) & ~(size_t)15;
+        if (bytes[i] & 3) ok = false;
+    }
+    if (!ok || total > MAP_BYTES / 2) {
+        for (int i = 0; i < n; i++) TRY(small_d2h(c, host[i], dev[i], bytes[i]));
+        return 0;
+    }
+    CopyBatch b;
+    b.n = (uint32_t)n;
+    for (int i = 0; i < n; i++) {
+        b.dst[i] = (uint32_t *)(c->dmap + MAP_BYTES / 2 + off[i]); b.src[i] = (const uint32_t *)dev[i]; b.nwords[i] = (uint32_t)(bytes[i] / 4);
+    }
+    LAUNCH(k_copy_multi, 1, 256, 0, c->stream, b);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++) memcpy(host[i], c->hmap + MAP_BYTES / 2 + off[i], bytes[i]);
+    return 0;
+}
 static int small_d2h_pair(dvdagpu_ctx *c, void *host_a, const void *dev_a, size_t bytes_a,
                           void *host_b, const void *dev_b, size_t bytes_b)
 {
-    const size_t off_b = (bytes_a + 15) & ~(size_t)15;
-    if (off_b + bytes_b > MAP_BYTES / 2 || ((bytes_a | bytes_b) & 3)) {
-        TRY(small_d2h(c, host_a, dev_a, bytes_a));
-        return small_d2h(c, host_b, dev_b, bytes_b);
-    }
-    CopyBatch b;
-    b.n = 2;
-    b.dst[0] = (uint32_t *)(c->dmap + MAP_BYTES / 2); b.src[0] = (const uint32_t *)dev_a; b.nwords[0] = (uint32_t)(bytes_a / 4);
-    b.dst[1] = (uint32_t *)(c->dmap + MAP_BYTES / 2 + off_b); b.src[1] = (const uint32_t *)dev_b; b.nwords[1] = (uint32_t)(bytes_b / 4);
-    LAUNCH(k_copy_multi, 1, 256, 0, c->stream, b);
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    memcpy(host_a, c->hmap + MAP_BYTES / 2, bytes_a);
-    memcpy(host_b, c->hmap + MAP_BYTES / 2 + off_b, bytes_b);
-    return 0;
+    void *const host[2] = {host_a, host_b};
+    const void *const dev[2] = {dev_a, dev_b};
+    const size_t bytes[2] = {bytes_a, bytes_b};
+    return small_d2h_multi(c, 2, host, dev, bytes);
 }
 
 static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n_sectors64,
@@ -530,7 +543,27 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         TRY(launch_segment_fill(d_tracks, n_tracks, trk_seg_base, valid, m.segs, nseg, s));
         TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, nullptr, nullptr, seg_au_base, 0, s));
         TRY(scan_u32_to_u32(seg_nau, seg_au_base, nseg, tmp, tmp_bytes, s));
-        TRY(read_back(c, seg_au_base + nseg, &nau));
+        // the groups (tile sizes) follow from the access-unit counts alone: set them up now and
+        // fetch all the sizes the next allocations need in one round trip
+        ENSURE(B_GROUPS, (size_t)ngroups * sizeof(GroupDev));
+        ENSURE(B_GRP_CELLS, (size_t)ngroups * 4); ENSURE(B_CELL_BASE, (size_t)(ngroups + 1) * 8);
+        ENSURE(B_GRP_CHUNKS, (size_t)ngroups * 4);
+        ENSURE(B_STATUS, 64);
+        m.groups = c->buf[B_GROUPS].as<GroupDev>();
+        uint32_t *grp_cells = c->buf[B_GRP_CELLS].as<uint32_t>(), *grp_chunks = c->buf[B_GRP_CHUNKS].as<uint32_t>();
+        uint64_t *cell_base = c->buf[B_CELL_BASE].as<uint64_t>();
+        uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
+        uint64_t cells = 0;
+        struct { uint32_t au, chunks; } most = {0, 0};
+        CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
+        TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, d_status + 1, s));
+        TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
+        {
+            void *const host[3] = {&nau, &cells, &most};
+            const void *const dev[3] = {seg_au_base + nseg, cell_base + ngroups, d_status + 1};
+            const size_t bytes[3] = {4, 8, sizeof most};
+            TRY(small_d2h_multi(c, 3, host, dev, bytes));
+        }
         m.nau = nau;
         const size_t naua = (size_t)nau + 1;
         ENSURE(B_AU_POS, naua * 8); ENSURE(B_AU_ERR, naua); ENSURE(B_AU, naua * sizeof(AuDev)); ENSURE(B_AU_SEG, naua * 4);
@@ -555,17 +588,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][1], c->aux_stream));
         c->kev_used[DVDAGPU_K_CHECKDATA] = true;
         CUDA_TRY(cudaEventRecord(c->aux_ev[1], c->aux_stream));
-        ENSURE(B_GROUPS, (size_t)ngroups * sizeof(GroupDev));
-        ENSURE(B_GRP_CELLS, (size_t)ngroups * 4); ENSURE(B_CELL_BASE, (size_t)(ngroups + 1) * 8);
-        ENSURE(B_GRP_CHUNKS, (size_t)ngroups * 4);
         ENSURE(B_SEG_FRAMES, (size_t)nseg * 4); ENSURE(B_SEG_FRAME_SCAN, (size_t)(nseg + 1) * 8);
-        ENSURE(B_STATUS, 64);
-        m.groups = c->buf[B_GROUPS].as<GroupDev>();
-        uint32_t *grp_cells = c->buf[B_GRP_CELLS].as<uint32_t>(), *grp_chunks = c->buf[B_GRP_CHUNKS].as<uint32_t>();
-        uint64_t *cell_base = c->buf[B_CELL_BASE].as<uint64_t>();
         uint32_t *seg_frames = c->buf[B_SEG_FRAMES].as<uint32_t>();
         uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
-        uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
 
         // The three-pass path (access-unit parallel) decodes what has the common shape; the complete
         // single-pass decoder takes the rest.  DVDAGPU_SINGLE_PASS=1 gives everything to the latter
@@ -585,12 +610,14 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].nseg && ht[i].nss > m.nss_max) m.nss_max = ht[i].nss;
         }
         for (int attempt = 0; attempt < 2; attempt++) {
-            CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
-            TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, d_status + 1, s));
-            TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
-            uint64_t cells = 0;
-            struct { uint32_t au, chunks; } most = {0, 0};
-            TRY(small_d2h_pair(c, &cells, cell_base + ngroups, 8, &most, d_status + 1, sizeof most));
+            if (attempt) {
+                // after a tile overflow: the groups again, from the frame counts now known
+                CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
+                TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, d_status + 1, s));
+                TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
+                TRY(small_d2h_pair(c, &cells, cell_base + ngroups, 8, &most, d_status + 1, sizeof most));
+            }
+            CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, s));         // (the maxima behind it stay)
             m.max_au = most.au; max_chunks = most.chunks;
             ENSURE(B_TILES, (cells * DVDA_LANES + 64 + 16 * DVDA_MAX_CH * DVDA_LANES) * sizeof(int32_t));   // 16 frames of slack: the filter passes read ahead
             ENSURE(B_BYPASS, cells * DVDA_LANES + 64);
