@@ -597,17 +597,18 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         // (the GPU tests run both ways).
         const bool use_fast = getenv("DVDAGPU_SINGLE_PASS") == nullptr;
         if (use_fast) {
-            ENSURE(B_AU_SNAP, naua * 2 * au_snap_bytes());
+            m.nss_max = 1;
+            for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].nseg && ht[i].nss > m.nss_max) m.nss_max = ht[i].nss;
+            // per-substream tables: [nss_max][nau] (the kernels index them as k * nau + A)
+            ENSURE(B_AU_SNAP, naua * m.nss_max * au_snap_bytes());
             m.au_snap = reinterpret_cast<AuSnap *>(c->buf[B_AU_SNAP].p);
-            ENSURE(B_AU_FCHG, naua * 2); ENSURE(B_SEG_CTX, (size_t)nseg * 2 * seg_ctx_bytes());
-            ENSURE(B_AU_DELTA, naua * 2 * au_delta_bytes());
+            ENSURE(B_AU_FCHG, naua * m.nss_max); ENSURE(B_SEG_CTX, (size_t)nseg * 2 * seg_ctx_bytes());
+            ENSURE(B_AU_DELTA, naua * m.nss_max * au_delta_bytes());
             m.au_fchg = c->buf[B_AU_FCHG].as<uint8_t>();
             m.seg_ctx = reinterpret_cast<SegCtx *>(c->buf[B_SEG_CTX].p);
             m.au_delta = reinterpret_cast<AuDelta *>(c->buf[B_AU_DELTA].p);
             // contexts exist only where pass A0 goes (substreams of up to four channels)
             CUDA_TRY(cudaMemsetAsync(m.seg_ctx, 0, (size_t)nseg * 2 * seg_ctx_bytes(), s));
-            m.nss_max = 1;
-            for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].nseg && ht[i].nss > m.nss_max) m.nss_max = ht[i].nss;
         }
         for (int attempt = 0; attempt < 2; attempt++) {
             if (attempt) {
