@@ -1,3 +1,8 @@
+"""Times the ways of decoding one long MLP track from host memory on a B200: plain decode +
+fetch, the copies alone, and dvdagpu_decode_track_pipelined with several part sizes.
+
+usage: python tools/time_pipe.py [seconds of audio]
+"""
 import importlib, os, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "gen"), os.path.join(ROOT, "oracle")):
