@@ -185,8 +185,13 @@ int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
 #ifndef DVDA_UNROLL
 #define DVDA_UNROLL 8
 #endif
+#ifndef RING_SLOTS
 #define RING_SLOTS 16                 // 16-byte slots per lane: 256 bytes
+#endif
+#ifndef CHUNK_WORDS
 #define CHUNK_WORDS 16                // 64 bytes per cp.async group
+#endif
+#define CHUNK_SLOTS (CHUNK_WORDS / 4)
 #define RING_WORDS (RING_SLOTS * 4)
 
 struct Rd {
@@ -212,11 +217,11 @@ __device__ __forceinline__ void rd_issue_chunk(Rd &r, uint32_t c)
 {
     const uint8_t *g = r.es + (uint64_t)c * (CHUNK_WORDS * 4);
 #pragma unroll
-    for (int t = 0; t < 4; t++) cp_async16(r.ring + (((c * 4 + t) & (RING_SLOTS - 1)) << 9), g + t * 16);
+    for (int t = 0; t < CHUNK_SLOTS; t++) cp_async16(r.ring + (((c * CHUNK_SLOTS + t) & (RING_SLOTS - 1)) << 9), g + t * 16);
 }
 // may chunk fill_c be written?  Its slot held chunk fill_c - 8, which must lie
 // entirely behind the read position (the slot held chunk fill_c - RING_CHUNKS).
-#define RING_CHUNKS (RING_SLOTS / 4)
+#define RING_CHUNKS (RING_SLOTS / CHUNK_SLOTS)
 __device__ __forceinline__ bool rd_room(const Rd &r) { return (int32_t)((r.fill_c - (RING_CHUNKS - 1)) * CHUNK_WORDS - r.next_w) <= 0; }
 
 __device__ __forceinline__ void rd_init(Rd &r, const uint8_t *es, uint32_t ring)
@@ -242,7 +247,9 @@ __device__ __forceinline__ void rd_prefetch(Rd &r, uint32_t need)
     const uint32_t landed = r.fill_c * CHUNK_WORDS;
 #pragma unroll
     for (int t = 0; t < 2; t++) {
-        if (r.fill_c * CHUNK_WORDS < r.next_w + RING_WORDS - CHUNK_WORDS && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
+#pragma unroll
+        for (int u = 0; u < 16 / CHUNK_WORDS; u++)
+            if (r.fill_c * CHUNK_WORDS < r.next_w + RING_WORDS - CHUNK_WORDS && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
         cp_commit();
     }
     cp_wait<2>();
