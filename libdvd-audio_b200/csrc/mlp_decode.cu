@@ -1144,7 +1144,7 @@ __device__ __forceinline__ bool au_seat(const MlpTables &m, const TrackDev &T, u
     grd_stage(b, m.es, col, au_pos);
     const AuLayout L = au_layout_from([&b, au_pos](uint32_t i) { return grd_byte(b, au_pos + i); }, T);
     // damage and the end-of-track rules are the complete decoder's business (check data runs
-    // beside this pass: the resolve pass looks at its verdicts)
+    // beside the passes; k_flag_damaged hands the segments it objects to over afterwards)
     if (!L.ok || au_pos + L.total > T.es_cut) return false;
     const uint32_t start = k ? L.end[0] : 0;
     const uint32_t len = L.end[k] - start - (L.chk0 ? 2 : 0);
@@ -1385,7 +1385,7 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
     Head nextv;
     uint32_t next_state = 0;
     if (S.n_au && !fallback) {
-        next_state = m.au_err[S.au_base] ? 0u : snaps[S.au_base].valid;
+        next_state = snaps[S.au_base].valid;
         const uint4 *src = reinterpret_cast<const uint4 *>(deltas + S.au_base);
 #pragma unroll
         for (int i = 0; i < 5; i++) nextv.v[i] = src[i];
@@ -1395,8 +1395,7 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
         const uint32_t state = next_state;
         Head u = nextv;
         if (a + 1 < S.n_au) {
-            // damaged or dropped access units (parity, CRC, changed stream parameters): complete decoder
-            next_state = m.au_err[A + 1] ? 0u : snaps[A + 1].valid;
+            next_state = snaps[A + 1].valid;
             const uint4 *src = reinterpret_cast<const uint4 *>(deltas + A + 1);
 #pragma unroll
             for (int i = 0; i < 5; i++) nextv.v[i] = src[i];
@@ -2163,6 +2162,15 @@ __global__ void k_flag_predecessors(MlpTables m)
     if (seg > T.seg_base) atomicOr(&m.ss_flags[k * m.nseg + seg - 1], SEG_FALLBACK);
 }
 
+__global__ void k_flag_damaged(MlpTables m)
+{
+    const uint32_t A = blockIdx.x * blockDim.x + threadIdx.x;
+    if (A >= m.nau || !m.au_err[A]) return;
+    const uint32_t seg = m.au_seg[A];
+    atomicOr(&m.ss_flags[seg], SEG_FALLBACK);
+    atomicOr(&m.ss_flags[m.nseg + seg], SEG_FALLBACK);
+}
+
 size_t au_snap_bytes() { return sizeof(AuSnap); }
 size_t seg_ctx_bytes() { return sizeof(SegCtx); }
 size_t au_delta_bytes() { return sizeof(AuDelta); }
@@ -2192,7 +2200,6 @@ int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_
     static const int slot[5] = {DVDAGPU_K_MLP_SEGCTX, DVDAGPU_K_MLP_AU_PARSE, DVDAGPU_K_MLP_RESOLVE, DVDAGPU_K_MLP_ENTROPY,
                                 DVDAGPU_K_MLP_FILTER};
     for (int pass = 0; pass < 5; pass++) {
-        if (pass == 2) CUDA_TRY(cudaStreamWaitEvent(s, checked, 0));     // the resolve pass reads the check-data verdicts
         CUDA_TRY(cudaEventRecord(kev[slot[pass]][0], s));
         if (pass == 1 && m.nau) LAUNCH(k_mlp_au_parse, dim3(div_up_u32(m.nau, GRD_THREADS), m.nss_max), GRD_THREADS, 0, s, m);
         if (launch_fast_pass<1>(pass, m, work[1], n_work[1], n_warps[1], s)) return -1;
@@ -2203,6 +2210,10 @@ int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_
         kev_used[slot[pass]] = true;
     }
     LAUNCH(k_flag_predecessors, div_up_u32((uint64_t)m.nseg * 2, 256), 256, 0, s, m);
+    // check data ran beside all this: segments with a damaged or dropped access unit (parity, CRC,
+    // changed stream parameters) go to the complete decoder, which knows where such a track ends
+    CUDA_TRY(cudaStreamWaitEvent(s, checked, 0));
+    if (m.nau) LAUNCH(k_flag_damaged, div_up_u32(m.nau, 256), 256, 0, s, m);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
