@@ -2373,6 +2373,25 @@ int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, const uin
 // length; a binary search covers the rest), and an AU whose parameters are
 // trivial — no matrix, no output shift, identity channel order — skips the
 // parameter set altogether: the kernel is then a pure transpose at HBM speed.
+// access unit holding frame F of a segment
+__device__ __forceinline__ AuDev au_of_frame(const MlpTables &m, const SegDev &S, uint32_t F, uint32_t nominal)
+{
+    const uint32_t n_ok = min(S.n_au, S.err_au);
+    const uint32_t ai = min(F / nominal, n_ok - 1);
+    AuDev au = m.au[S.au_base + ai];
+    if (F < au.frame0 || F >= au.frame0 + au.nframes) {
+        // irregular lengths or dropped AUs: last one with frame0 <= F (dropped AUs have no
+        // frames and share frame0 with their successor)
+        uint32_t lo = 0, hi = n_ok;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (m.au[S.au_base + mid].frame0 <= F) lo = mid; else hi = mid;
+        }
+        au = m.au[S.au_base + lo];
+    }
+    return au;
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
 {
@@ -2401,10 +2420,26 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
     }
     const uint8_t *bsrc = m.bypass + G.byp_off + (uint64_t)f0 * DVDA_LANES;
     for (uint32_t i = threadIdx.x; i < nf * 32; i += RM_THREADS) bsm[(i >> 5) * 33 + (i & 31)] = bsrc[i];
+    const uint32_t nominal = T.au_nominal;
+    // The noise generator steps once per frame from the seed at the start of the access unit.
+    // Its state at the first frame of the chunk is worked out once per segment here (up to an
+    // access unit of steps); a frame then needs at most 31 more.
+    __shared__ uint32_t chunk_seed[32];
+    if (threadIdx.x < G.nseg) {
+        const SegDev &S = m.segs[G.seg0 + threadIdx.x];
+        uint32_t seed = 0;
+        if (f0 < S.frames && min(S.n_au, S.err_au) > 0) {
+            const AuDev au = au_of_frame(m, S, f0, nominal);
+            if (m.psets[au.pset & 0x7FFFFFFFu].uses_noise) {
+                seed = au.seed;
+                for (uint32_t i = au.frame0; i < f0; i++) seed = noise_step(seed);
+            }
+        }
+        chunk_seed[threadIdx.x] = seed;
+    }
     __syncthreads();
 
     const uint32_t f = threadIdx.x & 31;                 // frame inside the chunk
-    const uint32_t nominal = T.au_nominal;
     const bool plain_order = !(T.assignment >= 0x12 && T.assignment <= 0x14);
     for (uint32_t l = threadIdx.x >> 5; l < G.nseg; l += RM_THREADS / 32) {
         const SegDev &S = m.segs[G.seg0 + l];
@@ -2412,20 +2447,7 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
         if (F >= S.frames) continue;
         // already written by the fused filter + output pass of the fast path?
         if (m.fast && T.nss == 1 && T.channels <= 4 && !(m.ss_flags_fast[G.seg0 + l] & SEG_FALLBACK)) continue;
-        // access unit holding frame F
-        const uint32_t n_ok = min(S.n_au, S.err_au);
-        uint32_t ai = min(F / nominal, n_ok - 1);
-        AuDev au = m.au[S.au_base + ai];
-        if (F < au.frame0 || F >= au.frame0 + au.nframes) {
-            // irregular lengths or dropped AUs: last one with frame0 <= F (dropped AUs have no
-            // frames and share frame0 with their successor)
-            uint32_t lo = 0, hi = n_ok;
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (m.au[S.au_base + mid].frame0 <= F) lo = mid; else hi = mid;
-            }
-            au = m.au[S.au_base + lo];
-        }
+        const AuDev au = au_of_frame(m, S, F, nominal);
         int32_t v[DVDA_MAX_CH];
 #pragma unroll
         for (uint32_t c = 0; c < DVDA_MAX_CH; c++) v[c] = (c < nch) ? sm[(c * 32 + f) * 33 + l] : 0;
@@ -2445,8 +2467,10 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
         if (ml) {
             int32_t n0 = 0, n1 = 0;
             if (P.uses_noise) {
-                uint32_t seed = au.seed;
-                for (uint32_t i = au.frame0; i < F; i++) seed = noise_step(seed);
+                // from the chunk's first frame if it lies in the same access unit, else from the unit's start
+                const bool same = au.frame0 <= f0;
+                uint32_t seed = same ? chunk_seed[l] : au.seed;
+                for (uint32_t i = same ? f0 : au.frame0; i < F; i++) seed = noise_step(seed);
                 const uint32_t sh = (seed >> 7) & 0xFFFF;
                 n0 = (int32_t)((uint32_t)(int32_t)(int8_t)(seed >> 15) << P.noise_shift);
                 n1 = (int32_t)((uint32_t)(int32_t)(int8_t)sh << P.noise_shift);
