@@ -80,21 +80,61 @@ def scratch_dir(tag):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region: NVML polled from a thread every
+    millisecond or so (the timed region is a few tens of milliseconds; `nvidia-smi -lms` is too
+    coarse for that and serves only as the fallback)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                   (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = False
+        self.thread = None
+        self.nvml = None
+
+    def _visible_index(self):
+        # NVML numbers the physical devices; CUDA_VISIBLE_DEVICES may remap them
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        bits = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for bit, name in self.REASON_BITS:
+                            if bits & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        break
+                    time.sleep(0.001)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -105,6 +145,13 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -123,7 +170,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_hbm_peak():
@@ -292,7 +339,6 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop()
 
         # ---- timed: end to end through the C ABI with host buffers
         if dist:
@@ -324,6 +370,7 @@ def main():
         # the copies run on the engine's own copy streams: take the larger of the event time on the
         # compute stream and the host wall time (every call returns only when its samples are in host memory)
         ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t_wall) * 1e3)
+        clocks = sampler.stop()                       # sampled across both timed regions (a query takes ~10 ms)
         # the two paths must agree with each other
         check = int(host_out[:: max(1, samples // 65536)].to(torch.int64).sum())
 
