@@ -109,6 +109,35 @@ def test_public_api(pkg, oracle, disc_cache, name):
     d.close()
 
 
+def test_readers_on_several_threads(pkg, oracle, disc_cache):
+    """Distinct track readers may be used from distinct threads (the reference keeps no
+    global state on the read path; here they share one engine behind a lock)."""
+    import threading
+    name = "c5_mixed"
+    directory, _ = disc_cache(name)
+    golden = GOLDEN[name]["tracks"]
+    failures = []
+
+    def work(tid):
+        try:
+            d = pkg.Disc(directory)
+            for rep in range(2):
+                for g in golden[tid::4]:
+                    info, pcm = d.read_track(g["title"], g["track"], chunk=2048 + 17 * tid)
+                    if len(pcm) != g["frames"] or oracle.fnv1a(pcm) != g["fnv"]:
+                        failures.append((tid, g["title"], g["track"]))
+            d.close()
+        except Exception as e:                      # noqa: BLE001 - reported below
+            failures.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not failures, failures
+
+
 def test_drop_in_dumper(pkg, oracle, disc_cache, tmp_path):
     """The api_dump program, linked against OUR library, prints what it prints when
     linked against the reference (golden records)."""
