@@ -53,8 +53,12 @@ __device__ __noinline__ bool sync_starts_segment(const uint8_t *es, uint64_t p, 
 // the ordered lists; a chunk with more matches than slots is searched again by its
 // thread (never seen outside of tests with synthetic pattern floods).
 #define SYNC_SLOTS 2
+#ifndef SYNC_WARPS
 #define SYNC_WARPS 8                  // warps per block
+#endif
+#ifndef SYNC_CHUNKS_PER_WARP
 #define SYNC_CHUNKS_PER_WARP 4
+#endif
 
 __global__ void __launch_bounds__(SYNC_WARPS * 32)
 k_sync_find(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t chunks, uint32_t *__restrict__ cnt_raw,
