@@ -107,12 +107,12 @@ enum {
     DVDAGPU_K_CARRY_FIX = 5,    /* segments needing the previous segment's FIR history */
     DVDAGPU_K_REMATRIX = 6,     /* matrices, bypass, shift, interleave */
     DVDAGPU_K_PCM_UNPACK = 7,
-    DVDAGPU_K_MLP_SEGCTX = 8,   /* three-pass path, A0: restart header + first access unit of every segment */
+    DVDAGPU_K_MLP_SEGCTX = 8,   /* three-pass path, A0: restart header of every segment -> parsing context */
     DVDAGPU_K_MLP_ENTROPY = 9,  /* three-pass path, B: residual entropy decode, one lane per access unit */
     DVDAGPU_K_MLP_FILTER = 10,  /* three-pass path, C: FIR/IIR prediction, one lane per channel (2 substreams) */
-    DVDAGPU_K_MLP_AU_PARSE = 12, /* three-pass path, A1: parameter block of every other access unit, as a delta */
-    DVDAGPU_K_MLP_RESOLVE = 13,  /* three-pass path, A2: parameter chain of every segment resolved per access unit */
-    DVDAGPU_K_MLP_FILTER_OUT = 11 /* three-pass path, single substream: prediction + rematrix + interleaved output */
+    DVDAGPU_K_MLP_FILTER_OUT = 11, /* three-pass path, C (1 substream): prediction + rematrix + interleaved output */
+    DVDAGPU_K_MLP_AU_PARSE = 12, /* three-pass path, A1: parameter block of every access unit, as a delta */
+    DVDAGPU_K_MLP_RESOLVE = 13   /* three-pass path, A2: parameter chain of every segment resolved per access unit */
 };
 
 /* number of CUDA devices the engine can use (0 = none) */
