@@ -1798,12 +1798,13 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
     constexpr int SPW = 32 / NCH;                        // segments per warp
     constexpr int SUB = (32 + SPW - 1) / SPW;            // warps per group
     constexpr int ROW = 32 * NCH + 4;                    // one segment's 32 frames (+4: rows stay 16-byte aligned, banks spread)
-    constexpr int WARP_WORDS = SPW * (ROW + 4);          // + per segment {output base lo, hi, frames, 16-byte aligned?}
+    constexpr int PATCH_WORDS = SPW * ROW;               // one patch; there are two, used in turn (bulk stores in flight)
+    constexpr int WARP_WORDS = 2 * PATCH_WORDS + SPW * 4; // + per segment {output base lo, hi, frames, 16-byte aligned?}
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * OUT_WARPS + wib;
     if (warp >= n_warps * SUB) return;
     int32_t *patch = out_sm + (size_t)wib * WARP_WORDS;
-    uint32_t *meta = reinterpret_cast<uint32_t *>(patch + SPW * ROW);
+    uint32_t *meta = reinterpret_cast<uint32_t *>(patch + 2 * PATCH_WORDS);
     const uint32_t gw = warp / SUB, sub = warp % SUB;
     // (group, substream) of this warp; only single-substream tracks are handled here
     uint32_t lo = 0, hi = n_work;
@@ -1858,29 +1859,38 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
     for (int j = 0; j < 8; j++) nx[j] = tp[j * tile_step];
     tp += 8 * tile_step;
 
+    // The patch of 32 frames leaves row by row (a row = 32 frames of a segment = 128 * NCH
+    // contiguous bytes of the output).  Whole, 16-byte aligned rows go out as bulk copies
+    // shared -> global, one instruction per row issued by the row's lane; the copy engine reads
+    // the patch while the warp fills the other one.  Ragged ends take plain stores.
     auto flush = [&](uint32_t f0) {
+        const int32_t *pb = patch + ((f0 >> 5) & 1) * PATCH_WORDS;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the parked samples, for the async proxy
         __syncwarp();
-        // The patch leaves as 16-byte pieces: piece q = row * (8 * NCH) + column, 32 pieces per
-        // step, so a step writes whole rows (32 frames of a segment = 128 * NCH contiguous bytes).
-        constexpr uint32_t ROW_QUADS = 8 * NCH, QUADS = SPW * ROW_QUADS;
-#pragma unroll
-        for (uint32_t t = 0; t < (QUADS + 31) / 32; t++) {
-            const uint32_t qd = t * 32 + lane, row = qd / ROW_QUADS, c4 = (qd % ROW_QUADS) * 4;
-            if (row >= (uint32_t)SPW) continue;
-            const uint4 mt = *reinterpret_cast<const uint4 *>(meta + row * 4);     // base lo, hi, frames, aligned
-            if (f0 >= mt.z) continue;
-            const int32_t *src = patch + row * ROW + c4;
-            int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * NCH) + c4;
-            const int4 v = *reinterpret_cast<const int4 *>(src);
-            if (f0 + 32 <= mt.z && mt.w) *reinterpret_cast<int4 *>(dst) = v;
-            else {
-                const uint32_t n = min(32u, mt.z - f0) * NCH;
-                if (c4 + 0 < n) dst[0] = v.x;
-                if (c4 + 1 < n) dst[1] = v.y;
-                if (c4 + 2 < n) dst[2] = v.z;
-                if (c4 + 3 < n) dst[3] = v.w;
+        uint32_t slow = 0;
+        if (lane < (uint32_t)SPW) {
+            const uint4 mt = *reinterpret_cast<const uint4 *>(meta + lane * 4);     // base lo, hi, frames, aligned
+            if (f0 < mt.z) {
+                if (f0 + 32 <= mt.z && mt.w) {
+                    int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * NCH);
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(pb + lane * ROW);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(dst), "r"(src), "n"(128 * NCH) : "memory");
+                } else slow = 1;
             }
         }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        uint32_t rows = __ballot_sync(0xFFFFFFFFu, slow);
+        while (rows) {
+            const uint32_t row = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const uint4 mt = *reinterpret_cast<const uint4 *>(meta + row * 4);
+            const uint32_t n = min(32u, mt.z - f0) * NCH;
+            int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * NCH);
+            for (uint32_t i = lane; i < n; i += 32) dst[i] = pb[row * ROW + i];
+        }
+        // the patch written one flush ago has been read by now: it is the one filled next
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
     };
 
@@ -1969,7 +1979,7 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
                 }
             }
             if (au_act) {
-                int32_t *pk = park + (f & 31) * NCH;
+                int32_t *pk = park + ((f >> 5) & 1) * PATCH_WORDS + (f & 31) * NCH;
 #pragma unroll
                 for (int j = 0; j < 8; j++) pk[j * NCH] = r[j];
             }
@@ -1978,6 +1988,7 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
         }
     }
     if (f & 31) flush(f & ~31u);
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory is given back at exit
     // FIR tail for a following segment that needs it
     if (mine) {
         int32_t *tail = m.fir_tail + (uint64_t)seg * (DVDA_MAX_CH * 8);
@@ -1991,7 +2002,7 @@ static int launch_one_filter_out(MlpTables m, const DecWork *work, uint32_t n_wo
 {
     if (!n_warps) return 0;
     constexpr int SPW = 32 / NCH, SUB = (32 + SPW - 1) / SPW;
-    const size_t smem = (size_t)OUT_WARPS * SPW * (32 * NCH + 4 + 4) * sizeof(int32_t);
+    const size_t smem = (size_t)OUT_WARPS * SPW * (2 * (32 * NCH + 4) + 4) * sizeof(int32_t);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
