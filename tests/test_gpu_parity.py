@@ -217,6 +217,30 @@ def test_large(pkg, oracle, engine, disc_cache, name):
         assert r.frames == g["frames"]
 
 
+def test_title_set_sharded_like_eight_ranks(pkg, oracle, engine, disc_cache):
+    """BASELINE.json configs[4]: the 64-track title set cut into 8 rank shards (shard.py, weights =
+    sectors per track).  Every shard is decoded by its own call, as a rank would, from the sector
+    window its tracks span; the union must be the reference's output for every track."""
+    import importlib
+    shard = importlib.import_module("libdvd-audio_b200.shard")
+    directory, _ = disc_cache("c5_titleset_64")
+    sectors = oracle.read_aobs(directory)
+    golden = GOLDEN["c5_titleset_64"]["tracks"]
+    assert len(golden) == 64
+    shards = shard.shard_tracks([g["last"] - g["first"] + 1 for g in golden], 8)
+    seen = []
+    for mine in shards:
+        assert mine
+        res = engine.decode_host(sectors, [(golden[i]["first"], golden[i]["last"], golden[i]["pts"]) for i in mine])
+        for r, i in zip(res, mine):
+            g = golden[i]
+            assert r.status == 0 and r.frames == g["frames"], (i, r.status, r.frames, g["frames"])
+            got = engine.fetch(r)
+            assert oracle.fnv1a(got) == g["fnv"], "track %d differs from the reference" % i
+            seen.append(i)
+    assert sorted(seen) == list(range(64))
+
+
 def test_device_resident_input(pkg, oracle, engine, disc_cache):
     """Sectors already in HBM (a torch tensor), engine on torch's stream."""
     import torch

@@ -11,7 +11,8 @@ import catalog
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = json.load(open(os.path.join(HERE, "golden", "catalog_golden.json")))
-CPU_DISCS = sorted(catalog.discs().keys())
+# the small catalog plus the 64-track title set of BASELINE.json configs[4] (scaled in length)
+CPU_DISCS = sorted(catalog.discs().keys()) + ["c5_titleset_64"]
 
 
 def oracle_tracks(oracle, directory, golden_tracks):
