@@ -205,10 +205,15 @@ __device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t *total)
 
 // ---- launch helpers (engine.cu counts launches for the stats) -------------
 extern thread_local uint32_t g_launch_count;
+// DVDAGPU_TRACE=1: an event behind every launch and the host time of its enqueue, printed as a
+// time line at the end of the decode (engine.cu)
+extern thread_local bool g_trace_on;
+void trace_mark(const char *what, cudaStream_t s);
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                         \
     do {                                                                       \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);            \
         g_launch_count++;                                                      \
+        if (g_trace_on) trace_mark(#kernel, (stream));                         \
     } while (0)
 
 static inline uint32_t div_up_u32(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }

@@ -26,6 +26,45 @@
 #define MAP_BYTES (1u << 20)      // mapped pinned staging area for small transfers
 
 thread_local uint32_t g_launch_count = 0;
+
+// ---- DVDAGPU_TRACE=1: time line of one decode (debug aid, not on by default) ---------------
+thread_local bool g_trace_on = false;
+#define TRACE_MAX 512
+struct TraceLog { int n; cudaEvent_t ev[TRACE_MAX]; const char *what[TRACE_MAX]; double host_us[TRACE_MAX]; bool gpu[TRACE_MAX]; int made; };
+static thread_local TraceLog g_trace = {0, {}, {}, {}, {}, 0};
+static double host_now_us()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+void trace_mark(const char *what, cudaStream_t s)
+{
+    TraceLog &t = g_trace;
+    if (t.n >= TRACE_MAX) return;
+    if (t.n >= t.made) { cudaEventCreate(&t.ev[t.n]); t.made = t.n + 1; }
+    t.what[t.n] = what; t.host_us[t.n] = host_now_us(); t.gpu[t.n] = s != (cudaStream_t)-1;
+    if (t.gpu[t.n]) cudaEventRecord(t.ev[t.n], s);
+    t.n++;
+}
+static void trace_host(const char *what) { if (g_trace_on) trace_mark(what, (cudaStream_t)-1); }
+static void trace_dump()
+{
+    TraceLog &t = g_trace;
+    if (t.n < 2) return;
+    cudaDeviceSynchronize();
+    int first_gpu = -1;
+    float prev = 0;
+    for (int i = 0; i < t.n; i++) {
+        if (!t.gpu[i]) { fprintf(stderr, "[trace] %-28s host %9.1f us\n", t.what[i], t.host_us[i] - t.host_us[0]); continue; }
+        if (first_gpu < 0) first_gpu = i;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t.ev[first_gpu], t.ev[i]);
+        fprintf(stderr, "[trace] %-28s host %9.1f us   done on device %9.1f us  (+%.1f)\n", t.what[i],
+                t.host_us[i] - t.host_us[0], ms * 1e3, (ms - prev) * 1e3);
+        prev = ms;
+    }
+}
 static thread_local char g_error[512] = "";
 
 void dvdagpu_set_error(const char *fmt, ...)
@@ -44,9 +83,11 @@ int upload_crc_table(const uint8_t *t);
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    uint32_t gen = 0;                         // counts allocations
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return 0;
+        gen++;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
@@ -82,6 +123,7 @@ struct dvdagpu_ctx {
     cudaStream_t h2d_stream, d2h_stream;      // copy engines of the pipelined path
     cudaStream_t aux_stream;                  // check data runs beside the header passes
     cudaEvent_t aux_ev[2];
+    uint32_t scan_tmp_gen = 0;                // allocation of the scan buffer that has been cleared
     cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
     int pcm_slot;                             // which PCM buffer the next decode writes
     uint8_t *hmap, *dmap;                     // mapped pinned staging area (host / device alias)
@@ -159,7 +201,13 @@ extern "C" dvdagpu_ctx *dvdagpu_create(int device)
     c->device = device;
     c->pcm_samples = 0;
     memset(&c->stats, 0, sizeof c->stats);
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // The decode chain runs at the highest stream priority, the side work (check data) at the
+    // lowest: blocks of the chain are placed first whenever an SM has room, so a large side
+    // kernel launched earlier fills the gaps instead of standing in front of the chain
+    // (measured on one box, bench step: 1.88 ms without priorities, 1.84 ms with).
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
         dvdagpu_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
         return nullptr;
@@ -175,7 +223,7 @@ extern "C" dvdagpu_ctx *dvdagpu_create(int device)
     }
     cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_least);
     for (auto &e : c->aux_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : c->pev) { cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming); }
     for (auto &e : c->ev) cudaEventCreate(&e);
@@ -282,6 +330,7 @@ static int small_d2h(dvdagpu_ctx *c, void *host, const void *dev, size_t bytes)
     // the upper half of the staging area is for read-backs
     LAUNCH(k_copy_words, 1, 256, 0, c->stream, (uint32_t *)(c->dmap + MAP_BYTES / 2), (const uint32_t *)dev, (uint32_t)(bytes / 4));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    trace_host("  (host has the read-back)");
     memcpy(host, c->hmap + MAP_BYTES / 2, bytes);
     return 0;
 }
@@ -357,6 +406,7 @@ static int small_d2h_multi(dvdagpu_ctx *c, int n, void *const host[], const void
     }
     LAUNCH(k_copy_multi, 1, 256, 0, c->stream, b);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    trace_host("  (host has the read-backs)");
     for (int i = 0; i < n; i++) memcpy(host[i], c->hmap + MAP_BYTES / 2 + off[i], bytes[i]);
     return 0;
 }
@@ -374,6 +424,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
 {
     g_error[0] = 0;
     g_launch_count = 0;
+    g_trace_on = getenv("DVDAGPU_TRACE") != nullptr;
+    g_trace.n = 0;
+    if (g_trace_on) trace_mark("decode begins", c->stream);
     c->map_used = 0;
     g_h2d_batch.n = 0;
     cudaStream_t s = c->stream;
@@ -406,6 +459,11 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     ENSURE(B_SCAN_TMP, scan_tmp_bytes((uint64_t)n_sectors * 2048 / 32 + 4096));
     void *tmp = c->buf[B_SCAN_TMP].p;
     const size_t tmp_bytes = c->buf[B_SCAN_TMP].cap;
+    if (c->scan_tmp_gen != c->buf[B_SCAN_TMP].gen) {
+        // the scans find their control words zero and leave them zero (scan.cu)
+        CUDA_TRY(cudaMemsetAsync(tmp, 0, tmp_bytes, s));
+        c->scan_tmp_gen = c->buf[B_SCAN_TMP].gen;
+    }
     uint32_t *sec_cnt = c->buf[B_SEC_CNT].as<uint32_t>(), *sec_bad = c->buf[B_SEC_BAD].as<uint32_t>();
     uint32_t *sec_base = c->buf[B_SEC_BASE].as<uint32_t>(), *bad_prefix = c->buf[B_BAD_PREFIX].as<uint32_t>();
     TRY(launch_sector_count(d_sectors, n_sectors, sec_cnt, sec_bad, s));
@@ -580,7 +638,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
 
         // ---------------- decode
-        // parity / CRC-8 on a second stream, beside the group set-up and the first header passes
+        // parity / CRC-8 on a second, low-priority stream, beside the group set-up and the header
+        // passes (starting it beside the entropy pass, or running it on its own in between, were
+        // measured too and cost more: DESIGN.md section 6)
         CUDA_TRY(cudaEventRecord(c->aux_ev[0], s));
         CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->aux_ev[0], 0));
         CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][0], c->aux_stream));
@@ -699,6 +759,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     if (any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, np, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));
     CUDA_TRY(cudaEventRecord(c->ev[4], s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    if (g_trace_on) { trace_host("decode done"); trace_dump(); g_trace_on = false; }
 
     // ---------------- results
     uint64_t es_used = 0;

@@ -85,82 +85,158 @@ __device__ AuLayout au_layout(const uint8_t *es, uint64_t pos, const TrackDev &T
 // One thread per access unit: parity and CRC-8 of each substream
 // (mlp.c:670-712, 1360-1399: parity over all bytes but the last two, CRC-8
 // (poly 0x63, start 0x3C) over the same bytes where the check byte is compared
-// with the value *in front of* the last table step).
-// The stream is read 16 bytes at a time; the CRC advances four bytes per step
-// with four 256-byte tables in shared memory (table k = "byte followed by k
-// zero bytes").  au_err: 0 ok, 1 = drop silently (stream parameters changed,
-// mlp.c:452-455), else ERR_* bits.
-#define CHK_THREADS 128
+// with the value *in front of* the last table step).  au_err: 0 ok, 1 = drop
+// silently (stream parameters changed, mlp.c:452-455), else ERR_* bits.
+//
+// The access units of a warp's 32 lanes follow each other in the elementary stream, so the
+// warp first copies their common byte range into its own window of shared memory (16-byte
+// asynchronous copies, coalesced: every byte of the stream crosses L1 once and DRAM traffic is
+// the stream itself), then every lane walks its own access unit there.  Lanes whose access
+// unit does not fit the window behind the first pending one wait for the next round.  A lane
+// works on four runs of 16-byte pieces at once (four independent table chains, four bytes per
+// step each) and joins them by carrying each run's state over the length of what follows it.
+// Tables: [0..3] "byte followed by k zero bytes", [4..11] "state carried over 16 << k zero bytes".
+__device__ __align__(16) uint8_t g_chk_tab[12][256];
+#define CHK_WARPS 4
+#define CHK_THREADS (CHK_WARPS * 32)
+#define CHK_WINDOW 16384          // bytes per warp; an access unit has at most 8190
+#define CHK_TAB_BYTES (12 * 256)
+#define CHK_SMEM_BYTES (CHK_TAB_BYTES + CHK_WARPS * CHK_WINDOW)
+__device__ __forceinline__ void chk_cp16(uint32_t smem, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
+}
 __global__ void __launch_bounds__(CHK_THREADS) k_checkdata(MlpTables m, const uint32_t *__restrict__ seg_au_base)
 {
-    __shared__ uint8_t T[4][256];
-    for (uint32_t i = threadIdx.x; i < 256; i += CHK_THREADS) {
-        const uint8_t t0 = c_crc8[i], t1 = c_crc8[t0], t2 = c_crc8[t1];
-        T[0][i] = t0; T[1][i] = t1; T[2][i] = t2; T[3][i] = c_crc8[t2];
-    }
+    extern __shared__ __align__(16) uint8_t chk_sm[];
+    uint8_t (*T)[256] = reinterpret_cast<uint8_t (*)[256]>(chk_sm);
+    uint8_t (*ADV)[256] = T + 4;
+    for (uint32_t i = threadIdx.x; i < CHK_TAB_BYTES / 16; i += CHK_THREADS)
+        reinterpret_cast<uint4 *>(chk_sm)[i] = reinterpret_cast<const uint4 *>(&g_chk_tab[0][0])[i];
     __syncthreads();
-#define CHK_WORD(wv)                                                                                       \
+#define CHK_STEP(c_, wv)                                                                                   \
     {                                                                                                      \
         const uint32_t w_ = (wv);                                                                          \
         pw ^= w_;                                                                                          \
-        crc = T[3][(crc ^ w_) & 0xFF] ^ T[2][(w_ >> 8) & 0xFF] ^ T[1][(w_ >> 16) & 0xFF] ^ T[0][w_ >> 24]; \
+        c_ = T[3][(c_ ^ w_) & 0xFF] ^ T[2][(w_ >> 8) & 0xFF] ^ T[1][(w_ >> 16) & 0xFF] ^ T[0][w_ >> 24];   \
     }
+#define CHK_WORD(wv) CHK_STEP(crc, wv)
+    // the state after `blocks` * 16 more zero bytes
+    auto carry = [&](uint32_t c, uint32_t blocks) {
+        for (uint32_t k = 0; blocks; k++, blocks >>= 1)
+            if (blocks & 1) c = ADV[k][c];
+        return c;
+    };
+    const uint32_t lane = threadIdx.x & 31;
+    uint8_t *const win = chk_sm + CHK_TAB_BYTES + (threadIdx.x >> 5) * CHK_WINDOW;
+    const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win);
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= m.nau) return;
-    const uint32_t si = upper_bound_dev(seg_au_base, m.nseg, a) - 1;
-    const TrackDev &Tr = m.tracks[m.segs[si].track];
-    const uint64_t pos = m.au_pos[a];
-    const AuLayout L = au_layout(m.es, pos, Tr);
-    uint32_t err = 0;
-    if (L.has_sync && L.params_differ) err = 1;
-    else if (!L.ok) err = ERR_SYNTAX;
-    else if (L.chk0) {
-        for (uint32_t k = 0; k < Tr.nss && !err; k++) {
-            const uint32_t start = k ? L.end[0] : 0;
-            const uint8_t *p = m.es + pos + L.data0 + start;
-            const uint32_t n = L.end[k] - start - 2;          // bytes covered
-            uint32_t parity = 0, crc = 0x3C, fin = 0;
-            if (n) {
-                // all bytes but the last advance the CRC; the last one only forms `fin`
-                const uint32_t body = n - 1;
-                uint32_t i = 0;
-                const uint32_t head = min(body, (uint32_t)((16 - ((uintptr_t)p & 15)) & 15));
-                for (; i < head; i++) { const uint32_t b = ld_u8(p + i); parity ^= b; crc = T[0][crc ^ b]; }
-                uint32_t pw = 0;
-                for (; i + 32 <= body; i += 32) {
-                    const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(p + i));
-                    const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(p + i + 16));
-                    CHK_WORD(v0.x) CHK_WORD(v0.y) CHK_WORD(v0.z) CHK_WORD(v0.w)
-                    CHK_WORD(v1.x) CHK_WORD(v1.y) CHK_WORD(v1.z) CHK_WORD(v1.w)
-                }
-                for (; i + 16 <= body; i += 16) {
-                    const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(p + i));
-                    CHK_WORD(v0.x) CHK_WORD(v0.y) CHK_WORD(v0.z) CHK_WORD(v0.w)
-                }
-                parity ^= (pw ^ (pw >> 8) ^ (pw >> 16) ^ (pw >> 24)) & 0xFF;
-                for (; i < body; i++) { const uint32_t b = ld_u8(p + i); parity ^= b; crc = T[0][crc ^ b]; }
-                const uint32_t last = ld_u8(p + body);
-                parity ^= last;
-                fin = crc ^ last;
-            }
-            if (((ld_u8(p + n) ^ parity) & 0xFF) != 0xA9) err = ERR_PARITY;
-            else if (ld_u8(p + n + 1) != fin) err = ERR_CRC;
-        }
+    const bool have = a < m.nau;
+    uint64_t pos = 0;
+    uint32_t total = 0;
+    if (have) {
+        pos = m.au_pos[a];
+        total = max(2u, (((ld_u8(m.es + pos) & 15u) << 8) | ld_u8(m.es + pos + 1)) * 2);
     }
-    m.au_err[a] = (uint8_t)err;
+    uint32_t pending = __ballot_sync(0xFFFFFFFFu, have);
+    while (pending) {
+        const int first = __ffs(pending) - 1;
+        const uint64_t base = __shfl_sync(0xFFFFFFFFu, pos, first) & ~15ull;
+        const bool fits = ((pending >> lane) & 1) && pos >= base && pos + total <= base + CHK_WINDOW;
+        const uint32_t now = __ballot_sync(0xFFFFFFFFu, fits);        // the first pending lane is always in
+        const uint32_t span = __reduce_max_sync(0xFFFFFFFFu, fits ? (uint32_t)(pos + total - base) : 0u);
+        const uint32_t n16 = (span + 15) >> 4;
+        const uint8_t *src = m.es + base;                             // (the pad behind the stream covers the round-up)
+        for (uint32_t i = lane; i < n16; i += 32) chk_cp16(win_s + i * 16, src + (uint64_t)i * 16);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (fits) {
+            const TrackDev &Tr = m.tracks[m.segs[m.au_seg[a]].track];
+            const uint8_t *au = win + (uint32_t)(pos - base);
+            const AuLayout L = au_layout_from([au](uint32_t i) { return (uint32_t)au[i]; }, Tr);
+            uint32_t err = 0;
+            if (L.has_sync && L.params_differ) err = 1;
+            else if (!L.ok) err = ERR_SYNTAX;
+            else if (L.chk0) {
+                for (uint32_t k = 0; k < Tr.nss && !err; k++) {
+                    const uint32_t start = k ? L.end[0] : 0;
+                    const uint8_t *p = au + L.data0 + start;          // same 16-byte phase as in the stream
+                    const uint32_t n = L.end[k] - start - 2;          // bytes covered
+                    uint32_t parity = 0, crc = 0x3C, fin = 0;
+                    if (n) {
+                        // all bytes but the last advance the CRC; the last one only forms `fin`
+                        const uint32_t body = n - 1;
+                        uint32_t i = 0;
+                        const uint32_t head = min(body, (uint32_t)((16 - ((uintptr_t)p & 15)) & 15));
+                        for (; i < head; i++) { const uint32_t b = p[i]; parity ^= b; crc = T[0][crc ^ b]; }
+                        uint32_t pw = 0;
+                        const uint32_t q = (body - i) >> 6;
+                        if (q) {
+                            uint32_t c1 = 0, c2 = 0, c3 = 0;
+                            const uint4 *r0 = reinterpret_cast<const uint4 *>(p + i);
+                            const uint4 *r1 = r0 + q, *r2 = r1 + q, *r3 = r2 + q;
+                            for (uint32_t j = 0; j < q; j++) {
+                                const uint4 v0 = r0[j], v1 = r1[j], v2 = r2[j], v3 = r3[j];
+                                CHK_STEP(crc, v0.x) CHK_STEP(c1, v1.x) CHK_STEP(c2, v2.x) CHK_STEP(c3, v3.x)
+                                CHK_STEP(crc, v0.y) CHK_STEP(c1, v1.y) CHK_STEP(c2, v2.y) CHK_STEP(c3, v3.y)
+                                CHK_STEP(crc, v0.z) CHK_STEP(c1, v1.z) CHK_STEP(c2, v2.z) CHK_STEP(c3, v3.z)
+                                CHK_STEP(crc, v0.w) CHK_STEP(c1, v1.w) CHK_STEP(c2, v2.w) CHK_STEP(c3, v3.w)
+                            }
+                            crc = carry(crc, q) ^ c1;
+                            crc = carry(crc, q) ^ c2;
+                            crc = carry(crc, q) ^ c3;
+                            i += q * 64;
+                        }
+                        for (; i + 16 <= body; i += 16) {
+                            const uint4 v0 = *reinterpret_cast<const uint4 *>(p + i);
+                            CHK_WORD(v0.x) CHK_WORD(v0.y) CHK_WORD(v0.z) CHK_WORD(v0.w)
+                        }
+                        parity ^= (pw ^ (pw >> 8) ^ (pw >> 16) ^ (pw >> 24)) & 0xFF;
+                        for (; i < body; i++) { const uint32_t b = p[i]; parity ^= b; crc = T[0][crc ^ b]; }
+                        const uint32_t last = p[body];
+                        parity ^= last;
+                        fin = crc ^ last;
+                    }
+                    if (((p[n] ^ parity) & 0xFF) != 0xA9) err = ERR_PARITY;
+                    else if (p[n + 1] != fin) err = ERR_CRC;
+                }
+            }
+            m.au_err[a] = (uint8_t)err;
+        }
+        pending &= ~now;
+        __syncwarp();                                                 // the window is overwritten by the next round
+    }
 #undef CHK_WORD
+#undef CHK_STEP
 }
 
 int upload_crc_table(const uint8_t *t)
 {
     CUDA_TRY(cudaMemcpyToSymbol(c_crc8, t, 256));
+    static uint8_t tab[12][256];
+    for (int i = 0; i < 256; i++) {
+        tab[0][i] = t[i];
+        for (int k = 1; k < 4; k++) tab[k][i] = t[tab[k - 1][i]];
+        uint8_t c = (uint8_t)i;
+        for (int z = 0; z < 16; z++) c = t[c];               // a zero byte: state -> t[state]
+        tab[4][i] = c;
+    }
+    for (int k = 5; k < 12; k++)
+        for (int i = 0; i < 256; i++) tab[k][i] = tab[k - 1][tab[k - 1][i]];
+    CUDA_TRY(cudaMemcpyToSymbol(g_chk_tab, tab, sizeof tab));
     return 0;
 }
 
 int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
 {
     if (!m.nau) return 0;
-    LAUNCH(k_checkdata, div_up_u32(m.nau, CHK_THREADS), CHK_THREADS, 0, s, m, seg_au_base);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_checkdata, cudaFuncAttributeMaxDynamicSharedMemorySize, CHK_SMEM_BYTES));
+        attr_set = true;
+    }
+    LAUNCH(k_checkdata, div_up_u32(m.nau, CHK_THREADS), CHK_THREADS, CHK_SMEM_BYTES, s, m, seg_au_base);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

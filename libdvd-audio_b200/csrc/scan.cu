@@ -1,9 +1,14 @@
 // scan.cu — exclusive prefix sums over the engine's index tables.
 //
 // The tables these run on (packets per sector, payload bytes per packet, syncs
-// per chunk, access units / frames per segment) are a few MB at most, so a plain
-// three-pass reduce / scan-of-sums / rescan is enough: every pass is coalesced
-// and the middle pass is one block.
+// per chunk, access units / frames per segment) are a few MB at most.  A scan
+// is one launch: every block sums its tile, publishes the sum, adds up the
+// sums its predecessors have published (one predecessor per thread, spinning
+// until it is there) and writes its tile's prefix sums.  Blocks number
+// themselves with a ticket as they start, so a block only ever waits for
+// blocks that are already running.  The last block to finish clears the
+// tickets and flags for the next scan; the control words must be zero before
+// the first one (the engine clears the buffer when it allocates it).
 #include "common.cuh"
 
 #define SCAN_THREADS 512
@@ -18,38 +23,7 @@ struct ScanBatch {
     uint32_t out64;                 // bit j: table j's prefix sums are 64-bit
 };
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(ScanBatch b, uint64_t n, uint64_t *__restrict__ sums, uint32_t nblocks)
-{
-    const uint32_t *__restrict__ in = b.in[blockIdx.y];
-    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
-    uint64_t v = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        const uint64_t i = base + (uint64_t)k * SCAN_THREADS + threadIdx.x;
-        if (i < n) v += in[i];
-    }
-    uint64_t total;
-    block_excl_scan<SCAN_THREADS>(v, &total);
-    if (threadIdx.x == 0) sums[(uint64_t)blockIdx.y * (nblocks + 2) + blockIdx.x] = total;
-}
-
-// one block per table: exclusive scan of the block sums in place, total behind them
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint64_t *all_sums, uint32_t nblocks)
-{
-    uint64_t *sums = all_sums + (uint64_t)blockIdx.x * (nblocks + 2);
-    uint64_t carry = 0;
-    for (uint32_t base = 0; base < nblocks; base += SCAN_THREADS) {
-        const uint32_t i = base + threadIdx.x;
-        const uint64_t v = i < nblocks ? sums[i] : 0;
-        uint64_t total;
-        const uint64_t ex = block_excl_scan<SCAN_THREADS>(v, &total);
-        if (i < nblocks) sums[i] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0) sums[nblocks] = carry;
-}
-
-// SINGLE: the table fits one tile, no block sums needed (one launch instead of three)
+// the table fits one tile (SINGLE): no block sums needed
 template <bool SINGLE>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(ScanBatch b, uint64_t n, const uint64_t *__restrict__ all_sums, uint32_t nblocks)
 {
@@ -86,9 +60,80 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(ScanBatch b, uint64
     }
 }
 
+// control words of one table: [0] next ticket, [1] blocks done, then per block {sum is there, sum}
+__device__ __forceinline__ uint64_t *scan_ctl(uint64_t *all, uint32_t table, uint32_t nblocks)
+{
+    return all + (uint64_t)table * (2 + 2 * (uint64_t)nblocks);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_chained(ScanBatch b, uint64_t n, uint64_t *__restrict__ ctl_all, uint32_t nblocks)
+{
+    __shared__ uint32_t s_ticket, s_last;
+    uint64_t *ctl = scan_ctl(ctl_all, blockIdx.y, nblocks);
+    volatile uint64_t *slots = ctl + 2;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(reinterpret_cast<unsigned int *>(ctl), 1u);
+    __syncthreads();
+    const uint32_t bid = s_ticket;
+    const uint32_t *__restrict__ in = b.in[blockIdx.y];
+    const uint64_t base = (uint64_t)bid * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t x[SCAN_ITEMS];
+    uint64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        x[k] = (base + k < n) ? in[base + k] : 0;
+        v += x[k];
+    }
+    uint64_t total;
+    uint64_t ex = block_excl_scan<SCAN_THREADS>(v, &total);
+    if (threadIdx.x == 0) {
+        slots[2 * bid + 1] = total;
+        __threadfence();
+        slots[2 * bid] = 1;
+    }
+    // the sums of all earlier tiles, one per thread (and per round of SCAN_THREADS tiles)
+    uint64_t before = 0;
+    for (int64_t j = (int64_t)bid - 1 - (int64_t)threadIdx.x; j >= 0; j -= SCAN_THREADS) {
+        while (slots[2 * j] == 0) __nanosleep(32);
+        __threadfence();
+        before += slots[2 * j + 1];
+    }
+    uint64_t before_all;
+    block_excl_scan<SCAN_THREADS>(before, &before_all);
+    ex += before_all;
+    if ((b.out64 >> blockIdx.y) & 1) {
+        uint64_t *out = static_cast<uint64_t *>(b.out[blockIdx.y]);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (base + k < n) out[base + k] = ex;
+            ex += x[k];
+        }
+        if (bid == nblocks - 1 && threadIdx.x == 0) out[n] = before_all + total;
+    } else {
+        uint32_t *out = static_cast<uint32_t *>(b.out[blockIdx.y]);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (base + k < n) out[base + k] = (uint32_t)ex;
+            ex += x[k];
+        }
+        if (bid == nblocks - 1 && threadIdx.x == 0) out[n] = (uint32_t)(before_all + total);
+    }
+    // whoever finishes last leaves the control words as they were found
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<unsigned int *>(ctl + 1), 1u) == nblocks - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        // (the sums too: the next scan may have another number of tiles and lay its words out differently)
+        for (uint32_t i = threadIdx.x; i < 2 * nblocks; i += SCAN_THREADS) slots[i] = 0;
+        if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = 0; }
+    }
+}
+
 size_t scan_tmp_bytes(uint64_t n)
 {
-    return (size_t)SCAN_MAX_JOBS * (div_up_u32(n ? n : 1, SCAN_TILE) + 2) * sizeof(uint64_t);
+    return (size_t)SCAN_MAX_JOBS * (2 * (size_t)div_up_u32(n ? n : 1, SCAN_TILE) + 2) * sizeof(uint64_t);
 }
 
 // exclusive prefix sums of njobs (<= 4) tables of n entries each; out[j] has n + 1 entries
@@ -110,9 +155,7 @@ int scan_batch(const uint32_t *const in[], void *const out[], const bool out64[]
     if (nblocks == 1) {
         LAUNCH(k_scan_apply<true>, dim3(1, njobs), SCAN_THREADS, 0, s, b, n, sums, nblocks);
     } else {
-        LAUNCH(k_scan_reduce, dim3(nblocks, njobs), SCAN_THREADS, 0, s, b, n, sums, nblocks);
-        LAUNCH(k_scan_sums, njobs, SCAN_THREADS, 0, s, sums, nblocks);
-        LAUNCH(k_scan_apply<false>, dim3(nblocks, njobs), SCAN_THREADS, 0, s, b, n, sums, nblocks);
+        LAUNCH(k_scan_chained, dim3(nblocks, njobs), SCAN_THREADS, 0, s, b, n, sums, nblocks);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
