@@ -419,6 +419,26 @@ static int small_d2h_pair(dvdagpu_ctx *c, void *host_a, const void *dev_a, size_
     return small_d2h_multi(c, 2, host, dev, bytes);
 }
 
+// Where every track's samples start in the output buffer (16-byte aligned tracks: vector and
+// bulk stores), computed on the device so that the output pass can be queued without a round
+// trip through the host.  `capacity`: samples the buffer was sized for in advance.
+#define OB_THREADS 256
+__global__ void __launch_bounds__(OB_THREADS) k_track_out_base(TrackDev *tracks, uint32_t n_tracks, uint32_t *status, uint64_t capacity)
+{
+    if (*status & SEG_OVERFLOW) return;
+    uint64_t carry = 0;
+    for (uint32_t base = 0; base < n_tracks; base += OB_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        uint64_t v = 0;
+        if (i < n_tracks && tracks[i].status == 0) v = tracks[i].frames * tracks[i].channels;
+        uint64_t total;
+        const uint64_t ex = block_excl_scan<OB_THREADS>((v + 3) & ~3ull, &total);
+        if (i < n_tracks) tracks[i].out_base = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && carry > capacity) atomicOr(status, STATUS_PCM_SMALL);
+}
+
 static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n_sectors64,
                             uint32_t n_tracks, const dvdagpu_track_desc *descs, dvdagpu_track_result *results)
 {
@@ -593,6 +613,14 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     m.tracks = d_tracks; m.n_tracks = n_tracks; m.nseg = nseg; m.ngroups = ngroups;
     uint32_t nau = 0;
     uint32_t max_chunks = 0, status = 0;
+    ENSURE(B_STATUS, 64);
+    uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
+    m.status = d_status;
+    // samples of the PCM tracks (known since the track set-up) and the alignment gaps
+    uint64_t pcm_fixed = 4ull * n_tracks + 64;
+    for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].status == 0 && ht[i].codec == 0) pcm_fixed += ht[i].frames * ht[i].channels;
+    const int pcm_buf = c->pcm_slot ? B_PCM2 : B_PCM;
+    bool out_queued = false;
     if (nseg) {
         ENSURE(B_SEGS, (size_t)nseg * sizeof(SegDev));
         ENSURE(B_SEG_NAU, (size_t)nseg * 4); ENSURE(B_SEG_AU_BASE, (size_t)(nseg + 1) * 4);
@@ -606,11 +634,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         ENSURE(B_GROUPS, (size_t)ngroups * sizeof(GroupDev));
         ENSURE(B_GRP_CELLS, (size_t)ngroups * 4); ENSURE(B_CELL_BASE, (size_t)(ngroups + 1) * 8);
         ENSURE(B_GRP_CHUNKS, (size_t)ngroups * 4);
-        ENSURE(B_STATUS, 64);
         m.groups = c->buf[B_GROUPS].as<GroupDev>();
         uint32_t *grp_cells = c->buf[B_GRP_CELLS].as<uint32_t>(), *grp_chunks = c->buf[B_GRP_CHUNKS].as<uint32_t>();
         uint64_t *cell_base = c->buf[B_CELL_BASE].as<uint64_t>();
-        uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
         uint64_t cells = 0;
         struct { uint32_t au, chunks; } most = {0, 0};
         CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
@@ -705,15 +731,28 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             // after an overflow they are simply computed again
             TRY(scan_u32_to_u64(seg_frames, seg_frame_scan, nseg, tmp, tmp_bytes, s));
             TRY(launch_track_finalize(m, seg_frame_scan, d_status, s));
+            // The output buffer is sized before the frame counts are known (every MLP sample has a
+            // place in the tiles, so the tiles' size bounds them), the tracks' places in it are
+            // computed on the device, and the fused output pass of the fast path is queued right
+            // here: the round trip below then costs the device nothing.
+            const uint64_t pcm_capacity = cells * DVDA_LANES + pcm_fixed;
+            ENSURE(pcm_buf, (pcm_capacity + 64) * sizeof(int32_t));
+            m.pcm = c->buf[pcm_buf].as<int32_t>();
+            LAUNCH(k_track_out_base, 1, OB_THREADS, 0, s, d_tracks, n_tracks, d_status, pcm_capacity);
+            CUDA_TRY(cudaEventRecord(c->ev[3], s));
+            out_queued = m.fast != 0;
+            if (out_queued) TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
             TRY(small_d2h_pair(c, &status, d_status, 4, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
             if (!(status & SEG_OVERFLOW)) break;
             if (attempt == 1) { dvdagpu_set_error("tile overflow persists"); return -1; }
         }
     } else {
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
+        CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, s));
+        LAUNCH(k_track_out_base, 1, OB_THREADS, 0, s, d_tracks, n_tracks, d_status, pcm_fixed);
         TRY(small_d2h(c, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
+        CUDA_TRY(cudaEventRecord(c->ev[3], s));
     }
-    CUDA_TRY(cudaEventRecord(c->ev[3], s));
     if (getenv("DVDAGPU_DEBUG")) {
         fprintf(stderr, "[dvdagpu] sectors=%u packets=%u es=%llu raw=%u valid=%u segs=%u groups=%u aus=%u\n",
                 n_sectors, np, (unsigned long long)es_total, n_raw, n_valid, nseg, ngroups, nau);
@@ -742,16 +781,19 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].status == 0 && ht[i].codec == 1) mlp_channel_mask |= 1u << ht[i].channels;
     for (uint32_t i = 0; i < n_tracks; i++) {
         total_samples = (total_samples + 3) & ~3ull;          // 16-byte aligned tracks (vector stores)
-        ht[i].out_base = total_samples;
+        if (ht[i].out_base != total_samples) { dvdagpu_set_error("internal: output layout"); return -1; }   // k_track_out_base
         if (ht[i].status == 0) total_samples += ht[i].frames * ht[i].channels;
         any_pcm |= ht[i].status == 0 && ht[i].codec == 0;
     }
-    const int pcm_buf = c->pcm_slot ? B_PCM2 : B_PCM;
     ENSURE(pcm_buf, (total_samples + 64) * sizeof(int32_t));
     m.pcm = c->buf[pcm_buf].as<int32_t>();
     c->pcm_samples = total_samples;
-    TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
-    if (nseg && m.fast) {
+    if (status & STATUS_PCM_SMALL) {
+        // (does not happen as long as the tiles bound the samples; the buffer has its real size now)
+        CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, s));
+        out_queued = false;
+    }
+    if (nseg && m.fast && !out_queued) {
         // fast path, single-substream tracks: filters + rematrix + interleaved output in one pass
         TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
     }

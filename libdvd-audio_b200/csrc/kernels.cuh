@@ -52,6 +52,7 @@ struct MlpTables {
     AuDelta *au_delta;             // [2][nau], written where the AU brings parameters
     uint32_t fast;                 // 1: the complete decoder only takes segments flagged SEG_FALLBACK
     uint32_t max_au;               // largest access-unit count of a segment
+    const uint32_t *status;        // the batch's status word (SEG_OVERFLOW, STATUS_*)
 };
 
 // demux.cu

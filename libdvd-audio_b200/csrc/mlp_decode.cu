@@ -1879,6 +1879,9 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * OUT_WARPS + wib;
     if (warp >= n_warps * SUB) return;
+    // queued before the host has seen the batch's status: nothing to do if the batch is decoded
+    // once more (tile overflow) or the output buffer sized in advance turned out too small
+    if (*m.status & (SEG_OVERFLOW | STATUS_PCM_SMALL)) return;
     int32_t *patch = out_sm + (size_t)wib * WARP_WORDS;
     uint32_t *meta = reinterpret_cast<uint32_t *>(patch + 2 * PATCH_WORDS);
     const uint32_t gw = warp / SUB, sub = warp % SUB;
