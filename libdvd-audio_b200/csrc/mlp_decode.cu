@@ -1640,6 +1640,53 @@ __device__ __forceinline__ void filt_take_delta(const AuDelta &D, uint32_t cc, u
         }
     }
 }
+// The same with the head fields already in registers (the fused output pass loads them one
+// access unit ahead): only the 64 bytes of coefficients and histories are fetched here, with
+// four independent loads.
+struct DeltaHead { uint32_t fchg, w0, qv, h1, h2, seed, pset; };
+__device__ __forceinline__ DeltaHead filt_load_head(const MlpTables &m, const AuDelta *deltas, uint32_t A, uint32_t cc, uint32_t c)
+{
+    DeltaHead H;
+    const AuDelta &D = deltas[A];
+    H.fchg = m.au_fchg[A];
+    H.w0 = *reinterpret_cast<const uint32_t *>(&D);                  // block_size, present, matrix_len
+    H.qv = D.q[c];
+    const uint32_t *hw = reinterpret_cast<const uint32_t *>(&D.ch[cc]);
+    H.h1 = hw[1]; H.h2 = hw[2];
+    const uint2 sp = *reinterpret_cast<const uint2 *>(&m.au[A].seed);
+    H.seed = sp.x; H.pset = sp.y;
+    return H;
+}
+__device__ __forceinline__ void filt_take_head(const DeltaHead &H, const AuDelta &D, uint32_t cc, FiltSetup &F,
+                                               int32_t (&cf)[8], int32_t (&ci)[8], int32_t (&ih)[8])
+{
+    const uint32_t h1 = H.h1, p = (H.h2 >> 16) & 0xFF;
+    if ((H.w0 >> 16) & AD_Q) F.q = H.qv;
+    if (!(p & (CD_FIR | CD_IIR))) return;
+    const uint4 *kw = reinterpret_cast<const uint4 *>(&D.cf[cc]);
+    const uint4 s0 = kw[0], s1 = kw[1], fc = kw[2], ic = kw[3];
+    if (p & CD_FIR) {
+        F.fo = h1 & 0xFF; F.fsh = (h1 >> 8) & 0xFF;
+        const uint32_t w[4] = {fc.x, fc.y, fc.z, fc.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
+            cf[j] = (uint32_t)j < F.fo ? v : 0;
+        }
+    }
+    if (p & CD_IIR) {
+        F.io = (h1 >> 16) & 0xFF; F.ish = h1 >> 24;
+        const uint32_t w[4] = {ic.x, ic.y, ic.z, ic.w};
+        const int32_t st[8] = {(int32_t)s0.x, (int32_t)s0.y, (int32_t)s0.z, (int32_t)s0.w,
+                               (int32_t)s1.x, (int32_t)s1.y, (int32_t)s1.z, (int32_t)s1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
+            ci[j] = (uint32_t)j < F.io ? v : 0;
+            ih[j] = ((p & CD_IIR_STATE) && (uint32_t)j < F.io) ? st[j] : 0;
+        }
+    }
+}
 __device__ __forceinline__ uint32_t filt_shift(const FiltSetup &F)
 {
     return (F.fsh > 0 && F.ish > 0) ? F.fsh : F.fo > 0 ? F.fsh : F.ish;
@@ -1973,27 +2020,30 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
         __syncwarp();
     };
 
+    // the head of the access unit that comes next is always in registers already: what a lane
+    // waits for at the top of an access unit is one round of four independent 16-byte loads
+    // (prefetched into L1), not a chain of dependent ones
+    DeltaHead H = filt_load_head(m, deltas, mine ? S.au_base : 0, cc, c0 + cc);
     while (f < max_frames) {
         // ---- next access unit: this channel's filter parameters, the frame's rematrix parameters
         const bool au_act = f < my_frames;
         if (au_act) {
             const uint32_t A = S.au_base + a;
-            // the next access unit's records, on their way while this one is filtered
-            prefetch_l1(&deltas[A + 1].ch[cc]); prefetch_l1(&deltas[A + 1].cf[cc]);
-            prefetch_l1(reinterpret_cast<const uint8_t *>(&deltas[A + 1].cf[cc]) + 32);
-            prefetch_l1(&m.au[A + 1]);
-            if ((m.au_fchg[A] >> cc) & 1) {
-                filt_take_delta(deltas[A], cc, c0 + cc, F, cf, ci, ih);
+            const uint32_t An = min(A + 1, m.nau);           // (the tables have one spare entry)
+            prefetch_l1(&deltas[An].cf[cc]);
+            prefetch_l1(reinterpret_cast<const uint8_t *>(&deltas[An].cf[cc]) + 32);
+            if ((H.fchg >> cc) & 1) {
+                filt_take_head(H, deltas[A], cc, F, cf, ci, ih);
                 shift = filt_shift(F); qmask = 0xFFFFFFFFu << F.q;
                 cls = F.fo | F.io << 4;
             }
-            const AuDev au = m.au[A];
-            seed = au.seed;
-            if (au.pset != pset) {
-                pset = au.pset;
+            seed = H.seed;
+            if (H.pset != pset) {
+                pset = H.pset;
                 P = &m.psets[pset & 0x7FFFFFFFu];
                 trivial = (pset & 0x80000000u) && plain_order;
             }
+            H = filt_load_head(m, deltas, An, cc, c0 + cc);
         } else {
             cls = 0;
 #pragma unroll
@@ -2280,6 +2330,7 @@ static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t
     else if (pass == 1) return 0;                       // one launch for all classes, see launch_mlp_fast
     else if (pass == 2) LAUNCH(k_mlp_resolve<NCH>, small, 128, 0, s, m, work, n_work, n_warps);
     else if (pass == 3) LAUNCH(k_mlp_entropy<NCH>, dim3(blocks, m.max_au ? m.max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
+    else if (m.nss_max < 2) return 0;                   // only tracks with two substreams are filtered by this pass
     else LAUNCH(k_mlp_filter<NCH>, div_up_u32((uint64_t)n_warps * NCH, 4), 128, 0, s, m, work, n_work, n_warps);
     return 0;
 }
