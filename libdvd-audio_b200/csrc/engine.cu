@@ -123,6 +123,7 @@ struct dvdagpu_ctx {
     cudaStream_t h2d_stream, d2h_stream;      // copy engines of the pipelined path
     cudaStream_t aux_stream;                  // check data runs beside the header passes
     cudaEvent_t aux_ev[2];
+    cudaStream_t aux_stream_hi = nullptr;     // side stream at the chain's own priority
     uint32_t scan_tmp_gen = 0;                // allocation of the scan buffer that has been cleared
     cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
     int pcm_slot;                             // which PCM buffer the next decode writes
@@ -224,6 +225,7 @@ extern "C" dvdagpu_ctx *dvdagpu_create(int device)
     cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_least);
+    cudaStreamCreateWithPriority(&c->aux_stream_hi, cudaStreamNonBlocking, prio_greatest);
     for (auto &e : c->aux_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : c->pev) { cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming); }
     for (auto &e : c->ev) cudaEventCreate(&e);
@@ -248,6 +250,7 @@ extern "C" void dvdagpu_destroy(dvdagpu_ctx *c)
     cudaStreamDestroy(c->h2d_stream);
     cudaStreamDestroy(c->d2h_stream);
     cudaStreamDestroy(c->aux_stream);
+    if (c->aux_stream_hi) cudaStreamDestroy(c->aux_stream_hi);
     for (auto &e : c->aux_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -664,16 +667,20 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
 
         // ---------------- decode
-        // parity / CRC-8 on a second, low-priority stream, beside the group set-up and the header
-        // passes (starting it beside the entropy pass, or running it on its own in between, were
-        // measured too and cost more: DESIGN.md section 6)
+        // Parity / CRC-8 on a second stream, beside the group set-up and the header passes.  Small
+        // access units: the windowed kernel on the low-priority stream (it fills what the chain
+        // leaves free).  Large ones: the direct kernel at the chain's own priority, which then runs
+        // first and lets the header passes follow.  Both pairings, and starting the check beside the
+        // entropy pass or on its own in between, were measured: DESIGN.md section 6.
+        // (a caller's stream has the default = lowest priority, like aux_stream)
+        cudaStream_t chk_stream = (checkdata_windowed(m) || s != c->own_stream) ? c->aux_stream : c->aux_stream_hi;
         CUDA_TRY(cudaEventRecord(c->aux_ev[0], s));
-        CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->aux_ev[0], 0));
-        CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][0], c->aux_stream));
-        TRY(launch_checkdata(m, seg_au_base, c->aux_stream));
-        CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][1], c->aux_stream));
+        CUDA_TRY(cudaStreamWaitEvent(chk_stream, c->aux_ev[0], 0));
+        CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][0], chk_stream));
+        TRY(launch_checkdata(m, seg_au_base, chk_stream));
+        CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][1], chk_stream));
         c->kev_used[DVDAGPU_K_CHECKDATA] = true;
-        CUDA_TRY(cudaEventRecord(c->aux_ev[1], c->aux_stream));
+        CUDA_TRY(cudaEventRecord(c->aux_ev[1], chk_stream));
         ENSURE(B_SEG_FRAMES, (size_t)nseg * 4); ENSURE(B_SEG_FRAME_SCAN, (size_t)(nseg + 1) * 8);
         uint32_t *seg_frames = c->buf[B_SEG_FRAMES].as<uint32_t>();
         uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();

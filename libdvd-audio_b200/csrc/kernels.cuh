@@ -100,6 +100,7 @@ int launch_group_offsets(GroupDev *groups, uint32_t ngroups, const uint64_t *cel
 
 // mlp_decode.cu
 int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s);
+bool checkdata_windowed(const MlpTables &m);     // which of the two kernels launch_checkdata picks
 // a run of decode warps: the groups of substream k of one track
 struct DecWork { uint32_t warp0, track, k, pad; };
 int launch_mlp_decode(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s);

@@ -211,6 +211,70 @@ __global__ void __launch_bounds__(CHK_THREADS) k_checkdata(MlpTables m, const ui
 #undef CHK_STEP
 }
 
+// The same check with every lane reading its access unit straight from the elementary stream,
+// 16 bytes at a time: for large access units (few of them fit a window, so the windowed kernel
+// above runs many rounds with most lanes idle) this is the faster one.
+#define CHKD_THREADS 128
+__global__ void __launch_bounds__(CHKD_THREADS) k_checkdata_direct(MlpTables m, const uint32_t *__restrict__ seg_au_base)
+{
+    __shared__ uint8_t T[4][256];
+    for (uint32_t i = threadIdx.x; i < 256; i += CHKD_THREADS) {
+        const uint8_t t0 = c_crc8[i], t1 = c_crc8[t0], t2 = c_crc8[t1];
+        T[0][i] = t0; T[1][i] = t1; T[2][i] = t2; T[3][i] = c_crc8[t2];
+    }
+    __syncthreads();
+#define CHK_WORD(wv)                                                                                       \
+    {                                                                                                      \
+        const uint32_t w_ = (wv);                                                                          \
+        pw ^= w_;                                                                                          \
+        crc = T[3][(crc ^ w_) & 0xFF] ^ T[2][(w_ >> 8) & 0xFF] ^ T[1][(w_ >> 16) & 0xFF] ^ T[0][w_ >> 24]; \
+    }
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= m.nau) return;
+    const uint32_t si = upper_bound_dev(seg_au_base, m.nseg, a) - 1;
+    const TrackDev &Tr = m.tracks[m.segs[si].track];
+    const uint64_t pos = m.au_pos[a];
+    const AuLayout L = au_layout(m.es, pos, Tr);
+    uint32_t err = 0;
+    if (L.has_sync && L.params_differ) err = 1;
+    else if (!L.ok) err = ERR_SYNTAX;
+    else if (L.chk0) {
+        for (uint32_t k = 0; k < Tr.nss && !err; k++) {
+            const uint32_t start = k ? L.end[0] : 0;
+            const uint8_t *p = m.es + pos + L.data0 + start;
+            const uint32_t n = L.end[k] - start - 2;          // bytes covered
+            uint32_t parity = 0, crc = 0x3C, fin = 0;
+            if (n) {
+                // all bytes but the last advance the CRC; the last one only forms `fin`
+                const uint32_t body = n - 1;
+                uint32_t i = 0;
+                const uint32_t head = min(body, (uint32_t)((16 - ((uintptr_t)p & 15)) & 15));
+                for (; i < head; i++) { const uint32_t b = ld_u8(p + i); parity ^= b; crc = T[0][crc ^ b]; }
+                uint32_t pw = 0;
+                for (; i + 32 <= body; i += 32) {
+                    const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(p + i));
+                    const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(p + i + 16));
+                    CHK_WORD(v0.x) CHK_WORD(v0.y) CHK_WORD(v0.z) CHK_WORD(v0.w)
+                    CHK_WORD(v1.x) CHK_WORD(v1.y) CHK_WORD(v1.z) CHK_WORD(v1.w)
+                }
+                for (; i + 16 <= body; i += 16) {
+                    const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(p + i));
+                    CHK_WORD(v0.x) CHK_WORD(v0.y) CHK_WORD(v0.z) CHK_WORD(v0.w)
+                }
+                parity ^= (pw ^ (pw >> 8) ^ (pw >> 16) ^ (pw >> 24)) & 0xFF;
+                for (; i < body; i++) { const uint32_t b = ld_u8(p + i); parity ^= b; crc = T[0][crc ^ b]; }
+                const uint32_t last = ld_u8(p + body);
+                parity ^= last;
+                fin = crc ^ last;
+            }
+            if (((ld_u8(p + n) ^ parity) & 0xFF) != 0xA9) err = ERR_PARITY;
+            else if (ld_u8(p + n + 1) != fin) err = ERR_CRC;
+        }
+    }
+    m.au_err[a] = (uint8_t)err;
+#undef CHK_WORD
+}
+
 int upload_crc_table(const uint8_t *t)
 {
     CUDA_TRY(cudaMemcpyToSymbol(c_crc8, t, 256));
@@ -228,9 +292,18 @@ int upload_crc_table(const uint8_t *t)
     return 0;
 }
 
+// access units of up to this many bytes on average go through the shared-memory windows
+#define CHK_WINDOWED_MAX_AU 512
+bool checkdata_windowed(const MlpTables &m) { return m.nau && m.es_total / m.nau <= CHK_WINDOWED_MAX_AU; }
+
 int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
 {
     if (!m.nau) return 0;
+    if (!checkdata_windowed(m)) {
+        LAUNCH(k_checkdata_direct, div_up_u32(m.nau, CHKD_THREADS), CHKD_THREADS, 0, s, m, seg_au_base);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_checkdata, cudaFuncAttributeMaxDynamicSharedMemorySize, CHK_SMEM_BYTES));
