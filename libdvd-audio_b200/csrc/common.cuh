@@ -222,6 +222,7 @@ static inline uint32_t div_up_u32(uint64_t a, uint64_t b) { return (uint32_t)((a
 // exclusive scans (scan.cu): out has n + 1 entries, out[n] = total
 int scan_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t s);
 int scan_u32_to_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t s);
+// total_copy (may be null): per table, a second place for its total, e.g. mapped host memory
 int scan_batch(const uint32_t *const in[], void *const out[], const bool out64[], int njobs, uint64_t n,
-               void *tmp, size_t tmp_bytes, cudaStream_t s);
+               void *tmp, size_t tmp_bytes, cudaStream_t s, uint64_t *const total_copy[] = nullptr);
 size_t scan_tmp_bytes(uint64_t n);

@@ -382,6 +382,17 @@ static int small_h2d(dvdagpu_ctx *c, void *dev, const void *host, size_t bytes)
     return flush_h2d(c);
 }
 
+// Totals the scans leave in the mapped staging area themselves (scan_batch's total_copy): slot j
+// as the device sees it, and the host's read once the stream has drained.
+static uint64_t *mapped_total_slot(dvdagpu_ctx *c, int j) { return reinterpret_cast<uint64_t *>(c->dmap + MAP_BYTES / 2) + j; }
+static int mapped_totals(dvdagpu_ctx *c, int n, uint64_t *host)
+{
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    trace_host("  (host has the totals)");
+    for (int j = 0; j < n; j++) host[j] = reinterpret_cast<volatile uint64_t *>(c->hmap + MAP_BYTES / 2)[j];
+    return 0;
+}
+
 template <typename T>
 static int read_back(dvdagpu_ctx *c, const T *dev, T *host)
 {
@@ -492,10 +503,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     TRY(launch_sector_count(d_sectors, n_sectors, sec_cnt, sec_bad, s));
     {
         const uint32_t *in[2] = {sec_cnt, sec_bad}; void *out[2] = {sec_base, bad_prefix}; const bool wide[2] = {false, false};
-        TRY(scan_batch(in, out, wide, 2, n_sectors, tmp, tmp_bytes, s));
+        uint64_t *const copy[2] = {mapped_total_slot(c, 0), nullptr};
+        TRY(scan_batch(in, out, wide, 2, n_sectors, tmp, tmp_bytes, s, copy));
     }
-    uint32_t np = 0;
-    TRY(read_back(c, sec_base + n_sectors, &np));
+    uint64_t total1 = 0;
+    TRY(mapped_totals(c, 1, &total1));
+    const uint32_t np = (uint32_t)total1;
 
     const size_t npa = (size_t)np + 1;
     ENSURE(B_PK_SECTOR, npa * 4); ENSURE(B_PK_OFF, npa * 2); ENSURE(B_PK_LEN, npa * 2);
@@ -518,10 +531,11 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         const uint32_t *in[4] = {pt.mlp_len, pt.pcm_frames, nonmlp, pstop};
         void *out[4] = {pk_es, pk_pf, nm_prefix, stop_prefix};
         const bool wide[4] = {true, true, false, false};
-        TRY(scan_batch(in, out, wide, 4, np, tmp, tmp_bytes, s));
+        uint64_t *const copy[4] = {mapped_total_slot(c, 0), nullptr, nullptr, nullptr};
+        TRY(scan_batch(in, out, wide, 4, np, tmp, tmp_bytes, s, copy));
     }
     uint64_t es_total = 0;
-    TRY(read_back(c, pk_es + np, &es_total));
+    TRY(mapped_totals(c, 1, &es_total));
 
     ENSURE(B_ES, es_total + DVDA_ES_PAD);
     uint8_t *es = c->buf[B_ES].as<uint8_t>();
@@ -543,8 +557,11 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     if (es_total) {
         TIMED(DVDAGPU_K_SYNC_SCAN, launch_sync_count(es, es_total, cnt_raw, cnt_valid, sync_slots, nslots, s));
         const uint32_t *in[2] = {cnt_raw, cnt_valid}; void *out[2] = {base_raw, base_valid}; const bool wide[2] = {false, false};
-        TRY(scan_batch(in, out, wide, 2, chunks, tmp, tmp_bytes, s));
-        TRY(small_d2h_pair(c, &n_raw, base_raw + chunks, 4, &n_valid, base_valid + chunks, 4));
+        uint64_t *const copy[2] = {mapped_total_slot(c, 0), mapped_total_slot(c, 1)};
+        TRY(scan_batch(in, out, wide, 2, chunks, tmp, tmp_bytes, s, copy));
+        uint64_t totals[2] = {0, 0};
+        TRY(mapped_totals(c, 2, totals));
+        n_raw = (uint32_t)totals[0]; n_valid = (uint32_t)totals[1];
     }
     ENSURE(B_RAW, ((size_t)n_raw + 1) * 8); ENSURE(B_VALID, ((size_t)n_valid + 1) * 8);
     uint64_t *raw = c->buf[B_RAW].as<uint64_t>(), *valid = c->buf[B_VALID].as<uint64_t>();

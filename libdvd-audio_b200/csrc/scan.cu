@@ -21,6 +21,7 @@ struct ScanBatch {
     const uint32_t *in[SCAN_MAX_JOBS];
     void *out[SCAN_MAX_JOBS];
     uint32_t out64;                 // bit j: table j's prefix sums are 64-bit
+    uint64_t *total_copy[SCAN_MAX_JOBS];   // where else to leave table j's total (mapped host memory), or null
 };
 
 // the table fits one tile (SINGLE): no block sums needed
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(ScanBatch b, uint64
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = (uint32_t)grand;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && b.total_copy[blockIdx.y]) *b.total_copy[blockIdx.y] = grand;
 }
 
 // control words of one table: [0] next ticket, [1] blocks done, then per block {sum is there, sum}
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chained(ScanBatch b, uint
         }
         if (bid == nblocks - 1 && threadIdx.x == 0) out[n] = (uint32_t)(before_all + total);
     }
+    if (bid == nblocks - 1 && threadIdx.x == 0 && b.total_copy[blockIdx.y]) *b.total_copy[blockIdx.y] = before_all + total;
     // whoever finishes last leaves the control words as they were found
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -138,7 +141,7 @@ size_t scan_tmp_bytes(uint64_t n)
 
 // exclusive prefix sums of njobs (<= 4) tables of n entries each; out[j] has n + 1 entries
 int scan_batch(const uint32_t *const in[], void *const out[], const bool out64[], int njobs, uint64_t n,
-               void *tmp, size_t tmp_bytes, cudaStream_t s)
+               void *tmp, size_t tmp_bytes, cudaStream_t s, uint64_t *const total_copy[])
 {
     if (njobs < 1 || njobs > SCAN_MAX_JOBS || tmp_bytes < scan_tmp_bytes(n)) {
         dvdagpu_set_error("scan: bad batch or temporary buffer too small");
@@ -149,6 +152,7 @@ int scan_batch(const uint32_t *const in[], void *const out[], const bool out64[]
     for (int j = 0; j < SCAN_MAX_JOBS; j++) {
         b.in[j] = in[j < njobs ? j : 0]; b.out[j] = out[j < njobs ? j : 0];
         if (j < njobs && out64[j]) b.out64 |= 1u << j;
+        b.total_copy[j] = (j < njobs && total_copy) ? total_copy[j] : nullptr;
     }
     uint64_t *sums = (uint64_t *)tmp;
     const uint32_t nblocks = div_up_u32(n ? n : 1, SCAN_TILE);
@@ -164,10 +168,10 @@ int scan_batch(const uint32_t *const in[], void *const out[], const bool out64[]
 int scan_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t s)
 {
     const uint32_t *i[1] = {in}; void *o[1] = {out}; const bool w[1] = {true};
-    return scan_batch(i, o, w, 1, n, tmp, tmp_bytes, s);
+    return scan_batch(i, o, w, 1, n, tmp, tmp_bytes, s, nullptr);
 }
 int scan_u32_to_u32(const uint32_t *in, uint32_t *out, uint64_t n, void *tmp, size_t tmp_bytes, cudaStream_t s)
 {
     const uint32_t *i[1] = {in}; void *o[1] = {out}; const bool w[1] = {false};
-    return scan_batch(i, o, w, 1, n, tmp, tmp_bytes, s);
+    return scan_batch(i, o, w, 1, n, tmp, tmp_bytes, s, nullptr);
 }
