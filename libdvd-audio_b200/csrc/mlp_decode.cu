@@ -2096,12 +2096,13 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
     // the head of the access unit that comes next is always in registers already: what a lane
     // waits for at the top of an access unit is one round of four independent 16-byte loads
     // (prefetched into L1), not a chain of dependent ones
-    DeltaHead H = filt_load_head(m, deltas, mine ? S.au_base : 0, cc, c0 + cc);
+    const uint32_t au_base = mine ? S.au_base : 0;       // (a register: S lives in global memory)
+    DeltaHead H = filt_load_head(m, deltas, au_base, cc, c0 + cc);
     while (f < max_frames) {
         // ---- next access unit: this channel's filter parameters, the frame's rematrix parameters
         const bool au_act = f < my_frames;
         if (au_act) {
-            const uint32_t A = S.au_base + a;
+            const uint32_t A = au_base + a;
             const uint32_t An = min(A + 1, m.nau);           // (the tables have one spare entry)
             prefetch_l1(&deltas[An].cf[cc]);
             prefetch_l1(reinterpret_cast<const uint8_t *>(&deltas[An].cf[cc]) + 32);
