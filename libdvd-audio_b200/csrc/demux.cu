@@ -89,8 +89,9 @@ __device__ __forceinline__ uint32_t channels_of(uint32_t a)
 }
 
 // one thread per sector: rows of the packet table
+// (`rows`: rows the table has room for — it is sized before the packet count is known to the host)
 __global__ void k_packet_fill(const uint8_t *__restrict__ sectors, uint32_t n_sectors,
-                              const uint32_t *__restrict__ sec_base, PacketTable pt)
+                              const uint32_t *__restrict__ sec_base, PacketTable pt, uint32_t rows)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_sectors) return;
@@ -127,6 +128,7 @@ __global__ void k_packet_fill(const uint8_t *__restrict__ sectors, uint32_t n_se
         } else {
             codec = 0xFF;
         }
+        if (i >= rows) break;                        // the host grows the table and comes back
         pt.sector[i] = s;
         pt.off[i] = (uint16_t)(payload + hdr);
         pt.len[i] = (uint16_t)rest;
@@ -140,10 +142,14 @@ __global__ void k_packet_fill(const uint8_t *__restrict__ sectors, uint32_t n_se
 }
 
 // per-packet flags that feed the prefix counts used by track setup
-__global__ void k_packet_flags(PacketTable pt, uint32_t np, uint32_t *__restrict__ nonmlp, uint32_t *__restrict__ pcm_stop)
+// (runs over all rows of the table; the ones behind the last packet are cleared so that the prefix
+// sums over the whole table end in the right totals)
+__global__ void k_packet_flags(PacketTable pt, uint32_t rows, const uint32_t *__restrict__ np_dev,
+                               uint32_t *__restrict__ nonmlp, uint32_t *__restrict__ pcm_stop)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= np) return;
+    if (i >= rows) return;
+    if (i >= *np_dev) { pt.mlp_len[i] = 0; pt.pcm_frames[i] = 0; nonmlp[i] = 0; pcm_stop[i] = 0; return; }
     nonmlp[i] = pt.codec[i] != CODEC_MLP;
     // a PCM track stops in front of a packet that is not PCM, changes the stream
     // parameters or holds no whole chunk (reference dvd-audio.c:1042-1056, 770-774)
@@ -261,11 +267,11 @@ int launch_sector_count(const uint8_t *sectors, uint32_t n_sectors, uint32_t *se
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_t *sec_base, PacketTable pt, uint32_t np,
+int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_t *sec_base, PacketTable pt, uint32_t rows,
                        uint32_t *nonmlp, uint32_t *pcm_stop, cudaStream_t s)
 {
-    LAUNCH(k_packet_fill, div_up_u32(n_sectors, 128), 128, 0, s, sectors, n_sectors, sec_base, pt);
-    if (np) LAUNCH(k_packet_flags, div_up_u32(np, 256), 256, 0, s, pt, np, nonmlp, pcm_stop);
+    LAUNCH(k_packet_fill, div_up_u32(n_sectors, 128), 128, 0, s, sectors, n_sectors, sec_base, pt, rows);
+    if (rows) LAUNCH(k_packet_flags, div_up_u32(rows, 256), 256, 0, s, pt, rows, sec_base + n_sectors, nonmlp, pcm_stop);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -124,6 +124,7 @@ struct dvdagpu_ctx {
     cudaStream_t aux_stream;                  // check data runs beside the header passes
     cudaEvent_t aux_ev[2];
     cudaStream_t aux_stream_hi = nullptr;     // side stream at the chain's own priority
+    uint32_t pk_last_sectors = 0, pk_last_np = 0;   // sector and packet count of the previous decode
     uint32_t scan_tmp_gen = 0;                // allocation of the scan buffer that has been cleared
     cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
     int pcm_slot;                             // which PCM buffer the next decode writes
@@ -506,36 +507,51 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         uint64_t *const copy[2] = {mapped_total_slot(c, 0), nullptr};
         TRY(scan_batch(in, out, wide, 2, n_sectors, tmp, tmp_bytes, s, copy));
     }
-    uint64_t total1 = 0;
-    TRY(mapped_totals(c, 1, &total1));
-    const uint32_t np = (uint32_t)total1;
-
-    const size_t npa = (size_t)np + 1;
-    ENSURE(B_PK_SECTOR, npa * 4); ENSURE(B_PK_OFF, npa * 2); ENSURE(B_PK_LEN, npa * 2);
-    ENSURE(B_PK_CODEC, npa); ENSURE(B_PK_PAD2, npa); ENSURE(B_PK_PARAMS, npa * 4);
-    ENSURE(B_PK_MLPLEN, npa * 4); ENSURE(B_PK_PCMF, npa * 4);
-    ENSURE(B_PK_ES, npa * 8); ENSURE(B_PK_PF, npa * 8);
-    ENSURE(B_PK_NONMLP, npa * 4); ENSURE(B_PK_NM_PREFIX, npa * 4);
-    ENSURE(B_PK_STOP, npa * 4); ENSURE(B_PK_STOP_PREFIX, npa * 4);
-    ENSURE(B_PK_YIELD, npa);
-    PacketTable pt;
-    pt.sector = c->buf[B_PK_SECTOR].as<uint32_t>(); pt.off = c->buf[B_PK_OFF].as<uint16_t>();
-    pt.len = c->buf[B_PK_LEN].as<uint16_t>(); pt.codec = c->buf[B_PK_CODEC].as<uint8_t>();
-    pt.pad2 = c->buf[B_PK_PAD2].as<uint8_t>(); pt.params = c->buf[B_PK_PARAMS].as<uint32_t>();
-    pt.mlp_len = c->buf[B_PK_MLPLEN].as<uint32_t>(); pt.pcm_frames = c->buf[B_PK_PCMF].as<uint32_t>();
-    uint64_t *pk_es = c->buf[B_PK_ES].as<uint64_t>(), *pk_pf = c->buf[B_PK_PF].as<uint64_t>();
-    uint32_t *nonmlp = c->buf[B_PK_NONMLP].as<uint32_t>(), *nm_prefix = c->buf[B_PK_NM_PREFIX].as<uint32_t>();
-    uint32_t *pstop = c->buf[B_PK_STOP].as<uint32_t>(), *stop_prefix = c->buf[B_PK_STOP_PREFIX].as<uint32_t>();
-    TRY(launch_packet_fill(d_sectors, n_sectors, sec_base, pt, np, nonmlp, pstop, s));
-    {
-        const uint32_t *in[4] = {pt.mlp_len, pt.pcm_frames, nonmlp, pstop};
-        void *out[4] = {pk_es, pk_pf, nm_prefix, stop_prefix};
-        const bool wide[4] = {true, true, false, false};
-        uint64_t *const copy[4] = {mapped_total_slot(c, 0), nullptr, nullptr, nullptr};
-        TRY(scan_batch(in, out, wide, 4, np, tmp, tmp_bytes, s, copy));
-    }
+    // The packet table is sized before the host knows the packet count (one audio packet per
+    // sector is the rule; room for a quarter more, and whatever earlier decodes needed): the
+    // table is filled, its prefix sums taken over all its rows, and only then does the host
+    // fetch the packet count and the size of the elementary stream, in one round trip.  If the
+    // table was too small it grows and the step is repeated.
+    uint32_t np = 0;
     uint64_t es_total = 0;
-    TRY(mapped_totals(c, 1, &es_total));
+    PacketTable pt;
+    uint64_t *pk_es = nullptr, *pk_pf = nullptr;
+    uint32_t *nonmlp = nullptr, *nm_prefix = nullptr, *pstop = nullptr, *stop_prefix = nullptr;
+    size_t rows = (size_t)n_sectors + n_sectors / 4 + 64;
+    if (c->pk_last_sectors == n_sectors) rows = std::max<size_t>(rows, (size_t)c->pk_last_np + 64);   // (the same input again)
+    for (int attempt = 0;; attempt++) {
+        const size_t npa = rows + 1;
+        ENSURE(B_PK_SECTOR, npa * 4); ENSURE(B_PK_OFF, npa * 2); ENSURE(B_PK_LEN, npa * 2);
+        ENSURE(B_PK_CODEC, npa); ENSURE(B_PK_PAD2, npa); ENSURE(B_PK_PARAMS, npa * 4);
+        ENSURE(B_PK_MLPLEN, npa * 4); ENSURE(B_PK_PCMF, npa * 4);
+        ENSURE(B_PK_ES, npa * 8); ENSURE(B_PK_PF, npa * 8);
+        ENSURE(B_PK_NONMLP, npa * 4); ENSURE(B_PK_NM_PREFIX, npa * 4);
+        ENSURE(B_PK_STOP, npa * 4); ENSURE(B_PK_STOP_PREFIX, npa * 4);
+        ENSURE(B_PK_YIELD, npa);
+        pt.sector = c->buf[B_PK_SECTOR].as<uint32_t>(); pt.off = c->buf[B_PK_OFF].as<uint16_t>();
+        pt.len = c->buf[B_PK_LEN].as<uint16_t>(); pt.codec = c->buf[B_PK_CODEC].as<uint8_t>();
+        pt.pad2 = c->buf[B_PK_PAD2].as<uint8_t>(); pt.params = c->buf[B_PK_PARAMS].as<uint32_t>();
+        pt.mlp_len = c->buf[B_PK_MLPLEN].as<uint32_t>(); pt.pcm_frames = c->buf[B_PK_PCMF].as<uint32_t>();
+        pk_es = c->buf[B_PK_ES].as<uint64_t>(); pk_pf = c->buf[B_PK_PF].as<uint64_t>();
+        nonmlp = c->buf[B_PK_NONMLP].as<uint32_t>(); nm_prefix = c->buf[B_PK_NM_PREFIX].as<uint32_t>();
+        pstop = c->buf[B_PK_STOP].as<uint32_t>(); stop_prefix = c->buf[B_PK_STOP_PREFIX].as<uint32_t>();
+        TRY(launch_packet_fill(d_sectors, n_sectors, sec_base, pt, (uint32_t)rows, nonmlp, pstop, s));
+        {
+            const uint32_t *in[4] = {pt.mlp_len, pt.pcm_frames, nonmlp, pstop};
+            void *out[4] = {pk_es, pk_pf, nm_prefix, stop_prefix};
+            const bool wide[4] = {true, true, false, false};
+            uint64_t *const copy[4] = {mapped_total_slot(c, 1), nullptr, nullptr, nullptr};
+            TRY(scan_batch(in, out, wide, 4, rows, tmp, tmp_bytes, s, copy));
+        }
+        uint64_t totals[2] = {0, 0};
+        TRY(mapped_totals(c, 2, totals));
+        np = (uint32_t)totals[0];
+        es_total = totals[1];
+        c->pk_last_sectors = n_sectors; c->pk_last_np = np;
+        if (np <= rows) break;
+        if (attempt) { dvdagpu_set_error("internal: packet table"); return -1; }
+        rows = (size_t)np + np / 8;
+    }
 
     ENSURE(B_ES, es_total + DVDA_ES_PAD);
     uint8_t *es = c->buf[B_ES].as<uint8_t>();

@@ -58,7 +58,8 @@ struct MlpTables {
 // demux.cu
 int upload_pcm_tables(const uint8_t *tables);
 int launch_sector_count(const uint8_t *sectors, uint32_t n_sectors, uint32_t *sec_cnt, uint32_t *sec_bad, cudaStream_t s);
-int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_t *sec_base, PacketTable pt, uint32_t np,
+// rows: rows the packet table has room for (the packet count is still on the device: sec_base[n_sectors])
+int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_t *sec_base, PacketTable pt, uint32_t rows,
                        uint32_t *nonmlp, uint32_t *pcm_stop, cudaStream_t s);
 int launch_es_gather(const uint8_t *sectors, PacketTable pt, uint32_t np, const uint64_t *pk_es, uint8_t *es, cudaStream_t s);
 int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t np, const uint64_t *pk_pf,
