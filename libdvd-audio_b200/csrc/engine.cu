@@ -125,6 +125,8 @@ struct dvdagpu_ctx {
     cudaEvent_t aux_ev[2];
     cudaStream_t aux_stream_hi = nullptr;     // side stream at the chain's own priority
     uint32_t pk_last_sectors = 0, pk_last_np = 0;   // sector and packet count of the previous decode
+    uint64_t sync_last_es = ~0ull;                  // stream size and sync counts of the previous decode
+    uint32_t sync_last_raw = 0, sync_last_valid = 0;
     uint32_t scan_tmp_gen = 0;                // allocation of the scan buffer that has been cleared
     cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
     int pcm_slot;                             // which PCM buffer the next decode writes
@@ -573,27 +575,45 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     if (es_total) {
         TIMED(DVDAGPU_K_SYNC_SCAN, launch_sync_count(es, es_total, cnt_raw, cnt_valid, sync_slots, nslots, s));
         const uint32_t *in[2] = {cnt_raw, cnt_valid}; void *out[2] = {base_raw, base_valid}; const bool wide[2] = {false, false};
-        uint64_t *const copy[2] = {mapped_total_slot(c, 0), mapped_total_slot(c, 1)};
-        TRY(scan_batch(in, out, wide, 2, chunks, tmp, tmp_bytes, s, copy));
-        uint64_t totals[2] = {0, 0};
-        TRY(mapped_totals(c, 2, totals));
-        n_raw = (uint32_t)totals[0]; n_valid = (uint32_t)totals[1];
+        TRY(scan_batch(in, out, wide, 2, chunks, tmp, tmp_bytes, s));
+    } else {
+        CUDA_TRY(cudaMemsetAsync(base_raw + chunks, 0, 4, s));
+        CUDA_TRY(cudaMemsetAsync(base_valid + chunks, 0, 4, s));
     }
-    ENSURE(B_RAW, ((size_t)n_raw + 1) * 8); ENSURE(B_VALID, ((size_t)n_valid + 1) * 8);
-    uint64_t *raw = c->buf[B_RAW].as<uint64_t>(), *valid = c->buf[B_VALID].as<uint64_t>();
-    if (n_raw) TRY(launch_sync_fill(es, es_total, cnt_raw, sync_slots, nslots, base_raw, base_valid, raw, valid, s));
-
     ENSURE(B_TRACKS, (size_t)n_tracks * sizeof(TrackDev));
     ENSURE(B_TRK_PK_LO, (size_t)n_tracks * 4); ENSURE(B_TRK_SEG_BASE, (size_t)(n_tracks + 1) * 4);
     ENSURE(B_TRK_GRP_BASE, (size_t)(n_tracks + 1) * 4);
     TrackDev *d_tracks = c->buf[B_TRACKS].as<TrackDev>();
     TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
-    TrackSetupArgs ta;
-    ta.es = es; ta.es_total = es_total; ta.n_sectors = n_sectors; ta.sec_base = sec_base; ta.bad_prefix = bad_prefix;
-    ta.pt = pt; ta.np = np; ta.pk_es = pk_es; ta.pk_pf = pk_pf; ta.pk_nonmlp = nm_prefix; ta.pk_pcm_stop = stop_prefix;
-    ta.raw = raw; ta.n_raw = n_raw; ta.valid = valid; ta.n_valid = n_valid;
-    TRY(launch_track_setup(ta, d_tracks, n_tracks, s));
-    TRY(small_d2h(c, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
+    // The sync lists are sized before their lengths are known to the host (a sync every 2 KiB of
+    // stream, or what the same input needed last time): they are filled, the tracks set up from
+    // them, and the lengths come back together with the track table.  Lists that were too small
+    // grow and the step is repeated.
+    uint64_t *raw = nullptr, *valid = nullptr;
+    size_t cap_raw = (size_t)(es_total / 2048) + 1024, cap_valid = cap_raw;
+    if (c->sync_last_es == es_total) { cap_raw = std::max<size_t>(cap_raw, c->sync_last_raw); cap_valid = std::max<size_t>(cap_valid, c->sync_last_valid); }
+    for (int attempt = 0;; attempt++) {
+        ENSURE(B_RAW, (cap_raw + 1) * 8); ENSURE(B_VALID, (cap_valid + 1) * 8);
+        raw = c->buf[B_RAW].as<uint64_t>(); valid = c->buf[B_VALID].as<uint64_t>();
+        if (es_total) TRY(launch_sync_fill(es, es_total, cnt_raw, sync_slots, nslots, base_raw, base_valid,
+                                           raw, (uint32_t)cap_raw, valid, (uint32_t)cap_valid, s));
+        TrackSetupArgs ta;
+        ta.es = es; ta.es_total = es_total; ta.n_sectors = n_sectors; ta.sec_base = sec_base; ta.bad_prefix = bad_prefix;
+        ta.pt = pt; ta.np = np; ta.pk_es = pk_es; ta.pk_pf = pk_pf; ta.pk_nonmlp = nm_prefix; ta.pk_pcm_stop = stop_prefix;
+        ta.raw = raw; ta.n_raw = base_raw + chunks; ta.cap_raw = (uint32_t)cap_raw;
+        ta.valid = valid; ta.n_valid = base_valid + chunks; ta.cap_valid = (uint32_t)cap_valid;
+        TRY(launch_track_setup(ta, d_tracks, n_tracks, s));
+        {
+            void *const host[3] = {&n_raw, &n_valid, ht.data()};
+            const void *const dev[3] = {base_raw + chunks, base_valid + chunks, d_tracks};
+            const size_t bytes[3] = {4, 4, n_tracks * sizeof(TrackDev)};
+            TRY(small_d2h_multi(c, 3, host, dev, bytes));
+        }
+        c->sync_last_es = es_total; c->sync_last_raw = n_raw; c->sync_last_valid = n_valid;
+        if (n_raw <= cap_raw && n_valid <= cap_valid) break;
+        if (attempt) { dvdagpu_set_error("internal: sync lists"); return -1; }
+        cap_raw = n_raw; cap_valid = n_valid;
+    }
 
     std::vector<uint32_t> h_pk_lo(n_tracks), h_seg_base(n_tracks + 1), h_grp_base(n_tracks + 1);
     uint32_t nseg = 0, ngroups = 0;

@@ -70,7 +70,8 @@ int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t np, const
 #define SYNC_SLOT_BYTES 4u        // per chunk: 2 slots of 16 bits
 int launch_sync_count(const uint8_t *es, uint64_t es_total, uint32_t *cnt_raw, uint32_t *cnt_valid, uint16_t *slots, uint32_t nslots, cudaStream_t s);
 int launch_sync_fill(const uint8_t *es, uint64_t es_total, const uint32_t *cnt_raw, const uint16_t *slots, uint32_t nslots,
-                     const uint32_t *base_raw, const uint32_t *base_valid, uint64_t *raw, uint64_t *valid, cudaStream_t s);
+                     const uint32_t *base_raw, const uint32_t *base_valid, uint64_t *raw, uint32_t cap_raw,
+                     uint64_t *valid, uint32_t cap_valid, cudaStream_t s);
 struct TrackSetupArgs {
     const uint8_t *es;
     uint64_t es_total;
@@ -83,10 +84,14 @@ struct TrackSetupArgs {
     const uint64_t *pk_pf;         // [np + 1] PCM frames
     const uint32_t *pk_nonmlp;     // [np + 1]
     const uint32_t *pk_pcm_stop;   // [np + 1]
+    // the sync lists: their lengths are still on the device when the kernel runs (the lists were
+    // sized in advance: cap_*; entries beyond were not written and the host comes back)
     const uint64_t *raw;
-    uint32_t n_raw;
+    const uint32_t *n_raw;
+    uint32_t cap_raw;
     const uint64_t *valid;
-    uint32_t n_valid;
+    const uint32_t *n_valid;
+    uint32_t cap_valid;
 };
 int launch_track_setup(TrackSetupArgs a, TrackDev *tracks, uint32_t n_tracks, cudaStream_t s);
 int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_seg_base,

@@ -128,8 +128,9 @@ k_sync_find(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t chunks, 
 __global__ void k_sync_emit(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t chunks,
                             const uint32_t *__restrict__ cnt_raw, const uint16_t *__restrict__ slots, uint32_t nslots,
                             const uint32_t *__restrict__ base_raw, const uint32_t *__restrict__ base_valid,
-                            uint64_t *__restrict__ raw, uint64_t *__restrict__ valid)
+                            uint64_t *__restrict__ raw, uint32_t cap_raw, uint64_t *__restrict__ valid, uint32_t cap_valid)
 {
+    // (the lists were sized before their lengths were known: nothing is written behind their ends)
     const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= chunks) return;
     const uint32_t n = cnt_raw[ch];
@@ -139,8 +140,9 @@ __global__ void k_sync_emit(const uint8_t *__restrict__ es, uint64_t es_total, u
     if (n <= nslots) {
         for (uint32_t i = 0; i < n; i++) {
             const uint32_t e = slots[(uint64_t)ch * SYNC_SLOTS + i];
-            raw[ir++] = p0 + (e & 0x7FFF);
-            if (e >> 15) valid[iv++] = p0 + (e & 0x7FFF);
+            if (ir < cap_raw) raw[ir] = p0 + (e & 0x7FFF);
+            ir++;
+            if (e >> 15) { if (iv < cap_valid) valid[iv] = p0 + (e & 0x7FFF); iv++; }
         }
         return;
     }
@@ -148,8 +150,9 @@ __global__ void k_sync_emit(const uint8_t *__restrict__ es, uint64_t es_total, u
         const uint64_t p = p0 + j;
         if (p + 8 > es_total) break;
         if (ld_be32(es + p + 4) != 0xF8726FBBu) continue;
-        raw[ir++] = p;
-        if (sync_starts_segment(es, p, es_total)) valid[iv++] = p;
+        if (ir < cap_raw) raw[ir] = p;
+        ir++;
+        if (sync_starts_segment(es, p, es_total)) { if (iv < cap_valid) valid[iv] = p; iv++; }
     }
 }
 
@@ -161,10 +164,11 @@ int launch_sync_count(const uint8_t *es, uint64_t es_total, uint32_t *cnt_raw, u
     return 0;
 }
 int launch_sync_fill(const uint8_t *es, uint64_t es_total, const uint32_t *cnt_raw, const uint16_t *slots, uint32_t nslots,
-                     const uint32_t *base_raw, const uint32_t *base_valid, uint64_t *raw, uint64_t *valid, cudaStream_t s)
+                     const uint32_t *base_raw, const uint32_t *base_valid, uint64_t *raw, uint32_t cap_raw,
+                     uint64_t *valid, uint32_t cap_valid, cudaStream_t s)
 {
     const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
-    LAUNCH(k_sync_emit, div_up_u32(chunks, 128), 128, 0, s, es, es_total, chunks, cnt_raw, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS, base_raw, base_valid, raw, valid);
+    LAUNCH(k_sync_emit, div_up_u32(chunks, 128), 128, 0, s, es, es_total, chunks, cnt_raw, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS, base_raw, base_valid, raw, cap_raw, valid, cap_valid);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -208,6 +212,7 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
 {
     const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
     if (ti >= n_tracks) return;
+    const uint32_t n_raw = min(*a.n_raw, a.cap_raw), n_valid = min(*a.n_valid, a.cap_valid);
     TrackDev T = tracks[ti];
     T.status = 1;
     T.error_flags = 0;
@@ -272,8 +277,8 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
             // open_mlp_track_reader / locate_mlp_parameters (dvd-audio.c:1094-1149, 1318-1365)
             const uint64_t es_avail = a.pk_es[T.pk_hi];
             const uint64_t es_lo = a.pk_es[T.pk_lo];
-            const uint32_t ci = lower_bound_dev(a.raw, a.n_raw, es_lo);
-            if (ci >= a.n_raw || a.raw[ci] + 18 > es_avail) {
+            const uint32_t ci = lower_bound_dev(a.raw, n_raw, es_lo);
+            if (ci >= n_raw || a.raw[ci] + 18 > es_avail) {
                 if (T.cont & TRACK_CONT_PREV) { T.status = 0; T.codec = 1; T.truncated = 1; }   // an empty part
                 break;                                               // reference asserts
             }
@@ -310,8 +315,8 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
                 if (a.pt.codec[pk_x] != CODEC_MLP) {
                     es_end = P0;                               // codec mismatch: nothing more
                 } else {
-                    const uint32_t cj = lower_bound_dev(a.raw, a.n_raw, P0);
-                    if (cj < a.n_raw && a.raw[cj] + 8 <= es_avail) es_end = a.raw[cj];
+                    const uint32_t cj = lower_bound_dev(a.raw, n_raw, P0);
+                    if (cj < n_raw && a.raw[cj] + 8 <= es_avail) es_end = a.raw[cj];
                     else if (T.cont & TRACK_CONT_NEXT) { es_end = es_avail; T.truncated = 1; }   // the parts behind are empty
                     else { es_end = (es_avail >= P0 + 8) ? es_avail - 7 : P0; T.truncated = 1; }
                 }
@@ -335,8 +340,8 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
                 T.es_end = T.es_cut = p;
             }
             // restart segments: the start plus every segment-starting sync inside (p, es_end)
-            T.cand_lo = upper_bound_dev(a.valid, a.n_valid, p);
-            const uint32_t cand_hi = lower_bound_dev(a.valid, a.n_valid, T.es_end);
+            T.cand_lo = upper_bound_dev(a.valid, n_valid, p);
+            const uint32_t cand_hi = lower_bound_dev(a.valid, n_valid, T.es_end);
             T.nseg = T.es_end > p ? 1 + (cand_hi > T.cand_lo ? cand_hi - T.cand_lo : 0) : 0;
             T.ngrp = (T.nseg + DVDA_LANES - 1) / DVDA_LANES;
         }
