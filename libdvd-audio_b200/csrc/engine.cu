@@ -521,6 +521,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     uint32_t *nonmlp = nullptr, *nm_prefix = nullptr, *pstop = nullptr, *stop_prefix = nullptr;
     size_t rows = (size_t)n_sectors + n_sectors / 4 + 64;
     if (c->pk_last_sectors == n_sectors) rows = std::max<size_t>(rows, (size_t)c->pk_last_np + 64);   // (the same input again)
+    // (test hook: DVDAGPU_SMALL_TABLES=1 starts every table sized in advance with room for one entry,
+    // so that each decode goes through the grow-and-repeat paths)
+    const bool small_tables = getenv("DVDAGPU_SMALL_TABLES") != nullptr;
+    if (small_tables) rows = 1;
     for (int attempt = 0;; attempt++) {
         const size_t npa = rows + 1;
         ENSURE(B_PK_SECTOR, npa * 4); ENSURE(B_PK_OFF, npa * 2); ENSURE(B_PK_LEN, npa * 2);
@@ -592,6 +596,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     uint64_t *raw = nullptr, *valid = nullptr;
     size_t cap_raw = (size_t)(es_total / 2048) + 1024, cap_valid = cap_raw;
     if (c->sync_last_es == es_total) { cap_raw = std::max<size_t>(cap_raw, c->sync_last_raw); cap_valid = std::max<size_t>(cap_valid, c->sync_last_valid); }
+    if (small_tables) cap_raw = cap_valid = 1;
     for (int attempt = 0;; attempt++) {
         ENSURE(B_RAW, (cap_raw + 1) * 8); ENSURE(B_VALID, (cap_valid + 1) * 8);
         raw = c->buf[B_RAW].as<uint64_t>(); valid = c->buf[B_VALID].as<uint64_t>();

@@ -94,6 +94,25 @@ def test_sync_search_overflow_path(pkg, oracle, disc_cache, name, monkeypatch):
         eng.close()
 
 
+@pytest.mark.parametrize("name", ["c5_mixed", "mlp_wild_0", "pcm_rates_ragged", "mlp_zero_yield", "mlp_short_segments"])
+def test_tables_sized_in_advance_grow(pkg, oracle, disc_cache, name, monkeypatch):
+    """The packet table and the sync lists are sized before their sizes are known; too small, they grow
+    and the step is repeated.  DVDAGPU_SMALL_TABLES=1 starts them with room for one entry."""
+    monkeypatch.setenv("DVDAGPU_SMALL_TABLES", "1")
+    eng = pkg.Engine(0)
+    try:
+        directory, _ = disc_cache(name)
+        sectors = oracle.read_aobs(directory)
+        golden = GOLDEN[name]["tracks"]
+        for _ in range(2):                      # (both decodes grow their tables: the hook applies to every decode)
+            res = eng.decode_host(sectors, [(g["first"], g["last"], g["pts"]) for g in golden])
+            for r, g in zip(res, golden):
+                assert r.status == 0 and r.frames == g["frames"], (name, g["title"], g["track"])
+                assert oracle.fnv1a(eng.fetch(r)) == g["fnv"], (name, g["title"], g["track"])
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("name", ["c5_mixed", "mlp_wild_1", "pcm_rates_ragged", "mlp_zero_yield"])
 def test_public_api(pkg, oracle, disc_cache, name):
     """dvda_open .. dvda_open_track_reader .. dvda_read, as a program written for the
