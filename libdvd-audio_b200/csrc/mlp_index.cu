@@ -193,24 +193,55 @@ __device__ __forceinline__ uint32_t channel_count(uint32_t a)
     return a <= 20 ? (uint32_t)((packed >> (3 * a)) & 7) : 0;
 }
 
+// The searches of the track set-up, by a whole warp: every lane probes the end of one of 32
+// stripes of the range, a ballot picks the stripe, four or five rounds instead of seventeen
+// dependent loads.  pred is monotone (false ... false true ... true); all lanes pass the same
+// arguments.  Returns the first index in [lo, hi) for which pred holds, hi if there is none.
+template <typename P>
+__device__ __forceinline__ uint32_t warp_first_true(uint32_t lo, uint32_t hi, P pred)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    if (lo >= hi) return hi;
+    while (hi - lo > 32) {
+        const uint32_t step = (hi - lo + 31) >> 5;
+        const uint64_t e = (uint64_t)lo + (uint64_t)(lane + 1) * step - 1;     // last index of this lane's stripe
+        const bool t = e >= hi || pred((uint32_t)e);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, t);
+        if (!m) return hi;
+        const uint32_t k = __ffs(m) - 1;
+        const uint64_t ek = (uint64_t)lo + (uint64_t)(k + 1) * step - 1;
+        lo += k * step;
+        if (ek < hi) hi = (uint32_t)ek;               // pred holds at ek: "none before it" means ek itself
+    }
+    const uint32_t i = lo + lane;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, i >= hi || pred(i));
+    if (!m) return hi;
+    return min(lo + (uint32_t)(__ffs(m) - 1), hi);
+}
+template <typename T>
+__device__ __forceinline__ uint32_t warp_lower_bound(const T *a, uint32_t n, T x)      // first a[i] >= x
+{
+    return warp_first_true(0u, n, [=](uint32_t i) { return a[i] >= x; });
+}
+template <typename T>
+__device__ __forceinline__ uint32_t warp_upper_bound(const T *a, uint32_t n, T x)      // first a[i] > x
+{
+    return warp_first_true(0u, n, [=](uint32_t i) { return a[i] > x; });
+}
 // first packet index i >= from whose prefix count differs from prefix[from], or np
-__device__ uint32_t first_flagged(const uint32_t *prefix, uint32_t np, uint32_t from)
+__device__ __forceinline__ uint32_t warp_first_flagged(const uint32_t *prefix, uint32_t np, uint32_t from)
 {
     if (from >= np) return np;
     const uint32_t base = prefix[from];
     // prefix[i + 1] > base  <=>  some flag in [from, i]
-    uint32_t lo = from, hi = np;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (prefix[mid + 1] > base) hi = mid; else lo = mid + 1;
-    }
-    return lo;
+    return warp_first_true(from, np, [=](uint32_t i) { return prefix[i + 1] > base; });
 }
 
-// One thread per track.  Everything is a table lookup or a binary search.
-__global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, uint32_t n_tracks)
+// One warp per track (all lanes hold the same values; the searches are shared out, lane 0 stores).
+// Everything is a table lookup or a search in a sorted table.
+__global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, uint32_t n_tracks)
 {
-    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ti = blockIdx.x * 2 + (threadIdx.x >> 5);
     if (ti >= n_tracks) return;
     const uint32_t n_raw = min(*a.n_raw, a.cap_raw), n_valid = min(*a.n_valid, a.cap_valid);
     TrackDev T = tracks[ti];
@@ -230,12 +261,8 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
         uint32_t dead = a.n_sectors;
         {
             const uint32_t base = a.bad_prefix[T.first_sector];
-            uint32_t lo = T.first_sector, hi = a.n_sectors;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (a.bad_prefix[mid + 1] > base) hi = mid; else lo = mid + 1;
-            }
-            dead = lo;
+            const uint32_t *bp = a.bad_prefix;
+            dead = warp_first_true(T.first_sector, a.n_sectors, [=](uint32_t i) { return bp[i + 1] > base; });
         }
         T.pk_lo = a.sec_base[T.first_sector];
         T.pk_hi = dead < a.n_sectors ? a.sec_base[dead + 1] : a.np;
@@ -260,15 +287,13 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
             const uint64_t total = (uint64_t)llround((double)T.pts_length * (double)T.rate / 90000.0);
             T.pcm_frame0 = a.pk_pf[T.pk_lo];
             // stop in front of the first later packet that is not PCM / differs / is empty
-            uint32_t stop = first_flagged(a.pk_pcm_stop, a.np, T.pk_lo + 1);
+            uint32_t stop = warp_first_flagged(a.pk_pcm_stop, a.np, T.pk_lo + 1);
             if (stop > T.pk_hi) stop = T.pk_hi;
             // ... and behind the packet in which the budget is used up: first i with
             // frames(pk_lo..i) >= total
-            uint32_t lo = T.pk_lo, hi = stop;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (a.pk_pf[mid + 1] - T.pcm_frame0 >= total) hi = mid; else lo = mid + 1;
-            }
+            const uint64_t *pf = a.pk_pf;
+            const uint64_t frame0 = T.pcm_frame0;
+            const uint32_t lo = warp_first_true(T.pk_lo, stop, [=](uint32_t i) { return pf[i + 1] - frame0 >= total; });
             T.pcm_pk_end = lo < stop ? lo + 1 : stop;
             T.truncated = (lo >= stop && stop == a.np);        // budget left, buffer used up
             T.frames = a.pk_pf[T.pcm_pk_end] - T.pcm_frame0;
@@ -277,7 +302,7 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
             // open_mlp_track_reader / locate_mlp_parameters (dvd-audio.c:1094-1149, 1318-1365)
             const uint64_t es_avail = a.pk_es[T.pk_hi];
             const uint64_t es_lo = a.pk_es[T.pk_lo];
-            const uint32_t ci = lower_bound_dev(a.raw, n_raw, es_lo);
+            const uint32_t ci = warp_lower_bound(a.raw, n_raw, es_lo);
             if (ci >= n_raw || a.raw[ci] + 18 > es_avail) {
                 if (T.cont & TRACK_CONT_PREV) { T.status = 0; T.codec = 1; T.truncated = 1; }   // an empty part
                 break;                                               // reference asserts
@@ -297,7 +322,7 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
             const uint32_t rc = T.g0_rate & 7;
             T.au_nominal = 40u << (rc > 2 ? 0 : rc);
             // the packet holding byte p + 17 is the last one consumed while opening
-            T.pk_open = upper_bound_dev(a.pk_es, a.np + 1, p + 17) - 1;
+            T.pk_open = warp_upper_bound(a.pk_es, a.np + 1, p + 17) - 1;
             // a continued part whose range holds no sync at all is empty: the sync it found
             // lies in (and will be found again by) a later part
             const bool empty_part = (T.cont & TRACK_CONT_PREV) && pk_x < T.pk_hi && p >= a.pk_es[pk_x];
@@ -307,7 +332,7 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
             // last access unit ended inside that packet (then the packet did yield)
             T.pk_check = T.pk_open + 1;
             if (T.cont & TRACK_CONT_PREV)
-                T.pk_check = p > es_lo ? upper_bound_dev(a.pk_es, a.np + 1, p - 1) : T.pk_lo;
+                T.pk_check = p > es_lo ? warp_upper_bound(a.pk_es, a.np + 1, p - 1) : T.pk_lo;
             // end of the track
             uint64_t es_end = es_avail;
             if (pk_x < T.pk_hi) {
@@ -315,7 +340,7 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
                 if (a.pt.codec[pk_x] != CODEC_MLP) {
                     es_end = P0;                               // codec mismatch: nothing more
                 } else {
-                    const uint32_t cj = lower_bound_dev(a.raw, n_raw, P0);
+                    const uint32_t cj = warp_lower_bound(a.raw, n_raw, P0);
                     if (cj < n_raw && a.raw[cj] + 8 <= es_avail) es_end = a.raw[cj];
                     else if (T.cont & TRACK_CONT_NEXT) { es_end = es_avail; T.truncated = 1; }   // the parts behind are empty
                     else { es_end = (es_avail >= P0 + 8) ? es_avail - 7 : P0; T.truncated = 1; }
@@ -324,14 +349,14 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
                 T.truncated = 1;                               // no packet behind last_sector in the buffer
             }
             // a non-MLP audio packet met while decoding ends the stream (dvd-audio.c:1203-1208)
-            const uint32_t nm = first_flagged(a.pk_nonmlp, a.np, (T.cont & TRACK_CONT_PREV) ? T.pk_lo : T.pk_open + 1);
+            const uint32_t nm = warp_first_flagged(a.pk_nonmlp, a.np, (T.cont & TRACK_CONT_PREV) ? T.pk_lo : T.pk_open + 1);
             if (nm < pk_x && nm < T.pk_hi && a.pk_es[nm] < es_end) es_end = a.pk_es[nm];
             if (es_end < p) es_end = p;
             T.es_end = es_end;
             // a part that is continued also answers for the packets its last access units end in
             T.pk_check_end = pk_x;
             if ((T.cont & TRACK_CONT_NEXT) && pk_x < T.pk_hi && es_end > a.pk_es[pk_x])
-                T.pk_check_end = min(T.pk_hi, upper_bound_dev(a.pk_es, a.np + 1, es_end - 1));
+                T.pk_check_end = min(T.pk_hi, warp_upper_bound(a.pk_es, a.np + 1, es_end - 1));
             T.es_cut = es_end;
             if (empty_part) T.es_end = T.es_cut = p;
             if (T.nss != 1 && T.nss != 2) {
@@ -340,19 +365,19 @@ __global__ void k_track_setup(TrackSetupArgs a, TrackDev *__restrict__ tracks, u
                 T.es_end = T.es_cut = p;
             }
             // restart segments: the start plus every segment-starting sync inside (p, es_end)
-            T.cand_lo = upper_bound_dev(a.valid, n_valid, p);
-            const uint32_t cand_hi = lower_bound_dev(a.valid, n_valid, T.es_end);
+            T.cand_lo = warp_upper_bound(a.valid, n_valid, p);
+            const uint32_t cand_hi = warp_lower_bound(a.valid, n_valid, T.es_end);
             T.nseg = T.es_end > p ? 1 + (cand_hi > T.cand_lo ? cand_hi - T.cand_lo : 0) : 0;
             T.ngrp = (T.nseg + DVDA_LANES - 1) / DVDA_LANES;
         }
         T.pk_x = pk_x;
     } while (0);
-    tracks[ti] = T;
+    if ((threadIdx.x & 31) == 0) tracks[ti] = T;
 }
 
 int launch_track_setup(TrackSetupArgs a, TrackDev *tracks, uint32_t n_tracks, cudaStream_t s)
 {
-    LAUNCH(k_track_setup, div_up_u32(n_tracks, 64), 64, 0, s, a, tracks, n_tracks);
+    LAUNCH(k_track_setup, div_up_u32(n_tracks, 2), 64, 0, s, a, tracks, n_tracks);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
