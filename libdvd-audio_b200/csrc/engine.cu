@@ -112,7 +112,7 @@ enum {
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
     B_SS_FLAGS, B_SS_FLAGS_PREV, B_SS_FLAGS_FAST, B_FIR_TAIL,
     B_GROUPS, B_GRP_CELLS, B_CELL_BASE, B_GRP_CHUNKS, B_GRP_CHUNK_BASE,
-    B_DEC_WORK, B_AU_SEG, B_AU_SNAP, B_FILT_SNAP, B_AU_FCHG, B_SEG_CTX, B_AU_DELTA, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_PCM,
+    B_DEC_WORK, B_AU_SEG, B_AU_SNAP, B_FILT_SNAP, B_AU_FCHG, B_SEG_CTX, B_AU_DELTA, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_AU_NOTED, B_PCM,
     B_COUNT
 };
 
@@ -688,7 +688,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         m.segs = c->buf[B_SEGS].as<SegDev>();
         uint32_t *seg_nau = c->buf[B_SEG_NAU].as<uint32_t>(), *seg_au_base = c->buf[B_SEG_AU_BASE].as<uint32_t>();
         TRY(launch_segment_fill(d_tracks, n_tracks, trk_seg_base, valid, m.segs, nseg, s));
-        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, nullptr, nullptr, seg_au_base, 0, s));
+        ENSURE(B_AU_NOTED, au_noted_bytes(nseg));
+        uint32_t *au_noted = c->buf[B_AU_NOTED].as<uint32_t>();
+        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, nullptr, nullptr, seg_au_base, au_noted, 0, s));
         TRY(scan_u32_to_u32(seg_nau, seg_au_base, nseg, tmp, tmp_bytes, s));
         // the groups (tile sizes) follow from the access-unit counts alone: set them up now and
         // fetch all the sizes the next allocations need in one round trip
@@ -720,7 +722,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         m.au_frames_ss = c->buf[B_AU_FRAMES].as<uint32_t>();
         m.ss_flags = c->buf[B_SS_FLAGS].as<uint32_t>(); m.ss_flags_prev = c->buf[B_SS_FLAGS_PREV].as<uint32_t>(); m.ss_flags_fast = c->buf[B_SS_FLAGS_FAST].as<uint32_t>();
         m.fir_tail = c->buf[B_FIR_TAIL].as<int32_t>();
-        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, m.au_pos, m.au_seg, seg_au_base, 1, s));
+        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, m.au_pos, m.au_seg, seg_au_base, au_noted, 1, s));
         TRY(launch_yield(m, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), s));
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
 

@@ -96,8 +96,11 @@ struct TrackSetupArgs {
 int launch_track_setup(TrackSetupArgs a, TrackDev *tracks, uint32_t n_tracks, cudaStream_t s);
 int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_seg_base,
                         const uint64_t *valid, SegDev *segs, uint32_t nseg, cudaStream_t s);
+// noted: scratch of au_noted_bytes(nseg) bytes shared by the two passes (count, then fill)
+size_t au_noted_bytes(uint32_t nseg);
 int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t nseg, const TrackDev *tracks,
-                    uint32_t *seg_nau, uint64_t *au_pos, uint32_t *au_seg, const uint32_t *seg_au_base, int fill, cudaStream_t s);
+                    uint32_t *seg_nau, uint64_t *au_pos, uint32_t *au_seg, const uint32_t *seg_au_base,
+                    uint32_t *noted, int fill, cudaStream_t s);
 int launch_yield(MlpTables m, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
                  uint8_t *pk_yield, cudaStream_t s);
 int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_grp_base, const SegDev *segs,

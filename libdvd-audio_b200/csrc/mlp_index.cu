@@ -412,45 +412,71 @@ int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_
 }
 
 // One thread per segment walks the chain of 12-bit access-unit lengths
-// (reference mlp.c:392-394).  Pass 1 counts, pass 2 (fill) records positions.
+// (reference mlp.c:392-394).  Pass 1 counts and notes the first AU_NOTED positions of the
+// segment (relative to its start; noted[j * nseg + segment]: coalesced).  Pass 2 (fill), once
+// the access units are numbered, copies them to their places — independent loads, not a second
+// walk down the chain; only a segment with more access units than were noted walks on from the
+// last noted one.
+#define AU_NOTED 32
 __global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ segs, uint32_t nseg,
                            const TrackDev *__restrict__ tracks, uint32_t *__restrict__ seg_nau,
                            uint64_t *__restrict__ au_pos, uint32_t *__restrict__ au_seg,
-                           const uint32_t *__restrict__ seg_au_base, int fill)
+                           const uint32_t *__restrict__ seg_au_base, uint32_t *__restrict__ noted, uint32_t n_noted, int fill)
 {
+    // (n_noted: positions noted per segment, AU_NOTED unless a test wants the walk-on path)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nseg) return;
     SegDev &S = segs[i];
-    if (fill) S.au_base = seg_au_base[i];
     const uint64_t limit = S.es_limit;
-    uint64_t pos = S.es_pos;
+    const uint64_t pos0 = S.es_pos;
+    if (fill) {
+        const uint32_t base = seg_au_base[i], n_au = S.n_au;
+        S.au_base = base;
+        const uint32_t copied = min(n_au, n_noted);
+#pragma unroll 8
+        for (uint32_t j = 0; j < copied; j++) {
+            au_pos[base + j] = pos0 + noted[(uint64_t)j * nseg + i];
+            au_seg[base + j] = i;
+        }
+        if (n_au > n_noted) {
+            uint64_t pos = pos0 + noted[(uint64_t)(n_noted - 1) * nseg + i];
+            for (uint32_t n = n_noted - 1; n < n_au; n++) {
+                if (n >= n_noted) { au_pos[base + n] = pos; au_seg[base + n] = i; }
+                pos += (((ld_u8(es + pos) & 15u) << 8) | ld_u8(es + pos + 1)) * 2;
+            }
+        }
+        return;
+    }
+    uint64_t pos = pos0;
     uint32_t n = 0;
     bool stalled = false;
     while (pos + 4 <= limit) {
         const uint32_t total = (((ld_u8(es + pos) & 15u) << 8) | ld_u8(es + pos + 1)) * 2;
         if (total < 4) { stalled = true; break; }              // the reference's queue never advances again
         if (pos + total > limit) break;                        // incomplete (end of track) or overshoot
-        if (fill) { au_pos[S.au_base + n] = pos; au_seg[S.au_base + n] = i; }
+        if (n < n_noted) noted[(uint64_t)n * nseg + i] = (uint32_t)(pos - pos0);
         pos += total;
         n++;
     }
-    if (!fill) {
-        seg_nau[i] = n;
-        S.n_au = n;
-        const TrackDev &T = tracks[S.track];
-        const bool last = (i + 1 - T.seg_base) == T.nseg;
-        // every segment but the last must land exactly on the next one; so must the last
-        // one of a part that is continued (the cut has to be a real access-unit boundary)
-        const bool must_land = !last || ((T.cont & TRACK_CONT_NEXT) && !T.truncated);
-        if (stalled || (must_land && pos != limit)) S.flags |= SEG_IRREGULAR;
-    }
+    seg_nau[i] = n;
+    S.n_au = n;
+    const TrackDev &T = tracks[S.track];
+    const bool last = (i + 1 - T.seg_base) == T.nseg;
+    // every segment but the last must land exactly on the next one; so must the last
+    // one of a part that is continued (the cut has to be a real access-unit boundary)
+    const bool must_land = !last || ((T.cont & TRACK_CONT_NEXT) && !T.truncated);
+    if (stalled || (must_land && pos != limit)) S.flags |= SEG_IRREGULAR;
 }
 
+size_t au_noted_bytes(uint32_t nseg) { return (size_t)AU_NOTED * nseg * sizeof(uint32_t); }
+
 int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t nseg, const TrackDev *tracks,
-                    uint32_t *seg_nau, uint64_t *au_pos, uint32_t *au_seg, const uint32_t *seg_au_base, int fill, cudaStream_t s)
+                    uint32_t *seg_nau, uint64_t *au_pos, uint32_t *au_seg, const uint32_t *seg_au_base,
+                    uint32_t *noted, int fill, cudaStream_t s)
 {
     if (!nseg) return 0;
-    LAUNCH(k_au_chase, div_up_u32(nseg, 128), 128, 0, s, es, segs, nseg, tracks, seg_nau, au_pos, au_seg, seg_au_base, fill);
+    const uint32_t n_noted = getenv("DVDAGPU_SMALL_TABLES") ? 2u : (uint32_t)AU_NOTED;          // (test hook)
+    LAUNCH(k_au_chase, div_up_u32(nseg, 128), 128, 0, s, es, segs, nseg, tracks, seg_nau, au_pos, au_seg, seg_au_base, noted, n_noted, fill);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
