@@ -125,7 +125,10 @@ void dvdagpu_destroy(dvdagpu_ctx *ctx);
 
 /* Run all work of this context on an existing CUDA stream (a cudaStream_t
  * passed as void*; NULL = the context's own stream).  Lets a caller time the
- * engine with its own events or order it after its own copies. */
+ * engine with its own events or order it after its own copies.  The context's
+ * own stream has the highest stream priority (its side work runs on a stream of
+ * the lowest, beside the decode chain); a caller's stream keeps whatever
+ * priority it was created with. */
 int dvdagpu_set_stream(dvdagpu_ctx *ctx, void *cuda_stream);
 
 /* Decode n_tracks tracks whose sectors live in HOST memory (`sectors`,

@@ -36,7 +36,7 @@ dev = torch.empty(samples, dtype=torch.int32, device="cuda")
 def d2h_only():
     hout.copy_(dev, non_blocking=True); torch.cuda.synchronize()
 print("D2H only: %.2f ms" % timeit(d2h_only))
-for part in (0, 38000, 26000, 19000, 13000, 9500):
+for part in (0, 76000, 51000, 38000, 30500, 26000):
     def pipe():
         r = eng.decode_track_pipelined(hin.data_ptr(), n, tr, hout.data_ptr(), samples, part_sectors=part)
         assert int(r.frames) * 2 == samples
