@@ -802,7 +802,8 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             // place in the tiles, so the tiles' size bounds them), the tracks' places in it are
             // computed on the device, and the fused output pass of the fast path is queued right
             // here: the round trip below then costs the device nothing.
-            const uint64_t pcm_capacity = cells * DVDA_LANES + pcm_fixed;
+            // (test hook: a capacity of one sample sends every decode through the "too small" path)
+            const uint64_t pcm_capacity = small_tables ? 1 : cells * DVDA_LANES + pcm_fixed;
             ENSURE(pcm_buf, (pcm_capacity + 64) * sizeof(int32_t));
             m.pcm = c->buf[pcm_buf].as<int32_t>();
             LAUNCH(k_track_out_base, 1, OB_THREADS, 0, s, d_tracks, n_tracks, d_status, pcm_capacity);
