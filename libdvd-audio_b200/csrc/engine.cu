@@ -677,6 +677,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     ENSURE(B_STATUS, 64);
     uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
     m.status = d_status;
+    m.any_fallback = d_status + 8;
     // samples of the PCM tracks (known since the track set-up) and the alignment gaps
     uint64_t pcm_fixed = 4ull * n_tracks + 64;
     for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].status == 0 && ht[i].codec == 0) pcm_fixed += ht[i].frames * ht[i].channels;

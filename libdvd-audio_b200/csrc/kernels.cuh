@@ -53,6 +53,7 @@ struct MlpTables {
     uint32_t fast;                 // 1: the complete decoder only takes segments flagged SEG_FALLBACK
     uint32_t max_au;               // largest access-unit count of a segment
     const uint32_t *status;        // the batch's status word (SEG_OVERFLOW, STATUS_*)
+    uint32_t *any_fallback;        // set by the flag kernels of the fast path when the complete decoder has work at all
 };
 
 // demux.cu

@@ -2241,6 +2241,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_BLOCKS) k_mlp_decode(M
                                                                uint32_t n_work, uint32_t n_warps)
 {
     extern __shared__ uint4 dyn_smem[];
+    if (m.fast && !*m.any_fallback) return;              // the fast path kept every segment
     uint4 (*ring)[RING_SLOTS][DVDA_LANES] = reinterpret_cast<uint4 (*)[RING_SLOTS][DVDA_LANES]>(dyn_smem);
     uint16_t (*lut)[512] = reinterpret_cast<uint16_t (*)[512]>(dyn_smem + DEC_WARPS * RING_SLOTS * DVDA_LANES);
     for (uint32_t i = threadIdx.x; i < 4 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry(i >> 9, i & 511);
@@ -2371,8 +2372,11 @@ __global__ void k_flag_predecessors(MlpTables m)
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t seg = idx >> 1, k = idx & 1;
     if (seg >= m.nseg) return;
-    if (!(m.ss_flags[k * m.nseg + seg] & SEG_WANTS_PREV)) return;
+    const uint32_t fl = m.ss_flags[k * m.nseg + seg];
     const TrackDev &T = m.tracks[m.segs[seg].track];
+    // (does the complete decoder have anything to do?  It and the carry fix leave at once if not.)
+    if (k < T.nss && (fl & (SEG_FALLBACK | SEG_WANTS_PREV))) *m.any_fallback = 1;
+    if (!(fl & SEG_WANTS_PREV)) return;
     if (seg > T.seg_base) atomicOr(&m.ss_flags[k * m.nseg + seg - 1], SEG_FALLBACK);
 }
 
@@ -2383,6 +2387,7 @@ __global__ void k_flag_damaged(MlpTables m)
     const uint32_t seg = m.au_seg[A];
     atomicOr(&m.ss_flags[seg], SEG_FALLBACK);
     atomicOr(&m.ss_flags[m.nseg + seg], SEG_FALLBACK);
+    *m.any_fallback = 1;
 }
 
 size_t au_snap_bytes() { return sizeof(AuSnap); }
@@ -2467,6 +2472,7 @@ __global__ void __launch_bounds__(FIX_THREADS) k_carry_fix(MlpTables m)
 {
     __shared__ uint16_t lut[4][512];
     __shared__ uint4 ring[RING_SLOTS][DVDA_LANES];
+    if (m.fast && !*m.any_fallback) return;              // nothing was handed to the complete decoder
     for (uint32_t i = threadIdx.x; i < 4 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry(i >> 9, i & 511);
     __syncthreads();
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
