@@ -275,9 +275,14 @@ __global__ void __launch_bounds__(CHKD_THREADS) k_checkdata_direct(MlpTables m, 
 #undef CHK_WORD
 }
 
+__global__ void k_huff_lut_build();       // further down, next to the table it fills
+
 int upload_crc_table(const uint8_t *t)
 {
     CUDA_TRY(cudaMemcpyToSymbol(c_crc8, t, 256));
+    k_huff_lut_build<<<1, 256>>>();
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
     static uint8_t tab[12][256];
     for (int i = 0; i < 256; i++) {
         tab[0][i] = t[i];
@@ -599,6 +604,20 @@ __device__ uint16_t huff_entry(uint32_t cb, uint32_t v9)
     if (!v9) return 0xFFFF;
     const uint32_t z = __clz(v9) - 23;
     return (uint16_t)((8 - z) | ((z + 1) << 8));
+}
+
+// The same table for every block: built once per device (upload_crc_table), copied into shared
+// memory by the kernels with 16-byte loads.
+__device__ __align__(16) uint16_t g_huff_lut[4][512];
+__global__ void k_huff_lut_build()
+{
+    for (uint32_t i = threadIdx.x; i < 4 * 512; i += blockDim.x) g_huff_lut[i >> 9][i & 511] = huff_entry(i >> 9, i & 511);
+}
+__device__ __forceinline__ void huff_lut_to_shared(uint16_t (*lut)[512])
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(&g_huff_lut[0][0]);
+    uint4 *dst = reinterpret_cast<uint4 *>(&lut[0][0]);
+    for (uint32_t i = threadIdx.x; i < 4 * 512 * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
 struct DecodeJob {
@@ -2244,7 +2263,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_BLOCKS) k_mlp_decode(M
     if (m.fast && !*m.any_fallback) return;              // the fast path kept every segment
     uint4 (*ring)[RING_SLOTS][DVDA_LANES] = reinterpret_cast<uint4 (*)[RING_SLOTS][DVDA_LANES]>(dyn_smem);
     uint16_t (*lut)[512] = reinterpret_cast<uint16_t (*)[512]>(dyn_smem + DEC_WARPS * RING_SLOTS * DVDA_LANES);
-    for (uint32_t i = threadIdx.x; i < 4 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry(i >> 9, i & 511);
+    huff_lut_to_shared(lut);
     __syncthreads();
     const uint32_t wib = threadIdx.x >> 5;
     const uint32_t warp = blockIdx.x * DEC_WARPS + wib;
@@ -2339,7 +2358,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_entropy(MlpTables m, con
     extern __shared__ uint4 dyn_smem[];
     uint4 (*ring)[RING_SLOTS][DVDA_LANES] = reinterpret_cast<uint4 (*)[RING_SLOTS][DVDA_LANES]>(dyn_smem);
     uint16_t (*lut)[512] = reinterpret_cast<uint16_t (*)[512]>(dyn_smem + DEC_WARPS * RING_SLOTS * DVDA_LANES);
-    for (uint32_t i = threadIdx.x; i < 4 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry(i >> 9, i & 511);
+    huff_lut_to_shared(lut);
     __syncthreads();
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * DEC_WARPS + wib;
@@ -2470,10 +2489,10 @@ int launch_mlp_decode(MlpTables m, const DecWork *const work[5], const uint32_t 
 #define FIX_THREADS 32
 __global__ void __launch_bounds__(FIX_THREADS) k_carry_fix(MlpTables m)
 {
-    __shared__ uint16_t lut[4][512];
+    __shared__ __align__(16) uint16_t lut[4][512];
     __shared__ uint4 ring[RING_SLOTS][DVDA_LANES];
     if (m.fast && !*m.any_fallback) return;              // nothing was handed to the complete decoder
-    for (uint32_t i = threadIdx.x; i < 4 * 512; i += blockDim.x) lut[i >> 9][i & 511] = huff_entry(i >> 9, i & 511);
+    huff_lut_to_shared(lut);
     __syncthreads();
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t seg = idx >> 1, k = idx & 1;
