@@ -537,7 +537,8 @@ __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tr
                               GroupDev *__restrict__ groups, uint32_t ngroups, uint32_t *__restrict__ grp_cells,
                               uint32_t *__restrict__ grp_chunks, uint32_t *__restrict__ max_au)
 {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per group, lane = segment of the group
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (g >= ngroups) return;
     const uint32_t t = upper_bound_dev(trk_grp_base, n_tracks, g) - 1;
     const TrackDev &T = tracks[t];
@@ -546,14 +547,15 @@ __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tr
     G.track = t;
     G.seg0 = T.seg_base + j * DVDA_LANES;
     G.nseg = min((uint32_t)DVDA_LANES, T.nseg - j * DVDA_LANES);
-    uint32_t cap = 0, most = 0;
-    for (uint32_t l = 0; l < G.nseg; l++) {
-        const SegDev &S = segs[G.seg0 + l];
-        most = max(most, S.n_au);
+    uint32_t need = 0, n_au = 0;
+    if (lane < G.nseg) {
+        const SegDev &S = segs[G.seg0 + lane];
+        n_au = S.n_au;
         // second attempt after an overflow: the frame counts are known
-        const uint32_t need = (S.flags & SEG_OVERFLOW) ? S.frames : S.n_au * T.au_nominal;
-        cap = max(cap, need);
+        need = (S.flags & SEG_OVERFLOW) ? S.frames : n_au * T.au_nominal;
     }
+    const uint32_t cap = __reduce_max_sync(0xFFFFFFFFu, need), most = __reduce_max_sync(0xFFFFFFFFu, n_au);
+    if (lane) return;
     G.cap = cap;
     G.tile_off = 0; G.byp_off = 0;
     groups[g] = G;
@@ -575,7 +577,7 @@ int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t
                        GroupDev *groups, uint32_t ngroups, uint32_t *grp_cells, uint32_t *grp_chunks, uint32_t *max_au, cudaStream_t s)
 {
     if (!ngroups) return 0;
-    LAUNCH(k_group_setup, div_up_u32(ngroups, 128), 128, 0, s, tracks, n_tracks, trk_grp_base, segs, groups, ngroups, grp_cells, grp_chunks, max_au);
+    LAUNCH(k_group_setup, div_up_u32((uint64_t)ngroups * 32, 128), 128, 0, s, tracks, n_tracks, trk_grp_base, segs, groups, ngroups, grp_cells, grp_chunks, max_au);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
