@@ -25,6 +25,20 @@
 #include "kernels.cuh"
 #include "../../include/dvdagpu.h"
 
+// "this kernel's attributes have been set on the current device" (function attributes are per
+// device; a process may run engines on several)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        const bool f = !done[dev];
+        done[dev] = true;
+        return f;
+    }
+};
+
 // ------------------------------------------------------------- check data
 
 __constant__ uint8_t c_crc8[256];   // CRC-8 poly 0x63, built by the engine
@@ -309,10 +323,9 @@ int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         CUDA_TRY(cudaFuncSetAttribute(k_checkdata, cudaFuncAttributeMaxDynamicSharedMemorySize, CHK_SMEM_BYTES));
-        attr_set = true;
     }
     LAUNCH(k_checkdata, div_up_u32(m.nau, CHK_THREADS), CHK_THREADS, CHK_SMEM_BYTES, s, m, seg_au_base);
     CUDA_TRY(cudaGetLastError());
@@ -2225,10 +2238,9 @@ static int launch_one_filter_out(MlpTables m, const DecWork *work, uint32_t n_wo
     if (!n_warps) return 0;
     constexpr int SPW = 32 / NCH, SUB = (32 + SPW - 1) / SPW;
     const size_t smem = (size_t)OUT_WARPS * SPW * (2 * (32 * NCH + 4) + 4) * sizeof(int32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     LAUNCH(k_mlp_filter_out<NCH>, div_up_u32((uint64_t)n_warps * SUB, OUT_WARPS), OUT_WARPS * 32, smem, s, m, work, n_work, n_warps);
     return 0;
@@ -2417,10 +2429,9 @@ template <int NCH>
 static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
 {
     if (!n_warps) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         CUDA_TRY(cudaFuncSetAttribute(k_mlp_entropy<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES));
-        attr_set = true;
     }
     const uint32_t blocks = div_up_u32(n_warps, DEC_WARPS);
     const uint32_t small = div_up_u32(n_warps, 4);
@@ -2461,10 +2472,9 @@ template <int NCH>
 static int launch_one_decode(MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
 {
     if (!n_warps) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES));
-        attr_set = true;
     }
     LAUNCH(k_mlp_decode<NCH>, div_up_u32(n_warps, DEC_WARPS), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
     return 0;
@@ -2745,10 +2755,9 @@ int launch_rematrix(MlpTables m, uint32_t max_chunks, uint32_t channel_mask, cud
     if (!max_chunks || !m.ngroups) return 0;
     const dim3 grid(m.ngroups, max_chunks);
     const size_t smem = (size_t)(DVDA_MAX_CH + 1) * 32 * 33 * sizeof(int32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         CUDA_TRY(cudaFuncSetAttribute(k_rematrix<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     // channel_mask: bit n = some MLP track of the batch has n channels
     if (channel_mask & 2) LAUNCH(k_rematrix<1>, grid, RM_THREADS, (size_t)2 * 32 * 33 * 4, s, m);

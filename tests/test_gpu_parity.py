@@ -260,6 +260,26 @@ def test_title_set_sharded_like_eight_ranks(pkg, oracle, engine, disc_cache):
     assert sorted(seen) == list(range(64))
 
 
+def test_two_devices_in_one_process(pkg, oracle, disc_cache):
+    """Engines on two GPUs of the box in one process (kernel attributes are per device)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    directory, _ = disc_cache("c5_mixed")
+    sectors = oracle.read_aobs(directory)
+    golden = GOLDEN["c5_mixed"]["tracks"]
+    engines = [pkg.Engine(0), pkg.Engine(1)]
+    try:
+        for eng in engines + engines[:1]:
+            res = eng.decode_host(sectors, [(g["first"], g["last"], g["pts"]) for g in golden])
+            for r, g in zip(res, golden):
+                assert r.status == 0 and r.frames == g["frames"]
+                assert oracle.fnv1a(eng.fetch(r)) == g["fnv"], (g["title"], g["track"])
+    finally:
+        for eng in engines:
+            eng.close()
+
+
 def test_device_resident_input(pkg, oracle, engine, disc_cache):
     """Sectors already in HBM (a torch tensor), engine on torch's stream."""
     import torch
