@@ -489,13 +489,26 @@ int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t nseg, const TrackD
 
 __global__ void k_yield_mark(MlpTables m, const uint32_t *__restrict__ seg_au_base, uint8_t *__restrict__ pk_yield)
 {
+    // The access units of a warp follow each other in the stream and end within a handful of
+    // packets: the warp searches the packet of its first access unit together (32 probes and a
+    // ballot per round), the lanes walk on from there.
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= m.nau) return;
-    const uint64_t pos = m.au_pos[a];
-    const uint32_t total = (((ld_u8(m.es + pos) & 15u) << 8) | ld_u8(m.es + pos + 1)) * 2;
-    const uint64_t last_byte = pos + total - 1;
-    const uint32_t pk = upper_bound_dev(m.pk_es, m.np + 1, last_byte) - 1;
-    pk_yield[pk] = 1;
+    const bool have = a < m.nau;
+    if (!__any_sync(0xFFFFFFFFu, have)) return;
+    uint64_t last_byte = 0;
+    if (have) {
+        const uint64_t pos = m.au_pos[a];
+        const uint32_t total = (((ld_u8(m.es + pos) & 15u) << 8) | ld_u8(m.es + pos + 1)) * 2;
+        last_byte = pos + total - 1;
+    }
+    const uint64_t x0 = __shfl_sync(0xFFFFFFFFu, last_byte, 0);          // lane 0 has the lowest access unit
+    const uint64_t *pk_es = m.pk_es;
+    uint32_t pk = warp_first_true(0u, m.np + 1, [=](uint32_t i) { return pk_es[i] > x0; }) - 1;
+    if (have) {
+        if (last_byte < x0) pk = upper_bound_dev(m.pk_es, m.np + 1, last_byte) - 1;   // (not in stream order: on its own)
+        else while (pk + 1 <= m.np && pk_es[pk + 1] <= last_byte) pk++;
+        pk_yield[pk] = 1;
+    }
     (void)seg_au_base;
 }
 
