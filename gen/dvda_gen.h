@@ -86,6 +86,9 @@ int dvda_gen_disc(const char *dir,
 
 const char *dvda_gen_error(void);
 
+/* 64-bit FNV-1a, continuing from h (the per-track hash oracle/api_dump.c prints) */
+uint64_t dvda_gen_fnv1a(const void *data, uint64_t nbytes, uint64_t h);
+
 #ifdef __cplusplus
 }
 #endif

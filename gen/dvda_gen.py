@@ -93,6 +93,8 @@ def lib():
             ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int32),
             ctypes.POINTER(Track), ctypes.POINTER(Info), ctypes.c_uint64]
         _lib.dvda_gen_error.restype = ctypes.c_char_p
+        _lib.dvda_gen_fnv1a.restype = ctypes.c_uint64
+        _lib.dvda_gen_fnv1a.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
     return _lib
 
 
@@ -166,3 +168,19 @@ def make_disc_multi(directory, titlesets, max_aob_bytes=0):
     data[63] = len(titlesets)
     open(path, "wb").write(bytes(data))
     return out
+
+
+def fnv1a(samples):
+    """64-bit FNV-1a over the little-endian bytes of an int32 array (numpy, or anything with
+    the buffer protocol), as oracle/api_dump.c prints it: 16 hex digits."""
+    import numpy as np
+    a = np.ascontiguousarray(samples)
+    if a.dtype != np.dtype("<i4"):
+        a = a.astype("<i4")
+    h = lib().dvda_gen_fnv1a(ctypes.c_void_p(a.ctypes.data), a.nbytes, 0xCBF29CE484222325)
+    return "%016x" % h
+
+
+def fnv1a_ptr(ptr, nbytes):
+    """The same over raw memory (e.g. a pinned torch tensor's data_ptr())."""
+    return "%016x" % lib().dvda_gen_fnv1a(ctypes.c_void_p(ptr), nbytes, 0xCBF29CE484222325)

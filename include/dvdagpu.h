@@ -112,7 +112,8 @@ enum {
     DVDAGPU_K_MLP_FILTER = 10,  /* three-pass path, C: FIR/IIR prediction, one lane per channel (2 substreams) */
     DVDAGPU_K_MLP_FILTER_OUT = 11, /* three-pass path, C (1 substream): prediction + rematrix + interleaved output */
     DVDAGPU_K_MLP_AU_PARSE = 12, /* three-pass path, A1: parameter block of every access unit, as a delta */
-    DVDAGPU_K_MLP_RESOLVE = 13   /* three-pass path, A2: parameter chain of every segment resolved per access unit */
+    DVDAGPU_K_MLP_RESOLVE = 13,  /* three-pass path, A2: parameter chain of every segment resolved per access unit */
+    DVDAGPU_K_MLP_FUSED = 14     /* default path: entropy decode + prediction + rematrix + interleaved output, one lane per channel */
 };
 
 /* number of CUDA devices the engine can use (0 = none) */

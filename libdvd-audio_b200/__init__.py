@@ -71,7 +71,7 @@ class Stats(ctypes.Structure):
                 ("kernel_ms", ctypes.c_float * 16)]
 
 KERNEL_NAMES = ["es_gather", "sync_scan", "au_chase", "checkdata", "mlp_decode", "carry_fix", "rematrix", "pcm_unpack",
-                "mlp_segctx", "mlp_entropy", "mlp_filter", "mlp_filter_out", "mlp_au_parse", "mlp_resolve"]
+                "mlp_segctx", "mlp_entropy", "mlp_filter", "mlp_filter_out", "mlp_au_parse", "mlp_resolve", "mlp_fused"]
 
 
 _engine = None

@@ -20,7 +20,7 @@ HOST_LIB = os.path.join(LIBDIR, "libdvd-audio.so")
 DUMP_BIN = os.path.join(LIBDIR, "b200_dump")
 WAV_BIN = os.path.join(LIBDIR, "dvda2wav")
 
-CU_FILES = ["scan.cu", "demux.cu", "mlp_index.cu", "mlp_decode.cu", "engine.cu"]
+CU_FILES = ["scan.cu", "demux.cu", "mlp_index.cu", "mlp_decode.cu", "mlp_fused.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I", INCLUDE,
@@ -46,8 +46,8 @@ def _run(cmd, verbose):
 
 def build_engine(force=False, verbose=False, ptxas_info=False):
     os.makedirs(OBJDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.cuh")] + [os.path.join(INCLUDE, "dvdagpu.h")]
-    objs = []
+    headers = [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.cuh", "mlp_common.cuh")] + [os.path.join(INCLUDE, "dvdagpu.h")]
+    objs, jobs = [], []
     for cu in CU_FILES:
         src = os.path.join(CSRC, cu)
         obj = os.path.join(OBJDIR, cu.replace(".cu", ".o"))
@@ -55,8 +55,13 @@ def build_engine(force=False, verbose=False, ptxas_info=False):
             flags = list(NVCC_FLAGS) + os.environ.get("DVDA_NVCC_EXTRA", "").split()
             if ptxas_info:
                 flags += ["-Xptxas", "-v"]
-            _run([_nvcc()] + flags + ["-c", src, "-o", obj], verbose)
+            jobs.append([_nvcc()] + flags + ["-c", src, "-o", obj])
         objs.append(obj)
+    if jobs:
+        # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda cmd: _run(cmd, verbose), jobs))
     if force or _newer(ENGINE_LIB, objs):
         _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", ENGINE_LIB] + objs, verbose)
     return ENGINE_LIB

@@ -39,6 +39,7 @@
 #define SEG_FALLBACK 8u        // the three-pass fast path gave up: decode with the complete decoder
 #define SEG_WANTS_PREV 16u     // ... because it needs the previous segment's FIR history
 #define STATUS_WANTS_REMATRIX 0x100u   // k_seg_finalize -> host: some segment still needs k_rematrix (fast path)
+#define STATUS_REDO 0x400u             // fused pass -> host: a segment it had taken turned out not to be for it (now flagged): decode again
 #define STATUS_PCM_SMALL 0x200u        // k_track_out_base -> output pass, host: the samples do not fit the buffer sized in advance
 
 // TrackDev.cont / dvdagpu_track_desc.flags

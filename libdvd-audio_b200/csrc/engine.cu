@@ -112,7 +112,7 @@ enum {
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
     B_SS_FLAGS, B_SS_FLAGS_PREV, B_SS_FLAGS_FAST, B_FIR_TAIL,
     B_GROUPS, B_GRP_CELLS, B_CELL_BASE, B_GRP_CHUNKS, B_GRP_CHUNK_BASE,
-    B_DEC_WORK, B_AU_SEG, B_AU_SNAP, B_FILT_SNAP, B_AU_FCHG, B_SEG_CTX, B_AU_DELTA, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_AU_NOTED, B_PCM,
+    B_DEC_WORK, B_FUSED_WORK, B_SS_STICKY, B_AU_SEG, B_AU_SNAP, B_FILT_SNAP, B_AU_FCHG, B_SEG_CTX, B_AU_DELTA, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_AU_NOTED, B_PCM,
     B_COUNT
 };
 
@@ -139,6 +139,7 @@ struct dvdagpu_ctx {
     dvdagpu_stats stats;
     uint64_t pcm_samples;
     std::vector<TrackDev> h_tracks;
+    const uint16_t *huff_lut = nullptr;       // device address of the Huffman table (per device)
 };
 
 // ---- constant tables, derived (not copied) --------------------------------
@@ -237,6 +238,8 @@ extern "C" dvdagpu_ctx *dvdagpu_create(int device)
     build_pcm_tables(pcm_tab);
     build_crc8(crc);
     if (upload_pcm_tables(&pcm_tab[0][0][0]) || upload_crc_table(crc)) { dvdagpu_destroy(c); return nullptr; }
+    c->huff_lut = huff_lut_device();
+    if (!c->huff_lut) { dvdagpu_set_error("no Huffman table on the device"); dvdagpu_destroy(c); return nullptr; }
     return c;
 }
 
@@ -651,6 +654,40 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     TRY(queue_h2d(c, trk_seg_base, h_seg_base.data(), (n_tracks + 1) * 4));
     TRY(queue_h2d(c, trk_grp_base, h_grp_base.data(), (n_tracks + 1) * 4));
 
+    // decode mode: the three-pass path (default), the header passes + the fused entropy / filter /
+    // output pass (DVDAGPU_FUSED=1: no tiles in HBM, but measured slower — DESIGN.md section 6), or the
+    // complete single-pass decoder alone (DVDAGPU_SINGLE_PASS=1); the GPU tests run all three
+    const int mode = getenv("DVDAGPU_SINGLE_PASS") ? 0 : getenv("DVDAGPU_FUSED") ? 2 : 1;
+    // work lists of the fused pass, by class (0: at most two channels per substream, 1: up to four):
+    // a run of warps per track
+    std::vector<FusedWork> h_fused[2];
+    uint32_t n_fwarps[2] = {0, 0};
+    if (mode == 2) {
+        for (uint32_t i = 0; i < n_tracks; i++) {
+            if (!ht[i].nseg) continue;
+            uint32_t n0 = ht[i].channels, n1 = 0;
+            if (ht[i].nss == 2) { n0 = 2; n1 = ht[i].channels > 2 ? ht[i].channels - 2 : 0; if (!n1) continue; }
+            else if (ht[i].nss != 1) continue;
+            if (n0 < 1 || n0 > 4 || n1 > 4) continue;
+            const int cl = (n0 > 2 || n1 > 2) ? 1 : 0;
+            FusedWork w = {n_fwarps[cl], i, n0, n1};
+            h_fused[cl].push_back(w);
+            n_fwarps[cl] += ht[i].ngrp * fused_warps_per_group(n0, n1);
+        }
+    }
+    const FusedWork *d_fused[2] = {nullptr, nullptr};
+    uint32_t n_fused[2] = {0, 0};
+    {
+        ENSURE(B_FUSED_WORK, (h_fused[0].size() + h_fused[1].size() + 1) * sizeof(FusedWork));
+        FusedWork *base = c->buf[B_FUSED_WORK].as<FusedWork>();
+        size_t off = 0;
+        for (int cl = 0; cl < 2; cl++) {
+            n_fused[cl] = (uint32_t)h_fused[cl].size();
+            d_fused[cl] = base + off;
+            if (n_fused[cl]) TRY(queue_h2d(c, base + off, h_fused[cl].data(), n_fused[cl] * sizeof(FusedWork)));
+            off += n_fused[cl];
+        }
+    }
     const DecWork *d_work[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t n_work[5] = {0, 0, 0, 0, 0};
     {
@@ -677,7 +714,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     ENSURE(B_STATUS, 64);
     uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
     m.status = d_status;
+    m.status_rw = d_status;
     m.any_fallback = d_status + 8;
+    m.huff_lut = c->huff_lut;
     // samples of the PCM tracks (known since the track set-up) and the alignment gaps
     uint64_t pcm_fixed = 4ull * n_tracks + 64;
     for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].status == 0 && ht[i].codec == 0) pcm_fixed += ht[i].frames * ht[i].channels;
@@ -749,8 +788,11 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         // The three-pass path (access-unit parallel) decodes what has the common shape; the complete
         // single-pass decoder takes the rest.  DVDAGPU_SINGLE_PASS=1 gives everything to the latter
         // (the GPU tests run both ways).
-        const bool use_fast = getenv("DVDAGPU_SINGLE_PASS") == nullptr;
+        const bool use_fast = mode != 0;
         if (use_fast) {
+            ENSURE(B_SS_STICKY, (size_t)nseg * 2 * 4);
+            m.ss_sticky = c->buf[B_SS_STICKY].as<uint32_t>();
+            CUDA_TRY(cudaMemsetAsync(m.ss_sticky, 0, (size_t)nseg * 2 * 4, s));
             m.nss_max = 1;
             for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].nseg && ht[i].nss > m.nss_max) m.nss_max = ht[i].nss;
             // per-substream tables: [nss_max][nau] (the kernels index them as k * nau + A)
@@ -764,9 +806,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             // contexts exist only where pass A0 goes (substreams of up to four channels)
             CUDA_TRY(cudaMemsetAsync(m.seg_ctx, 0, (size_t)nseg * 2 * seg_ctx_bytes(), s));
         }
-        for (int attempt = 0; attempt < 2; attempt++) {
+        for (int attempt = 0;; attempt++) {
             if (attempt) {
                 // after a tile overflow: the groups again, from the frame counts now known
+                // (after a STATUS_REDO of the fused pass the same steps are simply repeated)
                 CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
                 TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, d_status + 1, s));
                 TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
@@ -784,10 +827,10 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
                 // (start with every segment flagged: substreams with more than 4 channels
                 // are not visited by the fast path at all)
                 CUDA_TRY(cudaMemsetAsync(m.ss_flags, SEG_FALLBACK, (size_t)nseg * 2 * 4, s));
-                TRY(launch_mlp_fast(m, d_work, n_work, n_warps, c->kev, c->kev_used, c->aux_ev[1], s));
+                TRY(launch_mlp_fast(m, d_work, n_work, n_warps, c->kev, c->kev_used, c->aux_ev[1], mode == 2, s));
                 CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
                 CUDA_TRY(cudaMemcpyAsync(m.ss_flags_fast, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
-                m.fast = 1;
+                m.fast = (uint32_t)mode;
             }
             CUDA_TRY(cudaStreamWaitEvent(s, c->aux_ev[1], 0));
             // ... and decoded by the complete single-pass decoder (everything, without the fast path)
@@ -810,10 +853,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             LAUNCH(k_track_out_base, 1, OB_THREADS, 0, s, d_tracks, n_tracks, d_status, pcm_capacity);
             CUDA_TRY(cudaEventRecord(c->ev[3], s));
             out_queued = m.fast != 0;
-            if (out_queued) TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
+            if (m.fast == 1) TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
+            if (m.fast == 2) TIMED(DVDAGPU_K_MLP_FUSED, launch_mlp_fused(m, d_fused, n_fused, n_fwarps, s));
             TRY(small_d2h_pair(c, &status, d_status, 4, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
-            if (!(status & SEG_OVERFLOW)) break;
-            if (attempt == 1) { dvdagpu_set_error("tile overflow persists"); return -1; }
+            if (!(status & (SEG_OVERFLOW | STATUS_REDO))) break;
+            // (a redo flags at least one more segment each time; an overflow is settled by the second attempt)
+            if (attempt == 8) { dvdagpu_set_error((status & SEG_OVERFLOW) ? "tile overflow persists" : "the fused pass keeps asking for another attempt"); return -1; }
         }
     } else {
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
@@ -863,8 +908,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         out_queued = false;
     }
     if (nseg && m.fast && !out_queued) {
-        // fast path, single-substream tracks: filters + rematrix + interleaved output in one pass
-        TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
+        // fast path: filters (+ entropy decode) + rematrix + interleaved output in one pass
+        if (m.fast == 1) TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
+        else TIMED(DVDAGPU_K_MLP_FUSED, launch_mlp_fused(m, d_fused, n_fused, n_fwarps, s));
     }
     if (nseg && max_chunks && (!m.fast || (status & STATUS_WANTS_REMATRIX))) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, max_chunks, mlp_channel_mask, s));
     if (any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, np, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));

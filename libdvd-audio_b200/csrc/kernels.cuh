@@ -50,10 +50,14 @@ struct MlpTables {
     uint8_t *au_fchg;              // [2][nau]: bit cc = the filter set-up of channel cc changes with this access unit
     SegCtx *seg_ctx;               // [2][nseg]
     AuDelta *au_delta;             // [2][nau], written where the AU brings parameters
-    uint32_t fast;                 // 1: the complete decoder only takes segments flagged SEG_FALLBACK
+    uint32_t fast;                 // 1, 2: the complete decoder only takes segments flagged SEG_FALLBACK
+                                   // (1: three-pass path, 2: header passes + fused entropy/filter/output pass)
     uint32_t max_au;               // largest access-unit count of a segment
     const uint32_t *status;        // the batch's status word (SEG_OVERFLOW, STATUS_*)
     uint32_t *any_fallback;        // set by the flag kernels of the fast path when the complete decoder has work at all
+    uint32_t *ss_sticky;           // [2][nseg] SEG_FALLBACK the fused pass asked for (it found out too late: the decode is repeated)
+    uint32_t *status_rw;           // the batch's status word, for the kernels that set bits in it
+    const uint16_t *huff_lut;      // [4][512] Huffman look-up table in device memory (built once per device)
 };
 
 // demux.cu
@@ -120,8 +124,17 @@ size_t au_snap_bytes();
 size_t seg_ctx_bytes();
 size_t au_delta_bytes();
 // fast path: pass A (headers), B (entropy, one lane per access unit), C (filters, one lane per channel)
+// headers_only: passes A0 .. A2 alone (the fused pass does the rest)
 int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
-                    cudaEvent_t (*kev)[2], bool *kev_used, cudaEvent_t checked, cudaStream_t s);
+                    cudaEvent_t (*kev)[2], bool *kev_used, cudaEvent_t checked, bool headers_only, cudaStream_t s);
+const uint16_t *huff_lut_device();      // address of the table on the current device
+
+// mlp_fused.cu: entropy decode + prediction + rematrix + interleaved output in one pass.
+// A run of warps: the groups of one track, SUB warps each (lanes = (segment, channel) over both substreams).
+struct FusedWork { uint32_t warp0, track, n0, n1; };     // n0, n1: channels of substream 0 / 1 (n1 = 0: one substream)
+// work[c], n_work[c], n_warps[c] for class c: 0 = at most two channels per substream, 1 = up to four
+int launch_mlp_fused(MlpTables m, const FusedWork *const work[2], const uint32_t n_work[2], const uint32_t n_warps[2], cudaStream_t s);
+uint32_t fused_warps_per_group(uint32_t n0, uint32_t n1);
 int launch_seg_finalize(MlpTables m, uint32_t *seg_frames, uint32_t *status, cudaStream_t s);
 int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, const uint32_t *status, cudaStream_t s);
 int launch_rematrix(MlpTables m, uint32_t max_chunks, uint32_t channel_mask, cudaStream_t s);

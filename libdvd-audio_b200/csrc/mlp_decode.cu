@@ -23,21 +23,9 @@
 // matrices, LSB bypass and output shift, and writes interleaved frames.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "mlp_common.cuh"
 #include "../../include/dvdagpu.h"
 
-// "this kernel's attributes have been set on the current device" (function attributes are per
-// device; a process may run engines on several)
-struct PerDeviceOnce {
-    bool done[64] = {};
-    bool first()
-    {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-        const bool f = !done[dev];
-        done[dev] = true;
-        return f;
-    }
-};
 
 // ------------------------------------------------------------- check data
 
@@ -324,161 +312,12 @@ int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
         return 0;
     }
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) {
-        CUDA_TRY(cudaFuncSetAttribute(k_checkdata, cudaFuncAttributeMaxDynamicSharedMemorySize, CHK_SMEM_BYTES));
-    }
+    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_checkdata, cudaFuncAttributeMaxDynamicSharedMemorySize, CHK_SMEM_BYTES)); return 0; })) return -1;
     LAUNCH(k_checkdata, div_up_u32(m.nau, CHK_THREADS), CHK_THREADS, CHK_SMEM_BYTES, s, m, seg_au_base);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-// ------------------------------------------------------------- bit reader
-
-// MSB-first reader over the elementary stream (reference src/bitstream.c:1077-1111).
-//
-// Every lane walks its own stream, so plain loads would miss in a different
-// cache line per lane and — worse — any per-lane "refill when low" branch
-// diverges: an event that is rare for one lane happens almost every step for
-// some lane of the warp.  So:
-//   * each lane owns a 256-byte ring in shared memory (four 64-byte chunks),
-//     layout [16-byte slot][lane];
-//   * it fills the ring itself with cp.async (16 bytes per copy, L2 -> shared),
-//     at warp-uniform points (top of every 8-frame iteration): up to two chunks,
-//     always two commit groups, then wait_group 2 — everything issued in earlier
-//     iterations has landed, nothing ever waits on DRAM in steady state;
-//   * the hot loop tops the 64-bit window up without branching (the load from
-//     the ring is unconditional, the merge is predicated).
-// Headers use the same reader through the checked (cold) entry points.
-#ifndef DVDA_UNROLL
-#define DVDA_UNROLL 8
-#endif
-#ifndef RING_SLOTS
-#define RING_SLOTS 16                 // 16-byte slots per lane: 256 bytes
-#endif
-#ifndef CHUNK_WORDS
-#define CHUNK_WORDS 16                // 64 bytes per cp.async group
-#endif
-#define CHUNK_SLOTS (CHUNK_WORDS / 4)
-#define RING_WORDS (RING_SLOTS * 4)
-
-struct Rd {
-    const uint8_t *es;      // elementary stream (global)
-    uint32_t ring;          // shared-memory address of this lane's slot 0
-    uint64_t win;           // upcoming bits, MSB aligned
-    int32_t avail;          // valid bits in win
-    uint32_t next_w;        // absolute word index of the next word to pull
-    uint32_t fill_c;        // chunks [.., fill_c) have been issued
-    uint32_t safe_w;        // words [.., safe_w) are known to have landed
-    uint32_t base_w;        // word index the bit counter is relative to
-    uint32_t ahead;         // hot loop only: ring word next_w, fetched one step early
-};
-
-__device__ __forceinline__ void cp_async16(uint32_t smem, const void *g)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void rd_issue_chunk(Rd &r, uint32_t c)
-{
-    const uint8_t *g = r.es + (uint64_t)c * (CHUNK_WORDS * 4);
-#pragma unroll
-    for (int t = 0; t < CHUNK_SLOTS; t++) cp_async16(r.ring + (((c * CHUNK_SLOTS + t) & (RING_SLOTS - 1)) << 9), g + t * 16);
-}
-// may chunk fill_c be written?  Its slot held chunk fill_c - 8, which must lie
-// entirely behind the read position (the slot held chunk fill_c - RING_CHUNKS).
-#define RING_CHUNKS (RING_SLOTS / CHUNK_SLOTS)
-__device__ __forceinline__ bool rd_room(const Rd &r) { return (int32_t)((r.fill_c - (RING_CHUNKS - 1)) * CHUNK_WORDS - r.next_w) <= 0; }
-
-__device__ __forceinline__ void rd_init(Rd &r, const uint8_t *es, uint32_t ring)
-{
-    r.es = es; r.ring = ring; r.win = 0; r.avail = 0; r.next_w = 0; r.fill_c = 0; r.safe_w = 0; r.base_w = 0;
-}
-
-// cold: make sure words [next_w, next_w + need) are in the ring
-__device__ __forceinline__ void rd_slow_fill(Rd &r, uint32_t need)
-{
-    while (r.fill_c * CHUNK_WORDS < r.next_w + need + CHUNK_WORDS && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
-    cp_commit();
-    cp_wait<0>();
-    r.safe_w = r.fill_c * CHUNK_WORDS;
-}
-
-// warp-uniform prefetch point: keep the ring ~6 chunks ahead of the reader and
-// guarantee that the next `need` words have landed (the hot loop reads them
-// without checking).  In steady state the guarantee holds by construction;
-// right after a long header it may not, then the lane takes the slow path.
-__device__ __forceinline__ void rd_prefetch(Rd &r, uint32_t need)
-{
-    const uint32_t landed = r.fill_c * CHUNK_WORDS;
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-#pragma unroll
-        for (int u = 0; u < 16 / CHUNK_WORDS; u++)
-            if (r.fill_c * CHUNK_WORDS < r.next_w + RING_WORDS - CHUNK_WORDS && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
-        cp_commit();
-    }
-    cp_wait<2>();
-    r.safe_w = landed;
-    if (r.next_w + need > r.safe_w) rd_slow_fill(r, need);
-}
-
-// fill the whole ring ahead of the reader without waiting (cold starts: one DRAM
-// latency then covers ~450 bytes, about one access unit)
-__device__ __forceinline__ void rd_issue_ahead(Rd &r)
-{
-    while (r.fill_c * CHUNK_WORDS < r.next_w + RING_WORDS - CHUNK_WORDS && rd_room(r)) { rd_issue_chunk(r, r.fill_c); r.fill_c++; }
-    cp_commit();
-}
-
-// position the reader at an absolute byte offset
-__device__ __forceinline__ void rd_seat(Rd &r, uint64_t byte_pos)
-{
-    const uint32_t w = (uint32_t)(byte_pos >> 2);
-    if (w >= r.fill_c * CHUNK_WORDS || w + RING_WORDS - CHUNK_WORDS < r.fill_c * CHUNK_WORDS) {
-        cp_wait<0>();                       // nothing may still be landing in slots we reuse
-        r.fill_c = w / CHUNK_WORDS;
-        r.safe_w = r.fill_c * CHUNK_WORDS;
-    }
-    r.next_w = w;
-    r.base_w = w;
-    r.win = 0;
-    r.avail = 0;
-}
-
-__device__ __forceinline__ uint32_t rd_ring_word(const Rd &r, uint32_t w)
-{
-    uint32_t word;
-    const uint32_t addr = r.ring + (((w >> 2) & (RING_SLOTS - 1)) << 9) + ((w & 3) << 2);
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr) : "memory");
-    return __byte_perm(word, 0, 0x0123);
-}
-
-// checked pull (headers, generic path): avail must be <= 32
-__device__ __forceinline__ void rd_pull(Rd &r)
-{
-    if (r.next_w >= r.safe_w) rd_slow_fill(r, 48);
-    const uint32_t word = rd_ring_word(r, r.next_w);
-    r.win |= (uint64_t)word << (32 - r.avail);
-    r.avail += 32;
-    r.next_w++;
-}
-
-// hot pull: no branch; afterwards avail > 32.  The caller guarantees (through
-// rd_prefetch) that the next words have landed.  The ring word is fetched one
-// step ahead (r.ahead) so that the shared-memory latency is off the critical
-// path of the window; rd_hot_begin() primes it.
-__device__ __forceinline__ void rd_hot_begin(Rd &r) { r.ahead = rd_ring_word(r, r.next_w); }
-__device__ __forceinline__ void rd_top_up(Rd &r)
-{
-    const bool need = r.avail <= 32;
-    const uint64_t add = (uint64_t)r.ahead << ((32 - r.avail) & 63);
-    r.win |= need ? add : 0ull;
-    r.avail += need ? 32 : 0;
-    r.next_w += need ? 1u : 0u;
-    r.ahead = rd_ring_word(r, r.next_w);
-}
 
 // ---- reader for the header-only passes.  The 128 bytes behind a seat are fetched with
 // eight independent 16-byte loads into the thread's column of a shared-memory window
@@ -540,39 +379,6 @@ __device__ __forceinline__ void rd_pull(GRd &r)
     r.next_w++;
 }
 
-// next n bits (1..32) without consuming them
-template <typename RD>
-__device__ __forceinline__ uint32_t rd_peek(RD &r, uint32_t n)
-{
-    if (r.avail < (int32_t)n) rd_pull(r);
-    return (uint32_t)(r.win >> (64 - n));
-}
-template <typename RD>
-__device__ __forceinline__ void rd_drop(RD &r, uint32_t n) { r.win <<= n; r.avail -= n; }
-template <typename RD>
-__device__ __forceinline__ uint32_t rd_get(RD &r, uint32_t n)
-{
-    if (!n) return 0;
-    const uint32_t v = rd_peek(r, n);
-    rd_drop(r, n);
-    return v;
-}
-// two's complement, n in 1..32 (src/bitstream.c:1198-1206)
-template <typename RD>
-__device__ __forceinline__ int32_t rd_get_s(RD &r, uint32_t n)
-{
-    const uint32_t v = rd_get(r, n);
-    return (int32_t)(v << (32 - n)) >> (32 - n);
-}
-template <typename RD>
-__device__ __forceinline__ void rd_skip(RD &r, uint32_t n)
-{
-    while (n > 32) { rd_get(r, 32); n -= 32; }
-    rd_get(r, n);
-}
-// bits consumed since the reader was seated (counted from the seated word's first bit)
-template <typename RD>
-__device__ __forceinline__ uint32_t rd_pos(const RD &r) { return (r.next_w - r.base_w) * 32 - r.avail; }
 
 // ------------------------------------------------------------ decoder state
 
@@ -795,23 +601,6 @@ __device__ __forceinline__ bool channel_setup(const SubState &s, const ChanState
     return true;
 }
 
-// LSB-bypass bits of one frame: one bit per matrix that has the flag, in matrix order
-__device__ __forceinline__ uint32_t bypass_bits(Rd &b, uint32_t want_mask)
-{
-    uint32_t out = 0;
-    if (want_mask) {
-        uint32_t t = __popc(want_mask);
-        const uint32_t bits = rd_get(b, t);
-        uint32_t m = want_mask;
-        while (m) {
-            const uint32_t k = __ffs(m) - 1;
-            m &= m - 1;
-            t--;
-            out |= ((bits >> t) & 1u) << k;
-        }
-    }
-    return out;
-}
 
 // ---- one block, generic: any channel count, histories in local memory --------
 
@@ -877,13 +666,6 @@ __device__ uint32_t decode_block_generic(const MlpTables &m, const GroupDev &G, 
 // beyond the transmitted orders carry zero coefficients, so every lane runs the
 // same 16 multiply-adds whatever its filter orders are (no divergence).
 
-// 32 x 32 -> 64-bit multiply-add in one instruction (IMAD.WIDE)
-__device__ __forceinline__ long long mad_wide(int32_t a, int32_t b, long long c)
-{
-    long long d;
-    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
 
 template <int NCH>
 struct Hot {
@@ -1034,11 +816,6 @@ __device__ __forceinline__ uint32_t decode_block_fast(const MlpTables &m, const 
     return n;
 }
 
-__device__ __forceinline__ uint32_t noise_step(uint32_t seed)
-{
-    const uint32_t sh = (seed >> 7) & 0xFFFF;
-    return (seed << 16) ^ sh ^ (sh << 5);
-}
 
 // access-unit header through the reader: "4p 12u 16p", optional major sync,
 // substream directory (mlp.c:392-394, 614-668).  Leaves the reader anywhere.
@@ -1236,31 +1013,6 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
 // k_carry_fix), which is the complete implementation.
 // =============================================================================
 
-// RIFF WAVE slot of MLP channel c (table at mlp.c:416-438): identity except for
-// assignments 0x12-0x14
-__device__ __forceinline__ uint32_t wave_slot(uint32_t assignment, uint32_t c)
-{
-    if (assignment == 0x12 || assignment == 0x13) return (0x24310u >> (4 * c)) & 15;      // 0,1,3,4,2
-    if (assignment == 0x14) return (0x325410u >> (4 * c)) & 15;                          // 0,1,4,5,2,3
-    return c;
-}
-
-struct ChanSnap { int32_t sho; uint8_t cb, lsb_bits, q, shift; };
-struct AuSnap {
-    uint64_t bit0;          // absolute bit position (in the ES) of the first residual bit
-    uint64_t bit_end;       // absolute bit position of the end of the substream data
-    uint16_t block_size;
-    uint8_t want, valid;
-    uint8_t min_ch, nch, has_matrix, pad1;
-    ChanSnap ch[4];
-};
-
-// noise generator advanced by n frames
-__device__ __forceinline__ uint32_t noise_advance(uint32_t seed, uint32_t n)
-{
-    for (uint32_t i = 0; i < n; i++) seed = noise_step(seed);
-    return seed;
-}
 
 // ---- pass A: headers ------------------------------------------------------------
 //
@@ -1281,40 +1033,6 @@ __device__ __forceinline__ uint32_t noise_advance(uint32_t seed, uint32_t n)
 // flags, a restart header in the middle of a segment and everything malformed give
 // the segment to the complete decoder.
 
-struct SegCtx { uint32_t seed; uint8_t min_ch, max_ch, mmc, flags, noise_shift, ok, pad[2]; };
-
-#define CD_PRESENT 1u
-#define CD_FIR 2u
-#define CD_IIR 4u
-#define CD_IIR_STATE 8u
-#define CD_OFFSET 16u
-#define AD_BLOCK 1u
-#define AD_MATRIX 2u
-#define AD_SHIFT 4u
-#define AD_Q 8u
-struct ChanHead {
-    int32_t huff_offset;
-    uint8_t fir_order, fir_shift, iir_order, iir_shift;
-    uint8_t codebook, huff_lsbs, present, pad;
-};
-struct ChanCoef {
-    int32_t ist[8];                  // IIR history as transmitted: [0] pairs with coefficient 0
-    int16_t fir_c[8], iir_c[8];
-};
-struct __align__(16) AuDelta {
-    // head (80 bytes): all the resolve pass looks at
-    uint16_t block_size;
-    uint8_t present, matrix_len;
-    uint8_t mat_out[DVDA_MAX_MAT], mat_bypass[DVDA_MAX_MAT];
-    uint8_t out_shift[DVDA_MAX_CH], q[DVDA_MAX_CH];
-    ChanHead ch[4];
-    // bulk
-    ChanCoef cf[4];
-    int16_t coeff[DVDA_MAX_MAT][DVDA_MAX_CH];
-};
-static_assert(offsetof(AuDelta, cf) == 80 && sizeof(AuDelta) % 16 == 0, "AuDelta layout");
-
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // seat a reader on substream k of access unit A; false = not for the fast path
 __device__ __forceinline__ bool au_seat(const MlpTables &m, const TrackDev &T, uint32_t A, uint32_t k, GRd &b, uint32_t *col,
@@ -1633,7 +1351,8 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
             }
 #undef HEAD_U8
         }
-        if (block_size > nominal || nominal % block_size) { fallback = true; break; }
+        // (blocks of a multiple of eight frames: the entropy loops of the fast path step by eight)
+        if (block_size > nominal || nominal % block_size || (block_size & 7)) { fallback = true; break; }
 
         // per-channel constants of the AU's blocks (mlp.c:1151-1176, 1260-1270), packed as the
         // five 64-bit words behind the positions in the snapshot: block_size, want, valid, min_ch,
@@ -1709,93 +1428,6 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
     if (job.k == 0) S.frames = frames;
 }
 
-// ---- filter passes: one channel's set-up from the delta of an access unit -----------------
-struct FiltSetup { uint32_t fo, io, fsh, ish, q; };      // orders, shifts, quant_step_size in force
-
-__device__ __forceinline__ void filt_take_delta(const AuDelta &D, uint32_t cc, uint32_t c, FiltSetup &F,
-                                                int32_t (&cf)[8], int32_t (&ci)[8], int32_t (&ih)[8])
-{
-    const uint32_t *hw = reinterpret_cast<const uint32_t *>(&D.ch[cc]);
-    const uint32_t h1 = hw[1], h2 = hw[2];               // orders + shifts; codebook, lsbs, present
-    const uint32_t p = (h2 >> 16) & 0xFF;
-    if (D.present & AD_Q) F.q = D.q[c];
-    if (!(p & (CD_FIR | CD_IIR))) return;
-    const uint4 *kw = reinterpret_cast<const uint4 *>(&D.cf[cc]);
-    const uint4 s0 = kw[0], s1 = kw[1], fc = kw[2], ic = kw[3];
-    if (p & CD_FIR) {
-        F.fo = h1 & 0xFF; F.fsh = (h1 >> 8) & 0xFF;
-        const uint32_t w[4] = {fc.x, fc.y, fc.z, fc.w};
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
-            cf[j] = (uint32_t)j < F.fo ? v : 0;
-        }
-    }
-    if (p & CD_IIR) {
-        F.io = (h1 >> 16) & 0xFF; F.ish = h1 >> 24;
-        const uint32_t w[4] = {ic.x, ic.y, ic.z, ic.w};
-        const int32_t st[8] = {(int32_t)s0.x, (int32_t)s0.y, (int32_t)s0.z, (int32_t)s0.w,
-                               (int32_t)s1.x, (int32_t)s1.y, (int32_t)s1.z, (int32_t)s1.w};
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
-            ci[j] = (uint32_t)j < F.io ? v : 0;
-            // the history is replaced by what was sent (or emptied)
-            ih[j] = ((p & CD_IIR_STATE) && (uint32_t)j < F.io) ? st[j] : 0;
-        }
-    }
-}
-// The same with the head fields already in registers (the fused output pass loads them one
-// access unit ahead): only the 64 bytes of coefficients and histories are fetched here, with
-// four independent loads.
-struct DeltaHead { uint32_t fchg, w0, qv, h1, h2, seed, pset; };
-__device__ __forceinline__ DeltaHead filt_load_head(const MlpTables &m, const AuDelta *deltas, uint32_t A, uint32_t cc, uint32_t c)
-{
-    DeltaHead H;
-    const AuDelta &D = deltas[A];
-    H.fchg = m.au_fchg[A];
-    H.w0 = *reinterpret_cast<const uint32_t *>(&D);                  // block_size, present, matrix_len
-    H.qv = D.q[c];
-    const uint32_t *hw = reinterpret_cast<const uint32_t *>(&D.ch[cc]);
-    H.h1 = hw[1]; H.h2 = hw[2];
-    const uint2 sp = *reinterpret_cast<const uint2 *>(&m.au[A].seed);
-    H.seed = sp.x; H.pset = sp.y;
-    return H;
-}
-__device__ __forceinline__ void filt_take_head(const DeltaHead &H, const AuDelta &D, uint32_t cc, FiltSetup &F,
-                                               int32_t (&cf)[8], int32_t (&ci)[8], int32_t (&ih)[8])
-{
-    const uint32_t h1 = H.h1, p = (H.h2 >> 16) & 0xFF;
-    if ((H.w0 >> 16) & AD_Q) F.q = H.qv;
-    if (!(p & (CD_FIR | CD_IIR))) return;
-    const uint4 *kw = reinterpret_cast<const uint4 *>(&D.cf[cc]);
-    const uint4 s0 = kw[0], s1 = kw[1], fc = kw[2], ic = kw[3];
-    if (p & CD_FIR) {
-        F.fo = h1 & 0xFF; F.fsh = (h1 >> 8) & 0xFF;
-        const uint32_t w[4] = {fc.x, fc.y, fc.z, fc.w};
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
-            cf[j] = (uint32_t)j < F.fo ? v : 0;
-        }
-    }
-    if (p & CD_IIR) {
-        F.io = (h1 >> 16) & 0xFF; F.ish = h1 >> 24;
-        const uint32_t w[4] = {ic.x, ic.y, ic.z, ic.w};
-        const int32_t st[8] = {(int32_t)s0.x, (int32_t)s0.y, (int32_t)s0.z, (int32_t)s0.w,
-                               (int32_t)s1.x, (int32_t)s1.y, (int32_t)s1.z, (int32_t)s1.w};
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
-            ci[j] = (uint32_t)j < F.io ? v : 0;
-            ih[j] = ((p & CD_IIR_STATE) && (uint32_t)j < F.io) ? st[j] : 0;
-        }
-    }
-}
-__device__ __forceinline__ uint32_t filt_shift(const FiltSetup &F)
-{
-    return (F.fsh > 0 && F.ish > 0) ? F.fsh : F.fo > 0 ? F.fsh : F.ish;
-}
 
 // ---- pass B: entropy decode of one access unit -------------------------------------
 //
@@ -1999,24 +1631,6 @@ __device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint3
 #define OUT_MIN_BLOCKS 5
 #endif
 
-template <int NF, int NI>
-__device__ __forceinline__ void filt8(const int32_t (&cf)[8], const int32_t (&ci)[8], int32_t (&fh)[8], int32_t (&ih)[8],
-                                      int32_t (&r)[8], uint32_t shift, uint32_t qmask)
-{
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        long long s0 = 0, s1 = 0;
-#pragma unroll
-        for (int t = NF - 1; t >= 0; t--) s0 = mad_wide(cf[t], fh[(t - j) & 7], s0);   // oldest taps first:
-#pragma unroll
-        for (int t = NI - 1; t >= 0; t--) s1 = mad_wide(ci[t], ih[(t - j) & 7], s1);   // short dependent chain
-        const int32_t ssum = (NF + NI) ? (int32_t)((s0 + s1) >> shift) : 0;
-        const int32_t x = (int32_t)(((uint32_t)ssum + (uint32_t)r[j]) & qmask);
-        fh[(7 - j) & 7] = x;
-        ih[(7 - j) & 7] = (int32_t)((uint32_t)x - (uint32_t)ssum);
-        r[j] = x;
-    }
-}
 
 template <int NCH>
 __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_out(MlpTables m, const DecWork *__restrict__ work,
@@ -2239,9 +1853,7 @@ static int launch_one_filter_out(MlpTables m, const DecWork *work, uint32_t n_wo
     constexpr int SPW = 32 / NCH, SUB = (32 + SPW - 1) / SPW;
     const size_t smem = (size_t)OUT_WARPS * SPW * (2 * (32 * NCH + 4) + 4) * sizeof(int32_t);
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) {
-        CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); return 0; })) return -1;
     LAUNCH(k_mlp_filter_out<NCH>, div_up_u32((uint64_t)n_warps * SUB, OUT_WARPS), OUT_WARPS * 32, smem, s, m, work, n_work, n_warps);
     return 0;
 }
@@ -2430,9 +2042,7 @@ static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t
 {
     if (!n_warps) return 0;
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) {
-        CUDA_TRY(cudaFuncSetAttribute(k_mlp_entropy<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES));
-    }
+    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_mlp_entropy<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES)); return 0; })) return -1;
     const uint32_t blocks = div_up_u32(n_warps, DEC_WARPS);
     const uint32_t small = div_up_u32(n_warps, 4);
     if (pass == 0) LAUNCH(k_mlp_segctx, small, 128, 0, s, m, work, n_work, n_warps);
@@ -2444,12 +2054,30 @@ static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t
     return 0;
 }
 
+// what the fused pass gave up on in an earlier attempt of this decode stays flagged
+__global__ void k_flag_sticky(MlpTables m)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * m.nseg) return;
+    const uint32_t st = m.ss_sticky[i];
+    if (!st) return;
+    m.ss_flags[i] |= st;
+    *m.any_fallback = 1;
+}
+
+const uint16_t *huff_lut_device()
+{
+    void *p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_huff_lut) != cudaSuccess) return nullptr;
+    return reinterpret_cast<const uint16_t *>(p);
+}
+
 int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
-                    cudaEvent_t (*kev)[2], bool *kev_used, cudaEvent_t checked, cudaStream_t s)
+                    cudaEvent_t (*kev)[2], bool *kev_used, cudaEvent_t checked, bool headers_only, cudaStream_t s)
 {
     static const int slot[5] = {DVDAGPU_K_MLP_SEGCTX, DVDAGPU_K_MLP_AU_PARSE, DVDAGPU_K_MLP_RESOLVE, DVDAGPU_K_MLP_ENTROPY,
                                 DVDAGPU_K_MLP_FILTER};
-    for (int pass = 0; pass < 5; pass++) {
+    for (int pass = 0; pass < (headers_only ? 3 : 5); pass++) {
         CUDA_TRY(cudaEventRecord(kev[slot[pass]][0], s));
         if (pass == 1 && m.nau) LAUNCH(k_mlp_au_parse, dim3(div_up_u32(m.nau, GRD_THREADS), m.nss_max), GRD_THREADS, 0, s, m);
         if (launch_fast_pass<1>(pass, m, work[1], n_work[1], n_warps[1], s)) return -1;
@@ -2464,6 +2092,7 @@ int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_
     // changed stream parameters) go to the complete decoder, which knows where such a track ends
     CUDA_TRY(cudaStreamWaitEvent(s, checked, 0));
     if (m.nau) LAUNCH(k_flag_damaged, div_up_u32(m.nau, 256), 256, 0, s, m);
+    if (headers_only) LAUNCH(k_flag_sticky, div_up_u32((uint64_t)m.nseg * 2, 256), 256, 0, s, m);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -2473,9 +2102,7 @@ static int launch_one_decode(MlpTables m, const DecWork *work, uint32_t n_work, 
 {
     if (!n_warps) return 0;
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) {
-        CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES));
-    }
+    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES)); return 0; })) return -1;
     LAUNCH(k_mlp_decode<NCH>, div_up_u32(n_warps, DEC_WARPS), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
     return 0;
 }
@@ -2564,7 +2191,7 @@ __global__ void k_seg_finalize(MlpTables m, uint32_t *__restrict__ seg_frames, u
     S.flags = flags & ~SEG_NEEDS_CARRY;
     if (now & SEG_OVERFLOW) atomicOr(status, SEG_OVERFLOW);
     // anything left for k_rematrix once the fused filter + output pass has run?
-    if (m.fast && frames && (T.nss != 1 || T.channels > 4 || (m.ss_flags_fast[i] & SEG_FALLBACK))) atomicOr(status, STATUS_WANTS_REMATRIX);
+    if (m.fast && frames && !seg_output_done(m, T, i)) atomicOr(status, STATUS_WANTS_REMATRIX);
     S.err = err;
     S.err_au = stop;
     S.frames = frames;
@@ -2656,9 +2283,9 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
     if (!NCH && T.channels <= 2) return;                 // handled by the specialised instantiations
     const uint32_t nf = min(32u, G.cap - f0);
     int32_t *bsm = sm + nch * 32 * 33;
-    if (m.fast && T.nss == 1 && T.channels <= 4) {
-        // segments the fused filter + output pass has written need nothing here
-        const int left = (threadIdx.x < G.nseg) && (m.ss_flags_fast[G.seg0 + threadIdx.x] & SEG_FALLBACK);
+    if (m.fast) {
+        // segments the fused output pass has written need nothing here
+        const int left = (threadIdx.x < G.nseg) && !seg_output_done(m, T, G.seg0 + threadIdx.x);
         if (!__syncthreads_or(left)) return;
     }
 
@@ -2696,7 +2323,7 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
         const uint32_t F = f0 + f;                       // frame inside the segment
         if (F >= S.frames) continue;
         // already written by the fused filter + output pass of the fast path?
-        if (m.fast && T.nss == 1 && T.channels <= 4 && !(m.ss_flags_fast[G.seg0 + l] & SEG_FALLBACK)) continue;
+        if (seg_output_done(m, T, G.seg0 + l)) continue;
         const AuDev au = au_of_frame(m, S, F, nominal);
         int32_t v[DVDA_MAX_CH];
 #pragma unroll
@@ -2756,9 +2383,7 @@ int launch_rematrix(MlpTables m, uint32_t max_chunks, uint32_t channel_mask, cud
     const dim3 grid(m.ngroups, max_chunks);
     const size_t smem = (size_t)(DVDA_MAX_CH + 1) * 32 * 33 * sizeof(int32_t);
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) {
-        CUDA_TRY(cudaFuncSetAttribute(k_rematrix<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_rematrix<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); return 0; })) return -1;
     // channel_mask: bit n = some MLP track of the batch has n channels
     if (channel_mask & 2) LAUNCH(k_rematrix<1>, grid, RM_THREADS, (size_t)2 * 32 * 33 * 4, s, m);
     if (channel_mask & 4) LAUNCH(k_rematrix<2>, grid, RM_THREADS, (size_t)3 * 32 * 33 * 4, s, m);

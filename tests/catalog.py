@@ -111,35 +111,6 @@ GPU_LARGE = {
 }
 
 
-def _c5_titleset():
-    """BASELINE.json configs[4] in shape, scaled in length: one title set of 64 tracks
-    (2 titles x 32), 16 PCM tracks (16- and 24-bit, stereo and 6 channels) and 48 MLP tracks in
-    the styles of C2 / C3 / C4, seeds 2000 + track."""
-    titles = []
-    n = 0
-    for _title in range(2):
-        tracks = []
-        for i in range(32):
-            seed = 2000 + n
-            kind = i % 4
-            if kind == 0:
-                v = (i // 4) % 4
-                tracks.append(g.pcm(30_000 + 4_000 * v, bps=(16, 24, 24, 16)[v], assignment=(1, 1, 12, 12)[v],
-                                    rate=(48000, 96000, 96000, 48000)[v], seed=seed))
-            elif kind == 1:
-                tracks.append(g.mlp(40_000 + 800 * i, rate=96000, assignment=1, seed=seed, restart_interval=16,
-                                    fir_max=4, iir_max=4, noise_bits=13))
-            elif kind == 2:
-                tracks.append(g.mlp(16_000 + 400 * i, rate=96000, assignment=12, substreams=2, seed=seed,
-                                    restart_interval=16, matrices=3,
-                                    features=g.CHECKDATA | g.BYPASS | g.NOISE | g.QUANT | g.OUTSHIFT))
-            else:
-                tracks.append(g.mlp(64_000 + 1_600 * i, rate=192000, assignment=1, seed=seed, restart_interval=8,
-                                    features=g.CHECKDATA | g.MAX_ORDERS, fir_max=8, iir_max=4, codebooks=0x2,
-                                    min_lsbs=16, noise_bits=16))
-            n += 1
-        titles.append(tracks)
-    return titles
+import workloads  # noqa: E402  (gen/workloads.py: the config shapes shared with bench.py)
 
-
-GPU_LARGE["c5_titleset_64"] = _c5_titleset()
+GPU_LARGE["c5_titleset_64"] = workloads.c5_titleset(1)

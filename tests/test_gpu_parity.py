@@ -16,19 +16,22 @@ GOLDEN = json.load(open(os.path.join(HERE, "golden", "catalog_golden.json")))
 DISCS = sorted(catalog.discs().keys())
 
 
-@pytest.fixture(scope="module", params=["three-pass", "single-pass"])
+@pytest.fixture(scope="module", params=["three-pass", "fused", "single-pass"])
 def engine(pkg, request):
-    """Every test runs against both MLP decode paths: the access-unit-parallel three-pass
-    path with the complete decoder as its fall-back (default), and the complete single-pass
-    decoder alone (DVDAGPU_SINGLE_PASS=1)."""
+    """Every test runs against the three MLP decode paths: the three-pass path with the complete
+    decoder as its fall-back (default), the header passes + the fused entropy / filter / output
+    pass (DVDAGPU_FUSED=1), and the complete single-pass decoder alone (DVDAGPU_SINGLE_PASS=1)."""
+    os.environ.pop("DVDAGPU_SINGLE_PASS", None)
+    os.environ.pop("DVDAGPU_FUSED", None)
     if request.param == "single-pass":
         os.environ["DVDAGPU_SINGLE_PASS"] = "1"
-    else:
-        os.environ.pop("DVDAGPU_SINGLE_PASS", None)
+    elif request.param == "fused":
+        os.environ["DVDAGPU_FUSED"] = "1"
     e = pkg.Engine(0)
     yield e
     e.close()
     os.environ.pop("DVDAGPU_SINGLE_PASS", None)
+    os.environ.pop("DVDAGPU_FUSED", None)
 
 
 def check_track(oracle, eng, res, sectors, g, label):
@@ -258,6 +261,38 @@ def test_title_set_sharded_like_eight_ranks(pkg, oracle, engine, disc_cache):
             assert oracle.fnv1a(got) == g["fnv"], "track %d differs from the reference" % i
             seen.append(i)
     assert sorted(seen) == list(range(64))
+
+
+def test_title_set_sharded_by_units(pkg, oracle, engine, disc_cache):
+    """The way bench.py shards configs[4] over ranks: units = tracks and parts of long MLP tracks
+    (shard.plan_units), every rank decodes its units from its own compact sector window (the units'
+    sector ranges plus a margin, back to back); parts concatenate to their tracks."""
+    import importlib
+    shard = importlib.import_module("libdvd-audio_b200.shard")
+    directory, _ = disc_cache("c5_titleset_64")
+    sectors = oracle.read_aobs(directory)
+    n_total = len(sectors) // 2048
+    golden = GOLDEN["c5_titleset_64"]["tracks"]
+    tracks = [(g["first"], g["last"], g["pts"]) for g in golden]
+    codecs = [1 if g["codec"] == "MLP" else 0 for g in golden]
+    units = shard.plan_units(tracks, codecs, 8, units_per_rank=12, min_part_sectors=16)
+    assert any(u["parts"] > 1 for u in units)
+    got = {}
+    for mine in shard.assign_units(units, 8):
+        pieces, descs, at = [], [], 0
+        for u in mine:
+            stop = min(n_total, u["last"] + 1 + 64)
+            pieces.append(sectors[u["first"] * 2048: stop * 2048])
+            descs.append((at, at + (u["last"] - u["first"]), u["pts"], u["flags"]))
+            at += stop - u["first"]
+        res = engine.decode_host(np.concatenate(pieces), descs)
+        for u, r in zip(mine, res):
+            assert r.status == 0 and r.stopped != 2, (u, r.status, r.stopped)
+            got[(u["track"], u["part"])] = engine.fetch(r).reshape(-1) if r.frames else np.zeros(0, np.int32)
+    for ti, g in enumerate(golden):
+        pcm = np.concatenate([got[(ti, p)] for p in range(64) if (ti, p) in got])
+        assert len(pcm) == g["frames"] * g["ch"], (ti, len(pcm), g["frames"])
+        assert oracle.fnv1a(pcm) == g["fnv"], "track %d differs from the reference" % ti
 
 
 def test_two_devices_in_one_process(pkg, oracle, disc_cache):

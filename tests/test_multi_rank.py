@@ -61,3 +61,41 @@ def test_shard_edge_cases():
     assert sorted(i for p in parts for i in p) == list(range(17))
     assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     assert shard.reduce_job(3.5, 100) == (3.5, 100.0)
+
+
+def test_units_cover_every_sector_once():
+    """plan_units: whole tracks, long MLP tracks cut into parts with the DVDAGPU_PART_* flags;
+    assign_units: every unit on exactly one rank, loads balanced."""
+    sys.path.insert(0, ROOT)
+    shard = importlib.import_module("libdvd-audio_b200.shard")
+    tracks, at = [], 0
+    for n in (100, 9000, 40, 30000, 700, 12000, 5, 2500):
+        tracks.append((at, at + n - 1, n * 10))
+        at += n
+    codecs = [0, 1, 1, 1, 0, 0, 1, 1]                      # the 12000-sector track is PCM: never cut
+    for world in (1, 2, 8):
+        units = shard.plan_units(tracks, codecs, world, units_per_rank=4, min_part_sectors=512)
+        covered = []
+        for ti, (first, last, pts) in enumerate(tracks):
+            mine = [u for u in units if u["track"] == ti]
+            assert [u["part"] for u in mine] == list(range(len(mine))) and all(u["parts"] == len(mine) for u in mine)
+            assert mine[0]["first"] == first and mine[-1]["last"] == last
+            for a, b in zip(mine, mine[1:]):
+                assert b["first"] == a["last"] + 1
+            for i, u in enumerate(mine):
+                assert u["pts"] == pts
+                assert bool(u["flags"] & shard.PART_CONTINUES_PREVIOUS) == (i > 0)
+                assert bool(u["flags"] & shard.PART_CONTINUED_BY_NEXT) == (i + 1 < len(mine))
+            if codecs[ti] != 1 or world == 1:
+                assert len(mine) == 1
+            covered.append(sum(u["sectors"] for u in mine))
+        assert covered == [last - first + 1 for first, last, _p in tracks]
+        if world == 8:
+            assert len([u for u in units if u["track"] == 3]) > 4          # the long MLP track is shared out
+        per_rank = shard.assign_units(units, world)
+        seen = sorted((u["track"], u["part"]) for r in per_rank for u in r)
+        assert seen == sorted((u["track"], u["part"]) for u in units)
+        loads = [sum(u["sectors"] for u in r) for r in per_rank]
+        assert max(loads) - min(loads) <= max(u["sectors"] for u in units)
+        for r in per_rank:
+            assert [u["first"] for u in r] == sorted(u["first"] for u in r)
