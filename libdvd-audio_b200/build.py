@@ -20,7 +20,7 @@ HOST_LIB = os.path.join(LIBDIR, "libdvd-audio.so")
 DUMP_BIN = os.path.join(LIBDIR, "b200_dump")
 WAV_BIN = os.path.join(LIBDIR, "dvda2wav")
 
-CU_FILES = ["scan.cu", "demux.cu", "mlp_index.cu", "mlp_decode.cu", "mlp_fused.cu", "engine.cu"]
+CU_FILES = ["scan.cu", "demux.cu", "mlp_index.cu", "mlp_decode.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I", INCLUDE,

@@ -39,12 +39,48 @@
 #define SEG_FALLBACK 8u        // the three-pass fast path gave up: decode with the complete decoder
 #define SEG_WANTS_PREV 16u     // ... because it needs the previous segment's FIR history
 #define STATUS_WANTS_REMATRIX 0x100u   // k_seg_finalize -> host: some segment still needs k_rematrix (fast path)
-#define STATUS_REDO 0x400u             // fused pass -> host: a segment it had taken turned out not to be for it (now flagged): decode again
 #define STATUS_PCM_SMALL 0x200u        // k_track_out_base -> output pass, host: the samples do not fit the buffer sized in advance
 
 // TrackDev.cont / dvdagpu_track_desc.flags
 #define TRACK_CONT_PREV 1u
 #define TRACK_CONT_NEXT 2u
+
+// What the demux and index stages find out about the input, kept in device memory: the launch
+// sequence of a decode is fixed before any of it is known to the host.  Every table is sized in
+// advance (from the input's size, or from what the previous decode of this context needed), the
+// kernels take their bounds from here and their grids are sized for the tables' capacities; the
+// host reads this once, together with the results, when the decode is over, and repeats the
+// decode with larger tables if one was too small (`overflow`).
+struct DecCounts {
+    uint64_t np;               // audio packets (total of the per-sector counts)
+    uint64_t es_total;         // elementary-stream bytes
+    uint64_t n_raw, n_valid;   // sync patterns / those that start a restart segment
+    uint64_t nau;              // access units
+    uint64_t cells;            // tile cells (frames x channels per group, summed)
+    uint64_t pcm_fixed;        // samples of the PCM tracks + alignment slack of the output buffer
+    uint32_t nseg, ngroups;
+    uint32_t npairs;           // (group, substream) pairs: warps of the per-segment passes
+    uint32_t nwork;            // rows of the work list: (track, substream) pairs with segments
+    uint32_t nout_work;        // rows of the output pass's work list: tracks it takes
+    uint32_t nout_warps;       // its warps
+    uint32_t max_au;           // most access units in a segment
+    uint32_t max_chunks;       // most 32-frame chunks in a group
+    uint32_t any_pcm, any_mlp, nss_max;
+    uint32_t chan_mask;        // bit n: some MLP track has n channels
+    uint32_t overflow;         // CAP_* bits
+    uint32_t pad[3];
+    // what a table that overflowed would have needed (the counts above are zeroed then, so that
+    // the stages behind do nothing)
+    uint64_t need_rows, need_sync, need_seg, need_grp, need_au, need_cells;
+};
+#define CAP_ROWS 1u            // packet table
+#define CAP_SYNC 2u            // sync lists
+#define CAP_SEG 4u             // segment table
+#define CAP_GRP 8u             // group table, work list
+#define CAP_AU 16u             // access-unit tables
+#define CAP_CELLS 32u          // tiles
+#define CAP_MAX_AU 64u         // grid of the entropy pass (access units per segment)
+#define CAP_SHAPE 256u         // a kernel that was left out has work after all (PCM tracks, two substreams, ...)
 
 struct TrackDev {
     // inputs

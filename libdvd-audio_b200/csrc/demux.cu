@@ -163,12 +163,13 @@ __global__ void k_packet_flags(PacketTable pt, uint32_t rows, const uint32_t *__
 // One warp per MLP packet: payload bytes -> ES[es_off ...].  Byte-granular on
 // both sides (neither side is aligned); lanes take consecutive bytes so the
 // accesses coalesce into 32-byte segments.
-__global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t np,
+// (one warp per row of the packet table: the rows behind the last packet carry no bytes)
+__global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t rows,
                             const uint64_t *__restrict__ pk_es, uint8_t *__restrict__ es)
 {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    if (warp >= np) return;
+    if (warp >= rows) return;
     const uint32_t n = pt.mlp_len[warp];
     if (!n) return;
     const uint8_t *src = sectors + (uint64_t)pt.sector[warp] * DVDA_SECTOR + pt.off[warp] + pt.pad2[warp];
@@ -190,6 +191,24 @@ __global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt,
     if (tail0 + lane < n) dst[tail0 + lane] = ld_u8(src + tail0 + lane);
 }
 
+// Zero bytes behind the stream (bit readers may run ahead), and the packet table's capacity:
+// with more packets than rows the table is incomplete; the decode then runs on no packets at all
+// and the host comes back with a larger table.
+__global__ void k_es_tail(uint8_t *__restrict__ es, DecCounts *__restrict__ cnt, uint32_t rows)
+{
+    const uint64_t end = cnt->es_total;
+    for (uint32_t i = threadIdx.x; i < DVDA_ES_PAD / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(es + ((end + 15) & ~15ull))[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < 16 && end + threadIdx.x < ((end + 15) & ~15ull)) es[end + threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0 && cnt->np > rows) {
+        cnt->overflow |= CAP_ROWS;
+        cnt->need_rows = cnt->np;
+        cnt->np = 0;
+        cnt->es_total = 0;
+    }
+}
+
 // ---------------------------------------------------------------------- PCM
 
 // Sample order inside a chunk (two frames), as group lists: see
@@ -205,7 +224,8 @@ __constant__ uint8_t c_pcm_perm[2][6][36];
 // permutation) and consecutive lanes store consecutive samples.
 #define PCM_WARPS 8
 __global__ void __launch_bounds__(PCM_WARPS * 32)
-k_pcm_unpack(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t np,
+k_pcm_unpack(const uint8_t *__restrict__ sectors, PacketTable pt, const DecCounts *__restrict__ cnt,
+             const uint32_t *__restrict__ status,
              const uint64_t *__restrict__ pk_pf, const TrackDev *__restrict__ tracks,
              const uint32_t *__restrict__ trk_pk_lo, uint32_t n_tracks,
              int32_t *__restrict__ pcm)
@@ -214,7 +234,9 @@ k_pcm_unpack(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t np,
     __shared__ uint8_t inv_all[PCM_WARPS][40];
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t i = blockIdx.x * PCM_WARPS + wib;
-    if (i >= np || pt.codec[i] != CODEC_PCM) return;
+    // (queued before the host has seen the batch's status: nothing is written into an output buffer
+    // that turned out too small)
+    if (!cnt->any_pcm || (*status & STATUS_PCM_SMALL) || i >= cnt->np || pt.codec[i] != CODEC_PCM) return;
     // owning track: the last one whose first packet is <= i
     const uint32_t t = upper_bound_dev(trk_pk_lo, n_tracks, i);
     if (t == 0) return;
@@ -275,18 +297,19 @@ int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int launch_es_gather(const uint8_t *sectors, PacketTable pt, uint32_t np, const uint64_t *pk_es, uint8_t *es, cudaStream_t s)
+int launch_es_gather(const uint8_t *sectors, PacketTable pt, uint32_t rows, const uint64_t *pk_es, uint8_t *es,
+                     DecCounts *cnt, cudaStream_t s)
 {
-    if (!np) return 0;
-    LAUNCH(k_es_gather, div_up_u32((uint64_t)np * 32, 256), 256, 0, s, sectors, pt, np, pk_es, es);
+    if (rows) LAUNCH(k_es_gather, div_up_u32((uint64_t)rows * 32, 256), 256, 0, s, sectors, pt, rows, pk_es, es);
+    LAUNCH(k_es_tail, 1, 256, 0, s, es, cnt, rows);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t np, const uint64_t *pk_pf,
-                      const TrackDev *tracks, const uint32_t *trk_pk_lo, uint32_t n_tracks, int32_t *pcm, cudaStream_t s)
+int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t rows, const DecCounts *cnt, const uint32_t *status,
+                      const uint64_t *pk_pf, const TrackDev *tracks, const uint32_t *trk_pk_lo, uint32_t n_tracks, int32_t *pcm, cudaStream_t s)
 {
-    if (!np) return 0;
-    LAUNCH(k_pcm_unpack, div_up_u32(np, PCM_WARPS), PCM_WARPS * 32, 0, s, sectors, pt, np, pk_pf, tracks, trk_pk_lo, n_tracks, pcm);
+    if (!rows) return 0;
+    LAUNCH(k_pcm_unpack, div_up_u32(rows, PCM_WARPS), PCM_WARPS * 32, 0, s, sectors, pt, cnt, status, pk_pf, tracks, trk_pk_lo, n_tracks, pcm);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

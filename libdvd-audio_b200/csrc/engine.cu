@@ -111,9 +111,16 @@ enum {
     B_TRACKS, B_TRK_PK_LO, B_TRK_SEG_BASE, B_TRK_GRP_BASE,
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
     B_SS_FLAGS, B_SS_FLAGS_PREV, B_SS_FLAGS_FAST, B_FIR_TAIL,
-    B_GROUPS, B_GRP_CELLS, B_CELL_BASE, B_GRP_CHUNKS, B_GRP_CHUNK_BASE,
-    B_DEC_WORK, B_FUSED_WORK, B_SS_STICKY, B_AU_SEG, B_AU_SNAP, B_FILT_SNAP, B_AU_FCHG, B_SEG_CTX, B_AU_DELTA, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_AU_NOTED, B_PCM,
+    B_GROUPS, B_GRP_CELLS, B_CELL_BASE,
+    B_DEC_WORK, B_OUT_WORK, B_COUNTS, B_SEG_NEED, B_AU_SEG, B_AU_SNAP, B_FILT_SNAP, B_AU_FCHG, B_SEG_CTX, B_AU_DELTA, B_TILES, B_BYPASS, B_SEG_FRAMES, B_SEG_FRAME_SCAN, B_SCAN_TMP, B_STATUS, B_AU_NOTED, B_PCM,
     B_COUNT
+};
+
+// capacities and launch limits of one decode (see shape_from_input / shape_from_last)
+struct DecShape {
+    uint64_t rows = 0, sync = 0, seg = 0, grp = 0, au = 0, cells = 0, pcm_fixed = 0;
+    uint32_t max_au = 0, nss = 0, out_warps = 0;
+    bool any_pcm = true, any_mlp = true, windowed = true;
 };
 
 struct dvdagpu_ctx {
@@ -124,9 +131,12 @@ struct dvdagpu_ctx {
     cudaStream_t aux_stream;                  // check data runs beside the header passes
     cudaEvent_t aux_ev[2];
     cudaStream_t aux_stream_hi = nullptr;     // side stream at the chain's own priority
-    uint32_t pk_last_sectors = 0, pk_last_np = 0;   // sector and packet count of the previous decode
-    uint64_t sync_last_es = ~0ull;                  // stream size and sync counts of the previous decode
-    uint32_t sync_last_raw = 0, sync_last_valid = 0;
+    // what the previous decode of this context found and was sized for: the next one is sized from it
+    DecCounts last;
+    DecShape last_shape;
+    uint32_t last_sectors = 0, last_tracks = 0;
+    bool have_last = false;
+    uint32_t seg_need_cap = 0;                // rows of the seg_need table that has been cleared
     uint32_t scan_tmp_gen = 0;                // allocation of the scan buffer that has been cleared
     cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
     int pcm_slot;                             // which PCM buffer the next decode writes
@@ -308,7 +318,7 @@ extern "C" int dvdagpu_fetch(dvdagpu_ctx *c, uint64_t offset, uint64_t count, in
 
 // ---- one decode ----------------------------------------------------------------
 
-#define ENSURE(id, bytes) do { if (c->buf[id].ensure(bytes)) return -1; } while (0)
+#define ENSURE(id, bytes) do { if (c->buf[id].ensure(bytes)) { dvdagpu_set_error("%s (buffer %s, %zu bytes)", g_error, #id, (size_t)(bytes)); return -1; } } while (0)
 #define TRY(expr) do { if ((expr) != 0) return -1; } while (0)
 // device time of one kernel (or a short run of kernels) into stats.kernel_ms[id]
 #define TIMED(id, expr)                                                        \
@@ -388,23 +398,6 @@ static int small_h2d(dvdagpu_ctx *c, void *dev, const void *host, size_t bytes)
     return flush_h2d(c);
 }
 
-// Totals the scans leave in the mapped staging area themselves (scan_batch's total_copy): slot j
-// as the device sees it, and the host's read once the stream has drained.
-static uint64_t *mapped_total_slot(dvdagpu_ctx *c, int j) { return reinterpret_cast<uint64_t *>(c->dmap + MAP_BYTES / 2) + j; }
-static int mapped_totals(dvdagpu_ctx *c, int n, uint64_t *host)
-{
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    trace_host("  (host has the totals)");
-    for (int j = 0; j < n; j++) host[j] = reinterpret_cast<volatile uint64_t *>(c->hmap + MAP_BYTES / 2)[j];
-    return 0;
-}
-
-template <typename T>
-static int read_back(dvdagpu_ctx *c, const T *dev, T *host)
-{
-    return small_d2h(c, host, dev, sizeof(T));
-}
-
 // several read-backs, one round trip (each one costs tens of microseconds, more while bulk copies run)
 static int small_d2h_multi(dvdagpu_ctx *c, int n, void *const host[], const void *const dev[], const size_t bytes[])
 {
@@ -430,15 +423,6 @@ static int small_d2h_multi(dvdagpu_ctx *c, int n, void *const host[], const void
     for (int i = 0; i < n; i++) memcpy(host[i], c->hmap + MAP_BYTES / 2 + off[i], bytes[i]);
     return 0;
 }
-static int small_d2h_pair(dvdagpu_ctx *c, void *host_a, const void *dev_a, size_t bytes_a,
-                          void *host_b, const void *dev_b, size_t bytes_b)
-{
-    void *const host[2] = {host_a, host_b};
-    const void *const dev[2] = {dev_a, dev_b};
-    const size_t bytes[2] = {bytes_a, bytes_b};
-    return small_d2h_multi(c, 2, host, dev, bytes);
-}
-
 // Where every track's samples start in the output buffer (16-byte aligned tracks: vector and
 // bulk stores), computed on the device so that the output pass can be queued without a round
 // trip through the host.  `capacity`: samples the buffer was sized for in advance.
@@ -459,6 +443,49 @@ __global__ void __launch_bounds__(OB_THREADS) k_track_out_base(TrackDev *tracks,
     if (threadIdx.x == 0 && carry > capacity) atomicOr(status, STATUS_PCM_SMALL);
 }
 
+// ---- what the launches of a decode are sized for ------------------------------------------
+//
+// Nothing a decode finds out about its input goes back to the host before it is over, so every
+// table and grid is sized beforehand: from bounds the input's size gives (first decode of a
+// context, or an input unlike the previous one), or from what the previous decode needed, scaled
+// to the new input's size plus a margin (parts of one track, tracks of one title set, the same
+// input again: the common cases).  The kernels take the real counts from device memory; a table
+// that turns out too small stops the stages behind it, raises its CAP_* bit, and the decode is
+// repeated with that table at the size now known.
+static void shape_from_input(DecShape &sh, uint32_t n_sectors, uint32_t n_tracks)
+{
+    const uint64_t es_cap = (uint64_t)n_sectors * DVDA_SECTOR;
+    sh.rows = (uint64_t)n_sectors + n_sectors / 4 + 64;         // one audio packet per sector is the rule
+    sh.sync = es_cap / 2048 + 1024;                             // a sync every 2 KiB of stream
+    sh.seg = sh.sync + n_tracks;
+    sh.grp = sh.seg / DVDA_LANES + n_tracks + 1;
+    sh.au = es_cap / 256 + 1024;
+    sh.cells = es_cap / DVDA_LANES + 4096;                      // one sample per stream byte
+    sh.max_au = 64;
+    sh.nss = 2;
+    sh.out_warps = 8 * sh.grp;
+    sh.any_pcm = true; sh.any_mlp = true; sh.windowed = true;
+    sh.pcm_fixed = (uint64_t)n_sectors * (DVDA_SECTOR / 2) + 4ull * n_tracks + 64;   // 16-bit samples fill every sector
+}
+static uint64_t with_margin(uint64_t v, double scale) { return (uint64_t)((double)v * scale * 1.0625) + 64; }
+static void shape_from_last(DecShape &sh, const DecCounts &k, const DecShape &used, uint32_t last_sectors, uint32_t n_sectors, uint32_t n_tracks)
+{
+    const double scale = last_sectors ? (double)n_sectors / (double)last_sectors : 1.0;
+    sh.rows = with_margin(k.np, scale);
+    sh.sync = with_margin(k.n_raw > k.n_valid ? k.n_raw : k.n_valid, scale);
+    sh.seg = with_margin(k.nseg, scale);
+    sh.grp = with_margin(k.ngroups, scale) + n_tracks;
+    sh.au = with_margin(k.nau, scale);
+    sh.cells = with_margin(k.cells, scale);
+    sh.max_au = k.max_au ? k.max_au : 1;
+    sh.nss = k.nss_max ? k.nss_max : 1;
+    sh.out_warps = (uint32_t)with_margin(k.nout_warps, scale);
+    sh.any_pcm = k.any_pcm != 0; sh.any_mlp = k.any_mlp != 0;
+    sh.windowed = !k.nau || k.es_total / k.nau <= CHK_WINDOWED_MAX_AU_BYTES;
+    sh.pcm_fixed = k.any_pcm ? with_margin(k.pcm_fixed, scale) + 4ull * n_tracks : 4ull * n_tracks + 64;
+    (void)used;
+}
+
 static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n_sectors64,
                             uint32_t n_tracks, const dvdagpu_track_desc *descs, dvdagpu_track_result *results)
 {
@@ -467,8 +494,6 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     g_trace_on = getenv("DVDAGPU_TRACE") != nullptr;
     g_trace.n = 0;
     if (g_trace_on) trace_mark("decode begins", c->stream);
-    c->map_used = 0;
-    g_h2d_batch.n = 0;
     cudaStream_t s = c->stream;
     if (n_sectors64 == 0 || n_sectors64 > 0x7FFFFFFFull) { dvdagpu_set_error("bad sector count"); return -1; }
     if (!n_tracks) { c->pcm_samples = 0; return 0; }
@@ -483,53 +508,53 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return descs[a].first_sector < descs[b].first_sector; });
     std::vector<TrackDev> &ht = c->h_tracks;
     ht.assign(n_tracks, TrackDev());
-    for (uint32_t i = 0; i < n_tracks; i++) {
-        memset(&ht[i], 0, sizeof(TrackDev));
-        ht[i].first_sector = descs[order[i]].first_sector;
-        ht[i].last_sector = descs[order[i]].last_sector;
-        ht[i].pts_length = descs[order[i]].pts_length;
-        ht[i].cont = descs[order[i]].flags & 3u;
-    }
 
-    // ---------------- demux
-    ENSURE(B_SEC_CNT, (size_t)n_sectors * 4);
-    ENSURE(B_SEC_BAD, (size_t)n_sectors * 4);
-    ENSURE(B_SEC_BASE, (size_t)(n_sectors + 1) * 4);
-    ENSURE(B_BAD_PREFIX, (size_t)(n_sectors + 1) * 4);
-    ENSURE(B_SCAN_TMP, scan_tmp_bytes((uint64_t)n_sectors * 2048 / 32 + 4096));
-    void *tmp = c->buf[B_SCAN_TMP].p;
-    const size_t tmp_bytes = c->buf[B_SCAN_TMP].cap;
-    if (c->scan_tmp_gen != c->buf[B_SCAN_TMP].gen) {
-        // the scans find their control words zero and leave them zero (scan.cu)
-        CUDA_TRY(cudaMemsetAsync(tmp, 0, tmp_bytes, s));
-        c->scan_tmp_gen = c->buf[B_SCAN_TMP].gen;
-    }
-    uint32_t *sec_cnt = c->buf[B_SEC_CNT].as<uint32_t>(), *sec_bad = c->buf[B_SEC_BAD].as<uint32_t>();
-    uint32_t *sec_base = c->buf[B_SEC_BASE].as<uint32_t>(), *bad_prefix = c->buf[B_BAD_PREFIX].as<uint32_t>();
-    TRY(launch_sector_count(d_sectors, n_sectors, sec_cnt, sec_bad, s));
-    {
-        const uint32_t *in[2] = {sec_cnt, sec_bad}; void *out[2] = {sec_base, bad_prefix}; const bool wide[2] = {false, false};
-        uint64_t *const copy[2] = {mapped_total_slot(c, 0), nullptr};
-        TRY(scan_batch(in, out, wide, 2, n_sectors, tmp, tmp_bytes, s, copy));
-    }
-    // The packet table is sized before the host knows the packet count (one audio packet per
-    // sector is the rule; room for a quarter more, and whatever earlier decodes needed): the
-    // table is filled, its prefix sums taken over all its rows, and only then does the host
-    // fetch the packet count and the size of the elementary stream, in one round trip.  If the
-    // table was too small it grows and the step is repeated.
-    uint32_t np = 0;
-    uint64_t es_total = 0;
-    PacketTable pt;
-    uint64_t *pk_es = nullptr, *pk_pf = nullptr;
-    uint32_t *nonmlp = nullptr, *nm_prefix = nullptr, *pstop = nullptr, *stop_prefix = nullptr;
-    size_t rows = (size_t)n_sectors + n_sectors / 4 + 64;
-    if (c->pk_last_sectors == n_sectors) rows = std::max<size_t>(rows, (size_t)c->pk_last_np + 64);   // (the same input again)
+    // decode mode: the three-pass fast path with the complete decoder as its fall-back (default),
+    // or the complete single-pass decoder alone (DVDAGPU_SINGLE_PASS=1); the GPU tests run both
+    const bool use_fast = getenv("DVDAGPU_SINGLE_PASS") == nullptr;
     // (test hook: DVDAGPU_SMALL_TABLES=1 starts every table sized in advance with room for one entry,
     // so that each decode goes through the grow-and-repeat paths)
     const bool small_tables = getenv("DVDAGPU_SMALL_TABLES") != nullptr;
-    if (small_tables) rows = 1;
+    // (test hook: DVDAGPU_SYNC_SLOTS=0 sends every chunk with a match through the re-search path)
+    const uint32_t nslots = getenv("DVDAGPU_SYNC_SLOTS") ? (uint32_t)atoi(getenv("DVDAGPU_SYNC_SLOTS")) : 2u;
+
+    DecShape sh;
+    const bool similar = c->have_last && !small_tables && c->last_tracks == n_tracks &&
+                         n_sectors >= c->last_sectors / 2 && n_sectors / 2 <= c->last_sectors;
+    if (similar) shape_from_last(sh, c->last, c->last_shape, c->last_sectors, n_sectors, n_tracks);
+    else shape_from_input(sh, n_sectors, n_tracks);
+    if (small_tables) { sh.rows = sh.sync = sh.seg = sh.grp = sh.au = sh.cells = 1; sh.max_au = 1; sh.out_warps = 8; sh.pcm_fixed = 1; }
+    const uint64_t es_cap = (uint64_t)n_sectors * DVDA_SECTOR;
+    const uint32_t chunks_cap = div_up_u32(es_cap, SYNC_CHUNK);
+
+    DecCounts k;
+    uint32_t status = 0;
+    MlpTables m;
+    uint64_t total_samples = 0;
+    bool pcm_small_seen = false;
     for (int attempt = 0;; attempt++) {
-        const size_t npa = rows + 1;
+        if (attempt == 16) { dvdagpu_set_error("internal: the tables keep overflowing"); return -1; }
+        c->map_used = 0;
+        g_h2d_batch.n = 0;
+        for (uint32_t i = 0; i < n_tracks; i++) {
+            memset(&ht[i], 0, sizeof(TrackDev));
+            ht[i].first_sector = descs[order[i]].first_sector;
+            ht[i].last_sector = descs[order[i]].last_sector;
+            ht[i].pts_length = descs[order[i]].pts_length;
+            ht[i].cont = descs[order[i]].flags & 3u;
+        }
+        const uint32_t rows = (uint32_t)sh.rows, cap_sync = (uint32_t)sh.sync, cap_seg = (uint32_t)sh.seg, cap_grp = (uint32_t)sh.grp;
+        const uint32_t cap_au = (uint32_t)sh.au, cap_work = 2 * n_tracks, cap_pairs = 2 * cap_grp;
+        const uint64_t cells = sh.cells;
+        const uint32_t lim_nss = sh.nss;
+
+        // ---------------- buffers (they only ever grow)
+        ENSURE(B_COUNTS, sizeof(DecCounts) + 64);
+        ENSURE(B_STATUS, 64);
+        ENSURE(B_SEC_CNT, (size_t)n_sectors * 4); ENSURE(B_SEC_BAD, (size_t)n_sectors * 4);
+        ENSURE(B_SEC_BASE, (size_t)(n_sectors + 1) * 4); ENSURE(B_BAD_PREFIX, (size_t)(n_sectors + 1) * 4);
+        ENSURE(B_SCAN_TMP, scan_tmp_bytes(std::max<uint64_t>((uint64_t)n_sectors * 2048 / 32 + 4096, std::max<uint64_t>(rows, chunks_cap)) + 4096));
+        const size_t npa = (size_t)rows + 1;
         ENSURE(B_PK_SECTOR, npa * 4); ENSURE(B_PK_OFF, npa * 2); ENSURE(B_PK_LEN, npa * 2);
         ENSURE(B_PK_CODEC, npa); ENSURE(B_PK_PAD2, npa); ENSURE(B_PK_PARAMS, npa * 4);
         ENSURE(B_PK_MLPLEN, npa * 4); ENSURE(B_PK_PCMF, npa * 4);
@@ -537,388 +562,274 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         ENSURE(B_PK_NONMLP, npa * 4); ENSURE(B_PK_NM_PREFIX, npa * 4);
         ENSURE(B_PK_STOP, npa * 4); ENSURE(B_PK_STOP_PREFIX, npa * 4);
         ENSURE(B_PK_YIELD, npa);
+        ENSURE(B_ES, es_cap + 16 + DVDA_ES_PAD);
+        ENSURE(B_SYNC_CNT_RAW, (size_t)chunks_cap * 4); ENSURE(B_SYNC_CNT_VALID, (size_t)chunks_cap * 4);
+        ENSURE(B_SYNC_BASE_RAW, (size_t)(chunks_cap + 1) * 4); ENSURE(B_SYNC_BASE_VALID, (size_t)(chunks_cap + 1) * 4);
+        ENSURE(B_SYNC_SLOTS, (size_t)chunks_cap * SYNC_SLOT_BYTES);
+        ENSURE(B_RAW, ((size_t)cap_sync + 1) * 8); ENSURE(B_VALID, ((size_t)cap_sync + 1) * 8);
+        ENSURE(B_TRACKS, (size_t)n_tracks * sizeof(TrackDev));
+        ENSURE(B_TRK_PK_LO, (size_t)n_tracks * 4); ENSURE(B_TRK_SEG_BASE, (size_t)(n_tracks + 1) * 4);
+        ENSURE(B_TRK_GRP_BASE, (size_t)(n_tracks + 1) * 4);
+        ENSURE(B_DEC_WORK, ((size_t)cap_work + 1) * sizeof(DecWork)); ENSURE(B_OUT_WORK, ((size_t)n_tracks + 1) * sizeof(OutWork));
+        ENSURE(B_SEGS, ((size_t)cap_seg + 1) * sizeof(SegDev));
+        ENSURE(B_SEG_NAU, ((size_t)cap_seg + 1) * 4); ENSURE(B_SEG_AU_BASE, ((size_t)cap_seg + 1) * 4);
+        ENSURE(B_AU_NOTED, au_noted_bytes(cap_seg));
+        ENSURE(B_SEG_NEED, ((size_t)cap_seg + 1) * 4);
+        ENSURE(B_GROUPS, ((size_t)cap_grp + 1) * sizeof(GroupDev));
+        ENSURE(B_GRP_CELLS, ((size_t)cap_grp + 1) * 4); ENSURE(B_CELL_BASE, ((size_t)cap_grp + 1) * 8);
+        const size_t naua = (size_t)cap_au + 1;
+        ENSURE(B_AU_POS, naua * 8); ENSURE(B_AU_ERR, naua); ENSURE(B_AU, naua * sizeof(AuDev)); ENSURE(B_AU_SEG, naua * 4);
+        ENSURE(B_PSETS, naua * sizeof(ParamSet)); ENSURE(B_AU_FRAMES, naua * 2 * 4);
+        ENSURE(B_SS_FLAGS, ((size_t)cap_seg + 1) * 2 * 4); ENSURE(B_SS_FLAGS_PREV, ((size_t)cap_seg + 1) * 2 * 4);
+        ENSURE(B_SS_FLAGS_FAST, ((size_t)cap_seg + 1) * 2 * 4);
+        ENSURE(B_FIR_TAIL, ((size_t)cap_seg + 1) * 2 * DVDA_MAX_CH * 8 * 4);
+        ENSURE(B_SEG_FRAMES, ((size_t)cap_seg + 1) * 4); ENSURE(B_SEG_FRAME_SCAN, ((size_t)cap_seg + 1) * 8);
+        if (use_fast) {
+            // per-substream tables: [2][cap_au] (the kernels index them as k * cap_au + A)
+            ENSURE(B_AU_SNAP, naua * lim_nss * au_snap_bytes());
+            ENSURE(B_AU_FCHG, naua * lim_nss); ENSURE(B_SEG_CTX, ((size_t)cap_seg + 1) * 2 * seg_ctx_bytes());
+            ENSURE(B_AU_DELTA, naua * lim_nss * au_delta_bytes());
+        }
+        ENSURE(B_TILES, (cells * DVDA_LANES + 64 + 16 * DVDA_MAX_CH * DVDA_LANES) * sizeof(int32_t));   // 16 frames of slack: the filter passes read ahead
+        ENSURE(B_BYPASS, cells * DVDA_LANES + 64);
+        const int pcm_buf = c->pcm_slot ? B_PCM2 : B_PCM;
+        // (test hook: a capacity of one sample sends the decode through the "too small" path, once)
+        const uint64_t pcm_capacity = small_tables && !pcm_small_seen ? 1 : cells * DVDA_LANES + sh.pcm_fixed;
+        ENSURE(pcm_buf, (pcm_capacity + 64) * sizeof(int32_t));
+
+        void *tmp = c->buf[B_SCAN_TMP].p;
+        const size_t tmp_bytes = c->buf[B_SCAN_TMP].cap;
+        if (c->scan_tmp_gen != c->buf[B_SCAN_TMP].gen) {
+            // the scans find their control words zero and leave them zero (scan.cu)
+            CUDA_TRY(cudaMemsetAsync(tmp, 0, tmp_bytes, s));
+            c->scan_tmp_gen = c->buf[B_SCAN_TMP].gen;
+        }
+        DecCounts *cnt = c->buf[B_COUNTS].as<DecCounts>();
+        uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
+        CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(DecCounts), s));
+        CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
+        // frame counts a tile overflow of an earlier attempt found: kept across the attempts of one decode
+        uint32_t *seg_need = c->buf[B_SEG_NEED].as<uint32_t>();
+        if (attempt == 0 || c->seg_need_cap != cap_seg) {
+            CUDA_TRY(cudaMemsetAsync(seg_need, 0, ((size_t)cap_seg + 1) * 4, s));
+            c->seg_need_cap = cap_seg;
+        }
+
+        // ---------------- demux
+        uint32_t *sec_cnt = c->buf[B_SEC_CNT].as<uint32_t>(), *sec_bad = c->buf[B_SEC_BAD].as<uint32_t>();
+        uint32_t *sec_base = c->buf[B_SEC_BASE].as<uint32_t>(), *bad_prefix = c->buf[B_BAD_PREFIX].as<uint32_t>();
+        TRY(launch_sector_count(d_sectors, n_sectors, sec_cnt, sec_bad, s));
+        {
+            const uint32_t *in[2] = {sec_cnt, sec_bad}; void *out[2] = {sec_base, bad_prefix}; const bool wide[2] = {false, false};
+            uint64_t *const copy[2] = {&cnt->np, nullptr};
+            TRY(scan_batch(in, out, wide, 2, n_sectors, tmp, tmp_bytes, s, copy));
+        }
+        PacketTable pt;
         pt.sector = c->buf[B_PK_SECTOR].as<uint32_t>(); pt.off = c->buf[B_PK_OFF].as<uint16_t>();
         pt.len = c->buf[B_PK_LEN].as<uint16_t>(); pt.codec = c->buf[B_PK_CODEC].as<uint8_t>();
         pt.pad2 = c->buf[B_PK_PAD2].as<uint8_t>(); pt.params = c->buf[B_PK_PARAMS].as<uint32_t>();
         pt.mlp_len = c->buf[B_PK_MLPLEN].as<uint32_t>(); pt.pcm_frames = c->buf[B_PK_PCMF].as<uint32_t>();
-        pk_es = c->buf[B_PK_ES].as<uint64_t>(); pk_pf = c->buf[B_PK_PF].as<uint64_t>();
-        nonmlp = c->buf[B_PK_NONMLP].as<uint32_t>(); nm_prefix = c->buf[B_PK_NM_PREFIX].as<uint32_t>();
-        pstop = c->buf[B_PK_STOP].as<uint32_t>(); stop_prefix = c->buf[B_PK_STOP_PREFIX].as<uint32_t>();
-        TRY(launch_packet_fill(d_sectors, n_sectors, sec_base, pt, (uint32_t)rows, nonmlp, pstop, s));
+        uint64_t *pk_es = c->buf[B_PK_ES].as<uint64_t>(), *pk_pf = c->buf[B_PK_PF].as<uint64_t>();
+        uint32_t *nonmlp = c->buf[B_PK_NONMLP].as<uint32_t>(), *nm_prefix = c->buf[B_PK_NM_PREFIX].as<uint32_t>();
+        uint32_t *pstop = c->buf[B_PK_STOP].as<uint32_t>(), *stop_prefix = c->buf[B_PK_STOP_PREFIX].as<uint32_t>();
+        TRY(launch_packet_fill(d_sectors, n_sectors, sec_base, pt, rows, nonmlp, pstop, s));
         {
             const uint32_t *in[4] = {pt.mlp_len, pt.pcm_frames, nonmlp, pstop};
             void *out[4] = {pk_es, pk_pf, nm_prefix, stop_prefix};
             const bool wide[4] = {true, true, false, false};
-            uint64_t *const copy[4] = {mapped_total_slot(c, 1), nullptr, nullptr, nullptr};
+            uint64_t *const copy[4] = {&cnt->es_total, nullptr, nullptr, nullptr};
             TRY(scan_batch(in, out, wide, 4, rows, tmp, tmp_bytes, s, copy));
         }
-        uint64_t totals[2] = {0, 0};
-        TRY(mapped_totals(c, 2, totals));
-        np = (uint32_t)totals[0];
-        es_total = totals[1];
-        c->pk_last_sectors = n_sectors; c->pk_last_np = np;
-        if (np <= rows) break;
-        if (attempt) { dvdagpu_set_error("internal: packet table"); return -1; }
-        rows = (size_t)np + np / 8;
-    }
+        uint8_t *es = c->buf[B_ES].as<uint8_t>();
+        TIMED(DVDAGPU_K_ES_GATHER, launch_es_gather(d_sectors, pt, rows, pk_es, es, cnt, s));
+        CUDA_TRY(cudaEventRecord(c->ev[1], s));
 
-    ENSURE(B_ES, es_total + DVDA_ES_PAD);
-    uint8_t *es = c->buf[B_ES].as<uint8_t>();
-    CUDA_TRY(cudaMemsetAsync(es + es_total, 0, DVDA_ES_PAD, s));
-    TIMED(DVDAGPU_K_ES_GATHER, launch_es_gather(d_sectors, pt, np, pk_es, es, s));
-    CUDA_TRY(cudaEventRecord(c->ev[1], s));
-
-    // ---------------- index
-    const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
-    ENSURE(B_SYNC_CNT_RAW, (size_t)chunks * 4); ENSURE(B_SYNC_CNT_VALID, (size_t)chunks * 4);
-    ENSURE(B_SYNC_BASE_RAW, (size_t)(chunks + 1) * 4); ENSURE(B_SYNC_BASE_VALID, (size_t)(chunks + 1) * 4);
-    ENSURE(B_SYNC_SLOTS, (size_t)chunks * SYNC_SLOT_BYTES);
-    uint16_t *sync_slots = c->buf[B_SYNC_SLOTS].as<uint16_t>();
-    // (test hook: DVDAGPU_SYNC_SLOTS=0 sends every chunk with a match through the re-search path)
-    const uint32_t nslots = getenv("DVDAGPU_SYNC_SLOTS") ? (uint32_t)atoi(getenv("DVDAGPU_SYNC_SLOTS")) : 2u;
-    uint32_t *cnt_raw = c->buf[B_SYNC_CNT_RAW].as<uint32_t>(), *cnt_valid = c->buf[B_SYNC_CNT_VALID].as<uint32_t>();
-    uint32_t *base_raw = c->buf[B_SYNC_BASE_RAW].as<uint32_t>(), *base_valid = c->buf[B_SYNC_BASE_VALID].as<uint32_t>();
-    uint32_t n_raw = 0, n_valid = 0;
-    if (es_total) {
-        TIMED(DVDAGPU_K_SYNC_SCAN, launch_sync_count(es, es_total, cnt_raw, cnt_valid, sync_slots, nslots, s));
-        const uint32_t *in[2] = {cnt_raw, cnt_valid}; void *out[2] = {base_raw, base_valid}; const bool wide[2] = {false, false};
-        TRY(scan_batch(in, out, wide, 2, chunks, tmp, tmp_bytes, s));
-    } else {
-        CUDA_TRY(cudaMemsetAsync(base_raw + chunks, 0, 4, s));
-        CUDA_TRY(cudaMemsetAsync(base_valid + chunks, 0, 4, s));
-    }
-    ENSURE(B_TRACKS, (size_t)n_tracks * sizeof(TrackDev));
-    ENSURE(B_TRK_PK_LO, (size_t)n_tracks * 4); ENSURE(B_TRK_SEG_BASE, (size_t)(n_tracks + 1) * 4);
-    ENSURE(B_TRK_GRP_BASE, (size_t)(n_tracks + 1) * 4);
-    TrackDev *d_tracks = c->buf[B_TRACKS].as<TrackDev>();
-    TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
-    // The sync lists are sized before their lengths are known to the host (a sync every 2 KiB of
-    // stream, or what the same input needed last time): they are filled, the tracks set up from
-    // them, and the lengths come back together with the track table.  Lists that were too small
-    // grow and the step is repeated.
-    uint64_t *raw = nullptr, *valid = nullptr;
-    size_t cap_raw = (size_t)(es_total / 2048) + 1024, cap_valid = cap_raw;
-    if (c->sync_last_es == es_total) { cap_raw = std::max<size_t>(cap_raw, c->sync_last_raw); cap_valid = std::max<size_t>(cap_valid, c->sync_last_valid); }
-    if (small_tables) cap_raw = cap_valid = 1;
-    for (int attempt = 0;; attempt++) {
-        ENSURE(B_RAW, (cap_raw + 1) * 8); ENSURE(B_VALID, (cap_valid + 1) * 8);
-        raw = c->buf[B_RAW].as<uint64_t>(); valid = c->buf[B_VALID].as<uint64_t>();
-        if (es_total) TRY(launch_sync_fill(es, es_total, cnt_raw, sync_slots, nslots, base_raw, base_valid,
-                                           raw, (uint32_t)cap_raw, valid, (uint32_t)cap_valid, s));
+        // ---------------- index
+        uint16_t *sync_slots = c->buf[B_SYNC_SLOTS].as<uint16_t>();
+        uint32_t *cnt_raw = c->buf[B_SYNC_CNT_RAW].as<uint32_t>(), *cnt_valid = c->buf[B_SYNC_CNT_VALID].as<uint32_t>();
+        uint32_t *base_raw = c->buf[B_SYNC_BASE_RAW].as<uint32_t>(), *base_valid = c->buf[B_SYNC_BASE_VALID].as<uint32_t>();
+        uint64_t *raw = c->buf[B_RAW].as<uint64_t>(), *valid = c->buf[B_VALID].as<uint64_t>();
+        if (sh.any_mlp) {
+            TIMED(DVDAGPU_K_SYNC_SCAN, launch_sync_count(es, cnt, chunks_cap, cnt_raw, cnt_valid, sync_slots, nslots, s));
+            const uint32_t *in[2] = {cnt_raw, cnt_valid}; void *out[2] = {base_raw, base_valid}; const bool wide[2] = {false, false};
+            uint64_t *const copy[2] = {&cnt->n_raw, &cnt->n_valid};
+            TRY(scan_batch(in, out, wide, 2, chunks_cap, tmp, tmp_bytes, s, copy));
+            TRY(launch_sync_fill(es, cnt, chunks_cap, cnt_raw, sync_slots, nslots, base_raw, base_valid, raw, cap_sync, valid, cap_sync, s));
+        }
+        TrackDev *d_tracks = c->buf[B_TRACKS].as<TrackDev>();
+        TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
         TrackSetupArgs ta;
-        ta.es = es; ta.es_total = es_total; ta.n_sectors = n_sectors; ta.sec_base = sec_base; ta.bad_prefix = bad_prefix;
-        ta.pt = pt; ta.np = np; ta.pk_es = pk_es; ta.pk_pf = pk_pf; ta.pk_nonmlp = nm_prefix; ta.pk_pcm_stop = stop_prefix;
-        ta.raw = raw; ta.n_raw = base_raw + chunks; ta.cap_raw = (uint32_t)cap_raw;
-        ta.valid = valid; ta.n_valid = base_valid + chunks; ta.cap_valid = (uint32_t)cap_valid;
+        ta.es = es; ta.cnt = cnt; ta.n_sectors = n_sectors; ta.sec_base = sec_base; ta.bad_prefix = bad_prefix;
+        ta.pt = pt; ta.pk_es = pk_es; ta.pk_pf = pk_pf; ta.pk_nonmlp = nm_prefix; ta.pk_pcm_stop = stop_prefix;
+        ta.raw = raw; ta.cap_raw = cap_sync; ta.valid = valid; ta.cap_valid = cap_sync;
+        ta.mlp_searched = sh.any_mlp ? 1u : 0u;
         TRY(launch_track_setup(ta, d_tracks, n_tracks, s));
-        {
-            void *const host[3] = {&n_raw, &n_valid, ht.data()};
-            const void *const dev[3] = {base_raw + chunks, base_valid + chunks, d_tracks};
-            const size_t bytes[3] = {4, 4, n_tracks * sizeof(TrackDev)};
-            TRY(small_d2h_multi(c, 3, host, dev, bytes));
-        }
-        c->sync_last_es = es_total; c->sync_last_raw = n_raw; c->sync_last_valid = n_valid;
-        if (n_raw <= cap_raw && n_valid <= cap_valid) break;
-        if (attempt) { dvdagpu_set_error("internal: sync lists"); return -1; }
-        cap_raw = n_raw; cap_valid = n_valid;
-    }
+        uint32_t *trk_pk_lo = c->buf[B_TRK_PK_LO].as<uint32_t>(), *trk_seg_base = c->buf[B_TRK_SEG_BASE].as<uint32_t>();
+        uint32_t *trk_grp_base = c->buf[B_TRK_GRP_BASE].as<uint32_t>();
+        DecWork *d_work = c->buf[B_DEC_WORK].as<DecWork>();
+        OutWork *d_out_work = c->buf[B_OUT_WORK].as<OutWork>();
+        TRY(launch_track_plan(d_tracks, n_tracks, trk_pk_lo, trk_seg_base, trk_grp_base, d_work, d_out_work, cap_work, cap_seg, cap_grp,
+                              cap_sync, cnt, s));
 
-    std::vector<uint32_t> h_pk_lo(n_tracks), h_seg_base(n_tracks + 1), h_grp_base(n_tracks + 1);
-    uint32_t nseg = 0, ngroups = 0;
-    for (uint32_t i = 0; i < n_tracks; i++) {
-        h_pk_lo[i] = ht[i].pk_lo;
-        if (ht[i].status != 0 || ht[i].codec != 1) { ht[i].nseg = 0; ht[i].ngrp = 0; }
-        ht[i].seg_base = nseg; ht[i].grp_base = ngroups;
-        h_seg_base[i] = nseg; h_grp_base[i] = ngroups;
-        nseg += ht[i].nseg; ngroups += ht[i].ngrp;
-    }
-    h_seg_base[n_tracks] = nseg; h_grp_base[n_tracks] = ngroups;
-    // decode work lists, one per channel-count class (0 = generic, more than 4 channels):
-    // substream 0 of a two-substream stream carries the stereo pair (DVD-Audio layout)
-    std::vector<DecWork> h_work[5];
-    uint32_t n_warps[5] = {0, 0, 0, 0, 0};
-    for (uint32_t i = 0; i < n_tracks; i++) {
-        if (!ht[i].nseg) continue;
-        for (uint32_t k = 0; k < ht[i].nss; k++) {
-            const uint32_t nch = ht[i].nss == 1 ? ht[i].channels : (k == 0 ? 2 : ht[i].channels - 2);
-            const uint32_t cls = (nch >= 1 && nch <= 4) ? nch : 0;
-            DecWork w = {n_warps[cls], i, k, 0};
-            h_work[cls].push_back(w);
-            n_warps[cls] += ht[i].ngrp;
-        }
-    }
-    uint32_t *trk_pk_lo = c->buf[B_TRK_PK_LO].as<uint32_t>(), *trk_seg_base = c->buf[B_TRK_SEG_BASE].as<uint32_t>();
-    uint32_t *trk_grp_base = c->buf[B_TRK_GRP_BASE].as<uint32_t>();
-    TRY(queue_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
-    TRY(queue_h2d(c, trk_pk_lo, h_pk_lo.data(), n_tracks * 4));
-    TRY(queue_h2d(c, trk_seg_base, h_seg_base.data(), (n_tracks + 1) * 4));
-    TRY(queue_h2d(c, trk_grp_base, h_grp_base.data(), (n_tracks + 1) * 4));
-
-    // decode mode: the three-pass path (default), the header passes + the fused entropy / filter /
-    // output pass (DVDAGPU_FUSED=1: no tiles in HBM, but measured slower — DESIGN.md section 6), or the
-    // complete single-pass decoder alone (DVDAGPU_SINGLE_PASS=1); the GPU tests run all three
-    const int mode = getenv("DVDAGPU_SINGLE_PASS") ? 0 : getenv("DVDAGPU_FUSED") ? 2 : 1;
-    // work lists of the fused pass, by class (0: at most two channels per substream, 1: up to four):
-    // a run of warps per track
-    std::vector<FusedWork> h_fused[2];
-    uint32_t n_fwarps[2] = {0, 0};
-    if (mode == 2) {
-        for (uint32_t i = 0; i < n_tracks; i++) {
-            if (!ht[i].nseg) continue;
-            uint32_t n0 = ht[i].channels, n1 = 0;
-            if (ht[i].nss == 2) { n0 = 2; n1 = ht[i].channels > 2 ? ht[i].channels - 2 : 0; if (!n1) continue; }
-            else if (ht[i].nss != 1) continue;
-            if (n0 < 1 || n0 > 4 || n1 > 4) continue;
-            const int cl = (n0 > 2 || n1 > 2) ? 1 : 0;
-            FusedWork w = {n_fwarps[cl], i, n0, n1};
-            h_fused[cl].push_back(w);
-            n_fwarps[cl] += ht[i].ngrp * fused_warps_per_group(n0, n1);
-        }
-    }
-    const FusedWork *d_fused[2] = {nullptr, nullptr};
-    uint32_t n_fused[2] = {0, 0};
-    {
-        ENSURE(B_FUSED_WORK, (h_fused[0].size() + h_fused[1].size() + 1) * sizeof(FusedWork));
-        FusedWork *base = c->buf[B_FUSED_WORK].as<FusedWork>();
-        size_t off = 0;
-        for (int cl = 0; cl < 2; cl++) {
-            n_fused[cl] = (uint32_t)h_fused[cl].size();
-            d_fused[cl] = base + off;
-            if (n_fused[cl]) TRY(queue_h2d(c, base + off, h_fused[cl].data(), n_fused[cl] * sizeof(FusedWork)));
-            off += n_fused[cl];
-        }
-    }
-    const DecWork *d_work[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    uint32_t n_work[5] = {0, 0, 0, 0, 0};
-    {
-        size_t total = 0;
-        for (int cl = 0; cl < 5; cl++) total += h_work[cl].size();
-        ENSURE(B_DEC_WORK, (total + 1) * sizeof(DecWork));
-        DecWork *base = c->buf[B_DEC_WORK].as<DecWork>();
-        size_t off = 0;
-        for (int cl = 0; cl < 5; cl++) {
-            n_work[cl] = (uint32_t)h_work[cl].size();
-            d_work[cl] = base + off;
-            if (n_work[cl])
-                TRY(queue_h2d(c, base + off, h_work[cl].data(), n_work[cl] * sizeof(DecWork)));
-            off += n_work[cl];
-        }
-        TRY(flush_h2d(c));
-    }
-    MlpTables m;
-    memset(&m, 0, sizeof m);
-    m.es = es; m.es_total = es_total; m.pk_es = pk_es; m.np = np;
-    m.tracks = d_tracks; m.n_tracks = n_tracks; m.nseg = nseg; m.ngroups = ngroups;
-    uint32_t nau = 0;
-    uint32_t max_chunks = 0, status = 0;
-    ENSURE(B_STATUS, 64);
-    uint32_t *d_status = c->buf[B_STATUS].as<uint32_t>();
-    m.status = d_status;
-    m.status_rw = d_status;
-    m.any_fallback = d_status + 8;
-    m.huff_lut = c->huff_lut;
-    // samples of the PCM tracks (known since the track set-up) and the alignment gaps
-    uint64_t pcm_fixed = 4ull * n_tracks + 64;
-    for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].status == 0 && ht[i].codec == 0) pcm_fixed += ht[i].frames * ht[i].channels;
-    const int pcm_buf = c->pcm_slot ? B_PCM2 : B_PCM;
-    bool out_queued = false;
-    if (nseg) {
-        ENSURE(B_SEGS, (size_t)nseg * sizeof(SegDev));
-        ENSURE(B_SEG_NAU, (size_t)nseg * 4); ENSURE(B_SEG_AU_BASE, (size_t)(nseg + 1) * 4);
+        const PlanLimits lim = {cap_au, cells, sh.max_au, lim_nss, sh.out_warps, sh.any_pcm ? 1u : 0u, sh.any_mlp ? 1u : 0u};
+        memset(&m, 0, sizeof m);
+        m.es = es; m.pk_es = pk_es; m.cnt = cnt; m.cap_seg = cap_seg; m.cap_au = cap_au; m.cap_grp = cap_grp;
+        m.tracks = d_tracks; m.n_tracks = n_tracks;
+        m.status = d_status; m.status_rw = d_status; m.any_fallback = d_status + 8;
+        m.huff_lut = c->huff_lut;
+        m.seg_need = seg_need;
         m.segs = c->buf[B_SEGS].as<SegDev>();
-        uint32_t *seg_nau = c->buf[B_SEG_NAU].as<uint32_t>(), *seg_au_base = c->buf[B_SEG_AU_BASE].as<uint32_t>();
-        TRY(launch_segment_fill(d_tracks, n_tracks, trk_seg_base, valid, m.segs, nseg, s));
-        ENSURE(B_AU_NOTED, au_noted_bytes(nseg));
-        uint32_t *au_noted = c->buf[B_AU_NOTED].as<uint32_t>();
-        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, nullptr, nullptr, seg_au_base, au_noted, 0, s));
-        TRY(scan_u32_to_u32(seg_nau, seg_au_base, nseg, tmp, tmp_bytes, s));
-        // the groups (tile sizes) follow from the access-unit counts alone: set them up now and
-        // fetch all the sizes the next allocations need in one round trip
-        ENSURE(B_GROUPS, (size_t)ngroups * sizeof(GroupDev));
-        ENSURE(B_GRP_CELLS, (size_t)ngroups * 4); ENSURE(B_CELL_BASE, (size_t)(ngroups + 1) * 8);
-        ENSURE(B_GRP_CHUNKS, (size_t)ngroups * 4);
         m.groups = c->buf[B_GROUPS].as<GroupDev>();
-        uint32_t *grp_cells = c->buf[B_GRP_CELLS].as<uint32_t>(), *grp_chunks = c->buf[B_GRP_CHUNKS].as<uint32_t>();
-        uint64_t *cell_base = c->buf[B_CELL_BASE].as<uint64_t>();
-        uint64_t cells = 0;
-        struct { uint32_t au, chunks; } most = {0, 0};
-        CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
-        TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, d_status + 1, s));
-        TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
-        {
-            void *const host[3] = {&nau, &cells, &most};
-            const void *const dev[3] = {seg_au_base + nseg, cell_base + ngroups, d_status + 1};
-            const size_t bytes[3] = {4, 8, sizeof most};
-            TRY(small_d2h_multi(c, 3, host, dev, bytes));
-        }
-        m.nau = nau;
-        const size_t naua = (size_t)nau + 1;
-        ENSURE(B_AU_POS, naua * 8); ENSURE(B_AU_ERR, naua); ENSURE(B_AU, naua * sizeof(AuDev)); ENSURE(B_AU_SEG, naua * 4);
-        ENSURE(B_PSETS, naua * sizeof(ParamSet)); ENSURE(B_AU_FRAMES, naua * 2 * 4);
-        ENSURE(B_SS_FLAGS, (size_t)nseg * 2 * 4); ENSURE(B_SS_FLAGS_PREV, (size_t)nseg * 2 * 4); ENSURE(B_SS_FLAGS_FAST, (size_t)nseg * 2 * 4);
-        ENSURE(B_FIR_TAIL, (size_t)nseg * 2 * DVDA_MAX_CH * 8 * 4);
         m.au_pos = c->buf[B_AU_POS].as<uint64_t>(); m.au_err = c->buf[B_AU_ERR].as<uint8_t>(); m.au_seg = c->buf[B_AU_SEG].as<uint32_t>();
         m.au = c->buf[B_AU].as<AuDev>(); m.psets = c->buf[B_PSETS].as<ParamSet>();
         m.au_frames_ss = c->buf[B_AU_FRAMES].as<uint32_t>();
         m.ss_flags = c->buf[B_SS_FLAGS].as<uint32_t>(); m.ss_flags_prev = c->buf[B_SS_FLAGS_PREV].as<uint32_t>(); m.ss_flags_fast = c->buf[B_SS_FLAGS_FAST].as<uint32_t>();
         m.fir_tail = c->buf[B_FIR_TAIL].as<int32_t>();
-        TRY(launch_au_chase(es, m.segs, nseg, d_tracks, seg_nau, m.au_pos, m.au_seg, seg_au_base, au_noted, 1, s));
-        TRY(launch_yield(m, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), s));
-        CUDA_TRY(cudaEventRecord(c->ev[2], s));
-
-        // ---------------- decode
-        // Parity / CRC-8 on a second stream, beside the group set-up and the header passes.  Small
-        // access units: the windowed kernel on the low-priority stream (it fills what the chain
-        // leaves free).  Large ones: the direct kernel at the chain's own priority, which then runs
-        // first and lets the header passes follow.  Both pairings, and starting the check beside the
-        // entropy pass or on its own in between, were measured: DESIGN.md section 6.
-        // (a caller's stream has the default = lowest priority, like aux_stream)
-        cudaStream_t chk_stream = (checkdata_windowed(m) || s != c->own_stream) ? c->aux_stream : c->aux_stream_hi;
-        CUDA_TRY(cudaEventRecord(c->aux_ev[0], s));
-        CUDA_TRY(cudaStreamWaitEvent(chk_stream, c->aux_ev[0], 0));
-        CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][0], chk_stream));
-        TRY(launch_checkdata(m, seg_au_base, chk_stream));
-        CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][1], chk_stream));
-        c->kev_used[DVDAGPU_K_CHECKDATA] = true;
-        CUDA_TRY(cudaEventRecord(c->aux_ev[1], chk_stream));
-        ENSURE(B_SEG_FRAMES, (size_t)nseg * 4); ENSURE(B_SEG_FRAME_SCAN, (size_t)(nseg + 1) * 8);
-        uint32_t *seg_frames = c->buf[B_SEG_FRAMES].as<uint32_t>();
-        uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
-
-        // The three-pass path (access-unit parallel) decodes what has the common shape; the complete
-        // single-pass decoder takes the rest.  DVDAGPU_SINGLE_PASS=1 gives everything to the latter
-        // (the GPU tests run both ways).
-        const bool use_fast = mode != 0;
+        m.tiles = c->buf[B_TILES].as<int32_t>(); m.bypass = c->buf[B_BYPASS].as<uint8_t>();
+        m.pcm = c->buf[pcm_buf].as<int32_t>();
         if (use_fast) {
-            ENSURE(B_SS_STICKY, (size_t)nseg * 2 * 4);
-            m.ss_sticky = c->buf[B_SS_STICKY].as<uint32_t>();
-            CUDA_TRY(cudaMemsetAsync(m.ss_sticky, 0, (size_t)nseg * 2 * 4, s));
-            m.nss_max = 1;
-            for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].nseg && ht[i].nss > m.nss_max) m.nss_max = ht[i].nss;
-            // per-substream tables: [nss_max][nau] (the kernels index them as k * nau + A)
-            ENSURE(B_AU_SNAP, naua * m.nss_max * au_snap_bytes());
             m.au_snap = reinterpret_cast<AuSnap *>(c->buf[B_AU_SNAP].p);
-            ENSURE(B_AU_FCHG, naua * m.nss_max); ENSURE(B_SEG_CTX, (size_t)nseg * 2 * seg_ctx_bytes());
-            ENSURE(B_AU_DELTA, naua * m.nss_max * au_delta_bytes());
             m.au_fchg = c->buf[B_AU_FCHG].as<uint8_t>();
             m.seg_ctx = reinterpret_cast<SegCtx *>(c->buf[B_SEG_CTX].p);
             m.au_delta = reinterpret_cast<AuDelta *>(c->buf[B_AU_DELTA].p);
-            // contexts exist only where pass A0 goes (substreams of up to four channels)
-            CUDA_TRY(cudaMemsetAsync(m.seg_ctx, 0, (size_t)nseg * 2 * seg_ctx_bytes(), s));
         }
-        for (int attempt = 0;; attempt++) {
-            if (attempt) {
-                // after a tile overflow: the groups again, from the frame counts now known
-                // (after a STATUS_REDO of the fused pass the same steps are simply repeated)
-                CUDA_TRY(cudaMemsetAsync(d_status, 0, 64, s));
-                TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, ngroups, grp_cells, grp_chunks, d_status + 1, s));
-                TRY(scan_u32_to_u64(grp_cells, cell_base, ngroups, tmp, tmp_bytes, s));
-                TRY(small_d2h_pair(c, &cells, cell_base + ngroups, 8, &most, d_status + 1, sizeof most));
+        if (sh.any_mlp) {
+            uint32_t *seg_nau = c->buf[B_SEG_NAU].as<uint32_t>(), *seg_au_base = c->buf[B_SEG_AU_BASE].as<uint32_t>();
+            uint32_t *au_noted = c->buf[B_AU_NOTED].as<uint32_t>();
+            uint32_t *grp_cells = c->buf[B_GRP_CELLS].as<uint32_t>();
+            uint64_t *cell_base = c->buf[B_CELL_BASE].as<uint64_t>();
+            TRY(launch_segment_fill(d_tracks, n_tracks, trk_seg_base, valid, m.segs, cap_seg, cnt, s));
+            TRY(launch_au_chase(es, m.segs, cap_seg, cnt, d_tracks, seg_nau, nullptr, nullptr, seg_au_base, au_noted, 0, s));
+            {
+                const uint32_t *in[1] = {seg_nau}; void *out[1] = {seg_au_base}; const bool wide[1] = {false};
+                uint64_t *const copy[1] = {&cnt->nau};
+                TRY(scan_batch(in, out, wide, 1, cap_seg, tmp, tmp_bytes, s, copy));
             }
-            CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, s));         // (the maxima behind it stay)
-            m.max_au = most.au; max_chunks = most.chunks;
-            ENSURE(B_TILES, (cells * DVDA_LANES + 64 + 16 * DVDA_MAX_CH * DVDA_LANES) * sizeof(int32_t));   // 16 frames of slack: the filter passes read ahead
-            ENSURE(B_BYPASS, cells * DVDA_LANES + 64);
-            m.tiles = c->buf[B_TILES].as<int32_t>(); m.bypass = c->buf[B_BYPASS].as<uint8_t>();
-            TRY(launch_group_offsets(m.groups, ngroups, cell_base, s));
+            // the groups (tile sizes) follow from the access-unit counts alone
+            TRY(launch_group_setup(d_tracks, n_tracks, trk_grp_base, m.segs, m.groups, cap_grp, cnt, grp_cells, seg_need, s));
+            {
+                const uint32_t *in[1] = {grp_cells}; void *out[1] = {cell_base}; const bool wide[1] = {true};
+                uint64_t *const copy[1] = {&cnt->cells};
+                TRY(scan_batch(in, out, wide, 1, cap_grp, tmp, tmp_bytes, s, copy));
+            }
+            TRY(launch_plan_check(cnt, lim, s));
+            TRY(launch_au_chase(es, m.segs, cap_seg, cnt, d_tracks, seg_nau, m.au_pos, m.au_seg, seg_au_base, au_noted, 1, s));
+            TRY(launch_yield(m, rows, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), s));
+            CUDA_TRY(cudaEventRecord(c->ev[2], s));
+
+            // ---------------- decode
+            // Parity / CRC-8 on a second stream, beside the group set-up and the header passes.  Small
+            // access units: the windowed kernel on the low-priority stream (it fills what the chain
+            // leaves free).  Large ones: the direct kernel at the chain's own priority, which then runs
+            // first and lets the header passes follow.  Both pairings, and starting the check beside the
+            // entropy pass or on its own in between, were measured: DESIGN.md section 6.
+            // (a caller's stream has the default = lowest priority, like aux_stream)
+            cudaStream_t chk_stream = (sh.windowed || s != c->own_stream) ? c->aux_stream : c->aux_stream_hi;
+            CUDA_TRY(cudaEventRecord(c->aux_ev[0], s));
+            CUDA_TRY(cudaStreamWaitEvent(chk_stream, c->aux_ev[0], 0));
+            CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][0], chk_stream));
+            TRY(launch_checkdata(m, seg_au_base, sh.windowed, chk_stream));
+            CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][1], chk_stream));
+            c->kev_used[DVDAGPU_K_CHECKDATA] = true;
+            CUDA_TRY(cudaEventRecord(c->aux_ev[1], chk_stream));
+            uint32_t *seg_frames = c->buf[B_SEG_FRAMES].as<uint32_t>();
+            uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
+            TRY(launch_group_offsets(m.groups, cap_grp, cnt, cell_base, s));
             m.fast = 0;
             if (use_fast) {
-                // three passes with access-unit parallelism; what they give up on is flagged ...
-                // (start with every segment flagged: substreams with more than 4 channels
-                // are not visited by the fast path at all)
-                CUDA_TRY(cudaMemsetAsync(m.ss_flags, SEG_FALLBACK, (size_t)nseg * 2 * 4, s));
-                TRY(launch_mlp_fast(m, d_work, n_work, n_warps, c->kev, c->kev_used, c->aux_ev[1], mode == 2, s));
-                CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
-                CUDA_TRY(cudaMemcpyAsync(m.ss_flags_fast, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
-                m.fast = (uint32_t)mode;
+                // The three-pass path (access-unit parallel) decodes what has the common shape; what it
+                // gives up on is flagged (start with every segment flagged: substreams with more than 4
+                // channels are not visited by the fast path at all) ...
+                CUDA_TRY(cudaMemsetAsync(m.seg_ctx, 0, ((size_t)cap_seg + 1) * 2 * seg_ctx_bytes(), s));   // contexts exist only where pass A0 goes
+                CUDA_TRY(cudaMemsetAsync(m.ss_flags, SEG_FALLBACK, ((size_t)cap_seg + 1) * 2 * 4, s));
+                TRY(launch_mlp_fast(m, d_work, cap_pairs, sh.max_au, lim_nss, c->kev, c->kev_used, c->aux_ev[1], s));
+                CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, ((size_t)cap_seg + 1) * 2 * 4, cudaMemcpyDeviceToDevice, s));
+                CUDA_TRY(cudaMemcpyAsync(m.ss_flags_fast, m.ss_flags, ((size_t)cap_seg + 1) * 2 * 4, cudaMemcpyDeviceToDevice, s));
+                m.fast = 1;
             }
             CUDA_TRY(cudaStreamWaitEvent(s, c->aux_ev[1], 0));
             // ... and decoded by the complete single-pass decoder (everything, without the fast path)
-            TIMED(DVDAGPU_K_MLP_DECODE, launch_mlp_decode(m, d_work, n_work, n_warps, s));
-            CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, (size_t)nseg * 2 * 4, cudaMemcpyDeviceToDevice, s));
+            TIMED(DVDAGPU_K_MLP_DECODE, launch_mlp_decode(m, d_work, cap_pairs, s));
+            CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, ((size_t)cap_seg + 1) * 2 * 4, cudaMemcpyDeviceToDevice, s));
             TIMED(DVDAGPU_K_CARRY_FIX, launch_carry_fix(m, s));
             TRY(launch_seg_finalize(m, seg_frames, d_status, s));
-            // the track totals are computed before the status is known (one round trip for both);
-            // after an overflow they are simply computed again
-            TRY(scan_u32_to_u64(seg_frames, seg_frame_scan, nseg, tmp, tmp_bytes, s));
+            TRY(scan_u32_to_u64(seg_frames, seg_frame_scan, cap_seg, tmp, tmp_bytes, s));
             TRY(launch_track_finalize(m, seg_frame_scan, d_status, s));
-            // The output buffer is sized before the frame counts are known (every MLP sample has a
-            // place in the tiles, so the tiles' size bounds them), the tracks' places in it are
-            // computed on the device, and the fused output pass of the fast path is queued right
-            // here: the round trip below then costs the device nothing.
-            // (test hook: a capacity of one sample sends every decode through the "too small" path)
-            const uint64_t pcm_capacity = small_tables ? 1 : cells * DVDA_LANES + pcm_fixed;
-            ENSURE(pcm_buf, (pcm_capacity + 64) * sizeof(int32_t));
-            m.pcm = c->buf[pcm_buf].as<int32_t>();
-            LAUNCH(k_track_out_base, 1, OB_THREADS, 0, s, d_tracks, n_tracks, d_status, pcm_capacity);
-            CUDA_TRY(cudaEventRecord(c->ev[3], s));
-            out_queued = m.fast != 0;
-            if (m.fast == 1) TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
-            if (m.fast == 2) TIMED(DVDAGPU_K_MLP_FUSED, launch_mlp_fused(m, d_fused, n_fused, n_fwarps, s));
-            TRY(small_d2h_pair(c, &status, d_status, 4, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
-            if (!(status & (SEG_OVERFLOW | STATUS_REDO))) break;
-            // (a redo flags at least one more segment each time; an overflow is settled by the second attempt)
-            if (attempt == 8) { dvdagpu_set_error((status & SEG_OVERFLOW) ? "tile overflow persists" : "the fused pass keeps asking for another attempt"); return -1; }
+        } else {
+            TRY(launch_plan_check(cnt, lim, s));
+            CUDA_TRY(cudaEventRecord(c->ev[2], s));
         }
-    } else {
-        CUDA_TRY(cudaEventRecord(c->ev[2], s));
-        CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, s));
-        LAUNCH(k_track_out_base, 1, OB_THREADS, 0, s, d_tracks, n_tracks, d_status, pcm_fixed);
-        TRY(small_d2h(c, ht.data(), d_tracks, n_tracks * sizeof(TrackDev)));
+        // The output buffer was sized before the frame counts are known (every MLP sample has a place
+        // in the tiles, so the tiles' size bounds them); the tracks' places in it are computed on the device.
+        LAUNCH(k_track_out_base, 1, OB_THREADS, 0, s, d_tracks, n_tracks, d_status, pcm_capacity);
         CUDA_TRY(cudaEventRecord(c->ev[3], s));
-    }
-    if (getenv("DVDAGPU_DEBUG")) {
-        fprintf(stderr, "[dvdagpu] sectors=%u packets=%u es=%llu raw=%u valid=%u segs=%u groups=%u aus=%u\n",
-                n_sectors, np, (unsigned long long)es_total, n_raw, n_valid, nseg, ngroups, nau);
-        for (uint32_t i = 0; i < n_tracks; i++) {
-            const TrackDev &T = ht[i];
-            fprintf(stderr, "[dvdagpu] track %u: status=%d codec=%d err=%x ch=%u pk=[%u,%u) pk_x=%u pk_open=%u es=[%llu,%llu) cut=%llu nss=%u nseg=%u err_seg=%u frames=%llu trunc=%u\n",
-                    i, T.status, T.codec, T.error_flags, T.channels, T.pk_lo, T.pk_hi, T.pk_x, T.pk_open,
-                    (unsigned long long)T.es_start, (unsigned long long)T.es_end, (unsigned long long)T.es_cut,
-                    T.nss, T.nseg, T.err_seg, (unsigned long long)T.frames, T.truncated);
-            fprintf(stderr, "[dvdagpu]          cont=%u check=[%u,%u) stopped=%u\n", T.cont, T.pk_check, T.pk_check_end, T.stopped);
+
+        // ---------------- output
+        if (sh.any_mlp) {
+            if (m.fast) TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_out_work, sh.out_warps, s));
+            TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, s));
         }
-        if (nseg) {
-            std::vector<SegDev> hs(std::min<uint32_t>(nseg, 8));
-            cudaMemcpy(hs.data(), m.segs, hs.size() * sizeof(SegDev), cudaMemcpyDeviceToHost);
-            for (size_t i = 0; i < hs.size(); i++)
-                fprintf(stderr, "[dvdagpu] seg %zu: es=[%llu,%llu) n_au=%u au_base=%u flags=%x frames=%u err=%x err_au=%u frame0=%llu\n",
-                        i, (unsigned long long)hs[i].es_pos, (unsigned long long)hs[i].es_limit, hs[i].n_au, hs[i].au_base,
-                        hs[i].flags, hs[i].frames, hs[i].err, hs[i].err_au, (unsigned long long)hs[i].frame0);
+        if (sh.any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, rows, cnt, d_status, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));
+        CUDA_TRY(cudaEventRecord(c->ev[4], s));
+
+        // ---------------- the one round trip: counts, status, track table
+        {
+            void *const host[3] = {&k, &status, ht.data()};
+            const void *const dev[3] = {cnt, d_status, d_tracks};
+            const size_t bytes[3] = {sizeof(DecCounts), 4, n_tracks * sizeof(TrackDev)};
+            TRY(small_d2h_multi(c, 3, host, dev, bytes));
+        }
+        if (g_trace_on) { trace_host("decode done"); trace_dump(); g_trace_on = false; }
+        if (getenv("DVDAGPU_DEBUG")) {
+            fprintf(stderr, "[dvdagpu] attempt %d: sectors=%u packets=%llu es=%llu raw=%llu valid=%llu segs=%u groups=%u aus=%llu cells=%llu max_au=%u overflow=%x status=%x\n",
+                    attempt, n_sectors, (unsigned long long)k.np, (unsigned long long)k.es_total, (unsigned long long)k.n_raw,
+                    (unsigned long long)k.n_valid, k.nseg, k.ngroups, (unsigned long long)k.nau, (unsigned long long)k.cells, k.max_au, k.overflow, status);
+            for (uint32_t i = 0; i < n_tracks; i++) {
+                const TrackDev &T = ht[i];
+                fprintf(stderr, "[dvdagpu] track %u: status=%d codec=%d err=%x ch=%u pk=[%u,%u) pk_x=%u pk_open=%u es=[%llu,%llu) cut=%llu nss=%u nseg=%u err_seg=%u frames=%llu trunc=%u\n",
+                        i, T.status, T.codec, T.error_flags, T.channels, T.pk_lo, T.pk_hi, T.pk_x, T.pk_open,
+                        (unsigned long long)T.es_start, (unsigned long long)T.es_end, (unsigned long long)T.es_cut,
+                        T.nss, T.nseg, T.err_seg, (unsigned long long)T.frames, T.truncated);
+                fprintf(stderr, "[dvdagpu]          cont=%u check=[%u,%u) stopped=%u\n", T.cont, T.pk_check, T.pk_check_end, T.stopped);
+            }
+        }
+        // ---------------- a table too small, a kernel left out that had work, a tile or the output buffer too small?
+        if (!k.overflow && !(status & (SEG_OVERFLOW | STATUS_PCM_SMALL))) break;
+        DecShape in;
+        shape_from_input(in, n_sectors, n_tracks);
+        auto grow = [](uint64_t &cap, uint64_t need, uint64_t bound) { cap = std::max<uint64_t>(std::max<uint64_t>(need + need / 16 + 64, std::min<uint64_t>(cap * 4, bound)), cap); };
+        if (k.overflow & CAP_ROWS) grow(sh.rows, k.need_rows, in.rows);
+        if (k.overflow & CAP_SYNC) grow(sh.sync, k.need_sync, in.sync);
+        if (k.overflow & CAP_SEG) grow(sh.seg, k.need_seg, in.seg);
+        if (k.overflow & CAP_GRP) grow(sh.grp, k.need_grp, in.grp);
+        if (k.overflow & CAP_AU) grow(sh.au, k.need_au, in.au);
+        if (k.overflow & CAP_CELLS) grow(sh.cells, k.need_cells, in.cells);
+        if (k.overflow & CAP_MAX_AU) sh.max_au = std::max(k.max_au, sh.max_au * 2);
+        if (k.overflow & CAP_SHAPE) {
+            // an input unlike the previous one: everything at least as the input's size bounds it
+            sh.rows = std::max(sh.rows, in.rows); sh.sync = std::max(sh.sync, in.sync); sh.seg = std::max(sh.seg, in.seg);
+            sh.grp = std::max(sh.grp, in.grp); sh.au = std::max(sh.au, in.au); sh.cells = std::max(sh.cells, in.cells);
+            sh.max_au = std::max(sh.max_au, in.max_au); sh.out_warps = std::max(sh.out_warps, (uint32_t)(8 * sh.grp));
+            sh.pcm_fixed = std::max(sh.pcm_fixed, in.pcm_fixed);
+            sh.any_pcm = sh.any_mlp = true; sh.nss = 2;
+        }
+        if (status & STATUS_PCM_SMALL) {
+            pcm_small_seen = true;
+            uint64_t want = 64;
+            for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].status == 0) want += ht[i].frames * ht[i].channels + 4;
+            sh.pcm_fixed = std::max<uint64_t>(sh.pcm_fixed, want);   // (on top of what the tiles bound)
         }
     }
 
-    // ---------------- output
-    uint64_t total_samples = 0;
-    bool any_pcm = false;
-    uint32_t mlp_channel_mask = 0;
-    for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].status == 0 && ht[i].codec == 1) mlp_channel_mask |= 1u << ht[i].channels;
+    // ---------------- results
+    total_samples = 0;
     for (uint32_t i = 0; i < n_tracks; i++) {
         total_samples = (total_samples + 3) & ~3ull;          // 16-byte aligned tracks (vector stores)
         if (ht[i].out_base != total_samples) { dvdagpu_set_error("internal: output layout"); return -1; }   // k_track_out_base
         if (ht[i].status == 0) total_samples += ht[i].frames * ht[i].channels;
-        any_pcm |= ht[i].status == 0 && ht[i].codec == 0;
     }
-    ENSURE(pcm_buf, (total_samples + 64) * sizeof(int32_t));
-    m.pcm = c->buf[pcm_buf].as<int32_t>();
     c->pcm_samples = total_samples;
-    if (status & STATUS_PCM_SMALL) {
-        // (does not happen as long as the tiles bound the samples; the buffer has its real size now)
-        CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, s));
-        out_queued = false;
-    }
-    if (nseg && m.fast && !out_queued) {
-        // fast path: filters (+ entropy decode) + rematrix + interleaved output in one pass
-        if (m.fast == 1) TIMED(DVDAGPU_K_MLP_FILTER_OUT, launch_mlp_filter_out(m, d_work, n_work, n_warps, s));
-        else TIMED(DVDAGPU_K_MLP_FUSED, launch_mlp_fused(m, d_fused, n_fused, n_fwarps, s));
-    }
-    if (nseg && max_chunks && (!m.fast || (status & STATUS_WANTS_REMATRIX))) TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, max_chunks, mlp_channel_mask, s));
-    if (any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, np, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));
-    CUDA_TRY(cudaEventRecord(c->ev[4], s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (g_trace_on) { trace_host("decode done"); trace_dump(); g_trace_on = false; }
-
-    // ---------------- results
+    c->last = k; c->last_shape = sh; c->last_sectors = n_sectors; c->last_tracks = n_tracks; c->have_last = true;
     uint64_t es_used = 0;
     for (uint32_t i = 0; i < n_tracks; i++) {
         const TrackDev &T = ht[i];
@@ -938,12 +849,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.decode_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.output_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); c->stats.total_ms = ms;
-    for (int k = 0; k < 16; k++) {
-        if (c->kev_used[k] && cudaEventElapsedTime(&ms, c->kev[k][0], c->kev[k][1]) == cudaSuccess) c->stats.kernel_ms[k] = ms;
+    for (int kk = 0; kk < 16; kk++) {
+        if (c->kev_used[kk] && cudaEventElapsedTime(&ms, c->kev[kk][0], c->kev[kk][1]) == cudaSuccess) c->stats.kernel_ms[kk] = ms;
     }
     c->stats.launches = g_launch_count;
-    c->stats.segments = nseg;
-    c->stats.access_units = nau;
+    c->stats.segments = k.nseg;
+    c->stats.access_units = k.nau;
     c->stats.es_bytes = es_used;
     c->stats.samples = total_samples;
     return 0;

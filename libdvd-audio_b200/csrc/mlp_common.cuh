@@ -409,19 +409,18 @@ __device__ __forceinline__ void filt8(const int32_t (&cf)[8], const int32_t (&ci
 }
 
 
-// Has the output of this segment been written by an output pass of the fast path (m.fast: 1 = three
-// passes with the fused filter + output pass for single-substream tracks, 2 = the fused entropy +
-// filter + output pass, which also takes two-substream tracks)?  What is left goes through the
-// tiles and k_rematrix.
-__device__ __forceinline__ bool track_fusable(const MlpTables &m, const TrackDev &T)
+// Does the output pass of the fast path take this track (one substream of up to four channels,
+// or the stereo pair + up to four more in a second substream)?  What it does not take — and the
+// segments the header passes gave up on — goes through the tiles and k_rematrix.
+__device__ __forceinline__ bool track_fusable(const TrackDev &T)
 {
     if (T.nss == 1) return T.channels >= 1 && T.channels <= 4;
-    return m.fast == 2 && T.nss == 2 && T.channels >= 3 && T.channels <= 6;    // stereo pair + up to four more
+    return T.nss == 2 && T.channels >= 3 && T.channels <= 6;
 }
 __device__ __forceinline__ bool seg_output_done(const MlpTables &m, const TrackDev &T, uint32_t seg)
 {
-    if (!m.fast || !track_fusable(m, T)) return false;
+    if (!m.fast || !track_fusable(T)) return false;
     uint32_t fl = m.ss_flags_fast[seg];
-    if (T.nss == 2) fl |= m.ss_flags_fast[m.nseg + seg];
+    if (T.nss == 2) fl |= m.ss_flags_fast[m.cap_seg + seg];
     return !(fl & SEG_FALLBACK);
 }

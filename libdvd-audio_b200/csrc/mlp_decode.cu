@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(CHK_THREADS) k_checkdata(MlpTables m, const ui
     uint8_t *const win = chk_sm + CHK_TAB_BYTES + (threadIdx.x >> 5) * CHK_WINDOW;
     const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win);
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool have = a < m.nau;
+    const bool have = a < m.cnt->nau;
     uint64_t pos = 0;
     uint32_t total = 0;
     if (have) {
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(CHKD_THREADS) k_checkdata_direct(MlpTables m, 
         crc = T[3][(crc ^ w_) & 0xFF] ^ T[2][(w_ >> 8) & 0xFF] ^ T[1][(w_ >> 16) & 0xFF] ^ T[0][w_ >> 24]; \
     }
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= m.nau) return;
-    const uint32_t si = upper_bound_dev(seg_au_base, m.nseg, a) - 1;
+    if (a >= m.cnt->nau) return;
+    const uint32_t si = upper_bound_dev(seg_au_base, m.cnt->nseg, a) - 1;
     const TrackDev &Tr = m.tracks[m.segs[si].track];
     const uint64_t pos = m.au_pos[a];
     const AuLayout L = au_layout(m.es, pos, Tr);
@@ -301,19 +301,19 @@ int upload_crc_table(const uint8_t *t)
 
 // access units of up to this many bytes on average go through the shared-memory windows
 #define CHK_WINDOWED_MAX_AU 512
-bool checkdata_windowed(const MlpTables &m) { return m.nau && m.es_total / m.nau <= CHK_WINDOWED_MAX_AU; }
-
-int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, cudaStream_t s)
+// windowed: access units of up to CHK_WINDOWED_MAX_AU bytes on average (the host decides from
+// what it knows of the stream: both kernels are right for any input)
+int launch_checkdata(MlpTables m, const uint32_t *seg_au_base, bool windowed, cudaStream_t s)
 {
-    if (!m.nau) return 0;
-    if (!checkdata_windowed(m)) {
-        LAUNCH(k_checkdata_direct, div_up_u32(m.nau, CHKD_THREADS), CHKD_THREADS, 0, s, m, seg_au_base);
+    if (!m.cap_au) return 0;
+    if (!windowed) {
+        LAUNCH(k_checkdata_direct, div_up_u32(m.cap_au, CHKD_THREADS), CHKD_THREADS, 0, s, m, seg_au_base);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
     static PerDeviceOnce attr_once;
     if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_checkdata, cudaFuncAttributeMaxDynamicSharedMemorySize, CHK_SMEM_BYTES)); return 0; })) return -1;
-    LAUNCH(k_checkdata, div_up_u32(m.nau, CHK_THREADS), CHK_THREADS, CHK_SMEM_BYTES, s, m, seg_au_base);
+    LAUNCH(k_checkdata, div_up_u32(m.cap_au, CHK_THREADS), CHK_THREADS, CHK_SMEM_BYTES, s, m, seg_au_base);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -906,7 +906,7 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
         if (au_pos + L.total > T.es_cut) { stop_au = a; break; }  // end of track, not an error
         if (e == 1) {                                             // dropped access unit
             if (governing) { AuDev R = {frames, 0, s.seed, pset}; m.au[A] = R; }
-            m.au_frames_ss[job.k * m.nau + A] = 0;
+            m.au_frames_ss[job.k * m.cap_au + A] = 0;
             continue;
         }
         if (e) { err |= e; stop_au = a; break; }
@@ -935,7 +935,7 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
         // a restart header inside the AU reloads the noise seed before the AU is
         // rematrixed (mlp.c:828, 504-512): take it after the blocks
         const uint32_t seed0 = s.seed;
-        m.au_frames_ss[job.k * m.nau + A] = nf;
+        m.au_frames_ss[job.k * m.cap_au + A] = nf;
         if (governing) {
             // parameters in force after the AU's last block govern the whole AU (mlp.c:504-525)
             if (s.dirty || pset == 0xFFFFFFFFu) {
@@ -965,12 +965,12 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
     }
     cp_wait<0>();
     if (abandon) {
-        m.ss_flags[job.k * m.nseg + job.seg] = SEG_NEEDS_CARRY;
+        m.ss_flags[job.k * m.cap_seg + job.seg] = SEG_NEEDS_CARRY;
         return;
     }
 
     // last 8 outputs per channel: slot 7 = most recent (what a circular buffer with fhead = 0 expects)
-    int32_t *tail = m.fir_tail + ((uint64_t)job.k * m.nseg + job.seg) * (DVDA_MAX_CH * 8);
+    int32_t *tail = m.fir_tail + ((uint64_t)job.k * m.cap_seg + job.seg) * (DVDA_MAX_CH * 8);
     if (s.have_header) {
         if (NCH > 0) {
 #pragma unroll
@@ -984,7 +984,7 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
             }
         }
     }
-    m.ss_flags[job.k * m.nseg + job.seg] = flags;
+    m.ss_flags[job.k * m.cap_seg + job.seg] = flags;
     if (job.k == 0) S.frames = frames;
     if (err) atomicOr(&S.err, err);
     if (stop_au != 0xFFFFFFFFu) atomicMin(&S.err_au, stop_au);
@@ -1216,7 +1216,7 @@ __device__ __forceinline__ void segctx_segment(const MlpTables &m, const DecodeJ
             cx.ok = rd_pos(b) <= end_bits;
         }
     }
-    m.seg_ctx[job.k * m.nseg + job.seg] = cx;
+    m.seg_ctx[job.k * m.cap_seg + job.seg] = cx;
 }
 
 // A1: parameter block of one access unit as a delta
@@ -1225,14 +1225,14 @@ __device__ __forceinline__ void parse_au(const MlpTables &m, const DecodeJob &jo
     const SegDev &S = m.segs[job.seg];
     const TrackDev &T = m.tracks[S.track];
     const uint32_t A = S.au_base + a;
-    AuSnap &sn = m.au_snap[(uint64_t)job.k * m.nau + A];
-    const SegCtx cx = m.seg_ctx[job.k * m.nseg + job.seg];
+    AuSnap &sn = m.au_snap[(uint64_t)job.k * m.cap_au + A];
+    const SegCtx cx = m.seg_ctx[job.k * m.cap_seg + job.seg];
     uint32_t state = 0;                                   // 0: not for the fast path, 1: no parameters, 2: delta written
     GRd b;
     uint32_t end_bits;
     uint64_t origin;
     if (cx.ok && au_seat(m, T, A, job.k, b, col, end_bits, origin)) {
-        AuDelta &D = m.au_delta[(uint64_t)job.k * m.nau + A];
+        AuDelta &D = m.au_delta[(uint64_t)job.k * m.cap_au + A];
         if (a == 0) {
             // "parameters present", "restart header", the header itself (checked by pass A0)
             rd_skip(b, 2 + 113 + 6 * (cx.mmc + 1u) + 8);
@@ -1259,10 +1259,10 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
     const TrackDev &T = m.tracks[S.track];
     const bool governing = job.k + 1 == T.nss;
     const uint32_t nominal = T.au_nominal;
-    const SegCtx cx = m.seg_ctx[job.k * m.nseg + job.seg];
-    AuSnap *snaps = m.au_snap + (uint64_t)job.k * m.nau;
-    const AuDelta *deltas = m.au_delta + (uint64_t)job.k * m.nau;
-    uint8_t *fchg = m.au_fchg + (uint64_t)job.k * m.nau;
+    const SegCtx cx = m.seg_ctx[job.k * m.cap_seg + job.seg];
+    AuSnap *snaps = m.au_snap + (uint64_t)job.k * m.cap_au;
+    const AuDelta *deltas = m.au_delta + (uint64_t)job.k * m.cap_au;
+    uint8_t *fchg = m.au_fchg + (uint64_t)job.k * m.cap_au;
 
     // running state: what the entropy decoder needs, per channel of the substream
     uint32_t block_size = 8, want = 0, q8 = 0;            // q8: quant_step_size of channels 0..7, a nibble each
@@ -1274,7 +1274,9 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
 #pragma unroll
     for (int cc = 0; cc < NCH; cc++) { offset[cc] = 0; cb[cc] = 0; lsbs[cc] = 24; fo[cc] = io[cc] = fs[cc] = is[cc] = 0; }
     uint32_t seed = cx.seed, frames = 0, flags = 0, pset = 0xFFFFFFFFu;
-    bool fallback = !cx.ok || (uint32_t)(cx.max_ch - cx.min_ch + 1) != NCH;
+    // (the channel layout the later passes count on: one substream from channel 0 on, or the stereo
+    // pair in substream 0 and the rest, from channel 2 on, in substream 1)
+    bool fallback = !cx.ok || (uint32_t)(cx.max_ch - cx.min_ch + 1) != NCH || cx.min_ch != (job.k ? 2u : 0u);
 
     uint32_t seed_at = 0;                                 // frame the seed belongs to (advanced only when some matrix uses noise)
     bool uses_noise = false;
@@ -1397,13 +1399,13 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
 
         const uint32_t au_frame0 = frames;
         frames += nominal;
-        m.au_frames_ss[job.k * m.nau + A] = nominal;
+        m.au_frames_ss[job.k * m.cap_au + A] = nominal;
         if (governing) {
             if (dirty || pset == 0xFFFFFFFFu) {
                 ParamSet P;
                 memset(&P, 0, sizeof P);
                 P.matrix_len = (uint8_t)matrix_len; P.mmc = cx.mmc; P.noise_shift = cx.noise_shift;
-                const AuDelta &M = m.au_delta[(uint64_t)job.k * m.nau + mat_src];
+                const AuDelta &M = m.au_delta[(uint64_t)job.k * m.cap_au + mat_src];
                 uint32_t uses = 0;
                 for (uint32_t k = 0; k < matrix_len; k++) {
                     P.out_ch[k] = M.mat_out[k];
@@ -1424,7 +1426,7 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
         }
     }
     if (fallback) flags |= SEG_FALLBACK;
-    m.ss_flags[job.k * m.nseg + job.seg] = flags;
+    m.ss_flags[job.k * m.cap_seg + job.seg] = flags;
     if (job.k == 0) S.frames = frames;
 }
 
@@ -1447,11 +1449,11 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
     const uint32_t nch = T.channels, nominal = T.au_nominal;
     const uint32_t A = S.au_base + a;
     // pass A gave up on the segment: its later snapshots were never written
-    if (m.ss_flags[job.k * m.nseg + job.seg] & SEG_FALLBACK) return;
-    const AuSnap sn = m.au_snap[(uint64_t)job.k * m.nau + A];
+    if (m.ss_flags[job.k * m.cap_seg + job.seg] & SEG_FALLBACK) return;
+    const AuSnap sn = m.au_snap[(uint64_t)job.k * m.cap_au + A];
     if (!sn.valid) return;
     const uint32_t frame0 = a * nominal;
-    if (frame0 + nominal > G.cap) { atomicOr(&m.ss_flags[job.k * m.nseg + job.seg], SEG_OVERFLOW | SEG_FALLBACK); return; }
+    if (frame0 + nominal > G.cap) { atomicOr(&m.ss_flags[job.k * m.cap_seg + job.seg], SEG_OVERFLOW | SEG_FALLBACK); return; }
 
     Rd b;
     rd_init(b, m.es, ring);
@@ -1542,185 +1544,125 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
 #undef DVDA_WIN_LOAD
 #undef DVDA_WIN_STORE
     cp_wait<0>();
-    if (!ok || done != nominal) atomicOr(&m.ss_flags[job.k * m.nseg + job.seg], SEG_FALLBACK);
+    if (!ok || done != nominal) atomicOr(&m.ss_flags[job.k * m.cap_seg + job.seg], SEG_FALLBACK);
 }
 
-// ---- pass C: prediction filters of one channel over a whole segment -------------------
-__device__ __forceinline__ void filter_channel_segment(const MlpTables &m, uint32_t seg, uint32_t k, uint32_t cc, uint32_t lane)
-{
-    const SegDev &S = m.segs[seg];
-    const TrackDev &T = m.tracks[S.track];
-    if (T.nss != 2) return;                      // single substream: filter_output_segment does it
-    if ((m.ss_flags[seg] | m.ss_flags[m.nseg + seg]) & SEG_FALLBACK) return;
-    const GroupDev &G = m.groups[T.grp_base + (seg - T.seg_base) / DVDA_LANES];
-    const uint32_t nch = T.channels, nominal = T.au_nominal, cap = G.cap;
-    const AuSnap *snaps = m.au_snap + (uint64_t)k * m.nau;
-    const AuDelta *deltas = m.au_delta + (uint64_t)k * m.nau;
-    if (!S.n_au) return;
-    const uint32_t c = snaps[S.au_base].min_ch + cc;
-    int32_t fh[8], ih[8], cf[8], ci[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { fh[j] = 0; ih[j] = 0; cf[j] = 0; ci[j] = 0; }
-    int32_t *tile = m.tiles + G.tile_off + lane + (uint64_t)c * DVDA_LANES;
-    const uint32_t tile_step = nch * DVDA_LANES;
-    uint32_t f = 0;
-    int32_t nx[8];
-    uint32_t shift = 0, q = 0;
-    FiltSetup F = {0, 0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 8; j++) nx[j] = ((uint32_t)j < cap) ? tile[(uint64_t)j * tile_step] : 0;
-    for (uint32_t a = 0; a < S.n_au; a++) {
-        if ((m.au_fchg[(uint64_t)k * m.nau + S.au_base + a] >> cc) & 1) {
-            filt_take_delta(deltas[S.au_base + a], cc, c, F, cf, ci, ih);
-            shift = filt_shift(F); q = F.q;
-        }
-        // the nominal AU length is a multiple of 8 (40 * rate multiple); the residuals of
-        // the next 8 frames are loaded while the current 8 are filtered
-        for (uint32_t i = 0; i < nominal; i += 8) {
-            int32_t r[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = nx[j];
-            const bool more = (i + 8 < nominal) || (a + 1 < S.n_au);
-#pragma unroll
-            for (int j = 0; j < 8; j++) nx[j] = (more && f + 8 + j < cap) ? tile[(uint64_t)(8 + j) * tile_step] : 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                long long s0 = 0, s1 = 0;
-#pragma unroll
-                for (int t = 7; t >= 0; t--) {          // oldest taps first: short dependent chain
-                    s0 = mad_wide(cf[t], fh[(t - j) & 7], s0);
-                    s1 = mad_wide(ci[t], ih[(t - j) & 7], s1);
-                }
-                const int32_t ssum = (int32_t)((s0 + s1) >> shift);
-                int32_t v = (int32_t)((uint32_t)ssum + (uint32_t)r[j]);
-                v = (v >> q) << q;
-                fh[(7 - j) & 7] = v;
-                ih[(7 - j) & 7] = (int32_t)((uint32_t)v - (uint32_t)ssum);
-                r[j] = v;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) if (f + j < cap) tile[(uint64_t)j * tile_step] = r[j];
-            f += 8;
-            tile += (uint64_t)8 * tile_step;
-        }
-    }
-    int32_t *tail = m.fir_tail + ((uint64_t)k * m.nseg + seg) * (DVDA_MAX_CH * 8);
-#pragma unroll
-    for (int j = 0; j < 8; j++) tail[c * 8 + j] = fh[7 - j];
-}
-
-// ---- pass C', single-substream tracks: filters + rematrix + interleaved output ---------
+// ---- pass C: prediction filters + rematrix + interleaved output, one or two substreams ------
 //
-// One lane per (segment, channel): a warp takes SPW = 32 / NCH segments of a
-// group, lane = segment-in-warp * NCH + channel, so the NCH recurrences of a
-// segment run in neighbouring lanes and all lanes step through the frames of
-// their segments together (access units have the nominal length here).
-// Residuals come from the tile; the next 8 frames are loaded while the current 8
-// are filtered (the tile carries 16 frames of slack, no bounds tests).  Per
-// access unit the warp picks the smallest compiled tap count that covers the
-// filter orders of all its lanes (0, 4 or 8 taps each for FIR and IIR).
-// Access units whose parameters ask for more than a copy (matrices, bypass bits,
-// output shift, permuted channel order) take the slow branch: the NCH lanes of
-// a segment exchange their samples by shuffle and each applies the matrices for
-// the whole frame, keeping its own channel.  Finished frames are parked in a
-// shared-memory patch [segment][32 frames][NCH] and written out row by row every
-// 32 frames: 32 * NCH consecutive ints per segment, coalesced.  Runs after the
-// frame counts are final (it writes straight into the PCM buffer).
+// One lane per (segment, channel).  A segment of a track with n0 channels in substream 0 and n1
+// in substream 1 (n1 = 0: one substream) takes n0 + n1 neighbouring lanes, a warp takes
+// 32 / (n0 + n1) segments of a group, and all lanes step through the frames of their segments
+// together (access units have the nominal length here).  Residuals come from the tile; the
+// next 8 frames are loaded while the current 8 are filtered (the tile carries 16 frames of
+// slack, no bounds tests).  Per access unit the warp picks the smallest compiled tap count that
+// covers the filter orders of all its lanes (0, 4 or 8 taps each for FIR and IIR).  Access
+// units whose parameters ask for more than a copy (matrices, bypass bits, output shift, permuted
+// channel order) take the slow branch: the lanes of a segment exchange their samples by shuffle
+// — channels of both substreams meet there; substream 1's matrices govern all of them
+// (mlp.c:575-595) — and each applies the matrices for the whole frame, keeping its own channel.
+// Finished frames are parked in a shared-memory patch [segment][32 frames][channels] and leave
+// row by row every 32 frames as bulk copies shared -> global.  Runs after the frame counts are
+// final (it writes straight into the PCM buffer).
 #define OUT_WARPS 4
 #ifndef OUT_MIN_BLOCKS
 #define OUT_MIN_BLOCKS 5
 #endif
+#define OUT_PF 32                                       // frames per patch
+#define OUT_PATCH_WORDS (OUT_PF * 32 + 4 * 32)          // most a patch needs: spw rows of OUT_PF * lanes-per-segment + 4 words
+#define OUT_WARP_WORDS (2 * OUT_PATCH_WORDS + 4 * 32)   // two patches, used in turn (bulk stores in flight) + per segment {output base lo, hi, frames, aligned}
+#define OUT_SMEM_BYTES (OUT_WARPS * OUT_WARP_WORDS * 4)
+#define OUT_MAX_LPS 8
 
-
-template <int NCH>
-__global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_out(MlpTables m, const DecWork *__restrict__ work,
-                                                                   uint32_t n_work, uint32_t n_warps)
+__global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_out(MlpTables m, const OutWork *__restrict__ work)
 {
     extern __shared__ int32_t out_sm[];
-    constexpr int SPW = 32 / NCH;                        // segments per warp
-    constexpr int SUB = (32 + SPW - 1) / SPW;            // warps per group
-    constexpr int ROW = 32 * NCH + 4;                    // one segment's 32 frames (+4: rows stay 16-byte aligned, banks spread)
-    constexpr int PATCH_WORDS = SPW * ROW;               // one patch; there are two, used in turn (bulk stores in flight)
-    constexpr int WARP_WORDS = 2 * PATCH_WORDS + SPW * 4; // + per segment {output base lo, hi, frames, 16-byte aligned?}
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * OUT_WARPS + wib;
-    if (warp >= n_warps * SUB) return;
+    if (warp >= m.cnt->nout_warps) return;
     // queued before the host has seen the batch's status: nothing to do if the batch is decoded
     // once more (tile overflow) or the output buffer sized in advance turned out too small
     if (*m.status & (SEG_OVERFLOW | STATUS_PCM_SMALL)) return;
-    int32_t *patch = out_sm + (size_t)wib * WARP_WORDS;
-    uint32_t *meta = reinterpret_cast<uint32_t *>(patch + 2 * PATCH_WORDS);
-    const uint32_t gw = warp / SUB, sub = warp % SUB;
-    // (group, substream) of this warp; only single-substream tracks are handled here
-    uint32_t lo = 0, hi = n_work;
+
+    // ---- which track, group, segment, substream, channel
+    uint32_t lo = 0, hi = m.cnt->nout_work;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (work[mid].warp0 <= gw) lo = mid; else hi = mid;
+        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
     }
-    const DecWork W = work[lo];
+    const OutWork W = work[lo];
     const TrackDev &T = m.tracks[W.track];
-    if (T.nss != 1) return;
-    const GroupDev &G = m.groups[T.grp_base + (gw - W.warp0)];
-    const uint32_t nominal = T.au_nominal;
-
-    // per lane: its segment and channel (or nothing)
-    const uint32_t sl = lane / NCH, cc = lane % NCH;
-    const uint32_t sg = sub * SPW + sl;                  // segment inside the group = column of the tile
-    const bool have = sl < SPW && sg < G.nseg;
+    const uint32_t n0 = W.n0, lps = W.n0 + W.n1;            // lanes per segment = channels of the track
+    const uint32_t spw = 32 / lps;                         // segments per warp
+    const uint32_t sub_n = (32 + spw - 1) / spw;           // warps per group
+    const uint32_t rel = warp - W.warp0;
+    const GroupDev &G = m.groups[T.grp_base + rel / sub_n];
+    const uint32_t sub = rel % sub_n;
+    const uint32_t sl = lane / lps, j = lane - sl * lps;   // segment in the warp, channel of the track
+    const uint32_t k = j >= n0 ? 1u : 0u;                  // substream
+    const uint32_t cc = k ? j - n0 : j;                    // channel inside the substream
+    const uint32_t sg = sub * spw + sl;                    // segment inside the group = column of the tile
+    const bool have = sl < spw && sg < G.nseg;
     const uint32_t seg = G.seg0 + (have ? sg : 0);
     const SegDev &S = m.segs[seg];
-    const bool mine = have && !(m.ss_flags_fast[seg] & SEG_FALLBACK) && S.frames > 0;
+    uint32_t seg_flags = m.ss_flags_fast[seg];
+    if (W.n1) seg_flags |= m.ss_flags_fast[m.cap_seg + seg];
+    const bool mine = have && !(seg_flags & SEG_FALLBACK) && S.frames > 0;
     const uint32_t my_frames = mine ? S.frames : 0;
     const uint32_t max_frames = __reduce_max_sync(0xFFFFFFFFu, my_frames);
     if (!max_frames) return;
-    if (cc == 0 && sl < SPW) {
-        const uint64_t base = (mine ? S.frame0 : 0) * NCH;
+    const uint32_t nominal = T.au_nominal;
+
+    const uint32_t row_words = OUT_PF * lps + 4;           // a segment's row in a patch (+4: rows stay 16-byte aligned, banks spread)
+    int32_t *patch = out_sm + (size_t)wib * OUT_WARP_WORDS;
+    uint32_t *meta = reinterpret_cast<uint32_t *>(patch + 2 * OUT_PATCH_WORDS);
+    if (j == 0 && sl < spw) {
+        const uint64_t base = (mine ? S.frame0 : 0) * lps;
         meta[sl * 4 + 0] = (uint32_t)base; meta[sl * 4 + 1] = (uint32_t)(base >> 32); meta[sl * 4 + 2] = my_frames;
-        meta[sl * 4 + 3] = ((T.out_base + base) & 3) == 0;       // the rows of this segment start on 16-byte boundaries
+        meta[sl * 4 + 3] = ((T.out_base + base) & 3) == 0;        // the rows of this segment start on 16-byte boundaries
     }
     __syncwarp();
 
-    const AuDelta *deltas = m.au_delta;
+    const AuDelta *deltas = m.au_delta + (uint64_t)k * m.cap_au;
+    const uint8_t *fchg = m.au_fchg + (uint64_t)k * m.cap_au;
     FiltSetup F = {0, 0, 0, 0, 0};
-    const uint32_t c0 = mine ? m.au_snap[S.au_base].min_ch : 0;  // 0 for a single substream
     int32_t fh[8], ih[8], cf[8], ci[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { fh[j] = 0; ih[j] = 0; cf[j] = 0; ci[j] = 0; }
+    for (int t = 0; t < 8; t++) { fh[t] = 0; ih[t] = 0; cf[t] = 0; ci[t] = 0; }
     uint32_t shift = 0, qmask = 0xFFFFFFFFu;
-    constexpr uint32_t tile_step = NCH * DVDA_LANES;             // single substream: nch == NCH
-    const int32_t *tp = m.tiles + G.tile_off + (have ? sg : 0) + (uint64_t)(c0 + cc) * DVDA_LANES;
+    const uint32_t tile_step = lps * DVDA_LANES;
+    const int32_t *tp = m.tiles + G.tile_off + (have ? sg : 0) + (uint64_t)j * DVDA_LANES;
     const uint8_t *byp = m.bypass + G.byp_off + (have ? sg : 0);
     int32_t *const pcm_row = m.pcm + T.out_base;
     const bool plain_order = !(T.assignment >= 0x12 && T.assignment <= 0x14);
-    const uint32_t out_slot = wave_slot(T.assignment, cc);
-    const uint32_t group_lane0 = sl * NCH;                       // first lane of this segment's channels
-    int32_t *const park = patch + (sl < SPW ? sl : 0) * ROW + out_slot;
+    const uint32_t out_slot = wave_slot(T.assignment, j);
+    const uint32_t group_lane0 = sl * lps;                       // first lane of this segment's channels
+    int32_t *const park = patch + (sl < spw ? sl : 0) * row_words + out_slot;
 
     uint32_t seed = 0, pset = 0xFFFFFFFFu, f = 0, a = 0, cls = 0;
     const ParamSet *P = nullptr;
     bool trivial = true;
     int32_t nx[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) nx[j] = tp[j * tile_step];
+    for (int t = 0; t < 8; t++) nx[t] = tp[t * tile_step];
     tp += 8 * tile_step;
 
-    // The patch of 32 frames leaves row by row (a row = 32 frames of a segment = 128 * NCH
-    // contiguous bytes of the output).  Whole, 16-byte aligned rows go out as bulk copies
-    // shared -> global, one instruction per row issued by the row's lane; the copy engine reads
-    // the patch while the warp fills the other one.  Ragged ends take plain stores.
+    // The patch of 32 frames leaves row by row (a row = 32 frames of a segment, contiguous in the
+    // output).  Whole, 16-byte aligned rows go out as bulk copies shared -> global, one instruction
+    // per row issued by the row's lane; the copy engine reads the patch while the warp fills the
+    // other one.  Ragged ends take plain stores.
     auto flush = [&](uint32_t f0) {
-        const int32_t *pb = patch + ((f0 >> 5) & 1) * PATCH_WORDS;
+        const int32_t *pb = patch + ((f0 / OUT_PF) & 1) * OUT_PATCH_WORDS;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the parked samples, for the async proxy
         __syncwarp();
         uint32_t slow = 0;
-        if (lane < (uint32_t)SPW) {
+        if (lane < spw) {
             const uint4 mt = *reinterpret_cast<const uint4 *>(meta + lane * 4);     // base lo, hi, frames, aligned
             if (f0 < mt.z) {
-                if (f0 + 32 <= mt.z && mt.w) {
-                    int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * NCH);
-                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(pb + lane * ROW);
+                if (f0 + OUT_PF <= mt.z && mt.w) {
+                    int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * lps);
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(pb + lane * row_words);
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(dst), "r"(src), "n"(128 * NCH) : "memory");
+                                 :: "l"(dst), "r"(src), "r"(OUT_PF * 4 * lps) : "memory");
                 } else slow = 1;
             }
         }
@@ -1730,9 +1672,9 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
             const uint32_t row = __ffs(rows) - 1;
             rows &= rows - 1;
             const uint4 mt = *reinterpret_cast<const uint4 *>(meta + row * 4);
-            const uint32_t n = min(32u, mt.z - f0) * NCH;
-            int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * NCH);
-            for (uint32_t i = lane; i < n; i += 32) dst[i] = pb[row * ROW + i];
+            const uint32_t n = min((uint32_t)OUT_PF, mt.z - f0) * lps;
+            int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * lps);
+            for (uint32_t i = lane; i < n; i += 32) dst[i] = pb[row * row_words + i];
         }
         // the patch written one flush ago has been read by now: it is the one filled next
         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -1743,13 +1685,25 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
     // waits for at the top of an access unit is one round of four independent 16-byte loads
     // (prefetched into L1), not a chain of dependent ones
     const uint32_t au_base = mine ? S.au_base : 0;       // (a register: S lives in global memory)
-    DeltaHead H = filt_load_head(m, deltas, au_base, cc, c0 + cc);
+    auto load_head = [&](uint32_t A) {
+        DeltaHead H;
+        const AuDelta &D = deltas[A];
+        H.fchg = fchg[A];
+        H.w0 = *reinterpret_cast<const uint32_t *>(&D);                  // block_size, present, matrix_len
+        H.qv = D.q[j];
+        const uint32_t *hw = reinterpret_cast<const uint32_t *>(&D.ch[cc]);
+        H.h1 = hw[1]; H.h2 = hw[2];
+        const uint2 sp = *reinterpret_cast<const uint2 *>(&m.au[A].seed);
+        H.seed = sp.x; H.pset = sp.y;
+        return H;
+    };
+    DeltaHead H = load_head(au_base);
     while (f < max_frames) {
         // ---- next access unit: this channel's filter parameters, the frame's rematrix parameters
         const bool au_act = f < my_frames;
         if (au_act) {
             const uint32_t A = au_base + a;
-            const uint32_t An = min(A + 1, m.nau);           // (the tables have one spare entry)
+            const uint32_t An = min(A + 1, m.cap_au);        // (the tables have one spare entry)
             prefetch_l1(&deltas[An].cf[cc]);
             prefetch_l1(reinterpret_cast<const uint8_t *>(&deltas[An].cf[cc]) + 32);
             if ((H.fchg >> cc) & 1) {
@@ -1763,11 +1717,11 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
                 P = &m.psets[pset & 0x7FFFFFFFu];
                 trivial = (pset & 0x80000000u) && plain_order;
             }
-            H = filt_load_head(m, deltas, An, cc, c0 + cc);
+            H = load_head(An);
         } else {
             cls = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) { cf[j] = 0; ci[j] = 0; }
+            for (int t = 0; t < 8; t++) { cf[t] = 0; ci[t] = 0; }
         }
         a++;
         const uint32_t nf = __reduce_max_sync(0xFFFFFFFFu, ((cls & 15) + 3) >> 2);
@@ -1778,9 +1732,9 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
         for (uint32_t i = 0; i < nominal; i += 8) {
             int32_t r[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = nx[j];
+            for (int t = 0; t < 8; t++) r[t] = nx[t];
 #pragma unroll
-            for (int j = 0; j < 8; j++) nx[j] = tp[j * tile_step];
+            for (int t = 0; t < 8; t++) nx[t] = tp[t * tile_step];
             tp += 8 * tile_step;
             switch (code) {
             case 0: filt8<0, 0>(cf, ci, fh, ih, r, shift, qmask); break;
@@ -1797,73 +1751,62 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
                 // the shuffles need the whole warp: lanes without work just run along
                 const uint32_t fa = f < my_frames ? f : 0;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    int32_t v[NCH];
+                for (int t = 0; t < 8; t++) {
+                    int32_t v[OUT_MAX_LPS];
 #pragma unroll
-                    for (int c = 0; c < NCH; c++) v[c] = __shfl_sync(0xFFFFFFFFu, r[j], group_lane0 + c);
+                    for (int c = 0; c < OUT_MAX_LPS; c++) v[c] = __shfl_sync(0xFFFFFFFFu, r[t], group_lane0 + c);
                     if (au_act && !trivial) {
                         // noise, matrices in order, bypass bit, output shift (mlp.c:504-538, 1308-1358)
-                        const uint32_t bm = byp[(uint64_t)(fa + j) * DVDA_LANES];
+                        const uint32_t bm = byp[(uint64_t)(fa + t) * DVDA_LANES];
                         const uint32_t sh = (seed >> 7) & 0xFFFF;
-                        const int32_t n0 = (int32_t)((uint32_t)(int32_t)(int8_t)(seed >> 15) << P->noise_shift);
-                        const int32_t n1 = (int32_t)((uint32_t)(int32_t)(int8_t)sh << P->noise_shift);
+                        const int32_t z0 = (int32_t)((uint32_t)(int32_t)(int8_t)(seed >> 15) << P->noise_shift);
+                        const int32_t z1 = (int32_t)((uint32_t)(int32_t)(int8_t)sh << P->noise_shift);
                         const uint32_t ml = P->matrix_len, mmc = P->mmc;
-                        for (uint32_t k = 0; k < ml; k++) {
+                        for (uint32_t mk = 0; mk < ml; mk++) {
                             long long sum = 0;
 #pragma unroll
-                            for (int c = 0; c < NCH; c++) sum += (long long)v[c] * P->coeff[k][c];
-                            sum += (long long)n0 * P->coeff[k][mmc + 1];
-                            sum += (long long)n1 * P->coeff[k][mmc + 2];
-                            const uint32_t oc = P->out_ch[k], qq = P->q[oc];
-                            const int32_t rr = (((int32_t)(sum >> 14)) >> qq << qq) + (int32_t)((bm >> k) & 1);
+                            for (int c = 0; c < OUT_MAX_LPS; c++) if ((uint32_t)c <= mmc && (uint32_t)c < lps) sum += (long long)v[c] * P->coeff[mk][c];
+                            sum += (long long)z0 * P->coeff[mk][mmc + 1];
+                            sum += (long long)z1 * P->coeff[mk][mmc + 2];
+                            const uint32_t oc = P->out_ch[mk], qq = P->q[oc];
+                            const int32_t rr = (((int32_t)(sum >> 14)) >> qq << qq) + (int32_t)((bm >> mk) & 1);
 #pragma unroll
-                            for (int c = 0; c < NCH; c++) if ((uint32_t)c == oc) v[c] = rr;
+                            for (int c = 0; c < OUT_MAX_LPS; c++) if ((uint32_t)c == oc) v[c] = rr;
                         }
                         int32_t mineval = 0;
 #pragma unroll
-                        for (int c = 0; c < NCH; c++) if ((uint32_t)c == cc) mineval = v[c];
-                        r[j] = (int32_t)((uint32_t)mineval << P->out_shift[cc]);
+                        for (int c = 0; c < OUT_MAX_LPS; c++) if ((uint32_t)c == j) mineval = v[c];
+                        r[t] = j <= mmc ? (int32_t)((uint32_t)mineval << P->out_shift[j]) : mineval;
                     }
                     seed = noise_step(seed);
                 }
             }
             if (au_act) {
-                int32_t *pk = park + ((f >> 5) & 1) * PATCH_WORDS + (f & 31) * NCH;
+                int32_t *pk = park + ((f / OUT_PF) & 1) * OUT_PATCH_WORDS + (f & (OUT_PF - 1)) * lps;
 #pragma unroll
-                for (int j = 0; j < 8; j++) pk[j * NCH] = r[j];
+                for (int t = 0; t < 8; t++) pk[t * lps] = r[t];
             }
             f += 8;
-            if ((f & 31) == 0) flush(f - 32);
+            if ((f & (OUT_PF - 1)) == 0) flush(f - OUT_PF);
         }
     }
-    if (f & 31) flush(f & ~31u);
+    if (f & (OUT_PF - 1)) flush(f & ~(uint32_t)(OUT_PF - 1));
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory is given back at exit
     // FIR tail for a following segment that needs it
     if (mine) {
-        int32_t *tail = m.fir_tail + (uint64_t)seg * (DVDA_MAX_CH * 8);
+        int32_t *tail = m.fir_tail + ((uint64_t)k * m.cap_seg + seg) * (DVDA_MAX_CH * 8);
 #pragma unroll
-        for (int j = 0; j < 8; j++) tail[(c0 + cc) * 8 + j] = fh[7 - j];
+        for (int t = 0; t < 8; t++) tail[j * 8 + t] = fh[7 - t];
     }
 }
 
-template <int NCH>
-static int launch_one_filter_out(MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
+// cap_warps: warps the grid covers (the work list and its length are on the device)
+int launch_mlp_filter_out(MlpTables m, const OutWork *work, uint32_t cap_warps, cudaStream_t s)
 {
-    if (!n_warps) return 0;
-    constexpr int SPW = 32 / NCH, SUB = (32 + SPW - 1) / SPW;
-    const size_t smem = (size_t)OUT_WARPS * SPW * (2 * (32 * NCH + 4) + 4) * sizeof(int32_t);
+    if (!cap_warps) return 0;
     static PerDeviceOnce attr_once;
-    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); return 0; })) return -1;
-    LAUNCH(k_mlp_filter_out<NCH>, div_up_u32((uint64_t)n_warps * SUB, OUT_WARPS), OUT_WARPS * 32, smem, s, m, work, n_work, n_warps);
-    return 0;
-}
-
-int launch_mlp_filter_out(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s)
-{
-    if (launch_one_filter_out<1>(m, work[1], n_work[1], n_warps[1], s)) return -1;
-    if (launch_one_filter_out<2>(m, work[2], n_work[2], n_warps[2], s)) return -1;
-    if (launch_one_filter_out<3>(m, work[3], n_work[3], n_warps[3], s)) return -1;
-    if (launch_one_filter_out<4>(m, work[4], n_work[4], n_warps[4], s)) return -1;
+    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_mlp_filter_out, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OUT_SMEM_BYTES)); return 0; })) return -1;
+    LAUNCH(k_mlp_filter_out, div_up_u32(cap_warps, OUT_WARPS), OUT_WARPS * 32, OUT_SMEM_BYTES, s, m, work);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1874,14 +1817,36 @@ int launch_mlp_filter_out(MlpTables m, const DecWork *const work[5], const uint3
 #endif
 #define DEC_SMEM_BYTES (DEC_WARPS * RING_SLOTS * DVDA_LANES * 16 + 4 * 512 * 2)
 
-// One warp per (group, substream); lane = segment of the group.  One
-// instantiation per channel count (NCH = 0: generic, more than 4 channels), so
-// that the common stereo case is not compiled with the register budget of the
-// 4-channel one.  Each instantiation gets a dense list of exactly its warps
-// (DecWork rows: a run of warps = the groups of one track's substream).
-template <int NCH>
-__global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_BLOCKS) k_mlp_decode(MlpTables m, const DecWork *__restrict__ work,
-                                                               uint32_t n_work, uint32_t n_warps)
+// One warp per (group, substream) — a row of the work list covers the groups of one track's
+// substream; lane = segment of the group.  The kernels below look their warp up in the list (its
+// length and the number of warps are on the device: the grids cover what the tables have room for)
+// and dispatch on the substream's channel count: the per-channel-count code is compiled once per
+// count (NCH = 0: generic, more than 4 channels), so that the common stereo case does not run with
+// the unrolling of the 4-channel one.
+__device__ __forceinline__ bool pair_job(const MlpTables &m, const DecWork *work, uint32_t warp, uint32_t lane,
+                                         DecodeJob &job, uint32_t &nch)
+{
+    if (warp >= m.cnt->npairs) return false;
+    uint32_t lo = 0, hi = m.cnt->nwork;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
+    }
+    const DecWork W = work[lo];
+    const TrackDev &T = m.tracks[W.track];
+    const GroupDev &G = m.groups[T.grp_base + (warp - W.warp0)];
+    nch = W.nch;
+    if (lane >= G.nseg) return false;
+    job.seg = G.seg0 + lane;
+    job.k = W.k;
+    job.lane = lane;
+    // a track starts with empty histories; a continued part does not
+    job.exact_history = (job.seg == T.seg_base) && !(T.cont & TRACK_CONT_PREV);
+    return true;
+}
+
+// the complete decoder: everything (without the fast path), or what the fast path gave up on
+__global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_BLOCKS) k_mlp_decode(MlpTables m, const DecWork *__restrict__ work)
 {
     extern __shared__ uint4 dyn_smem[];
     if (m.fast && !*m.any_fallback) return;              // the fast path kept every segment
@@ -1889,81 +1854,60 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_BLOCKS) k_mlp_decode(M
     uint16_t (*lut)[512] = reinterpret_cast<uint16_t (*)[512]>(dyn_smem + DEC_WARPS * RING_SLOTS * DVDA_LANES);
     huff_lut_to_shared(lut);
     __syncthreads();
-    const uint32_t wib = threadIdx.x >> 5;
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * DEC_WARPS + wib;
-    const uint32_t lane = threadIdx.x & 31;
-    if (warp >= n_warps) return;
-    // last work row whose first warp is <= warp
-    uint32_t lo = 0, hi = n_work;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
-    }
-    const DecWork W = work[lo];
-    const TrackDev &T = m.tracks[W.track];
-    const GroupDev &G = m.groups[T.grp_base + (warp - W.warp0)];
-    if (lane >= G.nseg) return;
     DecodeJob job;
-    job.seg = G.seg0 + lane;
-    job.k = W.k;
-    job.lane = lane;
-    // a track starts with empty histories; a continued part does not
-    job.exact_history = (job.seg == T.seg_base) && !(T.cont & TRACK_CONT_PREV);
+    uint32_t nch;
+    if (!pair_job(m, work, warp, lane, job, nch)) return;
     if (m.fast) {
-        // after the three-pass fast path: only what it gave up on (any substream of the segment)
-        const uint32_t f = m.ss_flags_prev[job.seg] | (T.nss == 2 ? m.ss_flags_prev[m.nseg + job.seg] : 0);
+        // after the fast path: only what it gave up on (any substream of the segment)
+        const TrackDev &T = m.tracks[m.segs[job.seg].track];
+        const uint32_t f = m.ss_flags_prev[job.seg] | (T.nss == 2 ? m.ss_flags_prev[m.cap_seg + job.seg] : 0);
         if (!(f & SEG_FALLBACK)) return;
     }
     const uint32_t rs = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]);
-    decode_segment<NCH>(m, job, lut, rs, nullptr);
+    switch (nch) {
+    case 1: decode_segment<1>(m, job, lut, rs, nullptr); break;
+    case 2: decode_segment<2>(m, job, lut, rs, nullptr); break;
+    case 3: decode_segment<3>(m, job, lut, rs, nullptr); break;
+    case 4: decode_segment<4>(m, job, lut, rs, nullptr); break;
+    default: decode_segment<0>(m, job, lut, rs, nullptr); break;
+    }
 }
 
 // ---- fast path kernels ------------------------------------------------------------
 
-__device__ __forceinline__ bool fast_job(const MlpTables &m, const DecWork *work, uint32_t n_work, uint32_t warp,
-                                         uint32_t lane, DecodeJob &job)
-{
-    uint32_t lo = 0, hi = n_work;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
-    }
-    const DecWork W = work[lo];
-    const TrackDev &T = m.tracks[W.track];
-    const GroupDev &G = m.groups[T.grp_base + (warp - W.warp0)];
-    if (lane >= G.nseg) return false;
-    job.seg = G.seg0 + lane;
-    job.k = W.k;
-    job.lane = lane;
-    job.exact_history = (job.seg == T.seg_base) && !(T.cont & TRACK_CONT_PREV);
-    return true;
-}
-
-// pass A0 / A2: one warp per (group, substream), lane = segment
-__global__ void __launch_bounds__(GRD_THREADS) k_mlp_segctx(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
+// pass A0: one warp per (group, substream), lane = segment
+__global__ void __launch_bounds__(GRD_THREADS) k_mlp_segctx(MlpTables m, const DecWork *__restrict__ work)
 {
     __shared__ uint32_t window[GRD_WIN_WORDS * GRD_THREADS];
     const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (warp >= n_warps) return;
     DecodeJob job;
-    if (!fast_job(m, work, n_work, warp, lane, job)) return;
+    uint32_t nch;
+    if (!pair_job(m, work, warp, lane, job, nch) || nch < 1 || nch > 4) return;
     segctx_segment(m, job, window + threadIdx.x);
 }
-template <int NCH>
-__global__ void __launch_bounds__(128) k_mlp_resolve(MlpTables m, const DecWork *__restrict__ work, uint32_t n_work, uint32_t n_warps)
+// pass A2
+__global__ void __launch_bounds__(128) k_mlp_resolve(MlpTables m, const DecWork *__restrict__ work)
 {
     const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (warp >= n_warps) return;
     DecodeJob job;
-    if (!fast_job(m, work, n_work, warp, lane, job)) return;
-    resolve_segment<NCH>(m, job);
+    uint32_t nch;
+    if (!pair_job(m, work, warp, lane, job, nch)) return;
+    switch (nch) {
+    case 1: resolve_segment<1>(m, job); break;
+    case 2: resolve_segment<2>(m, job); break;
+    case 3: resolve_segment<3>(m, job); break;
+    case 4: resolve_segment<4>(m, job); break;
+    default: break;                                     // more than four channels: the complete decoder's
+    }
 }
 // pass A1: one thread per (access unit, substream), consecutive threads = consecutive access units
 __global__ void __launch_bounds__(GRD_THREADS) k_mlp_au_parse(MlpTables m)
 {
     __shared__ uint32_t window[GRD_WIN_WORDS * GRD_THREADS];
     const uint32_t A = blockIdx.x * GRD_THREADS + threadIdx.x, k = blockIdx.y;
-    if (A >= m.nau) return;
+    if (A >= m.cnt->nau) return;
     DecodeJob job;
     job.seg = m.au_seg[A];
     job.k = k;
@@ -1975,95 +1919,60 @@ __global__ void __launch_bounds__(GRD_THREADS) k_mlp_au_parse(MlpTables m)
 }
 
 // pass B: one warp per (group, substream, access unit index), lane = segment
-template <int NCH>
-__global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_entropy(MlpTables m, const DecWork *__restrict__ work,
-                                                                uint32_t n_work, uint32_t n_warps)
+__global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_entropy(MlpTables m, const DecWork *__restrict__ work)
 {
     extern __shared__ uint4 dyn_smem[];
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp0 = blockIdx.x * DEC_WARPS;
+    const uint32_t a = blockIdx.y;
+    if (warp0 >= m.cnt->npairs || a >= m.cnt->max_au) return;            // (before the table is copied: most blocks of an oversized grid)
     uint4 (*ring)[RING_SLOTS][DVDA_LANES] = reinterpret_cast<uint4 (*)[RING_SLOTS][DVDA_LANES]>(dyn_smem);
     uint16_t (*lut)[512] = reinterpret_cast<uint16_t (*)[512]>(dyn_smem + DEC_WARPS * RING_SLOTS * DVDA_LANES);
     huff_lut_to_shared(lut);
     __syncthreads();
-    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t warp = blockIdx.x * DEC_WARPS + wib;
-    const uint32_t a = blockIdx.y;
-    if (warp >= n_warps) return;
     DecodeJob job;
-    if (!fast_job(m, work, n_work, warp, lane, job)) return;
+    uint32_t nch;
+    if (!pair_job(m, work, warp0 + wib, lane, job, nch)) return;
     if (a >= m.segs[job.seg].n_au) return;
-    entropy_au<NCH>(m, job, a, lut, (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]));
-}
-
-// pass C: one warp per (group, substream, channel of the substream), lane = segment
-template <int NCH>
-__global__ void __launch_bounds__(128) k_mlp_filter(MlpTables m, const DecWork *__restrict__ work,
-                                                    uint32_t n_work, uint32_t n_warps)
-{
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t w = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (w >= n_warps * NCH) return;
-    DecodeJob job;
-    if (!fast_job(m, work, n_work, w / NCH, lane, job)) return;
-    filter_channel_segment(m, job.seg, job.k, w % NCH, lane);
+    const uint32_t rs = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]);
+    switch (nch) {
+    case 1: entropy_au<1>(m, job, a, lut, rs); break;
+    case 2: entropy_au<2>(m, job, a, lut, rs); break;
+    case 3: entropy_au<3>(m, job, a, lut, rs); break;
+    case 4: entropy_au<4>(m, job, a, lut, rs); break;
+    default: break;
+    }
 }
 
 // A segment that needs its predecessor's FIR history is decoded by the complete decoder
 // (+ k_carry_fix), which reads the predecessor's stored tail: have the complete decoder
-// produce that one too (the fused output pass would store it too late).
+// produce that one too (the output pass would store it too late).
 __global__ void k_flag_predecessors(MlpTables m)
 {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t seg = idx >> 1, k = idx & 1;
-    if (seg >= m.nseg) return;
-    const uint32_t fl = m.ss_flags[k * m.nseg + seg];
+    if (seg >= m.cnt->nseg) return;
+    const uint32_t fl = m.ss_flags[k * m.cap_seg + seg];
     const TrackDev &T = m.tracks[m.segs[seg].track];
     // (does the complete decoder have anything to do?  It and the carry fix leave at once if not.)
     if (k < T.nss && (fl & (SEG_FALLBACK | SEG_WANTS_PREV))) *m.any_fallback = 1;
     if (!(fl & SEG_WANTS_PREV)) return;
-    if (seg > T.seg_base) atomicOr(&m.ss_flags[k * m.nseg + seg - 1], SEG_FALLBACK);
+    if (seg > T.seg_base) atomicOr(&m.ss_flags[k * m.cap_seg + seg - 1], SEG_FALLBACK);
 }
 
 __global__ void k_flag_damaged(MlpTables m)
 {
     const uint32_t A = blockIdx.x * blockDim.x + threadIdx.x;
-    if (A >= m.nau || !m.au_err[A]) return;
+    if (A >= m.cnt->nau || !m.au_err[A]) return;
     const uint32_t seg = m.au_seg[A];
     atomicOr(&m.ss_flags[seg], SEG_FALLBACK);
-    atomicOr(&m.ss_flags[m.nseg + seg], SEG_FALLBACK);
+    atomicOr(&m.ss_flags[m.cap_seg + seg], SEG_FALLBACK);
     *m.any_fallback = 1;
 }
 
 size_t au_snap_bytes() { return sizeof(AuSnap); }
 size_t seg_ctx_bytes() { return sizeof(SegCtx); }
 size_t au_delta_bytes() { return sizeof(AuDelta); }
-
-template <int NCH>
-static int launch_fast_pass(int pass, MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
-{
-    if (!n_warps) return 0;
-    static PerDeviceOnce attr_once;
-    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_mlp_entropy<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES)); return 0; })) return -1;
-    const uint32_t blocks = div_up_u32(n_warps, DEC_WARPS);
-    const uint32_t small = div_up_u32(n_warps, 4);
-    if (pass == 0) LAUNCH(k_mlp_segctx, small, 128, 0, s, m, work, n_work, n_warps);
-    else if (pass == 1) return 0;                       // one launch for all classes, see launch_mlp_fast
-    else if (pass == 2) LAUNCH(k_mlp_resolve<NCH>, small, 128, 0, s, m, work, n_work, n_warps);
-    else if (pass == 3) LAUNCH(k_mlp_entropy<NCH>, dim3(blocks, m.max_au ? m.max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
-    else if (m.nss_max < 2) return 0;                   // only tracks with two substreams are filtered by this pass
-    else LAUNCH(k_mlp_filter<NCH>, div_up_u32((uint64_t)n_warps * NCH, 4), 128, 0, s, m, work, n_work, n_warps);
-    return 0;
-}
-
-// what the fused pass gave up on in an earlier attempt of this decode stays flagged
-__global__ void k_flag_sticky(MlpTables m)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * m.nseg) return;
-    const uint32_t st = m.ss_sticky[i];
-    if (!st) return;
-    m.ss_flags[i] |= st;
-    *m.any_fallback = 1;
-}
 
 const uint16_t *huff_lut_device()
 {
@@ -2072,52 +1981,44 @@ const uint16_t *huff_lut_device()
     return reinterpret_cast<const uint16_t *>(p);
 }
 
-int launch_mlp_fast(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5],
-                    cudaEvent_t (*kev)[2], bool *kev_used, cudaEvent_t checked, bool headers_only, cudaStream_t s)
+// The fast path up to the tiles: header passes A0 .. A2, entropy pass B, then the flags that hand
+// segments to the complete decoder.  cap_pairs: (group, substream) pairs the grids cover;
+// lim_max_au: access units per segment the entropy grid covers; lim_nss: substreams the parse grid covers.
+int launch_mlp_fast(MlpTables m, const DecWork *work, uint32_t cap_pairs, uint32_t lim_max_au, uint32_t lim_nss,
+                    cudaEvent_t (*kev)[2], bool *kev_used, cudaEvent_t checked, cudaStream_t s)
 {
-    static const int slot[5] = {DVDAGPU_K_MLP_SEGCTX, DVDAGPU_K_MLP_AU_PARSE, DVDAGPU_K_MLP_RESOLVE, DVDAGPU_K_MLP_ENTROPY,
-                                DVDAGPU_K_MLP_FILTER};
-    for (int pass = 0; pass < (headers_only ? 3 : 5); pass++) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_mlp_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES)); return 0; })) return -1;
+    static const int slot[4] = {DVDAGPU_K_MLP_SEGCTX, DVDAGPU_K_MLP_AU_PARSE, DVDAGPU_K_MLP_RESOLVE, DVDAGPU_K_MLP_ENTROPY};
+    const uint32_t small = div_up_u32(cap_pairs, 4);
+    for (int pass = 0; pass < 4 && cap_pairs; pass++) {
         CUDA_TRY(cudaEventRecord(kev[slot[pass]][0], s));
-        if (pass == 1 && m.nau) LAUNCH(k_mlp_au_parse, dim3(div_up_u32(m.nau, GRD_THREADS), m.nss_max), GRD_THREADS, 0, s, m);
-        if (launch_fast_pass<1>(pass, m, work[1], n_work[1], n_warps[1], s)) return -1;
-        if (launch_fast_pass<2>(pass, m, work[2], n_work[2], n_warps[2], s)) return -1;
-        if (launch_fast_pass<3>(pass, m, work[3], n_work[3], n_warps[3], s)) return -1;
-        if (launch_fast_pass<4>(pass, m, work[4], n_work[4], n_warps[4], s)) return -1;
+        if (pass == 0) LAUNCH(k_mlp_segctx, small, 128, 0, s, m, work);
+        else if (pass == 1) LAUNCH(k_mlp_au_parse, dim3(div_up_u32(m.cap_au, GRD_THREADS), lim_nss), GRD_THREADS, 0, s, m);
+        else if (pass == 2) LAUNCH(k_mlp_resolve, small, 128, 0, s, m, work);
+        else LAUNCH(k_mlp_entropy, dim3(div_up_u32(cap_pairs, DEC_WARPS), lim_max_au ? lim_max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work);
         CUDA_TRY(cudaEventRecord(kev[slot[pass]][1], s));
         kev_used[slot[pass]] = true;
     }
-    LAUNCH(k_flag_predecessors, div_up_u32((uint64_t)m.nseg * 2, 256), 256, 0, s, m);
+    if (m.cap_seg) LAUNCH(k_flag_predecessors, div_up_u32((uint64_t)m.cap_seg * 2, 256), 256, 0, s, m);
     // check data ran beside all this: segments with a damaged or dropped access unit (parity, CRC,
     // changed stream parameters) go to the complete decoder, which knows where such a track ends
     CUDA_TRY(cudaStreamWaitEvent(s, checked, 0));
-    if (m.nau) LAUNCH(k_flag_damaged, div_up_u32(m.nau, 256), 256, 0, s, m);
-    if (headers_only) LAUNCH(k_flag_sticky, div_up_u32((uint64_t)m.nseg * 2, 256), 256, 0, s, m);
+    if (m.cap_au) LAUNCH(k_flag_damaged, div_up_u32(m.cap_au, 256), 256, 0, s, m);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-template <int NCH>
-static int launch_one_decode(MlpTables m, const DecWork *work, uint32_t n_work, uint32_t n_warps, cudaStream_t s)
+int launch_mlp_decode(MlpTables m, const DecWork *work, uint32_t cap_pairs, cudaStream_t s)
 {
-    if (!n_warps) return 0;
+    if (!cap_pairs) return 0;
     static PerDeviceOnce attr_once;
-    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES)); return 0; })) return -1;
-    LAUNCH(k_mlp_decode<NCH>, div_up_u32(n_warps, DEC_WARPS), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work, n_work, n_warps);
-    return 0;
-}
-
-// work[c], n_work[c], n_warps[c] for channel class c = 0..4 (0 = generic)
-int launch_mlp_decode(MlpTables m, const DecWork *const work[5], const uint32_t n_work[5], const uint32_t n_warps[5], cudaStream_t s)
-{
-    if (launch_one_decode<0>(m, work[0], n_work[0], n_warps[0], s)) return -1;
-    if (launch_one_decode<1>(m, work[1], n_work[1], n_warps[1], s)) return -1;
-    if (launch_one_decode<2>(m, work[2], n_work[2], n_warps[2], s)) return -1;
-    if (launch_one_decode<3>(m, work[3], n_work[3], n_warps[3], s)) return -1;
-    if (launch_one_decode<4>(m, work[4], n_work[4], n_warps[4], s)) return -1;
+    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_mlp_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEC_SMEM_BYTES)); return 0; })) return -1;
+    LAUNCH(k_mlp_decode, div_up_u32(cap_pairs, DEC_WARPS), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
 
 // Segments whose first filtered block needs FIR history from the previous
 // segment (the reference never clears it, mlp.c:948-952), and segments the fast
@@ -2133,10 +2034,10 @@ __global__ void __launch_bounds__(FIX_THREADS) k_carry_fix(MlpTables m)
     __syncthreads();
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t seg = idx >> 1, k = idx & 1;
-    if (seg >= m.nseg) return;
+    if (seg >= m.cnt->nseg) return;
     const TrackDev &T = m.tracks[m.segs[seg].track];
     if (k >= T.nss) return;
-    const uint32_t *fl = m.ss_flags_prev + (uint64_t)k * m.nseg;   // as they were before any fix-up
+    const uint32_t *fl = m.ss_flags_prev + (uint64_t)k * m.cap_seg;   // as they were before any fix-up
     if (!(fl[seg] & SEG_NEEDS_CARRY)) return;
     // run head: predecessor (same track) is not waiting for a carry itself
     if (seg > T.seg_base && (fl[seg - 1] & SEG_NEEDS_CARRY)) return;
@@ -2150,7 +2051,7 @@ __global__ void __launch_bounds__(FIX_THREADS) k_carry_fix(MlpTables m)
     for (uint32_t s = seg; s < track_end && (fl[s] & SEG_NEEDS_CARRY); s++) {
         DecodeJob job;
         job.seg = s; job.k = k; job.lane = (s - T.seg_base) % DVDA_LANES; job.exact_history = true;
-        const int32_t *prev = m.fir_tail + ((uint64_t)k * m.nseg + (s - 1)) * (DVDA_MAX_CH * 8);
+        const int32_t *prev = m.fir_tail + ((uint64_t)k * m.cap_seg + (s - 1)) * (DVDA_MAX_CH * 8);
         // parsing does not depend on filter history, so the error bookkeeping of the
         // first pass (merged with atomics) is reproduced exactly
         decode_segment<0>(m, job, lut, rs, s > T.seg_base ? prev : nullptr);
@@ -2159,8 +2060,8 @@ __global__ void __launch_bounds__(FIX_THREADS) k_carry_fix(MlpTables m)
 
 int launch_carry_fix(MlpTables m, cudaStream_t s)
 {
-    if (!m.nseg) return 0;
-    LAUNCH(k_carry_fix, div_up_u32((uint64_t)m.nseg * 2, FIX_THREADS), FIX_THREADS, 0, s, m);
+    if (!m.cap_seg) return 0;
+    LAUNCH(k_carry_fix, div_up_u32((uint64_t)m.cap_seg * 2, FIX_THREADS), FIX_THREADS, 0, s, m);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -2171,12 +2072,11 @@ int launch_carry_fix(MlpTables m, cudaStream_t s)
 __global__ void k_seg_finalize(MlpTables m, uint32_t *__restrict__ seg_frames, uint32_t *__restrict__ status)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nseg) return;
+    if (i >= m.cap_seg) return;
+    if (i >= m.cnt->nseg) { seg_frames[i] = 0; return; }  // rows behind the last segment count nothing
     SegDev &S = m.segs[i];
     TrackDev &T = m.tracks[S.track];
-    // flags of this decode attempt; S.flags keeps SEG_OVERFLOW from an earlier one so
-    // that a second attempt sizes the tile from the counted frames
-    const uint32_t now = m.ss_flags[i] | (T.nss == 2 ? m.ss_flags[m.nseg + i] : 0);
+    const uint32_t now = m.ss_flags[i] | (T.nss == 2 ? m.ss_flags[m.cap_seg + i] : 0);
     uint32_t flags = S.flags | now;
     uint32_t err = S.err, stop = S.err_au;
     uint32_t frames = 0;
@@ -2184,12 +2084,13 @@ __global__ void k_seg_finalize(MlpTables m, uint32_t *__restrict__ seg_frames, u
     for (uint32_t a = 0; a < lim; a++) {
         const uint32_t A = S.au_base + a;
         const uint32_t nf = m.au_frames_ss[A];
-        if (T.nss == 2 && m.au_frames_ss[m.nau + A] != nf) { err |= ERR_SYNTAX; stop = a; break; }
+        if (T.nss == 2 && m.au_frames_ss[m.cap_au + A] != nf) { err |= ERR_SYNTAX; stop = a; break; }
         frames += nf;
     }
     if ((flags & SEG_IRREGULAR) && stop == 0xFFFFFFFFu) { err |= ERR_SYNTAX; stop = S.n_au; }
     S.flags = flags & ~SEG_NEEDS_CARRY;
-    if (now & SEG_OVERFLOW) atomicOr(status, SEG_OVERFLOW);
+    // a segment longer than its tile: the decode is repeated with the frame count found here
+    if (now & SEG_OVERFLOW) { atomicOr(status, SEG_OVERFLOW); m.seg_need[i] = max(m.seg_need[i], frames); }
     // anything left for k_rematrix once the fused filter + output pass has run?
     if (m.fast && frames && !seg_output_done(m, T, i)) atomicOr(status, STATUS_WANTS_REMATRIX);
     S.err = err;
@@ -2208,7 +2109,7 @@ __global__ void k_seg_finalize(MlpTables m, uint32_t *__restrict__ seg_frames, u
 __global__ void k_track_finalize(MlpTables m, const uint64_t *__restrict__ scan, const uint32_t *__restrict__ status)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.nseg) return;
+    if (i >= m.cnt->nseg) return;
     if (*status & SEG_OVERFLOW) return;                   // the batch is decoded once more: leave the counts alone
     SegDev &S = m.segs[i];
     TrackDev &T = m.tracks[S.track];
@@ -2223,15 +2124,15 @@ __global__ void k_track_finalize(MlpTables m, const uint64_t *__restrict__ scan,
 
 int launch_seg_finalize(MlpTables m, uint32_t *seg_frames, uint32_t *status, cudaStream_t s)
 {
-    if (!m.nseg) return 0;
-    LAUNCH(k_seg_finalize, div_up_u32(m.nseg, 128), 128, 0, s, m, seg_frames, status);
+    if (!m.cap_seg) return 0;
+    LAUNCH(k_seg_finalize, div_up_u32(m.cap_seg, 128), 128, 0, s, m, seg_frames, status);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, const uint32_t *status, cudaStream_t s)
 {
-    if (!m.nseg) return 0;
-    LAUNCH(k_track_finalize, div_up_u32(m.nseg, 128), 128, 0, s, m, seg_frame_scan, status);
+    if (!m.cap_seg) return 0;
+    LAUNCH(k_track_finalize, div_up_u32(m.cap_seg, 128), 128, 0, s, m, seg_frame_scan, status);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -2240,8 +2141,8 @@ int launch_track_finalize(MlpTables m, const uint64_t *seg_frame_scan, const uin
 
 #define RM_THREADS 256
 
-// One block per (group, 32-frame chunk): blockIdx.x = group, blockIdx.y = chunk
-// (groups with fewer chunks than the largest leave at once).  Loads the
+// A block takes (group, 32-frame chunk) items in turn (the grid is fixed: how many groups and
+// chunks there are is known on the device only).  It loads the
 // [32 frames][nch][32 lanes] patch of the tile coalesced, then every warp takes
 // segments (lanes of the patch) and its 32 threads take the 32 frames: noise,
 // matrices, bypass, shift, channel order, interleaved store.
@@ -2269,18 +2170,12 @@ __device__ __forceinline__ AuDev au_of_frame(const MlpTables &m, const SegDev &S
     return au;
 }
 
+// one (group, chunk) item; every return is taken by the whole block
 template <int NCH>
-__global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
+__device__ __forceinline__ void rematrix_chunk(const MlpTables &m, const GroupDev &G, const TrackDev &T, uint32_t f0, int32_t *sm)
 {
-    extern __shared__ int32_t sm[];                      // [nch][32][33] samples, then [32][33] bypass bytes as ints
-    const uint32_t g = blockIdx.x;
-    const GroupDev &G = m.groups[g];
-    const uint32_t f0 = blockIdx.y * 32;
-    if (f0 >= G.cap) return;
-    const TrackDev &T = m.tracks[G.track];
+    // sm: [nch][32][33] samples, then [32][33] bypass bytes as ints
     const uint32_t nch = NCH ? NCH : T.channels;
-    if (NCH && T.channels != NCH) return;
-    if (!NCH && T.channels <= 2) return;                 // handled by the specialised instantiations
     const uint32_t nf = min(32u, G.cap - f0);
     int32_t *bsm = sm + nch * 32 * 33;
     if (m.fast) {
@@ -2377,17 +2272,34 @@ __global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
     }
 }
 
-int launch_rematrix(MlpTables m, uint32_t max_chunks, uint32_t channel_mask, cudaStream_t s)
+#define RM_SMEM_BYTES ((DVDA_MAX_CH + 1) * 32 * 33 * 4)
+__global__ void __launch_bounds__(RM_THREADS) k_rematrix(MlpTables m)
 {
-    if (!max_chunks || !m.ngroups) return 0;
-    const dim3 grid(m.ngroups, max_chunks);
-    const size_t smem = (size_t)(DVDA_MAX_CH + 1) * 32 * 33 * sizeof(int32_t);
+    extern __shared__ int32_t rm_sm[];
+    // with the fast path: only if some segment was left for this pass (k_seg_finalize)
+    if (m.fast && !(*m.status & STATUS_WANTS_REMATRIX)) return;
+    if (*m.status & (SEG_OVERFLOW | STATUS_PCM_SMALL)) return;
+    const uint32_t chunks = m.cnt->max_chunks;
+    const uint64_t items = (uint64_t)m.cnt->ngroups * chunks;
+    for (uint64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const GroupDev &G = m.groups[it / chunks];
+        const uint32_t f0 = (uint32_t)(it % chunks) * 32;
+        if (f0 < G.cap) {
+            const TrackDev &T = m.tracks[G.track];
+            if (T.channels == 1) rematrix_chunk<1>(m, G, T, f0, rm_sm);
+            else if (T.channels == 2) rematrix_chunk<2>(m, G, T, f0, rm_sm);
+            else rematrix_chunk<0>(m, G, T, f0, rm_sm);
+        }
+        __syncthreads();                                  // the patch is overwritten by the next item
+    }
+}
+
+int launch_rematrix(MlpTables m, cudaStream_t s)
+{
+    if (!m.cap_grp) return 0;
     static PerDeviceOnce attr_once;
-    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_rematrix<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); return 0; })) return -1;
-    // channel_mask: bit n = some MLP track of the batch has n channels
-    if (channel_mask & 2) LAUNCH(k_rematrix<1>, grid, RM_THREADS, (size_t)2 * 32 * 33 * 4, s, m);
-    if (channel_mask & 4) LAUNCH(k_rematrix<2>, grid, RM_THREADS, (size_t)3 * 32 * 33 * 4, s, m);
-    if (channel_mask & ~6u) LAUNCH(k_rematrix<0>, grid, RM_THREADS, smem, s, m);
+    if (attr_once.run([&]() -> int { CUDA_TRY(cudaFuncSetAttribute(k_rematrix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM_BYTES)); return 0; })) return -1;
+    LAUNCH(k_rematrix, 148 * 4, RM_THREADS, RM_SMEM_BYTES, s, m);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -61,11 +61,18 @@ __device__ __noinline__ bool sync_starts_segment(const uint8_t *es, uint64_t p, 
 #endif
 
 __global__ void __launch_bounds__(SYNC_WARPS * 32)
-k_sync_find(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t chunks, uint32_t *__restrict__ cnt_raw,
+k_sync_find(const uint8_t *__restrict__ es, const DecCounts *__restrict__ cnt, uint32_t chunks_cap, uint32_t *__restrict__ cnt_raw,
             uint32_t *__restrict__ cnt_valid, uint16_t *__restrict__ slots, uint32_t nslots)
 {
+    // (the grid covers the chunks the stream buffer has room for: the ones behind the stream count nothing)
+    const uint64_t es_total = cnt->es_total;
+    const uint32_t chunks = (uint32_t)((es_total + SYNC_CHUNK - 1) / SYNC_CHUNK);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t chunk0 = (blockIdx.x * SYNC_WARPS + (threadIdx.x >> 5)) * SYNC_CHUNKS_PER_WARP;
+    if (chunk0 >= chunks) {
+        if (lane < SYNC_CHUNKS_PER_WARP && chunk0 + lane < chunks_cap) { cnt_raw[chunk0 + lane] = 0; cnt_valid[chunk0 + lane] = 0; }
+        return;
+    }
     // all loads of the warp's chunks first (the ES buffer is padded well past es_total)
     uint4 q[SYNC_CHUNKS_PER_WARP];
     uint2 nx[SYNC_CHUNKS_PER_WARP];
@@ -79,7 +86,10 @@ k_sync_find(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t chunks, 
 #pragma unroll
     for (int c = 0; c < SYNC_CHUNKS_PER_WARP; c++) {
         const uint32_t chunk = chunk0 + c;
-        if (chunk >= chunks) break;                                   // warp-uniform
+        if (chunk >= chunks) {                                        // warp-uniform
+            if (lane == 0 && chunk < chunks_cap) { cnt_raw[chunk] = 0; cnt_valid[chunk] = 0; }
+            continue;
+        }
         uint32_t w[6];
         w[0] = __byte_perm(q[c].x, 0, 0x0123); w[1] = __byte_perm(q[c].y, 0, 0x0123);
         w[2] = __byte_perm(q[c].z, 0, 0x0123); w[3] = __byte_perm(q[c].w, 0, 0x0123);
@@ -125,12 +135,14 @@ k_sync_find(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t chunks, 
     }
 }
 
-__global__ void k_sync_emit(const uint8_t *__restrict__ es, uint64_t es_total, uint32_t chunks,
+__global__ void k_sync_emit(const uint8_t *__restrict__ es, const DecCounts *__restrict__ cnt,
                             const uint32_t *__restrict__ cnt_raw, const uint16_t *__restrict__ slots, uint32_t nslots,
                             const uint32_t *__restrict__ base_raw, const uint32_t *__restrict__ base_valid,
                             uint64_t *__restrict__ raw, uint32_t cap_raw, uint64_t *__restrict__ valid, uint32_t cap_valid)
 {
     // (the lists were sized before their lengths were known: nothing is written behind their ends)
+    const uint64_t es_total = cnt->es_total;
+    const uint32_t chunks = (uint32_t)((es_total + SYNC_CHUNK - 1) / SYNC_CHUNK);
     const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= chunks) return;
     const uint32_t n = cnt_raw[ch];
@@ -156,19 +168,19 @@ __global__ void k_sync_emit(const uint8_t *__restrict__ es, uint64_t es_total, u
     }
 }
 
-int launch_sync_count(const uint8_t *es, uint64_t es_total, uint32_t *cnt_raw, uint32_t *cnt_valid, uint16_t *slots, uint32_t nslots, cudaStream_t s)
+// chunks_cap: chunks the stream buffer has room for (the stream's size is still on the device)
+int launch_sync_count(const uint8_t *es, const DecCounts *cnt, uint32_t chunks_cap, uint32_t *cnt_raw, uint32_t *cnt_valid,
+                      uint16_t *slots, uint32_t nslots, cudaStream_t s)
 {
-    const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
-    LAUNCH(k_sync_find, div_up_u32(chunks, SYNC_WARPS * SYNC_CHUNKS_PER_WARP), SYNC_WARPS * 32, 0, s, es, es_total, chunks, cnt_raw, cnt_valid, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS);
+    LAUNCH(k_sync_find, div_up_u32(chunks_cap, SYNC_WARPS * SYNC_CHUNKS_PER_WARP), SYNC_WARPS * 32, 0, s, es, cnt, chunks_cap, cnt_raw, cnt_valid, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int launch_sync_fill(const uint8_t *es, uint64_t es_total, const uint32_t *cnt_raw, const uint16_t *slots, uint32_t nslots,
+int launch_sync_fill(const uint8_t *es, const DecCounts *cnt, uint32_t chunks_cap, const uint32_t *cnt_raw, const uint16_t *slots, uint32_t nslots,
                      const uint32_t *base_raw, const uint32_t *base_valid, uint64_t *raw, uint32_t cap_raw,
                      uint64_t *valid, uint32_t cap_valid, cudaStream_t s)
 {
-    const uint32_t chunks = div_up_u32(es_total ? es_total : 1, SYNC_CHUNK);
-    LAUNCH(k_sync_emit, div_up_u32(chunks, 128), 128, 0, s, es, es_total, chunks, cnt_raw, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS, base_raw, base_valid, raw, cap_raw, valid, cap_valid);
+    LAUNCH(k_sync_emit, div_up_u32(chunks_cap, 128), 128, 0, s, es, cnt, cnt_raw, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS, base_raw, base_valid, raw, cap_raw, valid, cap_valid);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -243,7 +255,8 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
 {
     const uint32_t ti = blockIdx.x * 2 + (threadIdx.x >> 5);
     if (ti >= n_tracks) return;
-    const uint32_t n_raw = min(*a.n_raw, a.cap_raw), n_valid = min(*a.n_valid, a.cap_valid);
+    const uint32_t n_raw = (uint32_t)min(a.cnt->n_raw, (uint64_t)a.cap_raw), n_valid = (uint32_t)min(a.cnt->n_valid, (uint64_t)a.cap_valid);
+    const uint32_t np = (uint32_t)a.cnt->np;
     TrackDev T = tracks[ti];
     T.status = 1;
     T.error_flags = 0;
@@ -256,6 +269,7 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
     T.stopped = 0;
     T.pk_open = T.pk_check = T.pk_check_end = 0;
     do {
+        if (a.cnt->overflow) break;                            // a table was too small: the host comes back
         if (T.first_sector >= a.n_sectors) break;              // aob_reader_seek fails (aob.c:181-199)
         // a broken packet chain ends the stream for good (packet.c:60-116)
         uint32_t dead = a.n_sectors;
@@ -265,11 +279,11 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
             dead = warp_first_true(T.first_sector, a.n_sectors, [=](uint32_t i) { return bp[i + 1] > base; });
         }
         T.pk_lo = a.sec_base[T.first_sector];
-        T.pk_hi = dead < a.n_sectors ? a.sec_base[dead + 1] : a.np;
+        T.pk_hi = dead < a.n_sectors ? a.sec_base[dead + 1] : np;
         if (T.pk_lo >= T.pk_hi) break;                         // no audio packet
         const uint32_t codec = a.pt.codec[T.pk_lo];
         uint32_t pk_x = (T.last_sector < a.n_sectors - 1 && T.last_sector + 1 > T.last_sector)
-                            ? a.sec_base[T.last_sector + 1] : a.np;
+                            ? a.sec_base[T.last_sector + 1] : np;
 
         if (codec == CODEC_PCM) {
             // open_pcm_track_reader (dvd-audio.c:952-1014)
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
             const uint64_t total = (uint64_t)llround((double)T.pts_length * (double)T.rate / 90000.0);
             T.pcm_frame0 = a.pk_pf[T.pk_lo];
             // stop in front of the first later packet that is not PCM / differs / is empty
-            uint32_t stop = warp_first_flagged(a.pk_pcm_stop, a.np, T.pk_lo + 1);
+            uint32_t stop = warp_first_flagged(a.pk_pcm_stop, np, T.pk_lo + 1);
             if (stop > T.pk_hi) stop = T.pk_hi;
             // ... and behind the packet in which the budget is used up: first i with
             // frames(pk_lo..i) >= total
@@ -295,10 +309,11 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
             const uint64_t frame0 = T.pcm_frame0;
             const uint32_t lo = warp_first_true(T.pk_lo, stop, [=](uint32_t i) { return pf[i + 1] - frame0 >= total; });
             T.pcm_pk_end = lo < stop ? lo + 1 : stop;
-            T.truncated = (lo >= stop && stop == a.np);        // budget left, buffer used up
+            T.truncated = (lo >= stop && stop == np);        // budget left, buffer used up
             T.frames = a.pk_pf[T.pcm_pk_end] - T.pcm_frame0;
             T.status = 0;
         } else if (codec == CODEC_MLP) {
+            if (!a.mlp_searched) { atomicOr(&a.cnt->overflow, CAP_SHAPE); break; }   // the sync search was left out: the host comes back
             // open_mlp_track_reader / locate_mlp_parameters (dvd-audio.c:1094-1149, 1318-1365)
             const uint64_t es_avail = a.pk_es[T.pk_hi];
             const uint64_t es_lo = a.pk_es[T.pk_lo];
@@ -322,7 +337,7 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
             const uint32_t rc = T.g0_rate & 7;
             T.au_nominal = 40u << (rc > 2 ? 0 : rc);
             // the packet holding byte p + 17 is the last one consumed while opening
-            T.pk_open = warp_upper_bound(a.pk_es, a.np + 1, p + 17) - 1;
+            T.pk_open = warp_upper_bound(a.pk_es, np + 1, p + 17) - 1;
             // a continued part whose range holds no sync at all is empty: the sync it found
             // lies in (and will be found again by) a later part
             const bool empty_part = (T.cont & TRACK_CONT_PREV) && pk_x < T.pk_hi && p >= a.pk_es[pk_x];
@@ -332,7 +347,7 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
             // last access unit ended inside that packet (then the packet did yield)
             T.pk_check = T.pk_open + 1;
             if (T.cont & TRACK_CONT_PREV)
-                T.pk_check = p > es_lo ? warp_upper_bound(a.pk_es, a.np + 1, p - 1) : T.pk_lo;
+                T.pk_check = p > es_lo ? warp_upper_bound(a.pk_es, np + 1, p - 1) : T.pk_lo;
             // end of the track
             uint64_t es_end = es_avail;
             if (pk_x < T.pk_hi) {
@@ -349,14 +364,14 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
                 T.truncated = 1;                               // no packet behind last_sector in the buffer
             }
             // a non-MLP audio packet met while decoding ends the stream (dvd-audio.c:1203-1208)
-            const uint32_t nm = warp_first_flagged(a.pk_nonmlp, a.np, (T.cont & TRACK_CONT_PREV) ? T.pk_lo : T.pk_open + 1);
+            const uint32_t nm = warp_first_flagged(a.pk_nonmlp, np, (T.cont & TRACK_CONT_PREV) ? T.pk_lo : T.pk_open + 1);
             if (nm < pk_x && nm < T.pk_hi && a.pk_es[nm] < es_end) es_end = a.pk_es[nm];
             if (es_end < p) es_end = p;
             T.es_end = es_end;
             // a part that is continued also answers for the packets its last access units end in
             T.pk_check_end = pk_x;
             if ((T.cont & TRACK_CONT_NEXT) && pk_x < T.pk_hi && es_end > a.pk_es[pk_x])
-                T.pk_check_end = min(T.pk_hi, warp_upper_bound(a.pk_es, a.np + 1, es_end - 1));
+                T.pk_check_end = min(T.pk_hi, warp_upper_bound(a.pk_es, np + 1, es_end - 1));
             T.es_cut = es_end;
             if (empty_part) T.es_end = T.es_cut = p;
             if (T.nss != 1 && T.nss != 2) {
@@ -382,15 +397,137 @@ int launch_track_setup(TrackSetupArgs a, TrackDev *tracks, uint32_t n_tracks, cu
     return 0;
 }
 
+// ----------------------------------------------------------- the plan
+// One block: the tracks' places in the segment and group tables (prefix sums over the tracks,
+// in order), the work list of the per-segment passes, totals and flags for the host — what the
+// host used to compute between two round trips.
+#define PLAN_THREADS 256
+__global__ void __launch_bounds__(PLAN_THREADS)
+k_track_plan(TrackDev *__restrict__ tracks, uint32_t n_tracks, uint32_t *__restrict__ trk_pk_lo,
+             uint32_t *__restrict__ trk_seg_base, uint32_t *__restrict__ trk_grp_base,
+             DecWork *__restrict__ work, OutWork *__restrict__ out_work, uint32_t cap_work, uint32_t cap_seg, uint32_t cap_grp,
+             uint32_t cap_sync, DecCounts *__restrict__ cnt)
+{
+    __shared__ uint32_t s_flags[4];
+    if (threadIdx.x < 4) s_flags[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t seg_carry = 0, grp_carry = 0, pair_carry = 0, row_carry = 0, pcm_carry = 0, ow_carry = 0, orow_carry = 0;
+    for (uint32_t base = 0; base < n_tracks; base += PLAN_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t nseg = 0, ngrp = 0, nss = 0, out_warps = 0, n0 = 0, n1 = 0;
+        uint64_t pcm = 0;
+        if (i < n_tracks) {
+            TrackDev &T = tracks[i];
+            const bool mlp = T.status == 0 && T.codec == 1;
+            if (!mlp) { T.nseg = 0; T.ngrp = 0; }
+            nseg = T.nseg; ngrp = T.ngrp;
+            nss = (mlp && nseg) ? T.nss : 0;
+            if (T.status == 0 && T.codec == 0) { pcm = T.frames * T.channels; atomicOr(&s_flags[0], 1u); }
+            if (mlp && nseg) {
+                atomicOr(&s_flags[1], 1u);
+                atomicMax(&s_flags[2], T.nss);
+                atomicOr(&s_flags[3], 1u << T.channels);
+            }
+            trk_pk_lo[i] = T.pk_lo;
+            // the output pass: lanes = (segment, channel) over both substreams, 32 / channels segments per warp
+            if (nss && (T.nss == 1 ? (T.channels >= 1 && T.channels <= 4) : (T.nss == 2 && T.channels >= 3 && T.channels <= 6))) {
+                n0 = T.nss == 1 ? T.channels : 2; n1 = T.channels - n0;
+                const uint32_t spw = 32 / T.channels;
+                out_warps = ngrp * ((32 + spw - 1) / spw);
+            }
+        }
+        // (packed: two sums per scan)
+        uint64_t tot_a, tot_b, tot_c;
+        const uint64_t ex_a = block_excl_scan<PLAN_THREADS>((uint64_t)nseg | (uint64_t)ngrp << 32, &tot_a);
+        const uint64_t ex_b = block_excl_scan<PLAN_THREADS>((uint64_t)(ngrp * nss) | (uint64_t)nss << 32, &tot_b);
+        block_excl_scan<PLAN_THREADS>(pcm, &tot_c);
+        uint64_t tot_d;
+        const uint64_t ex_d = block_excl_scan<PLAN_THREADS>((uint64_t)out_warps | (uint64_t)(out_warps ? 1u : 0u) << 32, &tot_d);
+        if (out_warps) {
+            const uint32_t orow = (uint32_t)(orow_carry + (ex_d >> 32));
+            OutWork w = {(uint32_t)(ow_carry + (ex_d & 0xFFFFFFFFu)), i, n0, n1};
+            out_work[orow] = w;                            // (at most one row per track: the list has n_tracks rows)
+        }
+        ow_carry += tot_d & 0xFFFFFFFFu; orow_carry += tot_d >> 32;
+        if (i < n_tracks) {
+            TrackDev &T = tracks[i];
+            const uint32_t seg_base = (uint32_t)(seg_carry + (ex_a & 0xFFFFFFFFu));
+            const uint32_t grp_base = (uint32_t)(grp_carry + (ex_a >> 32));
+            T.seg_base = seg_base; T.grp_base = grp_base;
+            trk_seg_base[i] = seg_base; trk_grp_base[i] = grp_base;
+            uint32_t warp0 = (uint32_t)(pair_carry + (ex_b & 0xFFFFFFFFu));
+            uint32_t row = (uint32_t)(row_carry + (ex_b >> 32));
+            for (uint32_t k = 0; k < nss; k++, row++, warp0 += ngrp) {
+                // substream 0 of a two-substream stream carries the stereo pair (DVD-Audio layout)
+                const uint32_t nch = T.nss == 1 ? T.channels : (k == 0 ? 2 : T.channels - 2);
+                if (row < cap_work) { DecWork w = {warp0, i, k, nch}; work[row] = w; }
+            }
+        }
+        seg_carry += tot_a & 0xFFFFFFFFu; grp_carry += tot_a >> 32;
+        pair_carry += tot_b & 0xFFFFFFFFu; row_carry += tot_b >> 32;
+        pcm_carry += tot_c;
+    }
+    if (threadIdx.x == 0) {
+        trk_seg_base[n_tracks] = (uint32_t)seg_carry; trk_grp_base[n_tracks] = (uint32_t)grp_carry;
+        uint32_t over = cnt->overflow;
+        if (cnt->n_raw > cap_sync || cnt->n_valid > cap_sync) { over |= CAP_SYNC; cnt->need_sync = max(cnt->n_raw, cnt->n_valid); }
+        if (seg_carry > cap_seg) { over |= CAP_SEG; cnt->need_seg = seg_carry; }
+        if (grp_carry > cap_grp || row_carry > cap_work) { over |= CAP_GRP; cnt->need_grp = grp_carry; }
+        cnt->overflow = over;
+        // with a table too small nothing of the MLP side runs: the host comes back
+        const bool stop = (over & (CAP_SYNC | CAP_SEG | CAP_GRP | CAP_ROWS)) != 0;
+        cnt->nseg = stop ? 0u : (uint32_t)seg_carry;
+        cnt->ngroups = stop ? 0u : (uint32_t)grp_carry;
+        cnt->npairs = stop ? 0u : (uint32_t)pair_carry;
+        cnt->nwork = stop ? 0u : (uint32_t)row_carry;
+        cnt->nout_work = stop ? 0u : (uint32_t)orow_carry;
+        cnt->nout_warps = stop ? 0u : (uint32_t)ow_carry;
+        cnt->pcm_fixed = pcm_carry + 4ull * n_tracks + 64;
+        cnt->any_pcm = s_flags[0]; cnt->any_mlp = s_flags[1]; cnt->nss_max = s_flags[2] ? s_flags[2] : 1; cnt->chan_mask = s_flags[3];
+        cnt->max_au = 0; cnt->max_chunks = 0;
+    }
+}
+
+__global__ void k_plan_check(DecCounts *__restrict__ cnt, PlanLimits lim)
+{
+    uint32_t over = cnt->overflow;
+    if (cnt->nau > lim.cap_au) { over |= CAP_AU; cnt->need_au = cnt->nau; }
+    if (cnt->cells > lim.cap_cells) { over |= CAP_CELLS; cnt->need_cells = cnt->cells; }
+    if (cnt->max_au > lim.max_au) over |= CAP_MAX_AU;
+    // kernels that were left out, or sized for less, because the previous decode had no use for them
+    if ((cnt->any_pcm && !lim.pcm) || (cnt->any_mlp && !lim.mlp) || (cnt->any_mlp && cnt->nss_max > lim.nss) ||
+        cnt->nout_warps > lim.out_warps) over |= CAP_SHAPE;
+    cnt->overflow = over;
+    if (over & (CAP_AU | CAP_CELLS | CAP_MAX_AU | CAP_SHAPE)) {
+        // nothing may be written to tables that are too small, nothing read that was not written: the MLP side stops here
+        cnt->nau = 0; cnt->nseg = 0; cnt->ngroups = 0; cnt->npairs = 0; cnt->nwork = 0; cnt->nout_work = 0; cnt->nout_warps = 0;
+    }
+}
+
+int launch_track_plan(TrackDev *tracks, uint32_t n_tracks, uint32_t *trk_pk_lo, uint32_t *trk_seg_base, uint32_t *trk_grp_base,
+                      DecWork *work, OutWork *out_work, uint32_t cap_work, uint32_t cap_seg, uint32_t cap_grp, uint32_t cap_sync,
+                      DecCounts *cnt, cudaStream_t s)
+{
+    LAUNCH(k_track_plan, 1, PLAN_THREADS, 0, s, tracks, n_tracks, trk_pk_lo, trk_seg_base, trk_grp_base, work, out_work, cap_work, cap_seg, cap_grp, cap_sync, cnt);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int launch_plan_check(DecCounts *cnt, PlanLimits lim, cudaStream_t s)
+{
+    LAUNCH(k_plan_check, 1, 1, 0, s, cnt, lim);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------- segments and AUs
 
 // one thread per segment: where it starts and where it must end
 __global__ void k_segment_fill(const TrackDev *__restrict__ tracks, uint32_t n_tracks,
                                const uint32_t *__restrict__ trk_seg_base, const uint64_t *__restrict__ valid,
-                               SegDev *__restrict__ segs, uint32_t nseg)
+                               SegDev *__restrict__ segs, const DecCounts *__restrict__ cnt)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nseg) return;
+    if (i >= cnt->nseg) return;
     const uint32_t t = upper_bound_dev(trk_seg_base, n_tracks, i) - 1;
     const TrackDev &T = tracks[t];
     const uint32_t j = i - trk_seg_base[t];
@@ -403,10 +540,10 @@ __global__ void k_segment_fill(const TrackDev *__restrict__ tracks, uint32_t n_t
 }
 
 int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_seg_base,
-                        const uint64_t *valid, SegDev *segs, uint32_t nseg, cudaStream_t s)
+                        const uint64_t *valid, SegDev *segs, uint32_t cap_seg, const DecCounts *cnt, cudaStream_t s)
 {
-    if (!nseg) return 0;
-    LAUNCH(k_segment_fill, div_up_u32(nseg, 128), 128, 0, s, tracks, n_tracks, trk_seg_base, valid, segs, nseg);
+    if (!cap_seg) return 0;
+    LAUNCH(k_segment_fill, div_up_u32(cap_seg, 128), 128, 0, s, tracks, n_tracks, trk_seg_base, valid, segs, cnt);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -418,7 +555,8 @@ int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_
 // walk down the chain; only a segment with more access units than were noted walks on from the
 // last noted one.
 #define AU_NOTED 32
-__global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ segs, uint32_t nseg,
+__global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ segs, uint32_t nseg /* rows: stride of `noted` */,
+                           const DecCounts *__restrict__ cnt,
                            const TrackDev *__restrict__ tracks, uint32_t *__restrict__ seg_nau,
                            uint64_t *__restrict__ au_pos, uint32_t *__restrict__ au_seg,
                            const uint32_t *__restrict__ seg_au_base, uint32_t *__restrict__ noted, uint32_t n_noted, int fill)
@@ -426,6 +564,8 @@ __global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ 
     // (n_noted: positions noted per segment, AU_NOTED unless a test wants the walk-on path)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nseg) return;
+    if (i >= cnt->nseg) { if (!fill) seg_nau[i] = 0; return; }         // rows behind the last segment count nothing
+    if (fill && cnt->nau == 0) return;                                 // (the access-unit tables were too small: nothing is filled)
     SegDev &S = segs[i];
     const uint64_t limit = S.es_limit;
     const uint64_t pos0 = S.es_pos;
@@ -470,13 +610,13 @@ __global__ void k_au_chase(const uint8_t *__restrict__ es, SegDev *__restrict__ 
 
 size_t au_noted_bytes(uint32_t nseg) { return (size_t)AU_NOTED * nseg * sizeof(uint32_t); }
 
-int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t nseg, const TrackDev *tracks,
+int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t cap_seg, const DecCounts *cnt, const TrackDev *tracks,
                     uint32_t *seg_nau, uint64_t *au_pos, uint32_t *au_seg, const uint32_t *seg_au_base,
                     uint32_t *noted, int fill, cudaStream_t s)
 {
-    if (!nseg) return 0;
+    if (!cap_seg) return 0;
     const uint32_t n_noted = getenv("DVDAGPU_SMALL_TABLES") ? 2u : (uint32_t)AU_NOTED;          // (test hook)
-    LAUNCH(k_au_chase, div_up_u32(nseg, 128), 128, 0, s, es, segs, nseg, tracks, seg_nau, au_pos, au_seg, seg_au_base, noted, n_noted, fill);
+    LAUNCH(k_au_chase, div_up_u32(cap_seg, 128), 128, 0, s, es, segs, cap_seg, cnt, tracks, seg_nau, au_pos, au_seg, seg_au_base, noted, n_noted, fill);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -493,7 +633,8 @@ __global__ void k_yield_mark(MlpTables m, const uint32_t *__restrict__ seg_au_ba
     // packets: the warp searches the packet of its first access unit together (32 probes and a
     // ballot per round), the lanes walk on from there.
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool have = a < m.nau;
+    const bool have = a < m.cnt->nau;
+    const uint32_t np = (uint32_t)m.cnt->np;
     if (!__any_sync(0xFFFFFFFFu, have)) return;
     uint64_t last_byte = 0;
     if (have) {
@@ -503,10 +644,10 @@ __global__ void k_yield_mark(MlpTables m, const uint32_t *__restrict__ seg_au_ba
     }
     const uint64_t x0 = __shfl_sync(0xFFFFFFFFu, last_byte, 0);          // lane 0 has the lowest access unit
     const uint64_t *pk_es = m.pk_es;
-    uint32_t pk = warp_first_true(0u, m.np + 1, [=](uint32_t i) { return pk_es[i] > x0; }) - 1;
+    uint32_t pk = warp_first_true(0u, np + 1, [=](uint32_t i) { return pk_es[i] > x0; }) - 1;
     if (have) {
-        if (last_byte < x0) pk = upper_bound_dev(m.pk_es, m.np + 1, last_byte) - 1;   // (not in stream order: on its own)
-        else while (pk + 1 <= m.np && pk_es[pk + 1] <= last_byte) pk++;
+        if (last_byte < x0) pk = upper_bound_dev(m.pk_es, np + 1, last_byte) - 1;   // (not in stream order: on its own)
+        else while (pk + 1 <= np && pk_es[pk + 1] <= last_byte) pk++;
         pk_yield[pk] = 1;
     }
     (void)seg_au_base;
@@ -516,7 +657,7 @@ __global__ void k_yield_find(MlpTables m, PacketTable pt, const uint32_t *__rest
                              const uint8_t *__restrict__ pk_yield)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.np || pk_yield[i] || pt.codec[i] != CODEC_MLP) return;
+    if (i >= m.cnt->np || pk_yield[i] || pt.codec[i] != CODEC_MLP) return;
     // Tracks are sorted by first packet.  Normally the owner is the last track that
     // starts at or before packet i; parts of one long track may also answer for the
     // first packets of the parts behind them, so look a few tracks back as well.
@@ -530,13 +671,13 @@ __global__ void k_yield_find(MlpTables m, PacketTable pt, const uint32_t *__rest
     }
 }
 
-int launch_yield(MlpTables m, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
+int launch_yield(MlpTables m, uint32_t rows, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
                  uint8_t *pk_yield, cudaStream_t s)
 {
-    if (!m.np) return 0;
-    CUDA_TRY(cudaMemsetAsync(pk_yield, 0, m.np, s));
-    if (m.nau) LAUNCH(k_yield_mark, div_up_u32(m.nau, 256), 256, 0, s, m, seg_au_base, pk_yield);
-    LAUNCH(k_yield_find, div_up_u32(m.np, 256), 256, 0, s, m, pt, trk_pk_lo, pk_yield);
+    if (!rows) return 0;
+    CUDA_TRY(cudaMemsetAsync(pk_yield, 0, rows, s));
+    if (m.cap_au) LAUNCH(k_yield_mark, div_up_u32(m.cap_au, 256), 256, 0, s, m, seg_au_base, pk_yield);
+    LAUNCH(k_yield_find, div_up_u32(rows, 256), 256, 0, s, m, pt, trk_pk_lo, pk_yield);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -547,12 +688,13 @@ int launch_yield(MlpTables m, const uint32_t *seg_au_base, PacketTable pt, const
 // decoding warp.  Its tile holds `cap` frames per segment.
 __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tracks,
                               const uint32_t *__restrict__ trk_grp_base, const SegDev *__restrict__ segs,
-                              GroupDev *__restrict__ groups, uint32_t ngroups, uint32_t *__restrict__ grp_cells,
-                              uint32_t *__restrict__ grp_chunks, uint32_t *__restrict__ max_au)
+                              GroupDev *__restrict__ groups, uint32_t cap_grp, DecCounts *__restrict__ cnt,
+                              uint32_t *__restrict__ grp_cells, const uint32_t *__restrict__ seg_need)
 {
     // one warp per group, lane = segment of the group
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (g >= ngroups) return;
+    if (g >= cap_grp) return;
+    if (g >= cnt->ngroups) { if (lane == 0) grp_cells[g] = 0; return; }  // rows behind the last group count nothing
     const uint32_t t = upper_bound_dev(trk_grp_base, n_tracks, g) - 1;
     const TrackDev &T = tracks[t];
     const uint32_t j = g - trk_grp_base[t];
@@ -564,8 +706,8 @@ __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tr
     if (lane < G.nseg) {
         const SegDev &S = segs[G.seg0 + lane];
         n_au = S.n_au;
-        // second attempt after an overflow: the frame counts are known
-        need = (S.flags & SEG_OVERFLOW) ? S.frames : n_au * T.au_nominal;
+        // (another attempt after a tile overflow: the frame counts the previous one found)
+        need = max(n_au * T.au_nominal, seg_need[G.seg0 + lane]);
     }
     const uint32_t cap = __reduce_max_sync(0xFFFFFFFFu, need), most = __reduce_max_sync(0xFFFFFFFFu, n_au);
     if (lane) return;
@@ -573,31 +715,30 @@ __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tr
     G.tile_off = 0; G.byp_off = 0;
     groups[g] = G;
     grp_cells[g] = cap * T.channels;
-    grp_chunks[g] = (cap + 31) / 32;
-    atomicMax(max_au, most);
-    atomicMax(max_au + 1, (cap + 31) / 32);              // most 32-frame chunks in a group
+    atomicMax(&cnt->max_au, most);
+    atomicMax(&cnt->max_chunks, (cap + 31) / 32);        // most 32-frame chunks in a group
 }
 
-__global__ void k_group_offsets(GroupDev *__restrict__ groups, uint32_t ngroups, const uint64_t *__restrict__ cell_base)
+__global__ void k_group_offsets(GroupDev *__restrict__ groups, const DecCounts *__restrict__ cnt, const uint64_t *__restrict__ cell_base)
 {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ngroups) return;
+    if (g >= cnt->ngroups) return;
     groups[g].tile_off = cell_base[g] * DVDA_LANES;
     groups[g].byp_off = cell_base[g] * DVDA_LANES;
 }
 
 int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_grp_base, const SegDev *segs,
-                       GroupDev *groups, uint32_t ngroups, uint32_t *grp_cells, uint32_t *grp_chunks, uint32_t *max_au, cudaStream_t s)
+                       GroupDev *groups, uint32_t cap_grp, DecCounts *cnt, uint32_t *grp_cells, const uint32_t *seg_need, cudaStream_t s)
 {
-    if (!ngroups) return 0;
-    LAUNCH(k_group_setup, div_up_u32((uint64_t)ngroups * 32, 128), 128, 0, s, tracks, n_tracks, trk_grp_base, segs, groups, ngroups, grp_cells, grp_chunks, max_au);
+    if (!cap_grp) return 0;
+    LAUNCH(k_group_setup, div_up_u32((uint64_t)cap_grp * 32, 128), 128, 0, s, tracks, n_tracks, trk_grp_base, segs, groups, cap_grp, cnt, grp_cells, seg_need);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int launch_group_offsets(GroupDev *groups, uint32_t ngroups, const uint64_t *cell_base, cudaStream_t s)
+int launch_group_offsets(GroupDev *groups, uint32_t cap_grp, const DecCounts *cnt, const uint64_t *cell_base, cudaStream_t s)
 {
-    if (!ngroups) return 0;
-    LAUNCH(k_group_offsets, div_up_u32(ngroups, 128), 128, 0, s, groups, ngroups, cell_base);
+    if (!cap_grp) return 0;
+    LAUNCH(k_group_offsets, div_up_u32(cap_grp, 128), 128, 0, s, groups, cnt, cell_base);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

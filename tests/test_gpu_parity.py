@@ -16,22 +16,18 @@ GOLDEN = json.load(open(os.path.join(HERE, "golden", "catalog_golden.json")))
 DISCS = sorted(catalog.discs().keys())
 
 
-@pytest.fixture(scope="module", params=["three-pass", "fused", "single-pass"])
+@pytest.fixture(scope="module", params=["three-pass", "single-pass"])
 def engine(pkg, request):
-    """Every test runs against the three MLP decode paths: the three-pass path with the complete
-    decoder as its fall-back (default), the header passes + the fused entropy / filter / output
-    pass (DVDAGPU_FUSED=1), and the complete single-pass decoder alone (DVDAGPU_SINGLE_PASS=1)."""
+    """Every test runs against both MLP decode paths: the access-unit-parallel three-pass
+    path with the complete decoder as its fall-back (default), and the complete single-pass
+    decoder alone (DVDAGPU_SINGLE_PASS=1)."""
     os.environ.pop("DVDAGPU_SINGLE_PASS", None)
-    os.environ.pop("DVDAGPU_FUSED", None)
     if request.param == "single-pass":
         os.environ["DVDAGPU_SINGLE_PASS"] = "1"
-    elif request.param == "fused":
-        os.environ["DVDAGPU_FUSED"] = "1"
     e = pkg.Engine(0)
     yield e
     e.close()
     os.environ.pop("DVDAGPU_SINGLE_PASS", None)
-    os.environ.pop("DVDAGPU_FUSED", None)
 
 
 def check_track(oracle, eng, res, sectors, g, label):

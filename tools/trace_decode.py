@@ -9,11 +9,11 @@ for p in (ROOT, os.path.join(ROOT, "gen"), os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 import numpy as np, torch
 import dvda_gen as g, oracle
-import bench
+import workloads, bench
 pkg = importlib.import_module("libdvd-audio_b200")
 secs = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 config = sys.argv[2] if len(sys.argv) > 2 else "c2"
-titles, name, rate, ch = bench.workload_spec(g, config, secs, 1002)
+titles, name, rate, ch = workloads.spec(config, secs)
 d = "/dev/shm/trace_disc"; shutil.rmtree(d, ignore_errors=True)
 info = g.make_disc(d, titles)
 aob = oracle.read_aobs(d); shutil.rmtree(d)
