@@ -391,15 +391,23 @@ def measure(pkg, torch, eng, stream, disc_dir, config, steps, warmup, dist=None,
     e0.record(stream)
     for _ in range(steps):
         eng.decode_device(dev_in.data_ptr(), n_sectors, tracks)
+        launches += eng.stats()["launches"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # the same steps once more with the engine's per-kernel events switched on (they cost a step a
+    # few hundredths of a millisecond, so the figure above is taken without them): the kernel times
+    # behind `roofline` and `kernel_ms_per_step`
+    eng.set_profiling(True)
+    for _ in range(steps):
+        eng.decode_device(dev_in.data_ptr(), n_sectors, tracks)
         st = eng.stats()
-        launches += st["launches"]
         for k, v in st["kernel_ms"].items():
             kernel_ms[k] = kernel_ms.get(k, 0.0) + v
         for k in stage_ms:
             stage_ms[k] += st[k]
-    e1.record(stream)
+    eng.set_profiling(False)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
 
     # ---- timed: end to end through the C ABI with host buffers
     if dist:
@@ -715,11 +723,17 @@ def run_sharded(args, pkg, torch, g, workloads, dist, rank, world, local_rank, e
         for _ in range(args.steps):
             if descs:
                 eng.decode_device(dev_in.data_ptr(), n_sectors, descs)
-                st = eng.stats()
-                launches += st["launches"]
-                for k, v in st["kernel_ms"].items():
-                    kernel_ms[k] = kernel_ms.get(k, 0.0) + v
+                launches += eng.stats()["launches"]
         e1.record(stream)
+        torch.cuda.synchronize()
+        # (once more with the engine's per-kernel events on: the kernel times of the line)
+        eng.set_profiling(True)
+        for _ in range(args.steps):
+            if descs:
+                eng.decode_device(dev_in.data_ptr(), n_sectors, descs)
+                for k, v in eng.stats()["kernel_ms"].items():
+                    kernel_ms[k] = kernel_ms.get(k, 0.0) + v
+        eng.set_profiling(False)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
 

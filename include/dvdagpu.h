@@ -82,7 +82,9 @@ typedef struct {
     uint64_t pcm_offset;        /* first sample of the track in the engine's PCM buffer (in int32 units) */
 } dvdagpu_track_result;
 
-/* per-stage device times of the last decode, milliseconds (CUDA events) */
+/* per-stage device times of the last decode, milliseconds (CUDA events).  The times are only
+ * taken with profiling switched on (dvdagpu_set_profiling): the events cost a decode a few
+ * microseconds each, tens of microseconds while bulk copies run on the PCIe link. */
 typedef struct {
     float demux_ms;             /* sector scan + packet tables + elementary-stream gather */
     float index_ms;             /* sync search, access-unit chase, segment table */
@@ -174,6 +176,8 @@ void *dvdagpu_host_alloc(size_t bytes);
 void dvdagpu_host_free(void *p);
 
 int dvdagpu_get_stats(dvdagpu_ctx *ctx, dvdagpu_stats *out);
+/* per-stage and per-kernel CUDA-event timing of the following decodes on / off (default off) */
+int dvdagpu_set_profiling(dvdagpu_ctx *ctx, int on);
 
 /* message for the last failure on this thread ("" if none) */
 const char *dvdagpu_last_error(void);

@@ -33,7 +33,7 @@ ENGINE_SYMBOLS = [
     "dvdagpu_device_count", "dvdagpu_create", "dvdagpu_destroy", "dvdagpu_set_stream",
     "dvdagpu_decode_host", "dvdagpu_decode_device", "dvdagpu_decode_track_pipelined",
     "dvdagpu_fetch", "dvdagpu_pcm_device",
-    "dvdagpu_host_alloc", "dvdagpu_host_free", "dvdagpu_get_stats", "dvdagpu_last_error",
+    "dvdagpu_host_alloc", "dvdagpu_host_free", "dvdagpu_get_stats", "dvdagpu_set_profiling", "dvdagpu_last_error",
 ]
 # every function include/dvd-audio.h declares
 API_SYMBOLS = [
@@ -108,6 +108,7 @@ def engine_lib():
         L.dvdagpu_host_alloc.argtypes = [ctypes.c_size_t]
         L.dvdagpu_host_free.argtypes = [ctypes.c_void_p]
         L.dvdagpu_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+        L.dvdagpu_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.dvdagpu_last_error.restype = ctypes.c_char_p
         _engine = L
     return _engine
@@ -232,6 +233,10 @@ class Engine:
         n = ctypes.c_uint64()
         p = self.lib.dvdagpu_pcm_device(self.ctx, ctypes.byref(n))
         return p, n.value
+
+    def set_profiling(self, on):
+        """Per-stage / per-kernel CUDA-event times in stats() for the following decodes."""
+        self.lib.dvdagpu_set_profiling(self.ctx, 1 if on else 0)
 
     def stats(self):
         s = Stats()

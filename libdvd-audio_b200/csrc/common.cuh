@@ -251,8 +251,21 @@ void trace_mark(const char *what, cudaStream_t s);
     do {                                                                       \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);            \
         g_launch_count++;                                                      \
-        if (g_trace_on) trace_mark(#kernel, (stream));                         \
+        if (g_trace_on && !g_capturing) trace_mark(#kernel, (stream));         \
     } while (0)
+
+// timing events: inside a stream capture they are recorded as external events (readable after
+// the graph has run), outside as plain ones
+// Only with profiling switched on (dvdagpu_set_profiling): a timing event is a small write to host
+// memory in the middle of the launch sequence, and while bulk copies run on the link each of
+// them holds the stream up for tens of microseconds.
+extern thread_local bool g_capturing;
+extern thread_local bool g_profiling;
+static inline cudaError_t record_timing(cudaEvent_t e, cudaStream_t s)
+{
+    if (!g_profiling) return cudaSuccess;
+    return cudaEventRecordWithFlags(e, s, g_capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
 
 static inline uint32_t div_up_u32(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 

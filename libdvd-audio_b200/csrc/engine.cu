@@ -26,6 +26,8 @@
 #define MAP_BYTES (1u << 20)      // mapped pinned staging area for small transfers
 
 thread_local uint32_t g_launch_count = 0;
+thread_local bool g_capturing = false;
+thread_local bool g_profiling = false;
 
 // ---- DVDAGPU_TRACE=1: time line of one decode (debug aid, not on by default) ---------------
 thread_local bool g_trace_on = false;
@@ -123,6 +125,18 @@ struct DecShape {
     bool any_pcm = true, any_mlp = true, windowed = true;
 };
 
+// one decode in flight on a context
+struct DecJob {
+    const uint8_t *d_sectors = nullptr;
+    uint32_t n_sectors = 0, n_tracks = 0, nslots = 2;
+    std::vector<dvdagpu_track_desc> descs;
+    std::vector<uint32_t> order;
+    DecShape sh;
+    int attempt = 0;
+    bool use_fast = true, small_tables = false, pcm_small_seen = false, active = false;
+    uint32_t launches = 0;                    // kernels launched for this decode (all attempts)
+};
+
 struct dvdagpu_ctx {
     int device;
     cudaStream_t own_stream;
@@ -137,6 +151,14 @@ struct dvdagpu_ctx {
     uint32_t last_sectors = 0, last_tracks = 0;
     bool have_last = false;
     uint32_t seg_need_cap = 0;                // rows of the seg_need table that has been cleared
+    bool profiling = false;                   // per-stage / per-kernel CUDA events (dvdagpu_set_profiling)
+    DecJob job;                               // the decode in flight (decode_begin .. decode_end)
+    cudaEvent_t job_done = nullptr;
+    uint8_t *hback = nullptr, *dback = nullptr;   // mapped pinned memory the read-back of a decode lands in
+    size_t back_bytes = 0;
+    dvdagpu_ctx *peer = nullptr;              // a second context on the same device (pipelined path: two parts decode at once)
+    cudaGraphExec_t graph_exec = nullptr;     // the decode sequence as an executable graph (updated in place from decode to decode)
+    bool graph_ok = true, warmed = false;
     uint32_t scan_tmp_gen = 0;                // allocation of the scan buffer that has been cleared
     cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
     int pcm_slot;                             // which PCM buffer the next decode writes
@@ -241,6 +263,7 @@ extern "C" dvdagpu_ctx *dvdagpu_create(int device)
     cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_least);
     cudaStreamCreateWithPriority(&c->aux_stream_hi, cudaStreamNonBlocking, prio_greatest);
     for (auto &e : c->aux_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->job_done, cudaEventDisableTiming);
     for (auto &e : c->pev) { cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming); }
     for (auto &e : c->ev) cudaEventCreate(&e);
     for (auto &k : c->kev) { cudaEventCreate(&k[0]); cudaEventCreate(&k[1]); }
@@ -258,6 +281,10 @@ extern "C" void dvdagpu_destroy(dvdagpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->peer) { dvdagpu_destroy(c->peer); c->peer = nullptr; }
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->job_done) cudaEventDestroy(c->job_done);
+    if (c->hback) cudaFreeHost(c->hback);
     for (auto &b : c->buf) b.release();
     for (auto &e : c->ev) cudaEventDestroy(e);
     for (auto &k : c->kev) { cudaEventDestroy(k[0]); cudaEventDestroy(k[1]); }
@@ -276,6 +303,13 @@ extern "C" int dvdagpu_set_stream(dvdagpu_ctx *c, void *cuda_stream)
 {
     if (!c) return -1;
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return 0;
+}
+
+extern "C" int dvdagpu_set_profiling(dvdagpu_ctx *c, int on)
+{
+    if (!c) return -1;
+    c->profiling = on != 0;
     return 0;
 }
 
@@ -323,9 +357,9 @@ extern "C" int dvdagpu_fetch(dvdagpu_ctx *c, uint64_t offset, uint64_t count, in
 // device time of one kernel (or a short run of kernels) into stats.kernel_ms[id]
 #define TIMED(id, expr)                                                        \
     do {                                                                       \
-        CUDA_TRY(cudaEventRecord(c->kev[id][0], s));                           \
+        CUDA_TRY(record_timing(c->kev[id][0], s));                             \
         TRY(expr);                                                             \
-        CUDA_TRY(cudaEventRecord(c->kev[id][1], s));                           \
+        CUDA_TRY(record_timing(c->kev[id][1], s));                             \
         c->kev_used[id] = true;                                                \
     } while (0)
 
@@ -336,22 +370,6 @@ extern "C" int dvdagpu_fetch(dvdagpu_ctx *c, uint64_t offset, uint64_t count, in
 __global__ void k_copy_words(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint32_t nwords)
 {
     for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
-}
-
-// device -> host, synchronous
-static int small_d2h(dvdagpu_ctx *c, void *host, const void *dev, size_t bytes)
-{
-    if (bytes > MAP_BYTES / 2 || (bytes & 3)) {
-        CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        return 0;
-    }
-    // the upper half of the staging area is for read-backs
-    LAUNCH(k_copy_words, 1, 256, 0, c->stream, (uint32_t *)(c->dmap + MAP_BYTES / 2), (const uint32_t *)dev, (uint32_t)(bytes / 4));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    trace_host("  (host has the read-back)");
-    memcpy(host, c->hmap + MAP_BYTES / 2, bytes);
-    return 0;
 }
 
 // host -> device, asynchronous (the staging bytes stay untouched until the next decode).
@@ -398,31 +416,6 @@ static int small_h2d(dvdagpu_ctx *c, void *dev, const void *host, size_t bytes)
     return flush_h2d(c);
 }
 
-// several read-backs, one round trip (each one costs tens of microseconds, more while bulk copies run)
-static int small_d2h_multi(dvdagpu_ctx *c, int n, void *const host[], const void *const dev[], const size_t bytes[])
-{
-    size_t off[H2D_BATCH], total = 0;
-    bool ok = n <= H2D_BATCH;
-    for (int i = 0; i < n && ok; i++) {
-        off[i] = total;
-        total += (bytes[i] + 15) & ~(size_t)15;
-        if (bytes[i] & 3) ok = false;
-    }
-    if (!ok || total > MAP_BYTES / 2) {
-        for (int i = 0; i < n; i++) TRY(small_d2h(c, host[i], dev[i], bytes[i]));
-        return 0;
-    }
-    CopyBatch b;
-    b.n = (uint32_t)n;
-    for (int i = 0; i < n; i++) {
-        b.dst[i] = (uint32_t *)(c->dmap + MAP_BYTES / 2 + off[i]); b.src[i] = (const uint32_t *)dev[i]; b.nwords[i] = (uint32_t)(bytes[i] / 4);
-    }
-    LAUNCH(k_copy_multi, 1, 256, 0, c->stream, b);
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    trace_host("  (host has the read-backs)");
-    for (int i = 0; i < n; i++) memcpy(host[i], c->hmap + MAP_BYTES / 2 + off[i], bytes[i]);
-    return 0;
-}
 // Where every track's samples start in the output buffer (16-byte aligned tracks: vector and
 // bulk stores), computed on the device so that the output pass can be queued without a round
 // trip through the host.  `capacity`: samples the buffer was sized for in advance.
@@ -441,6 +434,18 @@ __global__ void __launch_bounds__(OB_THREADS) k_track_out_base(TrackDev *tracks,
         carry += total;
     }
     if (threadIdx.x == 0 && carry > capacity) atomicOr(status, STATUS_PCM_SMALL);
+}
+
+#define TRACKS_BY_ARG 192
+struct TrackArgs { uint32_t t[TRACKS_BY_ARG][4]; };
+__global__ void k_tracks_from_args(TrackDev *__restrict__ tracks, uint32_t n_tracks, const __grid_constant__ TrackArgs a)
+{
+    for (uint32_t i = threadIdx.x; i < n_tracks; i += blockDim.x) {
+        TrackDev T;
+        memset(&T, 0, sizeof T);
+        T.first_sector = a.t[i][0]; T.last_sector = a.t[i][1]; T.pts_length = a.t[i][2]; T.cont = a.t[i][3];
+        tracks[i] = T;
+    }
 }
 
 // ---- what the launches of a decode are sized for ------------------------------------------
@@ -486,24 +491,31 @@ static void shape_from_last(DecShape &sh, const DecCounts &k, const DecShape &us
     (void)used;
 }
 
-static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n_sectors64,
-                            uint32_t n_tracks, const dvdagpu_track_desc *descs, dvdagpu_track_result *results)
+static int decode_enqueue(dvdagpu_ctx *c);
+
+// One decode = decode_begin (sizes the tables, enqueues everything) + decode_end (waits for it,
+// reads counts, status and the track table, repeats the decode if a table was too small, fills the
+// results).  Between the two the host is free: the pipelined path starts the next part's decode on
+// the context's peer while this one runs.
+static int decode_begin(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n_sectors64,
+                        uint32_t n_tracks, const dvdagpu_track_desc *descs)
 {
     g_error[0] = 0;
-    g_launch_count = 0;
     g_trace_on = getenv("DVDAGPU_TRACE") != nullptr;
     g_trace.n = 0;
     if (g_trace_on) trace_mark("decode begins", c->stream);
-    cudaStream_t s = c->stream;
     if (n_sectors64 == 0 || n_sectors64 > 0x7FFFFFFFull) { dvdagpu_set_error("bad sector count"); return -1; }
+    DecJob &J = c->job;
+    J.n_tracks = n_tracks; J.active = false;
     if (!n_tracks) { c->pcm_samples = 0; return 0; }
     const uint32_t n_sectors = (uint32_t)n_sectors64;
     memset(&c->stats, 0, sizeof c->stats);
     memset(c->kev_used, 0, sizeof c->kev_used);
-    CUDA_TRY(cudaEventRecord(c->ev[0], s));
+    g_profiling = c->profiling || getenv("DVDAGPU_PROFILE") != nullptr;
 
     // tracks in sector order (the kernels binary-search them); results go back in caller order
-    std::vector<uint32_t> order(n_tracks);
+    std::vector<uint32_t> &order = J.order;
+    order.resize(n_tracks);
     for (uint32_t i = 0; i < n_tracks; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return descs[a].first_sector < descs[b].first_sector; });
     std::vector<TrackDev> &ht = c->h_tracks;
@@ -518,21 +530,40 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
     // (test hook: DVDAGPU_SYNC_SLOTS=0 sends every chunk with a match through the re-search path)
     const uint32_t nslots = getenv("DVDAGPU_SYNC_SLOTS") ? (uint32_t)atoi(getenv("DVDAGPU_SYNC_SLOTS")) : 2u;
 
-    DecShape sh;
+    DecShape &sh = J.sh;
+    sh = DecShape();
     const bool similar = c->have_last && !small_tables && c->last_tracks == n_tracks &&
                          n_sectors >= c->last_sectors / 2 && n_sectors / 2 <= c->last_sectors;
     if (similar) shape_from_last(sh, c->last, c->last_shape, c->last_sectors, n_sectors, n_tracks);
     else shape_from_input(sh, n_sectors, n_tracks);
     if (small_tables) { sh.rows = sh.sync = sh.seg = sh.grp = sh.au = sh.cells = 1; sh.max_au = 1; sh.out_warps = 8; sh.pcm_fixed = 1; }
+    J.d_sectors = d_sectors; J.n_sectors = n_sectors;
+    J.descs.assign(descs, descs + n_tracks);
+    J.use_fast = use_fast; J.small_tables = small_tables; J.nslots = nslots;
+    J.attempt = 0; J.pcm_small_seen = false; J.active = true; J.launches = 0;
+    return decode_enqueue(c);
+}
+
+// everything of one attempt, asynchronous on the context's stream(s), up to the read-back
+static int decode_enqueue(dvdagpu_ctx *c)
+{
+    DecJob &J = c->job;
+    cudaStream_t s = c->stream;
+    const uint8_t *d_sectors = J.d_sectors;
+    const uint32_t n_sectors = J.n_sectors, n_tracks = J.n_tracks, nslots = J.nslots;
+    const dvdagpu_track_desc *descs = J.descs.data();
+    const std::vector<uint32_t> &order = J.order;
+    std::vector<TrackDev> &ht = c->h_tracks;
+    const bool use_fast = J.use_fast, small_tables = J.small_tables, pcm_small_seen = J.pcm_small_seen;
+    const int attempt = J.attempt;
+    DecShape &sh = J.sh;
     const uint64_t es_cap = (uint64_t)n_sectors * DVDA_SECTOR;
     const uint32_t chunks_cap = div_up_u32(es_cap, SYNC_CHUNK);
-
-    DecCounts k;
-    uint32_t status = 0;
     MlpTables m;
-    uint64_t total_samples = 0;
-    bool pcm_small_seen = false;
-    for (int attempt = 0;; attempt++) {
+    g_profiling = c->profiling || getenv("DVDAGPU_PROFILE") != nullptr;
+    const uint32_t launches_before = g_launch_count;
+    struct CountLaunches { DecJob &J; uint32_t before; ~CountLaunches() { J.launches += g_launch_count - before; } } count_launches = {J, launches_before};
+    {
         if (attempt == 16) { dvdagpu_set_error("internal: the tables keep overflowing"); return -1; }
         c->map_used = 0;
         g_h2d_batch.n = 0;
@@ -597,6 +628,21 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         const uint64_t pcm_capacity = small_tables && !pcm_small_seen ? 1 : cells * DVDA_LANES + sh.pcm_fixed;
         ENSURE(pcm_buf, (pcm_capacity + 64) * sizeof(int32_t));
 
+        // ---------------- from here to the read-back everything is asynchronous on the stream(s): the
+        // sequence is captured into a CUDA graph and launched as one (the first decode of a context
+        // runs it directly: kernel attributes are set on first use).  A captured decode costs the
+        // GPU's front end one submission instead of forty: while bulk copies saturate the link, every
+        // separate launch waits its turn on it.
+        const bool graph = c->graph_ok && c->warmed && !g_trace_on && getenv("DVDAGPU_NO_GRAPH") == nullptr;
+        if (graph) {
+            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); c->graph_ok = false; }
+            else g_capturing = true;
+        }
+        struct CaptureGuard {                                // (an error return inside the capture must end it)
+            cudaStream_t s;
+            ~CaptureGuard() { if (g_capturing) { cudaGraph_t g = nullptr; cudaStreamEndCapture(s, &g); if (g) cudaGraphDestroy(g); g_capturing = false; cudaGetLastError(); } }
+        } capture_guard = {s};
+        CUDA_TRY(record_timing(c->ev[0], s));
         void *tmp = c->buf[B_SCAN_TMP].p;
         const size_t tmp_bytes = c->buf[B_SCAN_TMP].cap;
         if (c->scan_tmp_gen != c->buf[B_SCAN_TMP].gen) {
@@ -642,7 +688,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         }
         uint8_t *es = c->buf[B_ES].as<uint8_t>();
         TIMED(DVDAGPU_K_ES_GATHER, launch_es_gather(d_sectors, pt, rows, pk_es, es, cnt, s));
-        CUDA_TRY(cudaEventRecord(c->ev[1], s));
+        CUDA_TRY(record_timing(c->ev[1], s));
 
         // ---------------- index
         uint16_t *sync_slots = c->buf[B_SYNC_SLOTS].as<uint16_t>();
@@ -657,7 +703,16 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             TRY(launch_sync_fill(es, cnt, chunks_cap, cnt_raw, sync_slots, nslots, base_raw, base_valid, raw, cap_sync, valid, cap_sync, s));
         }
         TrackDev *d_tracks = c->buf[B_TRACKS].as<TrackDev>();
-        TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
+        // The track table's inputs.  Up to TRACKS_BY_ARG tracks travel as kernel arguments: no load
+        // from host memory stands in the decode chain (while bulk copies run on the link such a load
+        // waits behind them for a long time).
+        if (n_tracks <= TRACKS_BY_ARG) {
+            TrackArgs ta0;
+            for (uint32_t i = 0; i < n_tracks; i++) { ta0.t[i][0] = ht[i].first_sector; ta0.t[i][1] = ht[i].last_sector; ta0.t[i][2] = ht[i].pts_length; ta0.t[i][3] = ht[i].cont; }
+            LAUNCH(k_tracks_from_args, 1, 128, 0, s, d_tracks, n_tracks, ta0);
+        } else {
+            TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
+        }
         TrackSetupArgs ta;
         ta.es = es; ta.cnt = cnt; ta.n_sectors = n_sectors; ta.sec_base = sec_base; ta.bad_prefix = bad_prefix;
         ta.pt = pt; ta.pk_es = pk_es; ta.pk_pf = pk_pf; ta.pk_nonmlp = nm_prefix; ta.pk_pcm_stop = stop_prefix;
@@ -715,7 +770,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             TRY(launch_plan_check(cnt, lim, s));
             TRY(launch_au_chase(es, m.segs, cap_seg, cnt, d_tracks, seg_nau, m.au_pos, m.au_seg, seg_au_base, au_noted, 1, s));
             TRY(launch_yield(m, rows, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), s));
-            CUDA_TRY(cudaEventRecord(c->ev[2], s));
+            CUDA_TRY(record_timing(c->ev[2], s));
 
             // ---------------- decode
             // Parity / CRC-8 on a second stream, beside the group set-up and the header passes.  Small
@@ -727,9 +782,9 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             cudaStream_t chk_stream = (sh.windowed || s != c->own_stream) ? c->aux_stream : c->aux_stream_hi;
             CUDA_TRY(cudaEventRecord(c->aux_ev[0], s));
             CUDA_TRY(cudaStreamWaitEvent(chk_stream, c->aux_ev[0], 0));
-            CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][0], chk_stream));
+            CUDA_TRY(record_timing(c->kev[DVDAGPU_K_CHECKDATA][0], chk_stream));
             TRY(launch_checkdata(m, seg_au_base, sh.windowed, chk_stream));
-            CUDA_TRY(cudaEventRecord(c->kev[DVDAGPU_K_CHECKDATA][1], chk_stream));
+            CUDA_TRY(record_timing(c->kev[DVDAGPU_K_CHECKDATA][1], chk_stream));
             c->kev_used[DVDAGPU_K_CHECKDATA] = true;
             CUDA_TRY(cudaEventRecord(c->aux_ev[1], chk_stream));
             uint32_t *seg_frames = c->buf[B_SEG_FRAMES].as<uint32_t>();
@@ -757,12 +812,12 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             TRY(launch_track_finalize(m, seg_frame_scan, d_status, s));
         } else {
             TRY(launch_plan_check(cnt, lim, s));
-            CUDA_TRY(cudaEventRecord(c->ev[2], s));
+            CUDA_TRY(record_timing(c->ev[2], s));
         }
         // The output buffer was sized before the frame counts are known (every MLP sample has a place
         // in the tiles, so the tiles' size bounds them); the tracks' places in it are computed on the device.
         LAUNCH(k_track_out_base, 1, OB_THREADS, 0, s, d_tracks, n_tracks, d_status, pcm_capacity);
-        CUDA_TRY(cudaEventRecord(c->ev[3], s));
+        CUDA_TRY(record_timing(c->ev[3], s));
 
         // ---------------- output
         if (sh.any_mlp) {
@@ -770,15 +825,70 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             TIMED(DVDAGPU_K_REMATRIX, launch_rematrix(m, s));
         }
         if (sh.any_pcm) TIMED(DVDAGPU_K_PCM_UNPACK, launch_pcm_unpack(d_sectors, pt, rows, cnt, d_status, pk_pf, d_tracks, trk_pk_lo, n_tracks, m.pcm, s));
-        CUDA_TRY(cudaEventRecord(c->ev[4], s));
+        CUDA_TRY(record_timing(c->ev[4], s));
 
-        // ---------------- the one round trip: counts, status, track table
-        {
-            void *const host[3] = {&k, &status, ht.data()};
-            const void *const dev[3] = {cnt, d_status, d_tracks};
-            const size_t bytes[3] = {sizeof(DecCounts), 4, n_tracks * sizeof(TrackDev)};
-            TRY(small_d2h_multi(c, 3, host, dev, bytes));
+        if (g_capturing) {
+            cudaGraph_t captured = nullptr;
+            g_capturing = false;
+            CUDA_TRY(cudaStreamEndCapture(s, &captured));
+            bool ready = false;
+            if (c->graph_exec) {
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(c->graph_exec, captured, &info) == cudaSuccess) ready = true;
+                else { cudaGetLastError(); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+            }
+            if (!ready) {
+                const cudaError_t e = cudaGraphInstantiate(&c->graph_exec, captured, 0);
+                if (e != cudaSuccess) { cudaGraphDestroy(captured); dvdagpu_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return -1; }
+            }
+            cudaGraphDestroy(captured);
+            CUDA_TRY(cudaGraphLaunch(c->graph_exec, s));
         }
+        c->warmed = true;
+        // ---------------- the read-back of the one round trip: counts, status, track table go to
+        // mapped host memory behind everything else; decode_end() waits for the event
+        {
+            const size_t need = sizeof(DecCounts) + 64 + (size_t)n_tracks * sizeof(TrackDev);
+            if (need > c->back_bytes) {
+                if (c->hback) cudaFreeHost(c->hback);
+                c->hback = c->dback = nullptr; c->back_bytes = 0;
+                CUDA_TRY(cudaHostAlloc((void **)&c->hback, need + need / 2, cudaHostAllocMapped));
+                CUDA_TRY(cudaHostGetDevicePointer((void **)&c->dback, c->hback, 0));
+                c->back_bytes = need + need / 2;
+            }
+            CopyBatch bb;
+            bb.n = 3;
+            bb.dst[0] = (uint32_t *)c->dback; bb.src[0] = (const uint32_t *)cnt; bb.nwords[0] = sizeof(DecCounts) / 4;
+            bb.dst[1] = (uint32_t *)(c->dback + sizeof(DecCounts)); bb.src[1] = d_status; bb.nwords[1] = 1;
+            bb.dst[2] = (uint32_t *)(c->dback + sizeof(DecCounts) + 64); bb.src[2] = (const uint32_t *)d_tracks; bb.nwords[2] = (uint32_t)(n_tracks * sizeof(TrackDev) / 4);
+            LAUNCH(k_copy_multi, 1, 256, 0, s, bb);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(c->job_done, s));
+    }
+    return 0;
+}
+
+// waits for the decode begun by decode_begin, repeats it if a table was too small, fills the results
+static int decode_end(dvdagpu_ctx *c, dvdagpu_track_result *results)
+{
+    DecJob &J = c->job;
+    const uint32_t n_tracks = J.n_tracks;
+    if (!n_tracks) return 0;
+    if (!J.active) { dvdagpu_set_error("internal: no decode in flight"); return -1; }
+    const uint32_t n_sectors = J.n_sectors;
+    const std::vector<uint32_t> &order = J.order;
+    std::vector<TrackDev> &ht = c->h_tracks;
+    DecShape &sh = J.sh;
+    DecCounts k;
+    uint32_t status = 0;
+    uint64_t total_samples = 0;
+    for (;;) {
+        const int attempt = J.attempt;
+        CUDA_TRY(cudaEventSynchronize(c->job_done));
+        memcpy(&k, c->hback, sizeof(DecCounts));
+        memcpy(&status, c->hback + sizeof(DecCounts), 4);
+        memcpy(ht.data(), c->hback + sizeof(DecCounts) + 64, (size_t)n_tracks * sizeof(TrackDev));
         if (g_trace_on) { trace_host("decode done"); trace_dump(); g_trace_on = false; }
         if (getenv("DVDAGPU_DEBUG")) {
             fprintf(stderr, "[dvdagpu] attempt %d: sectors=%u packets=%llu es=%llu raw=%llu valid=%llu segs=%u groups=%u aus=%llu cells=%llu max_au=%u overflow=%x status=%x\n",
@@ -814,13 +924,14 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
             sh.any_pcm = sh.any_mlp = true; sh.nss = 2;
         }
         if (status & STATUS_PCM_SMALL) {
-            pcm_small_seen = true;
+            J.pcm_small_seen = true;
             uint64_t want = 64;
             for (uint32_t i = 0; i < n_tracks; i++) if (ht[i].status == 0) want += ht[i].frames * ht[i].channels + 4;
             sh.pcm_fixed = std::max<uint64_t>(sh.pcm_fixed, want);   // (on top of what the tiles bound)
         }
+        J.attempt++;
+        TRY(decode_enqueue(c));
     }
-
     // ---------------- results
     total_samples = 0;
     for (uint32_t i = 0; i < n_tracks; i++) {
@@ -829,6 +940,7 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         if (ht[i].status == 0) total_samples += ht[i].frames * ht[i].channels;
     }
     c->pcm_samples = total_samples;
+    J.active = false;
     c->last = k; c->last_shape = sh; c->last_sectors = n_sectors; c->last_tracks = n_tracks; c->have_last = true;
     uint64_t es_used = 0;
     for (uint32_t i = 0; i < n_tracks; i++) {
@@ -843,21 +955,33 @@ static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n
         R.frames = T.frames; R.pcm_offset = T.out_base; R.truncated = T.truncated; R.stopped = T.stopped;
         if (T.codec == 1) es_used += T.es_end - T.es_start;
     }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.demux_ms = ms;
-    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stats.index_ms = ms;
-    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.decode_ms = ms;
-    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.output_ms = ms;
-    cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); c->stats.total_ms = ms;
-    for (int kk = 0; kk < 16; kk++) {
-        if (c->kev_used[kk] && cudaEventElapsedTime(&ms, c->kev[kk][0], c->kev[kk][1]) == cudaSuccess) c->stats.kernel_ms[kk] = ms;
+    g_profiling = c->profiling || getenv("DVDAGPU_PROFILE") != nullptr;
+    if (g_profiling) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.demux_ms = ms;
+        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stats.index_ms = ms;
+        cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.decode_ms = ms;
+        cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.output_ms = ms;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); c->stats.total_ms = ms;
+        for (int kk = 0; kk < 16; kk++) {
+            if (c->kev_used[kk] && cudaEventElapsedTime(&ms, c->kev[kk][0], c->kev[kk][1]) == cudaSuccess) c->stats.kernel_ms[kk] = ms;
+        }
+        cudaGetLastError();
     }
-    c->stats.launches = g_launch_count;
+    c->stats.launches = J.launches;
     c->stats.segments = k.nseg;
     c->stats.access_units = k.nau;
     c->stats.es_bytes = es_used;
     c->stats.samples = total_samples;
     return 0;
+}
+
+
+static int decode_on_device(dvdagpu_ctx *c, const uint8_t *d_sectors, uint64_t n_sectors64,
+                            uint32_t n_tracks, const dvdagpu_track_desc *descs, dvdagpu_track_result *results)
+{
+    TRY(decode_begin(c, d_sectors, n_sectors64, n_tracks, descs));
+    return decode_end(c, results);
 }
 
 extern "C" int dvdagpu_decode_device(dvdagpu_ctx *c, const void *device_sectors, uint64_t n_sectors,
@@ -905,84 +1029,142 @@ extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sec
     CUDA_TRY(cudaSetDevice(c->device));
     const uint64_t first = track->first_sector;
     const uint64_t last = track->last_sector < n_sectors ? track->last_sector : n_sectors - 1;
-    if (!part_sectors) {
-        // a decode has a latency floor of a few milliseconds whatever its size, so few, large
-        // parts: about 75 MB of AOB each, between 2 and 8 of them
-        const uint64_t n = last >= first ? last - first + 1 : 0;
-        uint64_t parts = (n + 19000) / 38000;
-        parts = parts < 2 ? 2 : parts > 8 ? 8 : parts;
-        part_sectors = (uint32_t)((n + parts - 1) / parts);
-        if (part_sectors < 8192) part_sectors = 8192;
+    if (!part_sectors && getenv("DVDAGPU_PART_SECTORS")) part_sectors = (uint32_t)atoi(getenv("DVDAGPU_PART_SECTORS"));   // (tuning hook)
+    // Where the parts begin.  The download of the samples is the longest leg, so the parts are small
+    // enough for it to start early (a sixteenth of the track, at most 32 MB of AOB: the device
+    // buffers stay bounded however long the track is) and large enough for the latency floor of a
+    // decode — a chain of small dependent launches, about half a millisecond — not to outlast the
+    // download of the part before (two parts decode at once, see below).
+    std::vector<uint64_t> starts;
+    {
+        const uint64_t n = last >= first && first < n_sectors ? last - first + 1 : 0;
+        if (!part_sectors) part_sectors = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(n / 16, 8192), 16384);
+        if (n >= 2ull * part_sectors) for (uint64_t s0 = first; s0 <= last; s0 += part_sectors) starts.push_back(s0);
+        // (a last part of a few sectors would be all latency: the part before takes it)
+        if (starts.size() > 2 && last + 1 - starts.back() < part_sectors / 4) starts.pop_back();
     }
     const uint64_t margin = 64;
     dvdagpu_stats total_stats;
     memset(&total_stats, 0, sizeof total_stats);
 
-    bool fallback = first >= n_sectors || last < first || (last - first + 1) < 2ull * part_sectors;
+    bool fallback = starts.size() < 2;
     uint64_t total_samples = 0, total_frames = 0;
     dvdagpu_track_result merged;
     memset(&merged, 0, sizeof merged);
     if (!fallback) {
-        const uint32_t parts = (uint32_t)((last - first + 1 + part_sectors - 1) / part_sectors);
+        // Two contexts on the device take the parts in turn: a decode is a chain of dependent
+        // launches, most of them small, so two chains side by side cost little more than one, and
+        // while the host waits for part i - 1 part i is already running.
+        dvdagpu_ctx *X[2] = {c, c};
+        if (!getenv("DVDAGPU_PIPE_ONE_CONTEXT")) {
+            if (!c->peer) c->peer = dvdagpu_create(c->device);
+            if (c->peer) { X[1] = c->peer; c->peer->profiling = c->profiling; }
+        }
+        const bool two = X[1] != c;
+        const uint32_t parts = (uint32_t)starts.size();
         auto window = [&](uint32_t i, uint64_t &s0, uint64_t &len, uint64_t &e_rel) {
-            s0 = first + (uint64_t)i * part_sectors;
-            uint64_t e = s0 + part_sectors - 1;
-            if (e > last || i + 1 == parts) e = last;
+            s0 = starts[i];
+            const uint64_t e = i + 1 == parts ? last : starts[i + 1] - 1;
             uint64_t stop = (i + 1 == parts) ? n_sectors : e + 1 + margin;
             if (stop > n_sectors) stop = n_sectors;
             len = stop - s0;
             e_rel = e - s0;
         };
+        // part i: context i & 1 (with two contexts), sector / PCM slot of that context in turn
+        auto ctx_of = [&](uint32_t i) { return two ? X[i & 1] : c; };
+        auto slot_of = [&](uint32_t i) { return two ? (int)((i >> 1) & 1) : (int)(i & 1); };
+        const uint32_t reuse = two ? 4 : 2;                 // part i reuses the buffers of part i - reuse
+        // DVDAGPU_PIPE_TRACE=1: when every leg of every part began and ended (debug aid)
+        const bool ptrace = getenv("DVDAGPU_PIPE_TRACE") != nullptr;
+        std::vector<cudaEvent_t> tev;
+        std::vector<char> tkind;
+        auto tmark = [&](cudaStream_t st, char kind) { if (ptrace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); tkind.push_back(kind); } };
         auto upload = [&](uint32_t i) -> int {
             uint64_t s0, len, e_rel;
             window(i, s0, len, e_rel);
-            const int slot = i & 1, buf = slot ? B_SECTORS2 : B_SECTORS;
-            ENSURE(buf, len * DVDA_SECTOR + 256);
-            if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->h2d_stream, c->pev[1][slot], 0));   // part i-2 decoded
-            CUDA_TRY(cudaMemcpyAsync(c->buf[buf].p, sectors + s0 * DVDA_SECTOR, len * DVDA_SECTOR,
+            dvdagpu_ctx *x = ctx_of(i);
+            const int slot = slot_of(i), buf = slot ? B_SECTORS2 : B_SECTORS;
+            if (x->buf[buf].ensure(len * DVDA_SECTOR + 256)) return -1;
+            if (i >= reuse) CUDA_TRY(cudaStreamWaitEvent(c->h2d_stream, x->pev[1][slot], 0));   // part i - reuse decoded
+            tmark(c->h2d_stream, 'u');
+            CUDA_TRY(cudaMemcpyAsync(x->buf[buf].p, sectors + s0 * DVDA_SECTOR, len * DVDA_SECTOR,
                                      cudaMemcpyHostToDevice, c->h2d_stream));
-            CUDA_TRY(cudaEventRecord(c->pev[0][slot], c->h2d_stream));
+            CUDA_TRY(cudaEventRecord(x->pev[0][slot], c->h2d_stream));
+            tmark(c->h2d_stream, 'U');
             return 0;
         };
-        TRY(upload(0));
-        for (uint32_t i = 0; i < parts && !fallback; i++) {
-            if (i + 1 < parts) TRY(upload(i + 1));
+        auto begin = [&](uint32_t i) -> int {
             uint64_t s0, len, e_rel;
             window(i, s0, len, e_rel);
-            const int slot = i & 1;
-            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->pev[0][slot], 0));
-            if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->pev[2][slot], 0));       // PCM slot downloaded
-            c->pcm_slot = slot;
+            dvdagpu_ctx *x = ctx_of(i);
+            const int slot = slot_of(i);
+            CUDA_TRY(cudaStreamWaitEvent(x->stream, x->pev[0][slot], 0));
+            if (i >= reuse) CUDA_TRY(cudaStreamWaitEvent(x->stream, x->pev[2][slot], 0));       // PCM slot downloaded
+            x->pcm_slot = slot;
             dvdagpu_track_desc d = {0, (uint32_t)e_rel, track->pts_length,
                                     (i ? (uint32_t)DVDAGPU_PART_CONTINUES_PREVIOUS : (track->flags & 1u)) |
                                     (i + 1 < parts ? (uint32_t)DVDAGPU_PART_CONTINUED_BY_NEXT : (track->flags & 2u))};
+            tmark(x->stream, 'd');
+            return decode_begin(x, x->buf[slot ? B_SECTORS2 : B_SECTORS].as<uint8_t>(), len, 1, &d);
+        };
+        uint32_t begun = 0, ended = 0;
+        bool stop = false;                                   // the track ended inside a part: the parts behind are dropped
+        // waits for part i, queues its download; sets fallback / stop
+        auto end = [&](uint32_t i) -> int {
+            dvdagpu_ctx *x = ctx_of(i);
+            const int slot = slot_of(i);
             dvdagpu_track_result r;
-            TRY(decode_on_device(c, c->buf[slot ? B_SECTORS2 : B_SECTORS].as<uint8_t>(), len, 1, &d, &r));
-            CUDA_TRY(cudaEventRecord(c->pev[1][slot], c->stream));
-            add_stats(total_stats, c->stats);
+            TRY(decode_end(x, &r));
+            CUDA_TRY(cudaEventRecord(x->pev[1][slot], x->stream));
+            tmark(x->stream, 'D');
+            add_stats(total_stats, x->stats);
+            if (stop || fallback) return 0;                  // (drained only)
             // anything the parts cannot express: decode in one piece instead
             if (r.status != 0 || r.codec != 1 || r.stopped == 2 || (r.truncated && i + 1 < parts) ||
-                (i && (r.channels != merged.channels || r.sample_rate != merged.sample_rate))) { fallback = true; break; }
+                (i && (r.channels != merged.channels || r.sample_rate != merged.sample_rate))) { fallback = true; return 0; }
             if (i == 0) merged = r;
             const uint64_t n = r.frames * r.channels;
-            if (total_samples + n > pcm_capacity) {
-                cudaStreamSynchronize(c->d2h_stream);
-                dvdagpu_set_error("PCM buffer too small");
-                result->frames = 0;
-                return 3;
-            }
-            CUDA_TRY(cudaStreamWaitEvent(c->d2h_stream, c->pev[1][slot], 0));
-            if (n) CUDA_TRY(cudaMemcpyAsync(pcm_host + total_samples, c->buf[slot ? B_PCM2 : B_PCM].as<int32_t>() + r.pcm_offset,
+            if (total_samples + n > pcm_capacity) return 3;
+            tmark(c->d2h_stream, 'o');
+            if (n) CUDA_TRY(cudaMemcpyAsync(pcm_host + total_samples, x->buf[slot ? B_PCM2 : B_PCM].as<int32_t>() + r.pcm_offset,
                                             n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->d2h_stream));
-            CUDA_TRY(cudaEventRecord(c->pev[2][slot], c->d2h_stream));
+            CUDA_TRY(cudaEventRecord(x->pev[2][slot], c->d2h_stream));
+            tmark(c->d2h_stream, 'O');
             total_samples += n;
             total_frames += r.frames;
             merged.error_flags |= r.error_flags;
             merged.truncated = r.truncated;
-            if (r.stopped == 1) { merged.stopped = 1; break; }      // the track ended inside this part
+            if (r.stopped == 1) { merged.stopped = 1; stop = true; }
+            return 0;
+        };
+        // whatever happens, nothing may stay in flight behind this call (the buffers are reused)
+        auto drain = [&]() {
+            while (ended < begun) { dvdagpu_track_result r; decode_end(ctx_of(ended), &r); ended++; }
+            cudaStreamSynchronize(c->d2h_stream);
+            cudaStreamSynchronize(c->h2d_stream);
+        };
+        int rc = upload(0);
+        for (uint32_t i = 0; i < parts && !rc && !fallback && !stop; i++) {
+            if (i + 1 < parts) rc = upload(i + 1);
+            if (!rc) { rc = begin(i); if (!rc) begun++; }
+            // with two contexts the host now waits for the part before this one, with one for this one
+            while (!rc && ended < begun && (begun - ended > (two ? 1u : 0u) || i + 1 == parts) && !fallback) { rc = end(ended); ended++; }
         }
-        CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
-        CUDA_TRY(cudaStreamSynchronize(c->h2d_stream));
+        while (!rc && ended < begun) { rc = end(ended); ended++; }
+        drain();
+        if (ptrace && !fallback && !rc) {
+            // u/U upload begins / ends, d/D decode, o/O download, in the order they were queued
+            fprintf(stderr, "[pipe] %u parts on %d context(s); milliseconds from the first upload's begin:", parts, two ? 2 : 1);
+            for (size_t e = 0; e < tev.size(); e++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, tev[0], tev[e]);
+                fprintf(stderr, " %c%.2f", tkind[e], ms);
+            }
+            fprintf(stderr, "\n");
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+        if (rc == 3) { dvdagpu_set_error("PCM buffer too small"); memset(result, 0, sizeof *result); return 3; }
+        if (rc) { memset(result, 0, sizeof *result); return -1; }
     }
     if (fallback) {
         c->pcm_slot = 0;

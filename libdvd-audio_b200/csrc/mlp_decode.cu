@@ -1992,12 +1992,12 @@ int launch_mlp_fast(MlpTables m, const DecWork *work, uint32_t cap_pairs, uint32
     static const int slot[4] = {DVDAGPU_K_MLP_SEGCTX, DVDAGPU_K_MLP_AU_PARSE, DVDAGPU_K_MLP_RESOLVE, DVDAGPU_K_MLP_ENTROPY};
     const uint32_t small = div_up_u32(cap_pairs, 4);
     for (int pass = 0; pass < 4 && cap_pairs; pass++) {
-        CUDA_TRY(cudaEventRecord(kev[slot[pass]][0], s));
+        CUDA_TRY(record_timing(kev[slot[pass]][0], s));
         if (pass == 0) LAUNCH(k_mlp_segctx, small, 128, 0, s, m, work);
         else if (pass == 1) LAUNCH(k_mlp_au_parse, dim3(div_up_u32(m.cap_au, GRD_THREADS), lim_nss), GRD_THREADS, 0, s, m);
         else if (pass == 2) LAUNCH(k_mlp_resolve, small, 128, 0, s, m, work);
         else LAUNCH(k_mlp_entropy, dim3(div_up_u32(cap_pairs, DEC_WARPS), lim_max_au ? lim_max_au : 1), DEC_WARPS * 32, DEC_SMEM_BYTES, s, m, work);
-        CUDA_TRY(cudaEventRecord(kev[slot[pass]][1], s));
+        CUDA_TRY(record_timing(kev[slot[pass]][1], s));
         kev_used[slot[pass]] = true;
     }
     if (m.cap_seg) LAUNCH(k_flag_predecessors, div_up_u32((uint64_t)m.cap_seg * 2, 256), 256, 0, s, m);

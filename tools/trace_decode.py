@@ -27,4 +27,5 @@ os.environ["DVDAGPU_TRACE"] = "1"
 eng.decode_device(dev.data_ptr(), n, tr)
 del os.environ["DVDAGPU_TRACE"]
 st = eng.stats()
+eng.set_profiling(True); eng.decode_device(dev.data_ptr(), n, tr); st = eng.stats()
 print("total %.3f ms, launches %d" % (st["total_ms"], st["launches"]), file=sys.stderr)
