@@ -60,7 +60,13 @@ typedef struct {
  * keep the reference's per-packet rules exact across the cuts. */
 enum {
     DVDAGPU_PART_CONTINUES_PREVIOUS = 1,   /* not the real start of the track */
-    DVDAGPU_PART_CONTINUED_BY_NEXT = 2     /* not the real end of the track */
+    DVDAGPU_PART_CONTINUED_BY_NEXT = 2,    /* not the real end of the track */
+    /* A long PCM track is read in windows of whole sectors too: every packet is independent, what
+     * carries over is only the frame budget (dvd-audio.c:1016-1082).  With this flag pts_length holds
+     * the frames still to be delivered instead of the track's length in ticks; the window then
+     * behaves like the track from there on (whole packets, stop at a packet that is not PCM or
+     * changes the parameters). */
+    DVDAGPU_PCM_BUDGET_IN_FRAMES = 4
 };
 
 /* What the reference exposes through dvda_codec(), dvda_bits_per_sample(),
@@ -174,6 +180,10 @@ const void *dvdagpu_pcm_device(dvdagpu_ctx *ctx, uint64_t *n_samples);
 /* pinned host memory helpers for callers that stage sectors / PCM themselves */
 void *dvdagpu_host_alloc(size_t bytes);
 void dvdagpu_host_free(void *p);
+/* bytes of dvdagpu_host_alloc() memory live now, and the most that ever were (reset_peak: start a
+ * new measurement).  The host library's track readers keep their pinned memory bounded whatever
+ * the track's length; this is how a test sees it. */
+void dvdagpu_host_usage(uint64_t *live_bytes, uint64_t *peak_bytes, int reset_peak);
 
 int dvdagpu_get_stats(dvdagpu_ctx *ctx, dvdagpu_stats *out);
 /* per-stage and per-kernel CUDA-event timing of the following decodes on / off (default off) */

@@ -33,7 +33,7 @@ ENGINE_SYMBOLS = [
     "dvdagpu_device_count", "dvdagpu_create", "dvdagpu_destroy", "dvdagpu_set_stream",
     "dvdagpu_decode_host", "dvdagpu_decode_device", "dvdagpu_decode_track_pipelined",
     "dvdagpu_fetch", "dvdagpu_pcm_device",
-    "dvdagpu_host_alloc", "dvdagpu_host_free", "dvdagpu_get_stats", "dvdagpu_set_profiling", "dvdagpu_last_error",
+    "dvdagpu_host_alloc", "dvdagpu_host_free", "dvdagpu_host_usage", "dvdagpu_get_stats", "dvdagpu_set_profiling", "dvdagpu_last_error",
 ]
 # every function include/dvd-audio.h declares
 API_SYMBOLS = [
@@ -107,6 +107,7 @@ def engine_lib():
         L.dvdagpu_host_alloc.restype = ctypes.c_void_p
         L.dvdagpu_host_alloc.argtypes = [ctypes.c_size_t]
         L.dvdagpu_host_free.argtypes = [ctypes.c_void_p]
+        L.dvdagpu_host_usage.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
         L.dvdagpu_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
         L.dvdagpu_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.dvdagpu_last_error.restype = ctypes.c_char_p
@@ -149,6 +150,13 @@ def api_lib():
 
 class EngineError(RuntimeError):
     pass
+
+
+def host_usage(reset_peak=False):
+    """(live, peak) bytes of pinned host memory handed out by dvdagpu_host_alloc()."""
+    live, peak = ctypes.c_uint64(), ctypes.c_uint64()
+    engine_lib().dvdagpu_host_usage(ctypes.byref(live), ctypes.byref(peak), 1 if reset_peak else 0)
+    return live.value, peak.value
 
 
 class Engine:

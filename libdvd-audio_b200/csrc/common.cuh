@@ -44,6 +44,7 @@
 // TrackDev.cont / dvdagpu_track_desc.flags
 #define TRACK_CONT_PREV 1u
 #define TRACK_CONT_NEXT 2u
+#define TRACK_PCM_FRAMES 4u    // PCM: pts_length holds the frame budget itself (DVDAGPU_PCM_BUDGET_IN_FRAMES)
 
 // What the demux and index stages find out about the input, kept in device memory: the launch
 // sequence of a decode is fixed before any of it is known to the host.  Every table is sized in

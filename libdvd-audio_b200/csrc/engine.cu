@@ -158,7 +158,7 @@ struct dvdagpu_ctx {
     size_t back_bytes = 0;
     dvdagpu_ctx *peer = nullptr;              // a second context on the same device (pipelined path: two parts decode at once)
     cudaGraphExec_t graph_exec = nullptr;     // the decode sequence as an executable graph (updated in place from decode to decode)
-    bool graph_ok = true, warmed = false;
+    bool graph_ok = true, warmed = false, use_graph = false;
     uint32_t scan_tmp_gen = 0;                // allocation of the scan buffer that has been cleared
     cudaEvent_t pev[3][2];                    // [upload, decode, download][slot]
     int pcm_slot;                             // which PCM buffer the next decode writes
@@ -313,6 +313,15 @@ extern "C" int dvdagpu_set_profiling(dvdagpu_ctx *c, int on)
     return 0;
 }
 
+// pinned host memory handed out through the ABI: how much is live, and the most that ever was
+// (the host library's readers promise a bound on it; the tests hold them to it)
+#include <atomic>
+#include <map>
+#include <mutex>
+static std::mutex g_host_lock;
+static std::map<void *, size_t> g_host_sizes;
+static uint64_t g_host_live = 0, g_host_peak = 0;
+
 extern "C" void *dvdagpu_host_alloc(size_t bytes)
 {
     void *p = nullptr;
@@ -320,9 +329,29 @@ extern "C" void *dvdagpu_host_alloc(size_t bytes)
         dvdagpu_set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
+    std::lock_guard<std::mutex> hold(g_host_lock);
+    g_host_sizes[p] = bytes;
+    g_host_live += bytes;
+    if (g_host_live > g_host_peak) g_host_peak = g_host_live;
     return p;
 }
-extern "C" void dvdagpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void dvdagpu_host_free(void *p)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> hold(g_host_lock);
+        auto it = g_host_sizes.find(p);
+        if (it != g_host_sizes.end()) { g_host_live -= it->second; g_host_sizes.erase(it); }
+    }
+    cudaFreeHost(p);
+}
+extern "C" void dvdagpu_host_usage(uint64_t *live_bytes, uint64_t *peak_bytes, int reset_peak)
+{
+    std::lock_guard<std::mutex> hold(g_host_lock);
+    if (live_bytes) *live_bytes = g_host_live;
+    if (peak_bytes) *peak_bytes = g_host_peak;
+    if (reset_peak) g_host_peak = g_host_live;
+}
 
 extern "C" int dvdagpu_get_stats(dvdagpu_ctx *c, dvdagpu_stats *out)
 {
@@ -572,7 +601,7 @@ static int decode_enqueue(dvdagpu_ctx *c)
             ht[i].first_sector = descs[order[i]].first_sector;
             ht[i].last_sector = descs[order[i]].last_sector;
             ht[i].pts_length = descs[order[i]].pts_length;
-            ht[i].cont = descs[order[i]].flags & 3u;
+            ht[i].cont = descs[order[i]].flags & 7u;
         }
         const uint32_t rows = (uint32_t)sh.rows, cap_sync = (uint32_t)sh.sync, cap_seg = (uint32_t)sh.seg, cap_grp = (uint32_t)sh.grp;
         const uint32_t cap_au = (uint32_t)sh.au, cap_work = 2 * n_tracks, cap_pairs = 2 * cap_grp;
@@ -629,11 +658,13 @@ static int decode_enqueue(dvdagpu_ctx *c)
         ENSURE(pcm_buf, (pcm_capacity + 64) * sizeof(int32_t));
 
         // ---------------- from here to the read-back everything is asynchronous on the stream(s): the
-        // sequence is captured into a CUDA graph and launched as one (the first decode of a context
-        // runs it directly: kernel attributes are set on first use).  A captured decode costs the
-        // GPU's front end one submission instead of forty: while bulk copies saturate the link, every
-        // separate launch waits its turn on it.
-        const bool graph = c->graph_ok && c->warmed && !g_trace_on && getenv("DVDAGPU_NO_GRAPH") == nullptr;
+        // sequence can be captured into a CUDA graph and launched as one (the first decode of a context
+        // runs it directly: kernel attributes are set on first use).  The pipelined path does so: a
+        // captured decode costs the GPU's front end one submission instead of forty, and while bulk
+        // copies saturate the link every separate launch waits its turn on it (16 parts end to end:
+        // 14.1 ms launched one by one, 10.5 ms as graphs).  With the input resident the capture and
+        // the update of the executable graph cost the host more than they save (1.71 against 1.66 ms).
+        const bool graph = c->use_graph && c->graph_ok && c->warmed && !g_trace_on && getenv("DVDAGPU_NO_GRAPH") == nullptr;
         if (graph) {
             if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); c->graph_ok = false; }
             else g_capturing = true;
@@ -1061,6 +1092,11 @@ extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sec
             if (c->peer) { X[1] = c->peer; c->peer->profiling = c->profiling; }
         }
         const bool two = X[1] != c;
+        struct GraphMode {                                   // decodes of the parts are launched as graphs
+            dvdagpu_ctx *a, *b;
+            GraphMode(dvdagpu_ctx *a_, dvdagpu_ctx *b_) : a(a_), b(b_) { a->use_graph = b->use_graph = true; }
+            ~GraphMode() { a->use_graph = b->use_graph = false; }
+        } graph_mode(X[0], X[1]);
         const uint32_t parts = (uint32_t)starts.size();
         auto window = [&](uint32_t i, uint64_t &s0, uint64_t &len, uint64_t &e_rel) {
             s0 = starts[i];

@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
             T.codec = 0;
             T.pcm_chunk = (T.bits >> 3) * T.channels * 2;
             // frame budget: lround(pts * rate / 90000)
-            const uint64_t total = (uint64_t)llround((double)T.pts_length * (double)T.rate / 90000.0);
+            // (a window of a longer PCM track: the caller keeps the books and passes the frames still to come)
+            const uint64_t total = (T.cont & TRACK_PCM_FRAMES) ? (uint64_t)T.pts_length
+                                                               : (uint64_t)llround((double)T.pts_length * (double)T.rate / 90000.0);
             T.pcm_frame0 = a.pk_pf[T.pk_lo];
             // stop in front of the first later packet that is not PCM / differs / is empty
             uint32_t stop = warp_first_flagged(a.pk_pcm_stop, np, T.pk_lo + 1);
@@ -378,6 +380,14 @@ __global__ void __launch_bounds__(64) k_track_setup(TrackSetupArgs a, TrackDev *
                 // the first access unit is not a usable major sync: nothing decodes
                 T.error_flags |= ERR_SYNTAX;
                 T.es_end = T.es_cut = p;
+            }
+            // A continued part has to begin where a segment begins: at a major sync whose substreams
+            // open with a restart header.  If the first sync behind the cut is not one (a stream may
+            // carry major syncs without restart headers), the decoder state of the part before is
+            // needed: the caller has to decode the two parts as one.
+            if ((T.cont & TRACK_CONT_PREV) && !empty_part) {
+                const uint32_t vi = warp_lower_bound(a.valid, n_valid, p);
+                if (!(vi < n_valid && a.valid[vi] == p)) { T.stopped = 2; T.es_end = T.es_cut = p; }
             }
             // restart segments: the start plus every segment-starting sync inside (p, es_end)
             T.cand_lo = warp_upper_bound(a.valid, n_valid, p);

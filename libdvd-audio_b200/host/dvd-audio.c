@@ -5,13 +5,18 @@
  * ranges) is ordinary host code and mirrors the behaviour of the reference's
  * src/dvd-audio.c:324-595, 824-950 and src/audio_ts.c:38-73; it is written from
  * the table layouts, not from the reference's bit-reader
- * calls.  Everything from dvda_open_track_reader() on is different: the track's
- * sectors are read into pinned memory and handed to the CUDA engine
- * (include/dvdagpu.h), which decodes the whole track on the GPU; dvda_read()
- * then copies slices of the result.  There is no CPU decode path: if the engine
- * cannot be created, dvda_open_track_reader() fails.
+ * calls.  Everything from dvda_open_track_reader() on is different: a reader
+ * cuts its track into parts of a few thousand sectors, reads each part's
+ * sectors into pinned memory and hands it to a pool of CUDA engine contexts
+ * (include/dvdagpu.h; one worker thread per context, on one or several GPUs),
+ * which decode a few parts ahead of dvda_read(); dvda_read() copies from the
+ * part at the cursor.  Memory per reader is bounded by the parts in flight,
+ * whatever the track's length.  There is no CPU decode path: if no engine can
+ * be created, dvda_open_track_reader() fails.
  *
- * Environment: DVDA_B200_DEVICE selects the CUDA device (default 0).
+ * Environment: DVDA_B200_DEVICES ("all" or a list; default DVDA_B200_DEVICE or
+ * 0), DVDA_B200_CONTEXTS (contexts per device, default 2),
+ * DVDA_B200_PART_SECTORS (default 8192).
  */
 #define _POSIX_C_SOURCE 200809L
 #include "dvd-audio.h"
@@ -19,11 +24,13 @@
 
 #include <ctype.h>
 #include <dirent.h>
+#include <fcntl.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #define SECTOR_SIZE 2048u
 #define MAX_AOBS 9
@@ -59,13 +66,6 @@ struct DVDA_Track_s {
     struct disc_path disc;
     unsigned titleset, title, number;
     struct title_track t;
-};
-struct DVDA_Track_Reader_s {
-    dvda_codec_t codec;
-    unsigned bits, rate, channels, assignment;
-    unsigned long long frames, cursor;
-    int *pcm;                   /* frames * channels, pinned */
-    size_t pcm_bytes;
 };
 
 static char *dup_str(const char *s)
@@ -213,8 +213,7 @@ DVDA_Titleset *dvda_open_titleset(DVDA *dvda, unsigned titleset)
     if (!ts) { free(b); return NULL; }
     ts->number = titleset;
     if (!parse_ats(b, len, ts)) {
-        if (len >= 12 && !memcmp(b, "DVDAUDIO-ATS", 12)) fprintf(stderr, "I/O error\n");
-        else fprintf(stderr, "I/O error\n");
+        fprintf(stderr, "I/O error\n");
         free(ts->title);
         free(ts);
         free(b);
@@ -310,9 +309,10 @@ unsigned dvda_track_last_sector(const DVDA_Track *k) { return k->t.last_sector; 
 /* ------------------------------------------------------------ AOB access */
 
 /* the title set's ATS_tt_1.AOB .. ATS_tt_9.AOB as one run of sectors
-   (behaviour of src/aob.c:90-123, 181-213) */
+   (behaviour of src/aob.c:90-123, 181-213).  Positional reads on file
+   descriptors: several engine workers read their parts at the same time. */
 struct aob_set {
-    FILE *file[MAX_AOBS];
+    int fd[MAX_AOBS];
     unsigned long long sectors[MAX_AOBS];
     unsigned count;
     unsigned long long total;
@@ -320,7 +320,7 @@ struct aob_set {
 
 static void aobs_close(struct aob_set *a)
 {
-    for (unsigned i = 0; i < a->count; i++) fclose(a->file[i]);
+    for (unsigned i = 0; i < a->count; i++) close(a->fd[i]);
     a->count = 0;
 }
 
@@ -329,15 +329,15 @@ static void aobs_open(struct aob_set *a, const char *dir, unsigned titleset)
     memset(a, 0, sizeof *a);
     for (unsigned n = 1; n <= MAX_AOBS; n++) {
         char name[16];
-        snprintf(name, sizeof name, "ATS_%02u_%u.AOB", titleset % 100, n);
+        snprintf(name, sizeof name, "ATS_%02u_%u.AOB", titleset > 99 ? 99 : titleset, n);
         char *path = find_file(dir, name);
         if (!path) break;
         struct stat st;
-        FILE *f = NULL;
-        if (stat(path, &st) == 0) f = fopen(path, "rb");
+        int fd = -1;
+        if (stat(path, &st) == 0) fd = open(path, O_RDONLY);
         free(path);
-        if (!f) break;
-        a->file[a->count] = f;
+        if (fd < 0) break;
+        a->fd[a->count] = fd;
         a->sectors[a->count] = (unsigned long long)st.st_size / SECTOR_SIZE;
         a->total += a->sectors[a->count];
         a->count++;
@@ -345,7 +345,7 @@ static void aobs_open(struct aob_set *a, const char *dir, unsigned titleset)
 }
 
 /* reads sectors [first, first + n) into dst; returns sectors read */
-static unsigned long long aobs_read(struct aob_set *a, unsigned long long first, unsigned long long n, unsigned char *dst)
+static unsigned long long aobs_read(const struct aob_set *a, unsigned long long first, unsigned long long n, unsigned char *dst)
 {
     unsigned long long done = 0, base = 0;
     for (unsigned i = 0; i < a->count && done < n; i++) {
@@ -354,171 +354,409 @@ static unsigned long long aobs_read(struct aob_set *a, unsigned long long first,
         if (want < end) {
             unsigned long long take = end - want;
             if (take > n - done) take = n - done;
-            if (fseeko(a->file[i], (off_t)((want - base) * SECTOR_SIZE), SEEK_SET)) break;
-            const size_t got = fread(dst + done * SECTOR_SIZE, SECTOR_SIZE, (size_t)take, a->file[i]);
-            done += got;
-            if (got != take) break;
+            size_t bytes = (size_t)take * SECTOR_SIZE, got = 0;
+            off_t at = (off_t)((want - base) * SECTOR_SIZE);
+            while (got < bytes) {
+                const ssize_t r = pread(a->fd[i], dst + done * SECTOR_SIZE + got, bytes - got, at + (off_t)got);
+                if (r <= 0) break;
+                got += (size_t)r;
+            }
+            done += got / SECTOR_SIZE;
+            if (got != bytes) break;
         }
         base = end;
     }
     return done;
 }
 
-/* ------------------------------------------------------- engine + buffers */
+/* ------------------------------------------------------- the engine pool
+ *
+ * One worker thread per engine context.  DVDA_B200_DEVICES picks the CUDA
+ * devices ("all", or a comma-separated list; default: DVDA_B200_DEVICE or 0),
+ * DVDA_B200_CONTEXTS the contexts per device (default 2: while one part's
+ * samples travel to the host the next part is decoded).  A track reader cuts
+ * its track into parts of DVDA_B200_PART_SECTORS sectors (default 8192 = 16 MB)
+ * and deals them to the workers in turn, a few parts ahead of dvda_read(): the
+ * parts of a long track are decoded on all devices at once and gathered in
+ * order in the reader — a host-side gather, no other exchange.  Pinned memory
+ * per reader is bounded by the parts in flight, whatever the track's length. */
 
-static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
-static dvdagpu_ctx *g_engine;
-static int g_engine_failed;
+struct part_job;
+struct worker {
+    pthread_t thread;
+    dvdagpu_ctx *ctx;
+    int device;
+    pthread_mutex_t lock;
+    pthread_cond_t wake;
+    struct part_job *head, *tail;       /* queued jobs */
+    int quit;
+};
 
-/* small cache of pinned buffers: page-locking is slow, tracks come in a row */
-#define POOL_SLOTS 4
-static struct { void *p; size_t bytes; } g_pool[POOL_SLOTS];
+/* one part of a track: a window of sectors in, interleaved samples out */
+struct part_job {
+    struct part_job *next;
+    const struct aob_set *aobs;
+    unsigned long long first, n_sectors;        /* window in the title set's sector run */
+    dvdagpu_track_desc desc;                    /* relative to the window */
+    unsigned char *sec;  size_t sec_cap;        /* pinned */
+    int *pcm;            size_t pcm_cap;        /* pinned, in ints */
+    unsigned long long got;                     /* sectors read */
+    dvdagpu_track_result res;
+    int rc;                                     /* 0 ok, else the engine failed (message printed) */
+    int done;
+    pthread_mutex_t lock;
+    pthread_cond_t cond;
+};
 
-static void *pool_take(size_t bytes)
+static pthread_mutex_t g_pool_lock = PTHREAD_MUTEX_INITIALIZER;
+static struct worker *g_workers;
+static unsigned g_nworkers, g_next_worker;
+static int g_pool_failed;
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void run_job(struct worker *w, struct part_job *j)
 {
-    int best = -1;
-    for (int i = 0; i < POOL_SLOTS; i++)
-        if (g_pool[i].p && g_pool[i].bytes >= bytes && (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = i;
-    if (best >= 0) {
-        void *p = g_pool[best].p;
-        g_pool[best].p = NULL;
-        return p;
-    }
-    return dvdagpu_host_alloc(bytes);
-}
-
-static void pool_give(void *p, size_t bytes)
-{
-    if (!p) return;
-    int slot = -1;
-    for (int i = 0; i < POOL_SLOTS; i++) if (!g_pool[i].p) { slot = i; break; }
-    if (slot < 0) {
-        /* evict the smallest */
-        slot = 0;
-        for (int i = 1; i < POOL_SLOTS; i++) if (g_pool[i].bytes < g_pool[slot].bytes) slot = i;
-        if (g_pool[slot].bytes >= bytes) { dvdagpu_host_free(p); return; }
-        dvdagpu_host_free(g_pool[slot].p);
-    }
-    g_pool[slot].p = p;
-    g_pool[slot].bytes = bytes;
-}
-
-static dvdagpu_ctx *engine(void)
-{
-    if (!g_engine && !g_engine_failed) {
-        const char *dev = getenv("DVDA_B200_DEVICE");
-        g_engine = dvdagpu_create(dev ? atoi(dev) : 0);
-        if (!g_engine) {
-            g_engine_failed = 1;
-            fprintf(stderr, "libdvd-audio (B200): %s\n", dvdagpu_last_error());
+    j->rc = -1;
+    memset(&j->res, 0, sizeof j->res);
+    j->got = aobs_read(j->aobs, j->first, j->n_sectors, j->sec);
+    if (j->got) {
+        /* the window may be shorter than asked for (end of the title set) */
+        if (j->desc.last_sector >= j->got) j->desc.last_sector = (uint32_t)(j->got - 1);
+        j->rc = dvdagpu_decode_host(w->ctx, j->sec, j->got, 1, &j->desc, &j->res);
+        if (j->rc) fprintf(stderr, "libdvd-audio (B200): %s\n", dvdagpu_last_error());
+        if (!j->rc && j->res.status == DVDAGPU_TRACK_OK) {
+            const size_t n = (size_t)(j->res.frames * j->res.channels);
+            if (n > j->pcm_cap) {
+                dvdagpu_host_free(j->pcm);
+                j->pcm_cap = round_up(n + n / 8 + 1, 1 << 18);
+                j->pcm = dvdagpu_host_alloc(j->pcm_cap * sizeof(int));
+                if (!j->pcm) { j->pcm_cap = 0; j->rc = -1; fprintf(stderr, "libdvd-audio (B200): %s\n", dvdagpu_last_error()); }
+            }
+            if (!j->rc && n && dvdagpu_fetch(w->ctx, j->res.pcm_offset, n, j->pcm)) {
+                j->rc = -1;
+                fprintf(stderr, "libdvd-audio (B200): %s\n", dvdagpu_last_error());
+            }
         }
     }
-    return g_engine;
+    pthread_mutex_lock(&j->lock);
+    j->done = 1;
+    pthread_cond_signal(&j->cond);
+    pthread_mutex_unlock(&j->lock);
+}
+
+static void *worker_main(void *arg)
+{
+    struct worker *w = arg;
+    for (;;) {
+        pthread_mutex_lock(&w->lock);
+        while (!w->head && !w->quit) pthread_cond_wait(&w->wake, &w->lock);
+        struct part_job *j = w->head;
+        if (j) { w->head = j->next; if (!w->head) w->tail = NULL; }
+        const int quit = w->quit && !j;
+        pthread_mutex_unlock(&w->lock);
+        if (quit) break;
+        if (j) run_job(w, j);
+    }
+    return NULL;
+}
+
+static void pool_shutdown(void)
+{
+    pthread_mutex_lock(&g_pool_lock);
+    for (unsigned i = 0; i < g_nworkers; i++) {
+        struct worker *w = &g_workers[i];
+        pthread_mutex_lock(&w->lock);
+        w->quit = 1;
+        pthread_cond_signal(&w->wake);
+        pthread_mutex_unlock(&w->lock);
+        pthread_join(w->thread, NULL);
+        dvdagpu_destroy(w->ctx);
+    }
+    free(g_workers);
+    g_workers = NULL;
+    g_nworkers = 0;
+    pthread_mutex_unlock(&g_pool_lock);
+}
+
+/* the workers, created on first use; 0 if there is no usable engine (no CPU path) */
+static unsigned pool_workers(void)
+{
+    pthread_mutex_lock(&g_pool_lock);
+    if (!g_workers && !g_pool_failed) {
+        int devices[64], nd = 0;
+        const int present = dvdagpu_device_count();
+        const char *list = getenv("DVDA_B200_DEVICES");
+        if (list && !strcmp(list, "all")) {
+            for (int d = 0; d < present && nd < 64; d++) devices[nd++] = d;
+        } else if (list && *list) {
+            for (const char *p = list; *p && nd < 64;) {
+                char *end;
+                const long d = strtol(p, &end, 10);
+                if (end == p) break;
+                devices[nd++] = (int)d;
+                p = *end == ',' ? end + 1 : end;
+            }
+        } else {
+            const char *one = getenv("DVDA_B200_DEVICE");
+            devices[nd++] = one ? atoi(one) : 0;
+        }
+        const char *pc = getenv("DVDA_B200_CONTEXTS");
+        int per = pc ? atoi(pc) : 2;
+        if (per < 1) per = 1;
+        if (per > 4) per = 4;
+        g_workers = calloc((size_t)nd * (size_t)per, sizeof *g_workers);
+        /* contexts of one device are not neighbours in the list: consecutive parts go to different devices */
+        for (int k = 0; k < per && g_workers; k++) {
+            for (int i = 0; i < nd; i++) {
+                struct worker *w = &g_workers[g_nworkers];
+                w->ctx = dvdagpu_create(devices[i]);
+                if (!w->ctx) {
+                    if (k == 0) fprintf(stderr, "libdvd-audio (B200): %s\n", dvdagpu_last_error());
+                    continue;
+                }
+                w->device = devices[i];
+                pthread_mutex_init(&w->lock, NULL);
+                pthread_cond_init(&w->wake, NULL);
+                if (pthread_create(&w->thread, NULL, worker_main, w)) { dvdagpu_destroy(w->ctx); continue; }
+                g_nworkers++;
+            }
+        }
+        if (!g_nworkers) { free(g_workers); g_workers = NULL; g_pool_failed = 1; }
+        else atexit(pool_shutdown);
+    }
+    const unsigned n = g_nworkers;
+    pthread_mutex_unlock(&g_pool_lock);
+    return n;
+}
+
+static void pool_submit(struct part_job *j)
+{
+    pthread_mutex_lock(&g_pool_lock);
+    struct worker *w = &g_workers[g_next_worker++ % g_nworkers];
+    pthread_mutex_unlock(&g_pool_lock);
+    j->done = 0;
+    j->next = NULL;
+    pthread_mutex_lock(&w->lock);
+    if (w->tail) w->tail->next = j; else w->head = j;
+    w->tail = j;
+    pthread_cond_signal(&w->wake);
+    pthread_mutex_unlock(&w->lock);
+}
+
+static void job_wait(struct part_job *j)
+{
+    pthread_mutex_lock(&j->lock);
+    while (!j->done) pthread_cond_wait(&j->cond, &j->lock);
+    pthread_mutex_unlock(&j->lock);
 }
 
 /* ------------------------------------------------------------ track reader */
 
-static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+#define MAX_AHEAD 6
+#define PART_MARGIN 64          /* sectors behind a part: the run to the next major sync */
+
+struct DVDA_Track_Reader_s {
+    dvda_codec_t codec;
+    unsigned bits, rate, channels, assignment;
+    struct aob_set aobs;
+    unsigned long long first, last;             /* the track's sectors */
+    unsigned pts_length;
+    unsigned part_sectors;
+    /* part i lives in ring[i % slots] from its submission until the part behind it is taken */
+    struct part_job ring[MAX_AHEAD];
+    unsigned slots;
+    unsigned long long next_sector;             /* where the next part begins */
+    unsigned long long parts_submitted, parts_taken, parts_released;
+    int no_more;                                /* no further part will be submitted */
+    /* the part being read */
+    struct part_job *cur;
+    unsigned long long cur_frames, cur_pos;     /* frames in it, frames already handed out */
+    unsigned long long cur_skip;                /* samples at its front that belong to the part before (see take_part) */
+    unsigned long long pcm_budget;              /* PCM: frames still to come */
+    unsigned long long prev_first, prev_frames; /* MLP: the previous part, in case this one needs its filter history */
+    unsigned prev_flags;
+    int ended;
+};
+
+static void reader_free(DVDA_Track_Reader *r)
+{
+    /* nothing may be in flight when the buffers go */
+    for (unsigned long long i = r->parts_taken; i < r->parts_submitted; i++) job_wait(&r->ring[i % r->slots]);
+    for (unsigned i = 0; i < MAX_AHEAD; i++) {
+        if (r->ring[i].sec) dvdagpu_host_free(r->ring[i].sec);
+        if (r->ring[i].pcm) dvdagpu_host_free(r->ring[i].pcm);
+        pthread_mutex_destroy(&r->ring[i].lock);
+        pthread_cond_destroy(&r->ring[i].cond);
+    }
+    aobs_close(&r->aobs);
+    free(r);
+}
+
+/* fills slot `j` with the window [first, first + sectors + margin) and hands it to a worker */
+static int submit_window(DVDA_Track_Reader *r, struct part_job *j, unsigned long long first, unsigned long long sectors,
+                         unsigned long long margin, unsigned pts, unsigned flags)
+{
+    unsigned long long n = sectors + margin;
+    if (first + n > r->aobs.total) n = r->aobs.total - first;
+    const size_t bytes = round_up((size_t)n * SECTOR_SIZE, 1 << 16);
+    if (bytes > j->sec_cap) {
+        dvdagpu_host_free(j->sec);
+        j->sec = dvdagpu_host_alloc(bytes);
+        j->sec_cap = j->sec ? bytes : 0;
+        if (!j->sec) { fprintf(stderr, "libdvd-audio (B200): %s\n", dvdagpu_last_error()); return -1; }
+    }
+    j->aobs = &r->aobs;
+    j->first = first;
+    j->n_sectors = n;
+    j->desc.first_sector = 0;
+    j->desc.last_sector = (uint32_t)(sectors ? sectors - 1 : 0);
+    j->desc.pts_length = pts;
+    j->desc.flags = flags;
+    pool_submit(j);
+    return 0;
+}
+
+/* submits further parts of the track while there are any and slots are free */
+static void submit_next(DVDA_Track_Reader *r)
+{
+    while (!r->no_more && r->parts_submitted - r->parts_released < r->slots) {
+        struct part_job *j = &r->ring[r->parts_submitted % r->slots];
+        unsigned long long sectors, margin;
+        unsigned flags, pts = r->pts_length;
+        if (r->parts_submitted > 0 && r->codec == DVDA_PCM) {
+            /* PCM parts follow one another (each needs the frames still to come) and run on behind
+               the track's last sector while the budget lasts, like the reference (dvd-audio.c:1016-1082) */
+            if (r->parts_submitted > r->parts_taken) break;
+            if (!r->pcm_budget || r->next_sector >= r->aobs.total) { r->no_more = 1; break; }
+            sectors = r->aobs.total - r->next_sector;
+            if (sectors > r->part_sectors) sectors = r->part_sectors;
+            margin = 0;
+            flags = DVDAGPU_PCM_BUDGET_IN_FRAMES;
+            pts = r->pcm_budget > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)r->pcm_budget;
+        } else {
+            if (r->next_sector > r->last || r->next_sector >= r->aobs.total) { r->no_more = 1; break; }
+            sectors = r->last - r->next_sector + 1;
+            const int final = sectors <= r->part_sectors + r->part_sectors / 4;     /* (a short rest goes with the last part) */
+            if (!final) sectors = r->part_sectors;
+            margin = PART_MARGIN;
+            flags = (r->parts_submitted ? DVDAGPU_PART_CONTINUES_PREVIOUS : 0u) | (final ? 0u : DVDAGPU_PART_CONTINUED_BY_NEXT);
+            if (final) r->no_more = 1;
+        }
+        if (submit_window(r, j, r->next_sector, sectors, margin, pts, flags)) { r->no_more = 1; break; }
+        r->parts_submitted++;
+        r->next_sector += sectors;
+    }
+}
+
+/* makes the next finished part the current one; 0 when the track is over */
+static int take_part(DVDA_Track_Reader *r)
+{
+    for (;;) {
+        r->cur = NULL;
+        r->parts_released = r->parts_taken;         /* the part that was being read is done with */
+        if (r->ended) return 0;
+        submit_next(r);
+        if (r->parts_taken == r->parts_submitted) { r->ended = 1; return 0; }
+        const unsigned long long index = r->parts_taken;
+        struct part_job *j = &r->ring[index % r->slots];
+        job_wait(j);
+        r->parts_taken++;
+        if (getenv("DVDA_B200_DEBUG"))
+            fprintf(stderr, "[dvda] part %llu: sectors [%llu, +%llu) last %u flags %u -> rc %d status %d codec %d frames %llu stopped %u truncated %u err %x\n",
+                    index, j->first, j->got, j->desc.last_sector, j->desc.flags, j->rc, j->res.status, j->res.codec,
+                    (unsigned long long)j->res.frames, j->res.stopped, j->res.truncated, (unsigned)j->res.error_flags);
+        if (j->rc || j->res.status != DVDAGPU_TRACK_OK) { r->ended = 1; return 0; }
+        unsigned long long skip = 0;
+        const int is_pcm = j->res.codec == 0;
+        if (!is_pcm && j->res.stopped == 2) {
+            /* the part needs the filter history of the one before it (FIR state survives a restart
+               header, mlp.c:948-952): both are decoded as one window, the samples of the part before
+               are dropped */
+            const unsigned long long sectors = j->first + j->desc.last_sector + 1 - r->prev_first;
+            const unsigned flags = (r->prev_flags & DVDAGPU_PART_CONTINUES_PREVIOUS) | (j->desc.flags & DVDAGPU_PART_CONTINUED_BY_NEXT);
+            if (submit_window(r, j, r->prev_first, sectors, PART_MARGIN, r->pts_length, flags)) { r->ended = 1; return 0; }
+            job_wait(j);
+            if (j->rc || j->res.status != DVDAGPU_TRACK_OK || j->res.stopped == 2 || j->res.frames < r->prev_frames) { r->ended = 1; return 0; }
+            skip = r->prev_frames;
+            /* (the parts already submitted behind it were cut at the same places: they stay valid) */
+        } else if (!is_pcm && j->res.truncated && !(j->desc.flags & DVDAGPU_PART_CONTINUED_BY_NEXT) &&
+                   j->first + j->n_sectors < r->aobs.total && j->n_sectors < (1ull << 22)) {
+            /* the last part ran out of sectors before the next major sync: once more with a wider margin */
+            const unsigned long long sectors = j->desc.last_sector + 1ull;
+            if (submit_window(r, j, j->first, sectors, (j->n_sectors - sectors) * 8 + PART_MARGIN, r->pts_length, j->desc.flags)) { r->ended = 1; return 0; }
+            r->parts_taken--;           /* (the same part again) */
+            continue;
+        }
+        if (index == 0) {
+            r->codec = is_pcm ? DVDA_PCM : DVDA_MLP;
+            r->bits = j->res.bits_per_sample; r->rate = j->res.sample_rate;
+            r->channels = j->res.channels; r->assignment = j->res.channel_assignment;
+            if (is_pcm) {
+                const double total = (double)r->pts_length * (double)r->rate / (double)PTS_PER_SECOND;
+                r->pcm_budget = (unsigned long long)(total + 0.5);
+                /* the window was the part and its margin: all of it was delivered */
+                r->next_sector = j->first + j->got;
+                r->no_more = 0;
+            }
+        } else if (j->res.channels != r->channels || j->res.sample_rate != r->rate || j->res.bits_per_sample != r->bits ||
+                   (is_pcm ? DVDA_PCM : DVDA_MLP) != r->codec) {
+            r->ended = 1;               /* the stream changed its parameters: the track is over (dvd-audio.c:1049-1055) */
+            return 0;
+        }
+        if (j->res.error_flags & DVDAGPU_ERR_PARITY) fprintf(stderr, "parity mismatch\n");
+        if (j->res.error_flags & DVDAGPU_ERR_CRC) fprintf(stderr, "CRC-8 mismatch\n");
+        const unsigned long long frames = j->res.frames - skip;
+        if (is_pcm) {
+            r->pcm_budget = frames >= r->pcm_budget ? 0 : r->pcm_budget - frames;
+            /* over: the budget is used up, or the window ended early (a packet that is not PCM, changed parameters) */
+            if (!r->pcm_budget || !j->res.truncated) r->no_more = 1;
+            else if (index > 0) r->next_sector = j->first + j->got;
+        } else {
+            r->prev_first = j->first; r->prev_frames = j->res.frames; r->prev_flags = j->desc.flags;
+            if (j->res.stopped == 1) { r->no_more = 1; r->ended = 1; }      /* the track ended inside this part: nothing behind it counts */
+        }
+        r->cur = j;
+        r->cur_frames = frames;
+        r->cur_skip = skip * r->channels;
+        r->cur_pos = 0;
+        if (!r->ended) submit_next(r);  /* keep the workers busy while this part is read */
+        if (!frames) { if (r->ended) return 0; continue; }      /* (a part without a major sync is empty) */
+        return 1;
+    }
+}
 
 DVDA_Track_Reader *dvda_open_track_reader(const DVDA_Track *track)
 {
-    struct aob_set aobs;
-    aobs_open(&aobs, track->disc.audio_ts, track->titleset);
-    const unsigned long long first = track->t.first_sector;
-    if (!aobs.count || first >= aobs.total) { aobs_close(&aobs); return NULL; }
-
-    DVDA_Track_Reader *r = NULL;
-    pthread_mutex_lock(&g_lock);
-    dvdagpu_ctx *eng = engine();
-    if (!eng) goto out;
-
-    /* Read the track's sectors plus a margin for the run to the next major
-       sync into pinned memory; widen the window while the engine reports that
-       it ran out.  A probe of the first sectors tells the sample format, which
-       sizes the PCM buffer (from the track's PTS length) for the pipelined
-       decode; if that estimate is too small the one-piece path is used. */
-    unsigned long long last = track->t.last_sector < first ? first : track->t.last_sector;
-    unsigned long long margin = 64;
-    for (;;) {
-        unsigned long long stop = last + 1 + margin;
-        if (stop > aobs.total) stop = aobs.total;
-        const unsigned long long n = stop - first;
-        const size_t sec_bytes = round_up((size_t)n * SECTOR_SIZE, 1 << 20);
-        unsigned char *sec = pool_take(sec_bytes);
-        if (!sec) break;
-        const unsigned long long got = aobs_read(&aobs, first, n, sec);
-        dvdagpu_track_desc desc = {0, 0, track->t.pts_length, 0};
-        desc.last_sector = (uint32_t)(track->t.last_sector >= first ? track->t.last_sector - first : 0);
-        dvdagpu_track_result res;
-        memset(&res, 0, sizeof res);
-        int rc = got ? 0 : -1;
-        int *pcm = NULL;
-        size_t pcm_bytes = 0;
-        int have_pcm = 0;
-        if (!rc && got > 4096) {
-            /* long track: probe the format on a short window, then decode with overlapped copies */
-            dvdagpu_track_desc pd = {0, 63, track->t.pts_length, 0};
-            dvdagpu_track_result pr;
-            if (!dvdagpu_decode_host(eng, sec, 256, 1, &pd, &pr) && pr.status == DVDAGPU_TRACK_OK &&
-                pr.codec == 1 && pr.sample_rate && pr.channels) {
-                const double seconds = (double)track->t.pts_length / PTS_PER_SECOND + 2.0;
-                const unsigned long long cap = (unsigned long long)(seconds * pr.sample_rate) * pr.channels;
-                pcm_bytes = round_up((size_t)cap * sizeof(int) + 1, 1 << 20);
-                pcm = pool_take(pcm_bytes);
-                if (pcm) {
-                    rc = dvdagpu_decode_track_pipelined(eng, sec, got, &desc, 0, pcm, pcm_bytes / sizeof(int), &res);
-                    if (rc == 0) have_pcm = 1;
-                    else { pool_give(pcm, pcm_bytes); pcm = NULL; rc = 0; }   /* too small: one piece */
-                }
-            }
-        }
-        if (!rc && !have_pcm) rc = dvdagpu_decode_host(eng, sec, got, 1, &desc, &res);
-        pool_give(sec, sec_bytes);
-        if (rc) {
-            if (got) fprintf(stderr, "libdvd-audio (B200): %s\n", dvdagpu_last_error());
-            if (pcm) pool_give(pcm, pcm_bytes);
-            break;
-        }
-        if (res.status != DVDAGPU_TRACK_OK) { if (pcm) pool_give(pcm, pcm_bytes); break; }
-        if (res.truncated && stop < aobs.total) { if (pcm) pool_give(pcm, pcm_bytes); margin *= 8; continue; }
-
-        if (res.error_flags & DVDAGPU_ERR_PARITY) fprintf(stderr, "parity mismatch\n");
-        if (res.error_flags & DVDAGPU_ERR_CRC) fprintf(stderr, "CRC-8 mismatch\n");
-        r = calloc(1, sizeof *r);
-        if (!r) { if (pcm) pool_give(pcm, pcm_bytes); break; }
-        r->codec = res.codec ? DVDA_MLP : DVDA_PCM;
-        r->bits = res.bits_per_sample;
-        r->rate = res.sample_rate;
-        r->channels = res.channels;
-        r->assignment = res.channel_assignment;
-        r->frames = res.frames;
-        if (have_pcm) {
-            r->pcm = pcm;
-            r->pcm_bytes = pcm_bytes;
-        } else {
-            r->pcm_bytes = round_up((size_t)res.frames * res.channels * sizeof(int) + 1, 1 << 20);
-            r->pcm = pool_take(r->pcm_bytes);
-            if (!r->pcm || dvdagpu_fetch(eng, res.pcm_offset, res.frames * res.channels, r->pcm)) {
-                pool_give(r->pcm, r->pcm_bytes);
-                free(r);
-                r = NULL;
-            }
-        }
-        break;
+    DVDA_Track_Reader *r = calloc(1, sizeof *r);
+    if (!r) return NULL;
+    for (unsigned i = 0; i < MAX_AHEAD; i++) {
+        pthread_mutex_init(&r->ring[i].lock, NULL);
+        pthread_cond_init(&r->ring[i].cond, NULL);
     }
-out:
-    pthread_mutex_unlock(&g_lock);
-    aobs_close(&aobs);
+    aobs_open(&r->aobs, track->disc.audio_ts, track->titleset);
+    r->first = track->t.first_sector;
+    r->last = track->t.last_sector < r->first ? r->first : track->t.last_sector;
+    r->pts_length = track->t.pts_length;
+    const unsigned workers = (r->aobs.count && r->first < r->aobs.total) ? pool_workers() : 0;
+    if (!workers) { reader_free(r); return NULL; }
+    const char *ps = getenv("DVDA_B200_PART_SECTORS");
+    r->part_sectors = ps ? (unsigned)atoi(ps) : 8192u;
+    if (r->part_sectors < 16) r->part_sectors = 16;
+    r->next_sector = r->first;
+    /* the first part tells the format (and whether the track can be opened at all): it goes alone,
+       the parts behind it are cut according to the codec */
+    r->slots = 1;
+    const int ok = take_part(r);
+    if (!ok && !r->channels) { reader_free(r); return NULL; }
+    r->slots = workers + 1 > MAX_AHEAD ? MAX_AHEAD : workers + 1;
+    if (!r->ended) submit_next(r);
     return r;
 }
 
 void dvda_close_track_reader(DVDA_Track_Reader *r)
 {
-    if (!r) return;
-    pthread_mutex_lock(&g_lock);
-    pool_give(r->pcm, r->pcm_bytes);
-    pthread_mutex_unlock(&g_lock);
-    free(r);
+    if (r) reader_free(r);
 }
 
 dvda_codec_t dvda_codec(const DVDA_Track_Reader *r) { return r->codec; }
@@ -559,12 +797,19 @@ unsigned dvda_riff_wave_channel_mask(const DVDA_Track_Reader *r)
 
 unsigned dvda_read(DVDA_Track_Reader *r, unsigned pcm_frames, int buffer[])
 {
-    if (!pcm_frames) return 0;
-    unsigned long long left = r->frames - r->cursor;
-    unsigned n = left < pcm_frames ? (unsigned)left : pcm_frames;
-    if (n) {
-        memcpy(buffer, r->pcm + r->cursor * r->channels, (size_t)n * r->channels * sizeof(int));
-        r->cursor += n;
+    /* as much as was asked for, unless the track ends first (behaviour of src/dvd-audio.c:751-795);
+       the parts behind the one being read are decoded meanwhile */
+    unsigned done = 0;
+    while (done < pcm_frames) {
+        if (!r->cur || r->cur_pos == r->cur_frames) {
+            if (!take_part(r)) break;
+        }
+        unsigned long long n = r->cur_frames - r->cur_pos;
+        if (n > pcm_frames - done) n = pcm_frames - done;
+        memcpy(buffer + (size_t)done * r->channels, r->cur->pcm + r->cur_skip + r->cur_pos * r->channels,
+               (size_t)n * r->channels * sizeof(int));
+        r->cur_pos += n;
+        done += (unsigned)n;
     }
-    return n;
+    return done;
 }

@@ -127,6 +127,69 @@ def test_public_api(pkg, oracle, disc_cache, name):
     d.close()
 
 
+@pytest.mark.parametrize("name,part", [("c5_mixed", 16), ("mlp_wild_0", 16), ("mlp_wild_1", 24), ("mlp_fir_carry", 16),
+                                       ("mlp_zero_yield", 16), ("pcm_rates_ragged", 16), ("pcm_layouts", 16),
+                                       ("c1_large", 300), ("c2_large", 256), ("c3_large", 500), ("mlp_short_segments", 16)])
+def test_public_api_reads_long_tracks_in_parts(pkg, oracle, disc_cache, name, part, monkeypatch):
+    """The track reader cuts a track into parts, decoded ahead of dvda_read() by the pool of engine
+    contexts and gathered in order (small parts here, so that every catalog track is "long"): PCM
+    windows with the frame budget carried over, MLP parts cut at restart points, a part that needs its
+    predecessor's filter history decoded together with it."""
+    monkeypatch.setenv("DVDA_B200_PART_SECTORS", str(part))
+    directory, _ = disc_cache(name)
+    d = pkg.Disc(directory)
+    try:
+        for g in GOLDEN[name]["tracks"]:
+            info, pcm = d.read_track(g["title"], g["track"], chunk=4096 if g["track"] % 2 else 1013)
+            assert (info["codec"], info["channels"], info["bits_per_sample"], info["sample_rate"], info["mask"]) == \
+                   (g["codec"], g["ch"], g["bps"], g["rate"], g["mask"])
+            assert len(pcm) == g["frames"], (name, g["title"], g["track"], len(pcm), g["frames"])
+            assert oracle.fnv1a(pcm) == g["fnv"], (name, g["title"], g["track"])
+    finally:
+        d.close()
+
+
+def test_reader_memory_is_bounded(pkg, oracle, tmp_path):
+    """A track of more than a gigabyte read through the public API: the pinned host memory of the
+    reader stays under 256 MB (the reference streams with O(1) state, src/dvd-audio.c:751-795), and
+    the samples are the reference's."""
+    import subprocess
+    import dvda_gen as g
+    import workloads
+    directory = str(tmp_path / "AUDIO_TS")
+    g.make_disc(directory, [[workloads.c2_track(96000 * 2200, 4242)]])          # 37 minutes of 24/96 stereo: ~1.12 GB of AOB
+    assert sum(os.path.getsize(os.path.join(directory, f)) for f in os.listdir(directory)) > 1 << 30
+    ref = subprocess.Popen([oracle.REF_DUMP, directory], stdout=subprocess.PIPE, text=True)
+    pkg.host_usage(reset_peak=True)
+    live0, _ = pkg.host_usage()
+    d = pkg.Disc(directory)
+    L = d.L
+    ts = L.dvda_open_titleset(d.h, 1)
+    ti = L.dvda_open_title(ts, 1)
+    tr = L.dvda_open_track(ti, 1)
+    rd = L.dvda_open_track_reader(tr)
+    assert rd
+    import ctypes
+    chunk = 1 << 16
+    buf = np.empty(chunk * 2, dtype=np.int32)
+    frames, h = 0, 0xCBF29CE484222325
+    while True:
+        got = L.dvda_read(rd, chunk, ctypes.c_void_p(buf.ctypes.data))
+        if not got:
+            break
+        h = g.lib().dvda_gen_fnv1a(ctypes.c_void_p(buf.ctypes.data), got * 8, h)
+        frames += got
+    _live, peak = pkg.host_usage()
+    L.dvda_close_track_reader(rd)
+    L.dvda_close_track(tr); L.dvda_close_title(ti); L.dvda_close_titleset(ts)
+    d.close()
+    assert peak - live0 < 256 << 20, "reader held %d MB of pinned memory" % ((peak - live0) >> 20)
+    out = ref.communicate()[0]
+    want = oracle.parse_dump_lines(out)[0]
+    assert frames == want["frames"] == 96000 * 2200
+    assert "%016x" % h == want["fnv"]
+
+
 def test_readers_on_several_threads(pkg, oracle, disc_cache):
     """Distinct track readers may be used from distinct threads (the reference keeps no
     global state on the read path; here they share one engine behind a lock)."""

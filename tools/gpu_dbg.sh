@@ -1,4 +1,4 @@
 #!/bin/bash
 out=gpurun_out
-DVDAGPU_DEBUG=1 timeout 600 python -m pytest tests -m gpu -x -q > $out/dbg.log 2>&1
-grep -E "attempt|buffer|passed|failed" $out/dbg.log | tail -40
+DVDA_B200_DEBUG=1 timeout 600 python -m pytest tests -m gpu -x -q -k "reads_long_tracks_in_parts and mlp_wild_1" > $out/dbg.log 2>&1
+grep -E "dvda\]|passed|failed" $out/dbg.log | head -60
