@@ -399,6 +399,7 @@ static int gen_pcm_track(mux_t *m, const dvda_gen_track_t *t, dvda_gen_info_t *i
     int32_t smp[12];
     const uint32_t range = bps24 ? (1u << 24) : (1u << 16);
     int64_t payload = 0;
+    int64_t emitted_frames = 0;
     while (made < frames || have) {
         while (made < frames && have + chunk <= buf_chunks * chunk) {
             for (int i = 0; i < 2 * ch; i++) {
@@ -411,8 +412,11 @@ static int gen_pcm_track(mux_t *m, const dvda_gen_track_t *t, dvda_gen_info_t *i
         /* emit sectors while at least one sector's worth (or the tail) is buffered */
         size_t off = 0;
         while (have - off >= 2100 || (made >= frames && have - off > 0)) {
+            /* from the middle of the track on: other stream parameters (the second group's rate code) */
+            if ((t->features & DVDA_GEN_PCM_PARAM_CHANGE) && emitted_frames >= frames / 2) params[4] = (uint8_t)((params[4] & 0xF0) | ((params[4] & 0x0F) ^ 0x01));
             size_t used = mux_audio_sector(m, 0xA0, params, buf + off, have - off, chunk);
             if (used == (size_t)-1) { free(buf); return -1; }
+            emitted_frames += (int64_t)(used / chunk) * 2;
             off += used;
             payload += (int64_t)used;
         }
@@ -1166,6 +1170,14 @@ static int gen_mlp_track(mux_t *m, genc_t *e, const dvda_gen_track_t *t, dvda_ge
         if (is_sync && a != 0 && (t->features & DVDA_GEN_SYNC_NO_RST) && rng_pct(&e->rng, 30)) with_restart = 0;
         const size_t before = bw_bytes(&e->au);
         if (encode_au(e, is_sync, with_restart, a == 0)) return -1;
+        if (is_sync && a != 0 && (t->features & DVDA_GEN_SYNC_PARAM_DUP) && rng_pct(&e->rng, 35)) {
+            /* the same access unit twice; the first copy's major sync states another channel
+               assignment, so the decoder drops it without looking inside */
+            const size_t n = bw_bytes(&e->au) - before;
+            for (size_t i = 0; i < n; i++) bw_put(&e->au, 8, e->au.buf[before + i]);
+            uint8_t *dup = e->au.buf + before;
+            dup[11] = (uint8_t)((dup[11] & 0xE0) | (((dup[11] & 0x1F) + 1) % 21));
+        }
         /* G6: a non-sync AU must not look like a sync to the byte scanner.  The
            scanner tests every byte position, so check the window around the AU. */
         (void)before;
@@ -1326,6 +1338,15 @@ int dvda_gen_disc(const char *dir, int n_titles, const int32_t *tracks_per_title
     free(m.pend);
 
     if (!rc) {
+        /* tracks whose tables point somewhere else than where their audio starts */
+        for (int k = 0; k < total; k++) {
+            if (!tracks[k].start_shift) continue;
+            int64_t s = (int64_t)info[k].first_sector + tracks[k].start_shift;
+            const int64_t lo = k > 0 ? (int64_t)info[k - 1].first_sector + 1 : 0;
+            if (s < lo) s = lo;
+            if (s > (int64_t)m.sectors - 1) s = (int64_t)m.sectors - 1;
+            info[k].first_sector = (uint32_t)s;
+        }
         /* last sectors as the reference derives them (dvd-audio.c:459-499) */
         int k = 0;
         for (int t = 0; t < n_titles; t++) {

@@ -38,7 +38,11 @@ enum {
     DVDA_GEN_RANDOM_PADS  = 1 << 14, /* random pad_1 / pad_2 / stuffing per packet */
     DVDA_GEN_PCM_RAGGED   = 1 << 15, /* PCM packets end in a partial chunk */
     DVDA_GEN_TWO_PACKETS  = 1 << 16, /* two audio packets in some sectors */
-    DVDA_GEN_MAX_ORDERS   = 1 << 17  /* alternate FIR4+IIR4 / FIR8 (entropy + filter stress) */
+    DVDA_GEN_MAX_ORDERS   = 1 << 17, /* alternate FIR4+IIR4 / FIR8 (entropy + filter stress) */
+    DVDA_GEN_SYNC_PARAM_DUP = 1 << 18, /* in front of some major-sync access units a copy of the unit whose major
+                                        sync states other stream parameters: the decoder drops it (mlp.c:449-455) */
+    DVDA_GEN_PCM_PARAM_CHANGE = 1 << 19 /* PCM: from the middle of the track on the packets state other stream
+                                        parameters: the track ends there (dvd-audio.c:1049-1055) */
 };
 
 typedef struct {
@@ -60,6 +64,9 @@ typedef struct {
     int32_t matrices;         /* MLP: max matrices per substream (0..6) */
     int32_t noise_bits;       /* MLP: log2 amplitude of the unpredictable signal part */
     int32_t min_lsbs;         /* MLP: lower bound for LSB_bits (stress), 0 = fit */
+    int32_t start_shift;      /* sectors added to the first sector the title's tables state for this track
+                                 (may be negative): a track that does not start where its audio does
+                                 (reference TODO:64-80; the reference probes from the stated sector on) */
 } dvda_gen_track_t;
 
 /* what was written for each track (outputs) */

@@ -31,6 +31,8 @@ RANDOM_PADS = 1 << 14
 PCM_RAGGED = 1 << 15
 TWO_PACKETS = 1 << 16
 MAX_ORDERS = 1 << 17
+SYNC_PARAM_DUP = 1 << 18
+PCM_PARAM_CHANGE = 1 << 19
 
 RATE_CODE = {48000: 0, 96000: 1, 192000: 2, 44100: 8, 88200: 9, 176400: 10}
 BPS_CODE = {16: 0, 24: 2}
@@ -57,6 +59,7 @@ class Track(ctypes.Structure):
         ("matrices", ctypes.c_int32),
         ("noise_bits", ctypes.c_int32),
         ("min_lsbs", ctypes.c_int32),
+        ("start_shift", ctypes.c_int32),
     ]
 
 
@@ -98,22 +101,22 @@ def lib():
     return _lib
 
 
-def pcm(frames, bps=16, rate=48000, assignment=1, seed=1, features=0):
+def pcm(frames, bps=16, rate=48000, assignment=1, seed=1, features=0, start_shift=0):
     return dict(codec=0, bps_code=BPS_CODE[bps], rate_code=RATE_CODE[rate],
-                assignment=assignment, frames=frames, seed=seed, features=features)
+                assignment=assignment, frames=frames, seed=seed, features=features, start_shift=start_shift)
 
 
 def mlp(frames, bps=24, rate=96000, assignment=1, seed=1, features=CHECKDATA,
         substreams=1, au_frames=0, restart_interval=16, max_blocks=1,
         fir_max=4, iir_max=4, codebooks=0xF, matrices=0, noise_bits=12,
-        min_lsbs=0, join_previous=0):
+        min_lsbs=0, join_previous=0, start_shift=0):
     return dict(codec=1, bps_code=BPS_CODE[bps], rate_code=RATE_CODE[rate],
                 assignment=assignment, frames=frames, seed=seed, features=features,
                 substreams=substreams, au_frames=au_frames,
                 restart_interval=restart_interval, max_blocks=max_blocks,
                 fir_max=fir_max, iir_max=iir_max, codebooks=codebooks,
                 matrices=matrices, noise_bits=noise_bits, min_lsbs=min_lsbs,
-                join_previous=join_previous)
+                join_previous=join_previous, start_shift=start_shift)
 
 
 def make_disc(directory, titles, max_aob_bytes=0):

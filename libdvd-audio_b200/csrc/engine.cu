@@ -800,7 +800,9 @@ static int decode_enqueue(dvdagpu_ctx *c)
             }
             TRY(launch_plan_check(cnt, lim, s));
             TRY(launch_au_chase(es, m.segs, cap_seg, cnt, d_tracks, seg_nau, m.au_pos, m.au_seg, seg_au_base, au_noted, 1, s));
-            TRY(launch_yield(m, rows, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), s));
+            bool any_parts = false;
+            for (uint32_t i = 0; i < n_tracks; i++) any_parts |= (ht[i].cont & TRACK_CONT_NEXT) != 0;
+            TRY(launch_yield(m, rows, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), any_parts, s));
             CUDA_TRY(record_timing(c->ev[2], s));
 
             // ---------------- decode
@@ -1157,7 +1159,8 @@ extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sec
             if (stop || fallback) return 0;                  // (drained only)
             // anything the parts cannot express: decode in one piece instead
             if (r.status != 0 || r.codec != 1 || r.stopped == 2 || (r.truncated && i + 1 < parts) ||
-                (i && (r.channels != merged.channels || r.sample_rate != merged.sample_rate))) { fallback = true; return 0; }
+                (i && (r.channels != merged.channels || r.sample_rate != merged.sample_rate || r.bits_per_sample != merged.bits_per_sample ||
+                       r.channel_assignment != merged.channel_assignment))) { fallback = true; return 0; }
             if (i == 0) merged = r;
             const uint64_t n = r.frames * r.channels;
             if (total_samples + n > pcm_capacity) return 3;

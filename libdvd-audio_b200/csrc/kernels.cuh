@@ -122,8 +122,9 @@ size_t au_noted_bytes(uint32_t nseg);
 int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t cap_seg, const DecCounts *cnt, const TrackDev *tracks,
                     uint32_t *seg_nau, uint64_t *au_pos, uint32_t *au_seg, const uint32_t *seg_au_base,
                     uint32_t *noted, int fill, cudaStream_t s);
+// any_parts: some track of the batch is a part that is continued by another one
 int launch_yield(MlpTables m, uint32_t rows, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
-                 uint8_t *pk_yield, cudaStream_t s);
+                 uint8_t *pk_yield, bool any_parts, cudaStream_t s);
 int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_grp_base, const SegDev *segs,
                        GroupDev *groups, uint32_t cap_grp, DecCounts *cnt, uint32_t *grp_cells, const uint32_t *seg_need, cudaStream_t s);
 int launch_group_offsets(GroupDev *groups, uint32_t cap_grp, const DecCounts *cnt, const uint64_t *cell_base, cudaStream_t s);

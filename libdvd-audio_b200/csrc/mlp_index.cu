@@ -637,6 +637,7 @@ int launch_au_chase(const uint8_t *es, SegDev *segs, uint32_t cap_seg, const Dec
 // in which no access unit ends terminates the track.  Mark the packets in which
 // some access unit ends, then find the first unmarked one per track.
 
+__device__ __forceinline__ bool au_yields(const uint8_t *p, uint32_t total, const TrackDev &T);
 __global__ void k_yield_mark(MlpTables m, const uint32_t *__restrict__ seg_au_base, uint8_t *__restrict__ pk_yield)
 {
     // The access units of a warp follow each other in the stream and end within a handful of
@@ -647,10 +648,15 @@ __global__ void k_yield_mark(MlpTables m, const uint32_t *__restrict__ seg_au_ba
     const uint32_t np = (uint32_t)m.cnt->np;
     if (!__any_sync(0xFFFFFFFFu, have)) return;
     uint64_t last_byte = 0;
+    bool yields = false;
     if (have) {
         const uint64_t pos = m.au_pos[a];
-        const uint32_t total = (((ld_u8(m.es + pos) & 15u) << 8) | ld_u8(m.es + pos + 1)) * 2;
+        const uint8_t *p = m.es + pos;
+        const uint32_t total = (((ld_u8(p) & 15u) << 8) | ld_u8(p + 1)) * 2;
         last_byte = pos + total - 1;
+        // An access unit whose major sync states other stream parameters than the track's is dropped
+        // (mlp.c:449-455): it yields no frames, so it does not keep its packet alive either.
+        yields = au_yields(p, total, m.tracks[m.segs[m.au_seg[a]].track]);
     }
     const uint64_t x0 = __shfl_sync(0xFFFFFFFFu, last_byte, 0);          // lane 0 has the lowest access unit
     const uint64_t *pk_es = m.pk_es;
@@ -658,9 +664,43 @@ __global__ void k_yield_mark(MlpTables m, const uint32_t *__restrict__ seg_au_ba
     if (have) {
         if (last_byte < x0) pk = upper_bound_dev(m.pk_es, np + 1, last_byte) - 1;   // (not in stream order: on its own)
         else while (pk + 1 <= np && pk_es[pk + 1] <= last_byte) pk++;
-        pk_yield[pk] = 1;
+        if (yields) pk_yield[pk] = 1;
     }
     (void)seg_au_base;
+}
+
+// does the access unit at p (total bytes) yield frames, i.e. is it not one of those dropped for a
+// major sync that states other stream parameters than the track's (mlp.c:449-455)?
+__device__ __forceinline__ bool au_yields(const uint8_t *p, uint32_t total, const TrackDev &T)
+{
+    if (total < 32 || ld_be32(p + 4) != 0xF8726FBBu) return true;
+    const uint32_t ns = ld_u8(p + 20) >> 4;
+    if (ns != 1 && ns != 2) return true;
+    const uint32_t b8 = ld_u8(p + 8), b9 = ld_u8(p + 9), asg = ld_u8(p + 11) & 31;
+    return !((b8 >> 4) != T.g0_bps || (b8 & 15) != T.g1_bps || (b9 >> 4) != T.g0_rate || (b9 & 15) != T.g1_rate || asg != T.assignment);
+}
+
+// A part that is continued shares the packet its cut lies in with the part behind it: access units of
+// that part may end in the packet too, and keep it alive.  One thread per track walks on from the cut
+// while the access units still end inside that packet.
+__global__ void k_yield_tail(MlpTables m, uint8_t *__restrict__ pk_yield)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m.n_tracks) return;
+    const TrackDev &T = m.tracks[t];
+    if (T.status != 0 || T.codec != 1 || !(T.cont & TRACK_CONT_NEXT) || T.truncated || T.es_end <= T.es_start) return;
+    const uint32_t np = (uint32_t)m.cnt->np;
+    const uint32_t pk = upper_bound_dev(m.pk_es, np + 1, T.es_end - 1) - 1;      // the packet of the last byte in front of the cut
+    if (pk >= np) return;
+    const uint64_t pk_end = m.pk_es[pk + 1];
+    uint64_t pos = T.es_end;
+    const uint64_t avail = m.pk_es[min(T.pk_hi, np)];
+    while (pos + 4 <= pk_end && pos + 4 <= avail) {
+        const uint32_t total = (((ld_u8(m.es + pos) & 15u) << 8) | ld_u8(m.es + pos + 1)) * 2;
+        if (total < 4 || pos + total > pk_end) break;
+        if (au_yields(m.es + pos, total, T)) { pk_yield[pk] = 1; break; }
+        pos += total;
+    }
 }
 
 __global__ void k_yield_find(MlpTables m, PacketTable pt, const uint32_t *__restrict__ trk_pk_lo,
@@ -682,11 +722,12 @@ __global__ void k_yield_find(MlpTables m, PacketTable pt, const uint32_t *__rest
 }
 
 int launch_yield(MlpTables m, uint32_t rows, const uint32_t *seg_au_base, PacketTable pt, const uint32_t *trk_pk_lo,
-                 uint8_t *pk_yield, cudaStream_t s)
+                 uint8_t *pk_yield, bool any_parts, cudaStream_t s)
 {
     if (!rows) return 0;
     CUDA_TRY(cudaMemsetAsync(pk_yield, 0, rows, s));
     if (m.cap_au) LAUNCH(k_yield_mark, div_up_u32(m.cap_au, 256), 256, 0, s, m, seg_au_base, pk_yield);
+    if (any_parts) LAUNCH(k_yield_tail, div_up_u32(m.n_tracks, 128), 128, 0, s, m, pk_yield);
     LAUNCH(k_yield_find, div_up_u32(rows, 256), 256, 0, s, m, pt, trk_pk_lo, pk_yield);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -669,15 +669,22 @@ static int take_part(DVDA_Track_Reader *r)
         if (j->rc || j->res.status != DVDAGPU_TRACK_OK) { r->ended = 1; return 0; }
         unsigned long long skip = 0;
         const int is_pcm = j->res.codec == 0;
-        if (!is_pcm && j->res.stopped == 2) {
-            /* the part needs the filter history of the one before it (FIR state survives a restart
-               header, mlp.c:948-952): both are decoded as one window, the samples of the part before
-               are dropped */
+        const int other_params = index > 0 && (j->res.channels != r->channels || j->res.sample_rate != r->rate ||
+                                               j->res.bits_per_sample != r->bits || j->res.channel_assignment != r->assignment ||
+                                               (is_pcm ? DVDA_PCM : DVDA_MLP) != r->codec);
+        if (!is_pcm && index > 0 && r->codec == DVDA_MLP && (j->res.stopped == 2 || other_params)) {
+            /* The part cannot stand alone: it needs the decoder state of the one before it (FIR
+               history survives a restart header, mlp.c:948-952; a major sync without restart header),
+               or it begins at a major sync that states other stream parameters than the track's (such
+               an access unit is dropped, mlp.c:449-455 — but only the track's first sync says what
+               the track's parameters are).  Both parts are decoded as one window, the samples of the
+               part before are dropped. */
             const unsigned long long sectors = j->first + j->desc.last_sector + 1 - r->prev_first;
             const unsigned flags = (r->prev_flags & DVDAGPU_PART_CONTINUES_PREVIOUS) | (j->desc.flags & DVDAGPU_PART_CONTINUED_BY_NEXT);
             if (submit_window(r, j, r->prev_first, sectors, PART_MARGIN, r->pts_length, flags)) { r->ended = 1; return 0; }
             job_wait(j);
-            if (j->rc || j->res.status != DVDAGPU_TRACK_OK || j->res.stopped == 2 || j->res.frames < r->prev_frames) { r->ended = 1; return 0; }
+            if (j->rc || j->res.status != DVDAGPU_TRACK_OK || j->res.stopped == 2 || j->res.frames < r->prev_frames ||
+                j->res.channels != r->channels || j->res.sample_rate != r->rate || j->res.channel_assignment != r->assignment) { r->ended = 1; return 0; }
             skip = r->prev_frames;
             /* (the parts already submitted behind it were cut at the same places: they stay valid) */
         } else if (!is_pcm && j->res.truncated && !(j->desc.flags & DVDAGPU_PART_CONTINUED_BY_NEXT) &&
@@ -699,8 +706,7 @@ static int take_part(DVDA_Track_Reader *r)
                 r->next_sector = j->first + j->got;
                 r->no_more = 0;
             }
-        } else if (j->res.channels != r->channels || j->res.sample_rate != r->rate || j->res.bits_per_sample != r->bits ||
-                   (is_pcm ? DVDA_PCM : DVDA_MLP) != r->codec) {
+        } else if (skip == 0 && other_params) {
             r->ended = 1;               /* the stream changed its parameters: the track is over (dvd-audio.c:1049-1055) */
             return 0;
         }

@@ -98,7 +98,30 @@ def discs():
     d["mlp_short_segments"] = [[g.mlp(4000, seed=800, restart_interval=1, rate=48000),
                                 g.mlp(4000, seed=801, restart_interval=1, rate=48000, join_previous=1),
                                 g.mlp(4000, seed=802, restart_interval=2, max_blocks=4, features=RICH, matrices=2)]]
+    # ---- behaviours of the reference that have no other fixture
+    # a later major sync that states other stream parameters: the access unit is dropped (mlp.c:449-455)
+    d["mlp_param_dup"] = [[g.mlp(8000, rate=48000, seed=900, features=g.CHECKDATA | g.SYNC_PARAM_DUP, restart_interval=4),
+                           g.mlp(6000, seed=901, assignment=12, substreams=2, matrices=3, features=RICH | g.SYNC_PARAM_DUP,
+                                 restart_interval=3),
+                           g.mlp(12000, rate=192000, seed=902, features=g.CHECKDATA | g.SYNC_PARAM_DUP, restart_interval=2,
+                                 noise_bits=18)]]
+    # PCM packets that change the stream parameters end the track (dvd-audio.c:1049-1055)
+    d["pcm_param_change"] = [[g.pcm(6000, bps=16, seed=910, features=g.PCM_PARAM_CHANGE),
+                              g.pcm(5000, bps=24, assignment=12, rate=96000, seed=911, features=g.PCM_PARAM_CHANGE | g.RANDOM_PADS),
+                              g.pcm(3000, bps=16, seed=912)]]
+    # tracks whose tables do not point at the sector their audio starts in (reference TODO:64-80)
+    d["late_start"] = [[g.mlp(8000, seed=920, restart_interval=4),
+                        g.mlp(8000, seed=921, restart_interval=4, join_previous=1, start_shift=-3),
+                        g.mlp(6000, seed=922, restart_interval=4, join_previous=1, start_shift=2),
+                        g.pcm(6000, seed=923), g.pcm(6000, seed=924, start_shift=1)]]
+    # tracks that start in, end in and span AOB file boundaries (aob.c:101-123, 181-199): see MAX_AOB_BYTES
+    d["aob_split"] = [[g.mlp(20000, seed=930, restart_interval=8), g.pcm(40000, bps=24, rate=96000, seed=931),
+                       g.mlp(16000, seed=932, assignment=12, substreams=2, matrices=2, features=RICH)]]
     return d
+
+
+# discs whose AOB stream is cut into several files (dvda_gen's max_aob_bytes)
+MAX_AOB_BYTES = {"aob_split": 60 * 2048}
 
 
 GPU_LARGE = {

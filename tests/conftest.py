@@ -72,7 +72,7 @@ def disc_cache(tmp_path_factory, gen):
     def get(name):
         if name not in made:
             d = str(tmp_path_factory.mktemp(name))
-            made[name] = (d, gen.make_disc(d, specs[name]))
+            made[name] = (d, gen.make_disc(d, specs[name], catalog.MAX_AOB_BYTES.get(name, 0)))
         return made[name]
 
     return get

@@ -35,7 +35,7 @@ def main():
     specs.update(catalog.GPU_LARGE)
     for name, titles in specs.items():
         with tempfile.TemporaryDirectory() as d:
-            dvda_gen.make_disc(d, titles)
+            dvda_gen.make_disc(d, titles, catalog.MAX_AOB_BYTES.get(name, 0))
             rc, tracks, _samples, err = oracle.run_dump(oracle.REF_DUMP, d)
             if rc != 0:
                 raise SystemExit("reference failed on %s: %s" % (name, err))

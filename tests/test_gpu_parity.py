@@ -112,7 +112,8 @@ def test_tables_sized_in_advance_grow(pkg, oracle, disc_cache, name, monkeypatch
         eng.close()
 
 
-@pytest.mark.parametrize("name", ["c5_mixed", "mlp_wild_1", "pcm_rates_ragged", "mlp_zero_yield"])
+@pytest.mark.parametrize("name", ["c5_mixed", "mlp_wild_1", "pcm_rates_ragged", "mlp_zero_yield", "aob_split", "late_start",
+                                  "pcm_param_change", "mlp_param_dup"])
 def test_public_api(pkg, oracle, disc_cache, name):
     """dvda_open .. dvda_open_track_reader .. dvda_read, as a program written for the
     reference would call it (odd read sizes included)."""
@@ -129,7 +130,8 @@ def test_public_api(pkg, oracle, disc_cache, name):
 
 @pytest.mark.parametrize("name,part", [("c5_mixed", 16), ("mlp_wild_0", 16), ("mlp_wild_1", 24), ("mlp_fir_carry", 16),
                                        ("mlp_zero_yield", 16), ("pcm_rates_ragged", 16), ("pcm_layouts", 16),
-                                       ("c1_large", 300), ("c2_large", 256), ("c3_large", 500), ("mlp_short_segments", 16)])
+                                       ("c1_large", 300), ("c2_large", 256), ("c3_large", 500), ("mlp_short_segments", 16),
+                                       ("aob_split", 16), ("late_start", 16), ("pcm_param_change", 16), ("mlp_param_dup", 16)])
 def test_public_api_reads_long_tracks_in_parts(pkg, oracle, disc_cache, name, part, monkeypatch):
     """The track reader cuts a track into parts, decoded ahead of dvda_read() by the pool of engine
     contexts and gathered in order (small parts here, so that every catalog track is "long"): PCM
