@@ -163,32 +163,130 @@ __global__ void k_packet_flags(PacketTable pt, uint32_t rows, const uint32_t *__
 // One warp per MLP packet: payload bytes -> ES[es_off ...].  Byte-granular on
 // both sides (neither side is aligned); lanes take consecutive bytes so the
 // accesses coalesce into 32-byte segments.
-// (one warp per row of the packet table: the rows behind the last packet carry no bytes)
-__global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t rows,
-                            const uint64_t *__restrict__ pk_es, uint8_t *__restrict__ es)
+//
+// While it has the bytes in hand the warp also looks for the major-sync pattern F8 72 6F BB
+// (dvd-audio.c:1250-1286 find_major_sync tests exactly these four bytes, at offset 4 of an access
+// unit): every position whose first byte lies in this packet is this warp's, the few positions at
+// the packet's edges — the pattern may run on into the next packet — are checked byte by byte
+// through the packet table.  A match goes to the slots of its 512-byte chunk of the stream
+// (k_sync_validate / k_sync_emit order and judge them later): the elementary stream is not read
+// again for the search.
+__device__ __forceinline__ uint32_t stream_byte(const uint8_t *__restrict__ sectors, const PacketTable &pt, uint32_t np,
+                                                uint32_t row, uint32_t q, bool &have)
+{
+    // byte q of the stream counted from the first payload byte of packet `row` (q may lie in a later packet)
+    while (row < np) {
+        const uint32_t n = pt.mlp_len[row];
+        if (q < n) { have = true; return ld_u8(sectors + (uint64_t)pt.sector[row] * DVDA_SECTOR + pt.off[row] + pt.pad2[row] + q); }
+        q -= n;
+        row++;
+    }
+    have = false;
+    return 0;
+}
+__device__ __forceinline__ void sync_note(uint64_t p, uint32_t *__restrict__ cnt_raw, uint16_t *__restrict__ slots, uint32_t nslots)
+{
+    const uint32_t chunk = (uint32_t)(p / SYNC_CHUNK);
+    const uint32_t i = atomicAdd(&cnt_raw[chunk], 1u);
+    if (i < nslots) slots[(uint64_t)chunk * 2 + i] = (uint16_t)(p % SYNC_CHUNK);
+}
+__global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt, uint32_t rows, const DecCounts *__restrict__ cnt,
+                            const uint64_t *__restrict__ pk_es, uint8_t *__restrict__ es,
+                            uint32_t *__restrict__ cnt_raw, uint16_t *__restrict__ slots, uint32_t nslots)
 {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (warp >= rows) return;
+    // (a warp lives for a few memory latencies: everything it will need from the tables is asked
+    // for up front, the next packet's row included)
     const uint32_t n = pt.mlp_len[warp];
-    if (!n) return;
+    const uint32_t np = (uint32_t)cnt->np;
+    uint32_t nrow = warp + 1 < np ? warp + 1 : warp;
+    const uint32_t nlen0 = pt.mlp_len[nrow];
     const uint8_t *src = sectors + (uint64_t)pt.sector[warp] * DVDA_SECTOR + pt.off[warp] + pt.pad2[warp];
-    uint8_t *dst = es + pk_es[warp];
+    const uint8_t *nsrc = sectors + (uint64_t)pt.sector[nrow] * DVDA_SECTOR + pt.off[nrow] + pt.pad2[nrow];
+    const uint64_t es_off = pk_es[warp];
+    if (!n) return;
+    uint32_t nlen = warp + 1 < np ? nlen0 : 0u;
+    if (!nlen && warp + 1 < np) {
+        // (the next row carries no stream bytes: look further)
+        nrow = warp + 1;
+        while (nrow < np && pt.mlp_len[nrow] == 0) nrow++;
+        if (nrow < np) { nlen = pt.mlp_len[nrow]; nsrc = sectors + (uint64_t)pt.sector[nrow] * DVDA_SECTOR + pt.off[nrow] + pt.pad2[nrow]; }
+    }
+    uint8_t *dst = es + es_off;
     // head bytes up to a 4-byte boundary of dst, then whole words, then the tail
     const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
-    if (lane < head) dst[lane] = ld_u8(src + lane);
     const uint32_t words = (n - head) >> 2;
     const uint8_t *s = src + head;
     uint32_t *d = reinterpret_cast<uint32_t *>(dst + head);
     const uint32_t mis = (uint32_t)((uintptr_t)s & 3);
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(s - mis);
-    for (uint32_t i = lane; i < words; i += 32) {
-        const uint32_t a = __ldg(sw + i);
-        const uint32_t b = mis ? __ldg(sw + i + 1) : 0;   // still inside the sector (or the pad behind the buffer)
-        d[i] = __funnelshift_r(a, b, mis * 8);
+    // payload offset of the first byte of source word i: lo_w + 4 i
+    const int32_t lo_w = (int32_t)head - (int32_t)mis;
+
+    // The positions the words below do not cover: in front of the first word, behind the last one,
+    // and the last three of the packet, whose pattern would run on into the next packet.  A lane
+    // each (a dozen at most), loaded now, looked at when the copy is done.  (A pattern that would
+    // need more than the next packet with bytes — packets of under three bytes — goes the long way
+    // through the table.)
+    const int32_t hi_w = lo_w + 4 * (int32_t)words;        // first position behind the words' range
+    const uint32_t n_lo = lo_w > 0 ? (uint32_t)lo_w : 0u;
+    uint32_t first_hi = hi_w > 0 ? (uint32_t)hi_w : 0u;
+    if (n >= 3 && first_hi > n - 3) first_hi = n - 3;      // (positions behind n - 4 are nobody's in the loop below)
+    if (first_hi < n_lo) first_hi = n_lo;
+    const uint32_t n_edge = n_lo + (n > first_hi ? n - first_hi : 0u);
+    uint32_t edge_q = 0, edge_v = 0;
+    bool edge_ok = false;
+    if (lane < n_edge) {
+        edge_q = lane < n_lo ? lane : first_hi + (lane - n_lo);
+        edge_ok = true;
+        if (edge_q + 4 <= n) {
+            for (uint32_t k = 0; k < 4; k++) edge_v |= ld_u8(src + edge_q + k) << (8 * k);
+        } else if (edge_q + 4 - n <= nlen) {
+            for (uint32_t k = 0; k < 4; k++) edge_v |= (edge_q + k < n ? ld_u8(src + edge_q + k) : ld_u8(nsrc + (edge_q + k - n))) << (8 * k);
+        } else {
+            for (uint32_t k = 0; k < 4 && edge_ok; k++) {
+                bool have;
+                edge_v |= stream_byte(sectors, pt, np, warp, edge_q + k, have) << (8 * k);
+                edge_ok = have;
+            }
+        }
+    }
+
+    if (lane < head) dst[lane] = ld_u8(src + lane);
+    // The copy loop stays free of branches (its loads run ahead of one another); it only notes, a bit
+    // per round, in which of this lane's source words a byte F8 — the pattern's first — occurred
+    // (three instructions, true for one word in sixty).  Those words are looked at again below.
+    uint32_t seen = 0;
+    {
+        uint32_t j = 0;
+        for (uint32_t i = lane; i < words; i += 32, j++) {
+            const uint32_t a = __ldg(sw + i);
+            const uint32_t b = mis ? __ldg(sw + i + 1) : 0u;      // still inside the payload
+            d[i] = __funnelshift_r(a, b, mis * 8);
+            const uint32_t t = a ^ 0xF8F8F8F8u;
+            seen |= ((t - 0x01010101u) & ~t & 0x80808080u) ? 1u << (j & 31) : 0u;
+        }
+    }
+    while (seen) {
+        const uint32_t j = __ffs(seen) - 1;
+        seen &= seen - 1;
+        // (payloads are at most 2 KiB: 16 rounds; a bit stands for rounds j, j + 32, ... all the same)
+        for (uint32_t i = lane + 32 * j; i < words; i += 32 * 32) {
+            const uint32_t a = __ldg(sw + i);
+            const uint32_t b = lo_w + 4 * (int32_t)(i + 1) < (int32_t)n ? __ldg(sw + i + 1) : 0u;   // (only where it still holds payload bytes)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int32_t q = lo_w + 4 * (int32_t)i + k;
+                if (__funnelshift_r(a, b, 8 * k) == 0xBB6F72F8u && q >= 0 && (uint32_t)q + 4 <= n && es_off + (uint32_t)q >= 4)
+                    sync_note(es_off + (uint32_t)q - 4, cnt_raw, slots, nslots);
+            }
+        }
     }
     const uint32_t tail0 = head + words * 4;
     if (tail0 + lane < n) dst[tail0 + lane] = ld_u8(src + tail0 + lane);
+    if (edge_ok && edge_v == 0xBB6F72F8u && es_off + edge_q >= 4) sync_note(es_off + edge_q - 4, cnt_raw, slots, nslots);
 }
 
 // Zero bytes behind the stream (bit readers may run ahead), and the packet table's capacity:
@@ -298,9 +396,9 @@ int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_
     return 0;
 }
 int launch_es_gather(const uint8_t *sectors, PacketTable pt, uint32_t rows, const uint64_t *pk_es, uint8_t *es,
-                     DecCounts *cnt, cudaStream_t s)
+                     DecCounts *cnt, uint32_t *cnt_raw, uint16_t *slots, uint32_t nslots, cudaStream_t s)
 {
-    if (rows) LAUNCH(k_es_gather, div_up_u32((uint64_t)rows * 32, 256), 256, 0, s, sectors, pt, rows, pk_es, es);
+    if (rows) LAUNCH(k_es_gather, div_up_u32((uint64_t)rows * 32, 256), 256, 0, s, sectors, pt, rows, cnt, pk_es, es, cnt_raw, slots, nslots < 2 ? nslots : 2u);
     LAUNCH(k_es_tail, 1, 256, 0, s, es, cnt, rows);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -109,7 +109,7 @@ enum {
     B_SECTORS, B_SECTORS2, B_PCM2, B_SEC_CNT, B_SEC_BAD, B_SEC_BASE, B_BAD_PREFIX,
     B_PK_SECTOR, B_PK_OFF, B_PK_LEN, B_PK_CODEC, B_PK_PAD2, B_PK_PARAMS, B_PK_MLPLEN, B_PK_PCMF,
     B_PK_ES, B_PK_PF, B_PK_NONMLP, B_PK_NM_PREFIX, B_PK_STOP, B_PK_STOP_PREFIX, B_PK_YIELD,
-    B_ES, B_SYNC_SLOTS, B_SYNC_CNT_RAW, B_SYNC_CNT_VALID, B_SYNC_BASE_RAW, B_SYNC_BASE_VALID, B_RAW, B_VALID,
+    B_ES, B_SYNC_SLOTS, B_SYNC_CNT_RAW, B_SYNC_BASE_RAW, B_SYNC_BASE_VALID, B_RAW, B_VALID,
     B_TRACKS, B_TRK_PK_LO, B_TRK_SEG_BASE, B_TRK_GRP_BASE,
     B_SEGS, B_SEG_NAU, B_SEG_AU_BASE, B_AU_POS, B_AU_ERR, B_AU, B_PSETS, B_AU_FRAMES,
     B_SS_FLAGS, B_SS_FLAGS_PREV, B_SS_FLAGS_FAST, B_FIR_TAIL,
@@ -623,7 +623,7 @@ static int decode_enqueue(dvdagpu_ctx *c)
         ENSURE(B_PK_STOP, npa * 4); ENSURE(B_PK_STOP_PREFIX, npa * 4);
         ENSURE(B_PK_YIELD, npa);
         ENSURE(B_ES, es_cap + 16 + DVDA_ES_PAD);
-        ENSURE(B_SYNC_CNT_RAW, (size_t)chunks_cap * 4); ENSURE(B_SYNC_CNT_VALID, (size_t)chunks_cap * 4);
+        ENSURE(B_SYNC_CNT_RAW, (size_t)chunks_cap * 8);           // raw counts, then valid counts
         ENSURE(B_SYNC_BASE_RAW, (size_t)(chunks_cap + 1) * 4); ENSURE(B_SYNC_BASE_VALID, (size_t)(chunks_cap + 1) * 4);
         ENSURE(B_SYNC_SLOTS, (size_t)chunks_cap * SYNC_SLOT_BYTES);
         ENSURE(B_RAW, ((size_t)cap_sync + 1) * 8); ENSURE(B_VALID, ((size_t)cap_sync + 1) * 8);
@@ -718,16 +718,18 @@ static int decode_enqueue(dvdagpu_ctx *c)
             TRY(scan_batch(in, out, wide, 4, rows, tmp, tmp_bytes, s, copy));
         }
         uint8_t *es = c->buf[B_ES].as<uint8_t>();
-        TIMED(DVDAGPU_K_ES_GATHER, launch_es_gather(d_sectors, pt, rows, pk_es, es, cnt, s));
+        uint16_t *sync_slots = c->buf[B_SYNC_SLOTS].as<uint16_t>();
+        // (the two count tables are one buffer: cleared together; the gather counts the sync patterns it meets)
+        uint32_t *cnt_raw = c->buf[B_SYNC_CNT_RAW].as<uint32_t>(), *cnt_valid = cnt_raw + chunks_cap;
+        CUDA_TRY(cudaMemsetAsync(cnt_raw, 0, (size_t)chunks_cap * 8, s));
+        TIMED(DVDAGPU_K_ES_GATHER, launch_es_gather(d_sectors, pt, rows, pk_es, es, cnt, cnt_raw, sync_slots, nslots, s));
         CUDA_TRY(record_timing(c->ev[1], s));
 
         // ---------------- index
-        uint16_t *sync_slots = c->buf[B_SYNC_SLOTS].as<uint16_t>();
-        uint32_t *cnt_raw = c->buf[B_SYNC_CNT_RAW].as<uint32_t>(), *cnt_valid = c->buf[B_SYNC_CNT_VALID].as<uint32_t>();
         uint32_t *base_raw = c->buf[B_SYNC_BASE_RAW].as<uint32_t>(), *base_valid = c->buf[B_SYNC_BASE_VALID].as<uint32_t>();
         uint64_t *raw = c->buf[B_RAW].as<uint64_t>(), *valid = c->buf[B_VALID].as<uint64_t>();
         if (sh.any_mlp) {
-            TIMED(DVDAGPU_K_SYNC_SCAN, launch_sync_count(es, cnt, chunks_cap, cnt_raw, cnt_valid, sync_slots, nslots, s));
+            TIMED(DVDAGPU_K_SYNC_SCAN, launch_sync_validate(es, cnt, chunks_cap, cnt_raw, cnt_valid, sync_slots, nslots, s));
             const uint32_t *in[2] = {cnt_raw, cnt_valid}; void *out[2] = {base_raw, base_valid}; const bool wide[2] = {false, false};
             uint64_t *const copy[2] = {&cnt->n_raw, &cnt->n_valid};
             TRY(scan_batch(in, out, wide, 2, chunks_cap, tmp, tmp_bytes, s, copy));

@@ -70,8 +70,10 @@ int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_
                        uint32_t *nonmlp, uint32_t *pcm_stop, cudaStream_t s);
 // one warp per row of the packet table (the rows behind the last packet are empty); also zeroes the
 // pad behind the stream and checks the table's capacity against the packet count
+// ... and notes the major-sync patterns it comes across in the slots of their 512-byte chunks
+// (cnt_raw must be zero before)
 int launch_es_gather(const uint8_t *sectors, PacketTable pt, uint32_t rows, const uint64_t *pk_es, uint8_t *es,
-                     DecCounts *cnt, cudaStream_t s);
+                     DecCounts *cnt, uint32_t *cnt_raw, uint16_t *slots, uint32_t nslots, cudaStream_t s);
 int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t rows, const DecCounts *cnt, const uint32_t *status,
                       const uint64_t *pk_pf, const TrackDev *tracks, const uint32_t *trk_pk_lo, uint32_t n_tracks, int32_t *pcm, cudaStream_t s);
 
@@ -79,8 +81,9 @@ int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t rows, con
 #define SYNC_CHUNK 512u           // ES bytes per warp step of the sync search
 #define SYNC_SLOT_BYTES 4u        // per chunk: 2 slots of 16 bits
 // chunks_cap: chunks the stream buffer has room for (the stream's size is still on the device)
-int launch_sync_count(const uint8_t *es, const DecCounts *cnt, uint32_t chunks_cap, uint32_t *cnt_raw, uint32_t *cnt_valid,
-                      uint16_t *slots, uint32_t nslots, cudaStream_t s);
+// the chunks' matches (found by the gather) put in order and judged: which of them start a restart segment
+int launch_sync_validate(const uint8_t *es, const DecCounts *cnt, uint32_t chunks_cap, const uint32_t *cnt_raw, uint32_t *cnt_valid,
+                         uint16_t *slots, uint32_t nslots, cudaStream_t s);
 int launch_sync_fill(const uint8_t *es, const DecCounts *cnt, uint32_t chunks_cap, const uint32_t *cnt_raw, const uint16_t *slots, uint32_t nslots,
                      const uint32_t *base_raw, const uint32_t *base_valid, uint64_t *raw, uint32_t cap_raw,
                      uint64_t *valid, uint32_t cap_valid, cudaStream_t s);

@@ -300,6 +300,7 @@ struct __align__(16) AuDelta {
 static_assert(offsetof(AuDelta, cf) == 80 && sizeof(AuDelta) % 16 == 0, "AuDelta layout");
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- filter passes: one channel's set-up from the delta of an access unit -----------------
 struct FiltSetup { uint32_t fo, io, fsh, ish, q; };      // orders, shifts, quant_step_size in force

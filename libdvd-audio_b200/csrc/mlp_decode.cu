@@ -1572,6 +1572,9 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
 #define OUT_WARP_WORDS (2 * OUT_PATCH_WORDS + 4 * 32)   // two patches, used in turn (bulk stores in flight) + per segment {output base lo, hi, frames, aligned}
 #define OUT_SMEM_BYTES (OUT_WARPS * OUT_WARP_WORDS * 4)
 #define OUT_MAX_LPS 8
+#ifndef OUT_PREFETCH
+#define OUT_PREFETCH 3                                  // batches of eight frames the L2 prefetch runs ahead of the loads
+#endif
 
 __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_out(MlpTables m, const OutWork *__restrict__ work)
 {
@@ -1735,6 +1738,12 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
             for (int t = 0; t < 8; t++) r[t] = nx[t];
 #pragma unroll
             for (int t = 0; t < 8; t++) nx[t] = tp[t * tile_step];
+            // ... and the frames three batches further on are asked into L2: the loads above then
+            // find them there, a batch of filtering is more than an L2 latency but less than a DRAM one
+            if (f + 8 * (OUT_PREFETCH + 2) <= my_frames) {
+#pragma unroll
+                for (int t = 0; t < 8; t++) prefetch_l2(tp + (8 * OUT_PREFETCH + t) * tile_step);
+            }
             tp += 8 * tile_step;
             switch (code) {
             case 0: filt8<0, 0>(cf, ci, fh, ih, r, shift, qmask); break;

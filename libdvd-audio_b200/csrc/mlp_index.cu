@@ -45,94 +45,43 @@ __device__ __noinline__ bool sync_starts_segment(const uint8_t *es, uint64_t p, 
     return true;
 }
 
-// The elementary stream is read once.  k_sync_find: one warp per 512-byte chunk, one
-// 16-byte load per lane (the following 7 bytes come from the next lane), no block
-// barrier; the few matches of a chunk go, in stream order, into the chunk's slots
-// (offset in the chunk | valid << 15) next to its counts.  After the counts are
-// scanned, k_sync_emit (one thread per chunk) moves the slots to their places in
-// the ordered lists; a chunk with more matches than slots is searched again by its
-// thread (never seen outside of tests with synthetic pattern floods).
+// The sync patterns are found while the stream is gathered (k_es_gather, demux.cu): every
+// 512-byte chunk of the stream has a count and two slots (offset in the chunk).  k_sync_validate,
+// one thread per chunk with matches, puts a chunk's slots in stream order and judges them
+// (slot bit 15: starts a segment); after the counts are scanned, k_sync_emit (one thread per
+// chunk) moves the slots to their places in the ordered lists.  A chunk with more matches than
+// slots is searched again by its thread (never seen outside of tests with synthetic pattern
+// floods).
 #define SYNC_SLOTS 2
-#ifndef SYNC_WARPS
-#define SYNC_WARPS 8                  // warps per block
-#endif
-#ifndef SYNC_CHUNKS_PER_WARP
-#define SYNC_CHUNKS_PER_WARP 4
-#endif
 
-__global__ void __launch_bounds__(SYNC_WARPS * 32)
-k_sync_find(const uint8_t *__restrict__ es, const DecCounts *__restrict__ cnt, uint32_t chunks_cap, uint32_t *__restrict__ cnt_raw,
-            uint32_t *__restrict__ cnt_valid, uint16_t *__restrict__ slots, uint32_t nslots)
+__global__ void k_sync_validate(const uint8_t *__restrict__ es, const DecCounts *__restrict__ cnt, uint32_t chunks_cap,
+                                const uint32_t *__restrict__ cnt_raw, uint32_t *__restrict__ cnt_valid,
+                                uint16_t *__restrict__ slots, uint32_t nslots)
 {
-    // (the grid covers the chunks the stream buffer has room for: the ones behind the stream count nothing)
+    const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= chunks_cap) return;
+    const uint32_t n = cnt_raw[ch];
+    if (!n) return;                                            // (cnt_valid was cleared together with cnt_raw)
     const uint64_t es_total = cnt->es_total;
-    const uint32_t chunks = (uint32_t)((es_total + SYNC_CHUNK - 1) / SYNC_CHUNK);
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t chunk0 = (blockIdx.x * SYNC_WARPS + (threadIdx.x >> 5)) * SYNC_CHUNKS_PER_WARP;
-    if (chunk0 >= chunks) {
-        if (lane < SYNC_CHUNKS_PER_WARP && chunk0 + lane < chunks_cap) { cnt_raw[chunk0 + lane] = 0; cnt_valid[chunk0 + lane] = 0; }
-        return;
-    }
-    // all loads of the warp's chunks first (the ES buffer is padded well past es_total)
-    uint4 q[SYNC_CHUNKS_PER_WARP];
-    uint2 nx[SYNC_CHUNKS_PER_WARP];
-#pragma unroll
-    for (int c = 0; c < SYNC_CHUNKS_PER_WARP; c++) {
-        const uint64_t p0 = (uint64_t)(chunk0 + c) * SYNC_CHUNK + lane * 16;
-        const bool in = chunk0 + c < chunks;
-        q[c] = in ? __ldg(reinterpret_cast<const uint4 *>(es + p0)) : make_uint4(0, 0, 0, 0);
-        nx[c] = (in && lane == 31) ? __ldg(reinterpret_cast<const uint2 *>(es + p0 + 16)) : make_uint2(0, 0);
-    }
-#pragma unroll
-    for (int c = 0; c < SYNC_CHUNKS_PER_WARP; c++) {
-        const uint32_t chunk = chunk0 + c;
-        if (chunk >= chunks) {                                        // warp-uniform
-            if (lane == 0 && chunk < chunks_cap) { cnt_raw[chunk] = 0; cnt_valid[chunk] = 0; }
-            continue;
+    const uint64_t p0 = (uint64_t)ch * SYNC_CHUNK;
+    uint32_t nv = 0;
+    if (n <= nslots) {
+        uint32_t e[SYNC_SLOTS];
+        for (uint32_t i = 0; i < n; i++) e[i] = slots[(uint64_t)ch * SYNC_SLOTS + i] & 0x7FFFu;
+        if (n == 2 && e[0] > e[1]) { const uint32_t t = e[0]; e[0] = e[1]; e[1] = t; }      // (they arrived in any order)
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t v = sync_starts_segment(es, p0 + e[i], es_total) ? 1u : 0u;
+            nv += v;
+            slots[(uint64_t)ch * SYNC_SLOTS + i] = (uint16_t)(e[i] | (v << 15));
         }
-        uint32_t w[6];
-        w[0] = __byte_perm(q[c].x, 0, 0x0123); w[1] = __byte_perm(q[c].y, 0, 0x0123);
-        w[2] = __byte_perm(q[c].z, 0, 0x0123); w[3] = __byte_perm(q[c].w, 0, 0x0123);
-        w[4] = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
-        w[5] = __shfl_down_sync(0xFFFFFFFFu, w[1], 1);
-        if (lane == 31) { w[4] = __byte_perm(nx[c].x, 0, 0x0123); w[5] = __byte_perm(nx[c].y, 0, 0x0123); }
-        // the pattern at bytes p0+j+4 .. p0+j+7 for some j in 0..15?  (one shift and one compare each)
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < 16; j++) any |= __funnelshift_l(w[j / 4 + 2], w[j / 4 + 1], (j & 3) * 8) == 0xF8726FBBu;
-        if (!__any_sync(0xFFFFFFFFu, any)) {
-            if (lane == 0) { cnt_raw[chunk] = 0; cnt_valid[chunk] = 0; }
-            continue;
-        }
-        // rare: which positions exactly, and do they start segments
-        const uint64_t p0 = (uint64_t)chunk * SYNC_CHUNK + lane * 16;
-        uint32_t m_raw = 0, m_valid = 0;
-        if (any) {
-            for (int j = 0; j < 16; j++) {
-                const uint32_t v = __funnelshift_l(w[j / 4 + 2], w[j / 4 + 1], (j & 3) * 8);
-                if (v == 0xF8726FBBu && p0 + j + 8 <= es_total) {
-                    m_raw |= 1u << j;
-                    if (sync_starts_segment(es, p0 + j, es_total)) m_valid |= 1u << j;
-                }
-            }
-        }
-        const uint32_t mine = (uint32_t)__popc(m_raw) | ((uint32_t)__popc(m_valid) << 16);
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= (uint32_t)d) incl += o;
-        }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        if (lane == 0) { cnt_raw[chunk] = total & 0xFFFF; cnt_valid[chunk] = total >> 16; }
-        uint32_t i = (incl - mine) & 0xFFFF;
-        while (m_raw) {
-            const int j = __ffs(m_raw) - 1;
-            m_raw &= m_raw - 1;
-            if (i < nslots) slots[(uint64_t)chunk * SYNC_SLOTS + i] = (uint16_t)((lane * 16 + j) | (((m_valid >> j) & 1) << 15));
-            i++;
+    } else {
+        for (uint32_t j = 0; j < SYNC_CHUNK; j++) {
+            const uint64_t p = p0 + j;
+            if (p + 8 > es_total) break;
+            if (ld_be32(es + p + 4) == 0xF8726FBBu && sync_starts_segment(es, p, es_total)) nv++;
         }
     }
+    cnt_valid[ch] = nv;
 }
 
 __global__ void k_sync_emit(const uint8_t *__restrict__ es, const DecCounts *__restrict__ cnt,
@@ -168,11 +117,10 @@ __global__ void k_sync_emit(const uint8_t *__restrict__ es, const DecCounts *__r
     }
 }
 
-// chunks_cap: chunks the stream buffer has room for (the stream's size is still on the device)
-int launch_sync_count(const uint8_t *es, const DecCounts *cnt, uint32_t chunks_cap, uint32_t *cnt_raw, uint32_t *cnt_valid,
-                      uint16_t *slots, uint32_t nslots, cudaStream_t s)
+int launch_sync_validate(const uint8_t *es, const DecCounts *cnt, uint32_t chunks_cap, const uint32_t *cnt_raw, uint32_t *cnt_valid,
+                         uint16_t *slots, uint32_t nslots, cudaStream_t s)
 {
-    LAUNCH(k_sync_find, div_up_u32(chunks_cap, SYNC_WARPS * SYNC_CHUNKS_PER_WARP), SYNC_WARPS * 32, 0, s, es, cnt, chunks_cap, cnt_raw, cnt_valid, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS);
+    LAUNCH(k_sync_validate, div_up_u32(chunks_cap, 256), 256, 0, s, es, cnt, chunks_cap, cnt_raw, cnt_valid, slots, nslots < SYNC_SLOTS ? nslots : SYNC_SLOTS);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
