@@ -1285,6 +1285,16 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
     struct Head { uint4 v[5]; };
     Head nextv;
     uint32_t next_state = 0;
+    // (and, first of all, every access unit's record of the segment is asked into L2: the walk below
+    // is a chain of dependent steps, each of which would otherwise wait for DRAM — 36 of the 40 cycles
+    // between two instructions of this kernel went there)
+    if (!fallback) {
+        for (uint32_t a = 0; a < S.n_au; a++) {
+            prefetch_l2(&snaps[S.au_base + a].valid);
+            prefetch_l2(deltas + S.au_base + a);
+            prefetch_l2(reinterpret_cast<const uint8_t *>(deltas + S.au_base + a) + 64);
+        }
+    }
     if (S.n_au && !fallback) {
         next_state = snaps[S.au_base].valid;
         const uint4 *src = reinterpret_cast<const uint4 *>(deltas + S.au_base);
@@ -1572,29 +1582,16 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
 #define OUT_WARP_WORDS (2 * OUT_PATCH_WORDS + 4 * 32)   // two patches, used in turn (bulk stores in flight) + per segment {output base lo, hi, frames, aligned}
 #define OUT_SMEM_BYTES (OUT_WARPS * OUT_WARP_WORDS * 4)
 #define OUT_MAX_LPS 8
-#ifndef OUT_PREFETCH
-#define OUT_PREFETCH 3                                  // batches of eight frames the L2 prefetch runs ahead of the loads
-#endif
 
-__global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_out(MlpTables m, const OutWork *__restrict__ work)
+// LPS: lanes per segment = channels of the track, fixed at compile time for the common layouts
+// (2: stereo, 6: stereo pair + four more), 0: taken from the work list
+template <int LPS>
+__device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWork &W, uint32_t warp, int32_t *out_sm)
 {
-    extern __shared__ int32_t out_sm[];
+    constexpr int NL = LPS ? LPS : OUT_MAX_LPS;             // channels that can meet in the matrix step
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t warp = blockIdx.x * OUT_WARPS + wib;
-    if (warp >= m.cnt->nout_warps) return;
-    // queued before the host has seen the batch's status: nothing to do if the batch is decoded
-    // once more (tile overflow) or the output buffer sized in advance turned out too small
-    if (*m.status & (SEG_OVERFLOW | STATUS_PCM_SMALL)) return;
-
-    // ---- which track, group, segment, substream, channel
-    uint32_t lo = 0, hi = m.cnt->nout_work;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
-    }
-    const OutWork W = work[lo];
     const TrackDev &T = m.tracks[W.track];
-    const uint32_t n0 = W.n0, lps = W.n0 + W.n1;            // lanes per segment = channels of the track
+    const uint32_t n0 = W.n0, lps = LPS ? (uint32_t)LPS : W.n0 + W.n1;            // lanes per segment = channels of the track
     const uint32_t spw = 32 / lps;                         // segments per warp
     const uint32_t sub_n = (32 + spw - 1) / spw;           // warps per group
     const uint32_t rel = warp - W.warp0;
@@ -1738,12 +1735,6 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
             for (int t = 0; t < 8; t++) r[t] = nx[t];
 #pragma unroll
             for (int t = 0; t < 8; t++) nx[t] = tp[t * tile_step];
-            // ... and the frames three batches further on are asked into L2: the loads above then
-            // find them there, a batch of filtering is more than an L2 latency but less than a DRAM one
-            if (f + 8 * (OUT_PREFETCH + 2) <= my_frames) {
-#pragma unroll
-                for (int t = 0; t < 8; t++) prefetch_l2(tp + (8 * OUT_PREFETCH + t) * tile_step);
-            }
             tp += 8 * tile_step;
             switch (code) {
             case 0: filt8<0, 0>(cf, ci, fh, ih, r, shift, qmask); break;
@@ -1761,9 +1752,9 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
                 const uint32_t fa = f < my_frames ? f : 0;
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
-                    int32_t v[OUT_MAX_LPS];
+                    int32_t v[NL];
 #pragma unroll
-                    for (int c = 0; c < OUT_MAX_LPS; c++) v[c] = __shfl_sync(0xFFFFFFFFu, r[t], group_lane0 + c);
+                    for (int c = 0; c < NL; c++) v[c] = __shfl_sync(0xFFFFFFFFu, r[t], group_lane0 + c);
                     if (au_act && !trivial) {
                         // noise, matrices in order, bypass bit, output shift (mlp.c:504-538, 1308-1358)
                         const uint32_t bm = byp[(uint64_t)(fa + t) * DVDA_LANES];
@@ -1774,17 +1765,17 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
                         for (uint32_t mk = 0; mk < ml; mk++) {
                             long long sum = 0;
 #pragma unroll
-                            for (int c = 0; c < OUT_MAX_LPS; c++) if ((uint32_t)c <= mmc && (uint32_t)c < lps) sum += (long long)v[c] * P->coeff[mk][c];
+                            for (int c = 0; c < NL; c++) if ((uint32_t)c <= mmc && (uint32_t)c < lps) sum += (long long)v[c] * P->coeff[mk][c];
                             sum += (long long)z0 * P->coeff[mk][mmc + 1];
                             sum += (long long)z1 * P->coeff[mk][mmc + 2];
                             const uint32_t oc = P->out_ch[mk], qq = P->q[oc];
                             const int32_t rr = (((int32_t)(sum >> 14)) >> qq << qq) + (int32_t)((bm >> mk) & 1);
 #pragma unroll
-                            for (int c = 0; c < OUT_MAX_LPS; c++) if ((uint32_t)c == oc) v[c] = rr;
+                            for (int c = 0; c < NL; c++) if ((uint32_t)c == oc) v[c] = rr;
                         }
                         int32_t mineval = 0;
 #pragma unroll
-                        for (int c = 0; c < OUT_MAX_LPS; c++) if ((uint32_t)c == j) mineval = v[c];
+                        for (int c = 0; c < NL; c++) if ((uint32_t)c == j) mineval = v[c];
                         r[t] = j <= mmc ? (int32_t)((uint32_t)mineval << P->out_shift[j]) : mineval;
                     }
                     seed = noise_step(seed);
@@ -1806,6 +1797,28 @@ __global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_o
         int32_t *tail = m.fir_tail + ((uint64_t)k * m.cap_seg + seg) * (DVDA_MAX_CH * 8);
 #pragma unroll
         for (int t = 0; t < 8; t++) tail[j * 8 + t] = fh[7 - t];
+    }
+}
+
+__global__ void __launch_bounds__(OUT_WARPS * 32, OUT_MIN_BLOCKS) k_mlp_filter_out(MlpTables m, const OutWork *__restrict__ work)
+{
+    extern __shared__ int32_t out_sm[];
+    const uint32_t warp = blockIdx.x * OUT_WARPS + (threadIdx.x >> 5);
+    if (warp >= m.cnt->nout_warps) return;
+    // queued before the host has seen the batch's status: nothing to do if the batch is decoded
+    // once more (tile overflow) or the output buffer sized in advance turned out too small
+    if (*m.status & (SEG_OVERFLOW | STATUS_PCM_SMALL)) return;
+    // ---- which track
+    uint32_t lo = 0, hi = m.cnt->nout_work;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (work[mid].warp0 <= warp) lo = mid; else hi = mid;
+    }
+    const OutWork W = work[lo];
+    switch (W.n0 + W.n1) {
+    case 2: filter_out_warp<2>(m, W, warp, out_sm); break;
+    case 6: filter_out_warp<6>(m, W, warp, out_sm); break;
+    default: filter_out_warp<0>(m, W, warp, out_sm); break;
     }
 }
 
