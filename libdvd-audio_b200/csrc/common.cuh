@@ -140,14 +140,20 @@ struct GroupDev {
 };
 
 // rematrix parameters in force at the end of an access unit (reference mlp.c:504-525)
-struct ParamSet {
-    int16_t coeff[DVDA_MAX_MAT][DVDA_MAX_CH];
-    uint8_t out_ch[DVDA_MAX_MAT];
-    uint8_t matrix_len, mmc, noise_shift, uses_noise;
+struct alignas(16) ParamSet {
+    int16_t coeff[DVDA_MAX_MAT][DVDA_MAX_CH];   // a matrix row = one 16-byte load
+    uint8_t out_ch[DVDA_MAX_MAT];               // } one 8-byte load
+    uint8_t matrix_len, mmc;                    // }
     uint8_t q[DVDA_MAX_CH];
     uint8_t out_shift[DVDA_MAX_CH];
-    uint32_t pad;
+    uint8_t noise_shift, uses_noise;
+    uint8_t pad[6];
 };
+static_assert(sizeof(ParamSet) == 128, "ParamSet: 128 bytes, vector loads of its parts");
+
+// Segments a warp of the output pass takes: lanes = (segment, channel).  (At most 16: the warp
+// keeps 8 words per segment about its rows.)
+__host__ __device__ __forceinline__ uint32_t out_segs_per_warp(uint32_t channels) { return channels <= 1 ? 16u : 32u / channels; }
 
 struct AuDev {
     uint32_t frame0;           // first frame, segment-relative

@@ -209,9 +209,14 @@ __global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt,
     if (!n) return;
     uint32_t nlen = warp + 1 < np ? nlen0 : 0u;
     if (!nlen && warp + 1 < np) {
-        // (the next row carries no stream bytes: look further)
-        nrow = warp + 1;
-        while (nrow < np && pt.mlp_len[nrow] == 0) nrow++;
+        // (the next row carries no stream bytes: look further, 32 rows a round — a PCM track
+        // in between is thousands of them)
+        nrow = np;
+        for (uint32_t base = warp + 2; base < np; base += 32) {
+            const uint32_t r = base + lane;
+            const uint32_t hit = __ballot_sync(0xFFFFFFFFu, r < np && pt.mlp_len[r] != 0);
+            if (hit) { nrow = base + __ffs(hit) - 1; break; }
+        }
         if (nrow < np) { nlen = pt.mlp_len[nrow]; nsrc = sectors + (uint64_t)pt.sector[nrow] * DVDA_SECTOR + pt.off[nrow] + pt.pad2[nrow]; }
     }
     uint8_t *dst = es + es_off;

@@ -1565,23 +1565,83 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
 // together (access units have the nominal length here).  Residuals come from the tile; the
 // next 8 frames are loaded while the current 8 are filtered (the tile carries 16 frames of
 // slack, no bounds tests).  Per access unit the warp picks the smallest compiled tap count that
-// covers the filter orders of all its lanes (0, 4 or 8 taps each for FIR and IIR).  Access
-// units whose parameters ask for more than a copy (matrices, bypass bits, output shift, permuted
-// channel order) take the slow branch: the lanes of a segment exchange their samples by shuffle
-// — channels of both substreams meet there; substream 1's matrices govern all of them
-// (mlp.c:575-595) — and each applies the matrices for the whole frame, keeping its own channel.
-// Finished frames are parked in a shared-memory patch [segment][32 frames][channels] and leave
-// row by row every 32 frames as bulk copies shared -> global.  Runs after the frame counts are
-// final (it writes straight into the PCM buffer).
+// covers the filter orders of all its lanes (0, 4 or 8 taps each for FIR and IIR).  Filtered
+// samples are parked in a shared-memory patch [segment][32 frames][channels], in output channel
+// order.  When a patch is full the warp turns round: one lane per FRAME of a row applies what
+// the access unit's parameters ask for beyond a copy — noise, the matrices in order, bypass
+// bits, output shift (mlp.c:504-538, 1308-1358) — in place, each frame worked once with all its
+// channels in registers; channels of both substreams meet there and substream 1's matrices
+// govern all of them (mlp.c:575-595).  Then the patch leaves row by row as bulk copies
+// shared -> global.  Runs after the frame counts are final (it writes straight into the PCM
+// buffer).
 #define OUT_WARPS 4
 #ifndef OUT_MIN_BLOCKS
 #define OUT_MIN_BLOCKS 5
 #endif
 #define OUT_PF 32                                       // frames per patch
-#define OUT_PATCH_WORDS (OUT_PF * 32 + 4 * 32)          // most a patch needs: spw rows of OUT_PF * lanes-per-segment + 4 words
-#define OUT_WARP_WORDS (2 * OUT_PATCH_WORDS + 4 * 32)   // two patches, used in turn (bulk stores in flight) + per segment {output base lo, hi, frames, aligned}
+#define OUT_ROW_PAD 4                                    // per row: a note for the matrix step on each run of 8 frames
+#define OUT_PATCH_WORDS (OUT_PF * 32 + OUT_ROW_PAD * 32) // most a patch needs: spw rows of OUT_PF * lanes-per-segment + OUT_ROW_PAD words
+#define OUT_WARP_WORDS (2 * OUT_PATCH_WORDS + 8 * 16)   // two patches, used in turn (bulk stores in flight) + per segment {output base lo, hi, frames, aligned, parameter sets of two units in turn}
+#define NOTE_UNIT (1u << 23)                            // note of a run of 8 frames: noise seed (23 bits) | which of the two units | nothing to do
+#define NOTE_SKIP (1u << 24)
 #define OUT_SMEM_BYTES (OUT_WARPS * OUT_WARP_WORDS * 4)
 #define OUT_MAX_LPS 8
+
+// The matrix step of a patch of the output pass: lane = frame of a row.  The row's pad words say
+// which parameters govern each run of 8 frames and where the noise generator stood at its start.
+
+template <int NL>
+__device__ __forceinline__ void matrix_rows(const ParamSet *__restrict__ psets, int32_t *pb, const uint32_t *meta, const uint8_t *__restrict__ byp_rows,
+                                         uint32_t row_words, uint32_t lps, uint32_t spw, uint32_t slotmap, uint32_t f0, uint32_t fend)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t fr = f0 + lane;
+    for (uint32_t row = 0; row < spw; row++) {
+        int32_t *rw = pb + row * row_words;
+        const uint32_t note = (uint32_t)rw[OUT_PF * lps + (lane >> 3)];
+        if (fr >= fend || (note & NOTE_SKIP)) continue;
+        const uint32_t ps = meta[row * 8 + 4 + ((note / NOTE_UNIT) & 1)];
+        if (ps == 0xFFFFFFFFu) continue;
+        const ParamSet *Q = &psets[ps];
+        int32_t *px = rw + lane * lps;
+        int32_t v[NL];
+#pragma unroll
+        for (int c = 0; c < NL; c++) v[c] = (uint32_t)c < lps ? px[(slotmap >> (4 * c)) & 15] : 0;
+        const uint2 hd = __ldg(reinterpret_cast<const uint2 *>(Q->out_ch));        // out_ch[6], matrix_len, mmc
+        const uint64_t ocs = (uint64_t)hd.y << 32 | hd.x;
+        const uint32_t ml = (hd.y >> 16) & 0xFF, mmc = hd.y >> 24;
+        if (ml) {
+            uint32_t sd = note & (NOTE_UNIT - 1);
+            for (uint32_t i = 0; i < (lane & 7); i++) sd = noise_step(sd);
+            const uint32_t nsh = Q->noise_shift;
+            const int32_t z0 = (int32_t)((uint32_t)(int32_t)(int8_t)(sd >> 15) << nsh);
+            const int32_t z1 = (int32_t)((uint32_t)(int32_t)(int8_t)(sd >> 7) << nsh);
+            const uint32_t bm = byp_rows[(uint64_t)fr * DVDA_LANES + row];
+            const uint2 qw = __ldg(reinterpret_cast<const uint2 *>(Q->q));
+            const uint64_t qs = (uint64_t)qw.y << 32 | qw.x;
+            for (uint32_t mk = 0; mk < ml; mk++) {
+                const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(Q->coeff[mk]));
+                const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+                long long sum = (long long)z0 * Q->coeff[mk][mmc + 1] + (long long)z1 * Q->coeff[mk][mmc + 2];
+#pragma unroll
+                for (int c = 0; c < NL; c++) {
+                    const int32_t co = (int32_t)(int16_t)(w[c >> 1] >> (16 * (c & 1)));
+                    if ((uint32_t)c <= mmc) sum += (long long)v[c] * co;
+                }
+                const uint32_t oc = (uint32_t)(ocs >> (8 * mk)) & 0xFF, qq = (uint32_t)(qs >> (8 * oc)) & 0xFF;
+                const int32_t rr = (((int32_t)(sum >> 14)) >> qq << qq) + (int32_t)((bm >> mk) & 1);
+#pragma unroll
+                for (int c = 0; c < NL; c++) if ((uint32_t)c == oc) v[c] = rr;
+            }
+        }
+        const uint2 ow = __ldg(reinterpret_cast<const uint2 *>(Q->out_shift));
+        const uint64_t os = (uint64_t)ow.y << 32 | ow.x;
+#pragma unroll
+        for (int c = 0; c < NL; c++)
+            if ((uint32_t)c < lps)
+                px[(slotmap >> (4 * c)) & 15] = (uint32_t)c <= mmc ? (int32_t)((uint32_t)v[c] << ((uint32_t)(os >> (8 * c)) & 0xFF)) : v[c];
+    }
+}
 
 // LPS: lanes per segment = channels of the track, fixed at compile time for the common layouts
 // (2: stereo, 6: stereo pair + four more), 0: taken from the work list
@@ -1592,7 +1652,7 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TrackDev &T = m.tracks[W.track];
     const uint32_t n0 = W.n0, lps = LPS ? (uint32_t)LPS : W.n0 + W.n1;            // lanes per segment = channels of the track
-    const uint32_t spw = 32 / lps;                         // segments per warp
+    const uint32_t spw = LPS ? 32 / lps : out_segs_per_warp(lps);   // segments per warp
     const uint32_t sub_n = (32 + spw - 1) / spw;           // warps per group
     const uint32_t rel = warp - W.warp0;
     const GroupDev &G = m.groups[T.grp_base + rel / sub_n];
@@ -1612,13 +1672,13 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
     if (!max_frames) return;
     const uint32_t nominal = T.au_nominal;
 
-    const uint32_t row_words = OUT_PF * lps + 4;           // a segment's row in a patch (+4: rows stay 16-byte aligned, banks spread)
+    const uint32_t row_words = OUT_PF * lps + OUT_ROW_PAD; // a segment's row in a patch (rows stay 16-byte aligned, banks spread)
     int32_t *patch = out_sm + (size_t)wib * OUT_WARP_WORDS;
     uint32_t *meta = reinterpret_cast<uint32_t *>(patch + 2 * OUT_PATCH_WORDS);
     if (j == 0 && sl < spw) {
         const uint64_t base = (mine ? S.frame0 : 0) * lps;
-        meta[sl * 4 + 0] = (uint32_t)base; meta[sl * 4 + 1] = (uint32_t)(base >> 32); meta[sl * 4 + 2] = my_frames;
-        meta[sl * 4 + 3] = ((T.out_base + base) & 3) == 0;        // the rows of this segment start on 16-byte boundaries
+        meta[sl * 8 + 0] = (uint32_t)base; meta[sl * 8 + 1] = (uint32_t)(base >> 32); meta[sl * 8 + 2] = my_frames;
+        meta[sl * 8 + 3] = ((T.out_base + base) & 3) == 0;        // the rows of this segment start on 16-byte boundaries
     }
     __syncwarp();
 
@@ -1631,15 +1691,16 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
     uint32_t shift = 0, qmask = 0xFFFFFFFFu;
     const uint32_t tile_step = lps * DVDA_LANES;
     const int32_t *tp = m.tiles + G.tile_off + (have ? sg : 0) + (uint64_t)j * DVDA_LANES;
-    const uint8_t *byp = m.bypass + G.byp_off + (have ? sg : 0);
     int32_t *const pcm_row = m.pcm + T.out_base;
-    const bool plain_order = !(T.assignment >= 0x12 && T.assignment <= 0x14);
     const uint32_t out_slot = wave_slot(T.assignment, j);
-    const uint32_t group_lane0 = sl * lps;                       // first lane of this segment's channels
     int32_t *const park = patch + (sl < spw ? sl : 0) * row_words + out_slot;
+    uint32_t slotmap = 0;                                        // output slot of channel c, 4 bits each
+#pragma unroll
+    for (int c = 0; c < NL; c++) slotmap |= __shfl_sync(0xFFFFFFFFu, out_slot, c) << (4 * c);
+    const uint8_t *const byp_rows = m.bypass + G.byp_off + sub * spw;   // + frame * DVDA_LANES + row
+    bool patch_matrix = false;                                   // some access unit of the patch being filled wants the matrix step
 
     uint32_t seed = 0, pset = 0xFFFFFFFFu, f = 0, a = 0, cls = 0;
-    const ParamSet *P = nullptr;
     bool trivial = true;
     int32_t nx[8];
 #pragma unroll
@@ -1650,13 +1711,18 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
     // output).  Whole, 16-byte aligned rows go out as bulk copies shared -> global, one instruction
     // per row issued by the row's lane; the copy engine reads the patch while the warp fills the
     // other one.  Ragged ends take plain stores.
-    auto flush = [&](uint32_t f0) {
-        const int32_t *pb = patch + ((f0 / OUT_PF) & 1) * OUT_PATCH_WORDS;
+    auto flush = [&](uint32_t f0, uint32_t fend) {
+        int32_t *pb = patch + ((f0 / OUT_PF) & 1) * OUT_PATCH_WORDS;
+        if (patch_matrix) {
+            __syncwarp();
+            matrix_rows<NL>(m.psets, pb, meta, byp_rows, row_words, lps, spw, slotmap, f0, fend);
+            patch_matrix = false;
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the parked samples, for the async proxy
         __syncwarp();
         uint32_t slow = 0;
         if (lane < spw) {
-            const uint4 mt = *reinterpret_cast<const uint4 *>(meta + lane * 4);     // base lo, hi, frames, aligned
+            const uint4 mt = *reinterpret_cast<const uint4 *>(meta + lane * 8);     // base lo, hi, frames, aligned
             if (f0 < mt.z) {
                 if (f0 + OUT_PF <= mt.z && mt.w) {
                     int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * lps);
@@ -1671,7 +1737,7 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
         while (rows) {
             const uint32_t row = __ffs(rows) - 1;
             rows &= rows - 1;
-            const uint4 mt = *reinterpret_cast<const uint4 *>(meta + row * 4);
+            const uint4 mt = *reinterpret_cast<const uint4 *>(meta + row * 8);
             const uint32_t n = min((uint32_t)OUT_PF, mt.z - f0) * lps;
             int32_t *dst = pcm_row + (((uint64_t)mt.y << 32 | mt.x) + (uint64_t)f0 * lps);
             for (uint32_t i = lane; i < n; i += 32) dst[i] = pb[row * row_words + i];
@@ -1714,8 +1780,7 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
             seed = H.seed;
             if (H.pset != pset) {
                 pset = H.pset;
-                P = &m.psets[pset & 0x7FFFFFFFu];
-                trivial = (pset & 0x80000000u) && plain_order;
+                trivial = (pset & 0x80000000u) != 0;          // (a permuted channel order is dealt with when parking)
             }
             H = load_head(An);
         } else {
@@ -1723,11 +1788,19 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
 #pragma unroll
             for (int t = 0; t < 8; t++) { cf[t] = 0; ci[t] = 0; }
         }
+        if (j == 0 && sl < spw) meta[sl * 8 + 4 + (a & 1)] = au_act && !trivial ? pset & 0x7FFFFFFFu : 0xFFFFFFFFu;
         a++;
         const uint32_t nf = __reduce_max_sync(0xFFFFFFFFu, ((cls & 15) + 3) >> 2);
         const uint32_t ni = __reduce_max_sync(0xFFFFFFFFu, ((cls >> 4) + 3) >> 2);
         const uint32_t code = nf * 3 + ni;
         const bool any_matrix = __any_sync(0xFFFFFFFFu, au_act && !trivial);
+        if (any_matrix && !patch_matrix) {
+            // first unit of this patch to want the matrix step: the runs of 8 frames in front of it do not
+            patch_matrix = true;
+            if (j == 0 && sl < spw)
+                for (uint32_t b = 0; b < ((f & (OUT_PF - 1)) >> 3); b++)
+                    patch[((f / OUT_PF) & 1) * OUT_PATCH_WORDS + sl * row_words + OUT_PF * lps + b] = (int32_t)NOTE_SKIP;
+        }
 
         for (uint32_t i = 0; i < nominal; i += 8) {
             int32_t r[8];
@@ -1747,39 +1820,13 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
             case 7: filt8<8, 4>(cf, ci, fh, ih, r, shift, qmask); break;
             default: filt8<8, 8>(cf, ci, fh, ih, r, shift, qmask); break;
             }
+            // what the matrix step of this patch needs to know about these 8 frames
+            if (patch_matrix && j == 0 && sl < spw)
+                patch[((f / OUT_PF) & 1) * OUT_PATCH_WORDS + sl * row_words + OUT_PF * lps + ((f & (OUT_PF - 1)) >> 3)] =
+                    (int32_t)((seed & (NOTE_UNIT - 1)) | (a & 1 ? 0u : NOTE_UNIT));        // (a counts the unit already)
             if (any_matrix) {
-                // the shuffles need the whole warp: lanes without work just run along
-                const uint32_t fa = f < my_frames ? f : 0;
 #pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    int32_t v[NL];
-#pragma unroll
-                    for (int c = 0; c < NL; c++) v[c] = __shfl_sync(0xFFFFFFFFu, r[t], group_lane0 + c);
-                    if (au_act && !trivial) {
-                        // noise, matrices in order, bypass bit, output shift (mlp.c:504-538, 1308-1358)
-                        const uint32_t bm = byp[(uint64_t)(fa + t) * DVDA_LANES];
-                        const uint32_t sh = (seed >> 7) & 0xFFFF;
-                        const int32_t z0 = (int32_t)((uint32_t)(int32_t)(int8_t)(seed >> 15) << P->noise_shift);
-                        const int32_t z1 = (int32_t)((uint32_t)(int32_t)(int8_t)sh << P->noise_shift);
-                        const uint32_t ml = P->matrix_len, mmc = P->mmc;
-                        for (uint32_t mk = 0; mk < ml; mk++) {
-                            long long sum = 0;
-#pragma unroll
-                            for (int c = 0; c < NL; c++) if ((uint32_t)c <= mmc && (uint32_t)c < lps) sum += (long long)v[c] * P->coeff[mk][c];
-                            sum += (long long)z0 * P->coeff[mk][mmc + 1];
-                            sum += (long long)z1 * P->coeff[mk][mmc + 2];
-                            const uint32_t oc = P->out_ch[mk], qq = P->q[oc];
-                            const int32_t rr = (((int32_t)(sum >> 14)) >> qq << qq) + (int32_t)((bm >> mk) & 1);
-#pragma unroll
-                            for (int c = 0; c < NL; c++) if ((uint32_t)c == oc) v[c] = rr;
-                        }
-                        int32_t mineval = 0;
-#pragma unroll
-                        for (int c = 0; c < NL; c++) if ((uint32_t)c == j) mineval = v[c];
-                        r[t] = j <= mmc ? (int32_t)((uint32_t)mineval << P->out_shift[j]) : mineval;
-                    }
-                    seed = noise_step(seed);
-                }
+                for (int t = 0; t < 8; t++) seed = noise_step(seed);
             }
             if (au_act) {
                 int32_t *pk = park + ((f / OUT_PF) & 1) * OUT_PATCH_WORDS + (f & (OUT_PF - 1)) * lps;
@@ -1787,10 +1834,10 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
                 for (int t = 0; t < 8; t++) pk[t * lps] = r[t];
             }
             f += 8;
-            if ((f & (OUT_PF - 1)) == 0) flush(f - OUT_PF);
+            if ((f & (OUT_PF - 1)) == 0) { flush(f - OUT_PF, f); patch_matrix = any_matrix; }   // (the unit may go on into the next patch)
         }
     }
-    if (f & (OUT_PF - 1)) flush(f & ~(uint32_t)(OUT_PF - 1));
+    if (f & (OUT_PF - 1)) flush(f & ~(uint32_t)(OUT_PF - 1), f);
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory is given back at exit
     // FIR tail for a following segment that needs it
     if (mine) {

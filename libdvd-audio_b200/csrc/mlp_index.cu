@@ -390,7 +390,7 @@ k_track_plan(TrackDev *__restrict__ tracks, uint32_t n_tracks, uint32_t *__restr
             // the output pass: lanes = (segment, channel) over both substreams, 32 / channels segments per warp
             if (nss && (T.nss == 1 ? (T.channels >= 1 && T.channels <= 4) : (T.nss == 2 && T.channels >= 3 && T.channels <= 6))) {
                 n0 = T.nss == 1 ? T.channels : 2; n1 = T.channels - n0;
-                const uint32_t spw = 32 / T.channels;
+                const uint32_t spw = out_segs_per_warp(T.channels);
                 out_warps = ngrp * ((32 + spw - 1) / spw);
             }
         }

@@ -230,6 +230,21 @@ def test_drop_in_dumper(pkg, oracle, disc_cache, tmp_path):
     assert tracks == GOLDEN["c5_mixed"]["tracks"]
 
 
+@pytest.mark.parametrize("devices,contexts", [("all", "3"), ("0", "1")])
+def test_drop_in_dumper_on_every_device(pkg, oracle, disc_cache, tmp_path, monkeypatch, devices, contexts):
+    """The library's own pool of engine contexts over every GPU of the box (DVDA_B200_DEVICES=all;
+    one GPU: the same code with one device), parts small enough that every track is dealt out
+    across the workers and gathered in order: same records as the reference's."""
+    monkeypatch.setenv("DVDA_B200_DEVICES", devices)
+    monkeypatch.setenv("DVDA_B200_CONTEXTS", contexts)
+    monkeypatch.setenv("DVDA_B200_PART_SECTORS", "32")
+    for name in ("c5_mixed", "c3_mlp_6ch96", "aob_split"):
+        directory, _ = disc_cache(name)
+        rc, tracks, _samples, err = oracle.run_dump(pkg.DUMP_BIN, directory, str(tmp_path / (name + ".raw")))
+        assert rc == 0, err
+        assert tracks == GOLDEN[name]["tracks"], name
+
+
 def test_several_title_sets(pkg, oracle, tmp_path):
     """dvda_titleset_count / dvda_open_titleset(n) on a disc with three title sets, every
     track of every set against the reference library through the same dumper."""
