@@ -650,12 +650,13 @@ def run_sharded(args, pkg, torch, g, workloads, dist, rank, world, local_rank, e
 
         # ---- the plan: which tracks are MLP (those may be cut), units, their ranks
         tracks = [(i["first_sector"], i["last_sector"], i["pts_length"]) for _t, _k, i in ids]
-        codecs = []
+        codecs, weights = [], []
         for first, last, pts in tracks:
             n = min(8, n_total - first)
             r = eng.decode_host(aob[first * 2048:(first + n) * 2048], [(0, min(n - 1, last - first), pts)])
             codecs.append(int(r[0].codec) if r[0].status == 0 else -1)
-        units = shard.plan_units(tracks, codecs, world)
+            weights.append(shard.sector_weight(codecs[-1], int(r[0].channels)))
+        units = shard.plan_units(tracks, codecs, world, weights=weights)
         mine = shard.assign_units(units, world)[rank]
         # ---- this rank's sector window: its units' sector ranges (+ margin for the run to the next sync), back to back
         margin = 64
@@ -786,6 +787,8 @@ def run_sharded(args, pkg, torch, g, workloads, dist, rank, world, local_rank, e
         ms_floor = (time.perf_counter() - t_wall) * 1e3
         clocks = sampler.stop()
 
+        rank_ms = [None] * world
+        dist.all_gather_object(rank_ms, (round(ms / args.steps, 4), round(ms_e2e / args.steps, 3)))
         ms, total_samples = shard.reduce_job(ms, my_samples, dist, "cuda")            # MAX time, SUM samples
         ms_e2e, _ = shard.reduce_job(ms_e2e, my_samples, dist, "cuda")
         ms_floor, _ = shard.reduce_job(ms_floor, my_samples, dist, "cuda")
@@ -837,7 +840,8 @@ def run_sharded(args, pkg, torch, g, workloads, dist, rank, world, local_rank, e
                 "x_realtime": value / ch / rate,
                 "config": {"workload": name, "tracks": len(tracks), "units": len(units),
                            "units_per_rank": [l[2] for l in loads], "sectors_per_rank": [l[0] for l in loads],
-                           "samples_per_rank": [l[1] for l in loads], "aob_bytes": n_total * 2048,
+                           "samples_per_rank": [l[1] for l in loads], "step_ms_per_rank": [r[0] for r in rank_ms],
+                           "e2e_ms_per_rank": [r[1] for r in rank_ms], "aob_bytes": n_total * 2048,
                            "l2": "inputs larger than L2 (no flush needed)",
                            "parallelism": "one title set sharded over %d ranks by track and by parts of long MLP tracks "
                                           "(cut at restart points); host-side gather of the output, no collective" % world},

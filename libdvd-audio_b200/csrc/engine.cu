@@ -779,7 +779,7 @@ static int decode_enqueue(dvdagpu_ctx *c)
             m.au_snap = reinterpret_cast<AuSnap *>(c->buf[B_AU_SNAP].p);
             m.au_fchg = c->buf[B_AU_FCHG].as<uint8_t>();
             m.seg_ctx = reinterpret_cast<SegCtx *>(c->buf[B_SEG_CTX].p);
-            m.au_delta = reinterpret_cast<AuDelta *>(c->buf[B_AU_DELTA].p);
+            au_delta_split(c->buf[B_AU_DELTA].p, naua * lim_nss, m);
         }
         if (sh.any_mlp) {
             uint32_t *seg_nau = c->buf[B_SEG_NAU].as<uint32_t>(), *seg_au_base = c->buf[B_SEG_AU_BASE].as<uint32_t>();

@@ -22,7 +22,9 @@ struct PacketTable {
 
 struct AuSnap;      // mlp_common.cuh: what pass B needs to entropy-decode one access unit
 struct SegCtx;      // mlp_common.cuh: what a segment's restart header fixes for its parameter blocks
-struct AuDelta;     // mlp_common.cuh: the parameters one access unit transmits
+struct AuDelta;     // mlp_common.cuh: the parameters one access unit transmits (head)
+struct ChanCoef;    //   ... a channel's filter coefficients and histories
+struct MatCoef;     //   ... the matrix coefficients
 
 // everything the MLP kernels need to find their data.  Counts live in device memory (cnt);
 // the cap_* members are what the tables were sized for (strides of the per-substream tables).
@@ -54,6 +56,8 @@ struct MlpTables {
     uint8_t *au_fchg;              // [2][cap_au]: bit cc = the filter set-up of channel cc changes with this access unit
     SegCtx *seg_ctx;               // [2][cap_seg]
     AuDelta *au_delta;             // [2][cap_au], written where the AU brings parameters
+    ChanCoef *au_cf;               // [2][cap_au][4], where a channel's filters are transmitted
+    MatCoef *au_mcoef;             // [2][cap_au], where matrices are transmitted
     uint32_t fast;                 // 1: the complete decoder only takes segments flagged SEG_FALLBACK
     const uint32_t *status;        // the batch's status word (SEG_OVERFLOW, STATUS_*)
     uint32_t *any_fallback;        // set by the flag kernels of the fast path when the complete decoder has work at all
@@ -142,7 +146,8 @@ int launch_carry_fix(MlpTables m, cudaStream_t s);
 int launch_mlp_filter_out(MlpTables m, const OutWork *work, uint32_t cap_warps, cudaStream_t s);
 size_t au_snap_bytes();
 size_t seg_ctx_bytes();
-size_t au_delta_bytes();
+size_t au_delta_bytes();                 // per access unit and substream, all three tables
+void au_delta_split(void *base, size_t entries, MlpTables &m);   // places the three tables in one buffer of entries * au_delta_bytes()
 // fast path: pass A (headers), B (entropy, one lane per access unit), then the flags
 int launch_mlp_fast(MlpTables m, const DecWork *work, uint32_t cap_pairs, uint32_t lim_max_au, uint32_t lim_nss,
                     cudaEvent_t (*kev)[2], bool *kev_used, cudaEvent_t checked, cudaStream_t s);

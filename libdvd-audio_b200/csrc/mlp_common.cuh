@@ -286,18 +286,19 @@ struct ChanCoef {
     int32_t ist[8];                  // IIR history as transmitted: [0] pairs with coefficient 0
     int16_t fir_c[8], iir_c[8];
 };
+// What an access unit transmits, in three tables indexed alike ([2][cap_au]): the head is all the
+// resolve pass looks at and is written for every unit with parameters (consecutive units lie
+// next to each other: a segment's chain is a dense run of memory); filter coefficients and
+// matrix coefficients are written — and read — only where they are transmitted.
 struct __align__(16) AuDelta {
-    // head (80 bytes): all the resolve pass looks at
     uint16_t block_size;
     uint8_t present, matrix_len;
     uint8_t mat_out[DVDA_MAX_MAT], mat_bypass[DVDA_MAX_MAT];
     uint8_t out_shift[DVDA_MAX_CH], q[DVDA_MAX_CH];
     ChanHead ch[4];
-    // bulk
-    ChanCoef cf[4];
-    int16_t coeff[DVDA_MAX_MAT][DVDA_MAX_CH];
 };
-static_assert(offsetof(AuDelta, cf) == 80 && sizeof(AuDelta) % 16 == 0, "AuDelta layout");
+struct __align__(16) MatCoef { int16_t c[DVDA_MAX_MAT][DVDA_MAX_CH]; };
+static_assert(sizeof(AuDelta) == 80 && sizeof(ChanCoef) == 64 && sizeof(MatCoef) == 96, "AuDelta layout");
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -305,63 +306,16 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // ---- filter passes: one channel's set-up from the delta of an access unit -----------------
 struct FiltSetup { uint32_t fo, io, fsh, ish, q; };      // orders, shifts, quant_step_size in force
 
-__device__ __forceinline__ void filt_take_delta(const AuDelta &D, uint32_t cc, uint32_t c, FiltSetup &F,
-                                                int32_t (&cf)[8], int32_t (&ci)[8], int32_t (&ih)[8])
-{
-    const uint32_t *hw = reinterpret_cast<const uint32_t *>(&D.ch[cc]);
-    const uint32_t h1 = hw[1], h2 = hw[2];               // orders + shifts; codebook, lsbs, present
-    const uint32_t p = (h2 >> 16) & 0xFF;
-    if (D.present & AD_Q) F.q = D.q[c];
-    if (!(p & (CD_FIR | CD_IIR))) return;
-    const uint4 *kw = reinterpret_cast<const uint4 *>(&D.cf[cc]);
-    const uint4 s0 = kw[0], s1 = kw[1], fc = kw[2], ic = kw[3];
-    if (p & CD_FIR) {
-        F.fo = h1 & 0xFF; F.fsh = (h1 >> 8) & 0xFF;
-        const uint32_t w[4] = {fc.x, fc.y, fc.z, fc.w};
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
-            cf[j] = (uint32_t)j < F.fo ? v : 0;
-        }
-    }
-    if (p & CD_IIR) {
-        F.io = (h1 >> 16) & 0xFF; F.ish = h1 >> 24;
-        const uint32_t w[4] = {ic.x, ic.y, ic.z, ic.w};
-        const int32_t st[8] = {(int32_t)s0.x, (int32_t)s0.y, (int32_t)s0.z, (int32_t)s0.w,
-                               (int32_t)s1.x, (int32_t)s1.y, (int32_t)s1.z, (int32_t)s1.w};
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int32_t v = (int32_t)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
-            ci[j] = (uint32_t)j < F.io ? v : 0;
-            // the history is replaced by what was sent (or emptied)
-            ih[j] = ((p & CD_IIR_STATE) && (uint32_t)j < F.io) ? st[j] : 0;
-        }
-    }
-}
-// The same with the head fields already in registers (the fused output pass loads them one
-// access unit ahead): only the 64 bytes of coefficients and histories are fetched here, with
-// four independent loads.
+// The head fields are in registers already (the output pass loads them one access unit ahead):
+// only the 64 bytes of coefficients and histories are fetched here, with four independent loads.
 struct DeltaHead { uint32_t fchg, w0, qv, h1, h2, seed, pset; };
-__device__ __forceinline__ DeltaHead filt_load_head(const MlpTables &m, const AuDelta *deltas, uint32_t A, uint32_t cc, uint32_t c)
-{
-    DeltaHead H;
-    const AuDelta &D = deltas[A];
-    H.fchg = m.au_fchg[A];
-    H.w0 = *reinterpret_cast<const uint32_t *>(&D);                  // block_size, present, matrix_len
-    H.qv = D.q[c];
-    const uint32_t *hw = reinterpret_cast<const uint32_t *>(&D.ch[cc]);
-    H.h1 = hw[1]; H.h2 = hw[2];
-    const uint2 sp = *reinterpret_cast<const uint2 *>(&m.au[A].seed);
-    H.seed = sp.x; H.pset = sp.y;
-    return H;
-}
-__device__ __forceinline__ void filt_take_head(const DeltaHead &H, const AuDelta &D, uint32_t cc, FiltSetup &F,
+__device__ __forceinline__ void filt_take_head(const DeltaHead &H, const ChanCoef &K, FiltSetup &F,
                                                int32_t (&cf)[8], int32_t (&ci)[8], int32_t (&ih)[8])
 {
     const uint32_t h1 = H.h1, p = (H.h2 >> 16) & 0xFF;
     if ((H.w0 >> 16) & AD_Q) F.q = H.qv;
     if (!(p & (CD_FIR | CD_IIR))) return;
-    const uint4 *kw = reinterpret_cast<const uint4 *>(&D.cf[cc]);
+    const uint4 *kw = reinterpret_cast<const uint4 *>(&K);
     const uint4 s0 = kw[0], s1 = kw[1], fc = kw[2], ic = kw[3];
     if (p & CD_FIR) {
         F.fo = h1 & 0xFF; F.fsh = (h1 >> 8) & 0xFF;

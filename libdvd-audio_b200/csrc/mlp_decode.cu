@@ -1094,7 +1094,7 @@ __device__ __forceinline__ uint32_t pack16(int32_t lo, int32_t hi) { return ((ui
 // follows a restart header, where everything not transmitted falls back to its
 // default — the delta then states every field.
 template <typename RD>
-__device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D, const bool RESTART)
+__device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D, ChanCoef *CF, MatCoef &MC, const bool RESTART)
 {
     uint32_t present = 0, block_size = 8, matrix_len = 0;
     uint32_t mo[2] = {0, 0}, mb[2] = {0, 0};                    // mat_out / mat_bypass bytes 0-3, 4-5
@@ -1124,7 +1124,7 @@ __device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D, const bool REST
             for (uint32_t c = 0; c < DVDA_MAX_CH; c++) {
                 int16_t v = 0;
                 if (c < (uint32_t)cx.mmc + 3 && rd_get(b, 1)) v = (int16_t)((uint32_t)rd_get_s(b, frac + 2) << (14 - frac));
-                D.coeff[k][c] = v;
+                MC.c[k][c] = v;
             }
         }
     }
@@ -1169,7 +1169,7 @@ __device__ bool parse_delta(RD &b, const SegCtx &cx, AuDelta &D, const bool REST
         chw[cc * 3 + 1] = fo | fsh << 8 | io << 16 | ish << 24;
         chw[cc * 3 + 2] = cb | lsbs << 8 | p << 16;
         if (p & (CD_FIR | CD_IIR)) {
-            uint4 *k = reinterpret_cast<uint4 *>(&D.cf[cc]);
+            uint4 *k = reinterpret_cast<uint4 *>(&CF[cc]);
             k[0] = make_uint4((uint32_t)st[0], (uint32_t)st[1], (uint32_t)st[2], (uint32_t)st[3]);
             k[1] = make_uint4((uint32_t)st[4], (uint32_t)st[5], (uint32_t)st[6], (uint32_t)st[7]);
             k[2] = make_uint4(pack16(fc[0], fc[1]), pack16(fc[2], fc[3]), pack16(fc[4], fc[5]), pack16(fc[6], fc[7]));
@@ -1243,7 +1243,7 @@ __device__ __forceinline__ void parse_au(const MlpTables &m, const DecodeJob &jo
             if (rd_get(b, 1)) state = rd_get(b, 1) ? 0 : 2;
         }
         // one call site: the parser is the bulk of this kernel's code
-        if (state == 2 && !parse_delta(b, cx, D, a == 0)) state = 0;
+        if (state == 2 && !parse_delta(b, cx, D, m.au_cf + ((uint64_t)job.k * m.cap_au + A) * 4, m.au_mcoef[(uint64_t)job.k * m.cap_au + A], a == 0)) state = 0;
         if (rd_pos(b) > end_bits) state = 0;
         sn.bit0 = origin + rd_pos(b);
         sn.bit_end = origin + end_bits;
@@ -1416,11 +1416,12 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
                 memset(&P, 0, sizeof P);
                 P.matrix_len = (uint8_t)matrix_len; P.mmc = cx.mmc; P.noise_shift = cx.noise_shift;
                 const AuDelta &M = m.au_delta[(uint64_t)job.k * m.cap_au + mat_src];
+                const MatCoef &MC = m.au_mcoef[(uint64_t)job.k * m.cap_au + mat_src];
                 uint32_t uses = 0;
                 for (uint32_t k = 0; k < matrix_len; k++) {
                     P.out_ch[k] = M.mat_out[k];
-                    for (int c = 0; c < DVDA_MAX_CH; c++) P.coeff[k][c] = M.coeff[k][c];
-                    uses |= (M.coeff[k][cx.mmc + 1] != 0) | (M.coeff[k][cx.mmc + 2] != 0);
+                    for (int c = 0; c < DVDA_MAX_CH; c++) P.coeff[k][c] = MC.c[k][c];
+                    uses |= (MC.c[k][cx.mmc + 1] != 0) | (MC.c[k][cx.mmc + 2] != 0);
                 }
                 P.uses_noise = uses;
                 uses_noise = uses != 0;
@@ -1683,6 +1684,7 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
     __syncwarp();
 
     const AuDelta *deltas = m.au_delta + (uint64_t)k * m.cap_au;
+    const ChanCoef *coefs = m.au_cf + (uint64_t)k * m.cap_au * 4 + cc;      // + 4 * access unit
     const uint8_t *fchg = m.au_fchg + (uint64_t)k * m.cap_au;
     FiltSetup F = {0, 0, 0, 0, 0};
     int32_t fh[8], ih[8], cf[8], ci[8];
@@ -1770,10 +1772,10 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
         if (au_act) {
             const uint32_t A = au_base + a;
             const uint32_t An = min(A + 1, m.cap_au);        // (the tables have one spare entry)
-            prefetch_l1(&deltas[An].cf[cc]);
-            prefetch_l1(reinterpret_cast<const uint8_t *>(&deltas[An].cf[cc]) + 32);
+            prefetch_l1(&coefs[(uint64_t)An * 4]);
+            prefetch_l1(reinterpret_cast<const uint8_t *>(&coefs[(uint64_t)An * 4]) + 32);
             if ((H.fchg >> cc) & 1) {
-                filt_take_head(H, deltas[A], cc, F, cf, ci, ih);
+                filt_take_head(H, coefs[(uint64_t)A * 4], F, cf, ci, ih);
                 shift = filt_shift(F); qmask = 0xFFFFFFFFu << F.q;
                 cls = F.fo | F.io << 4;
             }
@@ -2041,7 +2043,14 @@ __global__ void k_flag_damaged(MlpTables m)
 
 size_t au_snap_bytes() { return sizeof(AuSnap); }
 size_t seg_ctx_bytes() { return sizeof(SegCtx); }
-size_t au_delta_bytes() { return sizeof(AuDelta); }
+size_t au_delta_bytes() { return sizeof(AuDelta) + 4 * sizeof(ChanCoef) + sizeof(MatCoef); }
+void au_delta_split(void *base, size_t entries, MlpTables &m)
+{
+    uint8_t *p = static_cast<uint8_t *>(base);
+    m.au_delta = reinterpret_cast<AuDelta *>(p);
+    m.au_cf = reinterpret_cast<ChanCoef *>(p + entries * sizeof(AuDelta));
+    m.au_mcoef = reinterpret_cast<MatCoef *>(p + entries * (sizeof(AuDelta) + 4 * sizeof(ChanCoef)));
+}
 
 const uint16_t *huff_lut_device()
 {

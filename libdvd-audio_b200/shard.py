@@ -32,35 +32,49 @@ def shard_tracks(weights, world):
     return out
 
 
-def plan_units(tracks, codecs, world, units_per_rank=4, min_part_sectors=4096):
+def plan_units(tracks, codecs, world, units_per_rank=4, min_part_sectors=4096, weights=None):
     """Cuts a title set into units of work for `world` ranks.
 
     tracks: [(first_sector, last_sector, pts_length), ...]; codecs: per track 1 = MLP (may be cut
-    into parts), anything else = one unit.  A track longer than the target unit size (the title
-    set's sectors / (world * units_per_rank)) is cut into equal parts of at least
-    min_part_sectors sectors.  Returns a list of dicts
-    {track, part, parts, first, last, pts, flags, sectors} in track / part order."""
-    total = sum(max(0, last - first + 1) for first, last, _p in tracks)
-    target = max(min_part_sectors, total // max(1, world * units_per_rank))
+    into parts), anything else = one unit; weights: per track, relative cost of decoding one of its
+    sectors (default 1: PCM sectors are several times cheaper than MLP ones, see sector_weight).
+    A track whose cost exceeds the target unit cost (the title set's cost / (world *
+    units_per_rank)) is cut into equal parts of at least min_part_sectors sectors.  Returns a list
+    of dicts {track, part, parts, first, last, pts, flags, sectors, cost} in track / part order."""
+    if weights is None:
+        weights = [1.0] * len(tracks)
+    total = sum(max(0, last - first + 1) * w for (first, last, _p), w in zip(tracks, weights))
+    target = max(1.0, total / max(1, world * units_per_rank))
     units = []
-    for ti, ((first, last, pts), codec) in enumerate(zip(tracks, codecs)):
+    for ti, ((first, last, pts), codec, w) in enumerate(zip(tracks, codecs, weights)):
         n = max(0, last - first + 1)
         parts = 1
-        if codec == 1 and world > 1 and n > target + target // 2:
-            parts = min((n + target - 1) // target, max(1, n // min_part_sectors))
+        goal = max(min_part_sectors, int(target / w)) if w > 0 else n      # sectors of this track that cost one target
+        if codec == 1 and world > 1 and n > goal + goal // 2:
+            parts = min((n + goal - 1) // goal, max(1, n // min_part_sectors))
         size = (n + parts - 1) // parts if parts else n
         for p in range(parts):
             s0 = first + p * size
             e = last if p + 1 == parts else s0 + size - 1
             flags = (PART_CONTINUES_PREVIOUS if p else 0) | (PART_CONTINUED_BY_NEXT if p + 1 < parts else 0)
-            units.append(dict(track=ti, part=p, parts=parts, first=s0, last=e, pts=pts, flags=flags, sectors=e - s0 + 1))
+            units.append(dict(track=ti, part=p, parts=parts, first=s0, last=e, pts=pts, flags=flags,
+                              sectors=e - s0 + 1, cost=(e - s0 + 1) * w))
     return units
 
 
+def sector_weight(codec, channels):
+    """Relative cost of decoding one sector on the GPU, from the single-GPU measurements of the
+    bench configurations: a PCM sector is unpacked in about a fifth of the time an MLP stereo
+    sector takes to decode; more channels per frame cost a little more per sector."""
+    if codec != 1:
+        return 0.2
+    return 1.0 + 0.06 * max(0, channels - 2)
+
+
 def assign_units(units, world):
-    """Greedy longest-first assignment of units to ranks by sector count.  Returns `world` lists
-    of units, each in sector order; every unit appears exactly once."""
-    picks = shard_tracks([u["sectors"] for u in units], world)
+    """Greedy longest-first assignment of units to ranks by cost (sector count x weight).
+    Returns `world` lists of units, each in sector order; every unit appears exactly once."""
+    picks = shard_tracks([u.get("cost", u["sectors"]) for u in units], world)
     return [[units[i] for i in sorted(mine, key=lambda i: units[i]["first"])] for mine in picks]
 
 
