@@ -47,6 +47,8 @@ for p in (ROOT, os.path.join(ROOT, "gen"), os.path.join(ROOT, "oracle")):
 
 METRIC = "decoded PCM samples/sec"
 UNIT = "samples/s"
+E2E_CONTEXTS = 2          # engine contexts per GPU in the end-to-end leg of a job with many tracks
+E2E_BATCHES = 8           # ... which is cut into about this many batches of consecutive tracks
 C5_SCALE = 40           # the title set's track lengths: ~80 000 restart segments, 10 000 per GPU of eight
 
 
@@ -354,6 +356,73 @@ def generate_async(config, seconds, seed, scale, tag):
     return subprocess.Popen([sys.executable, "-c", code]), d
 
 
+class ContextPool:
+    """Several engine contexts on one GPU, a host thread each (the C-ABI calls release the GIL), for
+    the end-to-end leg of a job with many tracks: the job is cut into batches of consecutive tracks
+    (or parts), and while one context's samples travel to the host the next batch is uploaded and
+    decoded on another — what the host library's own pool does behind dvda_read()
+    (DVDA_B200_CONTEXTS), here through the C ABI (dvdagpu_decode_host + dvdagpu_fetch)."""
+
+    def __init__(self, pkg, device, first, contexts=2):
+        self.engines = [first] + [pkg.Engine(device) for _ in range(max(0, contexts - 1))]
+
+    def run(self, host_ptr, batches, out_ptr):
+        """batches: [(first sector, sectors, track descriptors relative to it, [word offset of each track in the
+        output])].  Returns (launches, per batch [(frames, channels, status, error_flags)])."""
+        nxt, lock, errors = [0], threading.Lock(), []
+        launches = [0] * len(self.engines)
+        results = [None] * len(batches)
+
+        def work(ei):
+            e = self.engines[ei]
+            while not errors:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= len(batches):
+                    return
+                s0, n, descs, places = batches[i]
+                try:
+                    r2 = e.decode_host((host_ptr + s0 * 2048, n), descs)
+                    for r, off in zip(r2, places):
+                        e.fetch_into(r.pcm_offset, int(r.frames) * int(r.channels), out_ptr + 4 * off)
+                    results[i] = [(int(r.frames), int(r.channels), int(r.status), int(r.error_flags)) for r in r2]
+                    launches[ei] += e.stats()["launches"]
+                except Exception as ex:                       # noqa: BLE001 (reported by the caller)
+                    errors.append(ex)
+                    return
+
+        ts = [threading.Thread(target=work, args=(k,)) for k in range(len(self.engines))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errors:
+            raise errors[0]
+        return sum(launches), results
+
+    def close(self):
+        for e in self.engines[1:]:
+            e.close()
+
+
+def consecutive_batches(windows, want):
+    """Groups consecutive (first sector, sectors) windows into about `want` batches of similar size.
+    Returns lists of indices."""
+    total = sum(n for _s, n in windows)
+    goal = max(1, total // max(1, want))
+    out, cur, acc = [], [], 0
+    for i, (_s, n) in enumerate(windows):
+        cur.append(i)
+        acc += n
+        if acc >= goal:
+            out.append(cur)
+            cur, acc = [], 0
+    if cur:
+        out.append(cur)
+    return out
+
+
 def measure(pkg, torch, eng, stream, disc_dir, config, steps, warmup, dist=None, want_kernels=True):
     """Device-resident step and end-to-end step of one disc on the current GPU.  Returns a dict of
     raw numbers plus the pinned output tensor (for hashing) and the per-track results."""
@@ -414,6 +483,15 @@ def measure(pkg, torch, eng, stream, disc_dir, config, steps, warmup, dist=None,
         dist.barrier()
     torch.cuda.synchronize()
     single = len(tracks) == 1
+    pool, batches, groups = None, [], []
+    if not single:
+        # batches of consecutive tracks, dealt to two engine contexts
+        pool = ContextPool(pkg, torch.cuda.current_device(), eng, E2E_CONTEXTS)
+        groups = consecutive_batches([(f, l - f + 1) for f, l, _p in tracks], E2E_BATCHES)
+        for idx in groups:
+            s0 = min(tracks[i][0] for i in idx)
+            end = max(tracks[i][1] for i in idx) + 1
+            batches.append((s0, end - s0, [(tracks[i][0] - s0, tracks[i][1] - s0, tracks[i][2]) for i in idx], [offsets[i] for i in idx]))
 
     def e2e_step():
         if single:
@@ -422,11 +500,12 @@ def measure(pkg, torch, eng, stream, disc_dir, config, steps, warmup, dist=None,
             if int(r.frames) * int(r.channels) != samples:
                 raise SystemExit("pipelined decode returned %d frames" % r.frames)
         else:
-            r2 = eng.decode_host((host_in.data_ptr(), n_sectors), tracks)
-            for r, off in zip(r2, offsets):
-                if int(r.pcm_offset) != off:
-                    raise SystemExit("unexpected output layout")
-                eng.fetch_into(r.pcm_offset, int(r.frames) * int(r.channels), host_out.data_ptr() + 4 * off)
+            n_l, got = pool.run(host_in.data_ptr(), batches, host_out.data_ptr())
+            for idx, rs in zip(groups, got):
+                for i, (fr, chn, status, flags) in zip(idx, rs):
+                    if status or flags or fr != int(res[i].frames) or chn != int(res[i].channels):
+                        raise SystemExit("batched decode of track %d: %d frames, status %d, flags %x" % (i, fr, status, flags))
+            return n_l
         return eng.stats()["launches"]
 
     for _ in range(max(1, min(warmup, 2))):           # sizes the double buffers of the pipelined path
@@ -442,6 +521,8 @@ def measure(pkg, torch, eng, stream, disc_dir, config, steps, warmup, dist=None,
     # the copies run on the engine's own copy streams: take the larger of the event time on the
     # compute stream and the host wall time (every call returns only when its samples are in host memory)
     ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t_wall) * 1e3)
+    if pool:
+        pool.close()
     del dev_in
     return dict(ids=ids, res=res, offsets=offsets, frames=frames, samples=samples, n_sectors=n_sectors,
                 ms=ms, ms_e2e=ms_e2e, kernel_ms=kernel_ms, stage_ms=stage_ms, launches=launches,
@@ -474,7 +555,8 @@ def summarize(m, steps, name, config, peak):
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": m["ms_e2e"] / steps, "h2d_bytes_per_step": aob_bytes,
                 "d2h_bytes_per_step": 4 * m["samples"],
                 "path": "dvdagpu_decode_track_pipelined (pinned host in, pinned host out)" if m["single"]
-                else "dvdagpu_decode_host + dvdagpu_fetch per track (pinned host in, pinned host out)"},
+                else "batches of consecutive tracks on %d engine contexts: dvdagpu_decode_host + dvdagpu_fetch per track "
+                     "(pinned host in, pinned host out)" % E2E_CONTEXTS},
         "roofline_step": {"achieved": alg_bytes * steps / (m["ms"] * 1e-3) / 1e9, "unit": "GB/s",
                           "frac": alg_bytes * steps / (m["ms"] * 1e-3) / 1e9 / peak,
                           "algorithmic_bytes_per_step": alg_bytes},
@@ -739,19 +821,31 @@ def run_sharded(args, pkg, torch, g, workloads, dist, rank, world, local_rank, e
         ms = e0.elapsed_time(e1)
 
         # ---- timed: end to end — pinned sectors in, every sample into its place of the gathered buffer
+        # batches of consecutive units, dealt to two engine contexts: upload, decode and download overlap
+        pool = ContextPool(pkg, local_rank, eng, E2E_CONTEXTS)
+        windows = [(d[0], (descs[i + 1][0] if i + 1 < len(descs) else n_sectors) - d[0]) for i, d in enumerate(descs)]
+        groups = consecutive_batches(windows, E2E_BATCHES)
+        stage_off, at_s = [], 0
+        for u in mine:
+            stage_off.append(at_s)
+            at_s += u["frames"] * u["channels"]
+        batches = []
+        for idx in groups:
+            s0 = windows[idx[0]][0]
+            n = windows[idx[-1]][0] + windows[idx[-1]][1] - s0
+            places = [unit_off[(mine[i]["track"], mine[i]["part"])] if registered else stage_off[i] for i in idx]
+            batches.append((s0, n, [(descs[i][0] - s0, descs[i][1] - s0, descs[i][2], descs[i][3]) for i in idx], places))
+        e2e_out_ptr = out.ctypes.data if registered else staging.data_ptr()
+
         def e2e_step():
             if not descs:
                 return 0
-            r2 = eng.decode_host((host_in.data_ptr(), n_sectors), descs)
-            at_s = 0
-            for u, r in zip(mine, r2):
-                n = int(r.frames) * int(r.channels)
-                if registered:
-                    eng.fetch_into(r.pcm_offset, n, out.ctypes.data + 4 * unit_off[(u["track"], u["part"])])
-                else:
-                    eng.fetch_into(r.pcm_offset, n, staging.data_ptr() + 4 * at_s)
-                at_s += n
-            return eng.stats()["launches"]
+            n_l, got = pool.run(host_in.data_ptr(), batches, e2e_out_ptr)
+            for idx, rs in zip(groups, got):
+                for i, (fr, chn, status, flags) in zip(idx, rs):
+                    if status or flags or fr != mine[i]["frames"] or chn != mine[i]["channels"]:
+                        raise SystemExit("rank %d: batched decode of unit %r: %d frames, status %d, flags %x" % (rank, mine[i], fr, status, flags))
+            return n_l
 
         e2e_step()
         dist.barrier()
@@ -762,6 +856,7 @@ def run_sharded(args, pkg, torch, g, workloads, dist, rank, world, local_rank, e
             e2e_launches += e2e_step()
         torch.cuda.synchronize()
         ms_e2e = (time.perf_counter() - t_wall) * 1e3
+        pool.close()
         if not registered:
             at_s = 0
             for u in mine:
@@ -847,8 +942,8 @@ def run_sharded(args, pkg, torch, g, workloads, dist, rank, world, local_rank, e
                                           "(cut at restart points); host-side gather of the output, no collective" % world},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(aob_bytes),
                         "d2h_bytes_per_step": int(4 * total_samples), "gpu_launches": e2e_launches,
-                        "path": "per rank: dvdagpu_decode_host from pinned sectors + dvdagpu_fetch of every unit into its place of the "
-                                "gathered buffer (%s)" % ("shared host memory page-locked by every rank" if registered else "through a pinned staging buffer"),
+                        "path": "per rank: batches of consecutive units on %d engine contexts, dvdagpu_decode_host from pinned sectors + "
+                                "dvdagpu_fetch of every unit into its place of the gathered buffer (%s)" % (E2E_CONTEXTS, "shared host memory page-locked by every rank" if registered else "through a pinned staging buffer"),
                         "copy_floor_ms_per_step": ms_floor / args.steps,
                         "copy_floor_note": "the same bytes as plain pinned copies (H2D and D2H side by side) on all ranks at once"},
                 "gpu_launches": sum(l[3] for l in loads),

@@ -200,7 +200,7 @@ __global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt,
     // (a warp lives for a few memory latencies: everything it will need from the tables is asked
     // for up front, the next packet's row included)
     const uint32_t n = pt.mlp_len[warp];
-    const uint32_t np = (uint32_t)cnt->np;
+    const uint32_t np = min((uint32_t)cnt->np, rows);          // (more packets than rows: the table is incomplete, the decode will be repeated)
     uint32_t nrow = warp + 1 < np ? warp + 1 : warp;
     const uint32_t nlen0 = pt.mlp_len[nrow];
     const uint8_t *src = sectors + (uint64_t)pt.sector[warp] * DVDA_SECTOR + pt.off[warp] + pt.pad2[warp];

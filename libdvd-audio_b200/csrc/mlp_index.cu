@@ -611,7 +611,15 @@ __global__ void k_yield_mark(MlpTables m, const uint32_t *__restrict__ seg_au_ba
     uint32_t pk = warp_first_true(0u, np + 1, [=](uint32_t i) { return pk_es[i] > x0; }) - 1;
     if (have) {
         if (last_byte < x0) pk = upper_bound_dev(m.pk_es, np + 1, last_byte) - 1;   // (not in stream order: on its own)
-        else while (pk + 1 <= np && pk_es[pk + 1] <= last_byte) pk++;
+        else {
+            // a few packets on, as a rule; behind a track boundary inside the warp there may be thousands
+            // of rows without stream bytes (a PCM track) in between: search then
+            uint32_t steps = 0;
+            while (pk + 1 <= np && pk_es[pk + 1] <= last_byte) {
+                pk++;
+                if (++steps == 8) { pk = upper_bound_dev(m.pk_es, np + 1, last_byte) - 1; break; }
+            }
+        }
         if (yields) pk_yield[pk] = 1;
     }
     (void)seg_au_base;
