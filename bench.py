@@ -47,8 +47,9 @@ for p in (ROOT, os.path.join(ROOT, "gen"), os.path.join(ROOT, "oracle")):
 
 METRIC = "decoded PCM samples/sec"
 UNIT = "samples/s"
-E2E_CONTEXTS = 2          # engine contexts per GPU in the end-to-end leg of a job with many tracks
-E2E_BATCHES = 8           # ... which is cut into about this many batches of consecutive tracks
+E2E_CONTEXTS = int(os.environ.get("BENCH_E2E_CONTEXTS", "2"))   # engine contexts per GPU in the end-to-end leg of a job with many tracks
+POOL_TRACE = bool(os.environ.get("BENCH_POOL_TRACE"))
+E2E_BATCHES = int(os.environ.get("BENCH_E2E_BATCHES", "8"))     # ... which is cut into about this many batches of consecutive tracks
 C5_SCALE = 40           # the title set's track lengths: ~80 000 restart segments, 10 000 per GPU of eight
 
 
@@ -370,6 +371,7 @@ class ContextPool:
         """batches: [(first sector, sectors, track descriptors relative to it, [word offset of each track in the
         output])].  Returns (launches, per batch [(frames, channels, status, error_flags)])."""
         nxt, lock, errors = [0], threading.Lock(), []
+        self.t_run = time.perf_counter()
         launches = [0] * len(self.engines)
         results = [None] * len(batches)
 
@@ -383,9 +385,15 @@ class ContextPool:
                     return
                 s0, n, descs, places = batches[i]
                 try:
+                    t0 = time.perf_counter()
                     r2 = e.decode_host((host_ptr + s0 * 2048, n), descs)
+                    t1 = time.perf_counter()
                     for r, off in zip(r2, places):
                         e.fetch_into(r.pcm_offset, int(r.frames) * int(r.channels), out_ptr + 4 * off)
+                    if POOL_TRACE:
+                        sys.stderr.write("[pool] ctx %d batch %d: %d sectors, %d tracks, %d launches; decode_host %.2f..%.2f ms, fetched at %.2f ms (%d samples)\n"
+                                         % (ei, i, n, len(descs), e.stats()["launches"], (t0 - self.t_run) * 1e3, (t1 - self.t_run) * 1e3,
+                                            (time.perf_counter() - self.t_run) * 1e3, sum(int(r.frames) * int(r.channels) for r in r2)))
                     results[i] = [(int(r.frames), int(r.channels), int(r.status), int(r.error_flags)) for r in r2]
                     launches[ei] += e.stats()["launches"]
                 except Exception as ex:                       # noqa: BLE001 (reported by the caller)

@@ -648,7 +648,7 @@ static int decode_enqueue(dvdagpu_ctx *c)
             // per-substream tables: [2][cap_au] (the kernels index them as k * cap_au + A)
             ENSURE(B_AU_SNAP, naua * lim_nss * au_snap_bytes());
             ENSURE(B_AU_FCHG, naua * lim_nss); ENSURE(B_SEG_CTX, ((size_t)cap_seg + 1) * 2 * seg_ctx_bytes());
-            ENSURE(B_AU_DELTA, naua * lim_nss * au_delta_bytes());
+            ENSURE(B_AU_DELTA, naua * lim_nss * au_delta_bytes() + 256);      // (+ alignment of the second table)
         }
         ENSURE(B_TILES, (cells * DVDA_LANES + 64 + 16 * DVDA_MAX_CH * DVDA_LANES) * sizeof(int32_t));   // 16 frames of slack: the filter passes read ahead
         ENSURE(B_BYPASS, cells * DVDA_LANES + 64);

@@ -1289,11 +1289,13 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
     // is a chain of dependent steps, each of which would otherwise wait for DRAM — 36 of the 40 cycles
     // between two instructions of this kernel went there)
     if (!fallback) {
-        for (uint32_t a = 0; a < S.n_au; a++) {
-            prefetch_l2(&snaps[S.au_base + a].valid);
-            prefetch_l2(deltas + S.au_base + a);
-            prefetch_l2(reinterpret_cast<const uint8_t *>(deltas + S.au_base + a) + 64);
-        }
+        // (both tables are dense runs of memory for a segment: line by line)
+        const uint8_t *p0 = reinterpret_cast<const uint8_t *>(deltas + S.au_base), *p1 = reinterpret_cast<const uint8_t *>(deltas + S.au_base + S.n_au);
+        for (const uint8_t *p = p0; p < p1; p += 128) prefetch_l2(p);
+        if (p1 > p0) prefetch_l2(p1 - 1);
+        p0 = reinterpret_cast<const uint8_t *>(snaps + S.au_base); p1 = reinterpret_cast<const uint8_t *>(snaps + S.au_base + S.n_au);
+        for (const uint8_t *p = p0; p < p1; p += 128) prefetch_l2(p);
+        if (p1 > p0) prefetch_l2(p1 - 1);
     }
     if (S.n_au && !fallback) {
         next_state = snaps[S.au_base].valid;
@@ -1772,8 +1774,8 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
         if (au_act) {
             const uint32_t A = au_base + a;
             const uint32_t An = min(A + 1, m.cap_au);        // (the tables have one spare entry)
-            prefetch_l1(&coefs[(uint64_t)An * 4]);
-            prefetch_l1(reinterpret_cast<const uint8_t *>(&coefs[(uint64_t)An * 4]) + 32);
+            // (a prefetch brings a whole 128-byte line: the coefficients of a pair of channels — one lane asks)
+            if (!(cc & 1)) prefetch_l1(&coefs[(uint64_t)An * 4]);
             if ((H.fchg >> cc) & 1) {
                 filt_take_head(H, coefs[(uint64_t)A * 4], F, cf, ci, ih);
                 shift = filt_shift(F); qmask = 0xFFFFFFFFu << F.q;
@@ -2048,8 +2050,10 @@ void au_delta_split(void *base, size_t entries, MlpTables &m)
 {
     uint8_t *p = static_cast<uint8_t *>(base);
     m.au_delta = reinterpret_cast<AuDelta *>(p);
-    m.au_cf = reinterpret_cast<ChanCoef *>(p + entries * sizeof(AuDelta));
-    m.au_mcoef = reinterpret_cast<MatCoef *>(p + entries * (sizeof(AuDelta) + 4 * sizeof(ChanCoef)));
+    // (a pair of channels' coefficients = one 128-byte line)
+    uint8_t *cf = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(p + entries * sizeof(AuDelta)) + 127) & ~(uintptr_t)127);
+    m.au_cf = reinterpret_cast<ChanCoef *>(cf);
+    m.au_mcoef = reinterpret_cast<MatCoef *>(cf + entries * 4 * sizeof(ChanCoef));
 }
 
 const uint16_t *huff_lut_device()
