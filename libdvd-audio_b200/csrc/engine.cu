@@ -802,13 +802,8 @@ static int decode_enqueue(dvdagpu_ctx *c)
             }
             TRY(launch_plan_check(cnt, lim, s));
             TRY(launch_au_chase(es, m.segs, cap_seg, cnt, d_tracks, seg_nau, m.au_pos, m.au_seg, seg_au_base, au_noted, 1, s));
-            bool any_parts = false;
-            for (uint32_t i = 0; i < n_tracks; i++) any_parts |= (ht[i].cont & TRACK_CONT_NEXT) != 0;
-            TRY(launch_yield(m, rows, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), any_parts, s));
-            CUDA_TRY(record_timing(c->ev[2], s));
-
-            // ---------------- decode
-            // Parity / CRC-8 on a second stream, beside the group set-up and the header passes.  Small
+            // Parity / CRC-8 on a second stream, beside the rest of the index chain and the header passes
+            // (it needs the access units' positions, nothing else).  Small
             // access units: the windowed kernel on the low-priority stream (it fills what the chain
             // leaves free).  Large ones: the direct kernel at the chain's own priority, which then runs
             // first and lets the header passes follow.  Both pairings, and starting the check beside the
@@ -822,6 +817,12 @@ static int decode_enqueue(dvdagpu_ctx *c)
             CUDA_TRY(record_timing(c->kev[DVDAGPU_K_CHECKDATA][1], chk_stream));
             c->kev_used[DVDAGPU_K_CHECKDATA] = true;
             CUDA_TRY(cudaEventRecord(c->aux_ev[1], chk_stream));
+            bool any_parts = false;
+            for (uint32_t i = 0; i < n_tracks; i++) any_parts |= (ht[i].cont & TRACK_CONT_NEXT) != 0;
+            TRY(launch_yield(m, rows, seg_au_base, pt, trk_pk_lo, c->buf[B_PK_YIELD].as<uint8_t>(), any_parts, s));
+            CUDA_TRY(record_timing(c->ev[2], s));
+
+            // ---------------- decode
             uint32_t *seg_frames = c->buf[B_SEG_FRAMES].as<uint32_t>();
             uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
             TRY(launch_group_offsets(m.groups, cap_grp, cnt, cell_base, s));
