@@ -1102,9 +1102,21 @@ extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sec
             GraphMode(dvdagpu_ctx *a_, dvdagpu_ctx *b_) : a(a_), b(b_) { a->use_graph = b->use_graph = true; }
             ~GraphMode() { a->use_graph = b->use_graph = false; }
         } graph_mode(X[0], X[1]);
-        const uint32_t parts = (uint32_t)starts.size();
+        uint32_t parts = (uint32_t)starts.size();
+        // A PCM track (known once part 0 is decoded) goes on in windows of whole sectors: every packet
+        // stands alone, what carries over is the frame budget (dvd-audio.c:1016-1082) — so the parts
+        // follow one another (each is told the frames still to come), run on behind the track's last
+        // sector while the budget lasts, and only uploads and downloads overlap with the decodes.
+        bool pcm = false;
+        uint64_t pcm_budget = 0;
+        uint32_t restart_at = 0;                             // parts begun before the codec was known are decoded again
         auto window = [&](uint32_t i, uint64_t &s0, uint64_t &len, uint64_t &e_rel) {
             s0 = starts[i];
+            if (pcm && i) {
+                len = std::min<uint64_t>(part_sectors, n_sectors - s0);
+                e_rel = len - 1;
+                return;
+            }
             const uint64_t e = i + 1 == parts ? last : starts[i + 1] - 1;
             uint64_t stop = (i + 1 == parts) ? n_sectors : e + 1 + margin;
             if (stop > n_sectors) stop = n_sectors;
@@ -1145,6 +1157,7 @@ extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sec
             dvdagpu_track_desc d = {0, (uint32_t)e_rel, track->pts_length,
                                     (i ? (uint32_t)DVDAGPU_PART_CONTINUES_PREVIOUS : (track->flags & 1u)) |
                                     (i + 1 < parts ? (uint32_t)DVDAGPU_PART_CONTINUED_BY_NEXT : (track->flags & 2u))};
+            if (pcm && i) { d.pts_length = (uint32_t)std::min<uint64_t>(pcm_budget, 0xFFFFFFFFull); d.flags = DVDAGPU_PCM_BUDGET_IN_FRAMES; }
             tmark(x->stream, 'd');
             return decode_begin(x, x->buf[slot ? B_SECTORS2 : B_SECTORS].as<uint8_t>(), len, 1, &d);
         };
@@ -1160,11 +1173,32 @@ extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sec
             tmark(x->stream, 'D');
             add_stats(total_stats, x->stats);
             if (stop || fallback) return 0;                  // (drained only)
-            // anything the parts cannot express: decode in one piece instead
-            if (r.status != 0 || r.codec != 1 || r.stopped == 2 || (r.truncated && i + 1 < parts) ||
-                (i && (r.channels != merged.channels || r.sample_rate != merged.sample_rate || r.bits_per_sample != merged.bits_per_sample ||
-                       r.channel_assignment != merged.channel_assignment))) { fallback = true; return 0; }
+            const bool same_params = !i || (r.channels == merged.channels && r.sample_rate == merged.sample_rate &&
+                                            r.bits_per_sample == merged.bits_per_sample && r.channel_assignment == merged.channel_assignment);
+            if (pcm) {
+                // a window that does not open with a PCM packet of the same parameters: the track ended in front of it
+                if (r.status != 0 || r.codec != 0 || !same_params) { stop = true; merged.truncated = 0; return 0; }
+            } else if (i == 0 && r.status == 0 && r.codec == 0 && !(track->flags & 7u)) {
+                pcm = true;
+                const uint64_t total = (uint64_t)llround((double)track->pts_length * (double)r.sample_rate / 90000.0);
+                pcm_budget = total;
+                // the windows behind part 0 (all of its window was delivered, margin included)
+                uint64_t s0, len, e_rel;
+                window(0, s0, len, e_rel);
+                starts.resize(1);
+                for (uint64_t s1 = s0 + len; s1 < n_sectors; s1 += part_sectors) starts.push_back(s1);
+                parts = (uint32_t)starts.size();
+                restart_at = 1;
+            } else if (r.status != 0 || r.codec != 1 || r.stopped == 2 || (r.truncated && i + 1 < parts) || !same_params) {
+                // anything the parts cannot express: decode in one piece instead
+                fallback = true;
+                return 0;
+            }
             if (i == 0) merged = r;
+            if (pcm) {
+                pcm_budget = r.frames >= pcm_budget ? 0 : pcm_budget - r.frames;
+                if (!pcm_budget || !r.truncated) stop = true;      // used up, or the window ended early
+            }
             const uint64_t n = r.frames * r.channels;
             if (total_samples + n > pcm_capacity) return 3;
             tmark(c->d2h_stream, 'o');
@@ -1189,8 +1223,17 @@ extern "C" int dvdagpu_decode_track_pipelined(dvdagpu_ctx *c, const uint8_t *sec
         for (uint32_t i = 0; i < parts && !rc && !fallback && !stop; i++) {
             if (i + 1 < parts) rc = upload(i + 1);
             if (!rc) { rc = begin(i); if (!rc) begun++; }
-            // with two contexts the host now waits for the part before this one, with one for this one
-            while (!rc && ended < begun && (begun - ended > (two ? 1u : 0u) || i + 1 == parts) && !fallback) { rc = end(ended); ended++; }
+            // with two contexts the host now waits for the part before this one, with one (and for PCM parts,
+            // which need their predecessor's frame count) for this one
+            while (!rc && ended < begun && (begun - ended > (two && !pcm ? 1u : 0u) || i + 1 == parts) && !fallback && !restart_at) { rc = end(ended); ended++; }
+            if (restart_at && !rc) {
+                // the track is PCM: whatever was begun behind part 0 is waited for and decoded again as PCM windows
+                while (ended < begun) { dvdagpu_track_result r; decode_end(ctx_of(ended), &r); add_stats(total_stats, ctx_of(ended)->stats); ended++; }
+                begun = ended = restart_at;
+                i = restart_at - 1;
+                restart_at = 0;
+                if (!stop && i + 1 < parts) rc = upload(i + 1);      // (its window changed; the next round begins it)
+            }
         }
         while (!rc && ended < begun) { rc = end(ended); ended++; }
         drain();

@@ -453,10 +453,12 @@ def test_parts_concatenate_to_the_track(pkg, oracle, engine, disc_cache, name, p
 
 
 @pytest.mark.parametrize("name,part", [("c2_large", 256), ("c3_large", 500), ("c1_large", 300), ("mlp_fir_carry", 6),
-                                       ("mlp_wild_0", 7), ("mlp_zero_yield", 4), ("c5_mixed", 5)])
+                                       ("mlp_wild_0", 7), ("mlp_zero_yield", 4), ("c5_mixed", 5),
+                                       ("pcm_rates_ragged", 3), ("pcm_layouts", 2), ("pcm_param_change", 2), ("c1_pcm_2ch16", 4)])
 def test_pipelined_track_decode(pkg, oracle, engine, disc_cache, name, part):
     """dvdagpu_decode_track_pipelined (overlapped upload / decode / download, with its
-    own fallbacks) against the oracle."""
+    own fallbacks) against the oracle: MLP tracks in parts cut at restart points, PCM tracks in
+    windows that carry the frame budget along."""
     directory, _ = disc_cache(name)
     sectors = oracle.read_aobs(directory)
     n_sectors = len(sectors) // 2048
