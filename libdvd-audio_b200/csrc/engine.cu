@@ -938,6 +938,19 @@ static int decode_end(dvdagpu_ctx *c, dvdagpu_track_result *results)
                         T.nss, T.nseg, T.err_seg, (unsigned long long)T.frames, T.truncated);
                 fprintf(stderr, "[dvdagpu]          cont=%u check=[%u,%u) stopped=%u\n", T.cont, T.pk_check, T.pk_check_end, T.stopped);
             }
+            if (k.nseg && k.nseg <= 4096 && c->buf[B_SEGS].p && c->buf[B_SS_FLAGS].p && c->buf[B_SS_FLAGS_FAST].p) {
+                // the segment table with each substream's flags: after the fast path / at the end
+                const uint32_t cap_seg = (uint32_t)sh.seg;
+                std::vector<SegDev> hs(k.nseg);
+                std::vector<uint32_t> f_fast(2 * ((size_t)cap_seg + 1)), f_end(2 * ((size_t)cap_seg + 1));
+                cudaMemcpy(hs.data(), c->buf[B_SEGS].p, k.nseg * sizeof(SegDev), cudaMemcpyDeviceToHost);
+                cudaMemcpy(f_fast.data(), c->buf[B_SS_FLAGS_FAST].p, f_fast.size() * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(f_end.data(), c->buf[B_SS_FLAGS].p, f_end.size() * 4, cudaMemcpyDeviceToHost);
+                for (uint32_t i = 0; i < k.nseg; i++)
+                    fprintf(stderr, "[dvdagpu] seg %u: track %u frame0=%llu frames=%u n_au=%u flags=%x err=%x err_au=%u | fast ss0=%x ss1=%x | end ss0=%x ss1=%x\n",
+                            i, hs[i].track, (unsigned long long)hs[i].frame0, hs[i].frames, hs[i].n_au, hs[i].flags, hs[i].err, hs[i].err_au,
+                            f_fast[i], f_fast[cap_seg + i], f_end[i], f_end[cap_seg + i]);
+            }
         }
         // ---------------- a table too small, a kernel left out that had work, a tile or the output buffer too small?
         if (!k.overflow && !(status & (SEG_OVERFLOW | STATUS_PCM_SMALL))) break;

@@ -474,6 +474,67 @@ def test_pipelined_track_decode(pkg, oracle, engine, disc_cache, name, part):
         assert np.array_equal(got, ref["pcm"]), (name, g["track"])
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_streams(pkg, oracle, engine, tmp_path, seed):
+    """Streams nobody wrote down: per seed a disc of three tracks whose shape (channel layout,
+    substreams, access-unit size, restart interval, blocks per unit, filter orders, matrices,
+    syntax features, PCM in between) is drawn at random, every track against the oracle — in one
+    call for the title set and through the pipelined path track by track."""
+    import random
+    import dvda_gen as g
+    rnd = random.Random(7700 + seed)
+    layouts = [(0, 1), (1, 1), (1, 1), (2, 1), (3, 1), (9, 1), (20, 1), (6, 2), (12, 2), (12, 2), (18, 2), (19, 2), (20, 2)]
+    bits = [g.CHECKDATA, g.BYPASS, g.NOISE, g.QUANT, g.OUTSHIFT, g.EXTRAWORD, g.TERMINATOR, g.FLAGS, g.SPARSE,
+            g.MIDAU_PARAMS, g.MID_RESTART, g.SYNC_NO_RST, g.SS1_CHK_QUIRK, g.RANDOM_PADS, g.FIR_CARRY]
+
+    def mlp_track(join):
+        asg, nss = rnd.choice(layouts)
+        feats = 0
+        for b in bits:
+            if rnd.random() < 0.45:
+                feats |= b
+        rate = rnd.choice([44100, 48000, 96000, 96000, 192000])
+        fir = rnd.choice([0, 2, 4, 8])
+        return g.mlp(rnd.randrange(1500, 7000), bps=rnd.choice([16, 24, 24]), rate=rate, assignment=asg, seed=rnd.randrange(1, 1 << 20),
+                     features=feats, substreams=nss, au_frames=rnd.choice([0, 0, 40]) if rate <= 48000 else 0,
+                     restart_interval=rnd.choice([1, 2, 3, 5, 8, 16]), max_blocks=rnd.choice([1, 1, 2, 4]),
+                     fir_max=fir, iir_max=rnd.choice([0, 2, 4]) if fir <= 4 else 0,
+                     matrices=rnd.choice([0, 1, 2, 3, 6]), noise_bits=rnd.randrange(4, 20), join_previous=join)
+
+    tracks = [mlp_track(0)]
+    tracks.append(g.pcm(rnd.randrange(800, 5000), bps=rnd.choice([16, 24]), rate=rnd.choice([48000, 96000]),
+                        assignment=rnd.choice([0, 1, 3]), seed=rnd.randrange(1, 1 << 20)) if rnd.random() < 0.4 else mlp_track(0))
+    tracks.append(mlp_track(1 if tracks[1]["codec"] == 1 and rnd.random() < 0.3 and
+                            (tracks[1]["assignment"], tracks[1]["substreams"]) == (tracks[0]["assignment"], tracks[0]["substreams"]) else 0))
+    directory = str(tmp_path / "AUDIO_TS")
+    info = g.make_disc(directory, [tracks])
+    sectors = oracle.read_aobs(directory)
+    n_sectors = len(sectors) // 2048
+    descs = [(t["first_sector"], t["last_sector"], t["pts_length"]) for t in info[0]]
+    refs = [oracle.decode_track(sectors, *d) for d in descs]
+    # (the oracle is pinned on the catalog; on a stream drawn here the unmodified reference has the word)
+    rc, ref_tracks, _s, err = oracle.run_dump(oracle.REF_DUMP, directory)
+    assert rc == 0, err
+    assert len(ref_tracks) == len(refs)
+    for rt, ref in zip(ref_tracks, refs):
+        assert ref is not None and rt["frames"] == ref["frames"] and rt["fnv"] == oracle.fnv1a(ref["pcm"]), (seed, rt)
+    res = engine.decode_host(sectors, descs)
+    for i, (r, ref) in enumerate(zip(res, refs)):
+        assert (r.status == 0) == (ref is not None), (seed, i, tracks[i])
+        if ref is None:
+            continue
+        assert (r.frames, r.channels, r.bits_per_sample, r.sample_rate, r.error_flags) == \
+               (ref["frames"], ref["channels"], ref["bits_per_sample"], ref["sample_rate"], ref["error_flags"]), (seed, i, tracks[i])
+        assert np.array_equal(engine.fetch(r), ref["pcm"]), (seed, i, tracks[i])
+    for i, (d, ref) in enumerate(zip(descs, refs)):
+        if ref is None or not ref["frames"]:
+            continue
+        out = np.zeros(ref["frames"] * ref["channels"] + 1024, dtype=np.int32)
+        r = engine.decode_track_pipelined(sectors.ctypes.data, n_sectors, d, out.ctypes.data, len(out), part_sectors=rnd.choice([3, 5, 9]))
+        assert r.status == 0 and r.frames == ref["frames"], (seed, i, r.frames, ref["frames"], tracks[i])
+        assert np.array_equal(out[: r.frames * r.channels].reshape(-1, r.channels), ref["pcm"]), (seed, i, tracks[i])
+
+
 @pytest.mark.parametrize("name", ["c1_pcm_2ch16", "c2_mlp_2ch96", "pcm_layouts"])
 def test_dvda2wav_matches_the_reference_tool(pkg, oracle, disc_cache, tmp_path, name):
     """tools/dvda2wav.c on the GPU library writes the same .wav files, byte for byte, as the
