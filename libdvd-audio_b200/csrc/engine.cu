@@ -946,10 +946,32 @@ static int decode_end(dvdagpu_ctx *c, dvdagpu_track_result *results)
                 cudaMemcpy(hs.data(), c->buf[B_SEGS].p, k.nseg * sizeof(SegDev), cudaMemcpyDeviceToHost);
                 cudaMemcpy(f_fast.data(), c->buf[B_SS_FLAGS_FAST].p, f_fast.size() * 4, cudaMemcpyDeviceToHost);
                 cudaMemcpy(f_end.data(), c->buf[B_SS_FLAGS].p, f_end.size() * 4, cudaMemcpyDeviceToHost);
-                for (uint32_t i = 0; i < k.nseg; i++)
-                    fprintf(stderr, "[dvdagpu] seg %u: track %u frame0=%llu frames=%u n_au=%u flags=%x err=%x err_au=%u | fast ss0=%x ss1=%x | end ss0=%x ss1=%x\n",
-                            i, hs[i].track, (unsigned long long)hs[i].frame0, hs[i].frames, hs[i].n_au, hs[i].flags, hs[i].err, hs[i].err_au,
+                std::vector<AuDev> ha(k.nau <= 8192 ? k.nau : 0);
+                std::vector<ParamSet> hp(ha.size());
+                if (!ha.empty()) {
+                    cudaMemcpy(ha.data(), c->buf[B_AU].p, ha.size() * sizeof(AuDev), cudaMemcpyDeviceToHost);
+                    cudaMemcpy(hp.data(), c->buf[B_PSETS].p, hp.size() * sizeof(ParamSet), cudaMemcpyDeviceToHost);
+                }
+                for (uint32_t i = 0; i < k.nseg; i++) {
+                    fprintf(stderr, "[dvdagpu] seg %u: track %u frame0=%llu frames=%u n_au=%u au_base=%u flags=%x err=%x err_au=%u | fast ss0=%x ss1=%x | end ss0=%x ss1=%x\n",
+                            i, hs[i].track, (unsigned long long)hs[i].frame0, hs[i].frames, hs[i].n_au, hs[i].au_base, hs[i].flags, hs[i].err, hs[i].err_au,
                             f_fast[i], f_fast[cap_seg + i], f_end[i], f_end[cap_seg + i]);
+                    for (uint32_t a = 0; a < hs[i].n_au && hs[i].au_base + a < ha.size(); a++) {
+                        const AuDev &u = ha[hs[i].au_base + a];
+                        const uint32_t pi = u.pset & 0x7FFFFFFFu;
+                        fprintf(stderr, "[dvdagpu]     au %u: frame0=%u n=%u seed=%06x pset=%u%s", hs[i].au_base + a, u.frame0, u.nframes, u.seed & 0x7FFFFF, pi, (u.pset >> 31) ? " (trivial)" : "");
+                        if (pi < hp.size()) {
+                            const ParamSet &P = hp[pi];
+                            fprintf(stderr, " | ml=%u mmc=%u nsh=%u noise=%u", P.matrix_len, P.mmc, P.noise_shift, P.uses_noise);
+                            for (uint32_t mk = 0; mk < P.matrix_len && mk < DVDA_MAX_MAT; mk++) {
+                                fprintf(stderr, " m%u->%u:", mk, P.out_ch[mk]);
+                                for (int cc = 0; cc < DVDA_MAX_CH; cc++) fprintf(stderr, "%d,", P.coeff[mk][cc]);
+                            }
+                            fprintf(stderr, " q=%u,%u sh=%u,%u", P.q[0], P.q[1], P.out_shift[0], P.out_shift[1]);
+                        }
+                        fprintf(stderr, "\n");
+                    }
+                }
             }
         }
         // ---------------- a table too small, a kernel left out that had work, a tile or the output buffer too small?

@@ -1278,6 +1278,7 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
     // pair in substream 0 and the rest, from channel 2 on, in substream 1)
     bool fallback = !cx.ok || (uint32_t)(cx.max_ch - cx.min_ch + 1) != NCH || cx.min_ch != (job.k ? 2u : 0u);
 
+    bool first_cleared = false;
     uint32_t seed_at = 0;                                 // frame the seed belongs to (advanced only when some matrix uses noise)
     bool uses_noise = false;
     // The state byte and the head of the delta (five 16-byte loads) of the next access unit are
@@ -1398,6 +1399,7 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
             ow[1 + cc] = (uint64_t)(uint32_t)sho | (uint64_t)(cb[cc] | nb << 8 | q << 16 | shift << 24) << 32;
         }
         if (fallback) break;
+        first_cleared = true;                             // (the first block starts no FIR from history this segment does not have)
         // bytes 16..55 of the snapshot (the positions in front are pass A1's)
         static_assert(offsetof(AuSnap, block_size) == 16 && offsetof(AuSnap, want) == 18 && offsetof(AuSnap, valid) == 19 &&
                       offsetof(AuSnap, min_ch) == 20 && offsetof(AuSnap, nch) == 21 && offsetof(AuSnap, has_matrix) == 22 &&
@@ -1438,6 +1440,11 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
             m.au[A] = R;
         }
     }
+    // A segment handed to the complete decoder before its first block was looked at may turn out to
+    // need the previous segment's FIR history there (the reference never clears it): the predecessor
+    // then has to come from the complete decoder too, which stores its tail in time
+    // (k_flag_predecessors).  Only a first block seen to start without FIR taps rules that out.
+    if (fallback && !first_cleared && !job.exact_history) flags |= SEG_WANTS_PREV;
     if (fallback) flags |= SEG_FALLBACK;
     m.ss_flags[job.k * m.cap_seg + job.seg] = flags;
     if (job.k == 0) S.frames = frames;
