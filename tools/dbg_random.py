@@ -33,8 +33,11 @@ def disc(seed):
     tracks = [mlp_track(0)]
     tracks.append(g.pcm(rnd.randrange(800, 5000), bps=rnd.choice([16, 24]), rate=rnd.choice([48000, 96000]),
                         assignment=rnd.choice([0, 1, 3]), seed=rnd.randrange(1, 1 << 20)) if rnd.random() < 0.4 else mlp_track(0))
-    tracks.append(mlp_track(1 if tracks[1]["codec"] == 1 and rnd.random() < 0.3 and
-                            (tracks[1]["assignment"], tracks[1]["substreams"]) == (tracks[0]["assignment"], tracks[0]["substreams"]) else 0))
+    join = 1 if tracks[1]["codec"] == 1 and rnd.random() < 0.3 else 0
+    tracks.append(mlp_track(join))
+    if join:
+        for key in ("bps_code", "rate_code", "assignment", "substreams", "au_frames"):
+            tracks[2][key] = tracks[1][key]
     return tracks
 
 eng = pkg.Engine(0)
