@@ -286,6 +286,32 @@ def test_damage_is_caught_like_the_oracle(pkg, oracle, engine, disc_cache, name,
     check_track(oracle, engine, res[0], sectors, g, name + " damaged")
 
 
+@pytest.mark.parametrize("name", ["c2_mlp_2ch96", "c3_mlp_6ch96", "mlp_wild_0", "mlp_wild_1", "c5_mixed", "pcm_rates_ragged"])
+def test_random_damage(pkg, oracle, engine, disc_cache, name):
+    """Sixty single-bit flips per disc, anywhere in a track's sectors (pack and packet headers,
+    access-unit lengths, major syncs, parameters, residuals, check bytes): where the track ends,
+    which error is flagged and every sample delivered before it are the oracle's."""
+    import random
+    directory, _ = disc_cache(name)
+    clean = oracle.read_aobs(directory)
+    rnd = random.Random(4242 + len(name))
+    for _ in range(60):
+        g = rnd.choice(GOLDEN[name]["tracks"])
+        sectors = clean.copy()
+        off = rnd.randrange(g["first"] * 2048, (g["last"] + 1) * 2048)
+        bit = 1 << rnd.randrange(8)
+        sectors[off] ^= bit
+        ref = oracle.decode_track(sectors, g["first"], g["last"], g["pts"])
+        r = engine.decode_host(sectors, [(g["first"], g["last"], g["pts"])])[0]
+        where = (name, g["track"], off, bit)
+        if ref is None:
+            assert r.status != 0, where
+            continue
+        assert r.status == 0, where
+        assert (r.frames, r.error_flags, r.channels) == (ref["frames"], ref["error_flags"], ref["channels"]), where
+        assert np.array_equal(engine.fetch(r), ref["pcm"]), where
+
+
 def test_truncated_window_is_reported(pkg, oracle, engine, disc_cache):
     directory, _ = disc_cache("c2_mlp_2ch96")
     g = GOLDEN["c2_mlp_2ch96"]["tracks"][0]
