@@ -297,8 +297,16 @@ __global__ void k_es_gather(const uint8_t *__restrict__ sectors, PacketTable pt,
 // Zero bytes behind the stream (bit readers may run ahead), and the packet table's capacity:
 // with more packets than rows the table is incomplete; the decode then runs on no packets at all
 // and the host comes back with a larger table.
-__global__ void k_es_tail(uint8_t *__restrict__ es, DecCounts *__restrict__ cnt, uint32_t rows)
+__global__ void k_es_tail(uint8_t *__restrict__ es, DecCounts *__restrict__ cnt, uint32_t rows,
+                          TrackDev *__restrict__ tracks, uint32_t n_tracks, const __grid_constant__ TrackArgs ta)
 {
+    // (the track table's rows from the kernel arguments: this block is in the chain anyway)
+    for (uint32_t i = threadIdx.x; i < n_tracks; i += blockDim.x) {
+        TrackDev T;
+        memset(&T, 0, sizeof T);
+        T.first_sector = ta.t[i][0]; T.last_sector = ta.t[i][1]; T.pts_length = ta.t[i][2]; T.cont = ta.t[i][3];
+        tracks[i] = T;
+    }
     const uint64_t end = cnt->es_total;
     for (uint32_t i = threadIdx.x; i < DVDA_ES_PAD / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(es + ((end + 15) & ~15ull))[i] = make_uint4(0, 0, 0, 0);
@@ -400,11 +408,16 @@ int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+// any_mlp false: the previous decode of this shape met no MLP packet — the gather is left out (an
+// MLP track then raises CAP_SHAPE in the track set-up and the decode is repeated with it).
+// targs: the track descriptors, written into `tracks` on the way (nullptr: the caller has done that).
 int launch_es_gather(const uint8_t *sectors, PacketTable pt, uint32_t rows, const uint64_t *pk_es, uint8_t *es,
-                     DecCounts *cnt, uint32_t *cnt_raw, uint16_t *slots, uint32_t nslots, cudaStream_t s)
+                     DecCounts *cnt, uint32_t *cnt_raw, uint16_t *slots, uint32_t nslots, bool any_mlp,
+                     TrackDev *tracks, uint32_t n_tracks, const TrackArgs *targs, cudaStream_t s)
 {
-    if (rows) LAUNCH(k_es_gather, div_up_u32((uint64_t)rows * 32, 256), 256, 0, s, sectors, pt, rows, cnt, pk_es, es, cnt_raw, slots, nslots < 2 ? nslots : 2u);
-    LAUNCH(k_es_tail, 1, 256, 0, s, es, cnt, rows);
+    if (rows && any_mlp) LAUNCH(k_es_gather, div_up_u32((uint64_t)rows * 32, 256), 256, 0, s, sectors, pt, rows, cnt, pk_es, es, cnt_raw, slots, nslots < 2 ? nslots : 2u);
+    static const TrackArgs none = {};
+    LAUNCH(k_es_tail, 1, 256, 0, s, es, cnt, rows, tracks, targs ? n_tracks : 0u, targs ? *targs : none);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

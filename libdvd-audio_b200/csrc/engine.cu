@@ -465,18 +465,6 @@ __global__ void __launch_bounds__(OB_THREADS) k_track_out_base(TrackDev *tracks,
     if (threadIdx.x == 0 && carry > capacity) atomicOr(status, STATUS_PCM_SMALL);
 }
 
-#define TRACKS_BY_ARG 192
-struct TrackArgs { uint32_t t[TRACKS_BY_ARG][4]; };
-__global__ void k_tracks_from_args(TrackDev *__restrict__ tracks, uint32_t n_tracks, const __grid_constant__ TrackArgs a)
-{
-    for (uint32_t i = threadIdx.x; i < n_tracks; i += blockDim.x) {
-        TrackDev T;
-        memset(&T, 0, sizeof T);
-        T.first_sector = a.t[i][0]; T.last_sector = a.t[i][1]; T.pts_length = a.t[i][2]; T.cont = a.t[i][3];
-        tracks[i] = T;
-    }
-}
-
 // ---- what the launches of a decode are sized for ------------------------------------------
 //
 // Nothing a decode finds out about its input goes back to the host before it is over, so every
@@ -721,8 +709,17 @@ static int decode_enqueue(dvdagpu_ctx *c)
         uint16_t *sync_slots = c->buf[B_SYNC_SLOTS].as<uint16_t>();
         // (the two count tables are one buffer: cleared together; the gather counts the sync patterns it meets)
         uint32_t *cnt_raw = c->buf[B_SYNC_CNT_RAW].as<uint32_t>(), *cnt_valid = cnt_raw + chunks_cap;
-        CUDA_TRY(cudaMemsetAsync(cnt_raw, 0, (size_t)chunks_cap * 8, s));
-        TIMED(DVDAGPU_K_ES_GATHER, launch_es_gather(d_sectors, pt, rows, pk_es, es, cnt, cnt_raw, sync_slots, nslots, s));
+        if (sh.any_mlp) CUDA_TRY(cudaMemsetAsync(cnt_raw, 0, (size_t)chunks_cap * 8, s));
+        // The track table's inputs.  Up to TRACKS_BY_ARG tracks travel as kernel arguments: no load
+        // from host memory stands in the decode chain (while bulk copies run on the link such a load
+        // waits behind them for a long time).
+        TrackDev *d_tracks = c->buf[B_TRACKS].as<TrackDev>();
+        TrackArgs ta0;
+        const bool by_arg = n_tracks <= TRACKS_BY_ARG;
+        if (by_arg)
+            for (uint32_t i = 0; i < n_tracks; i++) { ta0.t[i][0] = ht[i].first_sector; ta0.t[i][1] = ht[i].last_sector; ta0.t[i][2] = ht[i].pts_length; ta0.t[i][3] = ht[i].cont; }
+        TIMED(DVDAGPU_K_ES_GATHER, launch_es_gather(d_sectors, pt, rows, pk_es, es, cnt, cnt_raw, sync_slots, nslots, sh.any_mlp,
+                                                    d_tracks, n_tracks, by_arg ? &ta0 : nullptr, s));
         CUDA_TRY(record_timing(c->ev[1], s));
 
         // ---------------- index
@@ -735,17 +732,7 @@ static int decode_enqueue(dvdagpu_ctx *c)
             TRY(scan_batch(in, out, wide, 2, chunks_cap, tmp, tmp_bytes, s, copy));
             TRY(launch_sync_fill(es, cnt, chunks_cap, cnt_raw, sync_slots, nslots, base_raw, base_valid, raw, cap_sync, valid, cap_sync, s));
         }
-        TrackDev *d_tracks = c->buf[B_TRACKS].as<TrackDev>();
-        // The track table's inputs.  Up to TRACKS_BY_ARG tracks travel as kernel arguments: no load
-        // from host memory stands in the decode chain (while bulk copies run on the link such a load
-        // waits behind them for a long time).
-        if (n_tracks <= TRACKS_BY_ARG) {
-            TrackArgs ta0;
-            for (uint32_t i = 0; i < n_tracks; i++) { ta0.t[i][0] = ht[i].first_sector; ta0.t[i][1] = ht[i].last_sector; ta0.t[i][2] = ht[i].pts_length; ta0.t[i][3] = ht[i].cont; }
-            LAUNCH(k_tracks_from_args, 1, 128, 0, s, d_tracks, n_tracks, ta0);
-        } else {
-            TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
-        }
+        if (!by_arg) TRY(small_h2d(c, d_tracks, ht.data(), n_tracks * sizeof(TrackDev)));
         TrackSetupArgs ta;
         ta.es = es; ta.cnt = cnt; ta.n_sectors = n_sectors; ta.sec_base = sec_base; ta.bad_prefix = bad_prefix;
         ta.pt = pt; ta.pk_es = pk_es; ta.pk_pf = pk_pf; ta.pk_nonmlp = nm_prefix; ta.pk_pcm_stop = stop_prefix;
@@ -756,10 +743,10 @@ static int decode_enqueue(dvdagpu_ctx *c)
         uint32_t *trk_grp_base = c->buf[B_TRK_GRP_BASE].as<uint32_t>();
         DecWork *d_work = c->buf[B_DEC_WORK].as<DecWork>();
         OutWork *d_out_work = c->buf[B_OUT_WORK].as<OutWork>();
-        TRY(launch_track_plan(d_tracks, n_tracks, trk_pk_lo, trk_seg_base, trk_grp_base, d_work, d_out_work, cap_work, cap_seg, cap_grp,
-                              cap_sync, cnt, s));
-
         const PlanLimits lim = {cap_au, cells, sh.max_au, lim_nss, sh.out_warps, sh.any_pcm ? 1u : 0u, sh.any_mlp ? 1u : 0u};
+        TRY(launch_track_plan(d_tracks, n_tracks, trk_pk_lo, trk_seg_base, trk_grp_base, d_work, d_out_work, cap_work, cap_seg, cap_grp,
+                              cap_sync, cnt, sh.any_mlp ? nullptr : &lim, s));
+
         memset(&m, 0, sizeof m);
         m.es = es; m.pk_es = pk_es; m.cnt = cnt; m.cap_seg = cap_seg; m.cap_au = cap_au; m.cap_grp = cap_grp;
         m.tracks = d_tracks; m.n_tracks = n_tracks;
@@ -825,16 +812,16 @@ static int decode_enqueue(dvdagpu_ctx *c)
             // ---------------- decode
             uint32_t *seg_frames = c->buf[B_SEG_FRAMES].as<uint32_t>();
             uint64_t *seg_frame_scan = c->buf[B_SEG_FRAME_SCAN].as<uint64_t>();
-            TRY(launch_group_offsets(m.groups, cap_grp, cnt, cell_base, s));
+            // (the group offsets' kernel also gives the fast path's segment tables their start values)
+            TRY(launch_group_offsets(m.groups, cap_grp, cnt, cell_base,
+                                     use_fast ? (void *)m.seg_ctx : nullptr, use_fast ? ((size_t)cap_seg + 1) * 2 * seg_ctx_bytes() : 0,
+                                     use_fast ? m.ss_flags : nullptr, use_fast ? (cap_seg + 1) * 2 : 0u, s));
             m.fast = 0;
             if (use_fast) {
                 // The three-pass path (access-unit parallel) decodes what has the common shape; what it
-                // gives up on is flagged (start with every segment flagged: substreams with more than 4
-                // channels are not visited by the fast path at all) ...
-                CUDA_TRY(cudaMemsetAsync(m.seg_ctx, 0, ((size_t)cap_seg + 1) * 2 * seg_ctx_bytes(), s));   // contexts exist only where pass A0 goes
-                CUDA_TRY(cudaMemsetAsync(m.ss_flags, SEG_FALLBACK, ((size_t)cap_seg + 1) * 2 * 4, s));
+                // gives up on is flagged ...
                 TRY(launch_mlp_fast(m, d_work, cap_pairs, sh.max_au, lim_nss, c->kev, c->kev_used, c->aux_ev[1], s));
-                CUDA_TRY(cudaMemcpyAsync(m.ss_flags_prev, m.ss_flags, ((size_t)cap_seg + 1) * 2 * 4, cudaMemcpyDeviceToDevice, s));
+                // (the flags as the fast path left them: what the complete decoder takes, what the output pass leaves alone)
                 CUDA_TRY(cudaMemcpyAsync(m.ss_flags_fast, m.ss_flags, ((size_t)cap_seg + 1) * 2 * 4, cudaMemcpyDeviceToDevice, s));
                 m.fast = 1;
             }
@@ -847,8 +834,7 @@ static int decode_enqueue(dvdagpu_ctx *c)
             TRY(scan_u32_to_u64(seg_frames, seg_frame_scan, cap_seg, tmp, tmp_bytes, s));
             TRY(launch_track_finalize(m, seg_frame_scan, d_status, s));
         } else {
-            TRY(launch_plan_check(cnt, lim, s));
-            CUDA_TRY(record_timing(c->ev[2], s));
+            CUDA_TRY(record_timing(c->ev[2], s));          // (the plan's block has checked the limits itself)
         }
         // The output buffer was sized before the frame counts are known (every MLP sample has a place
         // in the tiles, so the tiles' size bounds them); the tracks' places in it are computed on the device.

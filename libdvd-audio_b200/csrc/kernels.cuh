@@ -66,6 +66,11 @@ struct MlpTables {
     const uint16_t *huff_lut;      // [4][512] Huffman look-up table in device memory (built once per device)
 };
 
+// Track descriptors of a decode as a kernel argument (up to TRACKS_BY_ARG tracks): no load from
+// host memory stands in the decode chain.
+#define TRACKS_BY_ARG 192
+struct TrackArgs { uint32_t t[TRACKS_BY_ARG][4]; };   // first sector, last sector, PTS length, DVDAGPU_PART_* / budget flags
+
 // demux.cu
 int upload_pcm_tables(const uint8_t *tables);
 int launch_sector_count(const uint8_t *sectors, uint32_t n_sectors, uint32_t *sec_cnt, uint32_t *sec_bad, cudaStream_t s);
@@ -77,7 +82,8 @@ int launch_packet_fill(const uint8_t *sectors, uint32_t n_sectors, const uint32_
 // ... and notes the major-sync patterns it comes across in the slots of their 512-byte chunks
 // (cnt_raw must be zero before)
 int launch_es_gather(const uint8_t *sectors, PacketTable pt, uint32_t rows, const uint64_t *pk_es, uint8_t *es,
-                     DecCounts *cnt, uint32_t *cnt_raw, uint16_t *slots, uint32_t nslots, cudaStream_t s);
+                     DecCounts *cnt, uint32_t *cnt_raw, uint16_t *slots, uint32_t nslots, bool any_mlp,
+                     TrackDev *tracks, uint32_t n_tracks, const TrackArgs *targs, cudaStream_t s);
 int launch_pcm_unpack(const uint8_t *sectors, PacketTable pt, uint32_t rows, const DecCounts *cnt, const uint32_t *status,
                       const uint64_t *pk_pf, const TrackDev *tracks, const uint32_t *trk_pk_lo, uint32_t n_tracks, int32_t *pcm, cudaStream_t s);
 
@@ -115,12 +121,13 @@ int launch_track_setup(TrackSetupArgs a, TrackDev *tracks, uint32_t n_tracks, cu
 struct DecWork { uint32_t warp0, track, k, nch; };   // a run of warps: the groups of substream k (nch channels) of one track
 // the output pass of the fast path: a run of warps per track (n0, n1: channels of substream 0 / 1, n1 = 0: one substream)
 struct OutWork { uint32_t warp0, track, n0, n1; };
-int launch_track_plan(TrackDev *tracks, uint32_t n_tracks, uint32_t *trk_pk_lo, uint32_t *trk_seg_base, uint32_t *trk_grp_base,
-                      DecWork *work, OutWork *out_work, uint32_t cap_work, uint32_t cap_seg, uint32_t cap_grp, uint32_t cap_sync,
-                      DecCounts *cnt, cudaStream_t s);
 // after the access units are counted and the groups set up: capacities of the access-unit tables, the tiles
 // and the grids that were sized from the previous decode (lim_*: what the launches of this decode cover)
 struct PlanLimits { uint32_t cap_au; uint64_t cap_cells; uint32_t max_au, nss, out_warps, pcm, mlp; };
+int launch_track_plan(TrackDev *tracks, uint32_t n_tracks, uint32_t *trk_pk_lo, uint32_t *trk_seg_base, uint32_t *trk_grp_base,
+                      DecWork *work, OutWork *out_work, uint32_t cap_work, uint32_t cap_seg, uint32_t cap_grp, uint32_t cap_sync,
+                      DecCounts *cnt, const PlanLimits *check_now, cudaStream_t s);
+// (check_now: no MLP side follows — the plan's block does k_plan_check's work itself)
 int launch_plan_check(DecCounts *cnt, PlanLimits lim, cudaStream_t s);
 int launch_segment_fill(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_seg_base,
                         const uint64_t *valid, SegDev *segs, uint32_t cap_seg, const DecCounts *cnt, cudaStream_t s);
@@ -134,7 +141,8 @@ int launch_yield(MlpTables m, uint32_t rows, const uint32_t *seg_au_base, Packet
                  uint8_t *pk_yield, bool any_parts, cudaStream_t s);
 int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t *trk_grp_base, const SegDev *segs,
                        GroupDev *groups, uint32_t cap_grp, DecCounts *cnt, uint32_t *grp_cells, const uint32_t *seg_need, cudaStream_t s);
-int launch_group_offsets(GroupDev *groups, uint32_t cap_grp, const DecCounts *cnt, const uint64_t *cell_base, cudaStream_t s);
+int launch_group_offsets(GroupDev *groups, uint32_t cap_grp, const DecCounts *cnt, const uint64_t *cell_base,
+                         void *zero, size_t zero_bytes, uint32_t *flags, uint32_t n_flags, cudaStream_t s);
 
 // mlp_decode.cu
 // windowed: which of the two check-data kernels (small access units: shared-memory windows)

@@ -1043,7 +1043,7 @@ __device__ __forceinline__ bool au_seat(const MlpTables &m, const TrackDev &T, u
     grd_stage(b, m.es, col, au_pos);
     const AuLayout L = au_layout_from([&b, au_pos](uint32_t i) { return grd_byte(b, au_pos + i); }, T);
     // damage and the end-of-track rules are the complete decoder's business (check data runs
-    // beside the passes; k_flag_damaged hands the segments it objects to over afterwards)
+    // beside the passes; k_flag_fallbacks hands the segments it objects to over afterwards)
     if (!L.ok || au_pos + L.total > T.es_cut) return false;
     const uint32_t start = k ? L.end[0] : 0;
     const uint32_t len = L.end[k] - start - (L.chk0 ? 2 : 0);
@@ -1443,7 +1443,7 @@ __device__ __forceinline__ void resolve_segment(const MlpTables &m, const Decode
     // A segment handed to the complete decoder before its first block was looked at may turn out to
     // need the previous segment's FIR history there (the reference never clears it): the predecessor
     // then has to come from the complete decoder too, which stores its tail in time
-    // (k_flag_predecessors).  Only a first block seen to start without FIR taps rules that out.
+    // (k_flag_fallbacks).  Only a first block seen to start without FIR taps rules that out.
     if (fallback && !first_cleared && !job.exact_history) flags |= SEG_WANTS_PREV;
     if (fallback) flags |= SEG_FALLBACK;
     m.ss_flags[job.k * m.cap_seg + job.seg] = flags;
@@ -1942,7 +1942,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, DEC_MIN_BLOCKS) k_mlp_decode(M
     if (m.fast) {
         // after the fast path: only what it gave up on (any substream of the segment)
         const TrackDev &T = m.tracks[m.segs[job.seg].track];
-        const uint32_t f = m.ss_flags_prev[job.seg] | (T.nss == 2 ? m.ss_flags_prev[m.cap_seg + job.seg] : 0);
+        const uint32_t f = m.ss_flags_fast[job.seg] | (T.nss == 2 ? m.ss_flags_fast[m.cap_seg + job.seg] : 0);
         if (!(f & SEG_FALLBACK)) return;
     }
     const uint32_t rs = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][lane]);
@@ -2027,27 +2027,27 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) k_mlp_entropy(MlpTables m, con
 // A segment that needs its predecessor's FIR history is decoded by the complete decoder
 // (+ k_carry_fix), which reads the predecessor's stored tail: have the complete decoder
 // produce that one too (the output pass would store it too late).
-__global__ void k_flag_predecessors(MlpTables m)
+// (the two sets only OR the one bit into other segments' words: their order does not matter)
+__global__ void k_flag_fallbacks(MlpTables m)
 {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t seg = idx >> 1, k = idx & 1;
-    if (seg >= m.cnt->nseg) return;
-    const uint32_t fl = m.ss_flags[k * m.cap_seg + seg];
-    const TrackDev &T = m.tracks[m.segs[seg].track];
-    // (does the complete decoder have anything to do?  It and the carry fix leave at once if not.)
-    if (k < T.nss && (fl & (SEG_FALLBACK | SEG_WANTS_PREV))) *m.any_fallback = 1;
-    if (!(fl & SEG_WANTS_PREV)) return;
-    if (seg > T.seg_base) atomicOr(&m.ss_flags[k * m.cap_seg + seg - 1], SEG_FALLBACK);
-}
-
-__global__ void k_flag_damaged(MlpTables m)
-{
-    const uint32_t A = blockIdx.x * blockDim.x + threadIdx.x;
-    if (A >= m.cnt->nau || !m.au_err[A]) return;
-    const uint32_t seg = m.au_seg[A];
-    atomicOr(&m.ss_flags[seg], SEG_FALLBACK);
-    atomicOr(&m.ss_flags[m.cap_seg + seg], SEG_FALLBACK);
-    *m.any_fallback = 1;
+    {
+        const uint32_t seg = idx >> 1, k = idx & 1;
+        if (seg < m.cnt->nseg) {
+            const uint32_t fl = m.ss_flags[k * m.cap_seg + seg];
+            const TrackDev &T = m.tracks[m.segs[seg].track];
+            // (does the complete decoder have anything to do?  It and the carry fix leave at once if not.)
+            if (k < T.nss && (fl & (SEG_FALLBACK | SEG_WANTS_PREV))) *m.any_fallback = 1;
+            if ((fl & SEG_WANTS_PREV) && seg > T.seg_base) atomicOr(&m.ss_flags[k * m.cap_seg + seg - 1], SEG_FALLBACK);
+        }
+    }
+    const uint32_t A = idx;
+    if (A < m.cnt->nau && m.au_err[A]) {
+        const uint32_t seg = m.au_seg[A];
+        atomicOr(&m.ss_flags[seg], SEG_FALLBACK);
+        atomicOr(&m.ss_flags[m.cap_seg + seg], SEG_FALLBACK);
+        *m.any_fallback = 1;
+    }
 }
 
 size_t au_snap_bytes() { return sizeof(AuSnap); }
@@ -2089,11 +2089,11 @@ int launch_mlp_fast(MlpTables m, const DecWork *work, uint32_t cap_pairs, uint32
         CUDA_TRY(record_timing(kev[slot[pass]][1], s));
         kev_used[slot[pass]] = true;
     }
-    if (m.cap_seg) LAUNCH(k_flag_predecessors, div_up_u32((uint64_t)m.cap_seg * 2, 256), 256, 0, s, m);
     // check data ran beside all this: segments with a damaged or dropped access unit (parity, CRC,
-    // changed stream parameters) go to the complete decoder, which knows where such a track ends
+    // changed stream parameters) go to the complete decoder, which knows where such a track ends —
+    // as do the predecessors of segments that want their FIR history (one launch for both)
     CUDA_TRY(cudaStreamWaitEvent(s, checked, 0));
-    if (m.cap_au) LAUNCH(k_flag_damaged, div_up_u32(m.cap_au, 256), 256, 0, s, m);
+    if (m.cap_seg || m.cap_au) LAUNCH(k_flag_fallbacks, div_up_u32(max((uint64_t)m.cap_seg * 2, (uint64_t)m.cap_au), 256), 256, 0, s, m);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -360,11 +360,12 @@ int launch_track_setup(TrackSetupArgs a, TrackDev *tracks, uint32_t n_tracks, cu
 // in order), the work list of the per-segment passes, totals and flags for the host — what the
 // host used to compute between two round trips.
 #define PLAN_THREADS 256
+__device__ __forceinline__ void plan_check(DecCounts *__restrict__ cnt, const PlanLimits &lim);
 __global__ void __launch_bounds__(PLAN_THREADS)
 k_track_plan(TrackDev *__restrict__ tracks, uint32_t n_tracks, uint32_t *__restrict__ trk_pk_lo,
              uint32_t *__restrict__ trk_seg_base, uint32_t *__restrict__ trk_grp_base,
              DecWork *__restrict__ work, OutWork *__restrict__ out_work, uint32_t cap_work, uint32_t cap_seg, uint32_t cap_grp,
-             uint32_t cap_sync, DecCounts *__restrict__ cnt)
+             uint32_t cap_sync, DecCounts *__restrict__ cnt, uint32_t check_now, PlanLimits lim)
 {
     __shared__ uint32_t s_flags[4];
     if (threadIdx.x < 4) s_flags[threadIdx.x] = 0;
@@ -443,10 +444,11 @@ k_track_plan(TrackDev *__restrict__ tracks, uint32_t n_tracks, uint32_t *__restr
         cnt->pcm_fixed = pcm_carry + 4ull * n_tracks + 64;
         cnt->any_pcm = s_flags[0]; cnt->any_mlp = s_flags[1]; cnt->nss_max = s_flags[2] ? s_flags[2] : 1; cnt->chan_mask = s_flags[3];
         cnt->max_au = 0; cnt->max_chunks = 0;
+        if (check_now) plan_check(cnt, lim);
     }
 }
 
-__global__ void k_plan_check(DecCounts *__restrict__ cnt, PlanLimits lim)
+__device__ __forceinline__ void plan_check(DecCounts *__restrict__ cnt, const PlanLimits &lim)
 {
     uint32_t over = cnt->overflow;
     if (cnt->nau > lim.cap_au) { over |= CAP_AU; cnt->need_au = cnt->nau; }
@@ -462,11 +464,15 @@ __global__ void k_plan_check(DecCounts *__restrict__ cnt, PlanLimits lim)
     }
 }
 
+__global__ void k_plan_check(DecCounts *__restrict__ cnt, PlanLimits lim) { plan_check(cnt, lim); }
+
 int launch_track_plan(TrackDev *tracks, uint32_t n_tracks, uint32_t *trk_pk_lo, uint32_t *trk_seg_base, uint32_t *trk_grp_base,
                       DecWork *work, OutWork *out_work, uint32_t cap_work, uint32_t cap_seg, uint32_t cap_grp, uint32_t cap_sync,
-                      DecCounts *cnt, cudaStream_t s)
+                      DecCounts *cnt, const PlanLimits *check_now, cudaStream_t s)
 {
-    LAUNCH(k_track_plan, 1, PLAN_THREADS, 0, s, tracks, n_tracks, trk_pk_lo, trk_seg_base, trk_grp_base, work, out_work, cap_work, cap_seg, cap_grp, cap_sync, cnt);
+    const PlanLimits none = {};
+    LAUNCH(k_track_plan, 1, PLAN_THREADS, 0, s, tracks, n_tracks, trk_pk_lo, trk_seg_base, trk_grp_base, work, out_work, cap_work, cap_seg, cap_grp, cap_sync, cnt,
+           check_now ? 1u : 0u, check_now ? *check_now : none);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -726,9 +732,16 @@ __global__ void k_group_setup(const TrackDev *__restrict__ tracks, uint32_t n_tr
     atomicMax(&cnt->max_chunks, (cap + 31) / 32);        // most 32-frame chunks in a group
 }
 
-__global__ void k_group_offsets(GroupDev *__restrict__ groups, const DecCounts *__restrict__ cnt, const uint64_t *__restrict__ cell_base)
+// ... and, on the way, the start values of the fast path's per-segment tables (two stream
+// operations fewer in the chain): zero16 = 16-byte pieces to clear (segment contexts exist only
+// where pass A0 goes), flags = words to set to SEG_FALLBACK (every segment starts out flagged:
+// substreams with more than 4 channels are not visited by the fast path at all)
+__global__ void k_group_offsets(GroupDev *__restrict__ groups, const DecCounts *__restrict__ cnt, const uint64_t *__restrict__ cell_base,
+                                uint4 *__restrict__ zero16, uint32_t n_zero16, uint32_t *__restrict__ flags, uint32_t n_flags)
 {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+    for (uint32_t i = g; i < n_zero16; i += step) zero16[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = g; i < n_flags; i += step) flags[i] = SEG_FALLBACK;
     if (g >= cnt->ngroups) return;
     groups[g].tile_off = cell_base[g] * DVDA_LANES;
     groups[g].byp_off = cell_base[g] * DVDA_LANES;
@@ -742,10 +755,13 @@ int launch_group_setup(const TrackDev *tracks, uint32_t n_tracks, const uint32_t
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-int launch_group_offsets(GroupDev *groups, uint32_t cap_grp, const DecCounts *cnt, const uint64_t *cell_base, cudaStream_t s)
+int launch_group_offsets(GroupDev *groups, uint32_t cap_grp, const DecCounts *cnt, const uint64_t *cell_base,
+                         void *zero, size_t zero_bytes, uint32_t *flags, uint32_t n_flags, cudaStream_t s)
 {
-    if (!cap_grp) return 0;
-    LAUNCH(k_group_offsets, div_up_u32(cap_grp, 128), 128, 0, s, groups, cnt, cell_base);
+    if (!cap_grp && !zero_bytes && !n_flags) return 0;
+    const uint32_t n16 = (uint32_t)(zero_bytes / 16);          // (the caller's tables are whole 16-byte pieces)
+    const uint32_t work = max(max(cap_grp, n16), n_flags);
+    LAUNCH(k_group_offsets, min(div_up_u32(work, 128), 148u * 8), 128, 0, s, groups, cnt, cell_base, static_cast<uint4 *>(zero), n16, flags, n_flags);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
