@@ -1,4 +1,8 @@
-"""debug aid: decodes the random disc of a seed (tests/test_gpu_parity.py::test_random_streams) and prints where the engine differs from the oracle"""
+"""Fuzzing aid: decodes the random discs of the given seeds (the shapes of tests/test_gpu_parity.py::test_random_streams)
+in one call each and prints where the engine differs from the oracle.  DBG_TRACK=n: that track alone, with the
+engine's debug dump (segment and access-unit tables).
+
+usage: python tools/fuzz_engine.py seed [seed ...]"""
 import importlib, os, sys, random, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "gen"), os.path.join(ROOT, "oracle")):
