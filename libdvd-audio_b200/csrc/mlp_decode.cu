@@ -1600,24 +1600,35 @@ __device__ __forceinline__ void entropy_au(const MlpTables &m, const DecodeJob &
 // The matrix step of a patch of the output pass: lane = frame of a row.  The row's pad words say
 // which parameters govern each run of 8 frames and where the noise generator stood at its start.
 
+// Six-channel tracks (five rows of 196 words in a patch of 1152): the parameter sets of the two
+// access units a patch can touch are kept in the patches' unused tails, brought there by the
+// segment's lanes at the top of each unit — the frames of the matrix step then wait for shared
+// memory, not for a chain of dependent global loads.
+#define PSET_SM_OFF6 (5 * (OUT_PF * 6 + OUT_ROW_PAD))     // first free word of a patch
+#define PSET_SM_WORDS 32                                  // a ParamSet
+static_assert(PSET_SM_OFF6 + 5 * PSET_SM_WORDS <= OUT_PATCH_WORDS && (PSET_SM_OFF6 % 4) == 0, "room for five parameter sets behind the rows");
 template <int NL>
-__device__ __forceinline__ void matrix_rows(const ParamSet *__restrict__ psets, int32_t *pb, const uint32_t *meta, const uint8_t *__restrict__ byp_rows,
+__device__ __forceinline__ void matrix_rows(const ParamSet *__restrict__ psets, int32_t *pb, const int32_t *patch, const uint32_t *meta, const uint8_t *__restrict__ byp_rows,
                                          uint32_t row_words, uint32_t lps, uint32_t spw, uint32_t slotmap, uint32_t f0, uint32_t fend)
 {
+    constexpr bool SM = NL == 6;                          // parameter sets in shared memory
+    auto ld8 = [](const void *p) { return SM ? *reinterpret_cast<const uint2 *>(p) : __ldg(reinterpret_cast<const uint2 *>(p)); };
+    auto ld16 = [](const void *p) { return SM ? *reinterpret_cast<const uint4 *>(p) : __ldg(reinterpret_cast<const uint4 *>(p)); };
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t fr = f0 + lane;
     for (uint32_t row = 0; row < spw; row++) {
         int32_t *rw = pb + row * row_words;
         const uint32_t note = (uint32_t)rw[OUT_PF * lps + (lane >> 3)];
         if (fr >= fend || (note & NOTE_SKIP)) continue;
-        const uint32_t ps = meta[row * 8 + 4 + ((note / NOTE_UNIT) & 1)];
+        const uint32_t unit = (note / NOTE_UNIT) & 1;
+        const uint32_t ps = meta[row * 8 + 4 + unit];
         if (ps == 0xFFFFFFFFu) continue;
-        const ParamSet *Q = &psets[ps];
+        const ParamSet *Q = SM ? reinterpret_cast<const ParamSet *>(patch + unit * OUT_PATCH_WORDS + PSET_SM_OFF6 + row * PSET_SM_WORDS) : &psets[ps];
         int32_t *px = rw + lane * lps;
         int32_t v[NL];
 #pragma unroll
         for (int c = 0; c < NL; c++) v[c] = (uint32_t)c < lps ? px[(slotmap >> (4 * c)) & 15] : 0;
-        const uint2 hd = __ldg(reinterpret_cast<const uint2 *>(Q->out_ch));        // out_ch[6], matrix_len, mmc
+        const uint2 hd = ld8(Q->out_ch);                                           // out_ch[6], matrix_len, mmc
         const uint64_t ocs = (uint64_t)hd.y << 32 | hd.x;
         const uint32_t ml = (hd.y >> 16) & 0xFF, mmc = hd.y >> 24;
         if (ml) {
@@ -1627,10 +1638,10 @@ __device__ __forceinline__ void matrix_rows(const ParamSet *__restrict__ psets, 
             const int32_t z0 = (int32_t)((uint32_t)(int32_t)(int8_t)(sd >> 15) << nsh);
             const int32_t z1 = (int32_t)((uint32_t)(int32_t)(int8_t)(sd >> 7) << nsh);
             const uint32_t bm = byp_rows[(uint64_t)fr * DVDA_LANES + row];
-            const uint2 qw = __ldg(reinterpret_cast<const uint2 *>(Q->q));
+            const uint2 qw = ld8(Q->q);
             const uint64_t qs = (uint64_t)qw.y << 32 | qw.x;
             for (uint32_t mk = 0; mk < ml; mk++) {
-                const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(Q->coeff[mk]));
+                const uint4 cw = ld16(Q->coeff[mk]);
                 const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
                 long long sum = (long long)z0 * Q->coeff[mk][mmc + 1] + (long long)z1 * Q->coeff[mk][mmc + 2];
 #pragma unroll
@@ -1644,7 +1655,7 @@ __device__ __forceinline__ void matrix_rows(const ParamSet *__restrict__ psets, 
                 for (int c = 0; c < NL; c++) if ((uint32_t)c == oc) v[c] = rr;
             }
         }
-        const uint2 ow = __ldg(reinterpret_cast<const uint2 *>(Q->out_shift));
+        const uint2 ow = ld8(Q->out_shift);
         const uint64_t os = (uint64_t)ow.y << 32 | ow.x;
 #pragma unroll
         for (int c = 0; c < NL; c++)
@@ -1726,7 +1737,7 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
         int32_t *pb = patch + ((f0 / OUT_PF) & 1) * OUT_PATCH_WORDS;
         if (patch_matrix) {
             __syncwarp();
-            matrix_rows<NL>(m.psets, pb, meta, byp_rows, row_words, lps, spw, slotmap, f0, fend);
+            matrix_rows<NL>(m.psets, pb, patch, meta, byp_rows, row_words, lps, spw, slotmap, f0, fend);
             patch_matrix = false;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the parked samples, for the async proxy
@@ -1800,6 +1811,13 @@ __device__ __forceinline__ void filter_out_warp(const MlpTables &m, const OutWor
             for (int t = 0; t < 8; t++) { cf[t] = 0; ci[t] = 0; }
         }
         if (j == 0 && sl < spw) meta[sl * 8 + 4 + (a & 1)] = au_act && !trivial ? pset & 0x7FFFFFFFu : 0xFFFFFFFFu;
+        if (LPS == 6 && au_act && !trivial && sl < spw) {
+            // the unit's parameter set, eight pieces of 16 bytes, into the tail of the patch with the unit's parity
+            const uint4 *src = reinterpret_cast<const uint4 *>(&m.psets[pset & 0x7FFFFFFFu]);
+            uint4 *dst = reinterpret_cast<uint4 *>(patch + (a & 1) * OUT_PATCH_WORDS + PSET_SM_OFF6 + sl * PSET_SM_WORDS);
+            dst[j] = __ldg(src + j);
+            if (j < 2) dst[6 + j] = __ldg(src + 6 + j);
+        }
         a++;
         const uint32_t nf = __reduce_max_sync(0xFFFFFFFFu, ((cls & 15) + 3) >> 2);
         const uint32_t ni = __reduce_max_sync(0xFFFFFFFFu, ((cls >> 4) + 3) >> 2);
