@@ -2056,7 +2056,17 @@ __global__ void k_flag_fallbacks(MlpTables m)
             const TrackDev &T = m.tracks[m.segs[seg].track];
             // (does the complete decoder have anything to do?  It and the carry fix leave at once if not.)
             if (k < T.nss && (fl & (SEG_FALLBACK | SEG_WANTS_PREV))) *m.any_fallback = 1;
-            if ((fl & SEG_WANTS_PREV) && seg > T.seg_base) atomicOr(&m.ss_flags[k * m.cap_seg + seg - 1], SEG_FALLBACK);
+            if ((fl & SEG_WANTS_PREV) && seg > T.seg_base) {
+                // ... and where the predecessor may deliver next to nothing (no access unit, or its first one
+                // dropped or damaged: the check data has been through), the history reaches further back
+                // (k_carry_fix takes such segments along): up to the first one that stands on its own
+                uint32_t p = seg - 1;
+                atomicOr(&m.ss_flags[k * m.cap_seg + p], SEG_FALLBACK);
+                while (p > T.seg_base && (m.segs[p].n_au == 0 || m.au_err[m.segs[p].au_base] != 0)) {
+                    p--;
+                    atomicOr(&m.ss_flags[k * m.cap_seg + p], SEG_FALLBACK);
+                }
+            }
         }
     }
     const uint32_t A = idx;
@@ -2145,17 +2155,28 @@ __global__ void __launch_bounds__(FIX_THREADS) k_carry_fix(MlpTables m)
     const TrackDev &T = m.tracks[m.segs[seg].track];
     if (k >= T.nss) return;
     const uint32_t *fl = m.ss_flags_prev + (uint64_t)k * m.cap_seg;   // as they were before any fix-up
-    if (!(fl[seg] & SEG_NEEDS_CARRY)) return;
-    // run head: predecessor (same track) is not waiting for a carry itself
-    if (seg > T.seg_base && (fl[seg - 1] & SEG_NEEDS_CARRY)) return;
+    // A segment that delivered fewer than 8 frames (a dropped access unit, a track's stub) does not
+    // own the FIR history behind it: what its successor needs reaches back into the segment before.
+    // Such segments travel with the run — decoded again from their predecessor's tail they hand on
+    // the right one — so a run is a stretch of segments that need a carry or are that short.
+    auto in_run = [&](uint32_t s) { return (fl[s] & SEG_NEEDS_CARRY) != 0 || m.segs[s].frames < 8; };
+    if (!in_run(seg)) return;
+    // run head: predecessor (same track) is not part of a run itself
+    if (seg > T.seg_base && in_run(seg - 1)) return;
     const uint32_t track_end = T.seg_base + T.nseg;
+    {
+        // (a run in which nobody needs the history is left alone)
+        bool any = false;
+        for (uint32_t s = seg; s < track_end && in_run(s) && !any; s++) any = (fl[s] & SEG_NEEDS_CARRY) != 0;
+        if (!any) return;
+    }
     if (seg == T.seg_base && (T.cont & TRACK_CONT_PREV)) {
         // the history lives in a part decoded elsewhere: the caller has to decode the parts together
         m.tracks[m.segs[seg].track].stopped = 2;
         return;
     }
     const uint32_t rs = (uint32_t)__cvta_generic_to_shared(&ring[0][threadIdx.x & 31]);
-    for (uint32_t s = seg; s < track_end && (fl[s] & SEG_NEEDS_CARRY); s++) {
+    for (uint32_t s = seg; s < track_end && in_run(s); s++) {
         DecodeJob job;
         job.seg = s; job.k = k; job.lane = (s - T.seg_base) % DVDA_LANES; job.exact_history = true;
         const int32_t *prev = m.fir_tail + ((uint64_t)k * m.cap_seg + (s - 1)) * (DVDA_MAX_CH * 8);
@@ -2197,7 +2218,11 @@ __global__ void k_seg_finalize(MlpTables m, uint32_t *__restrict__ seg_frames, u
     if ((flags & SEG_IRREGULAR) && stop == 0xFFFFFFFFu) { err |= ERR_SYNTAX; stop = S.n_au; }
     S.flags = flags & ~SEG_NEEDS_CARRY;
     // a segment longer than its tile: the decode is repeated with the frame count found here
-    if (now & SEG_OVERFLOW) { atomicOr(status, SEG_OVERFLOW); m.seg_need[i] = max(m.seg_need[i], frames); }
+    // (frames that do not count — behind an error — may have run over as well: no reason to come back)
+    if ((now & SEG_OVERFLOW) && frames > m.groups[T.grp_base + (i - T.seg_base) / DVDA_LANES].cap) {
+        atomicOr(status, SEG_OVERFLOW);
+        m.seg_need[i] = max(m.seg_need[i], frames);
+    }
     // anything left for k_rematrix once the fused filter + output pass has run?
     if (m.fast && frames && !seg_output_done(m, T, i)) atomicOr(status, STATUS_WANTS_REMATRIX);
     S.err = err;
