@@ -984,6 +984,10 @@ __device__ __forceinline__ void decode_segment(const MlpTables &m, const DecodeJ
             }
         }
     }
+    else if (init_hist) {
+        // nothing of this segment was decoded (its access units dropped): the history it was given goes on as it came
+        for (int i = 0; i < DVDA_MAX_CH * 8; i++) tail[i] = init_hist[i];
+    }
     m.ss_flags[job.k * m.cap_seg + job.seg] = flags;
     if (job.k == 0) S.frames = frames;
     if (err) atomicOr(&S.err, err);
