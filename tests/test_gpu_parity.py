@@ -312,6 +312,29 @@ def test_random_damage(pkg, oracle, engine, disc_cache, name):
         assert np.array_equal(engine.fetch(r), ref["pcm"]), where
 
 
+@pytest.mark.parametrize("seed,track,offset,bit", [(581, 3, 40608, 1), (548, 1, 64447, 16)])
+def test_damage_found_by_fuzzing(pkg, oracle, engine, tmp_path, seed, track, offset, bit):
+    """Two single-bit flips on random discs that tools/fuzz_damage.py found the engine wrong on: a major
+    sync whose parameters no longer match (the access unit is dropped) in front of a segment that starts
+    with FIR taps — the history has to come from the segment before the dropped one (the unmodified
+    reference agrees with the oracle there); and a block size that overruns the tile in the very access
+    unit that ends the track with a syntax error (the engine kept asking for a larger tile)."""
+    import dvda_gen as g
+    tracks = _random_disc(seed)
+    directory = str(tmp_path / "AUDIO_TS")
+    info = g.make_disc(directory, [tracks])
+    sectors = oracle.read_aobs(directory).copy()
+    sectors[offset] ^= bit
+    t = info[0][track - 1]
+    desc = (t["first_sector"], t["last_sector"], t["pts_length"])
+    ref = oracle.decode_track(sectors, *desc)
+    assert ref is not None
+    r = engine.decode_host(sectors, [desc])[0]
+    assert r.status == 0
+    assert (r.frames, r.error_flags, r.channels) == (ref["frames"], ref["error_flags"], ref["channels"])
+    assert np.array_equal(engine.fetch(r), ref["pcm"])
+
+
 def test_truncated_window_is_reported(pkg, oracle, engine, disc_cache):
     directory, _ = disc_cache("c2_mlp_2ch96")
     g = GOLDEN["c2_mlp_2ch96"]["tracks"][0]
