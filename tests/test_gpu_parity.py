@@ -523,39 +523,7 @@ def test_pipelined_track_decode(pkg, oracle, engine, disc_cache, name, part):
         assert np.array_equal(got, ref["pcm"]), (name, g["track"])
 
 
-def _random_disc(seed):
-    """Three tracks whose shape (channel layout, substreams, access-unit size, restart interval,
-    blocks per unit, filter orders, matrices, syntax features, PCM in between) is drawn at random."""
-    import random
-    import dvda_gen as g
-    rnd = random.Random(7700 + seed)
-    layouts = [(0, 1), (1, 1), (1, 1), (2, 1), (3, 1), (9, 1), (20, 1), (6, 2), (12, 2), (12, 2), (18, 2), (19, 2), (20, 2)]
-    bits = [g.CHECKDATA, g.BYPASS, g.NOISE, g.QUANT, g.OUTSHIFT, g.EXTRAWORD, g.TERMINATOR, g.FLAGS, g.SPARSE,
-            g.MIDAU_PARAMS, g.MID_RESTART, g.SYNC_NO_RST, g.SS1_CHK_QUIRK, g.RANDOM_PADS, g.FIR_CARRY]
-
-    def mlp_track(join):
-        asg, nss = rnd.choice(layouts)
-        feats = 0
-        for b in bits:
-            if rnd.random() < 0.45:
-                feats |= b
-        rate = rnd.choice([44100, 48000, 96000, 96000, 192000])
-        fir = rnd.choice([0, 2, 4, 8])
-        return g.mlp(rnd.randrange(1500, 7000), bps=rnd.choice([16, 24, 24]), rate=rate, assignment=asg, seed=rnd.randrange(1, 1 << 20),
-                     features=feats, substreams=nss, au_frames=rnd.choice([0, 0, 40]) if rate <= 48000 else 0,
-                     restart_interval=rnd.choice([1, 2, 3, 5, 8, 16]), max_blocks=rnd.choice([1, 1, 2, 4]),
-                     fir_max=fir, iir_max=rnd.choice([0, 2, 4]) if fir <= 4 else 0,
-                     matrices=rnd.choice([0, 1, 2, 3, 6]), noise_bits=rnd.randrange(4, 20), join_previous=join)
-
-    tracks = [mlp_track(0)]
-    tracks.append(g.pcm(rnd.randrange(800, 5000), bps=rnd.choice([16, 24]), rate=rnd.choice([48000, 96000]),
-                        assignment=rnd.choice([0, 1, 3]), seed=rnd.randrange(1, 1 << 20)) if rnd.random() < 0.4 else mlp_track(0))
-    join = 1 if tracks[1]["codec"] == 1 and rnd.random() < 0.3 else 0
-    tracks.append(mlp_track(join))
-    if join:                                              # a joined track continues its predecessor's stream layout
-        for key in ("bps_code", "rate_code", "assignment", "substreams", "au_frames"):
-            tracks[2][key] = tracks[1][key]
-    return tracks
+_random_disc = catalog.random_disc
 
 
 @pytest.mark.parametrize("seed", range(40))

@@ -52,6 +52,30 @@ def test_oracle_matches_live_reference(oracle, disc_cache, tmp_path, name):
         assert np.array_equal(r["pcm"], p), t
 
 
+@pytest.mark.parametrize("seed", range(64))
+def test_oracle_matches_live_reference_on_random_discs(oracle, tmp_path, seed):
+    """The discs of the GPU suite's random-stream tests (tests/catalog.py: random_disc): the oracle is
+    pinned on them too, by the unmodified reference run on the very disc.  (Three of the 64 shapes —
+    joined tracks behind certain predecessors — make the reference segfault: nothing to compare with.)"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    import dvda_gen as g
+    directory = str(tmp_path / "AUDIO_TS")
+    info = g.make_disc(directory, [catalog.random_disc(seed)])
+    rc, ref_tracks, _samples, err = oracle.run_dump(oracle.REF_DUMP, directory)
+    if rc < 0:
+        pytest.skip("the unmodified reference does not survive this stream (signal %d)" % -rc)
+    assert rc == 0, err
+    sectors = oracle.read_aobs(directory)
+    assert len(ref_tracks) == len(info[0])
+    for rt, t in zip(ref_tracks, info[0]):
+        r = oracle.decode_track(sectors, t["first_sector"], t["last_sector"], t["pts_length"])
+        assert r is not None, rt
+        assert (r["channels"], r["bits_per_sample"], r["sample_rate"], r["frames"]) == (rt["ch"], rt["bps"], rt["rate"], rt["frames"]), rt
+        assert oracle.fnv1a(r["pcm"]) == rt["fnv"], rt
+        assert r["error_flags"] == 0
+
+
 def test_reference_read_size_does_not_matter(oracle, disc_cache, tmp_path):
     """dvda_read(…, n) with odd n returns the same samples (the zero-yield rule does not
     depend on the read pattern)."""
